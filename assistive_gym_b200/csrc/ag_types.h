@@ -1,0 +1,86 @@
+// ag_types.h — device-side data layout of the batched simulation.
+//
+// Layout rule: every per-env quantity is SoA with the env index fastest,
+// `[item][component][N]`, so that the 32 lanes of a warp (= 32 consecutive envs) touch one 128 B
+// line per scalar.  Template (scene) tables are shared by all envs and read through the read-only
+// path; all lanes of a warp read the same address (broadcast).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#define AG_MAXND 16          // max articulated DoFs per env (all articulated bodies together)
+#define AG_MAX_HULL 64       // max core vertices per collider
+#define AG_CF 20             // floats per contact record
+#define AG_MAXAC 16          // max contacts per env with an articulated side
+
+// contact record fields (float index within the [AG_CF] record)
+enum {
+  CF_PAX = 0, CF_PAY, CF_PAZ, CF_PBX, CF_PBY, CF_PBZ, CF_NX, CF_NY, CF_NZ, CF_DIST,
+  CF_RHS_N, CF_DINV_N, CF_RHS_T1, CF_DINV_T1, CF_RHS_T2, CF_DINV_T2, CF_MU, CF_LAM_N, CF_LAM_T1, CF_LAM_T2
+};
+// body kinds
+enum { BK_STATIC = 0, BK_FREE = 1, BK_ART = 2 };
+
+struct SimDev {
+  int N;
+  // ---- config
+  float dt; int iters; float erp, contact_erp, slop, resid_thr, contact_thr, lin_damp, ang_damp, vmax;
+  int cone, gyro, maxc;
+  // ---- template sizes
+  int nb, nl, nc, npair, ncon, nf, nart, ND, nparts, nmovcol, nmovlink, nalllink, nas /* art-side slots */, ngr /* generic rows */;
+  // ---- template tables (device, read-only)
+  const int *body_link0, *body_nlinks, *body_kind, *body_idx;
+  const float* body_gravity;
+  const int *link_body, *link_parent, *link_jtype, *link_dl, *link_haslimit, *link_col0, *link_ncol;
+  const float *link_axis, *link_jpos, *link_jquat, *link_com, *link_iquat, *link_inertia, *link_mass, *link_lower, *link_upper;
+  const int *col_link, *col_type, *col_v0, *col_nv, *col_p0, *col_np;
+  const float *col_radius, *col_thresh, *col_center, *col_half, *verts, *planes;
+  float max_thresh;
+  const int* pair_link;
+  const int *movcol, *movlink, *allcol, *alllink;
+  const int* con_link; const float *con_pivot, *con_quat, *con_maxforce;
+  const int* free_body;
+  const int *art_body, *art_dl0, *art_nd;
+  const int *dl_link, *dl_parent, *dl_type, *dl_art, *dl_part0, *dl_nparts;
+  const float *dl_mass, *dl_mc, *dl_J, *dl_damping;
+  const float *pt_mass, *pt_com, *pt_I;
+  // ---- motors (per link, shared by envs) + per-env targets
+  int* motor_mode; float *motor_kp, *motor_kd, *motor_maxf;
+  float *motor_target, *motor_applied;       // [nl][N]
+  // ---- per-env state
+  float *base_pos, *base_quat, *base_lin, *base_ang;   // [nb][3|4][N]
+  float *jq, *jqd;                                     // [nl][N]
+  float* friction;                                     // [nl][N]
+  int* body_mode;                                      // [nb][N]  0 inactive, 1 normal, 2 frozen
+  // ---- derived per-env
+  float *lpos, *lquat;                                 // [nl][3|4][N]
+  float *cmin, *cmax, *lmin, *lmax;                    // [nc|nl][3][N]
+  // ---- contacts
+  int* c_count;                                        // [N]
+  unsigned *c_key, *s_key;                             // [maxc][N] unsorted / sorted
+  float *c_data, *s_data;                              // [maxc][AG_CF][N]
+  int *s_ref;                                          // [maxc][4][N]: refA, refB, asA, asB
+  int* overflow;                                       // [N]
+  // ---- solver scratch
+  float *fcom, *fIinv;                                 // [nf][3|6][N]
+  float *jax, *jor;                                    // [ND][3][N] world joint axis / origin
+  float* Minv;                                         // [ND][ND][N]
+  float* dv;                                           // [ND + 6 nf][N]
+  float *dr_rhs, *dr_dinv, *dr_lam;                    // [3 ND][N] dof rows: lower limit, upper limit, motor
+  float *as_J, *as_MiJ;                                // [nas][AG_MAXND][N]
+  int* as_count;                                       // [N]
+  float* gr_data;                                      // [ngr][16][N] generic rows (fixed constraints)
+  int* gr_ref;                                         // [ngr][4][N]
+  int* iters_used;                                     // [N]
+};
+
+// generic row fields
+enum { GR_LX = 0, GR_LY, GR_LZ, GR_AAX, GR_AAY, GR_AAZ, GR_ABX, GR_ABY, GR_ABZ, GR_RHS, GR_DINV, GR_LO, GR_HI, GR_LAM, GR_PAD0, GR_PAD1 };
+
+// kernel-specific small parameter block
+struct KP {
+  int n;        // number of threads
+  int i0, i1, i2, i3;
+  float f0, f1;
+  const void* p0; void* p1; void* p2; void* p3; void* p4; void* p5;
+};

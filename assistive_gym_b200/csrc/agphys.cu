@@ -1,0 +1,709 @@
+// agphys.cu — kernels + C ABI (include/agphys.h) of the B200-native batched physics step.
+//
+// Build (product):  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// Build (kernel-logic harness, tests only):  g++ -x c++ -DAG_CPU_EMU ...   (never loaded by the package)
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../../include/agphys.h"
+#include "ag_device.cuh"
+#include "ag_feeding.cuh"
+
+#ifndef AG_CPU_EMU
+#include <cuda_runtime.h>
+#define AG_GLOBAL __global__
+#else
+#define AG_GLOBAL
+typedef void* cudaStream_t;
+#endif
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return -1; }
+
+// ------------------------------------------------------------------ kernel wrappers
+#ifndef AG_CPU_EMU
+#define AG_KERNEL(name, body)                                                   \
+  __global__ void __launch_bounds__(128) name(SimDev S, KP p) {                 \
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;                            \
+    if (tid < p.n) body(tid, S, p);                                             \
+  }
+#else
+#define AG_KERNEL(name, body) \
+  static void name(SimDev S, KP p) { for (int tid = 0; tid < p.n; tid++) body(tid, S, p); }
+#endif
+
+AG_KERNEL(k_fk, fk_body)
+AG_KERNEL(k_aabb, aabb_body)
+AG_KERNEL(k_linkaabb, linkaabb_body)
+AG_KERNEL(k_collide, collide_body)
+AG_KERNEL(k_sort, sort_body)
+AG_KERNEL(k_dyn, dyn_body)
+AG_KERNEL(k_rows, rows_body)
+AG_KERNEL(k_crows, crows_body)
+AG_KERNEL(k_pgs, pgs_body)
+AG_KERNEL(k_integrate, integrate_body)
+AG_KERNEL(k_gather, gather_body)
+AG_KERNEL(k_scatter, scatter_body)
+AG_KERNEL(k_linkstate, linkstate_body)
+AG_KERNEL(k_contact_query, contact_query_body)
+AG_KERNEL(k_closest, closest_body)
+AG_KERNEL(k_feed_pre, feeding_pre_body)
+AG_KERNEL(k_feed_food, feeding_food_body)
+AG_KERNEL(k_feed_post, feeding_post_body)
+
+// ------------------------------------------------------------------ host object
+struct AgSim {
+  SimDev S;
+  AgConfig cfg;
+  int device;
+  cudaStream_t stream;
+  uint64_t launches;
+  std::vector<void*> allocs;
+  // host copies of template info needed by the API
+  std::vector<int> body_link0, body_nlinks, body_kind, link_body;
+  int nl, nb;
+  // staging
+  float* d_stage; size_t stage_floats;
+  std::vector<float> h_stage;
+  int* d_mask; int* d_links; int* d_icount;
+  // feeding
+  FeedDev F; FeedDev* F_dev; bool feeding;
+  float *d_action, *d_obs, *d_reward, *d_done, *d_info;
+  float *h_pin_in, *h_pin_out;
+};
+
+#ifndef AG_CPU_EMU
+#define CK(x) do { cudaError_t err__ = (x); if (err__ != cudaSuccess) { g_err = std::string(#x) + ": " + cudaGetErrorString(err__); return -1; } } while (0)
+#define CKP(x) do { cudaError_t err__ = (x); if (err__ != cudaSuccess) { g_err = std::string(#x) + ": " + cudaGetErrorString(err__); return nullptr; } } while (0)
+#endif
+
+static void* dev_alloc(AgSim* s, size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+#ifndef AG_CPU_EMU
+  if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+  cudaMemset(p, 0, bytes);
+#else
+  p = calloc(1, bytes);
+#endif
+  s->allocs.push_back(p);
+  return p;
+}
+static int h2d(AgSim* s, void* d, const void* h, size_t bytes) {
+#ifndef AG_CPU_EMU
+  CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+#else
+  (void)s; memcpy(d, h, bytes);
+#endif
+  return 0;
+}
+static int d2h(AgSim* s, void* h, const void* d, size_t bytes) {
+#ifndef AG_CPU_EMU
+  CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+#else
+  (void)s; memcpy(h, d, bytes);
+#endif
+  return 0;
+}
+static int dev_zero(AgSim* s, void* d, size_t bytes) {
+#ifndef AG_CPU_EMU
+  CK(cudaMemsetAsync(d, 0, bytes, s->stream));
+#else
+  (void)s; memset(d, 0, bytes);
+#endif
+  return 0;
+}
+template <typename T>
+static const T* upload(AgSim* s, const std::vector<T>& v) {
+  T* d = (T*)dev_alloc(s, v.size() * sizeof(T));
+  if (d && !v.empty()) h2d(s, d, v.data(), v.size() * sizeof(T));
+  return d;
+}
+template <typename T>
+static T* dalloc(AgSim* s, size_t n) { return (T*)dev_alloc(s, n * sizeof(T)); }
+
+#ifndef AG_CPU_EMU
+#define LAUNCH(sim, kern, nthreads, kp)                                                     \
+  do {                                                                                      \
+    KP kp__ = (kp); kp__.n = (int)(nthreads);                                               \
+    if (kp__.n > 0) {                                                                       \
+      kern<<<(kp__.n + 127) / 128, 128, 0, (sim)->stream>>>((sim)->S, kp__);                \
+      (sim)->launches++;                                                                    \
+    }                                                                                       \
+  } while (0)
+#else
+#define LAUNCH(sim, kern, nthreads, kp) \
+  do { KP kp__ = (kp); kp__.n = (int)(nthreads); if (kp__.n > 0) { kern((sim)->S, kp__); (sim)->launches++; } } while (0)
+#endif
+
+static KP kp0() { KP p; memset(&p, 0, sizeof(p)); return p; }
+
+// ------------------------------------------------------------------ quaternion helpers on the host (double)
+struct HQ { double x, y, z, w; };
+static HQ hq_mul(HQ a, HQ b) {
+  return HQ{a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y, a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x,
+            a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w, a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z};
+}
+static void hq_mat(HQ q, double R[9]) {
+  double x = q.x, y = q.y, z = q.z, w = q.w;
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w); R[2] = 2 * (x * z + y * w);
+  R[3] = 2 * (x * y + z * w); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+  R[6] = 2 * (x * z - y * w); R[7] = 2 * (y * z + x * w); R[8] = 1 - 2 * (x * x + y * y);
+}
+
+extern "C" {
+
+const char* ag_last_error(void) { return g_err.c_str(); }
+
+void ag_default_config(AgConfig* c) {
+  c->dt = 0.02; c->num_substeps = 1; c->num_solver_iters = 50; c->erp = 0.2; c->contact_erp = 0.08;
+  c->linear_slop = 1e-5; c->residual_threshold = 1e-7; c->contact_threshold = 0.02;
+  c->linear_damping = 0.04; c->angular_damping = 0.04; c->max_coord_velocity = 100; c->hull_margin = 0.001;
+  c->cone_friction = 1; c->gyroscopic = 1; c->max_contacts = 128;
+}
+
+AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int device) {
+  if (!d || !cfg || n_envs <= 0) { g_err = "ag_create: bad arguments"; return nullptr; }
+  AgSim* s = new AgSim();
+  memset(&s->S, 0, sizeof(SimDev));
+  memset(&s->F, 0, sizeof(FeedDev));
+  s->cfg = *cfg; s->device = device; s->launches = 0; s->feeding = false; s->stream = nullptr; s->F_dev = nullptr;
+  s->d_stage = nullptr; s->stage_floats = 0;
+#ifndef AG_CPU_EMU
+  if (cudaSetDevice(device) != cudaSuccess) { g_err = "cudaSetDevice failed (is a CUDA device present? there is no CPU fallback)"; delete s; return nullptr; }
+  if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { g_err = "cudaStreamCreate failed"; delete s; return nullptr; }
+#endif
+  SimDev& S = s->S;
+  const int N = n_envs;
+  S.N = N;
+  int sub = cfg->num_substeps > 0 ? cfg->num_substeps : 1;
+  S.dt = (float)(cfg->dt / sub); S.iters = cfg->num_solver_iters; S.erp = (float)cfg->erp; S.contact_erp = (float)cfg->contact_erp;
+  S.slop = (float)cfg->linear_slop; S.resid_thr = (float)cfg->residual_threshold; S.contact_thr = (float)cfg->contact_threshold;
+  S.lin_damp = (float)cfg->linear_damping; S.ang_damp = (float)cfg->angular_damping; S.vmax = (float)cfg->max_coord_velocity;
+  S.cone = cfg->cone_friction; S.gyro = cfg->gyroscopic; S.maxc = cfg->max_contacts > 0 ? cfg->max_contacts : 128;
+  const int nb = d->n_bodies, nl = d->n_links, nc = d->n_colliders;
+  S.nb = nb; S.nl = nl; S.nc = nc; S.npair = d->n_pairs; S.ncon = d->n_constraints;
+  s->nb = nb; s->nl = nl;
+  s->body_link0.assign(d->body_link0, d->body_link0 + nb);
+  s->body_nlinks.assign(d->body_nlinks, d->body_nlinks + nb);
+  s->link_body.assign(d->link_body, d->link_body + nl);
+
+  // ---- classify bodies, live joints, dyn links
+  std::vector<double> subtree(nl, 0.0);
+  for (int k = nl - 1; k >= 0; k--) { subtree[k] += d->link_mass[k]; if (d->link_parent[k] >= 0) subtree[d->link_parent[k]] += subtree[k]; }
+  std::vector<int> live(nl, 0), link_dl(nl, -1), body_kind(nb, BK_STATIC), body_idx(nb, -1);
+  std::vector<int> free_body, art_body, art_dl0, art_nd, dl_link, dl_parent, dl_type, dl_art, dl_part0, dl_nparts;
+  std::vector<float> dl_mass, dl_mc, dl_J, dl_damping, pt_mass, pt_com, pt_I;
+  for (int b = 0; b < nb; b++) {
+    int l0 = d->body_link0[b], nlk = d->body_nlinks[b];
+    int nlive = 0;
+    for (int k = l0 + 1; k < l0 + nlk; k++) {
+      int jt = d->link_jtype[k];
+      if ((jt == AG_JOINT_REVOLUTE || jt == AG_JOINT_PRISMATIC) && subtree[k] > 0) { live[k] = 1; nlive++; }
+    }
+    if (d->link_jtype[l0] == AG_JOINT_FREE_BASE && d->link_mass[l0] > 0) {
+      if (nlive > 0) { g_err = "floating-base articulated bodies are not supported yet"; ag_destroy(s); return nullptr; }
+      body_kind[b] = BK_FREE; body_idx[b] = (int)free_body.size(); free_body.push_back(b);
+    } else if (nlive > 0) {
+      body_kind[b] = BK_ART; body_idx[b] = (int)art_body.size();
+      art_body.push_back(b); art_dl0.push_back((int)dl_link.size()); art_nd.push_back(nlive);
+      // relative transform of each link w.r.t. the dyn link that carries it (through fixed joints only)
+      std::vector<HQ> rq(nlk); std::vector<double> rp(3 * nlk, 0.0);
+      for (int k = l0; k < l0 + nlk; k++) {
+        int i = k - l0;
+        if (k == l0) { link_dl[k] = -1; rq[i] = HQ{0, 0, 0, 1}; continue; }
+        int par = d->link_parent[k];
+        if (live[k]) {
+          int dd = (int)dl_link.size();
+          link_dl[k] = dd; rq[i] = HQ{0, 0, 0, 1}; rp[3 * i] = rp[3 * i + 1] = rp[3 * i + 2] = 0;
+          dl_link.push_back(k); dl_parent.push_back(link_dl[par]); dl_type.push_back(d->link_jtype[k]); dl_art.push_back(body_idx[b]);
+          dl_damping.push_back((float)d->link_damping[k]);
+        } else {
+          link_dl[k] = link_dl[par];
+          // T_rel(k) = T_rel(par) * T_joint(k)   (fixed joint or locked joint at q=0; locked joints carry no mass)
+          int pi = par - l0;
+          double R[9]; hq_mat(rq[pi], R);
+          for (int a = 0; a < 3; a++) rp[3 * i + a] = rp[3 * pi + a] + R[3 * a] * d->link_jpos[3 * k] + R[3 * a + 1] * d->link_jpos[3 * k + 1] + R[3 * a + 2] * d->link_jpos[3 * k + 2];
+          rq[i] = hq_mul(rq[pi], HQ{d->link_jquat[4 * k], d->link_jquat[4 * k + 1], d->link_jquat[4 * k + 2], d->link_jquat[4 * k + 3]});
+        }
+      }
+      // merged inertias + parts
+      int d0 = art_dl0.back();
+      for (int dd = d0; dd < d0 + nlive; dd++) {
+        double m = 0, mc[3] = {0, 0, 0}, J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        dl_part0.push_back((int)pt_mass.size());
+        int np = 0;
+        for (int k = l0 + 1; k < l0 + nlk; k++) {
+          if (link_dl[k] != dd || d->link_mass[k] <= 0) continue;
+          int i = k - l0;
+          double R[9]; hq_mat(rq[i], R);
+          double c[3];
+          for (int a = 0; a < 3; a++) c[a] = rp[3 * i + a] + R[3 * a] * d->link_com[3 * k] + R[3 * a + 1] * d->link_com[3 * k + 1] + R[3 * a + 2] * d->link_com[3 * k + 2];
+          HQ qi = hq_mul(rq[i], HQ{d->link_iquat[4 * k], d->link_iquat[4 * k + 1], d->link_iquat[4 * k + 2], d->link_iquat[4 * k + 3]});
+          double Ri[9]; hq_mat(qi, Ri);
+          double Ic[9];
+          for (int a = 0; a < 3; a++) for (int bb = 0; bb < 3; bb++) {
+            double t = 0; for (int q = 0; q < 3; q++) t += Ri[3 * a + q] * d->link_inertia[3 * k + q] * Ri[3 * bb + q];
+            Ic[3 * a + bb] = t;
+          }
+          double mk = d->link_mass[k];
+          m += mk;
+          double cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+          for (int a = 0; a < 3; a++) { mc[a] += mk * c[a]; for (int bb = 0; bb < 3; bb++) J[3 * a + bb] += Ic[3 * a + bb] + mk * ((a == bb ? cc : 0.0) - c[a] * c[bb]); }
+          pt_mass.push_back((float)mk);
+          for (int a = 0; a < 3; a++) pt_com.push_back((float)c[a]);
+          pt_I.push_back((float)Ic[0]); pt_I.push_back((float)Ic[4]); pt_I.push_back((float)Ic[8]);
+          pt_I.push_back((float)Ic[1]); pt_I.push_back((float)Ic[2]); pt_I.push_back((float)Ic[5]);
+          np++;
+        }
+        dl_nparts.push_back(np);
+        dl_mass.push_back((float)m);
+        for (int a = 0; a < 3; a++) dl_mc.push_back((float)mc[a]);
+        dl_J.push_back((float)J[0]); dl_J.push_back((float)J[4]); dl_J.push_back((float)J[8]);
+        dl_J.push_back((float)J[1]); dl_J.push_back((float)J[2]); dl_J.push_back((float)J[5]);
+      }
+    }
+  }
+  S.nf = (int)free_body.size(); S.nart = (int)art_body.size(); S.ND = (int)dl_link.size(); S.nparts = (int)pt_mass.size();
+  if (S.ND > AG_MAXND) { g_err = "too many articulated DoFs per env (AG_MAXND)"; ag_destroy(s); return nullptr; }
+  s->body_kind = body_kind;
+  // movable lists
+  std::vector<int> link_col0(nl, 0), link_ncol(nl, 0);
+  for (int c = nc - 1; c >= 0; c--) { link_col0[d->col_link[c]] = c; link_ncol[d->col_link[c]]++; }
+  std::vector<int> movcol, movlink, allcol, alllink;
+  for (int k = 0; k < nl; k++) {
+    int b = d->link_body[k];
+    bool mov = (body_kind[b] == BK_FREE) || (body_kind[b] == BK_ART && link_dl[k] >= 0);
+    if (link_ncol[k] > 0) { alllink.push_back(k); if (mov) movlink.push_back(k); }
+    for (int c = link_col0[k]; c < link_col0[k] + link_ncol[k]; c++) { allcol.push_back(c); if (mov) movcol.push_back(c); }
+  }
+  S.nmovcol = (int)movcol.size(); S.nmovlink = (int)movlink.size(); S.nalllink = (int)alllink.size();
+  S.ngr = 6 * S.ncon; S.nas = 6 * S.ncon * 2 + 3 * AG_MAXAC;
+
+  // ---- upload template
+  auto f32 = [](const double* p, size_t n) { std::vector<float> v(n); for (size_t i = 0; i < n; i++) v[i] = (float)p[i]; return v; };
+  auto i32 = [](const int32_t* p, size_t n) { return std::vector<int>(p, p + n); };
+  S.body_link0 = upload(s, i32(d->body_link0, nb)); S.body_nlinks = upload(s, i32(d->body_nlinks, nb));
+  S.body_kind = upload(s, body_kind); S.body_idx = upload(s, body_idx);
+  S.body_gravity = upload(s, f32(d->body_gravity, 3 * nb));
+  S.link_body = upload(s, i32(d->link_body, nl)); S.link_parent = upload(s, i32(d->link_parent, nl));
+  S.link_jtype = upload(s, i32(d->link_jtype, nl)); S.link_dl = upload(s, link_dl);
+  S.link_haslimit = upload(s, i32(d->link_haslimit, nl)); S.link_col0 = upload(s, link_col0); S.link_ncol = upload(s, link_ncol);
+  S.link_axis = upload(s, f32(d->link_axis, 3 * nl)); S.link_jpos = upload(s, f32(d->link_jpos, 3 * nl));
+  S.link_jquat = upload(s, f32(d->link_jquat, 4 * nl)); S.link_com = upload(s, f32(d->link_com, 3 * nl));
+  S.link_iquat = upload(s, f32(d->link_iquat, 4 * nl)); S.link_inertia = upload(s, f32(d->link_inertia, 3 * nl));
+  S.link_mass = upload(s, f32(d->link_mass, nl)); S.link_lower = upload(s, f32(d->link_lower, nl)); S.link_upper = upload(s, f32(d->link_upper, nl));
+  S.col_link = upload(s, i32(d->col_link, nc)); S.col_type = upload(s, i32(d->col_type, nc));
+  S.col_v0 = upload(s, i32(d->col_v0, nc)); S.col_nv = upload(s, i32(d->col_nv, nc));
+  S.col_p0 = upload(s, i32(d->col_p0, nc)); S.col_np = upload(s, i32(d->col_np, nc));
+  S.col_radius = upload(s, f32(d->col_radius, nc)); S.col_thresh = upload(s, f32(d->col_thresh, nc));
+  S.max_thresh = 0.f; for (int c = 0; c < nc; c++) S.max_thresh = std::max(S.max_thresh, (float)d->col_thresh[c]); S.col_center = upload(s, f32(d->col_center, 3 * nc)); S.col_half = upload(s, f32(d->col_half, 3 * nc));
+  S.verts = upload(s, f32(d->verts, 3 * (size_t)d->n_verts)); S.planes = upload(s, f32(d->planes, 4 * (size_t)d->n_planes));
+  S.pair_link = upload(s, i32(d->pair_link, 2 * (size_t)d->n_pairs));
+  S.movcol = upload(s, movcol); S.movlink = upload(s, movlink); S.allcol = upload(s, allcol); S.alllink = upload(s, alllink);
+  s->S.nmovcol = (int)movcol.size();
+  S.con_link = upload(s, i32(d->con_link, 2 * (size_t)S.ncon)); S.con_pivot = upload(s, f32(d->con_pivot, 6 * (size_t)S.ncon));
+  S.con_quat = upload(s, f32(d->con_quat, 8 * (size_t)S.ncon)); S.con_maxforce = upload(s, f32(d->con_maxforce, S.ncon));
+  S.free_body = upload(s, free_body);
+  S.art_body = upload(s, art_body); S.art_dl0 = upload(s, art_dl0); S.art_nd = upload(s, art_nd);
+  S.dl_link = upload(s, dl_link); S.dl_parent = upload(s, dl_parent); S.dl_type = upload(s, dl_type); S.dl_art = upload(s, dl_art);
+  S.dl_part0 = upload(s, dl_part0); S.dl_nparts = upload(s, dl_nparts);
+  S.dl_mass = upload(s, dl_mass); S.dl_mc = upload(s, dl_mc); S.dl_J = upload(s, dl_J); S.dl_damping = upload(s, dl_damping);
+  S.pt_mass = upload(s, pt_mass); S.pt_com = upload(s, pt_com); S.pt_I = upload(s, pt_I);
+  // ---- per-env state
+  S.motor_mode = dalloc<int>(s, nl); S.motor_kp = dalloc<float>(s, nl); S.motor_kd = dalloc<float>(s, nl); S.motor_maxf = dalloc<float>(s, nl);
+  S.motor_target = dalloc<float>(s, (size_t)nl * N); S.motor_applied = dalloc<float>(s, (size_t)nl * N);
+  S.base_pos = dalloc<float>(s, (size_t)nb * 3 * N); S.base_quat = dalloc<float>(s, (size_t)nb * 4 * N);
+  S.base_lin = dalloc<float>(s, (size_t)nb * 3 * N); S.base_ang = dalloc<float>(s, (size_t)nb * 3 * N);
+  S.jq = dalloc<float>(s, (size_t)nl * N); S.jqd = dalloc<float>(s, (size_t)nl * N);
+  S.friction = dalloc<float>(s, (size_t)nl * N); S.body_mode = dalloc<int>(s, (size_t)nb * N);
+  S.lpos = dalloc<float>(s, (size_t)nl * 3 * N); S.lquat = dalloc<float>(s, (size_t)nl * 4 * N);
+  S.cmin = dalloc<float>(s, (size_t)nc * 3 * N); S.cmax = dalloc<float>(s, (size_t)nc * 3 * N);
+  S.lmin = dalloc<float>(s, (size_t)nl * 3 * N); S.lmax = dalloc<float>(s, (size_t)nl * 3 * N);
+  S.c_count = dalloc<int>(s, N); S.overflow = dalloc<int>(s, N); S.iters_used = dalloc<int>(s, N);
+  S.c_key = dalloc<unsigned>(s, (size_t)S.maxc * N); S.s_key = dalloc<unsigned>(s, (size_t)S.maxc * N);
+  S.c_data = dalloc<float>(s, (size_t)S.maxc * AG_CF * N); S.s_data = dalloc<float>(s, (size_t)S.maxc * AG_CF * N);
+  S.s_ref = dalloc<int>(s, (size_t)S.maxc * 4 * N);
+  S.fcom = dalloc<float>(s, (size_t)S.nf * 3 * N); S.fIinv = dalloc<float>(s, (size_t)S.nf * 6 * N);
+  S.jax = dalloc<float>(s, (size_t)S.ND * 3 * N); S.jor = dalloc<float>(s, (size_t)S.ND * 3 * N);
+  S.Minv = dalloc<float>(s, (size_t)S.ND * S.ND * N);
+  S.dv = dalloc<float>(s, (size_t)(S.ND + 6 * S.nf) * N);
+  S.dr_rhs = dalloc<float>(s, (size_t)3 * S.ND * N); S.dr_dinv = dalloc<float>(s, (size_t)3 * S.ND * N); S.dr_lam = dalloc<float>(s, (size_t)3 * S.ND * N);
+  S.as_J = dalloc<float>(s, (size_t)S.nas * AG_MAXND * N); S.as_MiJ = dalloc<float>(s, (size_t)S.nas * AG_MAXND * N);
+  S.as_count = dalloc<int>(s, N);
+  S.gr_data = dalloc<float>(s, (size_t)S.ngr * 16 * N); S.gr_ref = dalloc<int>(s, (size_t)S.ngr * 4 * N);
+  s->d_mask = dalloc<int>(s, N); s->d_links = dalloc<int>(s, 1024); s->d_icount = dalloc<int>(s, N);
+  if (!S.gr_ref || !S.as_MiJ || !S.s_data) { g_err = "device allocation failed"; ag_destroy(s); return nullptr; }
+  // defaults: friction from the template, all bodies active, identity quaternions
+  {
+    std::vector<float> fr((size_t)nl * N);
+    for (int k = 0; k < nl; k++) for (int e = 0; e < N; e++) fr[(size_t)k * N + e] = (float)d->link_friction[k];
+    h2d(s, S.friction, fr.data(), fr.size() * sizeof(float));
+    std::vector<int> md((size_t)nb * N, 1);
+    h2d(s, S.body_mode, md.data(), md.size() * sizeof(int));
+    std::vector<float> q((size_t)nb * 4 * N, 0.f);
+    for (int b = 0; b < nb; b++) for (int e = 0; e < N; e++) q[((size_t)b * 4 + 3) * N + e] = 1.f;
+    h2d(s, S.base_quat, q.data(), q.size() * sizeof(float));
+  }
+  return s;
+}
+
+void ag_destroy(AgSim* s) {
+  if (!s) return;
+#ifndef AG_CPU_EMU
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  for (void* p : s->allocs) cudaFree(p);
+  if (s->feeding) { cudaFreeHost(s->h_pin_in); cudaFreeHost(s->h_pin_out); }
+  if (s->stream) cudaStreamDestroy(s->stream);
+#else
+  for (void* p : s->allocs) free(p);
+  if (s->feeding) { free(s->h_pin_in); free(s->h_pin_out); }
+#endif
+  delete s;
+}
+
+int ag_num_envs(const AgSim* s) { return s->S.N; }
+void* ag_stream(AgSim* s) { return (void*)s->stream; }
+uint64_t ag_kernel_launches(const AgSim* s) { return s->launches; }
+
+// ---- staging helpers: host env-major [N][K] <-> device SoA via gather/scatter kernels
+static float* stage(AgSim* s, size_t floats) {
+  if (floats > s->stage_floats) {
+    s->d_stage = dalloc<float>(s, floats);
+    s->stage_floats = floats;
+  }
+  return s->d_stage;
+}
+static int set_mask(AgSim* s, const int32_t* mask) {
+  if (!mask) return 0;
+  return h2d(s, s->d_mask, mask, sizeof(int) * s->S.N);
+}
+// scatter host [N][K] rows into a device SoA array with `comp` components per item:
+// dst[(item*comp + c)*N + e] = src[e*K + j*comp + c] for item = items[j]
+static int scatter_host(AgSim* s, float* dst, int comp, int nitems, const int* items, const float* src, const int32_t* mask) {
+  const int N = s->S.N;
+  size_t K = (size_t)nitems * comp;
+  float* st = stage(s, K * N);
+  if (!st) return fail("staging alloc failed");
+  if (h2d(s, st, src, K * N * sizeof(float))) return -1;
+  if (nitems > 1024) return fail("too many items");
+  if (h2d(s, s->d_links, items, sizeof(int) * nitems)) return -1;
+  if (set_mask(s, mask)) return -1;
+  KP p = kp0(); p.i0 = comp; p.i1 = nitems; p.p0 = st; p.p1 = dst; p.p2 = s->d_links; p.p3 = mask ? s->d_mask : nullptr;
+  LAUNCH(s, k_scatter, (size_t)N * K, p);
+  return 0;
+}
+static int gather_host(AgSim* s, const float* srcdev, int comp, int nitems, const int* items, float* dst) {
+  const int N = s->S.N;
+  size_t K = (size_t)nitems * comp;
+  float* st = stage(s, K * N);
+  if (!st) return fail("staging alloc failed");
+  if (nitems > 1024) return fail("too many items");
+  if (h2d(s, s->d_links, items, sizeof(int) * nitems)) return -1;
+  KP p = kp0(); p.i0 = comp; p.i1 = nitems; p.p0 = srcdev; p.p1 = st; p.p2 = s->d_links;
+  LAUNCH(s, k_gather, (size_t)N * K, p);
+  return d2h(s, dst, st, K * N * sizeof(float));
+}
+
+int ag_set_base_pose(AgSim* s, int body, const float* pos, const float* quat, const int32_t* mask) {
+  if (body < 0 || body >= s->nb) return fail("bad body");
+  if (pos && scatter_host(s, s->S.base_pos, 3, 1, &body, pos, mask)) return -1;
+  if (quat && scatter_host(s, s->S.base_quat, 4, 1, &body, quat, mask)) return -1;
+  return 0;
+}
+int ag_set_base_velocity(AgSim* s, int body, const float* lin, const float* ang, const int32_t* mask) {
+  if (body < 0 || body >= s->nb) return fail("bad body");
+  if (lin && scatter_host(s, s->S.base_lin, 3, 1, &body, lin, mask)) return -1;
+  if (ang && scatter_host(s, s->S.base_ang, 3, 1, &body, ang, mask)) return -1;
+  return 0;
+}
+int ag_set_joint_state(AgSim* s, int n, const int32_t* links, const float* q, const float* qd, const int32_t* mask) {
+  if (q && scatter_host(s, s->S.jq, 1, n, links, q, mask)) return -1;
+  if (qd && scatter_host(s, s->S.jqd, 1, n, links, qd, mask)) return -1;
+  return 0;
+}
+int ag_set_link_friction(AgSim* s, int link, const float* mu, const int32_t* mask) {
+  return scatter_host(s, s->S.friction, 1, 1, &link, mu, mask);
+}
+int ag_set_body_active(AgSim* s, int body, const int32_t* active) {
+  if (body < 0 || body >= s->nb) return fail("bad body");
+  return h2d(s, s->S.body_mode + (size_t)body * s->S.N, active, sizeof(int) * s->S.N);
+}
+
+static void run_fk_all(AgSim* s) {
+  KP p = kp0(); p.i0 = 1;
+  LAUNCH(s, k_fk, s->S.N, p);
+  KP a = kp0(); a.p0 = s->S.allcol; a.i0 = s->S.nc;
+  LAUNCH(s, k_aabb, (size_t)s->S.nc * s->S.N, a);
+  KP l = kp0(); l.p0 = s->S.alllink; l.i0 = s->S.nalllink;
+  LAUNCH(s, k_linkaabb, (size_t)s->S.nalllink * s->S.N, l);
+}
+
+int ag_forward_kinematics(AgSim* s) { run_fk_all(s); return 0; }
+
+int ag_set_motor_host(AgSim* s, int n, const int32_t* links, int mode, const float* target, const float* kp, const float* kd, const float* maxf) {
+  std::vector<int> mm(s->nl); std::vector<float> a(s->nl), b(s->nl), c(s->nl);
+  d2h(s, mm.data(), s->S.motor_mode, sizeof(int) * s->nl); d2h(s, a.data(), s->S.motor_kp, sizeof(float) * s->nl);
+  d2h(s, b.data(), s->S.motor_kd, sizeof(float) * s->nl); d2h(s, c.data(), s->S.motor_maxf, sizeof(float) * s->nl);
+  for (int j = 0; j < n; j++) {
+    int k = links[j]; if (k < 0 || k >= s->nl) return fail("bad link");
+    mm[k] = mode; if (kp) a[k] = kp[j]; b[k] = kd ? kd[j] : 1.0f; if (maxf) c[k] = maxf[j];
+  }
+  h2d(s, s->S.motor_mode, mm.data(), sizeof(int) * s->nl); h2d(s, s->S.motor_kp, a.data(), sizeof(float) * s->nl);
+  h2d(s, s->S.motor_kd, b.data(), sizeof(float) * s->nl); h2d(s, s->S.motor_maxf, c.data(), sizeof(float) * s->nl);
+  if (target) return scatter_host(s, s->S.motor_target, 1, n, links, target, nullptr);
+  return 0;
+}
+int ag_set_motor_targets_dev(AgSim* s, int n, const int32_t* links, const float* target_dev) {
+  if (n > 1024) return fail("too many items");
+  if (h2d(s, s->d_links, links, sizeof(int) * n)) return -1;
+  KP p = kp0(); p.i0 = 1; p.i1 = n; p.p0 = target_dev; p.p1 = s->S.motor_target; p.p2 = s->d_links; p.p3 = nullptr;
+  LAUNCH(s, k_scatter, (size_t)s->S.N * n, p);
+  return 0;
+}
+
+int ag_set_motor_targets_host(AgSim* s, int n, const int32_t* links, const float* target) {
+  return scatter_host(s, s->S.motor_target, 1, n, links, target, nullptr);
+}
+
+static void substep(AgSim* s) {
+  SimDev& S = s->S;
+  const int N = S.N;
+  KP z = kp0();
+  LAUNCH(s, k_fk, N, z);
+  KP a = kp0(); a.p0 = S.movcol; a.i0 = S.nmovcol;
+  LAUNCH(s, k_aabb, (size_t)S.nmovcol * N, a);
+  KP l = kp0(); l.p0 = S.movlink; l.i0 = S.nmovlink;
+  LAUNCH(s, k_linkaabb, (size_t)S.nmovlink * N, l);
+  dev_zero(s, S.c_count, sizeof(int) * N);
+  int Npad = (N + 31) / 32 * 32;
+  KP c = kp0(); c.i0 = Npad;
+  LAUNCH(s, k_collide, (size_t)S.npair * Npad, c);
+  LAUNCH(s, k_sort, (size_t)S.maxc * N, z);
+  LAUNCH(s, k_dyn, N, z);
+  LAUNCH(s, k_rows, N, z);
+  LAUNCH(s, k_crows, (size_t)S.maxc * N, z);
+  LAUNCH(s, k_pgs, N, z);
+  LAUNCH(s, k_integrate, N, z);
+}
+
+int ag_step(AgSim* s, int n_steps) {
+  int sub = s->cfg.num_substeps > 0 ? s->cfg.num_substeps : 1;
+  for (int i = 0; i < n_steps * sub; i++) substep(s);
+  KP z = kp0();
+  LAUNCH(s, k_fk, s->S.N, z);
+#ifndef AG_CPU_EMU
+  CK(cudaGetLastError());
+#endif
+  return 0;
+}
+
+int ag_get_joint_states(AgSim* s, int n, const int32_t* links, float* q, float* qd, float* tau) {
+  if (q && gather_host(s, s->S.jq, 1, n, links, q)) return -1;
+  if (qd && gather_host(s, s->S.jqd, 1, n, links, qd)) return -1;
+  if (tau && gather_host(s, s->S.motor_applied, 1, n, links, tau)) return -1;
+  return 0;
+}
+
+int ag_get_link_states(AgSim* s, int n, const int32_t* links, float* pos, float* quat, float* com_pos, float* com_quat, float* lin_vel, float* ang_vel) {
+  const int N = s->S.N;
+  if (n > 1024) return fail("too many items");
+  // out record per (env, link): 20 floats: pos3 quat4 cpos3 cquat4 lin3 ang3
+  float* st = stage(s, (size_t)N * n * 20);
+  if (!st) return fail("staging alloc failed");
+  if (h2d(s, s->d_links, links, sizeof(int) * n)) return -1;
+  KP p = kp0(); p.i1 = n; p.p1 = st; p.p2 = s->d_links;
+  LAUNCH(s, k_linkstate, (size_t)N * n, p);
+  s->h_stage.resize((size_t)N * n * 20);
+  if (d2h(s, s->h_stage.data(), st, sizeof(float) * s->h_stage.size())) return -1;
+  for (size_t i = 0; i < (size_t)N * n; i++) {
+    const float* r = &s->h_stage[i * 20];
+    if (pos) memcpy(pos + 3 * i, r, 12);
+    if (quat) memcpy(quat + 4 * i, r + 3, 16);
+    if (com_pos) memcpy(com_pos + 3 * i, r + 7, 12);
+    if (com_quat) memcpy(com_quat + 4 * i, r + 10, 16);
+    if (lin_vel) memcpy(lin_vel + 3 * i, r + 14, 12);
+    if (ang_vel) memcpy(ang_vel + 3 * i, r + 17, 12);
+  }
+  return 0;
+}
+
+static int contact_query(AgSim* s, int body_a, int body_b, int link_a, int link_b, int max_pts, AgContact* out, int32_t* count, float* fsum) {
+  const int N = s->S.N;
+  if (body_a < 0 || body_a >= s->nb) return fail("bad body");
+  size_t rec = sizeof(AgContact) / sizeof(float);
+  float* st = stage(s, (size_t)N * max_pts * rec + (size_t)N);
+  if (!st) return fail("staging alloc failed");
+  KP p = kp0();
+  p.i0 = body_a; p.i1 = body_b; p.i2 = link_a < -1 ? -2 : (link_a < 0 ? s->body_link0[body_a] : s->body_link0[body_a] + 1 + link_a);
+  p.i3 = (body_b < 0 || link_b < -1) ? -2 : (link_b < 0 ? s->body_link0[body_b] : s->body_link0[body_b] + 1 + link_b);
+  p.f0 = (float)max_pts; p.p1 = st; p.p2 = s->d_icount; p.p3 = st + (size_t)N * max_pts * rec;
+  LAUNCH(s, k_contact_query, N, p);
+  if (out && max_pts > 0 && d2h(s, out, st, (size_t)N * max_pts * sizeof(AgContact))) return -1;
+  if (count && d2h(s, count, s->d_icount, sizeof(int) * N)) return -1;
+  if (fsum && d2h(s, fsum, st + (size_t)N * max_pts * rec, sizeof(float) * N)) return -1;
+  return 0;
+}
+int ag_get_contacts(AgSim* s, int body_a, int body_b, int link_a, int link_b, int max_pts, AgContact* out, int32_t* count) {
+  return contact_query(s, body_a, body_b, link_a, link_b, max_pts, out, count, nullptr);
+}
+int ag_contact_force_sum(AgSim* s, int body_a, int body_b, int link_a, int link_b, float* out) {
+  return contact_query(s, body_a, body_b, link_a, link_b, 0, nullptr, nullptr, out);
+}
+int ag_closest_points(AgSim* s, int body_a, int body_b, float distance, int max_pts, AgContact* out, int32_t* count) {
+  const int N = s->S.N;
+  if (body_a < 0 || body_a >= s->nb || body_b < 0 || body_b >= s->nb) return fail("bad body");
+  run_fk_all(s);
+  size_t rec = sizeof(AgContact) / sizeof(float);
+  float* st = stage(s, (size_t)N * std::max(1, max_pts) * rec);
+  if (!st) return fail("staging alloc failed");
+  KP p = kp0(); p.i0 = body_a; p.i1 = body_b; p.i2 = max_pts; p.f0 = distance; p.p1 = st; p.p2 = s->d_icount;
+  LAUNCH(s, k_closest, N, p);
+  if (out && max_pts > 0 && d2h(s, out, st, (size_t)N * max_pts * sizeof(AgContact))) return -1;
+  if (count && d2h(s, count, s->d_icount, sizeof(int) * N)) return -1;
+  return 0;
+}
+
+size_t ag_state_size(const AgSim* s) { return (size_t)s->nb * 13 + (size_t)s->nl * 2; }
+int ag_state_get(AgSim* s, float* out) {
+  const int N = s->S.N; size_t sz = ag_state_size(s);
+  std::vector<float> bp((size_t)s->nb * 3 * N), bq((size_t)s->nb * 4 * N), bl((size_t)s->nb * 3 * N), ba((size_t)s->nb * 3 * N), q((size_t)s->nl * N), qd((size_t)s->nl * N);
+  d2h(s, bp.data(), s->S.base_pos, bp.size() * 4); d2h(s, bq.data(), s->S.base_quat, bq.size() * 4);
+  d2h(s, bl.data(), s->S.base_lin, bl.size() * 4); d2h(s, ba.data(), s->S.base_ang, ba.size() * 4);
+  d2h(s, q.data(), s->S.jq, q.size() * 4); d2h(s, qd.data(), s->S.jqd, qd.size() * 4);
+  for (int e = 0; e < N; e++) {
+    float* o = out + sz * e;
+    for (int b = 0; b < s->nb; b++) {
+      for (int a = 0; a < 3; a++) { o[a] = bp[((size_t)b * 3 + a) * N + e]; o[7 + a] = bl[((size_t)b * 3 + a) * N + e]; o[10 + a] = ba[((size_t)b * 3 + a) * N + e]; }
+      for (int a = 0; a < 4; a++) o[3 + a] = bq[((size_t)b * 4 + a) * N + e];
+      o += 13;
+    }
+    for (int k = 0; k < s->nl; k++) { o[0] = q[(size_t)k * N + e]; o[1] = qd[(size_t)k * N + e]; o += 2; }
+  }
+  return 0;
+}
+int ag_state_set(AgSim* s, const float* in) {
+  const int N = s->S.N; size_t sz = ag_state_size(s);
+  std::vector<float> bp((size_t)s->nb * 3 * N), bq((size_t)s->nb * 4 * N), bl((size_t)s->nb * 3 * N), ba((size_t)s->nb * 3 * N), q((size_t)s->nl * N), qd((size_t)s->nl * N);
+  for (int e = 0; e < N; e++) {
+    const float* o = in + sz * e;
+    for (int b = 0; b < s->nb; b++) {
+      for (int a = 0; a < 3; a++) { bp[((size_t)b * 3 + a) * N + e] = o[a]; bl[((size_t)b * 3 + a) * N + e] = o[7 + a]; ba[((size_t)b * 3 + a) * N + e] = o[10 + a]; }
+      for (int a = 0; a < 4; a++) bq[((size_t)b * 4 + a) * N + e] = o[3 + a];
+      o += 13;
+    }
+    for (int k = 0; k < s->nl; k++) { q[(size_t)k * N + e] = o[0]; qd[(size_t)k * N + e] = o[1]; o += 2; }
+  }
+  h2d(s, s->S.base_pos, bp.data(), bp.size() * 4); h2d(s, s->S.base_quat, bq.data(), bq.size() * 4);
+  h2d(s, s->S.base_lin, bl.data(), bl.size() * 4); h2d(s, s->S.base_ang, ba.data(), ba.size() * 4);
+  h2d(s, s->S.jq, q.data(), q.size() * 4); h2d(s, s->S.jqd, qd.data(), qd.size() * 4);
+  run_fk_all(s);
+  return 0;
+}
+
+int ag_overflow_count(AgSim* s) {
+  std::vector<int> o(s->S.N);
+  if (d2h(s, o.data(), s->S.overflow, sizeof(int) * s->S.N)) return -1;
+  int n = 0; for (int v : o) n += v != 0;
+  return n;
+}
+
+// ------------------------------------------------------------------ fused FeedingEnv path
+int ag_feeding_init(AgSim* s, const AgFeedingParams* p, const int32_t* gender_is_male) {
+  const int N = s->S.N;
+  FeedDev& F = s->F;
+  F.P = *p;
+  if (p->n_foods > 16) return fail("too many foods");
+  F.male = dalloc<int>(s, N); F.food_state = dalloc<int>(s, N); F.iteration = dalloc<int>(s, N); F.task_success = dalloc<int>(s, N);
+  F.food_near = dalloc<int>(s, (size_t)N * 16);
+  F.action = dalloc<float>(s, (size_t)N * 7); F.rng = dalloc<unsigned long long>(s, N);
+  s->d_action = dalloc<float>(s, (size_t)N * 7); s->d_obs = dalloc<float>(s, (size_t)N * 25);
+  s->d_reward = dalloc<float>(s, N); s->d_done = dalloc<float>(s, N); s->d_info = dalloc<float>(s, (size_t)N * 4);
+  if (!s->d_info) return fail("device allocation failed");
+  if (h2d(s, F.male, gender_is_male, sizeof(int) * N)) return -1;
+#ifndef AG_CPU_EMU
+  CK(cudaMallocHost((void**)&s->h_pin_in, sizeof(float) * N * 7));
+  CK(cudaMallocHost((void**)&s->h_pin_out, sizeof(float) * N * 31));
+#else
+  s->h_pin_in = (float*)malloc(sizeof(float) * N * 7); s->h_pin_out = (float*)malloc(sizeof(float) * N * 31);
+#endif
+  s->F_dev = dalloc<FeedDev>(s, 1);
+  if (!s->F_dev || h2d(s, s->F_dev, &s->F, sizeof(FeedDev))) return fail("FeedDev upload failed");
+  s->feeding = true;
+  return ag_feeding_reset_episode(s, nullptr);
+}
+int ag_feeding_reset_episode(AgSim* s, const int32_t* env_mask) {
+  if (!s->feeding) return fail("ag_feeding_init not called");
+  const int N = s->S.N;
+  std::vector<int> fs(N), it(N), ts(N); std::vector<unsigned long long> rng(N);
+  d2h(s, fs.data(), s->F.food_state, sizeof(int) * N); d2h(s, it.data(), s->F.iteration, sizeof(int) * N);
+  d2h(s, ts.data(), s->F.task_success, sizeof(int) * N); d2h(s, rng.data(), s->F.rng, sizeof(unsigned long long) * N);
+  int full = (1 << s->F.P.n_foods) - 1;
+  for (int e = 0; e < N; e++) if (!env_mask || env_mask[e]) {
+    fs[e] = full | (full << 16); it[e] = 0; ts[e] = 0;
+    if (rng[e] == 0) rng[e] = (s->F.P.seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(e + 1)) | 1ull;
+  }
+  h2d(s, s->F.food_state, fs.data(), sizeof(int) * N); h2d(s, s->F.iteration, it.data(), sizeof(int) * N);
+  h2d(s, s->F.task_success, ts.data(), sizeof(int) * N); h2d(s, s->F.rng, rng.data(), sizeof(unsigned long long) * N);
+  return 0;
+}
+
+static int feeding_step_enqueue(AgSim* s, const float* action_dev, float* obs, float* reward, float* done, float* info) {
+  const int N = s->S.N;
+  KP p = kp0(); p.p0 = action_dev; p.p1 = s->F_dev;
+  LAUNCH(s, k_feed_pre, N, p);
+  for (int i = 0; i < s->F.P.frame_skip * (s->cfg.num_substeps > 0 ? s->cfg.num_substeps : 1); i++) substep(s);
+  KP z = kp0();
+  LAUNCH(s, k_fk, N, z);
+  KP a = kp0(); a.p0 = s->S.movcol; a.i0 = s->S.nmovcol;
+  LAUNCH(s, k_aabb, (size_t)s->S.nmovcol * N, a);
+  KP l = kp0(); l.p0 = s->S.movlink; l.i0 = s->S.nmovlink;
+  LAUNCH(s, k_linkaabb, (size_t)s->S.nmovlink * N, l);
+  KP f = kp0(); f.p1 = s->F_dev;
+  LAUNCH(s, k_feed_food, (size_t)N * s->F.P.n_foods, f);
+  KP q = kp0(); q.p0 = action_dev; q.p1 = s->F_dev; q.p2 = obs; q.p3 = reward; q.p4 = done; q.p5 = info;
+  LAUNCH(s, k_feed_post, N, q);
+  return 0;
+}
+int ag_feeding_step_dev(AgSim* s, const float* action_dev, float* obs_dev, float* reward_dev, float* done_dev, float* info_dev) {
+  if (!s->feeding) return fail("ag_feeding_init not called");
+  int rc = feeding_step_enqueue(s, action_dev, obs_dev, reward_dev, done_dev, info_dev);
+#ifndef AG_CPU_EMU
+  CK(cudaGetLastError());
+#endif
+  return rc;
+}
+int ag_feeding_step_host(AgSim* s, const float* action, float* obs, float* reward, float* done, float* info) {
+  if (!s->feeding) return fail("ag_feeding_init not called");
+  const int N = s->S.N;
+  memcpy(s->h_pin_in, action, sizeof(float) * N * 7);
+#ifndef AG_CPU_EMU
+  CK(cudaMemcpyAsync(s->d_action, s->h_pin_in, sizeof(float) * N * 7, cudaMemcpyHostToDevice, s->stream));
+#else
+  memcpy(s->d_action, s->h_pin_in, sizeof(float) * N * 7);
+#endif
+  if (feeding_step_enqueue(s, s->d_action, s->d_obs, s->d_reward, s->d_done, s->d_info)) return -1;
+#ifndef AG_CPU_EMU
+  CK(cudaMemcpyAsync(s->h_pin_out, s->d_obs, sizeof(float) * N * 25, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(s->h_pin_out + (size_t)N * 25, s->d_reward, sizeof(float) * N, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(s->h_pin_out + (size_t)N * 26, s->d_done, sizeof(float) * N, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(s->h_pin_out + (size_t)N * 27, s->d_info, sizeof(float) * N * 4, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+#else
+  memcpy(s->h_pin_out, s->d_obs, sizeof(float) * N * 25); memcpy(s->h_pin_out + (size_t)N * 25, s->d_reward, sizeof(float) * N);
+  memcpy(s->h_pin_out + (size_t)N * 26, s->d_done, sizeof(float) * N); memcpy(s->h_pin_out + (size_t)N * 27, s->d_info, sizeof(float) * N * 4);
+#endif
+  memcpy(obs, s->h_pin_out, sizeof(float) * N * 25);
+  memcpy(reward, s->h_pin_out + (size_t)N * 25, sizeof(float) * N);
+  memcpy(done, s->h_pin_out + (size_t)N * 26, sizeof(float) * N);
+  if (info) memcpy(info, s->h_pin_out + (size_t)N * 27, sizeof(float) * N * 4);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+"""BatchSim — numpy-facing wrapper of the C ABI (include/agphys.h) for N lock-step envs.
+
+This is the object the `pybullet`-shaped shim and the env classes talk to.  All arrays are
+env-major (`[N, k, c]`); the library transposes to its SoA device layout.  The CUDA library is
+mandatory: construction raises if it cannot be loaded or no CUDA device is present.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a, shape=None):
+    if a is None:
+        return None
+    a = np.asarray(a, dtype=np.float32)
+    if shape is not None:
+        a = np.broadcast_to(a, shape)
+    return np.ascontiguousarray(a)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+class BatchSim:
+    def __init__(self, scene, cfg=None, n_envs=1, device=0, _lib=None):
+        self.lib = _lib if _lib is not None else capi.load_library()
+        self.scene = scene
+        self.cfg = cfg or capi.default_config()
+        self.n = int(n_envs)
+        self._desc = scene.as_ctypes()
+        self.h = self.lib.ag_create(C.byref(self._desc), C.byref(self.cfg), self.n, int(device))
+        if not self.h:
+            raise RuntimeError('ag_create failed: %s' % self.lib.ag_last_error().decode())
+        self.contact_dtype = capi.CONTACT_DTYPE
+        for b in range(scene.n_bodies):
+            self.set_base_pose(b, scene['base_pos0'][b], scene['base_quat0'][b])
+        self.forward_kinematics()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.lib.ag_last_error().decode())
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.ag_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- setters
+    def set_base_pose(self, body, pos=None, quat=None, mask=None):
+        pos, quat = _f32(pos, (self.n, 3)), _f32(quat, (self.n, 4))
+        self._ck(self.lib.ag_set_base_pose(self.h, body, _p(pos), _p(quat), _p(_i32(mask))))
+
+    def set_base_velocity(self, body, lin=None, ang=None, mask=None):
+        lin, ang = _f32(lin, (self.n, 3)), _f32(ang, (self.n, 3))
+        self._ck(self.lib.ag_set_base_velocity(self.h, body, _p(lin), _p(ang), _p(_i32(mask))))
+
+    def set_joint_state(self, links, q=None, qd=None, mask=None):
+        links = _i32(links)
+        q, qd = _f32(q, (self.n, len(links))), _f32(qd, (self.n, len(links)))
+        self._ck(self.lib.ag_set_joint_state(self.h, len(links), _p(links), _p(q), _p(qd), _p(_i32(mask))))
+
+    def set_link_friction(self, link, mu, mask=None):
+        mu = _f32(mu, (self.n,))
+        self._ck(self.lib.ag_set_link_friction(self.h, int(link), _p(mu), _p(_i32(mask))))
+
+    def set_body_active(self, body, active):
+        m = _i32(np.broadcast_to(np.asarray(active, dtype=np.int32), (self.n,)))
+        self._ck(self.lib.ag_set_body_active(self.h, body, _p(m)))
+
+    def set_motor(self, links, mode, target=None, kp=None, kd=None, max_force=None):
+        links = _i32(links)
+        n = len(links)
+        target = _f32(target, (self.n, n))
+        kp = _f32(kp, (n,)) if kp is not None else None
+        kd = _f32(kd if kd is not None else 1.0, (n,))
+        mf = _f32(max_force, (n,)) if max_force is not None else None
+        self._ck(self.lib.ag_set_motor_host(self.h, n, _p(links), int(mode), _p(target), _p(kp), _p(kd), _p(mf)))
+
+    def set_motor_targets(self, links, target):
+        links = _i32(links)
+        t = _f32(target, (self.n, len(links)))
+        self._ck(self.lib.ag_set_motor_targets_host(self.h, len(links), _p(links), _p(t)))
+
+    def forward_kinematics(self):
+        self._ck(self.lib.ag_forward_kinematics(self.h))
+
+    def step(self, n_steps=1):
+        self._ck(self.lib.ag_step(self.h, int(n_steps)))
+
+    # ---- getters
+    def get_joint_states(self, links):
+        links = _i32(links)
+        n = len(links)
+        q, qd, tau = (np.zeros((self.n, n), dtype=np.float32) for _ in range(3))
+        self._ck(self.lib.ag_get_joint_states(self.h, n, _p(links), _p(q), _p(qd), _p(tau)))
+        return q, qd, tau
+
+    def get_link_states(self, links):
+        links = _i32(links)
+        n = len(links)
+        pos, cpos, lv, av = (np.zeros((self.n, n, 3), dtype=np.float32) for _ in range(4))
+        quat, cquat = (np.zeros((self.n, n, 4), dtype=np.float32) for _ in range(2))
+        self._ck(self.lib.ag_get_link_states(self.h, n, _p(links), _p(pos), _p(quat), _p(cpos), _p(cquat), _p(lv), _p(av)))
+        return dict(pos=pos, quat=quat, com_pos=cpos, com_quat=cquat, lin_vel=lv, ang_vel=av)
+
+    def get_contacts(self, body_a, body_b=-2, link_a=-2, link_b=-2, max_pts=64):
+        out = np.zeros((self.n, max_pts), dtype=self.contact_dtype)
+        cnt = np.zeros(self.n, dtype=np.int32)
+        self._ck(self.lib.ag_get_contacts(self.h, body_a, body_b, link_a, link_b, max_pts, _p(out), _p(cnt)))
+        return out, cnt
+
+    def contact_force_sum(self, body_a, body_b=-2, link_a=-2, link_b=-2):
+        out = np.zeros(self.n, dtype=np.float32)
+        self._ck(self.lib.ag_contact_force_sum(self.h, body_a, body_b, link_a, link_b, _p(out)))
+        return out
+
+    def closest_points(self, body_a, body_b, distance, max_pts=64):
+        out = np.zeros((self.n, max_pts), dtype=self.contact_dtype)
+        cnt = np.zeros(self.n, dtype=np.int32)
+        self._ck(self.lib.ag_closest_points(self.h, body_a, body_b, float(distance), max_pts, _p(out), _p(cnt)))
+        return out, cnt
+
+    def state_get(self):
+        sz = self.lib.ag_state_size(self.h)
+        out = np.zeros((self.n, sz), dtype=np.float32)
+        self._ck(self.lib.ag_state_get(self.h, _p(out)))
+        return out
+
+    def state_set(self, st):
+        st = _f32(st)
+        self._ck(self.lib.ag_state_set(self.h, _p(st)))
+
+    def kernel_launches(self):
+        return int(self.lib.ag_kernel_launches(self.h))
+
+    def overflow_count(self):
+        return int(self.lib.ag_overflow_count(self.h))
+
+    # ---- fused feeding path
+    def feeding_init(self, params, gender_is_male):
+        self._feed_params = params
+        g = _i32(np.broadcast_to(np.asarray(gender_is_male, dtype=np.int32), (self.n,)))
+        self._ck(self.lib.ag_feeding_init(self.h, C.byref(params), _p(g)))
+
+    def feeding_reset_episode(self, mask=None):
+        self._ck(self.lib.ag_feeding_reset_episode(self.h, _p(_i32(mask))))
+
+    def feeding_step_host(self, action):
+        a = _f32(action, (self.n, 7))
+        obs = np.zeros((self.n, 25), dtype=np.float32)
+        rew, done = np.zeros(self.n, dtype=np.float32), np.zeros(self.n, dtype=np.float32)
+        info = np.zeros((self.n, 4), dtype=np.float32)
+        self._ck(self.lib.ag_feeding_step_host(self.h, _p(a), _p(obs), _p(rew), _p(done), _p(info)))
+        return obs, rew, done, info
+
+    def feeding_step_dev(self, action_ptr, obs_ptr, reward_ptr, done_ptr, info_ptr):
+        self._ck(self.lib.ag_feeding_step_dev(self.h, C.c_void_p(action_ptr), C.c_void_p(obs_ptr), C.c_void_p(reward_ptr),
+                                              C.c_void_p(done_ptr), C.c_void_p(info_ptr)))

@@ -1,0 +1,214 @@
+/* agphys.h — C ABI of the B200-native batched physics step for Assistive Gym.
+ *
+ * Drop-in boundary: the reference drives its physics through ~60 `pybullet` C-extension calls
+ * (SURVEY.md §8(b)); every entry point below cites the reference call site(s) it replaces
+ * (paths relative to /root/reference/assistive_gym/envs).  The host-side mirror
+ * (`assistive_gym_b200/bullet_shim.py`) binds these with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - `extern "C"`, plain pointers and sizes only.  Return 0 on success, <0 on error;
+ *     `ag_last_error()` gives the message.  No exceptions cross the ABI.
+ *   - A simulation holds N lock-step copies ("envs") of one immutable scene template.
+ *   - Batched buffers are env-major: element (env e, item i, component c) of a [N][K][C] buffer is
+ *     at ((e*K)+i)*C + c.  `*_host` calls take host pointers and include the H2D/D2H copies;
+ *     `*_dev` calls take device pointers valid on the simulation's device and enqueue on the
+ *     simulation's stream.
+ *   - Quaternions are [x,y,z,w] (reference agents/agent.py:60, env.py:192).
+ *   - Link index == joint index == DFS pre-order over the URDF tree, base = -1 (reference
+ *     agents/jaco.py:8-18).  In this ABI links are addressed by *global link id* (int) obtained from
+ *     the scene description: `body_link0[body] + 1 + pybullet_link_index` (base: +0).
+ */
+#ifndef AGPHYS_H
+#define AGPHYS_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* joint types (per link: the joint that connects it to its parent) */
+enum { AG_JOINT_FIXED = 0, AG_JOINT_REVOLUTE = 1, AG_JOINT_PRISMATIC = 2,
+       AG_JOINT_FREE_BASE = 3, AG_JOINT_FIXED_BASE = 4 };
+/* collider core types: every convex collider is a vertex set ("core") swept by a sphere of
+ * `col_radius` (sphere = 1 vertex, capsule = 2, box/hull = n); HALFSPACE is the ground plane. */
+enum { AG_COL_SPHERE = 0, AG_COL_CAPSULE = 1, AG_COL_HULL = 2, AG_COL_HALFSPACE = 3 };
+/* motor modes (reference agents/agent.py:33 POSITION_CONTROL, agents/human.py:119 VELOCITY_CONTROL) */
+enum { AG_MOTOR_OFF = 0, AG_MOTOR_POSITION = 1, AG_MOTOR_VELOCITY = 2 };
+
+/* Solver / world parameters.  Defaults restate PyBullet's (SURVEY.md Appendix A — recalled, not
+ * verifiable in this container; every recalled constant is a field).  Replaces
+ * p.setTimeStep / p.setGravity / p.setPhysicsEngineParameter (env.py:104-107, dressing.py:184). */
+typedef struct AgConfig {
+  double dt;                 /* 0.02   env.py:21,104 */
+  int    num_substeps;       /* 1      Bullet numSubSteps=0 -> 1 (dressing.py:184 uses 8) */
+  int    num_solver_iters;   /* 50     Bullet numSolverIterations */
+  double erp;                /* 0.2    non-contact constraint ERP */
+  double contact_erp;        /* 0.08   PyBullet erp2 */
+  double linear_slop;        /* 1e-5 */
+  double residual_threshold; /* 1e-7   leastSquaresResidualThreshold (squared impulses); <=0 disables early exit */
+  double contact_threshold;  /* 0.02   contact breaking threshold FACTOR: points with distance <= factor * min(col_thresh_a, col_thresh_b) are contacts */
+  double linear_damping;     /* 0.04   btMultiBody default */
+  double angular_damping;    /* 0.04 */
+  double max_coord_velocity; /* 100 */
+  double hull_margin;        /* 0.001  collision margin of mesh/box hull colliders (already baked into col_radius by the builder; informational) */
+  int    cone_friction;      /* 1      implicit cone over the 2 friction directions; 0 = pyramid */
+  int    gyroscopic;         /* 1      include w x Iw for free bodies */
+  int    max_contacts;       /* per-env contact budget for the solver (default 128); overflow is flagged */
+} AgConfig;
+
+/* Immutable scene template (host arrays, copied by ag_create).  Built on the host by the
+ * `pybullet`-shaped builder calls the reference issues at reset time (loadURDF jaco.py:53,
+ * createMultiBody human_creation.py:280 / tool.py:34 / env.py:371-380, createConstraint tool.py:46,
+ * setCollisionFilterPair tool.py:44, changeDynamics human.py:110, setGravity(body=) agent.py:197). */
+typedef struct AgSceneDesc {
+  int n_bodies, n_links, n_colliders, n_verts, n_planes, n_pairs, n_constraints;
+  /* bodies [n_bodies] */
+  const int32_t* body_link0;    /* global id of the base link; links of a body are contiguous, DFS order */
+  const int32_t* body_nlinks;   /* number of links including the base */
+  const double*  body_gravity;  /* [n_bodies][3] per-body gravity (fork feature, agent.py:196-197) */
+  /* links [n_links] */
+  const int32_t* link_body;
+  const int32_t* link_parent;   /* global id of parent link, -1 for a base */
+  const int32_t* link_jtype;    /* AG_JOINT_* */
+  const double*  link_axis;     /* [n_links][3] joint axis in the link frame */
+  const double*  link_jpos;     /* [n_links][3] joint frame origin in the parent link frame */
+  const double*  link_jquat;    /* [n_links][4] joint frame orientation in the parent link frame */
+  const double*  link_com;      /* [n_links][3] centre of mass in the link frame */
+  const double*  link_iquat;    /* [n_links][4] inertial (principal) frame orientation in the link frame */
+  const double*  link_inertia;  /* [n_links][3] principal moments */
+  const double*  link_mass;     /* [n_links]   0 => static/locked ("static joints" trick, human.py:108-112) */
+  const double*  link_lower;    /* [n_links] joint limits; limit rows exist iff link_haslimit */
+  const double*  link_upper;
+  const int32_t* link_haslimit;
+  const double*  link_damping;  /* [n_links] joint damping */
+  const double*  link_friction; /* [n_links] lateral friction coefficient */
+  /* colliders [n_colliders]; vertices/planes are expressed in the owning link's frame */
+  const int32_t* col_link;
+  const int32_t* col_type;      /* AG_COL_* */
+  const double*  col_radius;    /* sphere/capsule radius, hull margin */
+  const double*  col_thresh;    /* Bullet's getAngularMotionDisc() of the shape; pair contact threshold =
+                                   AgConfig.contact_threshold * min(thresh_a, thresh_b) */
+  const int32_t* col_v0;        /* first core vertex */
+  const int32_t* col_nv;        /* number of core vertices (<= 64) */
+  const int32_t* col_p0;        /* first face plane (hulls), for the penetration fallback */
+  const int32_t* col_np;
+  const double*  col_center;    /* [n_colliders][3] local AABB centre of the core (link frame) */
+  const double*  col_half;      /* [n_colliders][3] local AABB half extents of the core */
+  const double*  verts;         /* [n_verts][3] */
+  const double*  planes;        /* [n_planes][4] (n, d): n.x <= d inside */
+  /* enabled collision pairs between links (global ids), after self-collision flags, parent-child
+   * exclusion and setCollisionFilterPair overrides; at least one side movable. */
+  const int32_t* pair_link;     /* [n_pairs][2] */
+  /* fixed user constraints (p.createConstraint JOINT_FIXED, tool.py:46-47) */
+  const int32_t* con_link;      /* [n_constraints][2] global ids (parent link, child link) */
+  const double*  con_pivot;     /* [n_constraints][2][3] pivot in each link's frame */
+  const double*  con_quat;      /* [n_constraints][2][4] constraint frame in each link's frame */
+  const double*  con_maxforce;  /* [n_constraints] */
+} AgSceneDesc;
+
+/* One contact point as returned by p.getContactPoints (agent.py:108-115: fields 3,4,5,6,9 used;
+ * distance [8] and normal [7] also filled). */
+typedef struct AgContact {
+  int32_t link_a, link_b;       /* global link ids */
+  float   pos_a[3], pos_b[3];   /* world, on the surfaces */
+  float   normal[3];            /* on B, pointing towards A */
+  float   distance;
+  float   normal_force;         /* accumulated normal impulse / dt of the last substep */
+} AgContact;
+
+typedef struct AgSim AgSim;     /* opaque */
+
+const char* ag_last_error(void);
+void        ag_default_config(AgConfig* cfg);
+
+/* --- lifetime: p.connect / p.resetSimulation / p.disconnect (env.py:34,92-97) ----------------- */
+AgSim* ag_create(const AgSceneDesc* scene, const AgConfig* cfg, int n_envs, int device);
+void   ag_destroy(AgSim* sim);
+int    ag_num_envs(const AgSim* sim);
+void*  ag_stream(AgSim* sim);   /* cudaStream_t the sim enqueues on */
+
+/* --- state setters (host buffers, env-major). p.resetBasePositionAndOrientation (agent.py:149),
+ * p.resetBaseVelocity (agent.py:152), p.resetJointState (agent.py:156,248,250).
+ * `env_mask` (int32[N], may be NULL = all) selects the envs written.  Base pose is the pose of the
+ * base LINK frame. */
+int ag_set_base_pose(AgSim* sim, int body, const float* pos, const float* quat, const int32_t* env_mask);
+int ag_set_base_velocity(AgSim* sim, int body, const float* lin, const float* ang, const int32_t* env_mask);
+int ag_set_joint_state(AgSim* sim, int n, const int32_t* links, const float* q, const float* qd, const int32_t* env_mask);
+/* per-env lateral friction of one link (env.py:120 randomises the plane's) */
+int ag_set_link_friction(AgSim* sim, int link, const float* mu, const int32_t* env_mask);
+/* per-env activation of a body (inactive bodies neither move nor collide; used for the
+ * male/female human variants, human.py:76-77) */
+int ag_set_body_active(AgSim* sim, int body, const int32_t* active);
+/* recompute link world poses from the state (after teleports); also done by ag_step */
+int ag_forward_kinematics(AgSim* sim);
+
+/* --- motors: p.setJointMotorControlArray(POSITION_CONTROL) (agent.py:33, robot.py:77) and
+ * p.setJointMotorControl2(VELOCITY_CONTROL, force=0) (human.py:119).  target is [N][n]
+ * (host or device per the suffix); kp/kd/max_force are per joint, shared by all envs. */
+int ag_set_motor_host(AgSim* sim, int n, const int32_t* links, int mode, const float* target,
+                      const float* kp, const float* kd, const float* max_force);
+int ag_set_motor_targets_dev(AgSim* sim, int n, const int32_t* links, const float* target_dev);
+int ag_set_motor_targets_host(AgSim* sim, int n, const int32_t* links, const float* target);
+
+/* --- the hot path: p.stepSimulation (env.py:226; feeding.py:179) ----------------------------- */
+int ag_step(AgSim* sim, int n_steps);
+
+/* --- read-back: p.getJointStates (agent.py:40,85), p.getLinkState (agent.py:52,54,72),
+ * p.getBasePositionAndOrientation / getBaseVelocity (agent.py:49,71) ------------------------- */
+int ag_get_joint_states(AgSim* sim, int n, const int32_t* links, float* q, float* qd, float* applied_torque);
+/* world pose of link frames ([N][n][3], [N][n][4]) and, optionally, COM pose and COM linear /
+ * angular velocity (NULL to skip). */
+int ag_get_link_states(AgSim* sim, int n, const int32_t* links, float* pos, float* quat,
+                       float* com_pos, float* com_quat, float* lin_vel, float* ang_vel);
+/* p.getContactPoints(bodyA[,bodyB,linkA,linkB]) (agent.py:100-116): body_b/link_a/link_b = -2 for
+ * "any" (link -1 is the base).  Writes up to max_pts contacts per env into out[N][max_pts] and the
+ * number found into count[N].  A is always the queried body (contacts are flipped as needed). */
+int ag_get_contacts(AgSim* sim, int body_a, int body_b, int link_a, int link_b, int max_pts,
+                    AgContact* out, int32_t* count);
+/* sum of normal forces between two bodies, per env ([N]); feeding.py:45-48 */
+int ag_contact_force_sum(AgSim* sim, int body_a, int body_b, int link_a, int link_b, float* out);
+/* p.getClosestPoints(bodyA, bodyB, distance) (agent.py:118-130; feeding.py:71): per env the
+ * closest pair over all collider pairs of the two bodies within `distance`, independent of
+ * collision filters.  count[N] = number of collider pairs within distance. */
+int ag_closest_points(AgSim* sim, int body_a, int body_b, float distance, int max_pts,
+                      AgContact* out, int32_t* count);
+
+/* --- fused FeedingEnv path (feeding.py:12-112 + env.py:174-235): action -> PD targets ->
+ * frame_skip substeps -> obs[25] / reward / done.  All buffers on the device. ------------------- */
+typedef struct AgFeedingParams {
+  int32_t robot_body, tool_body, human_body_m, human_body_f;
+  int32_t arm_links[7];         /* controllable joints (global link ids) */
+  int32_t ee_link;              /* right_end_effector */
+  int32_t head_link_m, head_link_f;
+  int32_t food_body0, n_foods;
+  float   arm_lower[7], arm_upper[7];
+  float   mouth_m[3], mouth_f[3];
+  float   action_multiplier;    /* 0.05 env.py:188 */
+  int32_t frame_skip;           /* 5 */
+  float   w_distance, w_action, w_food; /* config.ini [feeding] */
+  float   c_v, c_f, c_hf, c_fd, c_fdv;  /* config.ini [human_preferences] */
+  float   task_success_threshold;
+  uint64_t seed;
+} AgFeedingParams;
+int ag_feeding_init(AgSim* sim, const AgFeedingParams* p, const int32_t* gender_is_male);
+int ag_feeding_reset_episode(AgSim* sim, const int32_t* env_mask);
+int ag_feeding_step_dev(AgSim* sim, const float* action_dev, float* obs_dev, float* reward_dev,
+                        float* done_dev, float* info_dev);
+/* host-buffer variant (pinned or pageable): H2D of action, D2H of obs/reward/done/info inside */
+int ag_feeding_step_host(AgSim* sim, const float* action, float* obs, float* reward, float* done, float* info);
+
+/* --- checkpoint / parity: full per-env dynamic state as a flat float blob -------------------- */
+size_t ag_state_size(const AgSim* sim);           /* floats per env */
+int    ag_state_get(AgSim* sim, float* out);      /* [N][state_size] host */
+int    ag_state_set(AgSim* sim, const float* in);
+
+/* --- introspection for measurement --------------------------------------------------------- */
+uint64_t ag_kernel_launches(const AgSim* sim);    /* kernels launched since creation */
+int      ag_overflow_count(AgSim* sim);           /* envs that exceeded the contact budget last step */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGPHYS_H */

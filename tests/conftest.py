@@ -1,0 +1,37 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+
+
+@pytest.fixture(scope='session')
+def feeding():
+    from assistive_gym_b200.feeding_batch import FeedingBatch
+    return FeedingBatch()
+
+
+@pytest.fixture(scope='session')
+def emu_lib():
+    """Kernel bodies compiled for the host (tests/kernel_harness) — kernel-logic checks without a GPU."""
+    import subprocess
+    from assistive_gym_b200 import capi
+    so = os.path.join(ROOT, 'tests', 'kernel_harness', 'libagphys_emu.so')
+    subprocess.check_call([os.path.join(ROOT, 'tests', 'kernel_harness', 'build.sh')])
+    return capi.load_library(so)
+
+
+@pytest.fixture(scope='session')
+def gpu_lib():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from assistive_gym_b200 import capi
+    return capi.load_library()
