@@ -73,6 +73,11 @@ struct AgSim {
   FeedDev F; FeedDev* F_dev; bool feeding;
   float *d_action, *d_obs, *d_reward, *d_done, *d_info;
   float *h_pin_in, *h_pin_out;
+  // profiling
+  bool profiling;
+  std::vector<std::string> knames;
+  std::vector<int> ev_slot;
+  std::vector<void*> ev_begin, ev_end;
 };
 
 #ifndef AG_CPU_EMU
@@ -127,12 +132,20 @@ static const T* upload(AgSim* s, const std::vector<T>& v) {
 template <typename T>
 static T* dalloc(AgSim* s, size_t n) { return (T*)dev_alloc(s, n * sizeof(T)); }
 
+// per-kernel device timing (bench.py roofline): CUDA events recorded on the sim's own stream around
+// every launch while profiling is enabled; resolved lazily by ag_profile_get.
+#define AG_MAX_KNAMES 32
+static int prof_slot(AgSim* s, const char* name);
+static void prof_mark(AgSim* s, int slot, bool begin);
 #ifndef AG_CPU_EMU
 #define LAUNCH(sim, kern, nthreads, kp)                                                     \
   do {                                                                                      \
     KP kp__ = (kp); kp__.n = (int)(nthreads);                                               \
     if (kp__.n > 0) {                                                                       \
+      int ps__ = (sim)->profiling ? prof_slot((sim), #kern) : -1;                           \
+      if (ps__ >= 0) prof_mark((sim), ps__, true);                                          \
       kern<<<(kp__.n + 127) / 128, 128, 0, (sim)->stream>>>((sim)->S, kp__);                \
+      if (ps__ >= 0) prof_mark((sim), ps__, false);                                         \
       (sim)->launches++;                                                                    \
     }                                                                                       \
   } while (0)
@@ -140,6 +153,23 @@ static T* dalloc(AgSim* s, size_t n) { return (T*)dev_alloc(s, n * sizeof(T)); }
 #define LAUNCH(sim, kern, nthreads, kp) \
   do { KP kp__ = (kp); kp__.n = (int)(nthreads); if (kp__.n > 0) { kern((sim)->S, kp__); (sim)->launches++; } } while (0)
 #endif
+
+static int prof_slot(AgSim* s, const char* name) {
+  for (size_t i = 0; i < s->knames.size(); i++) if (s->knames[i] == name) return (int)i;
+  if (s->knames.size() >= AG_MAX_KNAMES) return -1;
+  s->knames.push_back(name);
+  return (int)s->knames.size() - 1;
+}
+static void prof_mark(AgSim* s, int slot, bool begin) {
+#ifndef AG_CPU_EMU
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, s->stream);
+  if (begin) { s->ev_slot.push_back(slot); s->ev_begin.push_back((void*)ev); } else s->ev_end.push_back((void*)ev);
+#else
+  (void)s; (void)slot; (void)begin;
+#endif
+}
 
 static KP kp0() { KP p; memset(&p, 0, sizeof(p)); return p; }
 
@@ -172,7 +202,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   AgSim* s = new AgSim();
   memset(&s->S, 0, sizeof(SimDev));
   memset(&s->F, 0, sizeof(FeedDev));
-  s->cfg = *cfg; s->device = device; s->launches = 0; s->feeding = false; s->stream = nullptr; s->F_dev = nullptr;
+  s->cfg = *cfg; s->device = device; s->launches = 0; s->feeding = false; s->stream = nullptr; s->F_dev = nullptr; s->profiling = false;
   s->d_stage = nullptr; s->stage_floats = 0;
 #ifndef AG_CPU_EMU
   if (cudaSetDevice(device) != cudaSuccess) { g_err = "cudaSetDevice failed (is a CUDA device present? there is no CPU fallback)"; delete s; return nullptr; }
@@ -370,6 +400,31 @@ void ag_destroy(AgSim* s) {
 int ag_num_envs(const AgSim* s) { return s->S.N; }
 void* ag_stream(AgSim* s) { return (void*)s->stream; }
 uint64_t ag_kernel_launches(const AgSim* s) { return s->launches; }
+
+int ag_profile_enable(AgSim* s, int on) {
+  s->profiling = on != 0;
+  return 0;
+}
+// Resolves the recorded events: per kernel name total milliseconds and launch count since the last call.
+int ag_profile_get(AgSim* s, int max_names, char* names, int name_stride, float* total_ms, int32_t* counts) {
+  int n = (int)s->knames.size();
+  if (n > max_names) n = max_names;
+  for (int i = 0; i < n; i++) { total_ms[i] = 0.f; counts[i] = 0; snprintf(names + (size_t)i * name_stride, name_stride, "%s", s->knames[i].c_str()); }
+#ifndef AG_CPU_EMU
+  CK(cudaStreamSynchronize(s->stream));
+  size_t m = std::min(s->ev_begin.size(), s->ev_end.size());
+  for (size_t i = 0; i < m; i++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, (cudaEvent_t)s->ev_begin[i], (cudaEvent_t)s->ev_end[i]);
+    int sl = s->ev_slot[i];
+    if (sl < n) { total_ms[sl] += ms; counts[sl] += 1; }
+  }
+  for (void* e : s->ev_begin) cudaEventDestroy((cudaEvent_t)e);
+  for (void* e : s->ev_end) cudaEventDestroy((cudaEvent_t)e);
+#endif
+  s->ev_begin.clear(); s->ev_end.clear(); s->ev_slot.clear();
+  return n;
+}
 
 // ---- staging helpers: host env-major [N][K] <-> device SoA via gather/scatter kernels
 static float* stage(AgSim* s, size_t floats) {

@@ -149,6 +149,25 @@ class BatchSim:
     def overflow_count(self):
         return int(self.lib.ag_overflow_count(self.h))
 
+    def profile_enable(self, on=True):
+        self._ck(self.lib.ag_profile_enable(self.h, int(bool(on))))
+
+    def profile_get(self):
+        """{kernel name: (total ms, launches)} since the last call."""
+        mx, stride = 32, 48
+        names = C.create_string_buffer(mx * stride)
+        ms = np.zeros(mx, dtype=np.float32)
+        cnt = np.zeros(mx, dtype=np.int32)
+        n = self.lib.ag_profile_get(self.h, mx, names, stride, _p(ms), _p(cnt))
+        out = {}
+        for i in range(max(n, 0)):
+            nm = names.raw[i * stride:(i + 1) * stride].split(b'\0')[0].decode()
+            out[nm] = (float(ms[i]), int(cnt[i]))
+        return out
+
+    def stream_ptr(self):
+        return int(self.lib.ag_stream(self.h) or 0)
+
     # ---- fused feeding path
     def feeding_init(self, params, gender_is_male):
         self._feed_params = params

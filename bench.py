@@ -1,0 +1,290 @@
+#!/usr/bin/env python3
+"""bench.py — env-steps/s of the batched FeedingJaco-v1 physics step (BASELINE.json metric).
+
+A "step" is one `env.step` over the whole batch: action -> PD targets -> 5 physics substeps ->
+obs / reward / done read-back (reference envs/feeding.py:12-37, envs/env.py:174-235).
+
+  python bench.py --gpus N --steps K --warmup W        (torchrun launches it for N > 1)
+  python bench.py --impl reference ...                 CPU arm: the oracle restatement on host cores
+                                                       (PyBullet, the real reference path, is not installable here)
+
+Prints ONE JSON line on rank 0.  `value` = device-resident throughput (actions already in HBM),
+`e2e` = the same metric through the host-buffer C-ABI call (H2D of actions, D2H of obs/reward/done
+inside the timed region), `roofline` = the dominant kernel's algorithmic bytes / measured device
+time against the measured HBM peak, `cpu_baseline` = the oracle timed on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_SUBSTEP = 2458          # algorithmic bytes per env-substep (12 288 B per env-step / 5)
+B_STEP = 12288
+BATCH_PER_GPU = 4096
+METRIC = 'env-steps/sec FeedingJaco-v1 @batch4096'
+
+
+def measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': float(np.max(mx)) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_oracle_rate(fb, n_envs, env_steps, threads, seed=0):
+    """env-steps/s of the CPU oracle on a bounded sample of the same workload."""
+    from assistive_gym_b200 import capi
+    from oracle.oracle_py import OracleSim
+    from tests.parity_cases import take_step_targets
+    cpu = OracleSim(fb.scene, capi.default_config(), n_envs, threads=threads)
+    rng = np.random.default_rng(seed)
+    fb.reset(cpu, rng, settle_steps=25)
+    t0 = time.perf_counter()
+    for _ in range(env_steps):
+        act = rng.uniform(-1, 1, size=(n_envs, 7))
+        tgt = take_step_targets(cpu.get_joint_states(fb.arm_links)[0], act, fb.arm_lower, fb.arm_upper)
+        cpu.set_motor_targets(fb.arm_links, tgt)
+        cpu.step(5)
+        # read-back that feeds obs / reward (same queries the reference issues per step)
+        cpu.get_link_states([fb.ee_link, int(fb.scene['body_link0'][fb.tool])])
+        for hb in fb.humans.values():
+            cpu.contact_force_sum(fb.tool, hb)
+            cpu.contact_force_sum(fb.robot, hb)
+    dt = time.perf_counter() - t0
+    return n_envs * env_steps / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  PyBullet cannot be installed here,
+    so this arm times the oracle port on all host cores; kind = "port"."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from assistive_gym_b200.feeding_batch import FeedingBatch
+    fb = FeedingBatch()
+    cores = os.cpu_count() or 1
+    n_envs = max(cores * 8, 32)
+    for _ in range(min(args.warmup, 1)):
+        cpu_oracle_rate(fb, cores, 1, cores)
+    rates, times = [], []
+    per_step_envsteps = 5
+    for _ in range(max(1, min(args.steps, 5))):
+        r, t = cpu_oracle_rate(fb, n_envs, per_step_envsteps, cores)
+        rates.append(r)
+        times.append(t)
+    v = float(np.median(rates))
+    sample = '%d envs x %d env-steps per timed sample, %d samples, oracle port (CPU restatement - PyBullet unavailable), %d threads' % (
+        n_envs, per_step_envsteps, len(rates), cores)
+    out = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
+           'warmup': args.warmup, 'ms_per_step': 1000.0 * float(np.median(times)), 'higher_is_better': True, 'scaling': 'weak',
+           'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+           'config': {'workload': 'FeedingJaco-v1, CPU restatement (PyBullet unavailable), %d envs' % n_envs, 'l2': 'n/a (CPU)'},
+           'cpu_baseline': {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+           'e2e': {'value': v, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+           'gpu_launches': 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='agphys')
+    ap.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='envs per GPU')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--profile-kernels', type=int, default=1)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the physics step has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from assistive_gym_b200 import capi
+    from assistive_gym_b200.feeding_batch import FeedingBatch
+    from assistive_gym_b200.sim import BatchSim
+
+    n = args.batch
+    W = max(args.warmup, 3)
+    K = args.steps
+    fb = FeedingBatch()
+    cfg = capi.default_config()
+    sim = BatchSim(fb.scene, cfg, n, device=local_rank)
+    # per-env seeds derive from the GLOBAL env id so results do not depend on the partition
+    rng = np.random.default_rng(1001 + rank * n)
+    s = fb.reset(sim, rng, settle_steps=25)
+    sim.feeding_init(fb.feeding_params(seed=1001 + rank * n), s['male'])
+    stream = torch.cuda.ExternalStream(sim.stream_ptr(), device=local_rank)
+    dev = torch.device('cuda', local_rank)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(rank)
+    actions = torch.rand((W + K, n, 7), generator=gen, device=dev) * 2 - 1
+    obs = torch.zeros((n, 25), device=dev)
+    rew = torch.zeros(n, device=dev)
+    done = torch.zeros(n, device=dev)
+    info = torch.zeros((n, 4), device=dev)
+    rew_all = torch.zeros(world * n, device=dev) if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)      # 256 MiB > 126 MB L2
+    torch.cuda.synchronize()
+
+    def one_step(i):
+        sim.feeding_step_dev(actions[i].data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), info.data_ptr())
+        if world > 1:   # the single collective of the path: all-gather of the reward tensor
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(rew_all, rew)
+
+    for i in range(W):
+        one_step(i)
+    torch.cuda.synchronize()
+    launches0 = sim.kernel_launches()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    if args.profile_kernels:
+        sim.profile_enable(True)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    for i in range(K):
+        flush.fill_(float(i))                 # L2 flush between timed iterations (default stream)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            starts[i].record(stream)
+        one_step(W + i)
+        with torch.cuda.stream(stream):
+            stops[i].record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    prof = sim.profile_get() if args.profile_kernels else {}
+    sim.profile_enable(False)
+    launches = sim.kernel_launches() - launches0
+    elapsed_ms = float(sum(a.elapsed_time(b) for a, b in zip(starts, stops)))
+    t = torch.tensor([elapsed_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * n * K / (elapsed_ms / 1000.0)
+
+    # ---- e2e: host buffers through the reference-facing call (H2D + D2H inside the timed region)
+    host_actions = np.random.default_rng(7 + rank).uniform(-1, 1, size=(K, n, 7)).astype(np.float32)
+    sim.feeding_step_host(host_actions[0])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        o_h, r_h, d_h, i_h = sim.feeding_step_host(host_actions[i])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * K / float(t.item())
+    overflow = sim.overflow_count()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        roof = None
+        if prof:
+            top = max(prof.items(), key=lambda kv: kv[1][0])
+            name, (ms, cnt) = top
+            per_launch_ms = ms / max(cnt, 1)
+            achieved = n * B_SUBSTEP / (per_launch_ms * 1e-3) / 1e9
+            total_kernel_ms = sum(v[0] for v in prof.values())
+            roof = {'bound': 'hbm', 'kernel': name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                    'traffic': None, 'peak_source': peak_src, 'kernel_ms_per_launch': per_launch_ms,
+                    'kernel_share_of_step': ms / total_kernel_ms if total_kernel_ms else None,
+                    'step_frac': value * B_STEP / 1e9 / peak / world,
+                    'per_kernel_ms_per_step': {k: v[0] / K for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+                    'note': 'the step is latency/issue bound, not HBM bound (SURVEY.md 8(d)); frac is reported per contract'}
+        out = {'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+               'ms_per_step': elapsed_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+               'data': 'synthetic',
+               'config': {'workload': 'FeedingJaco-v1, batch %d per GPU, 5 substeps/step, 50 PGS iters (early exit 1e-7), random actions' % n,
+                          'global_batch': world * n, 'parallelism': 'env-sharded x%d' % world,
+                          'l2': 'flushed between timed steps (256 MiB fill)', 'contact_budget': int(cfg.max_contacts),
+                          'envs_over_contact_budget': overflow,
+                          'collective': 'all_gather(reward) per step' if world > 1 else 'none'},
+               'clocks': clk,
+               'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n * 7 * 4, 'd2h_bytes_per_step': n * 31 * 4},
+               'gpu_launches': int(launches), 'roofline': roof}
+        if not args.no_cpu:
+            cores = os.cpu_count() or 1
+            v, tsec = cpu_oracle_rate(fb, max(8 * cores, 32), 10, cores)
+            out['cpu_baseline'] = {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+                                   'sample': '%d envs x 10 env-steps (%.1f s), CPU restatement (PyBullet unavailable), %d threads' % (max(8 * cores, 32), tsec, cores)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

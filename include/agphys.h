@@ -206,6 +206,9 @@ int    ag_state_set(AgSim* sim, const float* in);
 
 /* --- introspection for measurement --------------------------------------------------------- */
 uint64_t ag_kernel_launches(const AgSim* sim);    /* kernels launched since creation */
+/* per-kernel device time (CUDA events on the sim's stream around every launch while enabled) */
+int      ag_profile_enable(AgSim* sim, int on);
+int      ag_profile_get(AgSim* sim, int max_names, char* names, int name_stride, float* total_ms, int32_t* counts);
 int      ag_overflow_count(AgSim* sim);           /* envs that exceeded the contact budget last step */
 
 #ifdef __cplusplus

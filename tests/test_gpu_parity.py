@@ -1,0 +1,130 @@
+"""GPU parity tests proper: the CUDA build (through the C ABI) against the CPU oracle, plus
+size-independent properties at the benchmark batch size.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+from assistive_gym_b200 import capi
+from assistive_gym_b200.sim import BatchSim
+from tests import parity_cases as pc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def make_sim(gpu_lib):
+    return lambda scene, cfg, n: BatchSim(scene, cfg, n, device=0)
+
+
+def test_rollout_200_substeps_strict(feeding, make_sim):
+    err = pc.rollout_errors(feeding, make_sim, n=8, seed=0, env_steps=40, foods=False)
+    print('strict rollout errors', err)
+    assert err['q'] < pc.TOL_RAD, err
+    assert err['tool'] < pc.TOL_M and err['ee'] < pc.TOL_M and err['bowl'] < pc.TOL_M, err
+
+
+def test_rollout_200_substeps_with_food(feeding, make_sim):
+    err = pc.rollout_errors(feeding, make_sim, n=8, seed=1, env_steps=40, foods=True)
+    print('foods-on rollout errors', err)
+    assert err['q'] < 2e-3 and err['tool'] < 2e-3 and err['ee'] < 2e-3, err
+
+
+def test_onestep_synchronised(feeding, make_sim):
+    err = pc.onestep_errors(feeding, make_sim, n=8, seed=1, steps=30)
+    print('one-step errors', err)
+    assert err['q'] < 1e-5 and err['tool_pos'] < 1e-5, err
+    assert err['pos'] < pc.TOL_M, err
+
+
+def test_onestep_default_early_exit(feeding, make_sim):
+    """Default residual threshold (1e-7): the early-exit decision is discontinuous, so only the
+    well-conditioned quantities are bounded tightly."""
+    err = pc.onestep_errors(feeding, make_sim, n=8, seed=4, steps=20, residual_threshold=1e-7)
+    print('one-step errors (early exit)', err)
+    assert err['q'] < 1e-3 and err['tool_pos'] < pc.TOL_M, err
+
+
+def test_tool_on_body_contact(feeding, make_sim):
+    res = pc.tool_contact_case(feeding, make_sim, n=8, seed=2)
+    print('tool contact', res)
+    assert res['force'] > 1.0, res
+    assert res['force_rel'] < pc.TOL_FORCE, res
+    assert res['pos'] < pc.TOL_M and res['tool_pos'] < pc.TOL_M, res
+
+
+def test_fused_feeding_step_semantics(feeding, make_sim):
+    fb = feeding
+    n = 8
+    cfg = capi.default_config(residual_threshold=0.0)
+    cpu, dev, s = pc.synced_pair(fb, make_sim, n, 3, cfg)
+    dev.feeding_init(fb.feeding_params(), s['male'])
+    st = dict(male=s['male'], foods=np.ones((n, 8), dtype=bool), active=np.ones((n, 8), dtype=bool),
+              iteration=np.zeros(n, dtype=int), task_success=np.zeros(n, dtype=int))
+    rng = np.random.default_rng(11)
+    for k in range(6):
+        act = rng.uniform(-1.5, 1.5, size=(n, 7)).astype(np.float32)
+        tgt = pc.take_step_targets(cpu.get_joint_states(fb.arm_links)[0], act, fb.arm_lower, fb.arm_upper)
+        cpu.set_motor_targets(fb.arm_links, tgt)
+        cpu.step(5)
+        obs_ref, rew_ref, done_ref, _ = pc.feeding_semantics_reference(fb, cpu, act, st)
+        obs, rew, done, info = dev.feeding_step_host(act)
+        assert np.abs(obs - obs_ref).max() < 1e-3, (k, np.abs(obs - obs_ref).max(axis=0))
+        assert np.abs(rew - rew_ref).max() < 2e-3, (k, rew, rew_ref)
+        assert np.array_equal(done > 0.5, done_ref)
+
+
+def test_golden_fixture(feeding, make_sim):
+    """Committed oracle-generated fixture (tests/golden/make_golden.py): state after 10 substeps."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'feeding_10substeps.npz'))
+    fb = feeding
+    n = z['state0'].shape[0]
+    cfg = capi.default_config(residual_threshold=0.0)
+    dev = make_sim(fb.scene, cfg, n)
+    sample = {k[2:]: z[k] for k in z.files if k.startswith('s_')}
+    fb.reset(dev, np.random.default_rng(0), settle_steps=0, sample=sample)
+    dev.state_set(z['state0'])
+    dev.set_motor_targets(fb.arm_links, z['targets'])
+    dev.step(10)
+    st = dev.state_get().astype(np.float64)
+    nb = fb.scene.n_bodies
+    dq = np.abs(st[:, nb * 13:] - z['state10'][:, nb * 13:]).reshape(n, -1, 2)[:, :, 0].max()
+    dtool = np.abs(st[:, fb.tool * 13:fb.tool * 13 + 3] - z['state10'][:, fb.tool * 13:fb.tool * 13 + 3]).max()
+    assert dq < pc.TOL_RAD and dtool < pc.TOL_M, (dq, dtool)
+
+
+def test_batch4096_properties(feeding, make_sim):
+    """BASELINE.json batch size: replicated envs stay bit-identical (lock-step determinism), different
+    envs stay finite and normalised, the contact budget is not exceeded, foods stay in the spoon at rest."""
+    fb = feeding
+    n = 4096
+    cfg = capi.default_config()
+    dev = make_sim(fb.scene, cfg, n)
+    rng = np.random.default_rng(5)
+    s = fb.sample(n, rng)
+    for k in s:                 # envs [0:64) replicated into [64:128)
+        s[k][64:128] = s[k][0:64]
+    import copy
+    rep = np.random.default_rng(9)
+    fb.reset(dev, rep, settle_steps=0, sample=s)
+    st = dev.state_get()
+    st[64:128] = st[0:64]
+    dev.state_set(st)
+    q0 = dev.get_joint_states(fb.arm_links)[0]
+    dev.set_motor_targets(fb.arm_links, q0)
+    dev.step(25)
+    dev.feeding_init(fb.feeding_params(), s['male'])
+    act = np.zeros((n, 7), dtype=np.float32)
+    arng = np.random.default_rng(1)
+    for i in range(4):
+        act = arng.uniform(-1, 1, size=(n, 7)).astype(np.float32)
+        act[64:128] = act[0:64]
+        obs, rew, done, info = dev.feeding_step_host(act)
+    st = dev.state_get()
+    assert np.all(np.isfinite(st)) and np.all(np.isfinite(obs)) and np.all(np.isfinite(rew))
+    assert np.array_equal(st[0:64], st[64:128])            # bit-exact replication => deterministic ordering
+    assert np.array_equal(obs[0:64], obs[64:128])
+    nb = fb.scene.n_bodies
+    quat = st[:, :nb * 13].reshape(n, nb, 13)[:, :, 3:7]
+    assert np.abs(np.linalg.norm(quat, axis=-1) - 1).max() < 1e-4
+    assert dev.overflow_count() == 0
+    assert obs.shape == (n, 25)
