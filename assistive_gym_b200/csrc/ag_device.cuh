@@ -139,6 +139,7 @@ AG_HDN inline bool gjk_cores(const float* verts, int va0, int nA, int vb0, int n
   f3 v = mul(R, tv3(verts, va0)) + t - tv3(verts, vb0);
   if (dot(v, v) < 1e-20f) v = f3(1.f, 0.f, 0.f);
   bool overlap = false;
+  float lower_bound = 0.f;
   for (int it = 0; it < 32; it++) {
     // support of A in direction -v (A-local: R^T(-v)), support of B in +v
     f3 da = mulT(R, -v);
@@ -151,7 +152,9 @@ AG_HDN inline bool gjk_cores(const float* verts, int va0, int nA, int vb0, int n
     f3 sb = tv3(verts, vb0 + ib);
     f3 w = sa - sb;
     float vv = dot(v, v);
-    if (n > 0 && vv - dot(v, w) <= 1e-6f * vv) break;
+    float vw = dot(v, w);
+    if (n > 0 && vw > 0.f) lower_bound = fmaxf(lower_bound, vw / sqrtf(vv));
+    if (n > 0 && vv - vw <= 1e-6f * vv) break;
     bool dup = false;
     for (int i = 0; i < n; i++) if (IA[i] == ia && IB[i] == ib) dup = true;
     if (dup) break;
@@ -169,21 +172,33 @@ AG_HDN inline bool gjk_cores(const float* verts, int va0, int nA, int vb0, int n
       n = m;
     } else {
       float bestd = 1e30f; int bf = -1; float bl[3] = {0.f, 0.f, 0.f};
+      float bestd_all = 1e30f; int bf_all = 0; float bla[3] = {1.f, 0.f, 0.f};
       bool any_out = false;
       for (int f = 0; f < 4; f++) {
         int i0 = (f == 3) ? 1 : 0, i1 = (f == 0) ? 1 : ((f == 1) ? 2 : 3), i2 = (f == 0) ? 2 : ((f == 1) ? 3 : ((f == 2) ? 1 : 2)), i3 = (f == 0) ? 3 : ((f == 1) ? 1 : ((f == 2) ? 2 : 0));
         f3 a = W[i0], b = W[i1], c = W[i2], d = W[i3];
         f3 nn = cross(b - a, c - a);
         float sp = -dot(a, nn), sd = dot(d - a, nn);
-        bool outside = (sd == 0.f) ? true : (sp * sd < 0.f);
-        if (!outside) continue;
-        any_out = true;
+        // the origin counts as inside this face only if it is CLEARLY on the same side as the
+        // opposite vertex; flat (degenerate) tetrahedra and near-zero heights are treated as outside,
+        // otherwise fp32 rounding can report a false overlap for nearly coplanar support points
+        float nl = sqrtf(dot(nn, nn));
+        float tol_d = 1e-5f * nl * norm(d - a), tol_p = 2e-6f * nl * norm(a);
+        bool inside = (sp * sd > 0.f) && (fabsf(sd) > tol_d) && (fabsf(sp) > tol_p);
         float u, s, r; tri_origin(a, b, c, u, s, r);
         f3 pt = a * u + b * s + c * r;
         float dd = dot(pt, pt);
+        if (dd < bestd_all) { bestd_all = dd; bf_all = f; bla[0] = u; bla[1] = s; bla[2] = r; }
+        if (inside) continue;
+        any_out = true;
         if (dd < bestd) { bestd = dd; bf = f; bl[0] = u; bl[1] = s; bl[2] = r; }
       }
-      if (!any_out) { overlap = true; break; }
+      if (!any_out) {
+        // a positive lower bound on the distance (v.w/|v| of an earlier iteration) proves separation:
+        // then "inside" is a rounding artefact and the closest face is used instead
+        if (lower_bound <= 1e-6f) { overlap = true; break; }
+        bf = bf_all; bl[0] = bla[0]; bl[1] = bla[1]; bl[2] = bla[2];
+      }
       int f = bf;
       int id[3];
       id[0] = (f == 3) ? 1 : 0; id[1] = (f == 0) ? 1 : ((f == 1) ? 2 : 3); id[2] = (f == 0) ? 2 : ((f == 1) ? 3 : ((f == 2) ? 1 : 2));

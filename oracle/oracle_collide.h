@@ -66,6 +66,7 @@ static inline ClosestResult gjk_closest(const V3* A, int nA, const V3* B, int nB
   for (int i = 0; i < nB; i++) scale2 = std::max(scale2, dot(B[i] - A[0], B[i] - A[0]));
   const real eps_abs2 = std::max(real(1e-24), scale2 * real(1e-22));
   int it = 0;
+  real lower_bound = 0;
   for (; it < 64; it++) {
     int ia = 0, ib = 0;
     real best = -dot(v, A[0]);
@@ -74,7 +75,9 @@ static inline ClosestResult gjk_closest(const V3* A, int nA, const V3* B, int nB
     for (int i = 1; i < nB; i++) { real d = dot(v, B[i]); if (d > best) { best = d; ib = i; } }
     V3 w = A[ia] - B[ib];
     real vv = dot(v, v);
-    if (n > 0 && vv - dot(v, w) <= real(1e-12) * vv) break;  // no more progress: v is the closest vector
+    real vw = dot(v, w);
+    if (n > 0 && vw > 0) lower_bound = std::max(lower_bound, vw / std::sqrt(vv));
+    if (n > 0 && vv - vw <= real(1e-12) * vv) break;  // no more progress: v is the closest vector
     bool dup = false;
     for (int i = 0; i < n; i++) if (dot(W[i] - w, W[i] - w) <= eps_abs2) dup = true;
     if (dup) break;
@@ -97,21 +100,33 @@ static inline ClosestResult gjk_closest(const V3* A, int nA, const V3* B, int nB
       static const int F[4][4] = {{0, 1, 2, 3}, {0, 2, 3, 1}, {0, 3, 1, 2}, {1, 3, 2, 0}};
       real bestd = real(1e300);
       int bi = -1; real bl[3] = {0, 0, 0};
+      real bestd_all = real(1e300); int bi_all = 0; real bla[3] = {1, 0, 0};
       bool any_outside = false;
       for (int f = 0; f < 4; f++) {
         V3 a = W[F[f][0]], b = W[F[f][1]], c = W[F[f][2]], d = W[F[f][3]];
         V3 nrm = cross(b - a, c - a);
         real sp = -dot(a, nrm);        // origin side
         real sd = dot(d - a, nrm);     // opposite vertex side
-        bool outside = (sd == 0) ? true : (sp * sd < 0);
-        if (!outside) continue;
-        any_outside = true;
+        // inside only if clearly on the opposite vertex's side (degenerate tetrahedra count as outside)
+        real nl = norm(nrm);
+#ifdef ORACLE_FLOAT
+        real tol_d = real(1e-5) * nl * norm(d - a), tol_p = real(2e-6) * nl * norm(a);
+#else
+        real tol_d = real(1e-11) * nl * norm(d - a), tol_p = real(1e-13) * nl * norm(a);
+#endif
+        bool inside = (sp * sd > 0) && (std::fabs(sd) > tol_d) && (std::fabs(sp) > tol_p);
         real u, t, s; tri_origin(a, b, c, u, t, s);
         V3 p = a * u + b * t + c * s;
         real dd = dot(p, p);
+        if (dd < bestd_all) { bestd_all = dd; bi_all = f; bla[0] = u; bla[1] = t; bla[2] = s; }
+        if (inside) continue;
+        any_outside = true;
         if (dd < bestd) { bestd = dd; bi = f; bl[0] = u; bl[1] = t; bl[2] = s; }
       }
-      if (!any_outside) { out.overlap = true; break; }
+      if (!any_outside) {
+        if (lower_bound <= real(1e-9)) { out.overlap = true; break; }   // provably separated otherwise
+        bi = bi_all; bl[0] = bla[0]; bl[1] = bla[1]; bl[2] = bla[2];
+      }
       V3 tw[3], ta[3], tb[3];
       for (int i = 0; i < 3; i++) { tw[i] = W[F[bi][i]]; ta[i] = SA[F[bi][i]]; tb[i] = SB[F[bi][i]]; }
       int m = 0;
