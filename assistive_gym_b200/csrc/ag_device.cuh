@@ -38,6 +38,11 @@ AG_HD q4 tv4(const float* p, int i) { return q4(AG_LDG(p + 4 * i), AG_LDG(p + 4 
 AG_HD float cf_ld(const float* d, int slot, int f, int N, int e) { return d[((size_t)slot * AG_CF + f) * N + e]; }
 AG_HD void cf_st(float* d, int slot, int f, int N, int e, float v) { d[((size_t)slot * AG_CF + f) * N + e] = v; }
 
+// plane k of collider (local) -> (n, d)
+AG_HD void ld_plane(const float* planes, int k, f3& n, float& d) {
+  n = f3(AG_LDG(planes + 4 * k), AG_LDG(planes + 4 * k + 1), AG_LDG(planes + 4 * k + 2)); d = AG_LDG(planes + 4 * k + 3);
+}
+
 // ------------------------------------------------------------------ K1: forward kinematics
 // One lane per env.  p.i0 != 0: all bodies (reset / after teleports); else only movable bodies.
 AG_HDN inline void fk_body(int e, const SimDev& S, const KP& p) {
@@ -69,8 +74,16 @@ AG_HDN inline void aabb_body(int tid, const SimDev& S, const KP& p) {
   int e = tid % N, i = tid / N;
   int c = AG_LDG((const int*)p.p0 + i);
   int k = AG_LDG(S.col_link + c);
-  if (AG_LDG(S.col_type + c) == 3) {   // half-space: unbounded
-    st3(S.cmin, c, N, e, f3(-1e30f, -1e30f, -1e30f)); st3(S.cmax, c, N, e, f3(1e30f, 1e30f, 1e30f));
+  if (AG_LDG(S.col_type + c) == 3) {   // half-space: unbounded, except along an axis-aligned normal
+    f3 n; float d; ld_plane(S.planes, AG_LDG(S.col_p0 + c), n, d);
+    q4 q = ld4(S.lquat, k, N, e);
+    f3 nw = qrot(q, n);
+    float dw = d + dot(nw, ld3(S.lpos, k, N, e));
+    f3 mn(-1e30f, -1e30f, -1e30f), mx(1e30f, 1e30f, 1e30f);
+    if (nw.x > 0.999999f) mx.x = dw; else if (nw.x < -0.999999f) mn.x = -dw;
+    if (nw.y > 0.999999f) mx.y = dw; else if (nw.y < -0.999999f) mn.y = -dw;
+    if (nw.z > 0.999999f) mx.z = dw; else if (nw.z < -0.999999f) mn.z = -dw;
+    st3(S.cmin, c, N, e, mn); st3(S.cmax, c, N, e, mx);
     return;
   }
   f3 lp = ld3(S.lpos, k, N, e);
@@ -100,131 +113,130 @@ AG_HD bool aabb_ov(f3 amin, f3 amax, f3 bmin, f3 bmax, float m) {
            amin.z > bmax.z + m || bmin.z > amax.z + m);
 }
 
-// closest point on segment / triangle to the origin (barycentric), Ericson RTCD 5.1
-AG_HD void seg_origin(f3 a, f3 b, float& u, float& v) {
-  f3 ab = b - a;
-  float t = -dot(a, ab), den = dot(ab, ab);
-  if (t <= 0.f || den <= 0.f) { u = 1.f; v = 0.f; return; }
-  if (t >= den) { u = 0.f; v = 1.f; return; }
-  v = t / den; u = 1.f - v;
+// closest point on segment / triangle to the origin (barycentric), Ericson RTCD 5.1 — in fp64:
+// the simplex vertices are differences of support points that can be ~1 m apart while the origin is
+// ~1 mm from the simplex; in fp32 the Voronoi-region determinants lose all significance on such thin
+// simplices (measured on B200: 9 % of link-vs-table-edge queries off by up to 2 mm).
+AG_HD void seg_origin(d3 a, d3 b, double& u, double& v) {
+  d3 ab = b - a;
+  double t = -dot(a, ab), den = dot(ab, ab);
+  if (t <= 0.0 || den <= 0.0) { u = 1.0; v = 0.0; return; }
+  if (t >= den) { u = 0.0; v = 1.0; return; }
+  v = t / den; u = 1.0 - v;
 }
-AG_HD void tri_origin(f3 a, f3 b, f3 c, float& u, float& v, float& w) {
-  f3 ab = b - a, ac = c - a;
-  float d1 = -dot(ab, a), d2 = -dot(ac, a);
-  if (d1 <= 0.f && d2 <= 0.f) { u = 1.f; v = 0.f; w = 0.f; return; }
-  float d3 = -dot(ab, b), d4 = -dot(ac, b);
-  if (d3 >= 0.f && d4 <= d3) { u = 0.f; v = 1.f; w = 0.f; return; }
-  float vc = d1 * d4 - d3 * d2;
-  if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { float t = d1 / (d1 - d3); u = 1.f - t; v = t; w = 0.f; return; }
-  float d5 = -dot(ab, c), d6 = -dot(ac, c);
-  if (d6 >= 0.f && d5 <= d6) { u = 0.f; v = 0.f; w = 1.f; return; }
-  float vb = d5 * d2 - d1 * d6;
-  if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { float t = d2 / (d2 - d6); u = 1.f - t; v = 0.f; w = t; return; }
-  float va = d3 * d6 - d5 * d4;
-  if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) { float t = (d4 - d3) / ((d4 - d3) + (d5 - d6)); u = 0.f; v = 1.f - t; w = t; return; }
-  float den = 1.0f / (va + vb + vc);
-  v = vb * den; w = vc * den; u = 1.f - v - w;
+AG_HD void tri_origin(d3 a, d3 b, d3 c, double& u, double& v, double& w) {
+  d3 ab = b - a, ac = c - a;
+  double d1 = -dot(ab, a), d2 = -dot(ac, a);
+  if (d1 <= 0.0 && d2 <= 0.0) { u = 1.0; v = 0.0; w = 0.0; return; }
+  double d3_ = -dot(ab, b), d4 = -dot(ac, b);
+  if (d3_ >= 0.0 && d4 <= d3_) { u = 0.0; v = 1.0; w = 0.0; return; }
+  double vc = d1 * d4 - d3_ * d2;
+  if (vc <= 0.0 && d1 >= 0.0 && d3_ <= 0.0) { double t = d1 / (d1 - d3_); u = 1.0 - t; v = t; w = 0.0; return; }
+  double d5 = -dot(ab, c), d6 = -dot(ac, c);
+  if (d6 >= 0.0 && d5 <= d6) { u = 0.0; v = 0.0; w = 1.0; return; }
+  double vb = d5 * d2 - d1 * d6;
+  if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) { double t = d2 / (d2 - d6); u = 1.0 - t; v = 0.0; w = t; return; }
+  double va = d3_ * d6 - d5 * d4;
+  if (va <= 0.0 && (d4 - d3_) >= 0.0 && (d5 - d6) >= 0.0) { double t = (d4 - d3_) / ((d4 - d3_) + (d5 - d6)); u = 0.0; v = 1.0 - t; w = t; return; }
+  double den = 1.0 / (va + vb + vc);
+  v = vb * den; w = vc * den; u = 1.0 - v - w;
 }
 
 struct NpOut { f3 pa, pb, n; float d; };   // B-local frame: points on the surfaces, normal B->A, surface distance
 
 // GJK closest points between core A (A-local vertices mapped by R,t into B's frame) and core B.
+// Vertices, transforms and the support search are fp32; the simplex solve is fp64.
 // Returns true if the cores overlap.
 AG_HDN inline bool gjk_cores(const float* verts, int va0, int nA, int vb0, int nB, const m3& R, f3 t,
                              f3& pa, f3& pb, f3& nrm, float& dist) {
-  f3 W[4], PA[4], PB[4];
+  d3 W[4]; f3 PA[4], PB[4];
   int IA[4], IB[4];
-  float lam[4] = {1.f, 0.f, 0.f, 0.f};
+  double lam[4] = {1.0, 0.0, 0.0, 0.0};
   int n = 0;
-  f3 v = mul(R, tv3(verts, va0)) + t - tv3(verts, vb0);
-  if (dot(v, v) < 1e-20f) v = f3(1.f, 0.f, 0.f);
+  d3 v = to_d3(mul(R, tv3(verts, va0)) + t) - to_d3(tv3(verts, vb0));
+  if (dot(v, v) < 1e-20) v = d3(1.0, 0.0, 0.0);
   bool overlap = false;
-  float lower_bound = 0.f;
+  double lower_bound = 0.0;
   for (int it = 0; it < 32; it++) {
     // support of A in direction -v (A-local: R^T(-v)), support of B in +v
-    f3 da = mulT(R, -v);
+    f3 vf = to_f3(v);
+    f3 da = mulT(R, -vf);
     int ia = 0, ib = 0;
     float best = dot(da, tv3(verts, va0));
     for (int i = 1; i < nA; i++) { float d = dot(da, tv3(verts, va0 + i)); if (d > best) { best = d; ia = i; } }
-    best = dot(v, tv3(verts, vb0));
-    for (int i = 1; i < nB; i++) { float d = dot(v, tv3(verts, vb0 + i)); if (d > best) { best = d; ib = i; } }
+    best = dot(vf, tv3(verts, vb0));
+    for (int i = 1; i < nB; i++) { float d = dot(vf, tv3(verts, vb0 + i)); if (d > best) { best = d; ib = i; } }
     f3 sa = mul(R, tv3(verts, va0 + ia)) + t;
     f3 sb = tv3(verts, vb0 + ib);
-    f3 w = sa - sb;
-    float vv = dot(v, v);
-    float vw = dot(v, w);
-    if (n > 0 && vw > 0.f) lower_bound = fmaxf(lower_bound, vw / sqrtf(vv));
-    if (n > 0 && vv - vw <= 1e-6f * vv) break;
+    d3 w = to_d3(sa) - to_d3(sb);
+    double vv = dot(v, v);
+    double vw = dot(v, w);
+    if (n > 0 && vw > 0.0) lower_bound = fmax(lower_bound, vw / sqrt(vv));
+    if (n > 0 && vv - vw <= 1e-10 * vv) break;
     bool dup = false;
     for (int i = 0; i < n; i++) if (IA[i] == ia && IB[i] == ib) dup = true;
     if (dup) break;
     W[n] = w; PA[n] = sa; PB[n] = sb; IA[n] = ia; IB[n] = ib; n++;
-    if (n == 1) { lam[0] = 1.f; }
+    if (n == 1) { lam[0] = 1.0; }
     else if (n == 2) {
-      float u, s; seg_origin(W[0], W[1], u, s);
-      if (s <= 0.f) { n = 1; lam[0] = 1.f; }
-      else if (u <= 0.f) { W[0] = W[1]; PA[0] = PA[1]; PB[0] = PB[1]; IA[0] = IA[1]; IB[0] = IB[1]; n = 1; lam[0] = 1.f; }
+      double u, s; seg_origin(W[0], W[1], u, s);
+      if (s <= 0.0) { n = 1; lam[0] = 1.0; }
+      else if (u <= 0.0) { W[0] = W[1]; PA[0] = PA[1]; PB[0] = PB[1]; IA[0] = IA[1]; IB[0] = IB[1]; n = 1; lam[0] = 1.0; }
       else { lam[0] = u; lam[1] = s; }
     } else if (n == 3) {
-      float l3[3]; tri_origin(W[0], W[1], W[2], l3[0], l3[1], l3[2]);
+      double l3[3]; tri_origin(W[0], W[1], W[2], l3[0], l3[1], l3[2]);
       int m = 0;
-      for (int i = 0; i < 3; i++) if (l3[i] > 0.f) { W[m] = W[i]; PA[m] = PA[i]; PB[m] = PB[i]; IA[m] = IA[i]; IB[m] = IB[i]; lam[m] = l3[i]; m++; }
+      for (int i = 0; i < 3; i++) if (l3[i] > 0.0) { W[m] = W[i]; PA[m] = PA[i]; PB[m] = PB[i]; IA[m] = IA[i]; IB[m] = IB[i]; lam[m] = l3[i]; m++; }
       n = m;
     } else {
-      float bestd = 1e30f; int bf = -1; float bl[3] = {0.f, 0.f, 0.f};
-      float bestd_all = 1e30f; int bf_all = 0; float bla[3] = {1.f, 0.f, 0.f};
+      double bestd = 1e300; int bf = -1; double bl[3] = {0.0, 0.0, 0.0};
+      double bestd_all = 1e300; int bf_all = 0; double bla[3] = {1.0, 0.0, 0.0};
       bool any_out = false;
       for (int f = 0; f < 4; f++) {
         int i0 = (f == 3) ? 1 : 0, i1 = (f == 0) ? 1 : ((f == 1) ? 2 : 3), i2 = (f == 0) ? 2 : ((f == 1) ? 3 : ((f == 2) ? 1 : 2)), i3 = (f == 0) ? 3 : ((f == 1) ? 1 : ((f == 2) ? 2 : 0));
-        f3 a = W[i0], b = W[i1], c = W[i2], d = W[i3];
-        f3 nn = cross(b - a, c - a);
-        float sp = -dot(a, nn), sd = dot(d - a, nn);
-        // the origin counts as inside this face only if it is CLEARLY on the same side as the
-        // opposite vertex; flat (degenerate) tetrahedra and near-zero heights are treated as outside,
-        // otherwise fp32 rounding can report a false overlap for nearly coplanar support points
-        float nl = sqrtf(dot(nn, nn));
-        float tol_d = 1e-5f * nl * norm(d - a), tol_p = 2e-6f * nl * norm(a);
-        bool inside = (sp * sd > 0.f) && (fabsf(sd) > tol_d) && (fabsf(sp) > tol_p);
-        float u, s, r; tri_origin(a, b, c, u, s, r);
-        f3 pt = a * u + b * s + c * r;
-        float dd = dot(pt, pt);
+        d3 a = W[i0], b = W[i1], c = W[i2], d = W[i3];
+        d3 nn = cross(b - a, c - a);
+        double sp = -dot(a, nn), sd = dot(d - a, nn);
+        // inside only if CLEARLY on the opposite vertex's side; flat tetrahedra count as outside
+        double nl = sqrt(dot(nn, nn));
+        double tol_d = 1e-9 * nl * sqrt(dot(d - a, d - a)), tol_p = 1e-9 * nl * sqrt(dot(a, a));
+        bool inside = (sp * sd > 0.0) && (fabs(sd) > tol_d) && (fabs(sp) > tol_p);
+        double u, s, r; tri_origin(a, b, c, u, s, r);
+        d3 pt = a * u + b * s + c * r;
+        double dd = dot(pt, pt);
         if (dd < bestd_all) { bestd_all = dd; bf_all = f; bla[0] = u; bla[1] = s; bla[2] = r; }
         if (inside) continue;
         any_out = true;
         if (dd < bestd) { bestd = dd; bf = f; bl[0] = u; bl[1] = s; bl[2] = r; }
       }
       if (!any_out) {
-        // a positive lower bound on the distance (v.w/|v| of an earlier iteration) proves separation:
-        // then "inside" is a rounding artefact and the closest face is used instead
-        if (lower_bound <= 1e-6f) { overlap = true; break; }
+        // a positive lower bound on the distance (v.w/|v| of an earlier iteration) proves separation
+        if (lower_bound <= 1e-7) { overlap = true; break; }
         bf = bf_all; bl[0] = bla[0]; bl[1] = bla[1]; bl[2] = bla[2];
       }
       int f = bf;
       int id[3];
       id[0] = (f == 3) ? 1 : 0; id[1] = (f == 0) ? 1 : ((f == 1) ? 2 : 3); id[2] = (f == 0) ? 2 : ((f == 1) ? 3 : ((f == 2) ? 1 : 2));
-      f3 tw[3], ta[3], tb[3]; int tia[3], tib[3];
+      d3 tw[3]; f3 ta[3], tb[3]; int tia[3], tib[3];
       for (int i = 0; i < 3; i++) { tw[i] = W[id[i]]; ta[i] = PA[id[i]]; tb[i] = PB[id[i]]; tia[i] = IA[id[i]]; tib[i] = IB[id[i]]; }
       int m = 0;
-      for (int i = 0; i < 3; i++) if (bl[i] > 0.f) { W[m] = tw[i]; PA[m] = ta[i]; PB[m] = tb[i]; IA[m] = tia[i]; IB[m] = tib[i]; lam[m] = bl[i]; m++; }
+      for (int i = 0; i < 3; i++) if (bl[i] > 0.0) { W[m] = tw[i]; PA[m] = ta[i]; PB[m] = tb[i]; IA[m] = tia[i]; IB[m] = tib[i]; lam[m] = bl[i]; m++; }
       n = m;
     }
-    f3 nv(0.f, 0.f, 0.f);
-    for (int i = 0; i < n; i++) nv += W[i] * lam[i];
+    d3 nv(0.0, 0.0, 0.0);
+    for (int i = 0; i < n; i++) nv = nv + W[i] * lam[i];
     v = nv;
-    if (dot(v, v) <= 1e-14f) { overlap = true; break; }
+    if (dot(v, v) <= 1e-16) { overlap = true; break; }
   }
   if (overlap) return true;
-  pa = f3(); pb = f3();
-  for (int i = 0; i < n; i++) { pa += PA[i] * lam[i]; pb += PB[i] * lam[i]; }
-  f3 d = pa - pb;
-  dist = norm(d);
-  nrm = dist > 0.f ? d * (1.0f / dist) : f3(0.f, 0.f, 1.f);
+  d3 qa(0.0, 0.0, 0.0), qb(0.0, 0.0, 0.0);
+  for (int i = 0; i < n; i++) { qa = qa + to_d3(PA[i]) * lam[i]; qb = qb + to_d3(PB[i]) * lam[i]; }
+  d3 d = qa - qb;
+  double dn = sqrt(dot(d, d));
+  pa = to_f3(qa); pb = to_f3(qb);
+  dist = (float)dn;
+  nrm = dn > 0.0 ? to_f3(d * (1.0 / dn)) : f3(0.f, 0.f, 1.f);
   return false;
-}
-
-// plane k of collider (local) -> (n, d)
-AG_HD void ld_plane(const float* planes, int k, f3& n, float& d) {
-  n = f3(AG_LDG(planes + 4 * k), AG_LDG(planes + 4 * k + 1), AG_LDG(planes + 4 * k + 2)); d = AG_LDG(planes + 4 * k + 3);
 }
 
 // axis of least penetration over the face normals of both cores (B-local frame)
@@ -304,10 +316,16 @@ AG_HDN inline void face_cands(const SimDev& S, int vv0, int nV, float rV, bool v
   }
 }
 
+// Manifold selection.  The GJK primary point is arbitrary within a flat contact patch (any point of
+// two parallel faces is "closest"), so whenever feature candidates exist the manifold is built from
+// them only: deepest candidate first, then greedily the candidate farthest from the chosen set.
 AG_HDN inline int select_cands(const CandSel& cs, NpOut* out) {
-  int nc = 0; out[nc++] = cs.prim;
+  if (cs.np == 0) { out[0] = cs.prim; return 1; }
   bool used[12];
-  for (int i = 0; i < 12; i++) { used[i] = i >= cs.np; if (!used[i]) { f3 d = cs.pool[i].pa - cs.prim.pa; if (dot(d, d) < 1e-8f) used[i] = true; } }
+  int first = 0;
+  for (int i = 0; i < 12; i++) used[i] = i >= cs.np;
+  for (int i = 1; i < cs.np; i++) if (cs.pool[i].d < cs.pool[first].d) first = i;
+  int nc = 0; out[nc++] = cs.pool[first]; used[first] = true;
   while (nc < 4) {
     int bi = -1; float bd = 1e-8f;
     for (int i = 0; i < cs.np; i++) {
@@ -407,12 +425,13 @@ AG_HDN inline void collide_body(int tid, const SimDev& S, const KP& kp) {
   if (S.body_mode[(size_t)ba * N + e] == 0 || S.body_mode[(size_t)bb * N + e] == 0) return;
   float fac = S.contact_thr;
   f3 lamin = ld3(S.lmin, la, N, e), lamax = ld3(S.lmax, la, N, e), lbmin = ld3(S.lmin, lb, N, e), lbmax = ld3(S.lmax, lb, N, e);
-  if (!aabb_ov(lamin, lamax, lbmin, lbmax, fac * S.max_thresh)) return;
+  float tla = AG_LDG(S.link_thresh + la), tlb = AG_LDG(S.link_thresh + lb);
+  if (!aabb_ov(lamin, lamax, lbmin, lbmax, fac * fminf(tla, tlb))) return;
   int ca0 = AG_LDG(S.link_col0 + la), nca = AG_LDG(S.link_ncol + la), cb0 = AG_LDG(S.link_col0 + lb), ncb = AG_LDG(S.link_ncol + lb);
   for (int ca = ca0; ca < ca0 + nca; ca++) {
     f3 amin = ld3(S.cmin, ca, N, e), amax = ld3(S.cmax, ca, N, e);
     float tha = AG_LDG(S.col_thresh + ca);
-    if (!aabb_ov(amin, amax, lbmin, lbmax, fac * tha)) continue;
+    if (!aabb_ov(amin, amax, lbmin, lbmax, fac * fminf(tha, tlb))) continue;
     for (int cb = cb0; cb < cb0 + ncb; cb++) {
       float thr = fac * fminf(tha, AG_LDG(S.col_thresh + cb));   // size-relative breaking threshold
       if (!aabb_ov(amin, amax, ld3(S.cmin, cb, N, e), ld3(S.cmax, cb, N, e), thr)) continue;

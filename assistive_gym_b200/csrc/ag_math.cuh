@@ -37,6 +37,22 @@ AG_HD f3 fmin3(f3 a, f3 b) { return f3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a
 AG_HD f3 fmax3(f3 a, f3 b) { return f3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
 AG_HD float clampf(float v, float lo, float hi) { return fminf(hi, fmaxf(lo, v)); }
 
+// double-precision 3-vector: used only inside the GJK simplex solve (a handful of flops per
+// iteration), where fp32 cancellation on thin simplices of far-apart support points is fatal
+struct d3 {
+  double x, y, z;
+  AG_HD d3() : x(0.0), y(0.0), z(0.0) {}
+  AG_HD d3(double a, double b, double c) : x(a), y(b), z(c) {}
+};
+AG_HD d3 operator+(d3 a, d3 b) { return d3(a.x + b.x, a.y + b.y, a.z + b.z); }
+AG_HD d3 operator-(d3 a, d3 b) { return d3(a.x - b.x, a.y - b.y, a.z - b.z); }
+AG_HD d3 operator-(d3 a) { return d3(-a.x, -a.y, -a.z); }
+AG_HD d3 operator*(d3 a, double s) { return d3(a.x * s, a.y * s, a.z * s); }
+AG_HD double dot(d3 a, d3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+AG_HD d3 cross(d3 a, d3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+AG_HD d3 to_d3(f3 a) { return d3((double)a.x, (double)a.y, (double)a.z); }
+AG_HD f3 to_f3(d3 a) { return f3((float)a.x, (float)a.y, (float)a.z); }
+
 struct q4 {
   float x, y, z, w;
   AG_HD q4() : x(0.f), y(0.f), z(0.f), w(1.f) {}

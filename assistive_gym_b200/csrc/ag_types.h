@@ -34,7 +34,7 @@ struct SimDev {
   const int *link_body, *link_parent, *link_jtype, *link_dl, *link_haslimit, *link_col0, *link_ncol;
   const float *link_axis, *link_jpos, *link_jquat, *link_com, *link_iquat, *link_inertia, *link_mass, *link_lower, *link_upper;
   const int *col_link, *col_type, *col_v0, *col_nv, *col_p0, *col_np;
-  const float *col_radius, *col_thresh, *col_center, *col_half, *verts, *planes;
+  const float *col_radius, *col_thresh, *link_thresh, *col_center, *col_half, *verts, *planes;
   float max_thresh;
   const int* pair_link;
   const int *movcol, *movlink, *allcol, *alllink;

@@ -54,6 +54,7 @@ struct Scene {
   // derived
   std::vector<int> link_col0, link_ncol;   // colliders are grouped by link
   std::vector<real> subtree_mass;
+  std::vector<real> link_thresh;           // max col_thresh over the link's colliders
   std::vector<int> link_live;              // joint has a live DoF (template level)
   std::vector<int> link_dof;               // index of the DoF within its body (-1)
   std::vector<int> body_ndof;
@@ -140,6 +141,8 @@ void ingest(Scene& s, const AgSceneDesc* d) {
   // derived
   s.link_col0.assign(s.nl, 0); s.link_ncol.assign(s.nl, 0);
   for (int c = s.nc - 1; c >= 0; c--) { s.link_col0[s.col_link[c]] = c; s.link_ncol[s.col_link[c]]++; }
+  s.link_thresh.assign(s.nl, 0);
+  for (int c = 0; c < s.nc; c++) s.link_thresh[s.col_link[c]] = std::max(s.link_thresh[s.col_link[c]], s.col_thresh[c]);
   s.subtree_mass.assign(s.nl, 0);
   for (int k = s.nl - 1; k >= 0; k--) {
     s.subtree_mass[k] += s.link_mass[k];
@@ -213,7 +216,11 @@ void update_colliders(const Scene& s, Env& e) {
       e.wplanes[4 * p + 3] = s.planes[4 * p + 3] + dot(n, e.lpos[k]);
     }
     real r = s.col_radius[c];
-    if (s.col_type[c] == AG_COL_HALFSPACE) { mn = V3(-1e30, -1e30, -1e30); mx = V3(1e30, 1e30, 1e30); }
+    if (s.col_type[c] == AG_COL_HALFSPACE) {
+      mn = V3(-1e30, -1e30, -1e30); mx = V3(1e30, 1e30, 1e30);
+      const real* P = &e.wplanes[4 * s.col_p0[c]];     // axis-aligned half-spaces are bounded on one side
+      for (int a = 0; a < 3; a++) { if (P[a] > real(0.999999)) mx[a] = P[3]; else if (P[a] < real(-0.999999)) mn[a] = -P[3]; }
+    }
     e.cmin[c] = mn - V3(r, r, r); e.cmax[c] = mx + V3(r, r, r);
   }
   for (int k = 0; k < s.nl; k++) {
@@ -253,7 +260,11 @@ void face_candidates(const V3* V, int nV, real rV, const real* P, int nP, real r
     Cand c; c.d = d;
     V3 on_v = V[i] - nf * rV, on_f = proj + nf * rP;
     if (v_is_a) { c.pa = on_v; c.pb = on_f; c.n = nf; } else { c.pa = on_f; c.pb = on_v; c.n = -nf; }
-    out.push_back(c);
+    if (out.size() >= 13) {          // pool of 12 (+ the primary at index 0): replace the shallowest if deeper
+      size_t wi = 1; for (size_t q = 2; q < out.size(); q++) if (out[q].d > out[wi].d) wi = q;
+      if (d >= out[wi].d) continue;
+      out[wi] = c;
+    } else out.push_back(c);
   }
 }
 
@@ -293,20 +304,27 @@ int collide_pair(const Scene& s, const Env& e, int ca, int cb, real max_dist, bo
       if (npA > 0 && nB > 1) face_candidates(B, nB, rb, PA, npA, ra, -r.normal, pr.d, max_dist * real(0.5), max_dist, false, cand);
     }
   }
-  // select up to 4: primary, then greedily the candidate farthest from the chosen set (ties: deeper)
-  int chosen[4]; int nc = 0; chosen[nc++] = 0;
+  // Manifold selection (same rule as the CUDA side): the GJK primary is arbitrary within a flat
+  // contact patch, so when feature candidates exist only they are used: deepest first, then greedily
+  // the candidate farthest from the chosen set.  cand[0] is the primary, cand[1..] the pool.
+  int chosen[4]; int nc = 0;
   std::vector<char> used(cand.size(), 0); used[0] = 1;
-  for (size_t i = 1; i < cand.size(); i++) if (dot(cand[i].pa - cand[0].pa, cand[i].pa - cand[0].pa) < real(1e-8)) used[i] = 1;
-  while (nc < 4) {
-    int bi = -1; real bd = real(1e-8);
-    for (size_t i = 1; i < cand.size(); i++) {
-      if (used[i]) continue;
-      real md = real(1e30);
-      for (int k = 0; k < nc; k++) { V3 dd = cand[i].pa - cand[chosen[k]].pa; md = std::min(md, dot(dd, dd)); }
-      if (md > bd) { bd = md; bi = (int)i; }
+  if (cand.size() == 1) { chosen[nc++] = 0; }
+  else {
+    size_t first = 1;
+    for (size_t i = 2; i < cand.size(); i++) if (cand[i].d < cand[first].d) first = i;
+    chosen[nc++] = (int)first; used[first] = 1;
+    while (nc < 4) {
+      int bi = -1; real bd = real(1e-8);
+      for (size_t i = 1; i < cand.size(); i++) {
+        if (used[i]) continue;
+        real md = real(1e30);
+        for (int k = 0; k < nc; k++) { V3 dd = cand[i].pa - cand[chosen[k]].pa; md = std::min(md, dot(dd, dd)); }
+        if (md > bd) { bd = md; bi = (int)i; }
+      }
+      if (bi < 0) break;
+      used[bi] = 1; chosen[nc++] = bi;
     }
-    if (bi < 0) break;
-    used[bi] = 1; chosen[nc++] = bi;
   }
   for (int k = 0; k < nc; k++) {
     const Cand& c = cand[chosen[k]];
@@ -324,9 +342,9 @@ void detect_contacts(const Scene& s, const AgConfig& cfg, Env& e) {
   for (int p = 0; p < s.npair; p++) {
     int la = s.pair_link[2 * p], lb = s.pair_link[2 * p + 1];
     if (e.body_mode[s.link_body[la]] == 0 || e.body_mode[s.link_body[lb]] == 0) continue;
-    if (!aabb_overlap(e.lmin[la], e.lmax[la], e.lmin[lb], e.lmax[lb], fac * s.max_thresh)) continue;
+    if (!aabb_overlap(e.lmin[la], e.lmax[la], e.lmin[lb], e.lmax[lb], fac * std::min(s.link_thresh[la], s.link_thresh[lb]))) continue;
     for (int ca = s.link_col0[la]; ca < s.link_col0[la] + s.link_ncol[la]; ca++) {
-      if (!aabb_overlap(e.cmin[ca], e.cmax[ca], e.lmin[lb], e.lmax[lb], fac * s.col_thresh[ca])) continue;
+      if (!aabb_overlap(e.cmin[ca], e.cmax[ca], e.lmin[lb], e.lmax[lb], fac * std::min(s.col_thresh[ca], s.link_thresh[lb]))) continue;
       for (int cb = s.link_col0[lb]; cb < s.link_col0[lb] + s.link_ncol[lb]; cb++) {
         real thr = fac * std::min(s.col_thresh[ca], s.col_thresh[cb]);   // size-relative breaking threshold
         if (!aabb_overlap(e.cmin[ca], e.cmax[ca], e.cmin[cb], e.cmax[cb], thr)) continue;
@@ -1026,3 +1044,29 @@ int oracle_gjk(const double* A, int nA, const double* B, int nB, double* pa, dou
 }
 
 }  // extern "C"
+
+// diagnostics: narrowphase work per enabled link pair for one env (number of collider pairs that
+// survive the AABB culls, and the vertex-pair product they represent)
+extern "C" int oracle_debug_pair_work(void* h, int env, int32_t* n_narrow, double* vert_work) {
+  Sim* s = (Sim*)h; const Scene& sc = s->sc; Env& e = s->envs[env];
+  forward_kinematics(sc, e); update_colliders(sc, e);
+  real fac = (real)s->cfg.contact_threshold;
+  for (int p = 0; p < sc.npair; p++) {
+    n_narrow[p] = 0; vert_work[p] = 0;
+    int la = sc.pair_link[2 * p], lb = sc.pair_link[2 * p + 1];
+    if (e.body_mode[sc.link_body[la]] == 0 || e.body_mode[sc.link_body[lb]] == 0) continue;
+    if (!aabb_overlap(e.lmin[la], e.lmax[la], e.lmin[lb], e.lmax[lb], fac * std::min(sc.link_thresh[la], sc.link_thresh[lb]))) continue;
+    n_narrow[p] = -1;   // link-level overlap, maybe no collider pair
+    int cnt = 0;
+    for (int ca = sc.link_col0[la]; ca < sc.link_col0[la] + sc.link_ncol[la]; ca++) {
+      if (!aabb_overlap(e.cmin[ca], e.cmax[ca], e.lmin[lb], e.lmax[lb], fac * sc.col_thresh[ca])) continue;
+      for (int cb = sc.link_col0[lb]; cb < sc.link_col0[lb] + sc.link_ncol[lb]; cb++) {
+        real thr = fac * std::min(sc.col_thresh[ca], sc.col_thresh[cb]);
+        if (!aabb_overlap(e.cmin[ca], e.cmax[ca], e.cmin[cb], e.cmax[cb], thr)) continue;
+        cnt++; vert_work[p] += (double)(sc.col_nv[ca] + sc.col_nv[cb]);
+      }
+    }
+    if (cnt) n_narrow[p] = cnt;
+  }
+  return 0;
+}

@@ -66,3 +66,32 @@ def test_contact_budget_overflow_flag(feeding, make_sim):
     sim = make_sim(feeding.scene, cfg, 2)
     feeding.reset(sim, np.random.default_rng(0), settle_steps=3)
     assert sim.overflow_count() == 2
+
+
+def test_device_gjk_thin_simplex_accuracy(feeding, emu_lib):
+    """Device GJK (fp32 vertices, fp64 simplex solve) vs the double oracle on arm-link-vs-table-edge
+    configurations ~1 mm apart: the fp32-only version was off by up to 2 mm in 9 % of these."""
+    import ctypes as C
+    from assistive_gym_b200.scene import quat_to_mat
+    from oracle.oracle_py import gjk
+    emu_lib.ag_debug_gjk.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    sc = feeding.scene
+
+    def verts_of(link):
+        c = [c for c in range(sc.n_colliders) if sc['col_link'][c] == link][0]
+        return sc['verts'][sc['col_v0'][c]:sc['col_v0'][c] + sc['col_nv'][c]]
+    VA = verts_of(feeding.gl(feeding.robot, 3))
+    VB = verts_of(int(sc['body_link0'][feeding.table])) + np.array([0.25, -1.0, 0.0])
+    rng = np.random.default_rng(0)
+    d_dir = np.array([0, 0.8, -0.6])
+    for _ in range(300):
+        q = rng.normal(size=4)
+        A = VA @ quat_to_mat(q / np.linalg.norm(q)).T
+        A = A - A[np.argmin(A @ d_dir)] + np.array([rng.uniform(-0.6, 0.9), -0.5, 0.675]) + d_dir * rng.uniform(0.0005, 0.003)
+        ov64, pa, pb, d64 = gjk(A, VB)
+        A32, B32 = np.ascontiguousarray(A, dtype=np.float32), np.ascontiguousarray(VB, dtype=np.float32)
+        o = [np.zeros(3, np.float32) for _ in range(3)] + [np.zeros(1, np.float32)]
+        ov = emu_lib.ag_debug_gjk(A32.ctypes.data, len(A32), B32.ctypes.data, len(B32), *[x.ctypes.data for x in o])
+        assert not ov and not ov64
+        assert abs(float(o[3][0]) - d64) < 2e-6
+        assert np.arccos(np.clip(((pa - pb) / d64) @ o[2], -1, 1)) < 2e-3
