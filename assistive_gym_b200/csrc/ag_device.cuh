@@ -838,137 +838,189 @@ AG_HDN inline void crows_body(int tid, const SimDev& S, const KP&) {
 }
 
 // ------------------------------------------------------------------ K7: PGS
-// J.dv of one side
-AG_HD float side_jv(const SimDev& S, int e, int ref, int as, f3 lin, f3 ang_free) {
-  int kind = ref & 3, idx = ref >> 2; const int N = S.N;
+// One env per lane, one warp per block.  Everything the Gauss-Seidel sweep reads AND writes lives in
+// shared memory (`sm`, lane-strided so a warp access is conflict-free): velocity deltas, per-body
+// inverse inertias / COMs, the articulated M^-1, all impulses.  Global memory is only read through
+// the read-only path (row constants written by k_rows / k_crows), so the compiler may hoist those
+// loads across the shared-memory dependency chain.  Layout (floats per lane):
+//   [dv: ND+6nf][fcom: 3nf][fIinv: 6nf][Minv: ND*ND][lam: 3*maxc][dr_lam: 3ND][gr_lam: ngr]
+struct PgsLayout { int o_dv, o_fc, o_fi, o_mi, o_lam, o_dr, o_gr, total; };
+AG_HD PgsLayout pgs_layout(const SimDev& S) {
+  PgsLayout L;
+  L.o_dv = 0; L.o_fc = L.o_dv + S.ND + 6 * S.nf; L.o_fi = L.o_fc + 3 * S.nf; L.o_mi = L.o_fi + 6 * S.nf;
+  L.o_lam = L.o_mi + S.ND * S.ND; L.o_dr = L.o_lam + 3 * S.maxc; L.o_gr = L.o_dr + 3 * S.ND; L.total = L.o_gr + S.ngr;
+  return L;
+}
+#define SMF(i) sm[(size_t)(i) * stride]
+
+AG_HD float pgs_side_jv(const SimDev& S, int e, const float* sm, int stride, const PgsLayout& L, int ref, int as, f3 lin, f3 ang_free) {
+  int kind = ref & 3, idx = ref >> 2;
   if (kind == 1) {
-    int o = S.ND + 6 * idx;
-    f3 dvl(ld1(S.dv, o, N, e), ld1(S.dv, o + 1, N, e), ld1(S.dv, o + 2, N, e));
-    f3 dva(ld1(S.dv, o + 3, N, e), ld1(S.dv, o + 4, N, e), ld1(S.dv, o + 5, N, e));
-    return dot(lin, dvl) + dot(ang_free, dva);
+    int o = L.o_dv + S.ND + 6 * idx;
+    return lin.x * SMF(o) + lin.y * SMF(o + 1) + lin.z * SMF(o + 2) + ang_free.x * SMF(o + 3) + ang_free.y * SMF(o + 4) + ang_free.z * SMF(o + 5);
   } else if (kind == 2) {
     int a = AG_LDG(S.dl_art + idx), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
     float t = 0.f;
-    for (int i = 0; i < nd; i++) t += S.as_J[((size_t)as * AG_MAXND + i) * N + e] * ld1(S.dv, d0 + i, N, e);
+    const float* J = S.as_J + (size_t)as * AG_MAXND * S.N + e;
+    for (int i = 0; i < nd; i++) t += AG_LDG(J + (size_t)i * S.N) * SMF(L.o_dv + d0 + i);
     return t;
   }
   return 0.f;
 }
-AG_HD void side_apply(const SimDev& S, int e, int ref, int as, f3 lin, f3 ang_free, float dl) {
-  int kind = ref & 3, idx = ref >> 2; const int N = S.N;
+AG_HD void pgs_side_apply(const SimDev& S, int e, float* sm, int stride, const PgsLayout& L, int ref, int as, f3 lin, f3 ang_free, float dl) {
+  int kind = ref & 3, idx = ref >> 2;
   if (kind == 1) {
-    int o = S.ND + 6 * idx;
-    int b = AG_LDG(S.free_body + idx);
-    float invm = 1.0f / AG_LDG(S.link_mass + AG_LDG(S.body_link0 + b));
-    f3 ia = mul(ld_Iinv(S, idx, e), ang_free);
-    S.dv[(size_t)o * N + e] += lin.x * invm * dl; S.dv[(size_t)(o + 1) * N + e] += lin.y * invm * dl; S.dv[(size_t)(o + 2) * N + e] += lin.z * invm * dl;
-    S.dv[(size_t)(o + 3) * N + e] += ia.x * dl; S.dv[(size_t)(o + 4) * N + e] += ia.y * dl; S.dv[(size_t)(o + 5) * N + e] += ia.z * dl;
+    int o = L.o_dv + S.ND + 6 * idx;
+    float invm = AG_LDG(S.free_invm + idx) * dl;
+    int fi = L.o_fi + 6 * idx;
+    s3 Ii; Ii.xx = SMF(fi); Ii.yy = SMF(fi + 1); Ii.zz = SMF(fi + 2); Ii.xy = SMF(fi + 3); Ii.xz = SMF(fi + 4); Ii.yz = SMF(fi + 5);
+    f3 ia = mul(Ii, ang_free);
+    SMF(o) += lin.x * invm; SMF(o + 1) += lin.y * invm; SMF(o + 2) += lin.z * invm;
+    SMF(o + 3) += ia.x * dl; SMF(o + 4) += ia.y * dl; SMF(o + 5) += ia.z * dl;
   } else if (kind == 2) {
     int a = AG_LDG(S.dl_art + idx), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
-    for (int i = 0; i < nd; i++) S.dv[(size_t)(d0 + i) * N + e] += S.as_MiJ[((size_t)as * AG_MAXND + i) * N + e] * dl;
+    const float* M = S.as_MiJ + (size_t)as * AG_MAXND * S.N + e;
+    for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += AG_LDG(M + (size_t)i * S.N) * dl;
   }
+}
+AG_HD f3 pgs_rel(const float* sm, int stride, const PgsLayout& L, int ref, f3 p) {   // p - com of a free side
+  if ((ref & 3) != 1) return f3();
+  int o = L.o_fc + 3 * (ref >> 2);
+  return f3(p.x - SMF(o), p.y - SMF(o + 1), p.z - SMF(o + 2));
 }
 
-AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&) {
+AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm, int stride) {
   const int N = S.N;
   const int ND = S.ND;
-  int nvel = ND + 6 * S.nf;
-  for (int i = 0; i < nvel; i++) S.dv[(size_t)i * N + e] = 0.f;
+  const PgsLayout L = pgs_layout(S);
+  const int nvel = ND + 6 * S.nf;
+  // ---- stage per-env solver state into shared memory
+  for (int i = 0; i < nvel; i++) SMF(L.o_dv + i) = 0.f;
+  for (int i = 0; i < 3 * S.nf; i++) SMF(L.o_fc + i) = S.fcom[(size_t)i * N + e];
+  for (int i = 0; i < 6 * S.nf; i++) SMF(L.o_fi + i) = S.fIinv[(size_t)i * N + e];
+  for (int i = 0; i < ND * ND; i++) SMF(L.o_mi + i) = S.Minv[(size_t)i * N + e];
   int cnt = S.c_count[e]; if (cnt > S.maxc) cnt = S.maxc;
+  for (int i = 0; i < 3 * cnt; i++) SMF(L.o_lam + i) = 0.f;
+  for (int i = 0; i < 3 * ND; i++) SMF(L.o_dr + i) = 0.f;
+  for (int i = 0; i < S.ngr; i++) SMF(L.o_gr + i) = 0.f;
+  const float* sd = S.s_data;
   int used = 0;
+  bool done = false;
+#if defined(__CUDA_ARCH__)
+  const unsigned wmask = __activemask();
+#endif
   for (int it = 0; it < S.iters; it++) {
-    float resid = 0.f;
-    used = it + 1;
-    // joint limits (lower, upper) then motors
-    for (int r = 0; r < 3 * ND; r++) {
-      float dinv = ld1(S.dr_dinv, r, N, e);
-      if (dinv == 0.f) continue;
-      int d = r % ND; int kindr = r / ND;
-      float sgn = kindr == 1 ? -1.f : 1.f;
-      float lam = ld1(S.dr_lam, r, N, e);
-      float dl = ld1(S.dr_rhs, r, N, e) - sgn * ld1(S.dv, d, N, e) * dinv;
-      float lo, hi;
-      if (kindr == 2) { hi = S.motor_maxf[AG_LDG(S.dl_link + d)] * S.dt; lo = -hi; } else { lo = 0.f; hi = 1e30f; }
-      float sum = lam + dl;
-      if (sum < lo) { dl = lo - lam; sum = lo; } else if (sum > hi) { dl = hi - lam; sum = hi; }
-      st1(S.dr_lam, r, N, e, sum);
-      // dv += Minv[:, d] * sgn * dl (within the articulation of d)
-      int a = AG_LDG(S.dl_art + d), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
-      for (int i = 0; i < nd; i++) S.dv[(size_t)(d0 + i) * N + e] += S.Minv[((size_t)(d0 + i) * ND + d) * N + e] * (sgn * dl);
-      resid = fmaxf(resid, dl * dl);
+    if (!done) {
+      float resid = 0.f;
+      used = it + 1;
+      // joint limits (lower, upper) then motors: J = +-e_d
+      for (int r = 0; r < 3 * ND; r++) {
+        float dinv = AG_LDG(S.dr_dinv + (size_t)r * N + e);
+        if (dinv == 0.f) continue;
+        int d = r % ND; int kindr = r / ND;
+        float sgn = kindr == 1 ? -1.f : 1.f;
+        float lam = SMF(L.o_dr + r);
+        float dl = AG_LDG(S.dr_rhs + (size_t)r * N + e) - sgn * SMF(L.o_dv + d) * dinv;
+        float lo, hi;
+        if (kindr == 2) { hi = S.motor_maxf[AG_LDG(S.dl_link + d)] * S.dt; lo = -hi; } else { lo = 0.f; hi = 1e30f; }
+        float sum = lam + dl;
+        if (sum < lo) { dl = lo - lam; sum = lo; } else if (sum > hi) { dl = hi - lam; sum = hi; }
+        SMF(L.o_dr + r) = sum;
+        int a = AG_LDG(S.dl_art + d), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
+        float sdl = sgn * dl;
+        for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += SMF(L.o_mi + (d0 + i) * ND + d) * sdl;
+        resid = fmaxf(resid, dl * dl);
+      }
+      // fixed constraints
+      for (int r = 0; r < S.ngr; r++) {
+        const float* g = S.gr_data + (size_t)r * 16 * N + e;
+        float dinv = AG_LDG(g + (size_t)GR_DINV * N);
+        if (dinv == 0.f) continue;
+        const int* rf = S.gr_ref + (size_t)r * 4 * N + e;
+        int refA = AG_LDG(rf), refB = AG_LDG(rf + N), asA = AG_LDG(rf + 2 * (size_t)N), asB = AG_LDG(rf + 3 * (size_t)N);
+        f3 lin(AG_LDG(g + (size_t)GR_LX * N), AG_LDG(g + (size_t)GR_LY * N), AG_LDG(g + (size_t)GR_LZ * N));
+        f3 aA(AG_LDG(g + (size_t)GR_AAX * N), AG_LDG(g + (size_t)GR_AAY * N), AG_LDG(g + (size_t)GR_AAZ * N));
+        f3 aB(AG_LDG(g + (size_t)GR_ABX * N), AG_LDG(g + (size_t)GR_ABY * N), AG_LDG(g + (size_t)GR_ABZ * N));
+        float jv = pgs_side_jv(S, e, sm, stride, L, refA, asA, lin, aA) + pgs_side_jv(S, e, sm, stride, L, refB, asB, -lin, -aB);
+        float lam = SMF(L.o_gr + r);
+        float dl = AG_LDG(g + (size_t)GR_RHS * N) - jv * dinv;
+        float lo = AG_LDG(g + (size_t)GR_LO * N), hi = AG_LDG(g + (size_t)GR_HI * N);
+        float sum = lam + dl;
+        if (sum < lo) { dl = lo - lam; sum = lo; } else if (sum > hi) { dl = hi - lam; sum = hi; }
+        SMF(L.o_gr + r) = sum;
+        pgs_side_apply(S, e, sm, stride, L, refA, asA, lin, aA, dl); pgs_side_apply(S, e, sm, stride, L, refB, asB, -lin, -aB, dl);
+        resid = fmaxf(resid, dl * dl);
+      }
+      // contact normals
+      for (int s = 0; s < cnt; s++) {
+        const float* c = sd + (size_t)s * AG_CF * N + e;
+        float dinv = AG_LDG(c + (size_t)CF_DINV_N * N);
+        if (dinv == 0.f) continue;
+        const int* rf = S.s_ref + (size_t)s * 4 * N + e;
+        int refA = AG_LDG(rf), refB = AG_LDG(rf + N), asA = AG_LDG(rf + 2 * (size_t)N), asB = AG_LDG(rf + 3 * (size_t)N);
+        f3 n(AG_LDG(c + (size_t)CF_NX * N), AG_LDG(c + (size_t)CF_NY * N), AG_LDG(c + (size_t)CF_NZ * N));
+        f3 pa(AG_LDG(c + (size_t)CF_PAX * N), AG_LDG(c + (size_t)CF_PAY * N), AG_LDG(c + (size_t)CF_PAZ * N));
+        f3 pb(AG_LDG(c + (size_t)CF_PBX * N), AG_LDG(c + (size_t)CF_PBY * N), AG_LDG(c + (size_t)CF_PBZ * N));
+        f3 aA = cross(pgs_rel(sm, stride, L, refA, pa), n), aB = cross(pgs_rel(sm, stride, L, refB, pb), n);
+        float jv = pgs_side_jv(S, e, sm, stride, L, refA, asA, n, aA) + pgs_side_jv(S, e, sm, stride, L, refB, asB, -n, -aB);
+        float lam = SMF(L.o_lam + 3 * s);
+        float dl = AG_LDG(c + (size_t)CF_RHS_N * N) - jv * dinv;
+        float sum = lam + dl;
+        if (sum < 0.f) { dl = -lam; sum = 0.f; }
+        SMF(L.o_lam + 3 * s) = sum;
+        pgs_side_apply(S, e, sm, stride, L, refA, asA, n, aA, dl); pgs_side_apply(S, e, sm, stride, L, refB, asB, -n, -aB, dl);
+        resid = fmaxf(resid, dl * dl);
+      }
+      // friction (two directions per contact, cone or pyramid)
+      for (int s = 0; s < cnt; s++) {
+        const float* c = sd + (size_t)s * AG_CF * N + e;
+        if (AG_LDG(c + (size_t)CF_DINV_N * N) == 0.f) continue;
+        float l1 = SMF(L.o_lam + 3 * s + 1), l2 = SMF(L.o_lam + 3 * s + 2);
+        float lim = AG_LDG(c + (size_t)CF_MU * N) * SMF(L.o_lam + 3 * s);
+        if (lim <= 0.f && l1 == 0.f && l2 == 0.f) continue;
+        float dinv1 = AG_LDG(c + (size_t)CF_DINV_T1 * N), dinv2 = AG_LDG(c + (size_t)CF_DINV_T2 * N);
+        const int* rf = S.s_ref + (size_t)s * 4 * N + e;
+        int refA = AG_LDG(rf), refB = AG_LDG(rf + N), asA = AG_LDG(rf + 2 * (size_t)N), asB = AG_LDG(rf + 3 * (size_t)N);
+        f3 n(AG_LDG(c + (size_t)CF_NX * N), AG_LDG(c + (size_t)CF_NY * N), AG_LDG(c + (size_t)CF_NZ * N));
+        f3 pa(AG_LDG(c + (size_t)CF_PAX * N), AG_LDG(c + (size_t)CF_PAY * N), AG_LDG(c + (size_t)CF_PAZ * N));
+        f3 pb(AG_LDG(c + (size_t)CF_PBX * N), AG_LDG(c + (size_t)CF_PBY * N), AG_LDG(c + (size_t)CF_PBZ * N));
+        f3 t1, t2; plane_space(n, t1, t2);
+        f3 rA = pgs_rel(sm, stride, L, refA, pa), rB = pgs_rel(sm, stride, L, refB, pb);
+        f3 a1A = cross(rA, t1), a1B = cross(rB, t1), a2A = cross(rA, t2), a2B = cross(rB, t2);
+        float jv1 = pgs_side_jv(S, e, sm, stride, L, refA, asA + 1, t1, a1A) + pgs_side_jv(S, e, sm, stride, L, refB, asB + 1, -t1, -a1B);
+        float jv2 = pgs_side_jv(S, e, sm, stride, L, refA, asA + 2, t2, a2A) + pgs_side_jv(S, e, sm, stride, L, refB, asB + 2, -t2, -a2B);
+        float s1 = l1 + AG_LDG(c + (size_t)CF_RHS_T1 * N) - jv1 * dinv1;
+        float s2 = l2 + AG_LDG(c + (size_t)CF_RHS_T2 * N) - jv2 * dinv2;
+        if (S.cone) {
+          float m2 = s1 * s1 + s2 * s2;
+          if (m2 > lim * lim) { float k = lim / sqrtf(m2); s1 *= k; s2 *= k; }
+        } else { s1 = clampf(s1, -lim, lim); s2 = clampf(s2, -lim, lim); }
+        float d1 = s1 - l1, d2 = s2 - l2;
+        SMF(L.o_lam + 3 * s + 1) = s1; SMF(L.o_lam + 3 * s + 2) = s2;
+        pgs_side_apply(S, e, sm, stride, L, refA, asA + 1, t1, a1A, d1); pgs_side_apply(S, e, sm, stride, L, refB, asB + 1, -t1, -a1B, d1);
+        pgs_side_apply(S, e, sm, stride, L, refA, asA + 2, t2, a2A, d2); pgs_side_apply(S, e, sm, stride, L, refB, asB + 2, -t2, -a2B, d2);
+        resid = fmaxf(resid, fmaxf(d1 * d1, d2 * d2));
+      }
+      if (S.resid_thr > 0.f && resid <= S.resid_thr) done = true;
     }
-    // fixed constraints
-    for (int r = 0; r < S.ngr; r++) {
-      size_t gb = (size_t)r * 16 * N + e;
-      float dinv = S.gr_data[gb + (size_t)GR_DINV * N];
-      if (dinv == 0.f) continue;
-      size_t rb = (size_t)r * 4 * N + e;
-      int refA = S.gr_ref[rb], refB = S.gr_ref[rb + N], asA = S.gr_ref[rb + 2 * (size_t)N], asB = S.gr_ref[rb + 3 * (size_t)N];
-      f3 lin(S.gr_data[gb + (size_t)GR_LX * N], S.gr_data[gb + (size_t)GR_LY * N], S.gr_data[gb + (size_t)GR_LZ * N]);
-      f3 aA(S.gr_data[gb + (size_t)GR_AAX * N], S.gr_data[gb + (size_t)GR_AAY * N], S.gr_data[gb + (size_t)GR_AAZ * N]);
-      f3 aB(S.gr_data[gb + (size_t)GR_ABX * N], S.gr_data[gb + (size_t)GR_ABY * N], S.gr_data[gb + (size_t)GR_ABZ * N]);
-      float jv = side_jv(S, e, refA, asA, lin, aA) + side_jv(S, e, refB, asB, -lin, -aB);
-      float lam = S.gr_data[gb + (size_t)GR_LAM * N];
-      float dl = S.gr_data[gb + (size_t)GR_RHS * N] - jv * dinv;
-      float lo = S.gr_data[gb + (size_t)GR_LO * N], hi = S.gr_data[gb + (size_t)GR_HI * N];
-      float sum = lam + dl;
-      if (sum < lo) { dl = lo - lam; sum = lo; } else if (sum > hi) { dl = hi - lam; sum = hi; }
-      S.gr_data[gb + (size_t)GR_LAM * N] = sum;
-      side_apply(S, e, refA, asA, lin, aA, dl); side_apply(S, e, refB, asB, -lin, -aB, dl);
-      resid = fmaxf(resid, dl * dl);
-    }
-    // contact normals
-    for (int s = 0; s < cnt; s++) {
-      float dinv = cf_ld(S.s_data, s, CF_DINV_N, N, e);
-      if (dinv == 0.f) continue;
-      size_t rb = (size_t)s * 4 * N + e;
-      int refA = S.s_ref[rb], refB = S.s_ref[rb + N], asA = S.s_ref[rb + 2 * (size_t)N], asB = S.s_ref[rb + 3 * (size_t)N];
-      f3 n(cf_ld(S.s_data, s, CF_NX, N, e), cf_ld(S.s_data, s, CF_NY, N, e), cf_ld(S.s_data, s, CF_NZ, N, e));
-      f3 aA, aB;
-      if ((refA & 3) == 1) aA = cross(f3(cf_ld(S.s_data, s, CF_PAX, N, e), cf_ld(S.s_data, s, CF_PAY, N, e), cf_ld(S.s_data, s, CF_PAZ, N, e)) - ld3(S.fcom, refA >> 2, N, e), n);
-      if ((refB & 3) == 1) aB = cross(f3(cf_ld(S.s_data, s, CF_PBX, N, e), cf_ld(S.s_data, s, CF_PBY, N, e), cf_ld(S.s_data, s, CF_PBZ, N, e)) - ld3(S.fcom, refB >> 2, N, e), n);
-      float jv = side_jv(S, e, refA, asA, n, aA) + side_jv(S, e, refB, asB, -n, -aB);
-      float lam = cf_ld(S.s_data, s, CF_LAM_N, N, e);
-      float dl = cf_ld(S.s_data, s, CF_RHS_N, N, e) - jv * dinv;
-      float sum = lam + dl;
-      if (sum < 0.f) { dl = -lam; sum = 0.f; }
-      cf_st(S.s_data, s, CF_LAM_N, N, e, sum);
-      side_apply(S, e, refA, asA, n, aA, dl); side_apply(S, e, refB, asB, -n, -aB, dl);
-      resid = fmaxf(resid, dl * dl);
-    }
-    // friction (two directions per contact, cone or pyramid)
-    for (int s = 0; s < cnt; s++) {
-      float dinv1 = cf_ld(S.s_data, s, CF_DINV_T1, N, e), dinv2 = cf_ld(S.s_data, s, CF_DINV_T2, N, e);
-      if (cf_ld(S.s_data, s, CF_DINV_N, N, e) == 0.f) continue;
-      float l1 = cf_ld(S.s_data, s, CF_LAM_T1, N, e), l2 = cf_ld(S.s_data, s, CF_LAM_T2, N, e);
-      float lim = cf_ld(S.s_data, s, CF_MU, N, e) * cf_ld(S.s_data, s, CF_LAM_N, N, e);
-      if (lim <= 0.f && l1 == 0.f && l2 == 0.f) continue;
-      size_t rb = (size_t)s * 4 * N + e;
-      int refA = S.s_ref[rb], refB = S.s_ref[rb + N], asA = S.s_ref[rb + 2 * (size_t)N], asB = S.s_ref[rb + 3 * (size_t)N];
-      f3 n(cf_ld(S.s_data, s, CF_NX, N, e), cf_ld(S.s_data, s, CF_NY, N, e), cf_ld(S.s_data, s, CF_NZ, N, e));
-      f3 t1, t2; plane_space(n, t1, t2);
-      f3 rA, rB;
-      if ((refA & 3) == 1) rA = f3(cf_ld(S.s_data, s, CF_PAX, N, e), cf_ld(S.s_data, s, CF_PAY, N, e), cf_ld(S.s_data, s, CF_PAZ, N, e)) - ld3(S.fcom, refA >> 2, N, e);
-      if ((refB & 3) == 1) rB = f3(cf_ld(S.s_data, s, CF_PBX, N, e), cf_ld(S.s_data, s, CF_PBY, N, e), cf_ld(S.s_data, s, CF_PBZ, N, e)) - ld3(S.fcom, refB >> 2, N, e);
-      f3 a1A = cross(rA, t1), a1B = cross(rB, t1), a2A = cross(rA, t2), a2B = cross(rB, t2);
-      float jv1 = side_jv(S, e, refA, asA + 1, t1, a1A) + side_jv(S, e, refB, asB + 1, -t1, -a1B);
-      float jv2 = side_jv(S, e, refA, asA + 2, t2, a2A) + side_jv(S, e, refB, asB + 2, -t2, -a2B);
-      float s1 = l1 + cf_ld(S.s_data, s, CF_RHS_T1, N, e) - jv1 * dinv1;
-      float s2 = l2 + cf_ld(S.s_data, s, CF_RHS_T2, N, e) - jv2 * dinv2;
-      if (S.cone) {
-        float m2 = s1 * s1 + s2 * s2;
-        if (m2 > lim * lim) { float k = lim / sqrtf(m2); s1 *= k; s2 *= k; }
-      } else { s1 = clampf(s1, -lim, lim); s2 = clampf(s2, -lim, lim); }
-      float d1 = s1 - l1, d2 = s2 - l2;
-      cf_st(S.s_data, s, CF_LAM_T1, N, e, s1); cf_st(S.s_data, s, CF_LAM_T2, N, e, s2);
-      side_apply(S, e, refA, asA + 1, t1, a1A, d1); side_apply(S, e, refB, asB + 1, -t1, -a1B, d1);
-      side_apply(S, e, refA, asA + 2, t2, a2A, d2); side_apply(S, e, refB, asB + 2, -t2, -a2B, d2);
-      resid = fmaxf(resid, fmaxf(d1 * d1, d2 * d2));
-    }
-    if (S.resid_thr > 0.f && resid <= S.resid_thr) break;
+#if defined(__CUDA_ARCH__)
+    if (__all_sync(wmask, done)) break;     // the warp leaves the loop when every env has converged
+#else
+    if (done) break;
+#endif
   }
+  // ---- write back
   S.iters_used[e] = used;
+  for (int i = 0; i < nvel; i++) S.dv[(size_t)i * N + e] = SMF(L.o_dv + i);
+  for (int r = 0; r < 3 * ND; r++) S.dr_lam[(size_t)r * N + e] = SMF(L.o_dr + r);
+  for (int r = 0; r < S.ngr; r++) S.gr_data[((size_t)r * 16 + GR_LAM) * N + e] = SMF(L.o_gr + r);
+  for (int s = 0; s < cnt; s++) {
+    cf_st(S.s_data, s, CF_LAM_N, N, e, SMF(L.o_lam + 3 * s));
+    cf_st(S.s_data, s, CF_LAM_T1, N, e, SMF(L.o_lam + 3 * s + 1));
+    cf_st(S.s_data, s, CF_LAM_T2, N, e, SMF(L.o_lam + 3 * s + 2));
+  }
 }
+#undef SMF
 
 // ------------------------------------------------------------------ K8: apply deltas, integrate
 AG_HDN inline void integrate_body(int e, const SimDev& S, const KP&) {

@@ -39,7 +39,7 @@ struct SimDev {
   const int* pair_link;
   const int *movcol, *movlink, *allcol, *alllink;
   const int* con_link; const float *con_pivot, *con_quat, *con_maxforce;
-  const int* free_body;
+  const int* free_body; const float* free_invm;
   const int *art_body, *art_dl0, *art_nd;
   const int *dl_link, *dl_parent, *dl_type, *dl_art, *dl_part0, *dl_nparts;
   const float *dl_mass, *dl_mc, *dl_J, *dl_damping;

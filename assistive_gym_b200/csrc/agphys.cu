@@ -43,7 +43,19 @@ AG_KERNEL(k_sort, sort_body)
 AG_KERNEL(k_dyn, dyn_body)
 AG_KERNEL(k_rows, rows_body)
 AG_KERNEL(k_crows, crows_body)
-AG_KERNEL(k_pgs, pgs_body)
+// k_pgs: one warp per block, lane-strided dynamic shared memory (see pgs_body)
+#ifndef AG_CPU_EMU
+__global__ void __launch_bounds__(32) k_pgs(SimDev S, KP p) {
+  extern __shared__ float pgs_smem[];
+  int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid < p.n) pgs_body(tid, S, p, pgs_smem + threadIdx.x, blockDim.x);
+}
+#else
+static void k_pgs(SimDev S, KP p) {
+  std::vector<float> buf((size_t)pgs_layout(S).total);
+  for (int tid = 0; tid < p.n; tid++) pgs_body(tid, S, p, buf.data(), 1);
+}
+#endif
 AG_KERNEL(k_integrate, integrate_body)
 AG_KERNEL(k_gather, gather_body)
 AG_KERNEL(k_scatter, scatter_body)
@@ -341,6 +353,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   S.con_link = upload(s, i32(d->con_link, 2 * (size_t)S.ncon)); S.con_pivot = upload(s, f32(d->con_pivot, 6 * (size_t)S.ncon));
   S.con_quat = upload(s, f32(d->con_quat, 8 * (size_t)S.ncon)); S.con_maxforce = upload(s, f32(d->con_maxforce, S.ncon));
   S.free_body = upload(s, free_body);
+  { std::vector<float> im(free_body.size()); for (size_t f = 0; f < free_body.size(); f++) im[f] = (float)(1.0 / d->link_mass[d->body_link0[free_body[f]]]); S.free_invm = upload(s, im); }
   S.art_body = upload(s, art_body); S.art_dl0 = upload(s, art_dl0); S.art_nd = upload(s, art_nd);
   S.dl_link = upload(s, dl_link); S.dl_parent = upload(s, dl_parent); S.dl_type = upload(s, dl_type); S.dl_art = upload(s, dl_art);
   S.dl_part0 = upload(s, dl_part0); S.dl_nparts = upload(s, dl_nparts);
@@ -370,6 +383,13 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   S.gr_data = dalloc<float>(s, (size_t)S.ngr * 16 * N); S.gr_ref = dalloc<int>(s, (size_t)S.ngr * 4 * N);
   s->d_mask = dalloc<int>(s, N); s->d_links = dalloc<int>(s, 1024); s->d_icount = dalloc<int>(s, N);
   if (!S.gr_ref || !S.as_MiJ || !S.s_data) { g_err = "device allocation failed"; ag_destroy(s); return nullptr; }
+#ifndef AG_CPU_EMU
+  {
+    size_t smem = (size_t)pgs_layout(S).total * 32 * sizeof(float);
+    if (smem > 227 * 1024) { g_err = "PGS shared-memory footprint exceeds 227 KB per CTA: lower max_contacts"; ag_destroy(s); return nullptr; }
+    if (cudaFuncSetAttribute(k_pgs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { g_err = "cudaFuncSetAttribute(k_pgs) failed"; ag_destroy(s); return nullptr; }
+  }
+#endif
   // defaults: friction from the template, all bodies active, identity quaternions
   {
     std::vector<float> fr((size_t)nl * N);
@@ -544,7 +564,19 @@ static void substep(AgSim* s) {
   LAUNCH(s, k_dyn, N, z);
   LAUNCH(s, k_rows, N, z);
   LAUNCH(s, k_crows, (size_t)S.maxc * N, z);
+#ifndef AG_CPU_EMU
+  {
+    KP kp = z; kp.n = N;
+    size_t smem = (size_t)pgs_layout(S).total * 32 * sizeof(float);
+    int ps = s->profiling ? prof_slot(s, "k_pgs") : -1;
+    if (ps >= 0) prof_mark(s, ps, true);
+    k_pgs<<<(N + 31) / 32, 32, smem, s->stream>>>(S, kp);
+    if (ps >= 0) prof_mark(s, ps, false);
+    s->launches++;
+  }
+#else
   LAUNCH(s, k_pgs, N, z);
+#endif
   LAUNCH(s, k_integrate, N, z);
 }
 
