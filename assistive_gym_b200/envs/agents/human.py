@@ -1,0 +1,42 @@
+"""`Human` — joint / link index tables of the capsule person (reference envs/agents/human.py:5-58)."""
+import numpy as np
+
+from .agent import Agent
+
+right_arm_joints = list(range(0, 10))
+left_arm_joints = list(range(10, 20))
+head_joints = [20, 21, 22, 23]
+right_leg_joints = list(range(28, 35))
+left_leg_joints = list(range(35, 42))
+
+
+class Human(Agent):
+    # limb (link) indices, human.py:17-35
+    right_pecs, right_shoulder, right_elbow, right_wrist = 2, 5, 7, 9
+    left_pecs, left_shoulder, left_elbow, left_wrist = 12, 15, 17, 19
+    neck, head, stomach, waist = 20, 23, 24, 27
+    right_hip, right_knee, right_ankle, left_hip, left_knee, left_ankle = 30, 31, 34, 37, 38, 41
+    # joint indices, human.py:37-55
+    j_right_pecs_x, j_right_pecs_y, j_right_pecs_z = 0, 1, 2
+    j_right_shoulder_x, j_right_shoulder_y, j_right_shoulder_z = 3, 4, 5
+    j_right_elbow, j_right_forearm, j_right_wrist_x, j_right_wrist_y = 6, 7, 8, 9
+    j_left_pecs_x, j_left_pecs_y, j_left_pecs_z = 10, 11, 12
+    j_left_shoulder_x, j_left_shoulder_y, j_left_shoulder_z = 13, 14, 15
+    j_left_elbow, j_left_forearm, j_left_wrist_x, j_left_wrist_y = 16, 17, 18, 19
+    j_neck, j_head_x, j_head_y, j_head_z = 20, 21, 22, 23
+    j_waist_x, j_waist_y, j_waist_z = 25, 26, 27
+    j_right_hip_x, j_right_hip_y, j_right_hip_z, j_right_knee = 28, 29, 30, 31
+    j_right_ankle_x, j_right_ankle_y, j_right_ankle_z = 32, 33, 34
+    j_left_hip_x, j_left_hip_y, j_left_hip_z, j_left_knee = 35, 36, 37, 38
+    j_left_ankle_x, j_left_ankle_y, j_left_ankle_z = 39, 40, 41
+
+    def __init__(self, controllable_joint_indices, controllable=False):
+        super().__init__()
+        self.controllable_joint_indices = controllable_joint_indices
+        self.controllable = controllable
+        self.right_arm_joints, self.left_arm_joints, self.head_joints = right_arm_joints, left_arm_joints, head_joints
+        self.right_leg_joints, self.left_leg_joints = right_leg_joints, left_leg_joints
+        self.impairment, self.limit_scale, self.strength = 'none', 1.0, 1.0
+        self.tremors = np.zeros(10)
+        self.motor_forces, self.motor_gains = 1.0, 0.05
+        self.gender = 'male'          # per-env genders live in the env (`male` mask); N == 1 mirrors the reference attribute

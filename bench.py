@@ -175,8 +175,10 @@ def main():
     cfg = capi.default_config()
     sim = BatchSim(fb.scene, cfg, n, device=local_rank)
     # per-env seeds derive from the GLOBAL env id so results do not depend on the partition
-    rng = np.random.default_rng(1001 + rank * n)
-    s = fb.reset(sim, rng, settle_steps=25)
+    from assistive_gym_b200.sharding import sample_block, shard_range
+    lo, hi = shard_range(rank, world, world * n)
+    rng = np.random.default_rng(1001 + rank * n)           # only used for IK random restarts
+    s = fb.reset(sim, rng, settle_steps=25, sample=sample_block(fb, lo, hi))
     sim.feeding_init(fb.feeding_params(seed=1001 + rank * n), s['male'])
     stream = torch.cuda.ExternalStream(sim.stream_ptr(), device=local_rank)
     dev = torch.device('cuda', local_rank)

@@ -1,0 +1,70 @@
+"""The reference's class surface (gym.Env reset/step, AssistiveEnv / Agent / Robot / Human) on the
+batched backend: shapes, spaces, and agreement between the fused step and the same step done through
+the reference-shaped per-call API (take_step + _get_obs + get_food_rewards + human_preferences)."""
+import numpy as np
+import pytest
+
+from assistive_gym_b200 import capi
+
+
+def _make(lib, n_envs, seed):
+    from assistive_gym_b200 import envs
+    env = envs.make('assistive_gym:FeedingJaco-v1', n_envs=n_envs, seed=seed, config=capi.default_config(residual_threshold=0.0))
+    env._sim_lib = lib
+    return env
+
+
+def _check_surface(lib):
+    env = _make(lib, 1, 1001)
+    assert env.action_space.shape == (7,) and env.observation_space.shape == (25,)   # feeding.py:10: 18 + 7
+    obs = env.reset()
+    assert obs.shape == (25,) and np.all(np.isfinite(obs))
+    o, r, d, info = env.step(env.action_space.sample())
+    assert o.shape == (25,) and isinstance(r, float) and isinstance(d, bool)
+    assert set(info) >= {'total_force_on_human', 'task_success', 'action_robot_len', 'obs_robot_len'}
+    # Agent surface
+    q = env.robot.get_joint_angles(env.robot.controllable_joint_indices)
+    assert q.shape == (7,)
+    pos, orient = env.robot.get_pos_orient(env.robot.right_end_effector)
+    assert pos.shape == (3,) and orient.shape == (4,) and abs(np.linalg.norm(orient) - 1) < 1e-5
+    la, lb, pa, pb, f = env.tool.get_contact_points()
+    assert len(la) == len(f)
+    assert env.robot.lower_limits[2] == pytest.approx(0.820304748437)               # j2s7s300_joint_2 lower limit
+    # done after 200 steps (feeding.py:37)
+    for _ in range(199):
+        o, r, d, info = env.step(np.zeros(7, dtype=np.float32))
+    assert d is True
+    env.close()
+
+
+def _check_fused_vs_api(lib, n_envs):
+    a, b = _make(lib, n_envs, 7), _make(lib, n_envs, 7)
+    oa, ob = a.reset(), b.reset()
+    assert np.allclose(oa, ob, atol=1e-6)
+    rng = np.random.default_rng(0)
+    for k in range(4):
+        act = rng.uniform(-1, 1, size=(n_envs, 7)).astype(np.float32)
+        o1, r1, d1, _ = a.step(act if n_envs > 1 else act[0])
+        o2, r2, d2, _ = b.step_reference_api(act)
+        assert np.abs(np.asarray(o1) - np.asarray(o2)).max() < 1e-4, (k, np.abs(np.asarray(o1) - np.asarray(o2)).max())
+        assert np.abs(np.asarray(r1) - np.asarray(r2)).max() < 1e-4
+    a.close()
+    b.close()
+
+
+def test_surface_cpu_harness(emu_lib):
+    _check_surface(emu_lib)
+
+
+def test_fused_step_equals_reference_api_cpu_harness(emu_lib):
+    _check_fused_vs_api(emu_lib, 2)
+
+
+@pytest.mark.gpu
+def test_surface_gpu(gpu_lib):
+    _check_surface(None)
+
+
+@pytest.mark.gpu
+def test_fused_step_equals_reference_api_gpu(gpu_lib):
+    _check_fused_vs_api(None, 8)
