@@ -414,8 +414,10 @@ AG_HD int ag_atomic_add(int* p, int k) {
 #endif
 }
 
-// thread = (pair p, env lane), env fastest; p.i0 = padded env count.
-AG_HDN inline void collide_body(int tid, const SimDev& S, const KP& kp) {
+// K3a: thread = (link pair p, env lane), env fastest; p.i0 = padded env count.  Cheap AABB culls only:
+// surviving collider pairs are appended to the env's candidate list.  Light kernel (few registers,
+// full occupancy); the heavy GJK work runs in K3b with one thread per candidate.
+AG_HDN inline void pairs_body(int tid, const SimDev& S, const KP& kp) {
   const int N = S.N;
   int Npad = kp.i0;
   int e = tid % Npad, pr = tid / Npad;
@@ -435,18 +437,31 @@ AG_HDN inline void collide_body(int tid, const SimDev& S, const KP& kp) {
     for (int cb = cb0; cb < cb0 + ncb; cb++) {
       float thr = fac * fminf(tha, AG_LDG(S.col_thresh + cb));   // size-relative breaking threshold
       if (!aabb_ov(amin, amax, ld3(S.cmin, cb, N, e), ld3(S.cmax, cb, N, e), thr)) continue;
-      NpOut out[4];
-      int n = narrow_pair(S, e, ca, cb, thr, true, out);
-      for (int i = 0; i < n; i++) {
-        int slot = ag_atomic_inc(S.c_count + e);
-        if (slot >= S.maxc) continue;
-        S.c_key[(size_t)slot * N + e] = ((unsigned)ca * (unsigned)S.nc + (unsigned)cb) * 4u + (unsigned)i;
-        cf_st(S.c_data, slot, CF_PAX, N, e, out[i].pa.x); cf_st(S.c_data, slot, CF_PAY, N, e, out[i].pa.y); cf_st(S.c_data, slot, CF_PAZ, N, e, out[i].pa.z);
-        cf_st(S.c_data, slot, CF_PBX, N, e, out[i].pb.x); cf_st(S.c_data, slot, CF_PBY, N, e, out[i].pb.y); cf_st(S.c_data, slot, CF_PBZ, N, e, out[i].pb.z);
-        cf_st(S.c_data, slot, CF_NX, N, e, out[i].n.x); cf_st(S.c_data, slot, CF_NY, N, e, out[i].n.y); cf_st(S.c_data, slot, CF_NZ, N, e, out[i].n.z);
-        cf_st(S.c_data, slot, CF_DIST, N, e, out[i].d);
-      }
+      int slot = ag_atomic_inc(S.cand_count + e);
+      if (slot < S.maxcand) S.cand[(size_t)slot * N + e] = (unsigned)ca * (unsigned)S.nc + (unsigned)cb;
     }
+  }
+}
+
+// K3b: thread = (candidate slot, env): GJK / face fallback / manifold for one collider pair.
+AG_HDN inline void narrow_body(int tid, const SimDev& S, const KP&) {
+  const int N = S.N;
+  int e = tid % N, cs = tid / N;
+  int ncand = S.cand_count[e]; if (ncand > S.maxcand) ncand = S.maxcand;
+  if (cs >= ncand) return;
+  unsigned pk = S.cand[(size_t)cs * N + e];
+  int ca = (int)(pk / (unsigned)S.nc), cb = (int)(pk % (unsigned)S.nc);
+  float thr = S.contact_thr * fminf(AG_LDG(S.col_thresh + ca), AG_LDG(S.col_thresh + cb));
+  NpOut out[4];
+  int n = narrow_pair(S, e, ca, cb, thr, true, out);
+  for (int i = 0; i < n; i++) {
+    int slot = ag_atomic_inc(S.c_count + e);
+    if (slot >= S.maxc) continue;
+    S.c_key[(size_t)slot * N + e] = pk * 4u + (unsigned)i;
+    cf_st(S.c_data, slot, CF_PAX, N, e, out[i].pa.x); cf_st(S.c_data, slot, CF_PAY, N, e, out[i].pa.y); cf_st(S.c_data, slot, CF_PAZ, N, e, out[i].pa.z);
+    cf_st(S.c_data, slot, CF_PBX, N, e, out[i].pb.x); cf_st(S.c_data, slot, CF_PBY, N, e, out[i].pb.y); cf_st(S.c_data, slot, CF_PBZ, N, e, out[i].pb.z);
+    cf_st(S.c_data, slot, CF_NX, N, e, out[i].n.x); cf_st(S.c_data, slot, CF_NY, N, e, out[i].n.y); cf_st(S.c_data, slot, CF_NZ, N, e, out[i].n.z);
+    cf_st(S.c_data, slot, CF_DIST, N, e, out[i].d);
   }
 }
 
@@ -456,7 +471,7 @@ AG_HDN inline void sort_body(int tid, const SimDev& S, const KP&) {
   int e = tid % N, slot = tid / N;
   int cnt = S.c_count[e];
   int n = cnt < S.maxc ? cnt : S.maxc;
-  if (slot == 0) S.overflow[e] = cnt > S.maxc;
+  if (slot == 0) S.overflow[e] = (cnt > S.maxc) || (S.cand_count[e] > S.maxcand);
   if (slot >= n) return;
   unsigned key = S.c_key[(size_t)slot * N + e];
   int rank = 0;

@@ -56,6 +56,7 @@ struct SimDev {
   float *lpos, *lquat;                                 // [nl][3|4][N]
   float *cmin, *cmax, *lmin, *lmax;                    // [nc|nl][3][N]
   // ---- contacts
+  int* cand_count; unsigned* cand; int maxcand;        // narrowphase candidates (collider pairs) [maxcand][N]
   int* c_count;                                        // [N]
   unsigned *c_key, *s_key;                             // [maxc][N] unsorted / sorted
   float *c_data, *s_data;                              // [maxc][AG_CF][N]

@@ -38,7 +38,8 @@ static int fail(const std::string& m) { g_err = m; return -1; }
 AG_KERNEL(k_fk, fk_body)
 AG_KERNEL(k_aabb, aabb_body)
 AG_KERNEL(k_linkaabb, linkaabb_body)
-AG_KERNEL(k_collide, collide_body)
+AG_KERNEL(k_pairs, pairs_body)
+AG_KERNEL(k_narrow, narrow_body)
 AG_KERNEL(k_sort, sort_body)
 AG_KERNEL(k_dyn, dyn_body)
 AG_KERNEL(k_rows, rows_body)
@@ -85,6 +86,7 @@ struct AgSim {
   FeedDev F; FeedDev* F_dev; bool feeding;
   float *d_action, *d_obs, *d_reward, *d_done, *d_info;
   float *h_pin_in, *h_pin_out;
+  int pgs_lanes;
   // profiling
   bool profiling;
   std::vector<std::string> knames;
@@ -370,6 +372,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   S.cmin = dalloc<float>(s, (size_t)nc * 3 * N); S.cmax = dalloc<float>(s, (size_t)nc * 3 * N);
   S.lmin = dalloc<float>(s, (size_t)nl * 3 * N); S.lmax = dalloc<float>(s, (size_t)nl * 3 * N);
   S.c_count = dalloc<int>(s, N); S.overflow = dalloc<int>(s, N); S.iters_used = dalloc<int>(s, N);
+  S.maxcand = 4 * S.maxc; S.cand_count = dalloc<int>(s, N); S.cand = dalloc<unsigned>(s, (size_t)S.maxcand * N);
   S.c_key = dalloc<unsigned>(s, (size_t)S.maxc * N); S.s_key = dalloc<unsigned>(s, (size_t)S.maxc * N);
   S.c_data = dalloc<float>(s, (size_t)S.maxc * AG_CF * N); S.s_data = dalloc<float>(s, (size_t)S.maxc * AG_CF * N);
   S.s_ref = dalloc<int>(s, (size_t)S.maxc * 4 * N);
@@ -385,9 +388,19 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   if (!S.gr_ref || !S.as_MiJ || !S.s_data) { g_err = "device allocation failed"; ag_destroy(s); return nullptr; }
 #ifndef AG_CPU_EMU
   {
-    size_t smem = (size_t)pgs_layout(S).total * 32 * sizeof(float);
+    // Lanes (envs) per CTA of the latency-bound per-env kernels.  4096 envs are only 128 full warps
+    // for 592 warp schedulers, so partially filled warps (8 envs each) put a warp on every scheduler,
+    // shorten the per-warp iteration count (max over fewer envs) and reduce divergence.
+    const char* lp = getenv("AG_PGS_LANES");
+    s->pgs_lanes = lp ? atoi(lp) : 8;
+    if (s->pgs_lanes < 1 || s->pgs_lanes > 32) s->pgs_lanes = 8;
+    size_t smem = (size_t)pgs_layout(S).total * s->pgs_lanes * sizeof(float);
     if (smem > 227 * 1024) { g_err = "PGS shared-memory footprint exceeds 227 KB per CTA: lower max_contacts"; ag_destroy(s); return nullptr; }
     if (cudaFuncSetAttribute(k_pgs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { g_err = "cudaFuncSetAttribute(k_pgs) failed"; ag_destroy(s); return nullptr; }
+    // keep most of the unified L1/shared array as L1: the row constants are re-read every iteration
+    int blocks_per_sm = std::max(1, (N / s->pgs_lanes + 147) / 148);
+    int carve = (int)std::min<size_t>(100, (smem * blocks_per_sm * 100 + 228 * 1024 - 1) / (228 * 1024) + 5);
+    cudaFuncSetAttribute(k_pgs, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
   }
 #endif
   // defaults: friction from the template, all bodies active, identity quaternions
@@ -557,9 +570,11 @@ static void substep(AgSim* s) {
   KP l = kp0(); l.p0 = S.movlink; l.i0 = S.nmovlink;
   LAUNCH(s, k_linkaabb, (size_t)S.nmovlink * N, l);
   dev_zero(s, S.c_count, sizeof(int) * N);
+  dev_zero(s, S.cand_count, sizeof(int) * N);
   int Npad = (N + 31) / 32 * 32;
   KP c = kp0(); c.i0 = Npad;
-  LAUNCH(s, k_collide, (size_t)S.npair * Npad, c);
+  LAUNCH(s, k_pairs, (size_t)S.npair * Npad, c);
+  LAUNCH(s, k_narrow, (size_t)S.maxcand * N, z);
   LAUNCH(s, k_sort, (size_t)S.maxc * N, z);
   LAUNCH(s, k_dyn, N, z);
   LAUNCH(s, k_rows, N, z);
@@ -567,10 +582,11 @@ static void substep(AgSim* s) {
 #ifndef AG_CPU_EMU
   {
     KP kp = z; kp.n = N;
-    size_t smem = (size_t)pgs_layout(S).total * 32 * sizeof(float);
+    int L = s->pgs_lanes;
+    size_t smem = (size_t)pgs_layout(S).total * L * sizeof(float);
     int ps = s->profiling ? prof_slot(s, "k_pgs") : -1;
     if (ps >= 0) prof_mark(s, ps, true);
-    k_pgs<<<(N + 31) / 32, 32, smem, s->stream>>>(S, kp);
+    k_pgs<<<(N + L - 1) / L, L, smem, s->stream>>>(S, kp);
     if (ps >= 0) prof_mark(s, ps, false);
     s->launches++;
   }
