@@ -11,6 +11,7 @@
 // for the unconstrained velocity update, velocity-level PGS over joint limits, joint motors, fixed
 // constraints and frictional contacts, symplectic Euler.
 #pragma once
+#include <string.h>
 #include "ag_math.cuh"
 #include "ag_types.h"
 
@@ -853,22 +854,30 @@ AG_HDN inline void crows_body(int tid, const SimDev& S, const KP&) {
 }
 
 // ------------------------------------------------------------------ K7: PGS
-// One env per lane, one warp per block.  Everything the Gauss-Seidel sweep reads AND writes lives in
-// shared memory (`sm`, lane-strided so a warp access is conflict-free): velocity deltas, per-body
-// inverse inertias / COMs, the articulated M^-1, all impulses.  Global memory is only read through
-// the read-only path (row constants written by k_rows / k_crows), so the compiler may hoist those
-// loads across the shared-memory dependency chain.  Layout (floats per lane):
-//   [dv: ND+6nf][fcom: 3nf][fIinv: 6nf][Minv: ND*ND][lam: 3*maxc][dr_lam: 3ND][gr_lam: ngr]
-struct PgsLayout { int o_dv, o_fc, o_fi, o_mi, o_lam, o_dr, o_gr, total; };
+// One env per lane, a few lanes per CTA (AG_PGS_LANES, default 4).  The Gauss-Seidel chain of one env
+// is strictly sequential, so the kernel is latency-bound per row; measured on B200 (ncu, round 1):
+// with row constants read from global memory every iteration a row cost ~2 200 cycles (serialised L2
+// round trips, 17 % L1 hit rate).  Therefore EVERYTHING the sweep touches is staged once into shared
+// memory (`sm`, lane-strided => conflict-free): velocity deltas, per-body inverse inertias / COMs,
+// the articulated M^-1, all row constants (contacts, dof rows, fixed-constraint rows incl. their
+// articulated Jacobian sides) and all impulses.  Only the rare articulated sides of contact rows stay
+// in global memory.  Layout (floats per lane):
+//   [dv: ND+6nf][fcom: 3nf][fIinv: 6nf][Minv: ND*ND][lam: 3*maxc][dr: 3*(3ND)][gr: ngr*(16+2ND)][crec: 20*maxc]
+#define PGS_CREC 20
+struct PgsLayout { int o_dv, o_fc, o_fi, o_mi, o_lam, o_dr, o_gr, o_cr, total; };
 AG_HD PgsLayout pgs_layout(const SimDev& S) {
   PgsLayout L;
   L.o_dv = 0; L.o_fc = L.o_dv + S.ND + 6 * S.nf; L.o_fi = L.o_fc + 3 * S.nf; L.o_mi = L.o_fi + 6 * S.nf;
-  L.o_lam = L.o_mi + S.ND * S.ND; L.o_dr = L.o_lam + 3 * S.maxc; L.o_gr = L.o_dr + 3 * S.ND; L.total = L.o_gr + S.ngr;
+  L.o_lam = L.o_mi + S.ND * S.ND; L.o_dr = L.o_lam + 3 * S.maxc; L.o_gr = L.o_dr + 9 * S.ND;
+  L.o_cr = L.o_gr + S.ngr * (16 + 2 * S.ND); L.total = L.o_cr + PGS_CREC * S.maxc;
   return L;
 }
 #define SMF(i) sm[(size_t)(i) * stride]
+AG_HD float i2f_bits(int v) { float f; memcpy(&f, &v, 4); return f; }
+AG_HD int f2i_bits(float f) { int v; memcpy(&v, &f, 4); return v; }
 
-AG_HD float pgs_side_jv(const SimDev& S, int e, const float* sm, int stride, const PgsLayout& L, int ref, int as, f3 lin, f3 ang_free) {
+// J.dv of one side.  `artJ` >= 0: offset in sm of this side's articulated Jacobian (else global slot `as`)
+AG_HD float pgs_side_jv(const SimDev& S, int e, const float* sm, int stride, const PgsLayout& L, int ref, int as, int artJ, f3 lin, f3 ang_free) {
   int kind = ref & 3, idx = ref >> 2;
   if (kind == 1) {
     int o = L.o_dv + S.ND + 6 * idx;
@@ -876,13 +885,16 @@ AG_HD float pgs_side_jv(const SimDev& S, int e, const float* sm, int stride, con
   } else if (kind == 2) {
     int a = AG_LDG(S.dl_art + idx), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
     float t = 0.f;
-    const float* J = S.as_J + (size_t)as * AG_MAXND * S.N + e;
-    for (int i = 0; i < nd; i++) t += AG_LDG(J + (size_t)i * S.N) * SMF(L.o_dv + d0 + i);
+    if (artJ >= 0) { for (int i = 0; i < nd; i++) t += SMF(artJ + i) * SMF(L.o_dv + d0 + i); }
+    else {
+      const float* J = S.as_J + (size_t)as * AG_MAXND * S.N + e;
+      for (int i = 0; i < nd; i++) t += AG_LDG(J + (size_t)i * S.N) * SMF(L.o_dv + d0 + i);
+    }
     return t;
   }
   return 0.f;
 }
-AG_HD void pgs_side_apply(const SimDev& S, int e, float* sm, int stride, const PgsLayout& L, int ref, int as, f3 lin, f3 ang_free, float dl) {
+AG_HD void pgs_side_apply(const SimDev& S, int e, float* sm, int stride, const PgsLayout& L, int ref, int as, int artM, f3 lin, f3 ang_free, float dl) {
   int kind = ref & 3, idx = ref >> 2;
   if (kind == 1) {
     int o = L.o_dv + S.ND + 6 * idx;
@@ -894,14 +906,12 @@ AG_HD void pgs_side_apply(const SimDev& S, int e, float* sm, int stride, const P
     SMF(o + 3) += ia.x * dl; SMF(o + 4) += ia.y * dl; SMF(o + 5) += ia.z * dl;
   } else if (kind == 2) {
     int a = AG_LDG(S.dl_art + idx), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
-    const float* M = S.as_MiJ + (size_t)as * AG_MAXND * S.N + e;
-    for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += AG_LDG(M + (size_t)i * S.N) * dl;
+    if (artM >= 0) { for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += SMF(artM + i) * dl; }
+    else {
+      const float* M = S.as_MiJ + (size_t)as * AG_MAXND * S.N + e;
+      for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += AG_LDG(M + (size_t)i * S.N) * dl;
+    }
   }
-}
-AG_HD f3 pgs_rel(const float* sm, int stride, const PgsLayout& L, int ref, f3 p) {   // p - com of a free side
-  if ((ref & 3) != 1) return f3();
-  int o = L.o_fc + 3 * (ref >> 2);
-  return f3(p.x - SMF(o), p.y - SMF(o + 1), p.z - SMF(o + 2));
 }
 
 AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm, int stride) {
@@ -909,16 +919,50 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm, int st
   const int ND = S.ND;
   const PgsLayout L = pgs_layout(S);
   const int nvel = ND + 6 * S.nf;
-  // ---- stage per-env solver state into shared memory
+  // ---- stage the per-env solver state and all row constants into shared memory
   for (int i = 0; i < nvel; i++) SMF(L.o_dv + i) = 0.f;
   for (int i = 0; i < 3 * S.nf; i++) SMF(L.o_fc + i) = S.fcom[(size_t)i * N + e];
   for (int i = 0; i < 6 * S.nf; i++) SMF(L.o_fi + i) = S.fIinv[(size_t)i * N + e];
   for (int i = 0; i < ND * ND; i++) SMF(L.o_mi + i) = S.Minv[(size_t)i * N + e];
   int cnt = S.c_count[e]; if (cnt > S.maxc) cnt = S.maxc;
   for (int i = 0; i < 3 * cnt; i++) SMF(L.o_lam + i) = 0.f;
-  for (int i = 0; i < 3 * ND; i++) SMF(L.o_dr + i) = 0.f;
-  for (int i = 0; i < S.ngr; i++) SMF(L.o_gr + i) = 0.f;
-  const float* sd = S.s_data;
+  for (int r = 0; r < 3 * ND; r++) {      // dof rows: lambda, rhs, dinv
+    SMF(L.o_dr + 3 * r) = 0.f; SMF(L.o_dr + 3 * r + 1) = S.dr_rhs[(size_t)r * N + e]; SMF(L.o_dr + 3 * r + 2) = S.dr_dinv[(size_t)r * N + e];
+  }
+  const int GRW = 16 + 2 * ND;
+  for (int r = 0; r < S.ngr; r++) {       // fixed-constraint rows: 16 fields (GR_LAM reused as lambda, PAD0/1 = refs) + art sides
+    int o = L.o_gr + r * GRW;
+    const float* g = S.gr_data + (size_t)r * 16 * N + e;
+    for (int f = 0; f < 14; f++) SMF(o + f) = g[(size_t)f * N];
+    SMF(o + GR_LAM) = 0.f;
+    const int* rf = S.gr_ref + (size_t)r * 4 * N + e;
+    int refA = rf[0], refB = rf[N], asA = rf[2 * (size_t)N], asB = rf[3 * (size_t)N];
+    SMF(o + GR_PAD0) = i2f_bits(refA); SMF(o + GR_PAD1) = i2f_bits(refB);
+    // articulated side (at most one side of a fixed constraint is staged; a second one falls back to global)
+    int as = (refA & 3) == 2 ? asA : ((refB & 3) == 2 ? asB : -1);
+    for (int i = 0; i < ND; i++) {
+      SMF(o + 16 + i) = as >= 0 ? S.as_J[((size_t)as * AG_MAXND + i) * N + e] : 0.f;
+      SMF(o + 16 + ND + i) = as >= 0 ? S.as_MiJ[((size_t)as * AG_MAXND + i) * N + e] : 0.f;
+    }
+  }
+  for (int s = 0; s < cnt; s++) {         // contact records
+    int o = L.o_cr + s * PGS_CREC;
+    const float* c = S.s_data + (size_t)s * AG_CF * N + e;
+    const int* rf = S.s_ref + (size_t)s * 4 * N + e;
+    int refA = rf[0], refB = rf[N], asA = rf[2 * (size_t)N], asB = rf[3 * (size_t)N];
+    f3 pa(c[(size_t)CF_PAX * N], c[(size_t)CF_PAY * N], c[(size_t)CF_PAZ * N]);
+    f3 pb(c[(size_t)CF_PBX * N], c[(size_t)CF_PBY * N], c[(size_t)CF_PBZ * N]);
+    f3 rA, rB;
+    if ((refA & 3) == 1) { int q = L.o_fc + 3 * (refA >> 2); rA = f3(pa.x - SMF(q), pa.y - SMF(q + 1), pa.z - SMF(q + 2)); }
+    if ((refB & 3) == 1) { int q = L.o_fc + 3 * (refB >> 2); rB = f3(pb.x - SMF(q), pb.y - SMF(q + 1), pb.z - SMF(q + 2)); }
+    SMF(o) = c[(size_t)CF_NX * N]; SMF(o + 1) = c[(size_t)CF_NY * N]; SMF(o + 2) = c[(size_t)CF_NZ * N];
+    SMF(o + 3) = rA.x; SMF(o + 4) = rA.y; SMF(o + 5) = rA.z; SMF(o + 6) = rB.x; SMF(o + 7) = rB.y; SMF(o + 8) = rB.z;
+    SMF(o + 9) = c[(size_t)CF_RHS_N * N]; SMF(o + 10) = c[(size_t)CF_DINV_N * N];
+    SMF(o + 11) = c[(size_t)CF_RHS_T1 * N]; SMF(o + 12) = c[(size_t)CF_DINV_T1 * N];
+    SMF(o + 13) = c[(size_t)CF_RHS_T2 * N]; SMF(o + 14) = c[(size_t)CF_DINV_T2 * N];
+    SMF(o + 15) = c[(size_t)CF_MU * N];
+    SMF(o + 16) = i2f_bits(refA); SMF(o + 17) = i2f_bits(refB); SMF(o + 18) = i2f_bits(asA); SMF(o + 19) = i2f_bits(asB);
+  }
   int used = 0;
   bool done = false;
 #if defined(__CUDA_ARCH__)
@@ -930,17 +974,17 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm, int st
       used = it + 1;
       // joint limits (lower, upper) then motors: J = +-e_d
       for (int r = 0; r < 3 * ND; r++) {
-        float dinv = AG_LDG(S.dr_dinv + (size_t)r * N + e);
+        float dinv = SMF(L.o_dr + 3 * r + 2);
         if (dinv == 0.f) continue;
         int d = r % ND; int kindr = r / ND;
         float sgn = kindr == 1 ? -1.f : 1.f;
-        float lam = SMF(L.o_dr + r);
-        float dl = AG_LDG(S.dr_rhs + (size_t)r * N + e) - sgn * SMF(L.o_dv + d) * dinv;
+        float lam = SMF(L.o_dr + 3 * r);
+        float dl = SMF(L.o_dr + 3 * r + 1) - sgn * SMF(L.o_dv + d) * dinv;
         float lo, hi;
         if (kindr == 2) { hi = S.motor_maxf[AG_LDG(S.dl_link + d)] * S.dt; lo = -hi; } else { lo = 0.f; hi = 1e30f; }
         float sum = lam + dl;
         if (sum < lo) { dl = lo - lam; sum = lo; } else if (sum > hi) { dl = hi - lam; sum = hi; }
-        SMF(L.o_dr + r) = sum;
+        SMF(L.o_dr + 3 * r) = sum;
         int a = AG_LDG(S.dl_art + d), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
         float sdl = sgn * dl;
         for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += SMF(L.o_mi + (d0 + i) * ND + d) * sdl;
@@ -948,72 +992,68 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm, int st
       }
       // fixed constraints
       for (int r = 0; r < S.ngr; r++) {
-        const float* g = S.gr_data + (size_t)r * 16 * N + e;
-        float dinv = AG_LDG(g + (size_t)GR_DINV * N);
+        int o = L.o_gr + r * GRW;
+        float dinv = SMF(o + GR_DINV);
         if (dinv == 0.f) continue;
+        int refA = f2i_bits(SMF(o + GR_PAD0)), refB = f2i_bits(SMF(o + GR_PAD1));
+        f3 lin(SMF(o + GR_LX), SMF(o + GR_LY), SMF(o + GR_LZ));
+        f3 aA(SMF(o + GR_AAX), SMF(o + GR_AAY), SMF(o + GR_AAZ)), aB(SMF(o + GR_ABX), SMF(o + GR_ABY), SMF(o + GR_ABZ));
+        bool aArt = (refA & 3) == 2;      // which side owns the staged articulated rows
         const int* rf = S.gr_ref + (size_t)r * 4 * N + e;
-        int refA = AG_LDG(rf), refB = AG_LDG(rf + N), asA = AG_LDG(rf + 2 * (size_t)N), asB = AG_LDG(rf + 3 * (size_t)N);
-        f3 lin(AG_LDG(g + (size_t)GR_LX * N), AG_LDG(g + (size_t)GR_LY * N), AG_LDG(g + (size_t)GR_LZ * N));
-        f3 aA(AG_LDG(g + (size_t)GR_AAX * N), AG_LDG(g + (size_t)GR_AAY * N), AG_LDG(g + (size_t)GR_AAZ * N));
-        f3 aB(AG_LDG(g + (size_t)GR_ABX * N), AG_LDG(g + (size_t)GR_ABY * N), AG_LDG(g + (size_t)GR_ABZ * N));
-        float jv = pgs_side_jv(S, e, sm, stride, L, refA, asA, lin, aA) + pgs_side_jv(S, e, sm, stride, L, refB, asB, -lin, -aB);
-        float lam = SMF(L.o_gr + r);
-        float dl = AG_LDG(g + (size_t)GR_RHS * N) - jv * dinv;
-        float lo = AG_LDG(g + (size_t)GR_LO * N), hi = AG_LDG(g + (size_t)GR_HI * N);
+        int asB = (!aArt || (refB & 3) != 2) ? -1 : AG_LDG(rf + 3 * (size_t)N);
+        float jv = pgs_side_jv(S, e, sm, stride, L, refA, -1, aArt ? o + 16 : -1, lin, aA) +
+                   pgs_side_jv(S, e, sm, stride, L, refB, asB, (!aArt && (refB & 3) == 2) ? o + 16 : -1, -lin, -aB);
+        float lam = SMF(o + GR_LAM);
+        float dl = SMF(o + GR_RHS) - jv * dinv;
+        float lo = SMF(o + GR_LO), hi = SMF(o + GR_HI);
         float sum = lam + dl;
         if (sum < lo) { dl = lo - lam; sum = lo; } else if (sum > hi) { dl = hi - lam; sum = hi; }
-        SMF(L.o_gr + r) = sum;
-        pgs_side_apply(S, e, sm, stride, L, refA, asA, lin, aA, dl); pgs_side_apply(S, e, sm, stride, L, refB, asB, -lin, -aB, dl);
+        SMF(o + GR_LAM) = sum;
+        pgs_side_apply(S, e, sm, stride, L, refA, -1, aArt ? o + 16 + ND : -1, lin, aA, dl);
+        pgs_side_apply(S, e, sm, stride, L, refB, asB, (!aArt && (refB & 3) == 2) ? o + 16 + ND : -1, -lin, -aB, dl);
         resid = fmaxf(resid, dl * dl);
       }
       // contact normals
       for (int s = 0; s < cnt; s++) {
-        const float* c = sd + (size_t)s * AG_CF * N + e;
-        float dinv = AG_LDG(c + (size_t)CF_DINV_N * N);
+        int o = L.o_cr + s * PGS_CREC;
+        float dinv = SMF(o + 10);
         if (dinv == 0.f) continue;
-        const int* rf = S.s_ref + (size_t)s * 4 * N + e;
-        int refA = AG_LDG(rf), refB = AG_LDG(rf + N), asA = AG_LDG(rf + 2 * (size_t)N), asB = AG_LDG(rf + 3 * (size_t)N);
-        f3 n(AG_LDG(c + (size_t)CF_NX * N), AG_LDG(c + (size_t)CF_NY * N), AG_LDG(c + (size_t)CF_NZ * N));
-        f3 pa(AG_LDG(c + (size_t)CF_PAX * N), AG_LDG(c + (size_t)CF_PAY * N), AG_LDG(c + (size_t)CF_PAZ * N));
-        f3 pb(AG_LDG(c + (size_t)CF_PBX * N), AG_LDG(c + (size_t)CF_PBY * N), AG_LDG(c + (size_t)CF_PBZ * N));
-        f3 aA = cross(pgs_rel(sm, stride, L, refA, pa), n), aB = cross(pgs_rel(sm, stride, L, refB, pb), n);
-        float jv = pgs_side_jv(S, e, sm, stride, L, refA, asA, n, aA) + pgs_side_jv(S, e, sm, stride, L, refB, asB, -n, -aB);
+        int refA = f2i_bits(SMF(o + 16)), refB = f2i_bits(SMF(o + 17)), asA = f2i_bits(SMF(o + 18)), asB = f2i_bits(SMF(o + 19));
+        f3 n(SMF(o), SMF(o + 1), SMF(o + 2));
+        f3 aA = cross(f3(SMF(o + 3), SMF(o + 4), SMF(o + 5)), n), aB = cross(f3(SMF(o + 6), SMF(o + 7), SMF(o + 8)), n);
+        float jv = pgs_side_jv(S, e, sm, stride, L, refA, asA, -1, n, aA) + pgs_side_jv(S, e, sm, stride, L, refB, asB, -1, -n, -aB);
         float lam = SMF(L.o_lam + 3 * s);
-        float dl = AG_LDG(c + (size_t)CF_RHS_N * N) - jv * dinv;
+        float dl = SMF(o + 9) - jv * dinv;
         float sum = lam + dl;
         if (sum < 0.f) { dl = -lam; sum = 0.f; }
         SMF(L.o_lam + 3 * s) = sum;
-        pgs_side_apply(S, e, sm, stride, L, refA, asA, n, aA, dl); pgs_side_apply(S, e, sm, stride, L, refB, asB, -n, -aB, dl);
+        pgs_side_apply(S, e, sm, stride, L, refA, asA, -1, n, aA, dl); pgs_side_apply(S, e, sm, stride, L, refB, asB, -1, -n, -aB, dl);
         resid = fmaxf(resid, dl * dl);
       }
       // friction (two directions per contact, cone or pyramid)
       for (int s = 0; s < cnt; s++) {
-        const float* c = sd + (size_t)s * AG_CF * N + e;
-        if (AG_LDG(c + (size_t)CF_DINV_N * N) == 0.f) continue;
+        int o = L.o_cr + s * PGS_CREC;
+        if (SMF(o + 10) == 0.f) continue;
         float l1 = SMF(L.o_lam + 3 * s + 1), l2 = SMF(L.o_lam + 3 * s + 2);
-        float lim = AG_LDG(c + (size_t)CF_MU * N) * SMF(L.o_lam + 3 * s);
+        float lim = SMF(o + 15) * SMF(L.o_lam + 3 * s);
         if (lim <= 0.f && l1 == 0.f && l2 == 0.f) continue;
-        float dinv1 = AG_LDG(c + (size_t)CF_DINV_T1 * N), dinv2 = AG_LDG(c + (size_t)CF_DINV_T2 * N);
-        const int* rf = S.s_ref + (size_t)s * 4 * N + e;
-        int refA = AG_LDG(rf), refB = AG_LDG(rf + N), asA = AG_LDG(rf + 2 * (size_t)N), asB = AG_LDG(rf + 3 * (size_t)N);
-        f3 n(AG_LDG(c + (size_t)CF_NX * N), AG_LDG(c + (size_t)CF_NY * N), AG_LDG(c + (size_t)CF_NZ * N));
-        f3 pa(AG_LDG(c + (size_t)CF_PAX * N), AG_LDG(c + (size_t)CF_PAY * N), AG_LDG(c + (size_t)CF_PAZ * N));
-        f3 pb(AG_LDG(c + (size_t)CF_PBX * N), AG_LDG(c + (size_t)CF_PBY * N), AG_LDG(c + (size_t)CF_PBZ * N));
+        int refA = f2i_bits(SMF(o + 16)), refB = f2i_bits(SMF(o + 17)), asA = f2i_bits(SMF(o + 18)), asB = f2i_bits(SMF(o + 19));
+        f3 n(SMF(o), SMF(o + 1), SMF(o + 2));
         f3 t1, t2; plane_space(n, t1, t2);
-        f3 rA = pgs_rel(sm, stride, L, refA, pa), rB = pgs_rel(sm, stride, L, refB, pb);
+        f3 rA(SMF(o + 3), SMF(o + 4), SMF(o + 5)), rB(SMF(o + 6), SMF(o + 7), SMF(o + 8));
         f3 a1A = cross(rA, t1), a1B = cross(rB, t1), a2A = cross(rA, t2), a2B = cross(rB, t2);
-        float jv1 = pgs_side_jv(S, e, sm, stride, L, refA, asA + 1, t1, a1A) + pgs_side_jv(S, e, sm, stride, L, refB, asB + 1, -t1, -a1B);
-        float jv2 = pgs_side_jv(S, e, sm, stride, L, refA, asA + 2, t2, a2A) + pgs_side_jv(S, e, sm, stride, L, refB, asB + 2, -t2, -a2B);
-        float s1 = l1 + AG_LDG(c + (size_t)CF_RHS_T1 * N) - jv1 * dinv1;
-        float s2 = l2 + AG_LDG(c + (size_t)CF_RHS_T2 * N) - jv2 * dinv2;
+        float jv1 = pgs_side_jv(S, e, sm, stride, L, refA, asA + 1, -1, t1, a1A) + pgs_side_jv(S, e, sm, stride, L, refB, asB + 1, -1, -t1, -a1B);
+        float jv2 = pgs_side_jv(S, e, sm, stride, L, refA, asA + 2, -1, t2, a2A) + pgs_side_jv(S, e, sm, stride, L, refB, asB + 2, -1, -t2, -a2B);
+        float s1 = l1 + SMF(o + 11) - jv1 * SMF(o + 12);
+        float s2 = l2 + SMF(o + 13) - jv2 * SMF(o + 14);
         if (S.cone) {
           float m2 = s1 * s1 + s2 * s2;
           if (m2 > lim * lim) { float k = lim / sqrtf(m2); s1 *= k; s2 *= k; }
         } else { s1 = clampf(s1, -lim, lim); s2 = clampf(s2, -lim, lim); }
         float d1 = s1 - l1, d2 = s2 - l2;
         SMF(L.o_lam + 3 * s + 1) = s1; SMF(L.o_lam + 3 * s + 2) = s2;
-        pgs_side_apply(S, e, sm, stride, L, refA, asA + 1, t1, a1A, d1); pgs_side_apply(S, e, sm, stride, L, refB, asB + 1, -t1, -a1B, d1);
-        pgs_side_apply(S, e, sm, stride, L, refA, asA + 2, t2, a2A, d2); pgs_side_apply(S, e, sm, stride, L, refB, asB + 2, -t2, -a2B, d2);
+        pgs_side_apply(S, e, sm, stride, L, refA, asA + 1, -1, t1, a1A, d1); pgs_side_apply(S, e, sm, stride, L, refB, asB + 1, -1, -t1, -a1B, d1);
+        pgs_side_apply(S, e, sm, stride, L, refA, asA + 2, -1, t2, a2A, d2); pgs_side_apply(S, e, sm, stride, L, refB, asB + 2, -1, -t2, -a2B, d2);
         resid = fmaxf(resid, fmaxf(d1 * d1, d2 * d2));
       }
       if (S.resid_thr > 0.f && resid <= S.resid_thr) done = true;
@@ -1027,8 +1067,8 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm, int st
   // ---- write back
   S.iters_used[e] = used;
   for (int i = 0; i < nvel; i++) S.dv[(size_t)i * N + e] = SMF(L.o_dv + i);
-  for (int r = 0; r < 3 * ND; r++) S.dr_lam[(size_t)r * N + e] = SMF(L.o_dr + r);
-  for (int r = 0; r < S.ngr; r++) S.gr_data[((size_t)r * 16 + GR_LAM) * N + e] = SMF(L.o_gr + r);
+  for (int r = 0; r < 3 * ND; r++) S.dr_lam[(size_t)r * N + e] = SMF(L.o_dr + 3 * r);
+  for (int r = 0; r < S.ngr; r++) S.gr_data[((size_t)r * 16 + GR_LAM) * N + e] = SMF(L.o_gr + r * GRW + GR_LAM);
   for (int s = 0; s < cnt; s++) {
     cf_st(S.s_data, s, CF_LAM_N, N, e, SMF(L.o_lam + 3 * s));
     cf_st(S.s_data, s, CF_LAM_T1, N, e, SMF(L.o_lam + 3 * s + 1));

@@ -392,8 +392,8 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
     // for 592 warp schedulers, so partially filled warps (8 envs each) put a warp on every scheduler,
     // shorten the per-warp iteration count (max over fewer envs) and reduce divergence.
     const char* lp = getenv("AG_PGS_LANES");
-    s->pgs_lanes = lp ? atoi(lp) : 8;
-    if (s->pgs_lanes < 1 || s->pgs_lanes > 32) s->pgs_lanes = 8;
+    s->pgs_lanes = lp ? atoi(lp) : 4;
+    if (s->pgs_lanes < 1 || s->pgs_lanes > 32) s->pgs_lanes = 4;
     size_t smem = (size_t)pgs_layout(S).total * s->pgs_lanes * sizeof(float);
     if (smem > 227 * 1024) { g_err = "PGS shared-memory footprint exceeds 227 KB per CTA: lower max_contacts"; ag_destroy(s); return nullptr; }
     if (cudaFuncSetAttribute(k_pgs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { g_err = "cudaFuncSetAttribute(k_pgs) failed"; ag_destroy(s); return nullptr; }
@@ -707,6 +707,12 @@ int ag_state_set(AgSim* s, const float* in) {
   h2d(s, s->S.base_lin, bl.data(), bl.size() * 4); h2d(s, s->S.base_ang, ba.data(), ba.size() * 4);
   h2d(s, s->S.jq, q.data(), q.size() * 4); h2d(s, s->S.jqd, qd.data(), qd.size() * 4);
   run_fk_all(s);
+  return 0;
+}
+
+int ag_get_solver_stats(AgSim* s, int32_t* contacts, int32_t* iters) {
+  if (contacts && d2h(s, contacts, s->S.c_count, sizeof(int) * s->S.N)) return -1;
+  if (iters && d2h(s, iters, s->S.iters_used, sizeof(int) * s->S.N)) return -1;
   return 0;
 }
 

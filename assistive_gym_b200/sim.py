@@ -149,6 +149,11 @@ class BatchSim:
     def overflow_count(self):
         return int(self.lib.ag_overflow_count(self.h))
 
+    def solver_stats(self):
+        c, it = np.zeros(self.n, dtype=np.int32), np.zeros(self.n, dtype=np.int32)
+        self._ck(self.lib.ag_get_solver_stats(self.h, _p(c), _p(it)))
+        return c, it
+
     def profile_enable(self, on=True):
         self._ck(self.lib.ag_profile_enable(self.h, int(bool(on))))
 
