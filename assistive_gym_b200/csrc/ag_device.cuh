@@ -862,22 +862,23 @@ AG_HDN inline void crows_body(int tid, const SimDev& S, const KP&) {
 // the articulated M^-1, all row constants (contacts, dof rows, fixed-constraint rows incl. their
 // articulated Jacobian sides) and all impulses.  Only the rare articulated sides of contact rows stay
 // in global memory.  Layout (floats per lane):
-//   [dv: ND+6nf][fcom: 3nf][fIinv: 6nf][Minv: ND*ND][lam: 3*maxc][dr: 3*(3ND)][gr: ngr*(16+2ND)][crec: 20*maxc]
+//   [dv: ND+6nf][fcom: 3nf][fIinv: 6nf][invm: nf][Minv: ND*ND][lam: 3*maxc][dr: 5*(3ND)][gr: ngr*(16+2ND)][crec: 20*maxc]
 #define PGS_CREC 20
-struct PgsLayout { int o_dv, o_fc, o_fi, o_mi, o_lam, o_dr, o_gr, o_cr, total; };
+struct PgsLayout { int o_dv, o_fc, o_fi, o_fm, o_mi, o_lam, o_dr, o_gr, o_cr, total; };
 AG_HD PgsLayout pgs_layout(const SimDev& S) {
   PgsLayout L;
-  L.o_dv = 0; L.o_fc = L.o_dv + S.ND + 6 * S.nf; L.o_fi = L.o_fc + 3 * S.nf; L.o_mi = L.o_fi + 6 * S.nf;
-  L.o_lam = L.o_mi + S.ND * S.ND; L.o_dr = L.o_lam + 3 * S.maxc; L.o_gr = L.o_dr + 9 * S.ND;
+  L.o_dv = 0; L.o_fc = L.o_dv + S.ND + 6 * S.nf; L.o_fi = L.o_fc + 3 * S.nf; L.o_fm = L.o_fi + 6 * S.nf; L.o_mi = L.o_fm + S.nf;
+  L.o_lam = L.o_mi + S.ND * S.ND; L.o_dr = L.o_lam + 3 * S.maxc; L.o_gr = L.o_dr + 15 * S.ND;
   L.o_cr = L.o_gr + S.ngr * (16 + 2 * S.ND); L.total = L.o_cr + PGS_CREC * S.maxc;
   return L;
 }
-#define SMF(i) sm[(size_t)(i) * stride]
+#define SMF(i) sm[(i) * LANES]
 AG_HD float i2f_bits(int v) { float f; memcpy(&f, &v, 4); return f; }
 AG_HD int f2i_bits(float f) { int v; memcpy(&v, &f, 4); return v; }
 
 // J.dv of one side.  `artJ` >= 0: offset in sm of this side's articulated Jacobian (else global slot `as`)
-AG_HD float pgs_side_jv(const SimDev& S, int e, const float* sm, int stride, const PgsLayout& L, int ref, int as, int artJ, f3 lin, f3 ang_free) {
+template <int LANES>
+AG_HD float pgs_side_jv(const SimDev& S, int e, const float* sm, const PgsLayout& L, int ref, int as, int artJ, f3 lin, f3 ang_free) {
   int kind = ref & 3, idx = ref >> 2;
   if (kind == 1) {
     int o = L.o_dv + S.ND + 6 * idx;
@@ -894,11 +895,12 @@ AG_HD float pgs_side_jv(const SimDev& S, int e, const float* sm, int stride, con
   }
   return 0.f;
 }
-AG_HD void pgs_side_apply(const SimDev& S, int e, float* sm, int stride, const PgsLayout& L, int ref, int as, int artM, f3 lin, f3 ang_free, float dl) {
+template <int LANES>
+AG_HD void pgs_side_apply(const SimDev& S, int e, float* sm, const PgsLayout& L, int ref, int as, int artM, f3 lin, f3 ang_free, float dl) {
   int kind = ref & 3, idx = ref >> 2;
   if (kind == 1) {
     int o = L.o_dv + S.ND + 6 * idx;
-    float invm = AG_LDG(S.free_invm + idx) * dl;
+    float invm = SMF(L.o_fm + idx) * dl;
     int fi = L.o_fi + 6 * idx;
     s3 Ii; Ii.xx = SMF(fi); Ii.yy = SMF(fi + 1); Ii.zz = SMF(fi + 2); Ii.xy = SMF(fi + 3); Ii.xz = SMF(fi + 4); Ii.yz = SMF(fi + 5);
     f3 ia = mul(Ii, ang_free);
@@ -914,7 +916,8 @@ AG_HD void pgs_side_apply(const SimDev& S, int e, float* sm, int stride, const P
   }
 }
 
-AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm, int stride) {
+template <int LANES>
+AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm) {
   const int N = S.N;
   const int ND = S.ND;
   const PgsLayout L = pgs_layout(S);
@@ -923,11 +926,15 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm, int st
   for (int i = 0; i < nvel; i++) SMF(L.o_dv + i) = 0.f;
   for (int i = 0; i < 3 * S.nf; i++) SMF(L.o_fc + i) = S.fcom[(size_t)i * N + e];
   for (int i = 0; i < 6 * S.nf; i++) SMF(L.o_fi + i) = S.fIinv[(size_t)i * N + e];
+  for (int i = 0; i < S.nf; i++) SMF(L.o_fm + i) = AG_LDG(S.free_invm + i);
   for (int i = 0; i < ND * ND; i++) SMF(L.o_mi + i) = S.Minv[(size_t)i * N + e];
   int cnt = S.c_count[e]; if (cnt > S.maxc) cnt = S.maxc;
   for (int i = 0; i < 3 * cnt; i++) SMF(L.o_lam + i) = 0.f;
-  for (int r = 0; r < 3 * ND; r++) {      // dof rows: lambda, rhs, dinv
-    SMF(L.o_dr + 3 * r) = 0.f; SMF(L.o_dr + 3 * r + 1) = S.dr_rhs[(size_t)r * N + e]; SMF(L.o_dr + 3 * r + 2) = S.dr_dinv[(size_t)r * N + e];
+  for (int r = 0; r < 3 * ND; r++) {      // dof rows: lambda, rhs, dinv, lo, hi
+    int d = r % ND;
+    float hi = (r / ND == 2) ? S.motor_maxf[AG_LDG(S.dl_link + d)] * S.dt : 1e30f;
+    SMF(L.o_dr + 5 * r) = 0.f; SMF(L.o_dr + 5 * r + 1) = S.dr_rhs[(size_t)r * N + e]; SMF(L.o_dr + 5 * r + 2) = S.dr_dinv[(size_t)r * N + e];
+    SMF(L.o_dr + 5 * r + 3) = (r / ND == 2) ? -hi : 0.f; SMF(L.o_dr + 5 * r + 4) = hi;
   }
   const int GRW = 16 + 2 * ND;
   for (int r = 0; r < S.ngr; r++) {       // fixed-constraint rows: 16 fields (GR_LAM reused as lambda, PAD0/1 = refs) + art sides
@@ -974,17 +981,16 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm, int st
       used = it + 1;
       // joint limits (lower, upper) then motors: J = +-e_d
       for (int r = 0; r < 3 * ND; r++) {
-        float dinv = SMF(L.o_dr + 3 * r + 2);
+        float dinv = SMF(L.o_dr + 5 * r + 2);
         if (dinv == 0.f) continue;
         int d = r % ND; int kindr = r / ND;
         float sgn = kindr == 1 ? -1.f : 1.f;
-        float lam = SMF(L.o_dr + 3 * r);
-        float dl = SMF(L.o_dr + 3 * r + 1) - sgn * SMF(L.o_dv + d) * dinv;
-        float lo, hi;
-        if (kindr == 2) { hi = S.motor_maxf[AG_LDG(S.dl_link + d)] * S.dt; lo = -hi; } else { lo = 0.f; hi = 1e30f; }
+        float lam = SMF(L.o_dr + 5 * r);
+        float dl = SMF(L.o_dr + 5 * r + 1) - sgn * SMF(L.o_dv + d) * dinv;
+        float lo = SMF(L.o_dr + 5 * r + 3), hi = SMF(L.o_dr + 5 * r + 4);
         float sum = lam + dl;
         if (sum < lo) { dl = lo - lam; sum = lo; } else if (sum > hi) { dl = hi - lam; sum = hi; }
-        SMF(L.o_dr + 3 * r) = sum;
+        SMF(L.o_dr + 5 * r) = sum;
         int a = AG_LDG(S.dl_art + d), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
         float sdl = sgn * dl;
         for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += SMF(L.o_mi + (d0 + i) * ND + d) * sdl;
@@ -1001,36 +1007,65 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm, int st
         bool aArt = (refA & 3) == 2;      // which side owns the staged articulated rows
         const int* rf = S.gr_ref + (size_t)r * 4 * N + e;
         int asB = (!aArt || (refB & 3) != 2) ? -1 : AG_LDG(rf + 3 * (size_t)N);
-        float jv = pgs_side_jv(S, e, sm, stride, L, refA, -1, aArt ? o + 16 : -1, lin, aA) +
-                   pgs_side_jv(S, e, sm, stride, L, refB, asB, (!aArt && (refB & 3) == 2) ? o + 16 : -1, -lin, -aB);
+        float jv = pgs_side_jv<LANES>(S, e, sm, L, refA, -1, aArt ? o + 16 : -1, lin, aA) +
+                   pgs_side_jv<LANES>(S, e, sm, L, refB, asB, (!aArt && (refB & 3) == 2) ? o + 16 : -1, -lin, -aB);
         float lam = SMF(o + GR_LAM);
         float dl = SMF(o + GR_RHS) - jv * dinv;
         float lo = SMF(o + GR_LO), hi = SMF(o + GR_HI);
         float sum = lam + dl;
         if (sum < lo) { dl = lo - lam; sum = lo; } else if (sum > hi) { dl = hi - lam; sum = hi; }
         SMF(o + GR_LAM) = sum;
-        pgs_side_apply(S, e, sm, stride, L, refA, -1, aArt ? o + 16 + ND : -1, lin, aA, dl);
-        pgs_side_apply(S, e, sm, stride, L, refB, asB, (!aArt && (refB & 3) == 2) ? o + 16 + ND : -1, -lin, -aB, dl);
+        pgs_side_apply<LANES>(S, e, sm, L, refA, -1, aArt ? o + 16 + ND : -1, lin, aA, dl);
+        pgs_side_apply<LANES>(S, e, sm, L, refB, asB, (!aArt && (refB & 3) == 2) ? o + 16 + ND : -1, -lin, -aB, dl);
         resid = fmaxf(resid, dl * dl);
       }
-      // contact normals
+      // contact normals.  Free-body sides are held in registers for the whole row (one LDS round for the
+      // velocities, one for the inverse inertia, one STS round) instead of read-modify-write per component.
       for (int s = 0; s < cnt; s++) {
         int o = L.o_cr + s * PGS_CREC;
         float dinv = SMF(o + 10);
         if (dinv == 0.f) continue;
-        int refA = f2i_bits(SMF(o + 16)), refB = f2i_bits(SMF(o + 17)), asA = f2i_bits(SMF(o + 18)), asB = f2i_bits(SMF(o + 19));
+        int refA = f2i_bits(SMF(o + 16)), refB = f2i_bits(SMF(o + 17));
         f3 n(SMF(o), SMF(o + 1), SMF(o + 2));
-        f3 aA = cross(f3(SMF(o + 3), SMF(o + 4), SMF(o + 5)), n), aB = cross(f3(SMF(o + 6), SMF(o + 7), SMF(o + 8)), n);
-        float jv = pgs_side_jv(S, e, sm, stride, L, refA, asA, -1, n, aA) + pgs_side_jv(S, e, sm, stride, L, refB, asB, -1, -n, -aB);
+        bool fA = (refA & 3) == 1, fB = (refB & 3) == 1;
+        int oA = L.o_dv + ND + 6 * (refA >> 2), oB = L.o_dv + ND + 6 * (refB >> 2);
+        f3 vlA, vaA, vlB, vaB, aA, aB;
+        float jv = 0.f;
+        if (fA) {
+          vlA = f3(SMF(oA), SMF(oA + 1), SMF(oA + 2)); vaA = f3(SMF(oA + 3), SMF(oA + 4), SMF(oA + 5));
+          aA = cross(f3(SMF(o + 3), SMF(o + 4), SMF(o + 5)), n);
+          jv += dot(n, vlA) + dot(aA, vaA);
+        } else if ((refA & 3) == 2) jv += pgs_side_jv<LANES>(S, e, sm, L, refA, f2i_bits(SMF(o + 18)), -1, n, f3());
+        if (fB) {
+          vlB = f3(SMF(oB), SMF(oB + 1), SMF(oB + 2)); vaB = f3(SMF(oB + 3), SMF(oB + 4), SMF(oB + 5));
+          aB = cross(f3(SMF(o + 6), SMF(o + 7), SMF(o + 8)), n);
+          jv -= dot(n, vlB) + dot(aB, vaB);
+        } else if ((refB & 3) == 2) jv += pgs_side_jv<LANES>(S, e, sm, L, refB, f2i_bits(SMF(o + 19)), -1, -n, f3());
         float lam = SMF(L.o_lam + 3 * s);
         float dl = SMF(o + 9) - jv * dinv;
         float sum = lam + dl;
         if (sum < 0.f) { dl = -lam; sum = 0.f; }
         SMF(L.o_lam + 3 * s) = sum;
-        pgs_side_apply(S, e, sm, stride, L, refA, asA, -1, n, aA, dl); pgs_side_apply(S, e, sm, stride, L, refB, asB, -1, -n, -aB, dl);
+        if (fA) {
+          int fi = L.o_fi + 6 * (refA >> 2);
+          s3 Ii; Ii.xx = SMF(fi); Ii.yy = SMF(fi + 1); Ii.zz = SMF(fi + 2); Ii.xy = SMF(fi + 3); Ii.xz = SMF(fi + 4); Ii.yz = SMF(fi + 5);
+          float k = SMF(L.o_fm + (refA >> 2)) * dl;
+          f3 ia = mul(Ii, aA);
+          SMF(oA) = vlA.x + n.x * k; SMF(oA + 1) = vlA.y + n.y * k; SMF(oA + 2) = vlA.z + n.z * k;
+          SMF(oA + 3) = vaA.x + ia.x * dl; SMF(oA + 4) = vaA.y + ia.y * dl; SMF(oA + 5) = vaA.z + ia.z * dl;
+        } else if ((refA & 3) == 2) pgs_side_apply<LANES>(S, e, sm, L, refA, f2i_bits(SMF(o + 18)), -1, n, f3(), dl);
+        if (fB) {
+          int fi = L.o_fi + 6 * (refB >> 2);
+          s3 Ii; Ii.xx = SMF(fi); Ii.yy = SMF(fi + 1); Ii.zz = SMF(fi + 2); Ii.xy = SMF(fi + 3); Ii.xz = SMF(fi + 4); Ii.yz = SMF(fi + 5);
+          float k = SMF(L.o_fm + (refB >> 2)) * dl;
+          f3 ia = mul(Ii, aB);
+          SMF(oB) = vlB.x - n.x * k; SMF(oB + 1) = vlB.y - n.y * k; SMF(oB + 2) = vlB.z - n.z * k;
+          SMF(oB + 3) = vaB.x - ia.x * dl; SMF(oB + 4) = vaB.y - ia.y * dl; SMF(oB + 5) = vaB.z - ia.z * dl;
+        } else if ((refB & 3) == 2) pgs_side_apply<LANES>(S, e, sm, L, refB, f2i_bits(SMF(o + 19)), -1, -n, f3(), dl);
         resid = fmaxf(resid, dl * dl);
       }
-      // friction (two directions per contact, cone or pyramid)
+      // friction (two directions per contact, cone or pyramid): both directions share one load / store
+      // round of the two bodies' velocities
       for (int s = 0; s < cnt; s++) {
         int o = L.o_cr + s * PGS_CREC;
         if (SMF(o + 10) == 0.f) continue;
@@ -1040,10 +1075,28 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm, int st
         int refA = f2i_bits(SMF(o + 16)), refB = f2i_bits(SMF(o + 17)), asA = f2i_bits(SMF(o + 18)), asB = f2i_bits(SMF(o + 19));
         f3 n(SMF(o), SMF(o + 1), SMF(o + 2));
         f3 t1, t2; plane_space(n, t1, t2);
-        f3 rA(SMF(o + 3), SMF(o + 4), SMF(o + 5)), rB(SMF(o + 6), SMF(o + 7), SMF(o + 8));
-        f3 a1A = cross(rA, t1), a1B = cross(rB, t1), a2A = cross(rA, t2), a2B = cross(rB, t2);
-        float jv1 = pgs_side_jv(S, e, sm, stride, L, refA, asA + 1, -1, t1, a1A) + pgs_side_jv(S, e, sm, stride, L, refB, asB + 1, -1, -t1, -a1B);
-        float jv2 = pgs_side_jv(S, e, sm, stride, L, refA, asA + 2, -1, t2, a2A) + pgs_side_jv(S, e, sm, stride, L, refB, asB + 2, -1, -t2, -a2B);
+        bool fA = (refA & 3) == 1, fB = (refB & 3) == 1;
+        int oA = L.o_dv + ND + 6 * (refA >> 2), oB = L.o_dv + ND + 6 * (refB >> 2);
+        f3 vlA, vaA, vlB, vaB, a1A, a2A, a1B, a2B;
+        float jv1 = 0.f, jv2 = 0.f;
+        if (fA) {
+          vlA = f3(SMF(oA), SMF(oA + 1), SMF(oA + 2)); vaA = f3(SMF(oA + 3), SMF(oA + 4), SMF(oA + 5));
+          f3 rA(SMF(o + 3), SMF(o + 4), SMF(o + 5));
+          a1A = cross(rA, t1); a2A = cross(rA, t2);
+          jv1 += dot(t1, vlA) + dot(a1A, vaA); jv2 += dot(t2, vlA) + dot(a2A, vaA);
+        } else if ((refA & 3) == 2) {
+          jv1 += pgs_side_jv<LANES>(S, e, sm, L, refA, asA + 1, -1, t1, f3()); jv2 += pgs_side_jv<LANES>(S, e, sm, L, refA, asA + 2, -1, t2, f3());
+        }
+        if (fB) {
+          vlB = f3(SMF(oB), SMF(oB + 1), SMF(oB + 2)); vaB = f3(SMF(oB + 3), SMF(oB + 4), SMF(oB + 5));
+          f3 rB(SMF(o + 6), SMF(o + 7), SMF(o + 8));
+          a1B = cross(rB, t1); a2B = cross(rB, t2);
+          jv1 -= dot(t1, vlB) + dot(a1B, vaB); jv2 -= dot(t2, vlB) + dot(a2B, vaB);
+        } else if ((refB & 3) == 2) {
+          jv1 += pgs_side_jv<LANES>(S, e, sm, L, refB, asB + 1, -1, -t1, f3()); jv2 += pgs_side_jv<LANES>(S, e, sm, L, refB, asB + 2, -1, -t2, f3());
+        }
+        // NOTE: t1 and t2 are solved as one block against the same velocities (block Gauss-Seidel over the
+        // pair), exactly as the oracle does
         float s1 = l1 + SMF(o + 11) - jv1 * SMF(o + 12);
         float s2 = l2 + SMF(o + 13) - jv2 * SMF(o + 14);
         if (S.cone) {
@@ -1052,8 +1105,28 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm, int st
         } else { s1 = clampf(s1, -lim, lim); s2 = clampf(s2, -lim, lim); }
         float d1 = s1 - l1, d2 = s2 - l2;
         SMF(L.o_lam + 3 * s + 1) = s1; SMF(L.o_lam + 3 * s + 2) = s2;
-        pgs_side_apply(S, e, sm, stride, L, refA, asA + 1, -1, t1, a1A, d1); pgs_side_apply(S, e, sm, stride, L, refB, asB + 1, -1, -t1, -a1B, d1);
-        pgs_side_apply(S, e, sm, stride, L, refA, asA + 2, -1, t2, a2A, d2); pgs_side_apply(S, e, sm, stride, L, refB, asB + 2, -1, -t2, -a2B, d2);
+        if (fA) {
+          int fi = L.o_fi + 6 * (refA >> 2);
+          s3 Ii; Ii.xx = SMF(fi); Ii.yy = SMF(fi + 1); Ii.zz = SMF(fi + 2); Ii.xy = SMF(fi + 3); Ii.xz = SMF(fi + 4); Ii.yz = SMF(fi + 5);
+          float im = SMF(L.o_fm + (refA >> 2));
+          f3 ia = mul(Ii, a1A * d1 + a2A * d2);
+          f3 dl_ = (t1 * d1 + t2 * d2) * im;
+          SMF(oA) = vlA.x + dl_.x; SMF(oA + 1) = vlA.y + dl_.y; SMF(oA + 2) = vlA.z + dl_.z;
+          SMF(oA + 3) = vaA.x + ia.x; SMF(oA + 4) = vaA.y + ia.y; SMF(oA + 5) = vaA.z + ia.z;
+        } else if ((refA & 3) == 2) {
+          pgs_side_apply<LANES>(S, e, sm, L, refA, asA + 1, -1, t1, f3(), d1); pgs_side_apply<LANES>(S, e, sm, L, refA, asA + 2, -1, t2, f3(), d2);
+        }
+        if (fB) {
+          int fi = L.o_fi + 6 * (refB >> 2);
+          s3 Ii; Ii.xx = SMF(fi); Ii.yy = SMF(fi + 1); Ii.zz = SMF(fi + 2); Ii.xy = SMF(fi + 3); Ii.xz = SMF(fi + 4); Ii.yz = SMF(fi + 5);
+          float im = SMF(L.o_fm + (refB >> 2));
+          f3 ia = mul(Ii, a1B * d1 + a2B * d2);
+          f3 dl_ = (t1 * d1 + t2 * d2) * im;
+          SMF(oB) = vlB.x - dl_.x; SMF(oB + 1) = vlB.y - dl_.y; SMF(oB + 2) = vlB.z - dl_.z;
+          SMF(oB + 3) = vaB.x - ia.x; SMF(oB + 4) = vaB.y - ia.y; SMF(oB + 5) = vaB.z - ia.z;
+        } else if ((refB & 3) == 2) {
+          pgs_side_apply<LANES>(S, e, sm, L, refB, asB + 1, -1, -t1, f3(), d1); pgs_side_apply<LANES>(S, e, sm, L, refB, asB + 2, -1, -t2, f3(), d2);
+        }
         resid = fmaxf(resid, fmaxf(d1 * d1, d2 * d2));
       }
       if (S.resid_thr > 0.f && resid <= S.resid_thr) done = true;
@@ -1067,7 +1140,7 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm, int st
   // ---- write back
   S.iters_used[e] = used;
   for (int i = 0; i < nvel; i++) S.dv[(size_t)i * N + e] = SMF(L.o_dv + i);
-  for (int r = 0; r < 3 * ND; r++) S.dr_lam[(size_t)r * N + e] = SMF(L.o_dr + 3 * r);
+  for (int r = 0; r < 3 * ND; r++) S.dr_lam[(size_t)r * N + e] = SMF(L.o_dr + 5 * r);
   for (int r = 0; r < S.ngr; r++) S.gr_data[((size_t)r * 16 + GR_LAM) * N + e] = SMF(L.o_gr + r * GRW + GR_LAM);
   for (int s = 0; s < cnt; s++) {
     cf_st(S.s_data, s, CF_LAM_N, N, e, SMF(L.o_lam + 3 * s));

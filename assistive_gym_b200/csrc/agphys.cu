@@ -44,17 +44,19 @@ AG_KERNEL(k_sort, sort_body)
 AG_KERNEL(k_dyn, dyn_body)
 AG_KERNEL(k_rows, rows_body)
 AG_KERNEL(k_crows, crows_body)
-// k_pgs: one warp per block, lane-strided dynamic shared memory (see pgs_body)
+// k_pgs: a few envs per CTA, lane-strided dynamic shared memory (see pgs_body); LANES is a template
+// parameter so that every shared-memory offset folds into the LDS/STS immediate
 #ifndef AG_CPU_EMU
-__global__ void __launch_bounds__(32) k_pgs(SimDev S, KP p) {
+template <int LANES>
+__global__ void __launch_bounds__(LANES) k_pgs(SimDev S, KP p) {
   extern __shared__ float pgs_smem[];
-  int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid < p.n) pgs_body(tid, S, p, pgs_smem + threadIdx.x, blockDim.x);
+  int tid = blockIdx.x * LANES + threadIdx.x;
+  if (tid < p.n) pgs_body<LANES>(tid, S, p, pgs_smem + threadIdx.x);
 }
 #else
 static void k_pgs(SimDev S, KP p) {
   std::vector<float> buf((size_t)pgs_layout(S).total);
-  for (int tid = 0; tid < p.n; tid++) pgs_body(tid, S, p, buf.data(), 1);
+  for (int tid = 0; tid < p.n; tid++) pgs_body<1>(tid, S, p, buf.data());
 }
 #endif
 AG_KERNEL(k_integrate, integrate_body)
@@ -393,14 +395,18 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
     // shorten the per-warp iteration count (max over fewer envs) and reduce divergence.
     const char* lp = getenv("AG_PGS_LANES");
     s->pgs_lanes = lp ? atoi(lp) : 4;
-    if (s->pgs_lanes < 1 || s->pgs_lanes > 32) s->pgs_lanes = 4;
+    if (s->pgs_lanes != 1 && s->pgs_lanes != 2 && s->pgs_lanes != 4 && s->pgs_lanes != 8 && s->pgs_lanes != 32) s->pgs_lanes = 4;
     size_t smem = (size_t)pgs_layout(S).total * s->pgs_lanes * sizeof(float);
-    if (smem > 227 * 1024) { g_err = "PGS shared-memory footprint exceeds 227 KB per CTA: lower max_contacts"; ag_destroy(s); return nullptr; }
-    if (cudaFuncSetAttribute(k_pgs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { g_err = "cudaFuncSetAttribute(k_pgs) failed"; ag_destroy(s); return nullptr; }
-    // keep most of the unified L1/shared array as L1: the row constants are re-read every iteration
-    int blocks_per_sm = std::max(1, (N / s->pgs_lanes + 147) / 148);
-    int carve = (int)std::min<size_t>(100, (smem * blocks_per_sm * 100 + 228 * 1024 - 1) / (228 * 1024) + 5);
-    cudaFuncSetAttribute(k_pgs, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    if (smem > 227 * 1024) { g_err = "PGS shared-memory footprint exceeds 227 KB per CTA: lower max_contacts or AG_PGS_LANES"; ag_destroy(s); return nullptr; }
+    cudaError_t ce = cudaSuccess;
+    switch (s->pgs_lanes) {
+      case 1: ce = cudaFuncSetAttribute(k_pgs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
+      case 2: ce = cudaFuncSetAttribute(k_pgs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
+      case 4: ce = cudaFuncSetAttribute(k_pgs<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
+      case 8: ce = cudaFuncSetAttribute(k_pgs<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
+      default: ce = cudaFuncSetAttribute(k_pgs<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
+    }
+    if (ce != cudaSuccess) { g_err = "cudaFuncSetAttribute(k_pgs) failed"; ag_destroy(s); return nullptr; }
   }
 #endif
   // defaults: friction from the template, all bodies active, identity quaternions
@@ -586,7 +592,14 @@ static void substep(AgSim* s) {
     size_t smem = (size_t)pgs_layout(S).total * L * sizeof(float);
     int ps = s->profiling ? prof_slot(s, "k_pgs") : -1;
     if (ps >= 0) prof_mark(s, ps, true);
-    k_pgs<<<(N + L - 1) / L, L, smem, s->stream>>>(S, kp);
+    dim3 grid((N + L - 1) / L);
+    switch (L) {
+      case 1: k_pgs<1><<<grid, 1, smem, s->stream>>>(S, kp); break;
+      case 2: k_pgs<2><<<grid, 2, smem, s->stream>>>(S, kp); break;
+      case 4: k_pgs<4><<<grid, 4, smem, s->stream>>>(S, kp); break;
+      case 8: k_pgs<8><<<grid, 8, smem, s->stream>>>(S, kp); break;
+      default: k_pgs<32><<<grid, 32, smem, s->stream>>>(S, kp); break;
+    }
     if (ps >= 0) prof_mark(s, ps, false);
     s->launches++;
   }
