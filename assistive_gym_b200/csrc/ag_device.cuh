@@ -862,14 +862,14 @@ AG_HDN inline void crows_body(int tid, const SimDev& S, const KP&) {
 // the articulated M^-1, all row constants (contacts, dof rows, fixed-constraint rows incl. their
 // articulated Jacobian sides) and all impulses.  Only the rare articulated sides of contact rows stay
 // in global memory.  Layout (floats per lane):
-//   [dv: ND+6nf][fcom: 3nf][fIinv: 6nf][invm: nf][Minv: ND*ND][lam: 3*maxc][dr: 5*(3ND)][gr: ngr*(16+2ND)][crec: 20*maxc]
+//   [dv: ND+6nf][fcom: 3nf][fIinv: 6nf][invm: nf][Minv: ND*ND][lam: 3*maxc][dr: 5*(3ND)][gr: ngr*(16+2ND)][crec: 20*maxc][art sides: nas*2ND]
 #define PGS_CREC 20
-struct PgsLayout { int o_dv, o_fc, o_fi, o_fm, o_mi, o_lam, o_dr, o_gr, o_cr, total; };
+struct PgsLayout { int o_dv, o_fc, o_fi, o_fm, o_mi, o_lam, o_dr, o_gr, o_cr, o_as, total; };
 AG_HD PgsLayout pgs_layout(const SimDev& S) {
   PgsLayout L;
   L.o_dv = 0; L.o_fc = L.o_dv + S.ND + 6 * S.nf; L.o_fi = L.o_fc + 3 * S.nf; L.o_fm = L.o_fi + 6 * S.nf; L.o_mi = L.o_fm + S.nf;
   L.o_lam = L.o_mi + S.ND * S.ND; L.o_dr = L.o_lam + 3 * S.maxc; L.o_gr = L.o_dr + 15 * S.ND;
-  L.o_cr = L.o_gr + S.ngr * (16 + 2 * S.ND); L.total = L.o_cr + PGS_CREC * S.maxc;
+  L.o_cr = L.o_gr + S.ngr * (16 + 2 * S.ND); L.o_as = L.o_cr + PGS_CREC * S.maxc; L.total = L.o_as + S.nas * 2 * S.ND;
   return L;
 }
 #define SMF(i) sm[(i) * LANES]
@@ -886,11 +886,8 @@ AG_HD float pgs_side_jv(const SimDev& S, int e, const float* sm, const PgsLayout
   } else if (kind == 2) {
     int a = AG_LDG(S.dl_art + idx), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
     float t = 0.f;
-    if (artJ >= 0) { for (int i = 0; i < nd; i++) t += SMF(artJ + i) * SMF(L.o_dv + d0 + i); }
-    else {
-      const float* J = S.as_J + (size_t)as * AG_MAXND * S.N + e;
-      for (int i = 0; i < nd; i++) t += AG_LDG(J + (size_t)i * S.N) * SMF(L.o_dv + d0 + i);
-    }
+    if (artJ < 0) artJ = L.o_as + as * 2 * S.ND;          // staged copy of as_J[as]
+    for (int i = 0; i < nd; i++) t += SMF(artJ + i) * SMF(L.o_dv + d0 + i);
     return t;
   }
   return 0.f;
@@ -908,11 +905,8 @@ AG_HD void pgs_side_apply(const SimDev& S, int e, float* sm, const PgsLayout& L,
     SMF(o + 3) += ia.x * dl; SMF(o + 4) += ia.y * dl; SMF(o + 5) += ia.z * dl;
   } else if (kind == 2) {
     int a = AG_LDG(S.dl_art + idx), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
-    if (artM >= 0) { for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += SMF(artM + i) * dl; }
-    else {
-      const float* M = S.as_MiJ + (size_t)as * AG_MAXND * S.N + e;
-      for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += AG_LDG(M + (size_t)i * S.N) * dl;
-    }
+    if (artM < 0) artM = L.o_as + as * 2 * S.ND + S.ND;   // staged copy of as_MiJ[as]
+    for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += SMF(artM + i) * dl;
   }
 }
 
@@ -922,6 +916,9 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm) {
   const int ND = S.ND;
   const PgsLayout L = pgs_layout(S);
   const int nvel = ND + 6 * S.nf;
+#if defined(__CUDA_ARCH__)
+  long long t_begin = clock64();
+#endif
   // ---- stage the per-env solver state and all row constants into shared memory
   for (int i = 0; i < nvel; i++) SMF(L.o_dv + i) = 0.f;
   for (int i = 0; i < 3 * S.nf; i++) SMF(L.o_fc + i) = S.fcom[(size_t)i * N + e];
@@ -969,6 +966,14 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm) {
     SMF(o + 13) = c[(size_t)CF_RHS_T2 * N]; SMF(o + 14) = c[(size_t)CF_DINV_T2 * N];
     SMF(o + 15) = c[(size_t)CF_MU * N];
     SMF(o + 16) = i2f_bits(refA); SMF(o + 17) = i2f_bits(refB); SMF(o + 18) = i2f_bits(asA); SMF(o + 19) = i2f_bits(asB);
+  }
+  {                                        // articulated row sides allocated by k_rows / k_crows
+    int nas_used = S.as_count[e]; if (nas_used > S.nas) nas_used = S.nas;
+    for (int a = 0; a < nas_used; a++)
+      for (int i = 0; i < ND; i++) {
+        SMF(L.o_as + a * 2 * ND + i) = S.as_J[((size_t)a * AG_MAXND + i) * N + e];
+        SMF(L.o_as + a * 2 * ND + ND + i) = S.as_MiJ[((size_t)a * AG_MAXND + i) * N + e];
+      }
   }
   int used = 0;
   bool done = false;
@@ -1139,6 +1144,9 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm) {
   }
   // ---- write back
   S.iters_used[e] = used;
+#if defined(__CUDA_ARCH__)
+  S.pgs_cycles[e] = (int)(clock64() - t_begin);
+#endif
   for (int i = 0; i < nvel; i++) S.dv[(size_t)i * N + e] = SMF(L.o_dv + i);
   for (int r = 0; r < 3 * ND; r++) S.dr_lam[(size_t)r * N + e] = SMF(L.o_dr + 5 * r);
   for (int r = 0; r < S.ngr; r++) S.gr_data[((size_t)r * 16 + GR_LAM) * N + e] = SMF(L.o_gr + r * GRW + GR_LAM);

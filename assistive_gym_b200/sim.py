@@ -154,6 +154,11 @@ class BatchSim:
         self._ck(self.lib.ag_get_solver_stats(self.h, _p(c), _p(it)))
         return c, it
 
+    def pgs_cycles(self):
+        c = np.zeros(self.n, dtype=np.int32)
+        self._ck(self.lib.ag_get_pgs_cycles(self.h, _p(c)))
+        return c
+
     def profile_enable(self, on=True):
         self._ck(self.lib.ag_profile_enable(self.h, int(bool(on))))
 

@@ -211,7 +211,9 @@ int      ag_profile_enable(AgSim* sim, int on);
 int      ag_profile_get(AgSim* sim, int max_names, char* names, int name_stride, float* total_ms, int32_t* counts);
 int      ag_overflow_count(AgSim* sim);
 /* per-env contact count and PGS iterations used in the last substep (host int32[N] buffers, may be NULL) */
-int      ag_get_solver_stats(AgSim* sim, int32_t* contacts, int32_t* iters);           /* envs that exceeded the contact budget last step */
+int      ag_get_solver_stats(AgSim* sim, int32_t* contacts, int32_t* iters);
+/* SM cycles each env's lane spent inside the PGS kernel of the last substep (load-balance diagnostic) */
+int      ag_get_pgs_cycles(AgSim* sim, int32_t* cycles);           /* envs that exceeded the contact budget last step */
 
 #ifdef __cplusplus
 }
