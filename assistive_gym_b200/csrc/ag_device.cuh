@@ -862,14 +862,19 @@ AG_HDN inline void crows_body(int tid, const SimDev& S, const KP&) {
 // the articulated M^-1, all row constants (contacts, dof rows, fixed-constraint rows incl. their
 // articulated Jacobian sides) and all impulses.  Only the rare articulated sides of contact rows stay
 // in global memory.  Layout (floats per lane):
-//   [dv: ND+6nf][fcom: 3nf][fIinv: 6nf][invm: nf][Minv: ND*ND][lam: 3*maxc][dr: 5*(3ND)][gr: ngr*(16+2ND)][crec: 56*maxc][art sides: nas*2ND]
+//   [dv: ND+6nf][fcom: 3nf][fIinv: 6nf][invm: nf][Minv: ND*ND][lam: 3*maxc][dr: 5*(3ND)][gr: ngr*(16+2ND)][crec: 56*ccap][scratch: 56][art sides: acap*2ND]
 #define PGS_CREC 56
-struct PgsLayout { int o_dv, o_fc, o_fi, o_fm, o_mi, o_lam, o_dr, o_gr, o_cr, o_as, total; };
+struct PgsLayout { int o_dv, o_fc, o_fi, o_fm, o_mi, o_lam, o_dr, o_gr, o_cr, o_sc, o_as, ccap, acap, total; };
 AG_HD PgsLayout pgs_layout(const SimDev& S) {
   PgsLayout L;
   L.o_dv = 0; L.o_fc = L.o_dv + S.ND + 6 * S.nf; L.o_fi = L.o_fc + 3 * S.nf; L.o_fm = L.o_fi + 6 * S.nf; L.o_mi = L.o_fm + S.nf;
   L.o_lam = L.o_mi + S.ND * S.ND; L.o_dr = L.o_lam + 3 * S.maxc; L.o_gr = L.o_dr + 15 * S.ND;
-  L.o_cr = L.o_gr + S.ngr * (16 + 2 * S.ND); L.o_as = L.o_cr + PGS_CREC * S.maxc; L.total = L.o_as + S.nas * 2 * S.ND;
+  // staging caps: contact records / articulated sides beyond the cap (rare: p99 of contacts per env is ~37)
+  // are kept in global memory and copied through a one-record scratch, so that the shared-memory
+  // footprint per env stays small enough for >10 resident CTAs per SM
+  L.ccap = S.maxc < S.pgs_ccap ? S.maxc : S.pgs_ccap; L.acap = S.nas < S.pgs_acap ? S.nas : S.pgs_acap;
+  L.o_cr = L.o_gr + S.ngr * (16 + 2 * S.ND); L.o_sc = L.o_cr + PGS_CREC * L.ccap; L.o_as = L.o_sc + PGS_CREC;
+  L.total = L.o_as + L.acap * 2 * S.ND;
   return L;
 }
 #define SMF(i) sm[(i) * LANES]
@@ -886,8 +891,12 @@ AG_HD float pgs_side_jv(const SimDev& S, int e, const float* sm, const PgsLayout
   } else if (kind == 2) {
     int a = AG_LDG(S.dl_art + idx), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
     float t = 0.f;
-    if (artJ < 0) artJ = L.o_as + as * 2 * S.ND;          // staged copy of as_J[as]
-    for (int i = 0; i < nd; i++) t += SMF(artJ + i) * SMF(L.o_dv + d0 + i);
+    if (artJ < 0 && as < L.acap) artJ = L.o_as + as * 2 * S.ND;          // staged copy of as_J[as]
+    if (artJ >= 0) { for (int i = 0; i < nd; i++) t += SMF(artJ + i) * SMF(L.o_dv + d0 + i); }
+    else {
+      const float* J = S.as_J + (size_t)as * AG_MAXND * S.N + e;
+      for (int i = 0; i < nd; i++) t += AG_LDG(J + (size_t)i * S.N) * SMF(L.o_dv + d0 + i);
+    }
     return t;
   }
   return 0.f;
@@ -905,8 +914,12 @@ AG_HD void pgs_side_apply(const SimDev& S, int e, float* sm, const PgsLayout& L,
     SMF(o + 3) += ia.x * dl; SMF(o + 4) += ia.y * dl; SMF(o + 5) += ia.z * dl;
   } else if (kind == 2) {
     int a = AG_LDG(S.dl_art + idx), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
-    if (artM < 0) artM = L.o_as + as * 2 * S.ND + S.ND;   // staged copy of as_MiJ[as]
-    for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += SMF(artM + i) * dl;
+    if (artM < 0 && as < L.acap) artM = L.o_as + as * 2 * S.ND + S.ND;   // staged copy of as_MiJ[as]
+    if (artM >= 0) { for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += SMF(artM + i) * dl; }
+    else {
+      const float* M = S.as_MiJ + (size_t)as * AG_MAXND * S.N + e;
+      for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += AG_LDG(M + (size_t)i * S.N) * dl;
+    }
   }
 }
 
@@ -952,7 +965,8 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm) {
   // contact records: everything a row update needs, precomputed once (directions, r x dir, I^-1 (r x dir)):
   //  0 n, 3 t1, 6 t2 | per direction k (n,t1,t2) at 9+12k: aA(3) IaA(3) aB(3) IaB(3) | 45 rhs/dinv x3 | 51 mu | 52 refA refB asA asB
   for (int s = 0; s < cnt; s++) {
-    int o = L.o_cr + s * PGS_CREC;
+    const bool spill = s >= L.ccap;
+    int o = spill ? L.o_sc : L.o_cr + s * PGS_CREC;
     const float* c = S.s_data + (size_t)s * AG_CF * N + e;
     const int* rf = S.s_ref + (size_t)s * 4 * N + e;
     int refA = rf[0], refB = rf[N], asA = rf[2 * (size_t)N], asB = rf[3 * (size_t)N];
@@ -986,9 +1000,10 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm) {
     SMF(o + 49) = c[(size_t)CF_RHS_T2 * N]; SMF(o + 50) = c[(size_t)CF_DINV_T2 * N];
     SMF(o + 51) = c[(size_t)CF_MU * N];
     SMF(o + 52) = i2f_bits(refA); SMF(o + 53) = i2f_bits(refB); SMF(o + 54) = i2f_bits(asA); SMF(o + 55) = i2f_bits(asB);
+    if (spill) for (int i = 0; i < PGS_CREC; i++) S.pgs_spill[((size_t)(s - L.ccap) * PGS_CREC + i) * N + e] = SMF(o + i);
   }
   {                                        // articulated row sides allocated by k_rows / k_crows
-    int nas_used = S.as_count[e]; if (nas_used > S.nas) nas_used = S.nas;
+    int nas_used = S.as_count[e]; if (nas_used > L.acap) nas_used = L.acap;
     for (int a = 0; a < nas_used; a++)
       for (int i = 0; i < ND; i++) {
         SMF(L.o_as + a * 2 * ND + i) = S.as_J[((size_t)a * AG_MAXND + i) * N + e];
@@ -1048,6 +1063,7 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm) {
       // I^-1 (r x n) from the record, one STS round.
       for (int s = 0; s < cnt; s++) {
         int o = L.o_cr + s * PGS_CREC;
+        if (s >= L.ccap) { o = L.o_sc; for (int i = 0; i < PGS_CREC; i++) SMF(o + i) = S.pgs_spill[((size_t)(s - L.ccap) * PGS_CREC + i) * N + e]; }
         float dinv = SMF(o + 46);
         if (dinv == 0.f) continue;
         int refA = f2i_bits(SMF(o + 52)), refB = f2i_bits(SMF(o + 53));
@@ -1085,6 +1101,7 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm) {
       // the same velocities (as the oracle does), sharing one load / store round of the two bodies
       for (int s = 0; s < cnt; s++) {
         int o = L.o_cr + s * PGS_CREC;
+        if (s >= L.ccap) { o = L.o_sc; for (int i = 0; i < PGS_CREC; i++) SMF(o + i) = S.pgs_spill[((size_t)(s - L.ccap) * PGS_CREC + i) * N + e]; }
         if (SMF(o + 46) == 0.f) continue;
         float l1 = SMF(L.o_lam + 3 * s + 1), l2 = SMF(L.o_lam + 3 * s + 2);
         float lim = SMF(o + 51) * SMF(L.o_lam + 3 * s);
