@@ -862,19 +862,14 @@ AG_HDN inline void crows_body(int tid, const SimDev& S, const KP&) {
 // the articulated M^-1, all row constants (contacts, dof rows, fixed-constraint rows incl. their
 // articulated Jacobian sides) and all impulses.  Only the rare articulated sides of contact rows stay
 // in global memory.  Layout (floats per lane):
-//   [dv: ND+6nf][fcom: 3nf][fIinv: 6nf][invm: nf][Minv: ND*ND][lam: 3*maxc][dr: 5*(3ND)][gr: ngr*(16+2ND)][crec: 56*ccap][scratch: 56][art sides: acap*2ND]
-#define PGS_CREC 56
-struct PgsLayout { int o_dv, o_fc, o_fi, o_fm, o_mi, o_lam, o_dr, o_gr, o_cr, o_sc, o_as, ccap, acap, total; };
+//   [dv: ND+6nf][fcom: 3nf][fIinv: 6nf][invm: nf][Minv: ND*ND][lam: 3*maxc][dr: 5*(3ND)][gr: ngr*(16+2ND)][crec: 20*maxc][art sides: nas*2ND]
+#define PGS_CREC 20
+struct PgsLayout { int o_dv, o_fc, o_fi, o_fm, o_mi, o_lam, o_dr, o_gr, o_cr, o_as, total; };
 AG_HD PgsLayout pgs_layout(const SimDev& S) {
   PgsLayout L;
   L.o_dv = 0; L.o_fc = L.o_dv + S.ND + 6 * S.nf; L.o_fi = L.o_fc + 3 * S.nf; L.o_fm = L.o_fi + 6 * S.nf; L.o_mi = L.o_fm + S.nf;
   L.o_lam = L.o_mi + S.ND * S.ND; L.o_dr = L.o_lam + 3 * S.maxc; L.o_gr = L.o_dr + 15 * S.ND;
-  // staging caps: contact records / articulated sides beyond the cap (rare: p99 of contacts per env is ~37)
-  // are kept in global memory and copied through a one-record scratch, so that the shared-memory
-  // footprint per env stays small enough for >10 resident CTAs per SM
-  L.ccap = S.maxc < S.pgs_ccap ? S.maxc : S.pgs_ccap; L.acap = S.nas < S.pgs_acap ? S.nas : S.pgs_acap;
-  L.o_cr = L.o_gr + S.ngr * (16 + 2 * S.ND); L.o_sc = L.o_cr + PGS_CREC * L.ccap; L.o_as = L.o_sc + PGS_CREC;
-  L.total = L.o_as + L.acap * 2 * S.ND;
+  L.o_cr = L.o_gr + S.ngr * (16 + 2 * S.ND); L.o_as = L.o_cr + PGS_CREC * S.maxc; L.total = L.o_as + S.nas * 2 * S.ND;
   return L;
 }
 #define SMF(i) sm[(i) * LANES]
@@ -891,12 +886,8 @@ AG_HD float pgs_side_jv(const SimDev& S, int e, const float* sm, const PgsLayout
   } else if (kind == 2) {
     int a = AG_LDG(S.dl_art + idx), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
     float t = 0.f;
-    if (artJ < 0 && as < L.acap) artJ = L.o_as + as * 2 * S.ND;          // staged copy of as_J[as]
-    if (artJ >= 0) { for (int i = 0; i < nd; i++) t += SMF(artJ + i) * SMF(L.o_dv + d0 + i); }
-    else {
-      const float* J = S.as_J + (size_t)as * AG_MAXND * S.N + e;
-      for (int i = 0; i < nd; i++) t += AG_LDG(J + (size_t)i * S.N) * SMF(L.o_dv + d0 + i);
-    }
+    if (artJ < 0) artJ = L.o_as + as * 2 * S.ND;          // staged copy of as_J[as]
+    for (int i = 0; i < nd; i++) t += SMF(artJ + i) * SMF(L.o_dv + d0 + i);
     return t;
   }
   return 0.f;
@@ -914,12 +905,8 @@ AG_HD void pgs_side_apply(const SimDev& S, int e, float* sm, const PgsLayout& L,
     SMF(o + 3) += ia.x * dl; SMF(o + 4) += ia.y * dl; SMF(o + 5) += ia.z * dl;
   } else if (kind == 2) {
     int a = AG_LDG(S.dl_art + idx), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
-    if (artM < 0 && as < L.acap) artM = L.o_as + as * 2 * S.ND + S.ND;   // staged copy of as_MiJ[as]
-    if (artM >= 0) { for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += SMF(artM + i) * dl; }
-    else {
-      const float* M = S.as_MiJ + (size_t)as * AG_MAXND * S.N + e;
-      for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += AG_LDG(M + (size_t)i * S.N) * dl;
-    }
+    if (artM < 0) artM = L.o_as + as * 2 * S.ND + S.ND;   // staged copy of as_MiJ[as]
+    for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += SMF(artM + i) * dl;
   }
 }
 
@@ -962,48 +949,26 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm) {
       SMF(o + 16 + ND + i) = as >= 0 ? S.as_MiJ[((size_t)as * AG_MAXND + i) * N + e] : 0.f;
     }
   }
-  // contact records: everything a row update needs, precomputed once (directions, r x dir, I^-1 (r x dir)):
-  //  0 n, 3 t1, 6 t2 | per direction k (n,t1,t2) at 9+12k: aA(3) IaA(3) aB(3) IaB(3) | 45 rhs/dinv x3 | 51 mu | 52 refA refB asA asB
-  for (int s = 0; s < cnt; s++) {
-    const bool spill = s >= L.ccap;
-    int o = spill ? L.o_sc : L.o_cr + s * PGS_CREC;
+  for (int s = 0; s < cnt; s++) {         // contact records
+    int o = L.o_cr + s * PGS_CREC;
     const float* c = S.s_data + (size_t)s * AG_CF * N + e;
     const int* rf = S.s_ref + (size_t)s * 4 * N + e;
     int refA = rf[0], refB = rf[N], asA = rf[2 * (size_t)N], asB = rf[3 * (size_t)N];
     f3 pa(c[(size_t)CF_PAX * N], c[(size_t)CF_PAY * N], c[(size_t)CF_PAZ * N]);
     f3 pb(c[(size_t)CF_PBX * N], c[(size_t)CF_PBY * N], c[(size_t)CF_PBZ * N]);
-    f3 dir[3];
-    dir[0] = f3(c[(size_t)CF_NX * N], c[(size_t)CF_NY * N], c[(size_t)CF_NZ * N]);
-    plane_space(dir[0], dir[1], dir[2]);
-    f3 rA, rB; s3 IA, IB;
-    IA.xx = IA.yy = IA.zz = IA.xy = IA.xz = IA.yz = 0.f; IB = IA;
-    if ((refA & 3) == 1) {
-      int q = L.o_fc + 3 * (refA >> 2), fi = L.o_fi + 6 * (refA >> 2);
-      rA = f3(pa.x - SMF(q), pa.y - SMF(q + 1), pa.z - SMF(q + 2));
-      IA.xx = SMF(fi); IA.yy = SMF(fi + 1); IA.zz = SMF(fi + 2); IA.xy = SMF(fi + 3); IA.xz = SMF(fi + 4); IA.yz = SMF(fi + 5);
-    }
-    if ((refB & 3) == 1) {
-      int q = L.o_fc + 3 * (refB >> 2), fi = L.o_fi + 6 * (refB >> 2);
-      rB = f3(pb.x - SMF(q), pb.y - SMF(q + 1), pb.z - SMF(q + 2));
-      IB.xx = SMF(fi); IB.yy = SMF(fi + 1); IB.zz = SMF(fi + 2); IB.xy = SMF(fi + 3); IB.xz = SMF(fi + 4); IB.yz = SMF(fi + 5);
-    }
-    for (int k = 0; k < 3; k++) {
-      SMF(o + 3 * k) = dir[k].x; SMF(o + 3 * k + 1) = dir[k].y; SMF(o + 3 * k + 2) = dir[k].z;
-      f3 aA = cross(rA, dir[k]), aB = cross(rB, dir[k]);
-      f3 iA = mul(IA, aA), iB = mul(IB, aB);
-      int q = o + 9 + 12 * k;
-      SMF(q) = aA.x; SMF(q + 1) = aA.y; SMF(q + 2) = aA.z; SMF(q + 3) = iA.x; SMF(q + 4) = iA.y; SMF(q + 5) = iA.z;
-      SMF(q + 6) = aB.x; SMF(q + 7) = aB.y; SMF(q + 8) = aB.z; SMF(q + 9) = iB.x; SMF(q + 10) = iB.y; SMF(q + 11) = iB.z;
-    }
-    SMF(o + 45) = c[(size_t)CF_RHS_N * N]; SMF(o + 46) = c[(size_t)CF_DINV_N * N];
-    SMF(o + 47) = c[(size_t)CF_RHS_T1 * N]; SMF(o + 48) = c[(size_t)CF_DINV_T1 * N];
-    SMF(o + 49) = c[(size_t)CF_RHS_T2 * N]; SMF(o + 50) = c[(size_t)CF_DINV_T2 * N];
-    SMF(o + 51) = c[(size_t)CF_MU * N];
-    SMF(o + 52) = i2f_bits(refA); SMF(o + 53) = i2f_bits(refB); SMF(o + 54) = i2f_bits(asA); SMF(o + 55) = i2f_bits(asB);
-    if (spill) for (int i = 0; i < PGS_CREC; i++) S.pgs_spill[((size_t)(s - L.ccap) * PGS_CREC + i) * N + e] = SMF(o + i);
+    f3 rA, rB;
+    if ((refA & 3) == 1) { int q = L.o_fc + 3 * (refA >> 2); rA = f3(pa.x - SMF(q), pa.y - SMF(q + 1), pa.z - SMF(q + 2)); }
+    if ((refB & 3) == 1) { int q = L.o_fc + 3 * (refB >> 2); rB = f3(pb.x - SMF(q), pb.y - SMF(q + 1), pb.z - SMF(q + 2)); }
+    SMF(o) = c[(size_t)CF_NX * N]; SMF(o + 1) = c[(size_t)CF_NY * N]; SMF(o + 2) = c[(size_t)CF_NZ * N];
+    SMF(o + 3) = rA.x; SMF(o + 4) = rA.y; SMF(o + 5) = rA.z; SMF(o + 6) = rB.x; SMF(o + 7) = rB.y; SMF(o + 8) = rB.z;
+    SMF(o + 9) = c[(size_t)CF_RHS_N * N]; SMF(o + 10) = c[(size_t)CF_DINV_N * N];
+    SMF(o + 11) = c[(size_t)CF_RHS_T1 * N]; SMF(o + 12) = c[(size_t)CF_DINV_T1 * N];
+    SMF(o + 13) = c[(size_t)CF_RHS_T2 * N]; SMF(o + 14) = c[(size_t)CF_DINV_T2 * N];
+    SMF(o + 15) = c[(size_t)CF_MU * N];
+    SMF(o + 16) = i2f_bits(refA); SMF(o + 17) = i2f_bits(refB); SMF(o + 18) = i2f_bits(asA); SMF(o + 19) = i2f_bits(asB);
   }
   {                                        // articulated row sides allocated by k_rows / k_crows
-    int nas_used = S.as_count[e]; if (nas_used > L.acap) nas_used = L.acap;
+    int nas_used = S.as_count[e]; if (nas_used > S.nas) nas_used = S.nas;
     for (int a = 0; a < nas_used; a++)
       for (int i = 0; i < ND; i++) {
         SMF(L.o_as + a * 2 * ND + i) = S.as_J[((size_t)a * AG_MAXND + i) * N + e];
@@ -1059,75 +1024,86 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm) {
         pgs_side_apply<LANES>(S, e, sm, L, refB, asB, (!aArt && (refB & 3) == 2) ? o + 16 + ND : -1, -lin, -aB, dl);
         resid = fmaxf(resid, dl * dl);
       }
-      // contact normals.  Free-body sides: one LDS round for the two velocities, precomputed r x n and
-      // I^-1 (r x n) from the record, one STS round.
+      // contact normals.  Free-body sides are held in registers for the whole row (one LDS round for the
+      // velocities, one for the inverse inertia, one STS round) instead of read-modify-write per component.
       for (int s = 0; s < cnt; s++) {
         int o = L.o_cr + s * PGS_CREC;
-        if (s >= L.ccap) { o = L.o_sc; for (int i = 0; i < PGS_CREC; i++) SMF(o + i) = S.pgs_spill[((size_t)(s - L.ccap) * PGS_CREC + i) * N + e]; }
-        float dinv = SMF(o + 46);
+        float dinv = SMF(o + 10);
         if (dinv == 0.f) continue;
-        int refA = f2i_bits(SMF(o + 52)), refB = f2i_bits(SMF(o + 53));
+        int refA = f2i_bits(SMF(o + 16)), refB = f2i_bits(SMF(o + 17));
         f3 n(SMF(o), SMF(o + 1), SMF(o + 2));
         bool fA = (refA & 3) == 1, fB = (refB & 3) == 1;
         int oA = L.o_dv + ND + 6 * (refA >> 2), oB = L.o_dv + ND + 6 * (refB >> 2);
-        f3 vlA, vaA, vlB, vaB;
+        f3 vlA, vaA, vlB, vaB, aA, aB;
         float jv = 0.f;
         if (fA) {
           vlA = f3(SMF(oA), SMF(oA + 1), SMF(oA + 2)); vaA = f3(SMF(oA + 3), SMF(oA + 4), SMF(oA + 5));
-          jv += dot(n, vlA) + SMF(o + 9) * vaA.x + SMF(o + 10) * vaA.y + SMF(o + 11) * vaA.z;
-        } else if ((refA & 3) == 2) jv += pgs_side_jv<LANES>(S, e, sm, L, refA, f2i_bits(SMF(o + 54)), -1, n, f3());
+          aA = cross(f3(SMF(o + 3), SMF(o + 4), SMF(o + 5)), n);
+          jv += dot(n, vlA) + dot(aA, vaA);
+        } else if ((refA & 3) == 2) jv += pgs_side_jv<LANES>(S, e, sm, L, refA, f2i_bits(SMF(o + 18)), -1, n, f3());
         if (fB) {
           vlB = f3(SMF(oB), SMF(oB + 1), SMF(oB + 2)); vaB = f3(SMF(oB + 3), SMF(oB + 4), SMF(oB + 5));
-          jv -= dot(n, vlB) + SMF(o + 15) * vaB.x + SMF(o + 16) * vaB.y + SMF(o + 17) * vaB.z;
-        } else if ((refB & 3) == 2) jv += pgs_side_jv<LANES>(S, e, sm, L, refB, f2i_bits(SMF(o + 55)), -1, -n, f3());
+          aB = cross(f3(SMF(o + 6), SMF(o + 7), SMF(o + 8)), n);
+          jv -= dot(n, vlB) + dot(aB, vaB);
+        } else if ((refB & 3) == 2) jv += pgs_side_jv<LANES>(S, e, sm, L, refB, f2i_bits(SMF(o + 19)), -1, -n, f3());
         float lam = SMF(L.o_lam + 3 * s);
-        float dl = SMF(o + 45) - jv * dinv;
+        float dl = SMF(o + 9) - jv * dinv;
         float sum = lam + dl;
         if (sum < 0.f) { dl = -lam; sum = 0.f; }
         SMF(L.o_lam + 3 * s) = sum;
         if (fA) {
+          int fi = L.o_fi + 6 * (refA >> 2);
+          s3 Ii; Ii.xx = SMF(fi); Ii.yy = SMF(fi + 1); Ii.zz = SMF(fi + 2); Ii.xy = SMF(fi + 3); Ii.xz = SMF(fi + 4); Ii.yz = SMF(fi + 5);
           float k = SMF(L.o_fm + (refA >> 2)) * dl;
+          f3 ia = mul(Ii, aA);
           SMF(oA) = vlA.x + n.x * k; SMF(oA + 1) = vlA.y + n.y * k; SMF(oA + 2) = vlA.z + n.z * k;
-          SMF(oA + 3) = vaA.x + SMF(o + 12) * dl; SMF(oA + 4) = vaA.y + SMF(o + 13) * dl; SMF(oA + 5) = vaA.z + SMF(o + 14) * dl;
-        } else if ((refA & 3) == 2) pgs_side_apply<LANES>(S, e, sm, L, refA, f2i_bits(SMF(o + 54)), -1, n, f3(), dl);
+          SMF(oA + 3) = vaA.x + ia.x * dl; SMF(oA + 4) = vaA.y + ia.y * dl; SMF(oA + 5) = vaA.z + ia.z * dl;
+        } else if ((refA & 3) == 2) pgs_side_apply<LANES>(S, e, sm, L, refA, f2i_bits(SMF(o + 18)), -1, n, f3(), dl);
         if (fB) {
+          int fi = L.o_fi + 6 * (refB >> 2);
+          s3 Ii; Ii.xx = SMF(fi); Ii.yy = SMF(fi + 1); Ii.zz = SMF(fi + 2); Ii.xy = SMF(fi + 3); Ii.xz = SMF(fi + 4); Ii.yz = SMF(fi + 5);
           float k = SMF(L.o_fm + (refB >> 2)) * dl;
+          f3 ia = mul(Ii, aB);
           SMF(oB) = vlB.x - n.x * k; SMF(oB + 1) = vlB.y - n.y * k; SMF(oB + 2) = vlB.z - n.z * k;
-          SMF(oB + 3) = vaB.x - SMF(o + 18) * dl; SMF(oB + 4) = vaB.y - SMF(o + 19) * dl; SMF(oB + 5) = vaB.z - SMF(o + 20) * dl;
-        } else if ((refB & 3) == 2) pgs_side_apply<LANES>(S, e, sm, L, refB, f2i_bits(SMF(o + 55)), -1, -n, f3(), dl);
+          SMF(oB + 3) = vaB.x - ia.x * dl; SMF(oB + 4) = vaB.y - ia.y * dl; SMF(oB + 5) = vaB.z - ia.z * dl;
+        } else if ((refB & 3) == 2) pgs_side_apply<LANES>(S, e, sm, L, refB, f2i_bits(SMF(o + 19)), -1, -n, f3(), dl);
         resid = fmaxf(resid, dl * dl);
       }
-      // friction (two directions per contact, cone or pyramid): t1 and t2 are solved as one block against
-      // the same velocities (as the oracle does), sharing one load / store round of the two bodies
+      // friction (two directions per contact, cone or pyramid): both directions share one load / store
+      // round of the two bodies' velocities
       for (int s = 0; s < cnt; s++) {
         int o = L.o_cr + s * PGS_CREC;
-        if (s >= L.ccap) { o = L.o_sc; for (int i = 0; i < PGS_CREC; i++) SMF(o + i) = S.pgs_spill[((size_t)(s - L.ccap) * PGS_CREC + i) * N + e]; }
-        if (SMF(o + 46) == 0.f) continue;
+        if (SMF(o + 10) == 0.f) continue;
         float l1 = SMF(L.o_lam + 3 * s + 1), l2 = SMF(L.o_lam + 3 * s + 2);
-        float lim = SMF(o + 51) * SMF(L.o_lam + 3 * s);
+        float lim = SMF(o + 15) * SMF(L.o_lam + 3 * s);
         if (lim <= 0.f && l1 == 0.f && l2 == 0.f) continue;
-        int refA = f2i_bits(SMF(o + 52)), refB = f2i_bits(SMF(o + 53)), asA = f2i_bits(SMF(o + 54)), asB = f2i_bits(SMF(o + 55));
-        f3 t1(SMF(o + 3), SMF(o + 4), SMF(o + 5)), t2(SMF(o + 6), SMF(o + 7), SMF(o + 8));
+        int refA = f2i_bits(SMF(o + 16)), refB = f2i_bits(SMF(o + 17)), asA = f2i_bits(SMF(o + 18)), asB = f2i_bits(SMF(o + 19));
+        f3 n(SMF(o), SMF(o + 1), SMF(o + 2));
+        f3 t1, t2; plane_space(n, t1, t2);
         bool fA = (refA & 3) == 1, fB = (refB & 3) == 1;
         int oA = L.o_dv + ND + 6 * (refA >> 2), oB = L.o_dv + ND + 6 * (refB >> 2);
-        f3 vlA, vaA, vlB, vaB;
+        f3 vlA, vaA, vlB, vaB, a1A, a2A, a1B, a2B;
         float jv1 = 0.f, jv2 = 0.f;
         if (fA) {
           vlA = f3(SMF(oA), SMF(oA + 1), SMF(oA + 2)); vaA = f3(SMF(oA + 3), SMF(oA + 4), SMF(oA + 5));
-          jv1 += dot(t1, vlA) + SMF(o + 21) * vaA.x + SMF(o + 22) * vaA.y + SMF(o + 23) * vaA.z;
-          jv2 += dot(t2, vlA) + SMF(o + 33) * vaA.x + SMF(o + 34) * vaA.y + SMF(o + 35) * vaA.z;
+          f3 rA(SMF(o + 3), SMF(o + 4), SMF(o + 5));
+          a1A = cross(rA, t1); a2A = cross(rA, t2);
+          jv1 += dot(t1, vlA) + dot(a1A, vaA); jv2 += dot(t2, vlA) + dot(a2A, vaA);
         } else if ((refA & 3) == 2) {
           jv1 += pgs_side_jv<LANES>(S, e, sm, L, refA, asA + 1, -1, t1, f3()); jv2 += pgs_side_jv<LANES>(S, e, sm, L, refA, asA + 2, -1, t2, f3());
         }
         if (fB) {
           vlB = f3(SMF(oB), SMF(oB + 1), SMF(oB + 2)); vaB = f3(SMF(oB + 3), SMF(oB + 4), SMF(oB + 5));
-          jv1 -= dot(t1, vlB) + SMF(o + 27) * vaB.x + SMF(o + 28) * vaB.y + SMF(o + 29) * vaB.z;
-          jv2 -= dot(t2, vlB) + SMF(o + 39) * vaB.x + SMF(o + 40) * vaB.y + SMF(o + 41) * vaB.z;
+          f3 rB(SMF(o + 6), SMF(o + 7), SMF(o + 8));
+          a1B = cross(rB, t1); a2B = cross(rB, t2);
+          jv1 -= dot(t1, vlB) + dot(a1B, vaB); jv2 -= dot(t2, vlB) + dot(a2B, vaB);
         } else if ((refB & 3) == 2) {
           jv1 += pgs_side_jv<LANES>(S, e, sm, L, refB, asB + 1, -1, -t1, f3()); jv2 += pgs_side_jv<LANES>(S, e, sm, L, refB, asB + 2, -1, -t2, f3());
         }
-        float s1 = l1 + SMF(o + 47) - jv1 * SMF(o + 48);
-        float s2 = l2 + SMF(o + 49) - jv2 * SMF(o + 50);
+        // NOTE: t1 and t2 are solved as one block against the same velocities (block Gauss-Seidel over the
+        // pair), exactly as the oracle does
+        float s1 = l1 + SMF(o + 11) - jv1 * SMF(o + 12);
+        float s2 = l2 + SMF(o + 13) - jv2 * SMF(o + 14);
         if (S.cone) {
           float m2 = s1 * s1 + s2 * s2;
           if (m2 > lim * lim) { float k = lim / sqrtf(m2); s1 *= k; s2 *= k; }
@@ -1135,20 +1111,24 @@ AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm) {
         float d1 = s1 - l1, d2 = s2 - l2;
         SMF(L.o_lam + 3 * s + 1) = s1; SMF(L.o_lam + 3 * s + 2) = s2;
         if (fA) {
+          int fi = L.o_fi + 6 * (refA >> 2);
+          s3 Ii; Ii.xx = SMF(fi); Ii.yy = SMF(fi + 1); Ii.zz = SMF(fi + 2); Ii.xy = SMF(fi + 3); Ii.xz = SMF(fi + 4); Ii.yz = SMF(fi + 5);
           float im = SMF(L.o_fm + (refA >> 2));
+          f3 ia = mul(Ii, a1A * d1 + a2A * d2);
           f3 dl_ = (t1 * d1 + t2 * d2) * im;
           SMF(oA) = vlA.x + dl_.x; SMF(oA + 1) = vlA.y + dl_.y; SMF(oA + 2) = vlA.z + dl_.z;
-          SMF(oA + 3) = vaA.x + SMF(o + 24) * d1 + SMF(o + 36) * d2; SMF(oA + 4) = vaA.y + SMF(o + 25) * d1 + SMF(o + 37) * d2;
-          SMF(oA + 5) = vaA.z + SMF(o + 26) * d1 + SMF(o + 38) * d2;
+          SMF(oA + 3) = vaA.x + ia.x; SMF(oA + 4) = vaA.y + ia.y; SMF(oA + 5) = vaA.z + ia.z;
         } else if ((refA & 3) == 2) {
           pgs_side_apply<LANES>(S, e, sm, L, refA, asA + 1, -1, t1, f3(), d1); pgs_side_apply<LANES>(S, e, sm, L, refA, asA + 2, -1, t2, f3(), d2);
         }
         if (fB) {
+          int fi = L.o_fi + 6 * (refB >> 2);
+          s3 Ii; Ii.xx = SMF(fi); Ii.yy = SMF(fi + 1); Ii.zz = SMF(fi + 2); Ii.xy = SMF(fi + 3); Ii.xz = SMF(fi + 4); Ii.yz = SMF(fi + 5);
           float im = SMF(L.o_fm + (refB >> 2));
+          f3 ia = mul(Ii, a1B * d1 + a2B * d2);
           f3 dl_ = (t1 * d1 + t2 * d2) * im;
           SMF(oB) = vlB.x - dl_.x; SMF(oB + 1) = vlB.y - dl_.y; SMF(oB + 2) = vlB.z - dl_.z;
-          SMF(oB + 3) = vaB.x - SMF(o + 30) * d1 - SMF(o + 42) * d2; SMF(oB + 4) = vaB.y - SMF(o + 31) * d1 - SMF(o + 43) * d2;
-          SMF(oB + 5) = vaB.z - SMF(o + 32) * d1 - SMF(o + 44) * d2;
+          SMF(oB + 3) = vaB.x - ia.x; SMF(oB + 4) = vaB.y - ia.y; SMF(oB + 5) = vaB.z - ia.z;
         } else if ((refB & 3) == 2) {
           pgs_side_apply<LANES>(S, e, sm, L, refB, asB + 1, -1, -t1, f3(), d1); pgs_side_apply<LANES>(S, e, sm, L, refB, asB + 2, -1, -t2, f3(), d2);
         }

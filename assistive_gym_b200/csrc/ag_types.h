@@ -73,7 +73,6 @@ struct SimDev {
   float* gr_data;                                      // [ngr][16][N] generic rows (fixed constraints)
   int* gr_ref;                                         // [ngr][4][N]
   int* iters_used;                                     // [N]
-  int pgs_ccap, pgs_acap; float* pgs_spill;            // PGS staging caps + global spill of contact records [maxc-ccap][56][N]
   int* pgs_cycles;                                     // [N] SM cycles spent in k_pgs by each env's lane (diagnostic)
 };
 

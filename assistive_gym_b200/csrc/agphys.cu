@@ -374,11 +374,6 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   S.cmin = dalloc<float>(s, (size_t)nc * 3 * N); S.cmax = dalloc<float>(s, (size_t)nc * 3 * N);
   S.lmin = dalloc<float>(s, (size_t)nl * 3 * N); S.lmax = dalloc<float>(s, (size_t)nl * 3 * N);
   S.c_count = dalloc<int>(s, N); S.overflow = dalloc<int>(s, N); S.iters_used = dalloc<int>(s, N); S.pgs_cycles = dalloc<int>(s, N);
-  { const char* cc = getenv("AG_PGS_CCAP"); const char* ac = getenv("AG_PGS_ACAP");
-    S.pgs_ccap = cc ? atoi(cc) : 48; S.pgs_acap = ac ? atoi(ac) : 24;
-    if (S.pgs_ccap < 1) S.pgs_ccap = 1; if (S.pgs_acap < 0) S.pgs_acap = 0;
-    int nsp = S.maxc > S.pgs_ccap ? S.maxc - S.pgs_ccap : 0;
-    S.pgs_spill = dalloc<float>(s, (size_t)nsp * 56 * N); }
   S.maxcand = 4 * S.maxc; S.cand_count = dalloc<int>(s, N); S.cand = dalloc<unsigned>(s, (size_t)S.maxcand * N);
   S.c_key = dalloc<unsigned>(s, (size_t)S.maxc * N); S.s_key = dalloc<unsigned>(s, (size_t)S.maxc * N);
   S.c_data = dalloc<float>(s, (size_t)S.maxc * AG_CF * N); S.s_data = dalloc<float>(s, (size_t)S.maxc * AG_CF * N);
@@ -399,8 +394,8 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
     // for 592 warp schedulers, so partially filled warps (8 envs each) put a warp on every scheduler,
     // shorten the per-warp iteration count (max over fewer envs) and reduce divergence.
     const char* lp = getenv("AG_PGS_LANES");
-    s->pgs_lanes = lp ? atoi(lp) : 1;
-    if (s->pgs_lanes != 1 && s->pgs_lanes != 2 && s->pgs_lanes != 4 && s->pgs_lanes != 8 && s->pgs_lanes != 32) s->pgs_lanes = 1;
+    s->pgs_lanes = lp ? atoi(lp) : 4;
+    if (s->pgs_lanes != 1 && s->pgs_lanes != 2 && s->pgs_lanes != 4 && s->pgs_lanes != 8 && s->pgs_lanes != 32) s->pgs_lanes = 4;
     size_t smem = (size_t)pgs_layout(S).total * s->pgs_lanes * sizeof(float);
     if (smem > 227 * 1024) { g_err = "PGS shared-memory footprint exceeds 227 KB per CTA: lower max_contacts or AG_PGS_LANES"; ag_destroy(s); return nullptr; }
     cudaError_t ce = cudaSuccess;

@@ -96,11 +96,3 @@ def test_device_gjk_thin_simplex_accuracy(feeding, emu_lib):
         assert abs(float(o[3][0]) - d64) < 2e-6
         assert np.arccos(np.clip(((pa - pb) / d64) @ o[2], -1, 1)) < 2e-3
 
-
-def test_pgs_spill_paths_match(feeding, make_sim, monkeypatch):
-    """Contact records / articulated sides beyond the shared-memory staging caps take the global-memory
-    path: force tiny caps and check the step still matches the oracle."""
-    monkeypatch.setenv('AG_PGS_CCAP', '3')
-    monkeypatch.setenv('AG_PGS_ACAP', '2')
-    err = pc.onestep_errors(feeding, make_sim, n=2, seed=1, steps=12)
-    assert err['q'] < 1e-5 and err['tool_pos'] < 1e-5 and err['pos'] < pc.TOL_M, err
