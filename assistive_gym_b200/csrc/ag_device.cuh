@@ -910,8 +910,34 @@ AG_HD void pgs_side_apply(const SimDev& S, int e, float* sm, const PgsLayout& L,
   }
 }
 
+// K6c: longest-processing-time-first order for K7.  The PGS chain of an env is sequential and its
+// length varies 10x between envs (iterations used x rows), so CTAs are issued heaviest-first and envs
+// of similar weight share a warp.  Work is predicted from this substep's contact count and the
+// previous substep's iteration count.  64-bucket counting sort; p.p1 = histogram[64] (zeroed).
+AG_HD int pgs_work_bucket(const SimDev& S, int e) {
+  int cnt = S.c_count[e]; if (cnt > S.maxc) cnt = S.maxc;
+  int it = S.iters_used[e]; if (it < 1) it = 1;
+  int w = it * (3 * cnt + 3 * S.ND + S.ngr);          // predicted row updates
+  int b = 63 - w / 320;                               // heaviest work -> bucket 0
+  return b < 0 ? 0 : b;
+}
+AG_HDN inline void order_hist_body(int e, const SimDev& S, const KP& p) {
+  ag_atomic_inc((int*)p.p1 + pgs_work_bucket(S, e));
+}
+AG_HDN inline void order_scatter_body(int e, const SimDev& S, const KP& p) {
+  // p.p1 = exclusive prefix of the histogram (consumed by atomic increments)
+  int pos = ag_atomic_inc((int*)p.p1 + pgs_work_bucket(S, e));
+  S.pgs_order[pos] = e;
+}
+AG_HDN inline void order_prefix_body(int tid, const SimDev&, const KP& p) {
+  if (tid != 0) return;
+  int* h = (int*)p.p1; int acc = 0;
+  for (int b = 0; b < 64; b++) { int c = h[b]; h[b] = acc; acc += c; }
+}
+
 template <int LANES>
-AG_HDN inline void pgs_body(int e, const SimDev& S, const KP&, float* sm) {
+AG_HDN inline void pgs_body(int slot, const SimDev& S, const KP&, float* sm) {
+  const int e = S.pgs_order[slot];
   const int N = S.N;
   const int ND = S.ND;
   const PgsLayout L = pgs_layout(S);

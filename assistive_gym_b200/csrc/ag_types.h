@@ -73,6 +73,7 @@ struct SimDev {
   float* gr_data;                                      // [ngr][16][N] generic rows (fixed constraints)
   int* gr_ref;                                         // [ngr][4][N]
   int* iters_used;                                     // [N]
+  int* pgs_order; int* pgs_hist;                       // heaviest-first env order for K7 + its 64-bucket histogram
   int* pgs_cycles;                                     // [N] SM cycles spent in k_pgs by each env's lane (diagnostic)
 };
 

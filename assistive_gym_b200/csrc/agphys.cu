@@ -59,6 +59,9 @@ static void k_pgs(SimDev S, KP p) {
   for (int tid = 0; tid < p.n; tid++) pgs_body<1>(tid, S, p, buf.data());
 }
 #endif
+AG_KERNEL(k_order_hist, order_hist_body)
+AG_KERNEL(k_order_prefix, order_prefix_body)
+AG_KERNEL(k_order_scatter, order_scatter_body)
 AG_KERNEL(k_integrate, integrate_body)
 AG_KERNEL(k_gather, gather_body)
 AG_KERNEL(k_scatter, scatter_body)
@@ -374,6 +377,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   S.cmin = dalloc<float>(s, (size_t)nc * 3 * N); S.cmax = dalloc<float>(s, (size_t)nc * 3 * N);
   S.lmin = dalloc<float>(s, (size_t)nl * 3 * N); S.lmax = dalloc<float>(s, (size_t)nl * 3 * N);
   S.c_count = dalloc<int>(s, N); S.overflow = dalloc<int>(s, N); S.iters_used = dalloc<int>(s, N); S.pgs_cycles = dalloc<int>(s, N);
+  S.pgs_order = dalloc<int>(s, N); S.pgs_hist = dalloc<int>(s, 64);
   S.maxcand = 4 * S.maxc; S.cand_count = dalloc<int>(s, N); S.cand = dalloc<unsigned>(s, (size_t)S.maxcand * N);
   S.c_key = dalloc<unsigned>(s, (size_t)S.maxc * N); S.s_key = dalloc<unsigned>(s, (size_t)S.maxc * N);
   S.c_data = dalloc<float>(s, (size_t)S.maxc * AG_CF * N); S.s_data = dalloc<float>(s, (size_t)S.maxc * AG_CF * N);
@@ -585,6 +589,13 @@ static void substep(AgSim* s) {
   LAUNCH(s, k_dyn, N, z);
   LAUNCH(s, k_rows, N, z);
   LAUNCH(s, k_crows, (size_t)S.maxc * N, z);
+  {   // heaviest-first env order for the PGS kernel
+    dev_zero(s, S.pgs_hist, sizeof(int) * 64);
+    KP o = kp0(); o.p1 = S.pgs_hist;
+    LAUNCH(s, k_order_hist, N, o);
+    LAUNCH(s, k_order_prefix, 1, o);
+    LAUNCH(s, k_order_scatter, N, o);
+  }
 #ifndef AG_CPU_EMU
   {
     KP kp = z; kp.n = N;
