@@ -57,6 +57,7 @@ class AgContact(C.Structure):
 class AgFeedingParams(C.Structure):
     _fields_ = [('robot_body', C.c_int32), ('tool_body', C.c_int32), ('human_body_m', C.c_int32), ('human_body_f', C.c_int32),
                 ('arm_links', C.c_int32 * 7), ('ee_link', C.c_int32), ('head_link_m', C.c_int32), ('head_link_f', C.c_int32),
+                ('head_joints_m', C.c_int32 * 4), ('head_joints_f', C.c_int32 * 4),
                 ('food_body0', C.c_int32), ('n_foods', C.c_int32),
                 ('arm_lower', C.c_float * 7), ('arm_upper', C.c_float * 7), ('mouth_m', C.c_float * 3), ('mouth_f', C.c_float * 3),
                 ('action_multiplier', C.c_float), ('frame_skip', C.c_int32),
@@ -110,6 +111,8 @@ def load_library(path=None):
     lib.ag_closest_points.argtypes = [vp, ci, ci, C.c_float, ci, vp, vp]
     lib.ag_feeding_init.argtypes = [vp, C.POINTER(AgFeedingParams), vp]
     lib.ag_feeding_reset_episode.argtypes = [vp, vp]
+    lib.ag_feeding_set_tremor.argtypes = [vp, vp, vp, vp]
+    lib.ag_set_hard_limits.argtypes = [vp, ci, vp, ci]
     lib.ag_feeding_step_dev.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.ag_feeding_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.ag_state_size.restype = C.c_size_t
@@ -134,7 +137,7 @@ EXPORTED_SYMBOLS = [
     'ag_set_base_pose', 'ag_set_base_velocity', 'ag_set_joint_state', 'ag_set_link_friction',
     'ag_set_body_active', 'ag_forward_kinematics', 'ag_set_motor_host', 'ag_set_motor_targets_dev', 'ag_set_motor_targets_host',
     'ag_step', 'ag_get_joint_states', 'ag_get_link_states', 'ag_get_contacts', 'ag_contact_force_sum',
-    'ag_closest_points', 'ag_feeding_init', 'ag_feeding_reset_episode', 'ag_feeding_step_dev',
+    'ag_closest_points', 'ag_feeding_init', 'ag_feeding_reset_episode', 'ag_feeding_set_tremor', 'ag_set_hard_limits', 'ag_feeding_step_dev',
     'ag_feeding_step_host', 'ag_state_size', 'ag_state_get', 'ag_state_set', 'ag_kernel_launches',
     'ag_overflow_count', 'ag_get_solver_stats', 'ag_get_pgs_cycles', 'ag_profile_enable', 'ag_profile_get',
 ]

@@ -1207,8 +1207,13 @@ AG_HDN inline void integrate_body(int e, const SimDev& S, const KP&) {
     int b = AG_LDG(S.link_body + k);
     if (S.body_mode[(size_t)b * N + e] != 1) continue;
     float qd = clampf(ld1(S.jqd, k, N, e) + ld1(S.dv, d, N, e), -vmax, vmax);
+    float qn = ld1(S.jq, k, N, e) + dt * qd;
+    if (S.hard_limit[k]) {                      // Human.enforce_joint_limits: teleport back, zero velocity
+      float lo = AG_LDG(S.link_lower + k), hi = AG_LDG(S.link_upper + k);
+      if (qn < lo) { qn = lo; qd = 0.f; } else if (qn > hi) { qn = hi; qd = 0.f; }
+    }
     st1(S.jqd, k, N, e, qd);
-    st1(S.jq, k, N, e, ld1(S.jq, k, N, e) + dt * qd);
+    st1(S.jq, k, N, e, qn);
     st1(S.motor_applied, k, N, e, ld1(S.dr_lam, 2 * S.ND + d, N, e) / dt);
   }
   S.c_count[e] = S.c_count[e] > S.maxc ? S.maxc : S.c_count[e];

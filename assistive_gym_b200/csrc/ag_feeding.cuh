@@ -17,6 +17,7 @@ struct FeedDev {
   int *male, *food_state, *iteration, *task_success, *food_near;
   float* action;
   unsigned long long* rng;
+  int* tremor_on; float *tremor_rest, *tremor_amp;     // [N], [4][N], [4][N]
 };
 
 // ---- env-major host layout <-> SoA.  thread = (column j, env e), env fastest
@@ -162,6 +163,15 @@ AG_HDN inline void feeding_pre_body(int e, const SimDev& S, const KP& p) {
       q += a;
     }
     st1(S.motor_target, k, N, e, q);
+  }
+  // tremor (env.py:212-215): the head joints are driven to rest +- amplitude, sign flips every env step
+  if (F.tremor_on[e]) {
+    bool male = F.male[e] != 0;
+    float sgn = (F.iteration[e] % 2 == 0) ? 1.f : -1.f;
+    for (int j = 0; j < 4; j++) {
+      int k = male ? F.P.head_joints_m[j] : F.P.head_joints_f[j];
+      st1(S.motor_target, k, N, e, F.tremor_rest[(size_t)j * N + e] + sgn * F.tremor_amp[(size_t)j * N + e]);
+    }
   }
 }
 

@@ -46,6 +46,7 @@ struct SimDev {
   const float *pt_mass, *pt_com, *pt_I;
   // ---- motors (per link, shared by envs) + per-env targets
   int* motor_mode; float *motor_kp, *motor_kd, *motor_maxf;
+  int* hard_limit;                                     // [nl] clamp q to limits after integration (Human.enforce_joint_limits)
   float *motor_target, *motor_applied;       // [nl][N]
   // ---- per-env state
   float *base_pos, *base_quat, *base_lin, *base_ang;   // [nb][3|4][N]

@@ -319,7 +319,8 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
     }
   }
   S.nf = (int)free_body.size(); S.nart = (int)art_body.size(); S.ND = (int)dl_link.size(); S.nparts = (int)pt_mass.size();
-  if (S.ND > AG_MAXND) { g_err = "too many articulated DoFs per env (AG_MAXND)"; ag_destroy(s); return nullptr; }
+  for (int nd_a : art_nd) if (nd_a > AG_MAXND) { g_err = "too many DoFs in one articulated body (AG_MAXND)"; ag_destroy(s); return nullptr; }
+  if (S.ND > 32) { g_err = "too many articulated DoFs per env (32)"; ag_destroy(s); return nullptr; }
   s->body_kind = body_kind;
   // movable lists
   std::vector<int> link_col0(nl, 0), link_ncol(nl, 0);
@@ -367,6 +368,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   S.dl_mass = upload(s, dl_mass); S.dl_mc = upload(s, dl_mc); S.dl_J = upload(s, dl_J); S.dl_damping = upload(s, dl_damping);
   S.pt_mass = upload(s, pt_mass); S.pt_com = upload(s, pt_com); S.pt_I = upload(s, pt_I);
   // ---- per-env state
+  S.hard_limit = dalloc<int>(s, nl);
   S.motor_mode = dalloc<int>(s, nl); S.motor_kp = dalloc<float>(s, nl); S.motor_kd = dalloc<float>(s, nl); S.motor_maxf = dalloc<float>(s, nl);
   S.motor_target = dalloc<float>(s, (size_t)nl * N); S.motor_applied = dalloc<float>(s, (size_t)nl * N);
   S.base_pos = dalloc<float>(s, (size_t)nb * 3 * N); S.base_quat = dalloc<float>(s, (size_t)nb * 4 * N);
@@ -532,6 +534,13 @@ int ag_set_link_friction(AgSim* s, int link, const float* mu, const int32_t* mas
 int ag_set_body_active(AgSim* s, int body, const int32_t* active) {
   if (body < 0 || body >= s->nb) return fail("bad body");
   return h2d(s, s->S.body_mode + (size_t)body * s->S.N, active, sizeof(int) * s->S.N);
+}
+
+int ag_set_hard_limits(AgSim* s, int n, const int32_t* links, int on) {
+  std::vector<int> h(s->nl);
+  if (d2h(s, h.data(), s->S.hard_limit, sizeof(int) * s->nl)) return -1;
+  for (int j = 0; j < n; j++) { if (links[j] < 0 || links[j] >= s->nl) return fail("bad link"); h[links[j]] = on ? 1 : 0; }
+  return h2d(s, s->S.hard_limit, h.data(), sizeof(int) * s->nl);
 }
 
 static void run_fk_all(AgSim* s) {
@@ -758,6 +767,7 @@ int ag_feeding_init(AgSim* s, const AgFeedingParams* p, const int32_t* gender_is
   F.male = dalloc<int>(s, N); F.food_state = dalloc<int>(s, N); F.iteration = dalloc<int>(s, N); F.task_success = dalloc<int>(s, N);
   F.food_near = dalloc<int>(s, (size_t)N * 16);
   F.action = dalloc<float>(s, (size_t)N * 7); F.rng = dalloc<unsigned long long>(s, N);
+  F.tremor_on = dalloc<int>(s, N); F.tremor_rest = dalloc<float>(s, (size_t)N * 4); F.tremor_amp = dalloc<float>(s, (size_t)N * 4);
   s->d_action = dalloc<float>(s, (size_t)N * 7); s->d_obs = dalloc<float>(s, (size_t)N * 25);
   s->d_reward = dalloc<float>(s, N); s->d_done = dalloc<float>(s, N); s->d_info = dalloc<float>(s, (size_t)N * 4);
   if (!s->d_info) return fail("device allocation failed");
@@ -773,6 +783,19 @@ int ag_feeding_init(AgSim* s, const AgFeedingParams* p, const int32_t* gender_is
   s->feeding = true;
   return ag_feeding_reset_episode(s, nullptr);
 }
+int ag_feeding_set_tremor(AgSim* s, const int32_t* on, const float* rest, const float* amplitude) {
+  if (!s->feeding) return fail("ag_feeding_init not called");
+  const int N = s->S.N;
+  std::vector<int> o(N, 0); std::vector<float> r((size_t)4 * N, 0.f), a((size_t)4 * N, 0.f);
+  if (on) for (int e = 0; e < N; e++) {
+    o[e] = on[e];
+    for (int j = 0; j < 4; j++) { r[(size_t)j * N + e] = rest ? rest[(size_t)e * 4 + j] : 0.f; a[(size_t)j * N + e] = amplitude ? amplitude[(size_t)e * 4 + j] : 0.f; }
+  }
+  if (h2d(s, s->F.tremor_on, o.data(), sizeof(int) * N)) return -1;
+  if (h2d(s, s->F.tremor_rest, r.data(), sizeof(float) * 4 * N)) return -1;
+  return h2d(s, s->F.tremor_amp, a.data(), sizeof(float) * 4 * N);
+}
+
 int ag_feeding_reset_episode(AgSim* s, const int32_t* env_mask) {
   if (!s->feeding) return fail("ag_feeding_init not called");
   const int N = s->S.N;

@@ -184,6 +184,14 @@ class BatchSim:
         g = _i32(np.broadcast_to(np.asarray(gender_is_male, dtype=np.int32), (self.n,)))
         self._ck(self.lib.ag_feeding_init(self.h, C.byref(params), _p(g)))
 
+    def set_hard_limits(self, links, on=True):
+        links = _i32(links)
+        self._ck(self.lib.ag_set_hard_limits(self.h, len(links), _p(links), int(bool(on))))
+
+    def feeding_set_tremor(self, on, rest, amplitude):
+        o = _i32(np.broadcast_to(np.asarray(on, dtype=np.int32), (self.n,)))
+        self._ck(self.lib.ag_feeding_set_tremor(self.h, _p(o), _p(_f32(rest, (self.n, 4))), _p(_f32(amplitude, (self.n, 4)))))
+
     def feeding_reset_episode(self, mask=None):
         self._ck(self.lib.ag_feeding_reset_episode(self.h, _p(_i32(mask))))
 

@@ -138,9 +138,12 @@ int ag_set_base_velocity(AgSim* sim, int body, const float* lin, const float* an
 int ag_set_joint_state(AgSim* sim, int n, const int32_t* links, const float* q, const float* qd, const int32_t* env_mask);
 /* per-env lateral friction of one link (env.py:120 randomises the plane's) */
 int ag_set_link_friction(AgSim* sim, int link, const float* mu, const int32_t* env_mask);
-/* per-env activation of a body (inactive bodies neither move nor collide; used for the
- * male/female human variants, human.py:76-77) */
+/* per-env mode of a body: 0 = inactive (neither moves nor collides; the other-gender human,
+ * human.py:76-77), 1 = active, 2 = frozen (collides as a static body; a non-tremor human) */
 int ag_set_body_active(AgSim* sim, int body, const int32_t* active);
+/* Human.enforce_joint_limits (agent.py:240-250, called every substep for a human in `agents`,
+ * env.py:229): hard clamp of q to the joint limits with qd := 0, applied after integration. */
+int ag_set_hard_limits(AgSim* sim, int n, const int32_t* links, int on);
 /* recompute link world poses from the state (after teleports); also done by ag_step */
 int ag_forward_kinematics(AgSim* sim);
 
@@ -182,6 +185,7 @@ typedef struct AgFeedingParams {
   int32_t arm_links[7];         /* controllable joints (global link ids) */
   int32_t ee_link;              /* right_end_effector */
   int32_t head_link_m, head_link_f;
+  int32_t head_joints_m[4], head_joints_f[4]; /* neck, head x/y/z (global link ids): the tremor DoFs (human.py:89-90) */
   int32_t food_body0, n_foods;
   float   arm_lower[7], arm_upper[7];
   float   mouth_m[3], mouth_f[3];
@@ -194,6 +198,9 @@ typedef struct AgFeedingParams {
 } AgFeedingParams;
 int ag_feeding_init(AgSim* sim, const AgFeedingParams* p, const int32_t* gender_is_male);
 int ag_feeding_reset_episode(AgSim* sim, const int32_t* env_mask);
+/* tremor impairment (human.py:80-92, env.py:212-215): per env on/off, head-joint rest angles [N][4]
+ * and tremor amplitudes [N][4]; targets flip sign every env step.  NULL `on` switches tremor off. */
+int ag_feeding_set_tremor(AgSim* sim, const int32_t* on, const float* rest, const float* amplitude);
 int ag_feeding_step_dev(AgSim* sim, const float* action_dev, float* obs_dev, float* reward_dev,
                         float* done_dev, float* info_dev);
 /* host-buffer variant (pinned or pageable): H2D of action, D2H of obs/reward/done/info inside */

@@ -72,7 +72,7 @@ struct Env {
   std::vector<V3> base_pos, base_lin, base_ang;   // base LINK frame position, COM linear velocity, angular velocity (world)
   std::vector<Quat> base_quat;
   std::vector<real> q, qd;                        // per link
-  std::vector<int> motor_mode;
+  std::vector<int> motor_mode, hard_limit;
   std::vector<real> motor_target, motor_kp, motor_kd, motor_maxf, motor_applied;
   std::vector<real> friction;                     // per link
   std::vector<int> body_mode;                     // 0 inactive, 1 normal, 2 frozen
@@ -741,7 +741,11 @@ void step_env(const Scene& s, const AgConfig& cfg, Env& e) {
       } else {
         for (int k = l0 + 1; k < l0 + s.body_nlinks[b]; k++) if (s.link_live[k]) {
           real qd = std::min(vmax, std::max(-vmax, e.qd[k] + so.dv[o + s.link_dof[k]]));
-          e.qd[k] = qd; e.q[k] += dt * qd;
+          real qn = e.q[k] + dt * qd;
+          if (e.hard_limit[k]) {               // Human.enforce_joint_limits (agent.py:240-250)
+            if (qn < s.link_lower[k]) { qn = s.link_lower[k]; qd = 0; } else if (qn > s.link_upper[k]) { qn = s.link_upper[k]; qd = 0; }
+          }
+          e.qd[k] = qd; e.q[k] = qn;
         }
       }
     }
@@ -765,7 +769,7 @@ void init_env(const Scene& s, Env& e) {
   e.base_pos.assign(s.nb, V3()); e.base_lin.assign(s.nb, V3()); e.base_ang.assign(s.nb, V3());
   e.base_quat.assign(s.nb, Quat());
   e.q.assign(s.nl, 0); e.qd.assign(s.nl, 0);
-  e.motor_mode.assign(s.nl, AG_MOTOR_OFF);
+  e.motor_mode.assign(s.nl, AG_MOTOR_OFF); e.hard_limit.assign(s.nl, 0);
   e.motor_target.assign(s.nl, 0); e.motor_kp.assign(s.nl, 0); e.motor_kd.assign(s.nl, 0);
   e.motor_maxf.assign(s.nl, 0); e.motor_applied.assign(s.nl, 0);
   e.friction = s.link_friction;
@@ -836,6 +840,11 @@ int oracle_set_link_friction(void* h, int link, const double* mu, const int32_t*
 int oracle_set_body_mode(void* h, int body, const int32_t* mode) {
   Sim* s = (Sim*)h;
   for (int i = 0; i < s->N; i++) s->envs[i].body_mode[body] = mode[i];
+  return 0;
+}
+int oracle_set_hard_limits(void* h, int n, const int32_t* links, int on) {
+  Sim* s = (Sim*)h;
+  for (auto& e : s->envs) for (int j = 0; j < n; j++) e.hard_limit[links[j]] = on ? 1 : 0;
   return 0;
 }
 int oracle_set_motor(void* h, int n, const int32_t* links, int mode, const double* target, const double* kp,

@@ -44,6 +44,7 @@ def _load(f32=False):
     lib.oracle_set_link_friction.argtypes = [vp, ci, vp, vp]
     lib.oracle_set_body_mode.argtypes = [vp, ci, vp]
     lib.oracle_set_motor.argtypes = [vp, ci, vp, ci, vp, vp, vp, vp]
+    lib.oracle_set_hard_limits.argtypes = [vp, ci, vp, ci]
     lib.oracle_set_motor_targets.argtypes = [vp, ci, vp, vp]
     lib.oracle_forward_kinematics.argtypes = [vp]
     lib.oracle_step.argtypes = [vp, ci, ci]
@@ -140,6 +141,10 @@ class OracleSim:
         kd = _f64(kd if kd is not None else 1.0, (n,))
         mf = _f64(max_force, (n,)) if max_force is not None else None
         self.lib.oracle_set_motor(self.h, n, _p(links), int(mode), _p(target), _p(kp), _p(kd), _p(mf))
+
+    def set_hard_limits(self, links, on=True):
+        links = _i32(links)
+        self.lib.oracle_set_hard_limits(self.h, len(links), _p(links), int(bool(on)))
 
     def set_motor_targets(self, links, target):
         links = _i32(links)
