@@ -137,6 +137,9 @@ class AssistiveEnv(gym.Env):
         for i, agent in enumerate(self.agents):
             needs_action = not isinstance(agent, Human) or agent.controllable
             if not needs_action:
+                if isinstance(agent, Human) and agent.impairment == 'tremor':     # env.py:212-215
+                    sgn = 1.0 if self.iteration % 2 == 0 else -1.0
+                    agent.control(agent.controllable_joint_indices, agent.target_joint_angles + agent.tremors * sgn, gains[i], forces[i])
                 continue
             k = len(agent.controllable_joint_indices)
             action = actions[:, idx:idx + k].copy()

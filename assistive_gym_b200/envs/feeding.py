@@ -7,7 +7,7 @@ API — and exists so that tests can show the two paths agree."""
 import numpy as np
 
 from .. import capi
-from ..feeding_batch import HEAD_LINK, FeedingBatch
+from ..feeding_batch import HEAD_LINK, IMPAIRMENTS, FeedingBatch
 from ..kinematics import q_rot
 from ..sim import BatchSim
 from .agents.agent import Agent
@@ -21,6 +21,7 @@ class FeedingEnv(AssistiveEnv):
                          obs_robot_len=(18 + len(robot.controllable_joint_indices) - (len(robot.wheel_joint_indices) if robot.mobile else 0)),
                          obs_human_len=(19 + len(human.controllable_joint_indices)))
         self._fb = FeedingBatch()
+        self.human_impairment = 'random'      # build_assistive_env(human_impairment='random'), env.py:114
         self._cfg = config or capi.default_config()
         self._sim_lib = None
         self.total_food_count = 8
@@ -53,15 +54,30 @@ class FeedingEnv(AssistiveEnv):
         rng = np.random.default_rng(self.np_random.randint(0, 2 ** 31 - 1))
         self.robot.motor_gains = self.human.motor_gains = 0.025          # feeding.py:122
         self.agents = [self.robot]
-        s = fb.reset(self.id, rng, settle_steps=25)
+        s = fb.reset(self.id, rng, settle_steps=25, impairment=self.human_impairment)
         self.male = s['male'].astype(bool)
         self.human.gender = 'male' if self.male[0] else 'female'
+        # impairments (human.py:79-92).  The reference appends a tremor human to `agents`
+        # (env.py:130-131); here each gender's Human carries a per-env tremor mask.
+        tremor = s['impairment'] == 3
+        self.impairment = s['impairment']
+        self.human.impairment = IMPAIRMENTS[int(s['impairment'][0])]
+        self.human.limit_scale, self.human.strength = float(s['limit_scale'][0]), float(s['strength'][0])
+        rest = fb.tremor_rest_of(s)
+        for g, h in self.humans.items():
+            h.tremor_mask = tremor & (self.male if g == 'male' else ~self.male)
+            h.impairment = 'tremor' if h.tremor_mask.any() else 'none'
+            h.tremors = np.where(h.tremor_mask[:, None], s['tremors'], 0.0)
+            h.target_joint_angles = rest
+            h.motor_gains = self.human.motor_gains
+            if h.tremor_mask.any():
+                self.agents.append(h)
         self.mouth_pos = np.where(self.male[:, None], fb.mouth['male'], fb.mouth['female'])
         if not self._feeding_ready:
-            self.id.feeding_init(fb.feeding_params(seed=self._seed), s['male'])
+            fb.start_fused(self.id, s, seed=self._seed)
             self._feeding_ready = True
         else:
-            self.id.feeding_init(fb.feeding_params(seed=self._seed), s['male'])
+            fb.start_fused(self.id, s, seed=self._seed)
         self.foods = np.ones((self.n_envs, 8), dtype=bool)
         self.foods_active = np.ones((self.n_envs, 8), dtype=bool)
         self.task_success = np.zeros(self.n_envs, dtype=int)

@@ -10,7 +10,9 @@ Differences forced by lock-step batching (all documented in DESIGN.md):
   * both human genders are instantiated; per env the inactive one is switched off,
   * the target marker body (feeding.py:189) is not instantiated — the mouth target is computed,
   * IK is a batched damped-least-squares solve on the host instead of PyBullet's nullspace IK,
-  * the `tremor` impairment is not simulated yet (humans are static in every env).
+  * the head chain (neck + 3 head joints) keeps its mass in the template so that `tremor` envs can
+    simulate it (human.py:104-112 with impairment == 'tremor'); envs without tremor freeze the
+    whole human body (body mode 2), which is what mass-0 "static joints" amount to.
 """
 import numpy as np
 
@@ -28,6 +30,8 @@ JACO = dict(arm=[1, 2, 3, 4, 5, 6, 7], ee=8, gripper=[9, 11, 13], tool_joint=8, 
 HUMAN_PRESET = {6: -90, 16: -90, 28: -90, 31: 80, 35: -90, 38: 80}
 HEAD_JOINTS = (21, 22, 23)
 HEAD_LINK = 23
+TREMOR_JOINTS = (20, 21, 22, 23)      # human.head_joints = the controllable joints of FeedingEnv (feeding_envs.py)
+IMPAIRMENTS = ('none', 'limits', 'weakness', 'tremor')
 
 
 class FeedingBatch:
@@ -44,9 +48,11 @@ class FeedingBatch:
         for gender, z in (('male', 0.89), ('female', 0.86)):
             hb, info = create_human(b, gender=gender, static=True)
             b.bodies[hb].base_pos = np.array([0, 0.03, z])
-            # "static joints": every link mass -> 0 (human.py:108-112, non-tremor envs)
+            # "static joints": every non-controllable link mass -> 0 (human.py:108-112); the head
+            # joints stay dynamic in the template, per env they are frozen unless impairment == tremor
             for j in range(b.num_joints(hb)):
-                b.change_dynamics(hb, j, mass=0)
+                if j not in TREMOR_JOINTS:
+                    b.change_dynamics(hb, j, mass=0)
             self.humans[gender] = hb
         self.wheelchair = b.load_urdf('wheelchair_jaco', base_pos=wheelchair_pos, fixed_base=False)
         self.table = b.load_urdf('table_tall', base_pos=[0.25, -1.0, 0])
@@ -91,6 +97,9 @@ class FeedingBatch:
         P.ee_link = self.ee_link
         P.head_link_m = self.gl(self.humans['male'], HEAD_LINK)
         P.head_link_f = self.gl(self.humans['female'], HEAD_LINK)
+        for i, j in enumerate(TREMOR_JOINTS):
+            P.head_joints_m[i] = self.gl(self.humans['male'], j)
+            P.head_joints_f[i] = self.gl(self.humans['female'], j)
         P.food_body0, P.n_foods = self.foods[0], len(self.foods)
         for i in range(3):
             P.mouth_m[i] = self.mouth['male'][i]
@@ -102,10 +111,44 @@ class FeedingBatch:
         P.seed = seed
         return P
 
+    def start_fused(self, sim, sample=None, seed=1001):
+        """Arm the fused per-step kernels for the envs last put in place by `reset` (or `sample`)."""
+        s = sample or self.last_sample
+        sim.feeding_init(self.feeding_params(seed), s['male'])
+        imp = s.get('impairment')
+        if imp is not None and np.any(imp == 3):
+            rest = self.tremor_rest_of(s)
+            sim.feeding_set_tremor((imp == 3).astype(np.int32), rest, s['tremors'])
+
+    def tremor_rest_of(self, s):
+        """target_joint_angles of the head joints (human.py:122): neck 0, head x/y/z the sampled pose, limit-clipped."""
+        n = len(s['male'])
+        rest = np.zeros((n, 4))
+        rest[:, 1:] = np.deg2rad(s['head_deg'])
+        for g, hb in self.humans.items():
+            hl = [self.gl(hb, j) for j in TREMOR_JOINTS]
+            sel = s['male'].astype(bool) if g == 'male' else ~s['male'].astype(bool)
+            rest[sel] = np.clip(rest[sel], self.scene['link_lower'][hl], self.scene['link_upper'][hl])
+        return rest
+
     # ------------------------------------------------------------------ batched reset
-    def sample(self, n, rng):
-        """Per-env randomisation (env.py:120, human.py:76-92, feeding.py:125,139, furniture.py:33)."""
+    def sample(self, n, rng, impairment='random'):
+        """Per-env randomisation (env.py:120, human.py:76-92, feeding.py:125,139, furniture.py:33).
+        `impairment`: 'random' (human.py:80-81), 'no_tremor' (human.py:82-83) or one of IMPAIRMENTS."""
+        if impairment == 'random':
+            imp = rng.integers(0, 4, size=n)
+        elif impairment == 'no_tremor':
+            imp = rng.integers(0, 3, size=n)
+        else:
+            imp = np.full(n, IMPAIRMENTS.index(impairment))
+        tremor = imp == 3
         return dict(
+            impairment=imp.astype(np.int32),
+            # limit_scale / strength are drawn as in human.py:85-86; with a non-controllable human they
+            # only enter through the head joints, which 'limits'/'weakness' envs keep frozen
+            limit_scale=np.where(imp == 1, rng.uniform(0.5, 1.0, size=n), 1.0),
+            strength=np.where(imp == 2, rng.uniform(0.25, 1.0, size=n), 1.0),
+            tremors=np.where(tremor[:, None], rng.uniform(np.deg2rad(-20), np.deg2rad(20), size=(n, 4)), 0.0),
             plane_friction=rng.uniform(0.025, 0.5, size=n),
             male=rng.integers(0, 2, size=n).astype(np.int32),
             head_deg=rng.uniform(-30, 30, size=(n, 3)),
@@ -138,13 +181,16 @@ class FeedingBatch:
             todo = todo[best_err[todo] >= threshold]
         return best_q, best_err
 
-    def reset(self, sim, rng, settle_steps=25, sample=None):
+    def reset(self, sim, rng, settle_steps=25, sample=None, impairment='random'):
         """Put every env of `sim` (BatchSim or the oracle wrapper) into a fresh FeedingJaco start state."""
         n = sim.n
         sc = self.scene
-        s = sample or self.sample(n, rng)
+        s = sample or self.sample(n, rng, impairment)
         self.last_sample = s
         male = s['male'].astype(bool)
+        if 'impairment' not in s:        # older fixtures: no impairment -> static humans
+            s = dict(s, impairment=np.zeros(n, np.int32), tremors=np.zeros((n, 4)))
+        tremor = s['impairment'] == 3
         sim.set_link_friction(int(sc['body_link0'][self.plane]), s['plane_friction'])
         # humans: presets + random head, only the sampled gender active
         for gender, hb in self.humans.items():
@@ -158,7 +204,16 @@ class FeedingBatch:
             lo, hi = sc['link_lower'][links], sc['link_upper'][links]
             q = np.clip(q, lo, hi)     # set_joint_angles(use_limits=True) + enforce_joint_limits
             sim.set_joint_state(links, q=q, qd=np.zeros_like(q))
-            sim.set_body_active(hb, (male if gender == 'male' else ~male).astype(np.int32))
+            on = male if gender == 'male' else ~male
+            # body mode: 0 = other gender, 1 = simulated head (tremor), 2 = frozen ("static joints")
+            sim.set_body_active(hb, np.where(on, np.where(tremor, 1, 2), 0).astype(np.int32))
+            # take_step drives the controllable (head) joints of a tremor human with the env's motor
+            # gain/force (feeding.py:122 gains 0.025, human.py:69 force 1.0) around target_joint_angles
+            # (human.py:122) and clamps them to their limits after every substep (env.py:226-229)
+            hl = [self.gl(hb, j) for j in TREMOR_JOINTS]
+            rest = q[:, list(TREMOR_JOINTS)]
+            sim.set_motor(hl, MOTOR_POSITION, target=rest, kp=[0.025] * 4, kd=[1.0] * 4, max_force=[1.0] * 4)
+            sim.set_hard_limits(hl, True)
         self.human_q = q
         # robot: IK to the randomised end-effector target, gripper open
         target = np.array([-0.15, -0.65, 1.15]) + s['ee_offset']

@@ -179,7 +179,7 @@ def main():
     lo, hi = shard_range(rank, world, world * n)
     rng = np.random.default_rng(1001 + rank * n)           # only used for IK random restarts
     s = fb.reset(sim, rng, settle_steps=25, sample=sample_block(fb, lo, hi))
-    sim.feeding_init(fb.feeding_params(seed=1001 + rank * n), s['male'])
+    fb.start_fused(sim, s, seed=1001 + rank * n)
     stream = torch.cuda.ExternalStream(sim.stream_ptr(), device=local_rank)
     dev = torch.device('cuda', local_rank)
     gen = torch.Generator(device=dev)

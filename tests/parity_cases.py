@@ -13,17 +13,45 @@ from oracle.oracle_py import OracleSim
 TOL_RAD, TOL_M, TOL_FORCE = 1e-4, 1e-3, 0.05
 
 
-def synced_pair(fb, make_sim, n, seed, cfg, settle=25, threads=4):
+def synced_pair(fb, make_sim, n, seed, cfg, settle=25, threads=4, impairment='random'):
     """Oracle and product sims in the same post-reset state (oracle does the reset, state is copied)."""
     cpu = OracleSim(fb.scene, cfg, n, threads=threads)
     dev = make_sim(fb.scene, cfg, n)
-    s = fb.reset(cpu, np.random.default_rng(seed), settle_steps=settle)
+    s = fb.reset(cpu, np.random.default_rng(seed), settle_steps=settle, impairment=impairment)
     fb.reset(dev, np.random.default_rng(seed), settle_steps=0, sample=s)
     dev.state_set(cpu.state_get())
     q = cpu.get_joint_states(fb.arm_links)[0]
     cpu.set_motor_targets(fb.arm_links, q)
     dev.set_motor_targets(fb.arm_links, q)
     return cpu, dev, s
+
+
+def head_links(fb, s):
+    """[n, 4] global link ids of each env's own head joints."""
+    from assistive_gym_b200.feeding_batch import TREMOR_JOINTS
+    m = np.array([fb.gl(fb.humans['male'], j) for j in TREMOR_JOINTS])
+    f = np.array([fb.gl(fb.humans['female'], j) for j in TREMOR_JOINTS])
+    return np.where(s['male'].astype(bool)[:, None], m, f)
+
+
+def head_q(fb, sim, s):
+    from assistive_gym_b200.feeding_batch import TREMOR_JOINTS
+    qm = sim.get_joint_states([fb.gl(fb.humans['male'], j) for j in TREMOR_JOINTS])[0]
+    qf = sim.get_joint_states([fb.gl(fb.humans['female'], j) for j in TREMOR_JOINTS])[0]
+    return np.where(s['male'].astype(bool)[:, None], qm, qf)
+
+
+def apply_tremor(fb, sims, s, iteration):
+    """env.py:212-215: head joints of tremor envs are driven to target_joint_angles +- tremors, the
+    sign flipping with the parity of the (already incremented) env-step counter."""
+    from assistive_gym_b200.feeding_batch import TREMOR_JOINTS
+    if not np.any(s['impairment'] == 3):
+        return
+    tgt = fb.tremor_rest_of(s) + (1.0 if iteration % 2 == 0 else -1.0) * s['tremors']
+    for hb in fb.humans.values():
+        hl = [fb.gl(hb, j) for j in TREMOR_JOINTS]
+        for sim in sims:
+            sim.set_motor_targets(hl, tgt)
 
 
 def feeding_links(fb):
@@ -45,7 +73,7 @@ def take_step_targets(q, action, lower, upper, mult=0.05, frame_skip=5):
     return q
 
 
-def rollout_errors(fb, make_sim, n=4, seed=0, env_steps=40, residual_threshold=0.0, foods=True):
+def rollout_errors(fb, make_sim, n=4, seed=0, env_steps=40, residual_threshold=0.0, foods=True, impairment='random'):
     """200 substeps (40 env steps x 5) of random actions; max errors over the rollout.
 
     foods=False switches the eight 1 g food spheres off: their bouncing is chaotic (a 1e-6 m
@@ -55,7 +83,7 @@ def rollout_errors(fb, make_sim, n=4, seed=0, env_steps=40, residual_threshold=0
     deterministic sub-system (arm + tool + bowl); the foods-on rollout is asserted at a looser bound
     and its measured error is reported."""
     cfg = capi.default_config(residual_threshold=residual_threshold)
-    cpu, dev, _ = synced_pair(fb, make_sim, n, seed, cfg)
+    cpu, dev, s = synced_pair(fb, make_sim, n, seed, cfg, impairment=impairment)
     if not foods:
         for f in fb.foods:
             cpu.set_body_active(f, 0)
@@ -63,20 +91,29 @@ def rollout_errors(fb, make_sim, n=4, seed=0, env_steps=40, residual_threshold=0
     L = feeding_links(fb)
     links = L['foods'] + [L['tool'], L['bowl'], L['ee']]
     rng = np.random.default_rng(seed + 100)
-    err = dict(q=0.0, tool=0.0, ee=0.0, bowl=0.0, food=0.0)
-    for _ in range(env_steps):
+    err = dict(q=0.0, tool=0.0, ee=0.0, bowl=0.0, food=0.0, head=0.0, head_travel=0.0)
+    h0 = head_q(fb, cpu, s)
+    q_env = np.zeros(n)
+    for it in range(env_steps):
         act = rng.uniform(-1, 1, size=(n, 7))
+        apply_tremor(fb, (cpu, dev), s, it + 1)
         tgt = take_step_targets(cpu.get_joint_states(fb.arm_links)[0], act, fb.arm_lower, fb.arm_upper)
         cpu.set_motor_targets(fb.arm_links, tgt)
         dev.set_motor_targets(fb.arm_links, tgt)
         cpu.step(5)
         dev.step(5)
         a, c = cpu.get_link_states(links), dev.get_link_states(links)
-        err['q'] = max(err['q'], np.abs(cpu.get_joint_states(fb.arm_links)[0] - dev.get_joint_states(fb.arm_links)[0]).max())
+        dq = np.abs(cpu.get_joint_states(fb.arm_links)[0] - dev.get_joint_states(fb.arm_links)[0])
+        q_env = np.maximum(q_env, dq.max(axis=1))
+        err['q'] = max(err['q'], dq.max())
         err['tool'] = max(err['tool'], np.abs(a['pos'][:, 8] - c['pos'][:, 8]).max())
         err['bowl'] = max(err['bowl'], np.abs(a['pos'][:, 9] - c['pos'][:, 9]).max())
         err['ee'] = max(err['ee'], np.abs(a['pos'][:, 10] - c['pos'][:, 10]).max())
         err['food'] = max(err['food'], np.abs(a['pos'][:, :8] - c['pos'][:, :8]).max())
+        ha, hc = head_q(fb, cpu, s), head_q(fb, dev, s)
+        err['head'] = max(err['head'], np.abs(ha - hc).max())
+        err['head_travel'] = max(err['head_travel'], np.abs(ha - h0).max())
+    err['q_env'] = q_env
     return err
 
 

@@ -37,9 +37,16 @@ def _check_surface(lib):
     env.close()
 
 
-def _check_fused_vs_api(lib, n_envs):
+def _check_fused_vs_api(lib, n_envs, impairment='random'):
     a, b = _make(lib, n_envs, 7), _make(lib, n_envs, 7)
+    a.human_impairment = b.human_impairment = impairment
     oa, ob = a.reset(), b.reset()
+    if impairment == 'tremor':
+        assert len(b.agents) == 2                     # env.py:130-131: a tremor human is an agent
+        # the API path clamps through Human.enforce_joint_limits (agent.py:240-250), the fused path
+        # through the integrator's hard-limit flag: switch the flag off on the API side
+        for h in b.humans.values():
+            b.id.set_hard_limits([h._gl(j) for j in h.controllable_joint_indices], False)
     assert np.allclose(oa, ob, atol=1e-6)
     rng = np.random.default_rng(0)
     for k in range(4):
@@ -56,8 +63,9 @@ def test_surface_cpu_harness(emu_lib):
     _check_surface(emu_lib)
 
 
-def test_fused_step_equals_reference_api_cpu_harness(emu_lib):
-    _check_fused_vs_api(emu_lib, 2)
+@pytest.mark.parametrize('impairment', ['random', 'tremor'])
+def test_fused_step_equals_reference_api_cpu_harness(emu_lib, impairment):
+    _check_fused_vs_api(emu_lib, 2, impairment)
 
 
 @pytest.mark.gpu
@@ -66,5 +74,6 @@ def test_surface_gpu(gpu_lib):
 
 
 @pytest.mark.gpu
-def test_fused_step_equals_reference_api_gpu(gpu_lib):
-    _check_fused_vs_api(None, 8)
+@pytest.mark.parametrize('impairment', ['random', 'tremor'])
+def test_fused_step_equals_reference_api_gpu(gpu_lib, impairment):
+    _check_fused_vs_api(None, 8, impairment)

@@ -28,6 +28,26 @@ def test_rollout_200_substeps_with_food(feeding, make_sim):
     assert err['q'] < 2e-3 and err['tool'] < 2e-3 and err['ee'] < 2e-3, err
 
 
+def test_rollout_tremor_head(feeding, make_sim):
+    """impairment == tremor in every env: simulated 4-DoF head chain, +-tremor targets, hard limits."""
+    err = pc.rollout_errors(feeding, make_sim, n=8, seed=6, env_steps=40, foods=False, impairment='tremor')
+    print('tremor rollout errors', err)
+    assert err['head_travel'] > 0.02, err
+    assert err['head'] < pc.TOL_RAD and err['q'] < pc.TOL_RAD, err
+    assert err['tool'] < pc.TOL_M and err['bowl'] < pc.TOL_M, err
+
+
+def test_rollout_strict_population(feeding, make_sim):
+    """64 envs x 100 substeps.  PGS stops after exactly 50 iterations; in rare steps an active-set
+    switch (a contact opening/closing) lands on the last iteration in fp64 but not in fp32 and the
+    arm takes a ~1e-4..1e-3 rad kick (both converge to the same answer with more iterations).  The
+    strict tolerance is therefore asserted on the population: the median env and >= 90 % of envs."""
+    err = pc.rollout_errors(feeding, make_sim, n=64, seed=9, env_steps=20, foods=False)
+    q = err['q_env']
+    print('population: median %.3g  p90 %.3g  max %.3g  within tol %.3f' % (np.median(q), np.quantile(q, 0.9), q.max(), (q < pc.TOL_RAD).mean()))
+    assert np.median(q) < 1e-5 and (q < pc.TOL_RAD).mean() >= 0.9 and q.max() < 5e-3, err
+
+
 def test_onestep_synchronised(feeding, make_sim):
     err = pc.onestep_errors(feeding, make_sim, n=8, seed=1, steps=30)
     print('one-step errors', err)
@@ -51,12 +71,13 @@ def test_tool_on_body_contact(feeding, make_sim):
     assert res['pos'] < pc.TOL_M and res['tool_pos'] < pc.TOL_M, res
 
 
-def test_fused_feeding_step_semantics(feeding, make_sim):
+@pytest.mark.parametrize('impairment', ['random', 'tremor'])
+def test_fused_feeding_step_semantics(feeding, make_sim, impairment):
     fb = feeding
     n = 8
     cfg = capi.default_config(residual_threshold=0.0)
-    cpu, dev, s = pc.synced_pair(fb, make_sim, n, 3, cfg)
-    dev.feeding_init(fb.feeding_params(), s['male'])
+    cpu, dev, s = pc.synced_pair(fb, make_sim, n, 3, cfg, impairment=impairment)
+    fb.start_fused(dev, s)
     st = dict(male=s['male'], foods=np.ones((n, 8), dtype=bool), active=np.ones((n, 8), dtype=bool),
               iteration=np.zeros(n, dtype=int), task_success=np.zeros(n, dtype=int))
     rng = np.random.default_rng(11)
@@ -64,6 +85,7 @@ def test_fused_feeding_step_semantics(feeding, make_sim):
         act = rng.uniform(-1.5, 1.5, size=(n, 7)).astype(np.float32)
         tgt = pc.take_step_targets(cpu.get_joint_states(fb.arm_links)[0], act, fb.arm_lower, fb.arm_upper)
         cpu.set_motor_targets(fb.arm_links, tgt)
+        pc.apply_tremor(fb, (cpu,), s, k + 1)
         cpu.step(5)
         obs_ref, rew_ref, done_ref, _ = pc.feeding_semantics_reference(fb, cpu, act, st)
         obs, rew, done, info = dev.feeding_step_host(act)
@@ -112,7 +134,7 @@ def test_batch4096_properties(feeding, make_sim):
     q0 = dev.get_joint_states(fb.arm_links)[0]
     dev.set_motor_targets(fb.arm_links, q0)
     dev.step(25)
-    dev.feeding_init(fb.feeding_params(), s['male'])
+    fb.start_fused(dev, s)
     act = np.zeros((n, 7), dtype=np.float32)
     arng = np.random.default_rng(1)
     for i in range(4):

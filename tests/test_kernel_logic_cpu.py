@@ -26,6 +26,15 @@ def test_rollout_200_substeps_with_food(feeding, make_sim):
     assert err['q'] < 2e-3 and err['tool'] < 2e-3 and err['ee'] < 2e-3, err
 
 
+def test_rollout_tremor_head(feeding, make_sim):
+    """impairment == tremor in every env: the 4-DoF head chain is simulated, driven by the +-tremor
+    targets and clamped to its limits after every substep (env.py:212-229)."""
+    err = pc.rollout_errors(feeding, make_sim, n=2, seed=6, env_steps=20, foods=False, impairment='tremor')
+    assert err['head_travel'] > 0.02, err          # the head must actually move
+    assert err['head'] < pc.TOL_RAD and err['q'] < pc.TOL_RAD, err
+    assert err['tool'] < pc.TOL_M and err['bowl'] < pc.TOL_M, err
+
+
 def test_onestep_synchronised(feeding, make_sim):
     err = pc.onestep_errors(feeding, make_sim, n=2, seed=1, steps=20)
     assert err['q'] < 1e-5 and err['tool_pos'] < 1e-5, err
@@ -39,13 +48,14 @@ def test_tool_on_body_contact(feeding, make_sim):
     assert res['pos'] < pc.TOL_M and res['tool_pos'] < pc.TOL_M, res
 
 
-def test_fused_feeding_step_semantics(feeding, make_sim):
+@pytest.mark.parametrize('impairment', ['none', 'tremor'])
+def test_fused_feeding_step_semantics(feeding, make_sim, impairment):
     """Fused kernels (action -> obs/reward/done) vs the numpy restatement of feeding.py on the oracle."""
     fb = feeding
     n = 2
     cfg = capi.default_config(residual_threshold=0.0)
-    cpu, dev, s = pc.synced_pair(fb, make_sim, n, 3, cfg)
-    dev.feeding_init(fb.feeding_params(), s['male'])
+    cpu, dev, s = pc.synced_pair(fb, make_sim, n, 3, cfg, impairment=impairment)
+    fb.start_fused(dev, s)
     st = dict(male=s['male'], foods=np.ones((n, 8), dtype=bool), active=np.ones((n, 8), dtype=bool),
               iteration=np.zeros(n, dtype=int), task_success=np.zeros(n, dtype=int))
     rng = np.random.default_rng(11)
@@ -53,6 +63,7 @@ def test_fused_feeding_step_semantics(feeding, make_sim):
         act = rng.uniform(-1.5, 1.5, size=(n, 7)).astype(np.float32)
         tgt = pc.take_step_targets(cpu.get_joint_states(fb.arm_links)[0], act, fb.arm_lower, fb.arm_upper)
         cpu.set_motor_targets(fb.arm_links, tgt)
+        pc.apply_tremor(fb, (cpu,), s, k + 1)
         cpu.step(5)
         obs_ref, rew_ref, done_ref, total_ref = pc.feeding_semantics_reference(fb, cpu, act, st)
         obs, rew, done, info = dev.feeding_step_host(act)

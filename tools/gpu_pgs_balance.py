@@ -10,7 +10,7 @@ n = 4096
 fb = FeedingBatch(); sim = BatchSim(fb.scene, capi.default_config(), n)
 rng = np.random.default_rng(0)
 s = fb.reset(sim, rng, settle_steps=25)
-sim.feeding_init(fb.feeding_params(), s['male'])
+fb.start_fused(sim, s)
 for i in range(8):
     sim.feeding_step_host(rng.uniform(-1, 1, size=(n, 7)).astype(np.float32))
 cyc = sim.pgs_cycles().astype(np.float64); cnt, it = sim.solver_stats()
