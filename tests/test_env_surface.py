@@ -42,7 +42,7 @@ def _check_fused_vs_api(lib, n_envs, impairment='random'):
     a.human_impairment = b.human_impairment = impairment
     oa, ob = a.reset(), b.reset()
     if impairment == 'tremor':
-        assert len(b.agents) == 2                     # env.py:130-131: a tremor human is an agent
+        assert len(b.agents) >= 2                     # env.py:130-131: a tremor human is an agent
         # the API path clamps through Human.enforce_joint_limits (agent.py:240-250), the fused path
         # through the integrator's hard-limit flag: switch the flag off on the API side
         for h in b.humans.values():
