@@ -676,513 +676,8 @@ AG_HDN inline void dyn_body(int e, const SimDev& S, const KP&) {
   }
 }
 
-// ------------------------------------------------------------------ K6: constraint rows
-// side reference encoding: (idx << 2) | kind, kind: 0 static, 1 free body (idx = f), 2 articulated (idx = dyn link)
-AG_HD int link_ref(const SimDev& S, int e, int link) {
-  int b = AG_LDG(S.link_body + link);
-  int kind = AG_LDG(S.body_kind + b);
-  if (S.body_mode[(size_t)b * S.N + e] != 1) return 0;
-  if (kind == BK_FREE) return (AG_LDG(S.body_idx + b) << 2) | 1;
-  if (kind == BK_ART) { int d = AG_LDG(S.link_dl + link); return d < 0 ? 0 : ((d << 2) | 2); }
-  return 0;
-}
+// K6 (constraint rows) and K7 (PGS) live in ag_solver.cuh
 
-AG_HD s3 ld_Iinv(const SimDev& S, int f, int e) {
-  size_t ib = (size_t)f * 6 * S.N + e; size_t N = S.N;
-  s3 r; r.xx = S.fIinv[ib]; r.yy = S.fIinv[ib + N]; r.zz = S.fIinv[ib + 2 * N]; r.xy = S.fIinv[ib + 3 * N]; r.xz = S.fIinv[ib + 4 * N]; r.yz = S.fIinv[ib + 5 * N];
-  return r;
-}
-
-// Fill the articulated side slot `as` with J (unit force `lin` at world point p + torque `ang` on dyn link d)
-// and M^-1 J^T; returns J M^-1 J^T and accumulates J.qd into rel.
-AG_HDN inline float art_side(const SimDev& S, int e, int as, int d, f3 p, f3 lin, f3 ang, float& rel) {
-  const int N = S.N;
-  float J[AG_MAXND];
-  int a = AG_LDG(S.dl_art + d), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
-  for (int i = 0; i < nd; i++) J[i] = 0.f;
-  int j = d;
-  while (j >= 0) {
-    f3 axw = ld3(S.jax, j, N, e), o = ld3(S.jor, j, N, e);
-    J[j - d0] = (AG_LDG(S.dl_type + j) == 1) ? (dot(lin, cross(axw, p - o)) + dot(ang, axw)) : dot(lin, axw);
-    j = AG_LDG(S.dl_parent + j);
-  }
-  float diag = 0.f;
-  for (int i = 0; i < nd; i++) {
-    float m = 0.f;
-    for (int k = 0; k < nd; k++) m += S.Minv[((size_t)(d0 + i) * S.ND + (d0 + k)) * N + e] * J[k];
-    S.as_J[((size_t)as * AG_MAXND + i) * N + e] = J[i];
-    S.as_MiJ[((size_t)as * AG_MAXND + i) * N + e] = m;
-    diag += J[i] * m;
-    rel += J[i] * ld1(S.jqd, AG_LDG(S.dl_link + d0 + i), N, e);
-  }
-  return diag;
-}
-
-// diag and relative velocity contribution of one side for direction `dir` (force on this side = sign*dir at p)
-AG_HDN inline float side_terms(const SimDev& S, int e, int ref, int as, f3 p, f3 lin, f3 ang, float& rel) {
-  int kind = ref & 3, idx = ref >> 2;
-  if (kind == 1) {
-    int b = AG_LDG(S.free_body + idx);
-    float invm = 1.0f / AG_LDG(S.link_mass + AG_LDG(S.body_link0 + b));
-    f3 r = p - ld3(S.fcom, idx, S.N, e);
-    f3 t = cross(r, lin) + ang;
-    s3 Ii = ld_Iinv(S, idx, e);
-    f3 v = ld3(S.base_lin, b, S.N, e), w = ld3(S.base_ang, b, S.N, e);
-    rel += dot(lin, v) + dot(t, w);
-    return invm * dot(lin, lin) + dot(t, mul(Ii, t));
-  } else if (kind == 2) {
-    return art_side(S, e, as, idx, p, lin, ang, rel);
-  }
-  return 0.f;
-}
-
-// K6a: one lane per env: joint-limit rows, motor rows, fixed-constraint rows
-AG_HDN inline void rows_body(int e, const SimDev& S, const KP&) {
-  const int N = S.N;
-  const float dt = S.dt;
-  S.as_count[e] = 6 * S.ncon;   // art-side slots [0, 6 ncon) are reserved for side A/B of the fixed constraints
-  for (int d = 0; d < S.ND; d++) {
-    int k = AG_LDG(S.dl_link + d);
-    float Mdd = S.Minv[((size_t)d * S.ND + d) * N + e];
-    float q = ld1(S.jq, k, N, e), qd = ld1(S.jqd, k, N, e);
-    float dinv = Mdd > 0.f ? 1.0f / Mdd : 0.f;
-    // limits: a row only while violated
-    float rl = 0.f, dl = 0.f, ru = 0.f, du = 0.f;
-    if (AG_LDG(S.link_haslimit + k) && dinv > 0.f) {
-      float penl = q - AG_LDG(S.link_lower + k), penu = AG_LDG(S.link_upper + k) - q;
-      if (penl <= 0.f) { dl = dinv; rl = (-penl * S.erp / dt - qd) * dinv; }
-      if (penu <= 0.f) { du = dinv; ru = (-penu * S.erp / dt + qd) * dinv; }
-    }
-    st1(S.dr_rhs, d, N, e, rl); st1(S.dr_dinv, d, N, e, dl); st1(S.dr_lam, d, N, e, 0.f);
-    st1(S.dr_rhs, S.ND + d, N, e, ru); st1(S.dr_dinv, S.ND + d, N, e, du); st1(S.dr_lam, S.ND + d, N, e, 0.f);
-    // motor
-    float rm = 0.f, dm = 0.f;
-    int mode = S.motor_mode[k];
-    float maxi = S.motor_maxf[k] * dt;
-    if (mode != 0 && maxi > 0.f && dinv > 0.f) {
-      float vt = (mode == 1) ? (S.motor_kp[k] * (ld1(S.motor_target, k, N, e) - q) / dt + qd - S.motor_kd[k] * qd)
-                             : ld1(S.motor_target, k, N, e);
-      dm = dinv; rm = (vt - qd) * dinv;
-    }
-    st1(S.dr_rhs, 2 * S.ND + d, N, e, rm); st1(S.dr_dinv, 2 * S.ND + d, N, e, dm); st1(S.dr_lam, 2 * S.ND + d, N, e, 0.f);
-  }
-  for (int c = 0; c < S.ncon; c++) {
-    int ka = AG_LDG(S.con_link + 2 * c), kb = AG_LDG(S.con_link + 2 * c + 1);
-    int refA = link_ref(S, e, ka), refB = link_ref(S, e, kb);
-    int ba = AG_LDG(S.link_body + ka), bb = AG_LDG(S.link_body + kb);
-    bool on = S.body_mode[(size_t)ba * N + e] != 0 && S.body_mode[(size_t)bb * N + e] != 0;
-    q4 qa = ld4(S.lquat, ka, N, e), qb = ld4(S.lquat, kb, N, e);
-    f3 pa = ld3(S.lpos, ka, N, e) + qrot(qa, tv3(S.con_pivot, 2 * c));
-    f3 pb = ld3(S.lpos, kb, N, e) + qrot(qb, tv3(S.con_pivot, 2 * c + 1));
-    q4 fa = qmul(qa, tv4(S.con_quat, 2 * c)), fb = qmul(qb, tv4(S.con_quat, 2 * c + 1));
-    q4 qe = qmul(fa, qconj(fb));
-    if (qe.w < 0.f) qe = q4(-qe.x, -qe.y, -qe.z, -qe.w);
-    f3 perr = pa - pb, aerr(2.f * qe.x, 2.f * qe.y, 2.f * qe.z);
-    float maxi = AG_LDG(S.con_maxforce + c) * dt;
-    for (int i = 0; i < 6; i++) {
-      int r = 6 * c + i;
-      f3 axv(i % 3 == 0 ? 1.f : 0.f, i % 3 == 1 ? 1.f : 0.f, i % 3 == 2 ? 1.f : 0.f);
-      f3 lin = i < 3 ? axv : f3(), ang = i < 3 ? f3() : axv;
-      float rel = 0.f, diag = 0.f;
-      // art-side slots: side A uses slot r (two-sided articulated constraints share: B uses 6 ncon + ... not supported)
-      diag += side_terms(S, e, refA, r, pa, lin, ang, rel);
-      float relb = 0.f;
-      int asB = -1;
-      if ((refB & 3) == 2) { asB = ag_atomic_inc(S.as_count + e); if (asB >= S.nas) { asB = -1; } }
-      if ((refB & 3) != 2 || asB >= 0) diag += side_terms(S, e, refB, asB, pb, -lin, -ang, relb);
-      rel += relb;
-      float err = i < 3 ? comp(perr, i) : comp(aerr, i - 3);
-      float dinv = (on && diag > 1e-20f) ? 1.0f / diag : 0.f;
-      size_t gb = (size_t)r * 16 * N + e;
-      f3 angA = f3(), angB = f3();
-      if ((refA & 3) == 1) { angA = cross(pa - ld3(S.fcom, refA >> 2, N, e), lin) + ang; }
-      if ((refB & 3) == 1) { angB = cross(pb - ld3(S.fcom, refB >> 2, N, e), lin) + ang; }
-      S.gr_data[gb + (size_t)GR_LX * N] = lin.x; S.gr_data[gb + (size_t)GR_LY * N] = lin.y; S.gr_data[gb + (size_t)GR_LZ * N] = lin.z;
-      S.gr_data[gb + (size_t)GR_AAX * N] = angA.x; S.gr_data[gb + (size_t)GR_AAY * N] = angA.y; S.gr_data[gb + (size_t)GR_AAZ * N] = angA.z;
-      S.gr_data[gb + (size_t)GR_ABX * N] = angB.x; S.gr_data[gb + (size_t)GR_ABY * N] = angB.y; S.gr_data[gb + (size_t)GR_ABZ * N] = angB.z;
-      S.gr_data[gb + (size_t)GR_RHS * N] = (-err * S.erp / dt - rel) * dinv;
-      S.gr_data[gb + (size_t)GR_DINV * N] = dinv;
-      S.gr_data[gb + (size_t)GR_LO * N] = -maxi; S.gr_data[gb + (size_t)GR_HI * N] = maxi;
-      S.gr_data[gb + (size_t)GR_LAM * N] = 0.f;
-      size_t rb = (size_t)r * 4 * N + e;
-      S.gr_ref[rb] = refA; S.gr_ref[rb + N] = refB; S.gr_ref[rb + 2 * (size_t)N] = ((refA & 3) == 2) ? r : -1; S.gr_ref[rb + 3 * (size_t)N] = asB;
-    }
-  }
-}
-
-// K6b: contact rows, thread = (sorted slot, env)
-AG_HDN inline void crows_body(int tid, const SimDev& S, const KP&) {
-  const int N = S.N;
-  int e = tid % N, slot = tid / N;
-  int cnt = S.c_count[e]; if (cnt > S.maxc) cnt = S.maxc;
-  if (slot >= cnt) return;
-  unsigned key = S.s_key[(size_t)slot * N + e];
-  unsigned pairk = key >> 2;
-  int ca = (int)(pairk / (unsigned)S.nc), cb = (int)(pairk % (unsigned)S.nc);
-  int ka = AG_LDG(S.col_link + ca), kb = AG_LDG(S.col_link + cb);
-  int refA = link_ref(S, e, ka), refB = link_ref(S, e, kb);
-  f3 pa(cf_ld(S.s_data, slot, CF_PAX, N, e), cf_ld(S.s_data, slot, CF_PAY, N, e), cf_ld(S.s_data, slot, CF_PAZ, N, e));
-  f3 pb(cf_ld(S.s_data, slot, CF_PBX, N, e), cf_ld(S.s_data, slot, CF_PBY, N, e), cf_ld(S.s_data, slot, CF_PBZ, N, e));
-  f3 n(cf_ld(S.s_data, slot, CF_NX, N, e), cf_ld(S.s_data, slot, CF_NY, N, e), cf_ld(S.s_data, slot, CF_NZ, N, e));
-  float dist = cf_ld(S.s_data, slot, CF_DIST, N, e);
-  int asA = -1, asB = -1;
-  if ((refA & 3) == 2) { asA = ag_atomic_add(S.as_count + e, 3); if (asA + 3 > S.nas) { asA = -1; refA = 0; } }
-  if ((refB & 3) == 2) { asB = ag_atomic_add(S.as_count + e, 3); if (asB + 3 > S.nas) { asB = -1; refB = 0; } }
-  f3 t1, t2; plane_space(n, t1, t2);
-  float mu = ld1(S.friction, ka, N, e) * ld1(S.friction, kb, N, e);
-  float dt = S.dt;
-  for (int d = 0; d < 3; d++) {
-    f3 dir = d == 0 ? n : (d == 1 ? t1 : t2);
-    float rel = 0.f, diag = 0.f;
-    diag += side_terms(S, e, refA, asA + d, pa, dir, f3(), rel);
-    diag += side_terms(S, e, refB, asB + d, pb, -dir, f3(), rel);
-    float dinv = diag > 1e-20f ? 1.0f / diag : 0.f;
-    float rhs;
-    if (d == 0) {
-      float pen = dist + S.slop;
-      float poserr, velerr = -rel;
-      if (pen > 0.f) { poserr = 0.f; velerr -= pen / dt; } else poserr = -pen * S.contact_erp / dt;
-      rhs = (poserr + velerr) * dinv;
-    } else rhs = -rel * dinv;
-    cf_st(S.s_data, slot, CF_RHS_N + 2 * d, N, e, rhs);
-    cf_st(S.s_data, slot, CF_DINV_N + 2 * d, N, e, dinv);
-    cf_st(S.s_data, slot, CF_LAM_N + d, N, e, 0.f);
-  }
-  cf_st(S.s_data, slot, CF_MU, N, e, mu);
-  size_t rb = (size_t)slot * 4 * N + e;
-  S.s_ref[rb] = refA; S.s_ref[rb + N] = refB; S.s_ref[rb + 2 * (size_t)N] = asA; S.s_ref[rb + 3 * (size_t)N] = asB;
-}
-
-// ------------------------------------------------------------------ K7: PGS
-// One env per lane, a few lanes per CTA (AG_PGS_LANES, default 4).  The Gauss-Seidel chain of one env
-// is strictly sequential, so the kernel is latency-bound per row; measured on B200 (ncu, round 1):
-// with row constants read from global memory every iteration a row cost ~2 200 cycles (serialised L2
-// round trips, 17 % L1 hit rate).  Therefore EVERYTHING the sweep touches is staged once into shared
-// memory (`sm`, lane-strided => conflict-free): velocity deltas, per-body inverse inertias / COMs,
-// the articulated M^-1, all row constants (contacts, dof rows, fixed-constraint rows incl. their
-// articulated Jacobian sides) and all impulses.  Only the rare articulated sides of contact rows stay
-// in global memory.  Layout (floats per lane):
-//   [dv: ND+6nf][fcom: 3nf][fIinv: 6nf][invm: nf][Minv: ND*ND][lam: 3*maxc][dr: 5*(3ND)][gr: ngr*(16+2ND)][crec: 20*maxc][art sides: nas*2ND]
-#define PGS_CREC 20
-struct PgsLayout { int o_dv, o_fc, o_fi, o_fm, o_mi, o_lam, o_dr, o_gr, o_cr, o_as, total; };
-AG_HD PgsLayout pgs_layout(const SimDev& S) {
-  PgsLayout L;
-  L.o_dv = 0; L.o_fc = L.o_dv + S.ND + 6 * S.nf; L.o_fi = L.o_fc + 3 * S.nf; L.o_fm = L.o_fi + 6 * S.nf; L.o_mi = L.o_fm + S.nf;
-  L.o_lam = L.o_mi + S.ND * S.ND; L.o_dr = L.o_lam + 3 * S.maxc; L.o_gr = L.o_dr + 15 * S.ND;
-  L.o_cr = L.o_gr + S.ngr * (16 + 2 * S.ND); L.o_as = L.o_cr + PGS_CREC * S.maxc; L.total = L.o_as + S.nas * 2 * S.ND;
-  return L;
-}
-#define SMF(i) sm[(i) * LANES]
-AG_HD float i2f_bits(int v) { float f; memcpy(&f, &v, 4); return f; }
-AG_HD int f2i_bits(float f) { int v; memcpy(&v, &f, 4); return v; }
-
-// J.dv of one side.  `artJ` >= 0: offset in sm of this side's articulated Jacobian (else global slot `as`)
-template <int LANES>
-AG_HD float pgs_side_jv(const SimDev& S, int e, const float* sm, const PgsLayout& L, int ref, int as, int artJ, f3 lin, f3 ang_free) {
-  int kind = ref & 3, idx = ref >> 2;
-  if (kind == 1) {
-    int o = L.o_dv + S.ND + 6 * idx;
-    return lin.x * SMF(o) + lin.y * SMF(o + 1) + lin.z * SMF(o + 2) + ang_free.x * SMF(o + 3) + ang_free.y * SMF(o + 4) + ang_free.z * SMF(o + 5);
-  } else if (kind == 2) {
-    int a = AG_LDG(S.dl_art + idx), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
-    float t = 0.f;
-    if (artJ < 0) artJ = L.o_as + as * 2 * S.ND;          // staged copy of as_J[as]
-    for (int i = 0; i < nd; i++) t += SMF(artJ + i) * SMF(L.o_dv + d0 + i);
-    return t;
-  }
-  return 0.f;
-}
-template <int LANES>
-AG_HD void pgs_side_apply(const SimDev& S, int e, float* sm, const PgsLayout& L, int ref, int as, int artM, f3 lin, f3 ang_free, float dl) {
-  int kind = ref & 3, idx = ref >> 2;
-  if (kind == 1) {
-    int o = L.o_dv + S.ND + 6 * idx;
-    float invm = SMF(L.o_fm + idx) * dl;
-    int fi = L.o_fi + 6 * idx;
-    s3 Ii; Ii.xx = SMF(fi); Ii.yy = SMF(fi + 1); Ii.zz = SMF(fi + 2); Ii.xy = SMF(fi + 3); Ii.xz = SMF(fi + 4); Ii.yz = SMF(fi + 5);
-    f3 ia = mul(Ii, ang_free);
-    SMF(o) += lin.x * invm; SMF(o + 1) += lin.y * invm; SMF(o + 2) += lin.z * invm;
-    SMF(o + 3) += ia.x * dl; SMF(o + 4) += ia.y * dl; SMF(o + 5) += ia.z * dl;
-  } else if (kind == 2) {
-    int a = AG_LDG(S.dl_art + idx), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
-    if (artM < 0) artM = L.o_as + as * 2 * S.ND + S.ND;   // staged copy of as_MiJ[as]
-    for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += SMF(artM + i) * dl;
-  }
-}
-
-// K6c: longest-processing-time-first order for K7.  The PGS chain of an env is sequential and its
-// length varies 10x between envs (iterations used x rows), so CTAs are issued heaviest-first and envs
-// of similar weight share a warp.  Work is predicted from this substep's contact count and the
-// previous substep's iteration count.  64-bucket counting sort; p.p1 = histogram[64] (zeroed).
-AG_HD int pgs_work_bucket(const SimDev& S, int e) {
-  int cnt = S.c_count[e]; if (cnt > S.maxc) cnt = S.maxc;
-  int it = S.iters_used[e]; if (it < 1) it = 1;
-  int w = it * (3 * cnt + 3 * S.ND + S.ngr);          // predicted row updates
-  int b = 63 - w / 320;                               // heaviest work -> bucket 0
-  return b < 0 ? 0 : b;
-}
-AG_HDN inline void order_hist_body(int e, const SimDev& S, const KP& p) {
-  ag_atomic_inc((int*)p.p1 + pgs_work_bucket(S, e));
-}
-AG_HDN inline void order_scatter_body(int e, const SimDev& S, const KP& p) {
-  // p.p1 = exclusive prefix of the histogram (consumed by atomic increments)
-  int pos = ag_atomic_inc((int*)p.p1 + pgs_work_bucket(S, e));
-  S.pgs_order[pos] = e;
-}
-AG_HDN inline void order_prefix_body(int tid, const SimDev&, const KP& p) {
-  if (tid != 0) return;
-  int* h = (int*)p.p1; int acc = 0;
-  for (int b = 0; b < 64; b++) { int c = h[b]; h[b] = acc; acc += c; }
-}
-
-template <int LANES>
-AG_HDN inline void pgs_body(int slot, const SimDev& S, const KP&, float* sm) {
-  const int e = S.pgs_order[slot];
-  const int N = S.N;
-  const int ND = S.ND;
-  const PgsLayout L = pgs_layout(S);
-  const int nvel = ND + 6 * S.nf;
-#if defined(__CUDA_ARCH__)
-  long long t_begin = clock64();
-#endif
-  // ---- stage the per-env solver state and all row constants into shared memory
-  for (int i = 0; i < nvel; i++) SMF(L.o_dv + i) = 0.f;
-  for (int i = 0; i < 3 * S.nf; i++) SMF(L.o_fc + i) = S.fcom[(size_t)i * N + e];
-  for (int i = 0; i < 6 * S.nf; i++) SMF(L.o_fi + i) = S.fIinv[(size_t)i * N + e];
-  for (int i = 0; i < S.nf; i++) SMF(L.o_fm + i) = AG_LDG(S.free_invm + i);
-  for (int i = 0; i < ND * ND; i++) SMF(L.o_mi + i) = S.Minv[(size_t)i * N + e];
-  int cnt = S.c_count[e]; if (cnt > S.maxc) cnt = S.maxc;
-  for (int i = 0; i < 3 * cnt; i++) SMF(L.o_lam + i) = 0.f;
-  for (int r = 0; r < 3 * ND; r++) {      // dof rows: lambda, rhs, dinv, lo, hi
-    int d = r % ND;
-    float hi = (r / ND == 2) ? S.motor_maxf[AG_LDG(S.dl_link + d)] * S.dt : 1e30f;
-    SMF(L.o_dr + 5 * r) = 0.f; SMF(L.o_dr + 5 * r + 1) = S.dr_rhs[(size_t)r * N + e]; SMF(L.o_dr + 5 * r + 2) = S.dr_dinv[(size_t)r * N + e];
-    SMF(L.o_dr + 5 * r + 3) = (r / ND == 2) ? -hi : 0.f; SMF(L.o_dr + 5 * r + 4) = hi;
-  }
-  const int GRW = 16 + 2 * ND;
-  for (int r = 0; r < S.ngr; r++) {       // fixed-constraint rows: 16 fields (GR_LAM reused as lambda, PAD0/1 = refs) + art sides
-    int o = L.o_gr + r * GRW;
-    const float* g = S.gr_data + (size_t)r * 16 * N + e;
-    for (int f = 0; f < 14; f++) SMF(o + f) = g[(size_t)f * N];
-    SMF(o + GR_LAM) = 0.f;
-    const int* rf = S.gr_ref + (size_t)r * 4 * N + e;
-    int refA = rf[0], refB = rf[N], asA = rf[2 * (size_t)N], asB = rf[3 * (size_t)N];
-    SMF(o + GR_PAD0) = i2f_bits(refA); SMF(o + GR_PAD1) = i2f_bits(refB);
-    // articulated side (at most one side of a fixed constraint is staged; a second one falls back to global)
-    int as = (refA & 3) == 2 ? asA : ((refB & 3) == 2 ? asB : -1);
-    for (int i = 0; i < ND; i++) {
-      SMF(o + 16 + i) = as >= 0 ? S.as_J[((size_t)as * AG_MAXND + i) * N + e] : 0.f;
-      SMF(o + 16 + ND + i) = as >= 0 ? S.as_MiJ[((size_t)as * AG_MAXND + i) * N + e] : 0.f;
-    }
-  }
-  for (int s = 0; s < cnt; s++) {         // contact records
-    int o = L.o_cr + s * PGS_CREC;
-    const float* c = S.s_data + (size_t)s * AG_CF * N + e;
-    const int* rf = S.s_ref + (size_t)s * 4 * N + e;
-    int refA = rf[0], refB = rf[N], asA = rf[2 * (size_t)N], asB = rf[3 * (size_t)N];
-    f3 pa(c[(size_t)CF_PAX * N], c[(size_t)CF_PAY * N], c[(size_t)CF_PAZ * N]);
-    f3 pb(c[(size_t)CF_PBX * N], c[(size_t)CF_PBY * N], c[(size_t)CF_PBZ * N]);
-    f3 rA, rB;
-    if ((refA & 3) == 1) { int q = L.o_fc + 3 * (refA >> 2); rA = f3(pa.x - SMF(q), pa.y - SMF(q + 1), pa.z - SMF(q + 2)); }
-    if ((refB & 3) == 1) { int q = L.o_fc + 3 * (refB >> 2); rB = f3(pb.x - SMF(q), pb.y - SMF(q + 1), pb.z - SMF(q + 2)); }
-    SMF(o) = c[(size_t)CF_NX * N]; SMF(o + 1) = c[(size_t)CF_NY * N]; SMF(o + 2) = c[(size_t)CF_NZ * N];
-    SMF(o + 3) = rA.x; SMF(o + 4) = rA.y; SMF(o + 5) = rA.z; SMF(o + 6) = rB.x; SMF(o + 7) = rB.y; SMF(o + 8) = rB.z;
-    SMF(o + 9) = c[(size_t)CF_RHS_N * N]; SMF(o + 10) = c[(size_t)CF_DINV_N * N];
-    SMF(o + 11) = c[(size_t)CF_RHS_T1 * N]; SMF(o + 12) = c[(size_t)CF_DINV_T1 * N];
-    SMF(o + 13) = c[(size_t)CF_RHS_T2 * N]; SMF(o + 14) = c[(size_t)CF_DINV_T2 * N];
-    SMF(o + 15) = c[(size_t)CF_MU * N];
-    SMF(o + 16) = i2f_bits(refA); SMF(o + 17) = i2f_bits(refB); SMF(o + 18) = i2f_bits(asA); SMF(o + 19) = i2f_bits(asB);
-  }
-  {                                        // articulated row sides allocated by k_rows / k_crows
-    int nas_used = S.as_count[e]; if (nas_used > S.nas) nas_used = S.nas;
-    for (int a = 0; a < nas_used; a++)
-      for (int i = 0; i < ND; i++) {
-        SMF(L.o_as + a * 2 * ND + i) = S.as_J[((size_t)a * AG_MAXND + i) * N + e];
-        SMF(L.o_as + a * 2 * ND + ND + i) = S.as_MiJ[((size_t)a * AG_MAXND + i) * N + e];
-      }
-  }
-  int used = 0;
-  bool done = false;
-#if defined(__CUDA_ARCH__)
-  const unsigned wmask = __activemask();
-#endif
-  for (int it = 0; it < S.iters; it++) {
-    if (!done) {
-      float resid = 0.f;
-      used = it + 1;
-      // joint limits (lower, upper) then motors: J = +-e_d
-      for (int r = 0; r < 3 * ND; r++) {
-        float dinv = SMF(L.o_dr + 5 * r + 2);
-        if (dinv == 0.f) continue;
-        int d = r % ND; int kindr = r / ND;
-        float sgn = kindr == 1 ? -1.f : 1.f;
-        float lam = SMF(L.o_dr + 5 * r);
-        float dl = SMF(L.o_dr + 5 * r + 1) - sgn * SMF(L.o_dv + d) * dinv;
-        float lo = SMF(L.o_dr + 5 * r + 3), hi = SMF(L.o_dr + 5 * r + 4);
-        float sum = lam + dl;
-        if (sum < lo) { dl = lo - lam; sum = lo; } else if (sum > hi) { dl = hi - lam; sum = hi; }
-        SMF(L.o_dr + 5 * r) = sum;
-        int a = AG_LDG(S.dl_art + d), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
-        float sdl = sgn * dl;
-        for (int i = 0; i < nd; i++) SMF(L.o_dv + d0 + i) += SMF(L.o_mi + (d0 + i) * ND + d) * sdl;
-        resid = fmaxf(resid, dl * dl);
-      }
-      // fixed constraints
-      for (int r = 0; r < S.ngr; r++) {
-        int o = L.o_gr + r * GRW;
-        float dinv = SMF(o + GR_DINV);
-        if (dinv == 0.f) continue;
-        int refA = f2i_bits(SMF(o + GR_PAD0)), refB = f2i_bits(SMF(o + GR_PAD1));
-        f3 lin(SMF(o + GR_LX), SMF(o + GR_LY), SMF(o + GR_LZ));
-        f3 aA(SMF(o + GR_AAX), SMF(o + GR_AAY), SMF(o + GR_AAZ)), aB(SMF(o + GR_ABX), SMF(o + GR_ABY), SMF(o + GR_ABZ));
-        bool aArt = (refA & 3) == 2;      // which side owns the staged articulated rows
-        const int* rf = S.gr_ref + (size_t)r * 4 * N + e;
-        int asB = (!aArt || (refB & 3) != 2) ? -1 : AG_LDG(rf + 3 * (size_t)N);
-        float jv = pgs_side_jv<LANES>(S, e, sm, L, refA, -1, aArt ? o + 16 : -1, lin, aA) +
-                   pgs_side_jv<LANES>(S, e, sm, L, refB, asB, (!aArt && (refB & 3) == 2) ? o + 16 : -1, -lin, -aB);
-        float lam = SMF(o + GR_LAM);
-        float dl = SMF(o + GR_RHS) - jv * dinv;
-        float lo = SMF(o + GR_LO), hi = SMF(o + GR_HI);
-        float sum = lam + dl;
-        if (sum < lo) { dl = lo - lam; sum = lo; } else if (sum > hi) { dl = hi - lam; sum = hi; }
-        SMF(o + GR_LAM) = sum;
-        pgs_side_apply<LANES>(S, e, sm, L, refA, -1, aArt ? o + 16 + ND : -1, lin, aA, dl);
-        pgs_side_apply<LANES>(S, e, sm, L, refB, asB, (!aArt && (refB & 3) == 2) ? o + 16 + ND : -1, -lin, -aB, dl);
-        resid = fmaxf(resid, dl * dl);
-      }
-      // contact normals.  Free-body sides are held in registers for the whole row (one LDS round for the
-      // velocities, one for the inverse inertia, one STS round) instead of read-modify-write per component.
-      for (int s = 0; s < cnt; s++) {
-        int o = L.o_cr + s * PGS_CREC;
-        float dinv = SMF(o + 10);
-        if (dinv == 0.f) continue;
-        int refA = f2i_bits(SMF(o + 16)), refB = f2i_bits(SMF(o + 17));
-        f3 n(SMF(o), SMF(o + 1), SMF(o + 2));
-        bool fA = (refA & 3) == 1, fB = (refB & 3) == 1;
-        int oA = L.o_dv + ND + 6 * (refA >> 2), oB = L.o_dv + ND + 6 * (refB >> 2);
-        f3 vlA, vaA, vlB, vaB, aA, aB;
-        float jv = 0.f;
-        if (fA) {
-          vlA = f3(SMF(oA), SMF(oA + 1), SMF(oA + 2)); vaA = f3(SMF(oA + 3), SMF(oA + 4), SMF(oA + 5));
-          aA = cross(f3(SMF(o + 3), SMF(o + 4), SMF(o + 5)), n);
-          jv += dot(n, vlA) + dot(aA, vaA);
-        } else if ((refA & 3) == 2) jv += pgs_side_jv<LANES>(S, e, sm, L, refA, f2i_bits(SMF(o + 18)), -1, n, f3());
-        if (fB) {
-          vlB = f3(SMF(oB), SMF(oB + 1), SMF(oB + 2)); vaB = f3(SMF(oB + 3), SMF(oB + 4), SMF(oB + 5));
-          aB = cross(f3(SMF(o + 6), SMF(o + 7), SMF(o + 8)), n);
-          jv -= dot(n, vlB) + dot(aB, vaB);
-        } else if ((refB & 3) == 2) jv += pgs_side_jv<LANES>(S, e, sm, L, refB, f2i_bits(SMF(o + 19)), -1, -n, f3());
-        float lam = SMF(L.o_lam + 3 * s);
-        float dl = SMF(o + 9) - jv * dinv;
-        float sum = lam + dl;
-        if (sum < 0.f) { dl = -lam; sum = 0.f; }
-        SMF(L.o_lam + 3 * s) = sum;
-        if (fA) {
-          int fi = L.o_fi + 6 * (refA >> 2);
-          s3 Ii; Ii.xx = SMF(fi); Ii.yy = SMF(fi + 1); Ii.zz = SMF(fi + 2); Ii.xy = SMF(fi + 3); Ii.xz = SMF(fi + 4); Ii.yz = SMF(fi + 5);
-          float k = SMF(L.o_fm + (refA >> 2)) * dl;
-          f3 ia = mul(Ii, aA);
-          SMF(oA) = vlA.x + n.x * k; SMF(oA + 1) = vlA.y + n.y * k; SMF(oA + 2) = vlA.z + n.z * k;
-          SMF(oA + 3) = vaA.x + ia.x * dl; SMF(oA + 4) = vaA.y + ia.y * dl; SMF(oA + 5) = vaA.z + ia.z * dl;
-        } else if ((refA & 3) == 2) pgs_side_apply<LANES>(S, e, sm, L, refA, f2i_bits(SMF(o + 18)), -1, n, f3(), dl);
-        if (fB) {
-          int fi = L.o_fi + 6 * (refB >> 2);
-          s3 Ii; Ii.xx = SMF(fi); Ii.yy = SMF(fi + 1); Ii.zz = SMF(fi + 2); Ii.xy = SMF(fi + 3); Ii.xz = SMF(fi + 4); Ii.yz = SMF(fi + 5);
-          float k = SMF(L.o_fm + (refB >> 2)) * dl;
-          f3 ia = mul(Ii, aB);
-          SMF(oB) = vlB.x - n.x * k; SMF(oB + 1) = vlB.y - n.y * k; SMF(oB + 2) = vlB.z - n.z * k;
-          SMF(oB + 3) = vaB.x - ia.x * dl; SMF(oB + 4) = vaB.y - ia.y * dl; SMF(oB + 5) = vaB.z - ia.z * dl;
-        } else if ((refB & 3) == 2) pgs_side_apply<LANES>(S, e, sm, L, refB, f2i_bits(SMF(o + 19)), -1, -n, f3(), dl);
-        resid = fmaxf(resid, dl * dl);
-      }
-      // friction (two directions per contact, cone or pyramid): both directions share one load / store
-      // round of the two bodies' velocities
-      for (int s = 0; s < cnt; s++) {
-        int o = L.o_cr + s * PGS_CREC;
-        if (SMF(o + 10) == 0.f) continue;
-        float l1 = SMF(L.o_lam + 3 * s + 1), l2 = SMF(L.o_lam + 3 * s + 2);
-        float lim = SMF(o + 15) * SMF(L.o_lam + 3 * s);
-        if (lim <= 0.f && l1 == 0.f && l2 == 0.f) continue;
-        int refA = f2i_bits(SMF(o + 16)), refB = f2i_bits(SMF(o + 17)), asA = f2i_bits(SMF(o + 18)), asB = f2i_bits(SMF(o + 19));
-        f3 n(SMF(o), SMF(o + 1), SMF(o + 2));
-        f3 t1, t2; plane_space(n, t1, t2);
-        bool fA = (refA & 3) == 1, fB = (refB & 3) == 1;
-        int oA = L.o_dv + ND + 6 * (refA >> 2), oB = L.o_dv + ND + 6 * (refB >> 2);
-        f3 vlA, vaA, vlB, vaB, a1A, a2A, a1B, a2B;
-        float jv1 = 0.f, jv2 = 0.f;
-        if (fA) {
-          vlA = f3(SMF(oA), SMF(oA + 1), SMF(oA + 2)); vaA = f3(SMF(oA + 3), SMF(oA + 4), SMF(oA + 5));
-          f3 rA(SMF(o + 3), SMF(o + 4), SMF(o + 5));
-          a1A = cross(rA, t1); a2A = cross(rA, t2);
-          jv1 += dot(t1, vlA) + dot(a1A, vaA); jv2 += dot(t2, vlA) + dot(a2A, vaA);
-        } else if ((refA & 3) == 2) {
-          jv1 += pgs_side_jv<LANES>(S, e, sm, L, refA, asA + 1, -1, t1, f3()); jv2 += pgs_side_jv<LANES>(S, e, sm, L, refA, asA + 2, -1, t2, f3());
-        }
-        if (fB) {
-          vlB = f3(SMF(oB), SMF(oB + 1), SMF(oB + 2)); vaB = f3(SMF(oB + 3), SMF(oB + 4), SMF(oB + 5));
-          f3 rB(SMF(o + 6), SMF(o + 7), SMF(o + 8));
-          a1B = cross(rB, t1); a2B = cross(rB, t2);
-          jv1 -= dot(t1, vlB) + dot(a1B, vaB); jv2 -= dot(t2, vlB) + dot(a2B, vaB);
-        } else if ((refB & 3) == 2) {
-          jv1 += pgs_side_jv<LANES>(S, e, sm, L, refB, asB + 1, -1, -t1, f3()); jv2 += pgs_side_jv<LANES>(S, e, sm, L, refB, asB + 2, -1, -t2, f3());
-        }
-        // NOTE: t1 and t2 are solved as one block against the same velocities (block Gauss-Seidel over the
-        // pair), exactly as the oracle does
-        float s1 = l1 + SMF(o + 11) - jv1 * SMF(o + 12);
-        float s2 = l2 + SMF(o + 13) - jv2 * SMF(o + 14);
-        if (S.cone) {
-          float m2 = s1 * s1 + s2 * s2;
-          if (m2 > lim * lim) { float k = lim / sqrtf(m2); s1 *= k; s2 *= k; }
-        } else { s1 = clampf(s1, -lim, lim); s2 = clampf(s2, -lim, lim); }
-        float d1 = s1 - l1, d2 = s2 - l2;
-        SMF(L.o_lam + 3 * s + 1) = s1; SMF(L.o_lam + 3 * s + 2) = s2;
-        if (fA) {
-          int fi = L.o_fi + 6 * (refA >> 2);
-          s3 Ii; Ii.xx = SMF(fi); Ii.yy = SMF(fi + 1); Ii.zz = SMF(fi + 2); Ii.xy = SMF(fi + 3); Ii.xz = SMF(fi + 4); Ii.yz = SMF(fi + 5);
-          float im = SMF(L.o_fm + (refA >> 2));
-          f3 ia = mul(Ii, a1A * d1 + a2A * d2);
-          f3 dl_ = (t1 * d1 + t2 * d2) * im;
-          SMF(oA) = vlA.x + dl_.x; SMF(oA + 1) = vlA.y + dl_.y; SMF(oA + 2) = vlA.z + dl_.z;
-          SMF(oA + 3) = vaA.x + ia.x; SMF(oA + 4) = vaA.y + ia.y; SMF(oA + 5) = vaA.z + ia.z;
-        } else if ((refA & 3) == 2) {
-          pgs_side_apply<LANES>(S, e, sm, L, refA, asA + 1, -1, t1, f3(), d1); pgs_side_apply<LANES>(S, e, sm, L, refA, asA + 2, -1, t2, f3(), d2);
-        }
-        if (fB) {
-          int fi = L.o_fi + 6 * (refB >> 2);
-          s3 Ii; Ii.xx = SMF(fi); Ii.yy = SMF(fi + 1); Ii.zz = SMF(fi + 2); Ii.xy = SMF(fi + 3); Ii.xz = SMF(fi + 4); Ii.yz = SMF(fi + 5);
-          float im = SMF(L.o_fm + (refB >> 2));
-          f3 ia = mul(Ii, a1B * d1 + a2B * d2);
-          f3 dl_ = (t1 * d1 + t2 * d2) * im;
-          SMF(oB) = vlB.x - dl_.x; SMF(oB + 1) = vlB.y - dl_.y; SMF(oB + 2) = vlB.z - dl_.z;
-          SMF(oB + 3) = vaB.x - ia.x; SMF(oB + 4) = vaB.y - ia.y; SMF(oB + 5) = vaB.z - ia.z;
-        } else if ((refB & 3) == 2) {
-          pgs_side_apply<LANES>(S, e, sm, L, refB, asB + 1, -1, -t1, f3(), d1); pgs_side_apply<LANES>(S, e, sm, L, refB, asB + 2, -1, -t2, f3(), d2);
-        }
-        resid = fmaxf(resid, fmaxf(d1 * d1, d2 * d2));
-      }
-      if (S.resid_thr > 0.f && resid <= S.resid_thr) done = true;
-    }
-#if defined(__CUDA_ARCH__)
-    if (__all_sync(wmask, done)) break;     // the warp leaves the loop when every env has converged
-#else
-    if (done) break;
-#endif
-  }
-  // ---- write back
-  S.iters_used[e] = used;
-#if defined(__CUDA_ARCH__)
-  S.pgs_cycles[e] = (int)(clock64() - t_begin);
-#endif
-  for (int i = 0; i < nvel; i++) S.dv[(size_t)i * N + e] = SMF(L.o_dv + i);
-  for (int r = 0; r < 3 * ND; r++) S.dr_lam[(size_t)r * N + e] = SMF(L.o_dr + 5 * r);
-  for (int r = 0; r < S.ngr; r++) S.gr_data[((size_t)r * 16 + GR_LAM) * N + e] = SMF(L.o_gr + r * GRW + GR_LAM);
-  for (int s = 0; s < cnt; s++) {
-    cf_st(S.s_data, s, CF_LAM_N, N, e, SMF(L.o_lam + 3 * s));
-    cf_st(S.s_data, s, CF_LAM_T1, N, e, SMF(L.o_lam + 3 * s + 1));
-    cf_st(S.s_data, s, CF_LAM_T2, N, e, SMF(L.o_lam + 3 * s + 2));
-  }
-}
-#undef SMF
 
 // ------------------------------------------------------------------ K8: apply deltas, integrate
 AG_HDN inline void integrate_body(int e, const SimDev& S, const KP&) {

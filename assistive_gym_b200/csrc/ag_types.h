@@ -11,7 +11,6 @@
 #define AG_MAXND 16          // max articulated DoFs per env (all articulated bodies together)
 #define AG_MAX_HULL 64       // max core vertices per collider
 #define AG_CF 20             // floats per contact record
-#define AG_MAXAC 16          // max contacts per env with an articulated side
 
 // contact record fields (float index within the [AG_CF] record)
 enum {
@@ -40,7 +39,8 @@ struct SimDev {
   const int *movcol, *movlink, *allcol, *alllink;
   const int* con_link; const float *con_pivot, *con_quat, *con_maxforce;
   const int* free_body; const float* free_invm;
-  const int *art_body, *art_dl0, *art_nd;
+  const int *art_body, *art_dl0, *art_nd, *art_voff;   // art_voff: start of the articulation's block in the solver's velocity vector
+  int NDp;                                             // dof part of that vector (every articulation padded to 4)
   const int *dl_link, *dl_parent, *dl_type, *dl_art, *dl_part0, *dl_nparts;
   const float *dl_mass, *dl_mc, *dl_J, *dl_damping;
   const float *pt_mass, *pt_com, *pt_I;
@@ -61,25 +61,21 @@ struct SimDev {
   int* c_count;                                        // [N]
   unsigned *c_key, *s_key;                             // [maxc][N] unsorted / sorted
   float *c_data, *s_data;                              // [maxc][AG_CF][N]
-  int *s_ref;                                          // [maxc][4][N]: refA, refB, asA, asB
+  int *s_ref;                                          // [maxc][4][N]: refA, refB, stream slot of the normal row, of the friction pair
   int* overflow;                                       // [N]
   // ---- solver scratch
   float *fcom, *fIinv;                                 // [nf][3|6][N]
   float *jax, *jor;                                    // [ND][3][N] world joint axis / origin
   float* Minv;                                         // [ND][ND][N]
   float* dv;                                           // [ND + 6 nf][N]
-  float *dr_rhs, *dr_dinv, *dr_lam;                    // [3 ND][N] dof rows: lower limit, upper limit, motor
-  float *as_J, *as_MiJ;                                // [nas][AG_MAXND][N]
-  int* as_count;                                       // [N]
-  float* gr_data;                                      // [ngr][16][N] generic rows (fixed constraints)
-  int* gr_ref;                                         // [ngr][4][N]
+  float* dr_lam;                                       // [3 ND][N] impulses of the dof rows: lower limit, upper limit, motor
+  float* gr_lam;                                       // [ngr][N] impulses of the fixed-constraint rows
+  int rs_nbuf;                                         // ring depth of K7 (1 KB chunks per env in shared memory)
+  float* rs_data; int rs_cap; int* rs_nslots;          // packed row stream: [N][rs_cap] slots of 32 floats (ag_solver.cuh), used slots [N]
   int* iters_used;                                     // [N]
   int* pgs_order; int* pgs_hist;                       // heaviest-first env order for K7 + its 64-bucket histogram
   int* pgs_cycles;                                     // [N] SM cycles spent in k_pgs by each env's lane (diagnostic)
 };
-
-// generic row fields
-enum { GR_LX = 0, GR_LY, GR_LZ, GR_AAX, GR_AAY, GR_AAZ, GR_ABX, GR_ABY, GR_ABZ, GR_RHS, GR_DINV, GR_LO, GR_HI, GR_LAM, GR_PAD0, GR_PAD1 };
 
 // kernel-specific small parameter block
 struct KP {

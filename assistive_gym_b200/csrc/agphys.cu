@@ -10,6 +10,7 @@
 #include <algorithm>
 #include "../../include/agphys.h"
 #include "ag_device.cuh"
+#include "ag_solver.cuh"
 #include "ag_feeding.cuh"
 
 #ifndef AG_CPU_EMU
@@ -44,19 +45,22 @@ AG_KERNEL(k_sort, sort_body)
 AG_KERNEL(k_dyn, dyn_body)
 AG_KERNEL(k_rows, rows_body)
 AG_KERNEL(k_crows, crows_body)
-// k_pgs: a few envs per CTA, lane-strided dynamic shared memory (see pgs_body); LANES is a template
-// parameter so that every shared-memory offset folds into the LDS/STS immediate
+// k_pgs: LANES envs per CTA (one env per thread); per-lane shared memory = velocity deltas + impulses +
+// a two-deep ring of 1 KB row-stream chunks filled by TMA bulk copies (see ag_solver.cuh)
 #ifndef AG_CPU_EMU
 template <int LANES>
 __global__ void __launch_bounds__(LANES) k_pgs(SimDev S, KP p) {
-  extern __shared__ float pgs_smem[];
+  extern __shared__ __align__(128) float pgs_smem[];
+  const int stride = p.i0;                           // rs_lane_floats(S)
   int tid = blockIdx.x * LANES + threadIdx.x;
-  if (tid < p.n) pgs_body<LANES>(tid, S, p, pgs_smem + threadIdx.x);
+  const unsigned base = (unsigned)__cvta_generic_to_shared(pgs_smem);
+  if (tid < p.n) pgs_body(tid, S, p, pgs_smem + threadIdx.x * stride, base + threadIdx.x * stride * 4, base + LANES * stride * 4 + 8 * S.rs_nbuf * threadIdx.x);
 }
 #else
 static void k_pgs(SimDev S, KP p) {
-  std::vector<float> buf((size_t)pgs_layout(S).total);
-  for (int tid = 0; tid < p.n; tid++) pgs_body<1>(tid, S, p, buf.data());
+  std::vector<float> buf((size_t)rs_lane_floats(S) + 8);
+  float* base = (float*)(((uintptr_t)buf.data() + 15) & ~(uintptr_t)15);
+  for (int tid = 0; tid < p.n; tid++) pgs_body(tid, S, p, base, (rs_addr)base, 0);
 }
 #endif
 AG_KERNEL(k_order_hist, order_hist_body)
@@ -333,7 +337,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
     for (int c = link_col0[k]; c < link_col0[k] + link_ncol[k]; c++) { allcol.push_back(c); if (mov) movcol.push_back(c); }
   }
   S.nmovcol = (int)movcol.size(); S.nmovlink = (int)movlink.size(); S.nalllink = (int)alllink.size();
-  S.ngr = 6 * S.ncon; S.nas = 6 * S.ncon * 2 + 3 * AG_MAXAC;
+  S.ngr = 6 * S.ncon; S.nas = 0;
 
   // ---- upload template
   auto f32 = [](const double* p, size_t n) { std::vector<float> v(n); for (size_t i = 0; i < n; i++) v[i] = (float)p[i]; return v; };
@@ -363,6 +367,11 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   S.free_body = upload(s, free_body);
   { std::vector<float> im(free_body.size()); for (size_t f = 0; f < free_body.size(); f++) im[f] = (float)(1.0 / d->link_mass[d->body_link0[free_body[f]]]); S.free_invm = upload(s, im); }
   S.art_body = upload(s, art_body); S.art_dl0 = upload(s, art_dl0); S.art_nd = upload(s, art_nd);
+  {
+    std::vector<int> art_voff; int acc = 0;
+    for (int nd_a : art_nd) { art_voff.push_back(acc); acc += (nd_a + 3) & ~3; }
+    S.art_voff = upload(s, art_voff); S.NDp = acc;
+  }
   S.dl_link = upload(s, dl_link); S.dl_parent = upload(s, dl_parent); S.dl_type = upload(s, dl_type); S.dl_art = upload(s, dl_art);
   S.dl_part0 = upload(s, dl_part0); S.dl_nparts = upload(s, dl_nparts);
   S.dl_mass = upload(s, dl_mass); S.dl_mc = upload(s, dl_mc); S.dl_J = upload(s, dl_J); S.dl_damping = upload(s, dl_damping);
@@ -388,12 +397,14 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   S.jax = dalloc<float>(s, (size_t)S.ND * 3 * N); S.jor = dalloc<float>(s, (size_t)S.ND * 3 * N);
   S.Minv = dalloc<float>(s, (size_t)S.ND * S.ND * N);
   S.dv = dalloc<float>(s, (size_t)(S.ND + 6 * S.nf) * N);
-  S.dr_rhs = dalloc<float>(s, (size_t)3 * S.ND * N); S.dr_dinv = dalloc<float>(s, (size_t)3 * S.ND * N); S.dr_lam = dalloc<float>(s, (size_t)3 * S.ND * N);
-  S.as_J = dalloc<float>(s, (size_t)S.nas * AG_MAXND * N); S.as_MiJ = dalloc<float>(s, (size_t)S.nas * AG_MAXND * N);
-  S.as_count = dalloc<int>(s, N);
-  S.gr_data = dalloc<float>(s, (size_t)S.ngr * 16 * N); S.gr_ref = dalloc<int>(s, (size_t)S.ngr * 4 * N);
+  S.dr_lam = dalloc<float>(s, (size_t)3 * S.ND * N);
+  // row stream: worst case 4 slots per contact (free-free: 1 normal + 2 friction; articulated sides: 2 + 3) plus chunk padding
+  { const char* nbp = getenv("AG_PGS_NBUF"); S.rs_nbuf = nbp ? atoi(nbp) : 2; if (S.rs_nbuf != 2 && S.rs_nbuf != 4 && S.rs_nbuf != 8) S.rs_nbuf = 2; }
+  S.rs_cap = ((3 * S.ND + 3 * S.ngr + 4 * S.maxc + 8) + RS_CHUNK - 1) / RS_CHUNK * RS_CHUNK;
+  S.rs_data = dalloc<float>(s, (size_t)S.rs_cap * RS_SLOT * N); S.rs_nslots = dalloc<int>(s, N);
+  S.gr_lam = dalloc<float>(s, (size_t)S.ngr * N);
   s->d_mask = dalloc<int>(s, N); s->d_links = dalloc<int>(s, 1024); s->d_icount = dalloc<int>(s, N);
-  if (!S.gr_ref || !S.as_MiJ || !S.s_data) { g_err = "device allocation failed"; ag_destroy(s); return nullptr; }
+  if (!S.gr_lam || !S.rs_data || !S.rs_nslots || !S.s_data) { g_err = "device allocation failed"; ag_destroy(s); return nullptr; }
 #ifndef AG_CPU_EMU
   {
     // Lanes (envs) per CTA of the latency-bound per-env kernels.  4096 envs are only 128 full warps
@@ -402,7 +413,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
     const char* lp = getenv("AG_PGS_LANES");
     s->pgs_lanes = lp ? atoi(lp) : 4;
     if (s->pgs_lanes != 1 && s->pgs_lanes != 2 && s->pgs_lanes != 4 && s->pgs_lanes != 8 && s->pgs_lanes != 32) s->pgs_lanes = 4;
-    size_t smem = (size_t)pgs_layout(S).total * s->pgs_lanes * sizeof(float);
+    size_t smem = (size_t)rs_lane_floats(S) * s->pgs_lanes * sizeof(float) + 8 * S.rs_nbuf * s->pgs_lanes;
     if (smem > 227 * 1024) { g_err = "PGS shared-memory footprint exceeds 227 KB per CTA: lower max_contacts or AG_PGS_LANES"; ag_destroy(s); return nullptr; }
     cudaError_t ce = cudaSuccess;
     switch (s->pgs_lanes) {
@@ -607,9 +618,9 @@ static void substep(AgSim* s) {
   }
 #ifndef AG_CPU_EMU
   {
-    KP kp = z; kp.n = N;
+    KP kp = z; kp.n = N; kp.i0 = rs_lane_floats(S);
     int L = s->pgs_lanes;
-    size_t smem = (size_t)pgs_layout(S).total * L * sizeof(float);
+    size_t smem = (size_t)kp.i0 * L * sizeof(float) + 8 * S.rs_nbuf * L;
     int ps = s->profiling ? prof_slot(s, "k_pgs") : -1;
     if (ps >= 0) prof_mark(s, ps, true);
     dim3 grid((N + L - 1) / L);

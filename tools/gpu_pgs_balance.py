@@ -6,7 +6,7 @@ import numpy as np
 from assistive_gym_b200 import capi
 from assistive_gym_b200.feeding_batch import FeedingBatch
 from assistive_gym_b200.sim import BatchSim
-n = 4096
+n = int(os.environ.get("AG_N", "4096"))
 fb = FeedingBatch(); sim = BatchSim(fb.scene, capi.default_config(), n)
 rng = np.random.default_rng(0)
 s = fb.reset(sim, rng, settle_steps=25)
