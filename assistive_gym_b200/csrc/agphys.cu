@@ -411,8 +411,8 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
     // for 592 warp schedulers, so partially filled warps (8 envs each) put a warp on every scheduler,
     // shorten the per-warp iteration count (max over fewer envs) and reduce divergence.
     const char* lp = getenv("AG_PGS_LANES");
-    s->pgs_lanes = lp ? atoi(lp) : 4;
-    if (s->pgs_lanes != 1 && s->pgs_lanes != 2 && s->pgs_lanes != 4 && s->pgs_lanes != 8 && s->pgs_lanes != 32) s->pgs_lanes = 4;
+    s->pgs_lanes = lp ? atoi(lp) : 1;
+    if (s->pgs_lanes != 1 && s->pgs_lanes != 2 && s->pgs_lanes != 4 && s->pgs_lanes != 8 && s->pgs_lanes != 32) s->pgs_lanes = 1;
     size_t smem = (size_t)rs_lane_floats(S) * s->pgs_lanes * sizeof(float) + 8 * S.rs_nbuf * s->pgs_lanes;
     if (smem > 227 * 1024) { g_err = "PGS shared-memory footprint exceeds 227 KB per CTA: lower max_contacts or AG_PGS_LANES"; ag_destroy(s); return nullptr; }
     cudaError_t ce = cudaSuccess;
