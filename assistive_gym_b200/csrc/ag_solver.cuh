@@ -157,91 +157,75 @@ AG_HD void rs_header(float* d, int code, int ns, int offA, int nA, int offB, int
   d[0] = i2f_bits(code | (ns << 4)); d[1] = i2f_bits(offA | (nA << 16)); d[2] = i2f_bits(offB | (nB << 16)); d[3] = i2f_bits(lam);
 }
 
-// K6a: one lane per env: joint-limit rows, motor rows, fixed-constraint rows; then the slot layout of
-// this substep's contact rows (normal rows in contact order, then friction pairs in contact order)
-AG_HDN inline void rows_body(int e, const SimDev& S, const KP&) {
+// Is dof row r = kind * ND + d (kind 0 lower limit, 1 upper limit, 2 motor) live this substep?  If so: its constants.
+struct DofRow { float rhs, dinv, lo, hi, sgn; };
+AG_HD bool dof_row(const SimDev& S, int e, int kind, int d, DofRow& R) {
   const int N = S.N;
   const float dt = S.dt;
+  int k = AG_LDG(S.dl_link + d);
+  float Mdd = S.Minv[((size_t)d * S.ND + d) * N + e];
+  if (!(Mdd > 0.f)) return false;
+  R.dinv = 1.0f / Mdd; R.lo = 0.f; R.hi = 1e30f; R.sgn = 1.f;
+  float q = ld1(S.jq, k, N, e), qd = ld1(S.jqd, k, N, e);
+  if (kind < 2) {             // limits: a row only while violated
+    if (!AG_LDG(S.link_haslimit + k)) return false;
+    if (kind == 0) { float pen = q - AG_LDG(S.link_lower + k); if (pen > 0.f) return false; R.rhs = (-pen * S.erp / dt - qd) * R.dinv; }
+    else { float pen = AG_LDG(S.link_upper + k) - q; if (pen > 0.f) return false; R.rhs = (-pen * S.erp / dt + qd) * R.dinv; R.sgn = -1.f; }
+  } else {
+    int mode = S.motor_mode[k];
+    float maxi = S.motor_maxf[k] * dt;
+    if (mode == 0 || !(maxi > 0.f)) return false;
+    float vt = (mode == 1) ? (S.motor_kp[k] * (ld1(S.motor_target, k, N, e) - q) / dt + qd - S.motor_kd[k] * qd)
+                           : ld1(S.motor_target, k, N, e);
+    R.rhs = (vt - qd) * R.dinv; R.lo = -maxi; R.hi = maxi;
+  }
+  return true;
+}
+// sides of fixed constraint c in record order (articulation / lone dynamic side first)
+AG_HD bool con_sides(const SimDev& S, int e, int c, int& refA, int& refB, bool& swapped) {
+  const int N = S.N;
+  int ka = AG_LDG(S.con_link + 2 * c), kb = AG_LDG(S.con_link + 2 * c + 1);
+  int ba = AG_LDG(S.link_body + ka), bb = AG_LDG(S.link_body + kb);
+  if (S.body_mode[(size_t)ba * N + e] == 0 || S.body_mode[(size_t)bb * N + e] == 0) return false;
+  refA = link_ref(S, e, ka); refB = link_ref(S, e, kb);
+  swapped = rs_swap_sides(refA, refB);
+  if (swapped) { int t = refA; refA = refB; refB = t; }
+  return ((refA | refB) & 3) != 0;
+}
+
+// K6a: one lane per env: the slot layout of this substep's row stream in solver order -- joint-limit rows,
+// motor rows, fixed-constraint rows, contact normal rows (contact order), friction pairs (contact order).
+// Cheap and sequential; the records themselves are written by K6b with one thread per row.
+// row_off [3 ND + ngr][N]: slot of each dof / fixed-constraint row (-1: not live); s_ref[..][2,3]: contact rows.
+AG_HDN inline void rows_body(int e, const SimDev& S, const KP&) {
+  const int N = S.N;
   float* rs = S.rs_data + (size_t)e * S.rs_cap * RS_SLOT;
   const int cap = S.rs_cap;
   int pos = 0;
   bool over = false;
-  // dof rows in solver order: all lower limits, all upper limits, all motors (J = +-e_d)
   for (int kind = 0; kind < 3; kind++) {
     for (int d = 0; d < S.ND; d++) {
-      int k = AG_LDG(S.dl_link + d);
-      int r = kind * S.ND + d;
-      float Mdd = S.Minv[((size_t)d * S.ND + d) * N + e];
-      if (!(Mdd > 0.f)) continue;
-      float dinv = 1.0f / Mdd;
-      float q = ld1(S.jq, k, N, e), qd = ld1(S.jqd, k, N, e);
-      float rhs, lo = 0.f, hi = 1e30f, sgn = 1.f;
-      if (kind < 2) {           // limits: a row only while violated
-        if (!AG_LDG(S.link_haslimit + k)) continue;
-        if (kind == 0) { float pen = q - AG_LDG(S.link_lower + k); if (pen > 0.f) continue; rhs = (-pen * S.erp / dt - qd) * dinv; }
-        else { float pen = AG_LDG(S.link_upper + k) - q; if (pen > 0.f) continue; rhs = (-pen * S.erp / dt + qd) * dinv; sgn = -1.f; }
-      } else {
-        int mode = S.motor_mode[k];
-        float maxi = S.motor_maxf[k] * dt;
-        if (mode == 0 || !(maxi > 0.f)) continue;
-        float vt = (mode == 1) ? (S.motor_kp[k] * (ld1(S.motor_target, k, N, e) - q) / dt + qd - S.motor_kd[k] * qd)
-                               : ld1(S.motor_target, k, N, e);
-        rhs = (vt - qd) * dinv; lo = -maxi; hi = maxi;
+      DofRow R;
+      int o = -1;
+      if (dof_row(S, e, kind, d, R)) {
+        int nd4 = rs_pad4(AG_LDG(S.art_nd + AG_LDG(S.dl_art + d)));
+        o = rs_alloc(pos, rs_slots(8 + 2 * nd4), rs, cap);
+        if (o < 0) over = true;
       }
-      int a = AG_LDG(S.dl_art + d), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a), vo = AG_LDG(S.art_voff + a);
-      int nd4 = rs_pad4(nd);
-      int ns = rs_slots(8 + 2 * nd4);
-      int o = rs_alloc(pos, ns, rs, cap);
-      if (o < 0) { over = true; continue; }
-      float* dst = rs + (size_t)o * RS_SLOT;
-      rs_header(dst, RK_ROW_GEN, ns, vo, nd4, 0, 0, r);
-      dst[4] = rhs; dst[5] = dinv; dst[6] = lo; dst[7] = hi;
-      for (int i = 0; i < nd4; i++) {
-        dst[8 + i] = (i == d - d0) ? sgn : 0.f;
-        dst[8 + nd4 + i] = i < nd ? sgn * S.Minv[((size_t)(d0 + i) * S.ND + d) * N + e] : 0.f;
-      }
+      S.row_off[(size_t)(kind * S.ND + d) * N + e] = o;
     }
   }
-  // fixed constraints: 3 translation + 3 rotation rows each
   for (int c = 0; c < S.ncon; c++) {
-    int ka = AG_LDG(S.con_link + 2 * c), kb = AG_LDG(S.con_link + 2 * c + 1);
-    int refA = link_ref(S, e, ka), refB = link_ref(S, e, kb);
-    int ba = AG_LDG(S.link_body + ka), bb = AG_LDG(S.link_body + kb);
-    bool on = S.body_mode[(size_t)ba * N + e] != 0 && S.body_mode[(size_t)bb * N + e] != 0;
-    if (!on) continue;
-    q4 qa = ld4(S.lquat, ka, N, e), qb = ld4(S.lquat, kb, N, e);
-    f3 pa = ld3(S.lpos, ka, N, e) + qrot(qa, tv3(S.con_pivot, 2 * c));
-    f3 pb = ld3(S.lpos, kb, N, e) + qrot(qb, tv3(S.con_pivot, 2 * c + 1));
-    q4 fa = qmul(qa, tv4(S.con_quat, 2 * c)), fb = qmul(qb, tv4(S.con_quat, 2 * c + 1));
-    q4 qe = qmul(fa, qconj(fb));
-    if (qe.w < 0.f) qe = q4(-qe.x, -qe.y, -qe.z, -qe.w);
-    f3 perr = pa - pb, aerr(2.f * qe.x, 2.f * qe.y, 2.f * qe.z);
-    float maxi = AG_LDG(S.con_maxforce + c) * dt;
-    float sg = 1.f;
-    if (rs_swap_sides(refA, refB)) { int t = refA; refA = refB; refB = t; f3 tp = pa; pa = pb; pb = tp; sg = -1.f; }
-    int offA, nA, offB, nB;
-    side_dims(S, refA, offA, nA); side_dims(S, refB, offB, nB);
-    if (nA + nB == 0) continue;
-    int ns, code = rs_row_code(refA, refB, nA, nB, ns);
-    int pA = code == RK_ROW_GEN ? rs_pad4(nA) : nA, pB = code == RK_ROW_GEN ? rs_pad4(nB) : nB;
-    int oM = code == RK_ROW_F ? 16 : (code == RK_ROW_FF ? 20 : 8 + pA + pB);
+    int refA, refB; bool sw;
+    bool on = con_sides(S, e, c, refA, refB, sw);
+    int offA, nA, offB, nB, ns = 0;
+    if (on) { side_dims(S, refA, offA, nA); side_dims(S, refB, offB, nB); rs_row_code(refA, refB, nA, nB, ns); }
     for (int i = 0; i < 6; i++) {
-      f3 axv(i % 3 == 0 ? 1.f : 0.f, i % 3 == 1 ? 1.f : 0.f, i % 3 == 2 ? 1.f : 0.f);
-      f3 lin = i < 3 ? axv : f3(), ang = i < 3 ? f3() : axv;
-      int o = rs_alloc(pos, ns, rs, cap);
-      if (o < 0) { over = true; continue; }
-      float* dst = rs + (size_t)o * RS_SLOT;
-      float rel = 0.f;
-      float diag = emit_side(S, e, refA, pa, lin * sg, ang * sg, dst + 8, dst + oM, pA, rel) +
-                   emit_side(S, e, refB, pb, lin * (-sg), ang * (-sg), dst + 8 + pA, dst + oM + pA, pB, rel);
-      if (!(diag > 1e-20f)) { dst[0] = i2f_bits(RK_PAD | (ns << 4)); continue; }
-      float dinv = 1.0f / diag;
-      float err = i < 3 ? comp(perr, i) : comp(aerr, i - 3);     // measured before the side swap: J is unchanged by it
-      rs_header(dst, code, ns, offA, pA, offB, pB, 3 * S.ND + 6 * c + i);
-      dst[4] = (-err * S.erp / dt - rel) * dinv; dst[5] = dinv; dst[6] = -maxi; dst[7] = maxi;
+      int o = -1;
+      if (on) { o = rs_alloc(pos, ns, rs, cap); if (o < 0) over = true; }
+      S.row_off[(size_t)(3 * S.ND + 6 * c + i) * N + e] = o;
     }
   }
-  // contact rows: sides and slot offsets (the records themselves are written by K6b, one thread per contact)
   int cnt = S.c_count[e]; if (cnt > S.maxc) cnt = S.maxc;
   for (int pass = 0; pass < 2; pass++) {
     for (int s = 0; s < cnt; s++) {
@@ -270,10 +254,68 @@ AG_HDN inline void rows_body(int e, const SimDev& S, const KP&) {
   if (over) S.overflow[e] = 1;
 }
 
-// K6b: contact rows, thread = (sorted slot, env)
+// K6b, rows part: thread = (dof / fixed-constraint row r, env): write the record K6a reserved
+AG_HDN inline void drow_body(int r, int e, const SimDev& S) {
+  const int N = S.N;
+  const float dt = S.dt;
+  int o = S.row_off[(size_t)r * N + e];
+  if (o < 0) return;
+  float* dst = S.rs_data + ((size_t)e * S.rs_cap + o) * RS_SLOT;
+  if (r < 3 * S.ND) {
+    int kind = r / S.ND, d = r % S.ND;
+    DofRow R;
+    if (!dof_row(S, e, kind, d, R)) return;           // cannot happen: K6a saw the same state
+    int a = AG_LDG(S.dl_art + d), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a), vo = AG_LDG(S.art_voff + a);
+    int nd4 = rs_pad4(nd);
+    rs_header(dst, RK_ROW_GEN, rs_slots(8 + 2 * nd4), vo, nd4, 0, 0, r);
+    dst[4] = R.rhs; dst[5] = R.dinv; dst[6] = R.lo; dst[7] = R.hi;
+    for (int i = 0; i < nd4; i++) {
+      dst[8 + i] = (i == d - d0) ? R.sgn : 0.f;
+      dst[8 + nd4 + i] = i < nd ? R.sgn * S.Minv[((size_t)(d0 + i) * S.ND + d) * N + e] : 0.f;
+    }
+    return;
+  }
+  // fixed constraint c, row i: 3 translation + 3 rotation rows
+  int c = (r - 3 * S.ND) / 6, i = (r - 3 * S.ND) % 6;
+  int refA, refB; bool sw;
+  if (!con_sides(S, e, c, refA, refB, sw)) return;
+  int ka = AG_LDG(S.con_link + 2 * c), kb = AG_LDG(S.con_link + 2 * c + 1);
+  q4 qa = ld4(S.lquat, ka, N, e), qb = ld4(S.lquat, kb, N, e);
+  f3 pa = ld3(S.lpos, ka, N, e) + qrot(qa, tv3(S.con_pivot, 2 * c));
+  f3 pb = ld3(S.lpos, kb, N, e) + qrot(qb, tv3(S.con_pivot, 2 * c + 1));
+  float err;
+  if (i < 3) err = comp(pa - pb, i);
+  else {
+    q4 fa = qmul(qa, tv4(S.con_quat, 2 * c)), fb = qmul(qb, tv4(S.con_quat, 2 * c + 1));
+    q4 qe = qmul(fa, qconj(fb));
+    if (qe.w < 0.f) qe = q4(-qe.x, -qe.y, -qe.z, -qe.w);
+    err = 2.f * comp(f3(qe.x, qe.y, qe.z), i - 3);
+  }
+  float sg = 1.f;
+  if (sw) { f3 tp = pa; pa = pb; pb = tp; sg = -1.f; }     // err was measured before the swap: J is unchanged by it
+  float maxi = AG_LDG(S.con_maxforce + c) * dt;
+  int offA, nA, offB, nB;
+  side_dims(S, refA, offA, nA); side_dims(S, refB, offB, nB);
+  int ns, code = rs_row_code(refA, refB, nA, nB, ns);
+  int pA = code == RK_ROW_GEN ? rs_pad4(nA) : nA, pB = code == RK_ROW_GEN ? rs_pad4(nB) : nB;
+  int oM = code == RK_ROW_F ? 16 : (code == RK_ROW_FF ? 20 : 8 + pA + pB);
+  f3 axv(i % 3 == 0 ? 1.f : 0.f, i % 3 == 1 ? 1.f : 0.f, i % 3 == 2 ? 1.f : 0.f);
+  f3 lin = i < 3 ? axv : f3(), ang = i < 3 ? f3() : axv;
+  float rel = 0.f;
+  float diag = emit_side(S, e, refA, pa, lin * sg, ang * sg, dst + 8, dst + oM, pA, rel) +
+               emit_side(S, e, refB, pb, lin * (-sg), ang * (-sg), dst + 8 + pA, dst + oM + pA, pB, rel);
+  if (!(diag > 1e-20f)) { dst[0] = i2f_bits(RK_PAD | (ns << 4)); return; }
+  float dinv = 1.0f / diag;
+  rs_header(dst, code, ns, offA, pA, offB, pB, r);
+  dst[4] = (-err * S.erp / dt - rel) * dinv; dst[5] = dinv; dst[6] = -maxi; dst[7] = maxi;
+}
+
+// K6b: thread = (row, env): rows [0, maxc) are the sorted contacts, rows [maxc, maxc + 3 ND + ngr) the dof and
+// fixed-constraint rows
 AG_HDN inline void crows_body(int tid, const SimDev& S, const KP&) {
   const int N = S.N;
   int e = tid % N, slot = tid / N;
+  if (slot >= S.maxc) { drow_body(slot - S.maxc, e, S); return; }
   int cnt = S.c_count[e]; if (cnt > S.maxc) cnt = S.maxc;
   if (slot >= cnt) return;
   for (int d = 0; d < 3; d++) cf_st(S.s_data, slot, CF_LAM_N + d, N, e, 0.f);

@@ -71,6 +71,7 @@ struct SimDev {
   float* dr_lam;                                       // [3 ND][N] impulses of the dof rows: lower limit, upper limit, motor
   float* gr_lam;                                       // [ngr][N] impulses of the fixed-constraint rows
   int rs_nbuf;                                         // ring depth of K7 (1 KB chunks per env in shared memory)
+  int* row_off;                                        // [3 ND + ngr][N] stream slot of each dof / fixed-constraint row (-1: not live)
   float* rs_data; int rs_cap; int* rs_nslots;          // packed row stream: [N][rs_cap] slots of 32 floats (ag_solver.cuh), used slots [N]
   int* iters_used;                                     // [N]
   int* pgs_order; int* pgs_hist;                       // heaviest-first env order for K7 + its 64-bucket histogram

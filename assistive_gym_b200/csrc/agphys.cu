@@ -36,11 +36,20 @@ static int fail(const std::string& m) { g_err = m; return -1; }
   static void name(SimDev S, KP p) { for (int tid = 0; tid < p.n; tid++) body(tid, S, p); }
 #endif
 
+#ifndef AG_CPU_EMU
+#define AG_KERNEL_B(name, body, minblocks)                                      \
+  __global__ void __launch_bounds__(128, minblocks) name(SimDev S, KP p) {      \
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;                            \
+    if (tid < p.n) body(tid, S, p);                                             \
+  }
+#else
+#define AG_KERNEL_B(name, body, minblocks) AG_KERNEL(name, body)
+#endif
 AG_KERNEL(k_fk, fk_body)
 AG_KERNEL(k_aabb, aabb_body)
 AG_KERNEL(k_linkaabb, linkaabb_body)
 AG_KERNEL(k_pairs, pairs_body)
-AG_KERNEL(k_narrow, narrow_body)
+AG_KERNEL_B(k_narrow, narrow_body, 3)
 AG_KERNEL(k_sort, sort_body)
 AG_KERNEL(k_dyn, dyn_body)
 AG_KERNEL(k_rows, rows_body)
@@ -402,7 +411,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   { const char* nbp = getenv("AG_PGS_NBUF"); S.rs_nbuf = nbp ? atoi(nbp) : 2; if (S.rs_nbuf != 2 && S.rs_nbuf != 4 && S.rs_nbuf != 8) S.rs_nbuf = 2; }
   S.rs_cap = ((3 * S.ND + 3 * S.ngr + 4 * S.maxc + 8) + RS_CHUNK - 1) / RS_CHUNK * RS_CHUNK;
   S.rs_data = dalloc<float>(s, (size_t)S.rs_cap * RS_SLOT * N); S.rs_nslots = dalloc<int>(s, N);
-  S.gr_lam = dalloc<float>(s, (size_t)S.ngr * N);
+  S.gr_lam = dalloc<float>(s, (size_t)S.ngr * N); S.row_off = dalloc<int>(s, (size_t)(3 * S.ND + S.ngr) * N);
   s->d_mask = dalloc<int>(s, N); s->d_links = dalloc<int>(s, 1024); s->d_icount = dalloc<int>(s, N);
   if (!S.gr_lam || !S.rs_data || !S.rs_nslots || !S.s_data) { g_err = "device allocation failed"; ag_destroy(s); return nullptr; }
 #ifndef AG_CPU_EMU
@@ -608,7 +617,7 @@ static void substep(AgSim* s) {
   LAUNCH(s, k_sort, (size_t)S.maxc * N, z);
   LAUNCH(s, k_dyn, N, z);
   LAUNCH(s, k_rows, N, z);
-  LAUNCH(s, k_crows, (size_t)S.maxc * N, z);
+  LAUNCH(s, k_crows, (size_t)(S.maxc + 3 * S.ND + S.ngr) * N, z);
   {   // heaviest-first env order for the PGS kernel
     dev_zero(s, S.pgs_hist, sizeof(int) * 64);
     KP o = kp0(); o.p1 = S.pgs_hist;
