@@ -148,7 +148,35 @@ struct NpOut { f3 pa, pb, n; float d; };   // B-local frame: points on the surfa
 // GJK closest points between core A (A-local vertices mapped by R,t into B's frame) and core B.
 // Vertices, transforms and the support search are fp32; the simplex solve is fp64.
 // Returns true if the cores overlap.
-AG_HDN inline bool gjk_cores(const float* verts, int va0, int nA, int vb0, int nB, const m3& R, f3 t,
+// Support search over a collider's core vertices stored 4 at a time as [x0..x3][y0..y3][z0..z3] (`vq`, 16 B
+// aligned, padded with copies of vertex 0): 3 vector loads per 4 vertices, 4 independent dot products in
+// flight, first index wins ties exactly like a scalar scan.
+struct alignas(16) vq4 { float x, y, z, w; };
+AG_HD vq4 ldq4(const float* p) {
+#if defined(__CUDA_ARCH__)
+  float4 v = __ldg((const float4*)p); vq4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+#else
+  return *(const vq4*)p;
+#endif
+}
+AG_HD int support4(const float* vq, int g0, int n, f3 d) {
+  int bi = 0; float best = -3.0e38f;
+  const int ng = (n + 3) >> 2;
+  const float* p = vq + (size_t)g0 * 12;
+  for (int g = 0; g < ng; g++, p += 12) {
+    vq4 X = ldq4(p), Y = ldq4(p + 4), Z = ldq4(p + 8);
+    float d0 = d.x * X.x + d.y * Y.x + d.z * Z.x, d1 = d.x * X.y + d.y * Y.y + d.z * Z.y;
+    float d2 = d.x * X.z + d.y * Y.z + d.z * Z.z, d3v = d.x * X.w + d.y * Y.w + d.z * Z.w;
+    if (d0 > best) { best = d0; bi = 4 * g; }
+    if (d1 > best) { best = d1; bi = 4 * g + 1; }
+    if (d2 > best) { best = d2; bi = 4 * g + 2; }
+    if (d3v > best) { best = d3v; bi = 4 * g + 3; }
+  }
+  return bi < n ? bi : 0;      // a pad entry can only tie with vertex 0, never beat it; guard anyway
+}
+
+// `vq` / ga0, gb0: the packed copies of the two cores (group offsets); verts / va0, vb0: the plain copies
+AG_HDN inline bool gjk_cores(const float* verts, const float* vq, int va0, int ga0, int nA, int vb0, int gb0, int nB, const m3& R, f3 t,
                              f3& pa, f3& pb, f3& nrm, float& dist) {
   d3 W[4]; f3 PA[4], PB[4];
   int IA[4], IB[4];
@@ -162,11 +190,7 @@ AG_HDN inline bool gjk_cores(const float* verts, int va0, int nA, int vb0, int n
     // support of A in direction -v (A-local: R^T(-v)), support of B in +v
     f3 vf = to_f3(v);
     f3 da = mulT(R, -vf);
-    int ia = 0, ib = 0;
-    float best = dot(da, tv3(verts, va0));
-    for (int i = 1; i < nA; i++) { float d = dot(da, tv3(verts, va0 + i)); if (d > best) { best = d; ia = i; } }
-    best = dot(vf, tv3(verts, vb0));
-    for (int i = 1; i < nB; i++) { float d = dot(vf, tv3(verts, vb0 + i)); if (d > best) { best = d; ib = i; } }
+    int ia = support4(vq, ga0, nA, da), ib = support4(vq, gb0, nB, vf);
     f3 sa = mul(R, tv3(verts, va0 + ia)) + t;
     f3 sb = tv3(verts, vb0 + ib);
     d3 w = to_d3(sa) - to_d3(sb);
@@ -384,7 +408,7 @@ AG_HDN inline int narrow_pair(const SimDev& S, int e, int ca, int cb, float max_
   m3 R = mul(transpose(RB), qmat(qA));
   f3 t = mulT(RB, posA - posB);
   f3 pa, pb, nrm; float dist = 0.f;
-  bool ov = gjk_cores(S.verts, va0, nA, vb0, nB, R, t, pa, pb, nrm, dist);
+  bool ov = gjk_cores(S.verts, S.vertq, va0, AG_LDG(S.col_g0 + ca), nA, vb0, AG_LDG(S.col_g0 + cb), nB, R, t, pa, pb, nrm, dist);
   if (ov) pen_faces(S, va0, nA, pa0, npA, vb0, nB, pb0, npB, R, t, pa, pb, nrm, dist);
   float d = dist - ra - rb;
   if (d > max_dist) return 0;

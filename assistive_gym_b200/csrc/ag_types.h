@@ -34,6 +34,7 @@ struct SimDev {
   const float *link_axis, *link_jpos, *link_jquat, *link_com, *link_iquat, *link_inertia, *link_mass, *link_lower, *link_upper;
   const int *col_link, *col_type, *col_v0, *col_nv, *col_p0, *col_np;
   const float *col_radius, *col_thresh, *link_thresh, *col_center, *col_half, *verts, *planes;
+  const float* vertq; const int* col_g0;               // core vertices packed 4 at a time ([x0..3][y0..3][z0..3]) for the GJK support search, first group per collider
   float max_thresh;
   const int* pair_link;
   const int *movcol, *movlink, *allcol, *alllink;

@@ -367,6 +367,18 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   S.col_radius = upload(s, f32(d->col_radius, nc)); S.col_thresh = upload(s, f32(d->col_thresh, nc));
   S.max_thresh = 0.f; for (int c = 0; c < nc; c++) S.max_thresh = std::max(S.max_thresh, (float)d->col_thresh[c]);
   { std::vector<float> lt(nl, 0.f); for (int c = 0; c < nc; c++) lt[d->col_link[c]] = std::max(lt[d->col_link[c]], (float)d->col_thresh[c]); S.link_thresh = upload(s, lt); } S.col_center = upload(s, f32(d->col_center, 3 * nc)); S.col_half = upload(s, f32(d->col_half, 3 * nc));
+  {
+    std::vector<float> vq; std::vector<int> g0(nc);
+    for (int c = 0; c < nc; c++) {
+      g0[c] = (int)(vq.size() / 12);
+      int v0 = d->col_v0[c], nv = d->col_nv[c];
+      for (int g = 0; g < (nv + 3) / 4; g++)
+        for (int comp = 0; comp < 3; comp++)
+          for (int k = 0; k < 4; k++) { int i = 4 * g + k; vq.push_back((float)d->verts[3 * (size_t)(v0 + (i < nv ? i : 0)) + comp]); }
+    }
+    if (vq.empty()) vq.resize(12, 0.f);
+    S.vertq = upload(s, vq); S.col_g0 = upload(s, g0);
+  }
   S.verts = upload(s, f32(d->verts, 3 * (size_t)d->n_verts)); S.planes = upload(s, f32(d->planes, 4 * (size_t)d->n_planes));
   S.pair_link = upload(s, i32(d->pair_link, 2 * (size_t)d->n_pairs));
   S.movcol = upload(s, movcol); S.movlink = upload(s, movlink); S.allcol = upload(s, allcol); S.alllink = upload(s, alllink);
@@ -892,9 +904,16 @@ int ag_feeding_step_host(AgSim* s, const float* action, float* obs, float* rewar
 extern "C" int ag_debug_gjk(const float* A, int nA, const float* B, int nB, float* pa, float* pb, float* nrm, float* dist) {
   std::vector<float> v((size_t)3 * (nA + nB));
   memcpy(v.data(), A, sizeof(float) * 3 * nA); memcpy(v.data() + 3 * nA, B, sizeof(float) * 3 * nB);
+  std::vector<float> vqs((size_t)12 * ((nA + 3) / 4 + (nB + 3) / 4) + 4);
+  float* vq = (float*)(((uintptr_t)vqs.data() + 15) & ~(uintptr_t)15);
+  int gB = (nA + 3) / 4;
+  for (int side = 0; side < 2; side++) {
+    const float* src = side ? B : A; int nv = side ? nB : nA; float* dstq = vq + (side ? 12 * gB : 0);
+    for (int g = 0; g < (nv + 3) / 4; g++) for (int comp = 0; comp < 3; comp++) for (int k = 0; k < 4; k++) { int i = 4 * g + k; dstq[12 * g + 4 * comp + k] = src[3 * (i < nv ? i : 0) + comp]; }
+  }
   m3 R; for (int i = 0; i < 9; i++) R.m[i] = (i % 4 == 0) ? 1.f : 0.f;
   f3 a, b, n; float d = 0.f;
-  bool ov = gjk_cores(v.data(), 0, nA, nA, nB, R, f3(), a, b, n, d);
+  bool ov = gjk_cores(v.data(), vq, 0, 0, nA, nA, gB, nB, R, f3(), a, b, n, d);
   pa[0] = a.x; pa[1] = a.y; pa[2] = a.z; pb[0] = b.x; pb[1] = b.y; pb[2] = b.z; nrm[0] = n.x; nrm[1] = n.y; nrm[2] = n.z; *dist = d;
   return ov ? 1 : 0;
 }
