@@ -518,8 +518,16 @@ static int set_mask(AgSim* s, const int32_t* mask) {
 }
 // scatter host [N][K] rows into a device SoA array with `comp` components per item:
 // dst[(item*comp + c)*N + e] = src[e*K + j*comp + c] for item = items[j]
+static int check_items(const AgSim* s, const float* arr, int nitems, const int* items) {
+  // the item-indexed arrays are per body (base_*) or per link (everything else)
+  int limit = (arr == s->S.base_pos || arr == s->S.base_quat || arr == s->S.base_lin || arr == s->S.base_ang) ? s->nb : s->nl;
+  if (nitems < 0 || (nitems > 0 && !items)) return fail("bad item list");
+  for (int j = 0; j < nitems; j++) if (items[j] < 0 || items[j] >= limit) return fail(limit == s->nb ? "bad body" : "bad link");
+  return 0;
+}
 static int scatter_host(AgSim* s, float* dst, int comp, int nitems, const int* items, const float* src, const int32_t* mask) {
   const int N = s->S.N;
+  if (check_items(s, dst, nitems, items)) return -1;
   size_t K = (size_t)nitems * comp;
   float* st = stage(s, K * N);
   if (!st) return fail("staging alloc failed");
@@ -533,6 +541,7 @@ static int scatter_host(AgSim* s, float* dst, int comp, int nitems, const int* i
 }
 static int gather_host(AgSim* s, const float* srcdev, int comp, int nitems, const int* items, float* dst) {
   const int N = s->S.N;
+  if (check_items(s, srcdev, nitems, items)) return -1;
   size_t K = (size_t)nitems * comp;
   float* st = stage(s, K * N);
   if (!st) return fail("staging alloc failed");
@@ -601,6 +610,7 @@ int ag_set_motor_host(AgSim* s, int n, const int32_t* links, int mode, const flo
 }
 int ag_set_motor_targets_dev(AgSim* s, int n, const int32_t* links, const float* target_dev) {
   if (n > 1024) return fail("too many items");
+  if (check_items(s, s->S.motor_target, n, links)) return -1;
   if (h2d(s, s->d_links, links, sizeof(int) * n)) return -1;
   KP p = kp0(); p.i0 = 1; p.i1 = n; p.p0 = target_dev; p.p1 = s->S.motor_target; p.p2 = s->d_links; p.p3 = nullptr;
   LAUNCH(s, k_scatter, (size_t)s->S.N * n, p);
@@ -682,6 +692,7 @@ int ag_get_joint_states(AgSim* s, int n, const int32_t* links, float* q, float* 
 int ag_get_link_states(AgSim* s, int n, const int32_t* links, float* pos, float* quat, float* com_pos, float* com_quat, float* lin_vel, float* ang_vel) {
   const int N = s->S.N;
   if (n > 1024) return fail("too many items");
+  for (int j = 0; j < n; j++) if (links[j] < 0 || links[j] >= s->nl) return fail("bad link");
   // out record per (env, link): 20 floats: pos3 quat4 cpos3 cquat4 lin3 ang3
   float* st = stage(s, (size_t)N * n * 20);
   if (!st) return fail("staging alloc failed");

@@ -141,6 +141,22 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes (read + write) of one launch of `kernel` from the newest committed `ncu --set full` summary
+    (profiles/r*_ncu_<kernel>.csv, written by tools/ncu_summary.py); (None, None) if there is none."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_ncu_%s.csv' % kernel)))
+    if not files:
+        return None, None
+    unit = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    tot = 0.0
+    for r in csv.reader(open(files[-1])):
+        if len(r) >= 4 and r[1] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            tot += float(r[3].replace(',', '')) * unit.get(r[2], 1.0)
+    return (tot if tot > 0 else None), os.path.relpath(files[-1], ROOT)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -263,7 +279,7 @@ def main():
             achieved = n * B_SUBSTEP / (per_launch_ms * 1e-3) / 1e9
             total_kernel_ms = sum(v[0] for v in prof.values())
             roof = {'bound': 'hbm', 'kernel': name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                    'traffic': None, 'peak_source': peak_src, 'kernel_ms_per_launch': per_launch_ms,
+                    'traffic': ncu_traffic(name)[0], 'traffic_source': ncu_traffic(name)[1], 'peak_source': peak_src, 'kernel_ms_per_launch': per_launch_ms,
                     'kernel_share_of_step': ms / total_kernel_ms if total_kernel_ms else None,
                     'step_frac': value * B_STEP / 1e9 / peak / world,
                     'per_kernel_ms_per_step': {k: v[0] / K for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
