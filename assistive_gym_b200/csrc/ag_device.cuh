@@ -49,7 +49,7 @@ AG_HD void ld_plane(const float* planes, int k, f3& n, float& d) {
 AG_HDN inline void fk_body(int e, const SimDev& S, const KP& p) {
   const int N = S.N;
   for (int b = 0; b < S.nb; b++) {
-    if (!p.i0 && AG_LDG(S.body_kind + b) == BK_STATIC) continue;
+    if (!p.i0 && (AG_LDG(S.body_kind + b) == BK_STATIC || S.body_mode[(size_t)b * N + e] != 1)) continue;   // off / frozen bodies keep their poses
     int l0 = AG_LDG(S.body_link0 + b), nlk = AG_LDG(S.body_nlinks + b);
     f3 bp = ld3(S.base_pos, b, N, e);
     q4 bq = ld4(S.base_quat, b, N, e);
