@@ -463,9 +463,25 @@ AG_HDN inline void pairs_body(int tid, const SimDev& S, const KP& kp) {
       float thr = fac * fminf(tha, AG_LDG(S.col_thresh + cb));   // size-relative breaking threshold
       if (!aabb_ov(amin, amax, ld3(S.cmin, cb, N, e), ld3(S.cmax, cb, N, e), thr)) continue;
       int slot = ag_atomic_inc(S.cand_count + e);
-      if (slot < S.maxcand) S.cand[(size_t)slot * N + e] = (unsigned)ca * (unsigned)S.nc + (unsigned)cb;
+      // word = (255 - cost) << 24 | pair id: ascending order = most expensive GJK first, ties by pair (K3a')
+      int cost = AG_LDG(S.col_nv + ca) + AG_LDG(S.col_nv + cb); if (cost > 255) cost = 255;
+      if (slot < S.maxcand) S.cand[(size_t)slot * N + e] = ((unsigned)(255 - cost) << 24) | ((unsigned)ca * (unsigned)S.nc + (unsigned)cb);
     }
   }
+}
+
+// K3a': thread = (candidate slot, env): order the env's candidates by (cost descending, pair id).  Every env is
+// a copy of the same scene, so after this the 32 envs of a warp of K3b work on pairs of similar cost at the same
+// slot (the un-ordered atomic arrival order left 9 of 32 lanes active); it also makes the list deterministic.
+AG_HDN inline void csort_body(int tid, const SimDev& S, const KP&) {
+  const int N = S.N;
+  int e = tid % N, cs = tid / N;
+  int n = S.cand_count[e]; if (n > S.maxcand) n = S.maxcand;
+  if (cs >= n) return;
+  unsigned w = S.cand[(size_t)cs * N + e];
+  int rank = 0;
+  for (int j = 0; j < n; j++) rank += (S.cand[(size_t)j * N + e] < w) ? 1 : 0;
+  S.cand_s[(size_t)rank * N + e] = w;
 }
 
 // K3b: thread = (candidate slot, env): GJK / face fallback / manifold for one collider pair.
@@ -474,19 +490,22 @@ AG_HDN inline void narrow_body(int tid, const SimDev& S, const KP&) {
   int e = tid % N, cs = tid / N;
   int ncand = S.cand_count[e]; if (ncand > S.maxcand) ncand = S.maxcand;
   if (cs >= ncand) return;
-  unsigned pk = S.cand[(size_t)cs * N + e];
+  unsigned pk = S.cand_s[(size_t)cs * N + e] & 0xffffffu;
   int ca = (int)(pk / (unsigned)S.nc), cb = (int)(pk % (unsigned)S.nc);
   float thr = S.contact_thr * fminf(AG_LDG(S.col_thresh + ca), AG_LDG(S.col_thresh + cb));
   NpOut out[4];
   int n = narrow_pair(S, e, ca, cb, thr, true, out);
   for (int i = 0; i < n; i++) {
+    // raw contacts land in arrival order in a buffer 4x the contact budget; K4 keeps the `maxc` smallest keys,
+    // so which contacts survive an over-budget env does not depend on the arrival order
     int slot = ag_atomic_inc(S.c_count + e);
-    if (slot >= S.maxc) continue;
+    if (slot >= S.maxraw) continue;
     S.c_key[(size_t)slot * N + e] = pk * 4u + (unsigned)i;
-    cf_st(S.c_data, slot, CF_PAX, N, e, out[i].pa.x); cf_st(S.c_data, slot, CF_PAY, N, e, out[i].pa.y); cf_st(S.c_data, slot, CF_PAZ, N, e, out[i].pa.z);
-    cf_st(S.c_data, slot, CF_PBX, N, e, out[i].pb.x); cf_st(S.c_data, slot, CF_PBY, N, e, out[i].pb.y); cf_st(S.c_data, slot, CF_PBZ, N, e, out[i].pb.z);
-    cf_st(S.c_data, slot, CF_NX, N, e, out[i].n.x); cf_st(S.c_data, slot, CF_NY, N, e, out[i].n.y); cf_st(S.c_data, slot, CF_NZ, N, e, out[i].n.z);
-    cf_st(S.c_data, slot, CF_DIST, N, e, out[i].d);
+    float* c = S.c_data + (size_t)slot * AG_CFR * N + e;
+    c[(size_t)CF_PAX * N] = out[i].pa.x; c[(size_t)CF_PAY * N] = out[i].pa.y; c[(size_t)CF_PAZ * N] = out[i].pa.z;
+    c[(size_t)CF_PBX * N] = out[i].pb.x; c[(size_t)CF_PBY * N] = out[i].pb.y; c[(size_t)CF_PBZ * N] = out[i].pb.z;
+    c[(size_t)CF_NX * N] = out[i].n.x; c[(size_t)CF_NY * N] = out[i].n.y; c[(size_t)CF_NZ * N] = out[i].n.z;
+    c[(size_t)CF_DIST * N] = out[i].d;
   }
 }
 
@@ -495,14 +514,17 @@ AG_HDN inline void sort_body(int tid, const SimDev& S, const KP&) {
   const int N = S.N;
   int e = tid % N, slot = tid / N;
   int cnt = S.c_count[e];
-  int n = cnt < S.maxc ? cnt : S.maxc;
-  if (slot == 0) S.overflow[e] = (cnt > S.maxc) || (S.cand_count[e] > S.maxcand);
+  int n = cnt < S.maxraw ? cnt : S.maxraw;
+  // sticky flag (cleared by ag_overflow_count): contacts over budget were dropped (by key order, or by arrival
+  // order beyond the raw buffer), or candidate pairs beyond `maxcand` were dropped
+  if (slot == 0 && ((cnt > S.maxc) || (S.cand_count[e] > S.maxcand))) S.overflow[e] = 1;
   if (slot >= n) return;
   unsigned key = S.c_key[(size_t)slot * N + e];
   int rank = 0;
   for (int j = 0; j < n; j++) rank += (S.c_key[(size_t)j * N + e] < key) ? 1 : 0;
+  if (rank >= S.maxc) return;
   S.s_key[(size_t)rank * N + e] = key;
-  for (int f = 0; f <= CF_DIST; f++) cf_st(S.s_data, rank, f, N, e, cf_ld(S.c_data, slot, f, N, e));
+  for (int f = 0; f <= CF_DIST; f++) cf_st(S.s_data, rank, f, N, e, S.c_data[((size_t)slot * AG_CFR + f) * N + e]);
 }
 
 // ------------------------------------------------------------------ K5: unconstrained dynamics

@@ -11,6 +11,7 @@
 #define AG_MAXND 16          // max articulated DoFs per env (all articulated bodies together)
 #define AG_MAX_HULL 64       // max core vertices per collider
 #define AG_CF 20             // floats per contact record
+#define AG_CFR 10            // floats per raw (unsorted) contact record: the first 10 fields
 
 // contact record fields (float index within the [AG_CF] record)
 enum {
@@ -58,10 +59,11 @@ struct SimDev {
   float *lpos, *lquat;                                 // [nl][3|4][N]
   float *cmin, *cmax, *lmin, *lmax;                    // [nc|nl][3][N]
   // ---- contacts
-  int* cand_count; unsigned* cand; int maxcand;        // narrowphase candidates (collider pairs) [maxcand][N]
+  int* cand_count; unsigned *cand, *cand_s; int maxcand; // narrowphase candidates (collider pairs) [maxcand][N]: arrival order / cost order
   int* c_count;                                        // [N]
-  unsigned *c_key, *s_key;                             // [maxc][N] unsorted / sorted
-  float *c_data, *s_data;                              // [maxc][AG_CF][N]
+  int maxraw;                                          // capacity of the raw (arrival-order) contact buffer = 4 maxc
+  unsigned *c_key, *s_key;                             // [maxraw][N] unsorted / [maxc][N] sorted
+  float *c_data, *s_data;                              // [maxraw][AG_CFR][N] raw / [maxc][AG_CF][N] sorted
   int *s_ref;                                          // [maxc][4][N]: refA, refB, stream slot of the normal row, of the friction pair
   int* overflow;                                       // [N]
   // ---- solver scratch

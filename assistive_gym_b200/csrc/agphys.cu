@@ -49,6 +49,7 @@ AG_KERNEL(k_fk, fk_body)
 AG_KERNEL(k_aabb, aabb_body)
 AG_KERNEL(k_linkaabb, linkaabb_body)
 AG_KERNEL(k_pairs, pairs_body)
+AG_KERNEL(k_csort, csort_body)
 AG_KERNEL_B(k_narrow, narrow_body, 3)
 AG_KERNEL(k_sort, sort_body)
 AG_KERNEL(k_dyn, dyn_body)
@@ -410,9 +411,11 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   S.lmin = dalloc<float>(s, (size_t)nl * 3 * N); S.lmax = dalloc<float>(s, (size_t)nl * 3 * N);
   S.c_count = dalloc<int>(s, N); S.overflow = dalloc<int>(s, N); S.iters_used = dalloc<int>(s, N); S.pgs_cycles = dalloc<int>(s, N);
   S.pgs_order = dalloc<int>(s, N); S.pgs_hist = dalloc<int>(s, 64);
-  S.maxcand = 4 * S.maxc; S.cand_count = dalloc<int>(s, N); S.cand = dalloc<unsigned>(s, (size_t)S.maxcand * N);
-  S.c_key = dalloc<unsigned>(s, (size_t)S.maxc * N); S.s_key = dalloc<unsigned>(s, (size_t)S.maxc * N);
-  S.c_data = dalloc<float>(s, (size_t)S.maxc * AG_CF * N); S.s_data = dalloc<float>(s, (size_t)S.maxc * AG_CF * N);
+  S.maxcand = 4 * S.maxc; S.cand_count = dalloc<int>(s, N); S.cand = dalloc<unsigned>(s, (size_t)S.maxcand * N); S.cand_s = dalloc<unsigned>(s, (size_t)S.maxcand * N);
+  if ((size_t)nc * nc >= (1u << 24)) { g_err = "too many colliders (pair id must fit 24 bits)"; ag_destroy(s); return nullptr; }
+  S.maxraw = 4 * S.maxc;
+  S.c_key = dalloc<unsigned>(s, (size_t)S.maxraw * N); S.s_key = dalloc<unsigned>(s, (size_t)S.maxc * N);
+  S.c_data = dalloc<float>(s, (size_t)S.maxraw * AG_CFR * N); S.s_data = dalloc<float>(s, (size_t)S.maxc * AG_CF * N);
   S.s_ref = dalloc<int>(s, (size_t)S.maxc * 4 * N);
   S.fcom = dalloc<float>(s, (size_t)S.nf * 3 * N); S.fIinv = dalloc<float>(s, (size_t)S.nf * 6 * N);
   S.jax = dalloc<float>(s, (size_t)S.ND * 3 * N); S.jor = dalloc<float>(s, (size_t)S.ND * 3 * N);
@@ -635,8 +638,9 @@ static void substep(AgSim* s) {
   int Npad = (N + 31) / 32 * 32;
   KP c = kp0(); c.i0 = Npad;
   LAUNCH(s, k_pairs, (size_t)S.npair * Npad, c);
+  LAUNCH(s, k_csort, (size_t)S.maxcand * N, z);
   LAUNCH(s, k_narrow, (size_t)S.maxcand * N, z);
-  LAUNCH(s, k_sort, (size_t)S.maxc * N, z);
+  LAUNCH(s, k_sort, (size_t)S.maxraw * N, z);
   LAUNCH(s, k_dyn, N, z);
   LAUNCH(s, k_rows, N, z);
   LAUNCH(s, k_crows, (size_t)(S.maxc + 3 * S.ND + S.ngr) * N, z);
@@ -798,6 +802,7 @@ int ag_overflow_count(AgSim* s) {
   std::vector<int> o(s->S.N);
   if (d2h(s, o.data(), s->S.overflow, sizeof(int) * s->S.N)) return -1;
   int n = 0; for (int v : o) n += v != 0;
+  if (n && dev_zero(s, s->S.overflow, sizeof(int) * s->S.N)) return -1;     // the flags are sticky until read
   return n;
 }
 

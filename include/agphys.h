@@ -216,7 +216,9 @@ uint64_t ag_kernel_launches(const AgSim* sim);    /* kernels launched since crea
 /* per-kernel device time (CUDA events on the sim's stream around every launch while enabled) */
 int      ag_profile_enable(AgSim* sim, int on);
 int      ag_profile_get(AgSim* sim, int max_names, char* names, int name_stride, float* total_ms, int32_t* counts);
-int      ag_overflow_count(AgSim* sim);
+int      ag_overflow_count(AgSim* sim);            /* envs that exceeded the contact / candidate budget in any substep since the
+                                                      last call (sticky flags, cleared by this call); surviving contacts are the
+                                                      smallest keys (collider pair, point), independent of arrival order */
 /* per-env contact count and PGS iterations used in the last substep (host int32[N] buffers, may be NULL) */
 int      ag_get_solver_stats(AgSim* sim, int32_t* contacts, int32_t* iters);
 /* SM cycles each env's lane spent inside the PGS kernel of the last substep (load-balance diagnostic) */

@@ -90,6 +90,24 @@ def _check_state_roundtrip(fb, mk):
     assert np.array_equal(sim.state_get(), a)
 
 
+def _check_overflow_determinism(fb, mk):
+    """Contact budget too small (32 for ~80 contacts; the raw buffer holds 4x the budget): the surviving contacts
+    are chosen by key, not by the order in which threads happened to append them, so runs from the same state
+    agree bit for bit; the flag is sticky until read."""
+    cfg = capi.default_config(max_contacts=32)
+    sim = mk(fb.scene, cfg, 64)
+    fb.reset(sim, np.random.default_rng(2), settle_steps=0)
+    st = sim.state_get()
+    sim.step(10)
+    a = sim.state_get()
+    assert sim.overflow_count() == 64
+    for _ in range(3):
+        sim.state_set(st)
+        sim.step(10)
+        assert np.array_equal(sim.state_get(), a)
+    assert np.all(np.isfinite(a))
+
+
 def _check_abi_errors(lib):
     scene, ball = _falling_sphere_scene(True)
     cfg = capi.default_config()
@@ -126,6 +144,10 @@ def test_state_roundtrip_cpu(feeding, mk_cpu):
     _check_state_roundtrip(feeding, mk_cpu)
 
 
+def test_overflow_determinism_cpu(feeding, mk_cpu):
+    _check_overflow_determinism(feeding, mk_cpu)
+
+
 def test_abi_errors_cpu(emu_lib):
     _check_abi_errors(emu_lib)
 
@@ -154,6 +176,11 @@ def test_batch_invariance_gpu(feeding, mk_gpu):
 @pytest.mark.gpu
 def test_state_roundtrip_gpu(feeding, mk_gpu):
     _check_state_roundtrip(feeding, mk_gpu)
+
+
+@pytest.mark.gpu
+def test_overflow_determinism_gpu(feeding, mk_gpu):
+    _check_overflow_determinism(feeding, mk_gpu)
 
 
 @pytest.mark.gpu
