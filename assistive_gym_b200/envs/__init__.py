@@ -1,6 +1,7 @@
+from .bed_bathing_envs import BedBathingSawyerEnv  # noqa: F401
 from .feeding_envs import FeedingJacoEnv  # noqa: F401
 
-ENV_REGISTRY = {'FeedingJaco-v1': FeedingJacoEnv}
+ENV_REGISTRY = {'FeedingJaco-v1': FeedingJacoEnv, 'BedBathingSawyer-v1': BedBathingSawyerEnv}
 
 
 def make(env_id, **kw):

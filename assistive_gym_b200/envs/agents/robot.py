@@ -66,3 +66,25 @@ class Jaco(Robot):
                          {'scratch_itch': [0, np.pi / 2.0, 0], 'feeding': [np.pi / 2.0, 0, np.pi / 2.0], 'drinking': [0, np.pi / 2.0, 0],
                           'bed_bathing': [0, np.pi / 2.0, 0], 'dressing': [[0, -np.pi / 2.0, 0]], 'arm_manipulation': [0, np.pi / 2.0, 0]},
                          wheelchair_mounted=True, half_range=False)
+
+
+class Sawyer(Robot):
+    """reference envs/agents/sawyer.py:6-49 (the constants of the hot path)."""
+
+    def __init__(self, controllable_joints='right'):
+        arm = [3, 8, 9, 10, 11, 13, 16]
+        super().__init__(controllable_joints, arm, arm, [], 19, 19, [20, 22], [20, 22],
+                         {'scratch_itch': [0.015, -0.015], 'feeding': [0, 0], 'drinking': [0.025, -0.025], 'bed_bathing': [0.0125, -0.0125],
+                          'dressing': [0, 0], 'arm_manipulation': [0.01, -0.01]},
+                         18, 18,
+                         {'scratch_itch': [0, 0.125, 0], 'feeding': [-0.1, 0.12, -0.02], 'drinking': [0.05, 0.125, 0],
+                          'bed_bathing': [0, 0.1175, 0], 'arm_manipulation': [0.075, 0.235, 0]},
+                         {'scratch_itch': [0, 0, np.pi / 2.0], 'feeding': [np.pi / 2.0 - 0.1, 0, np.pi / 2.0], 'drinking': [0, 0, np.pi / 2.0],
+                          'bed_bathing': [np.pi / 2.0, 0, np.pi / 2.0], 'arm_manipulation': [0, 0, np.pi / 2.0]},
+                         [18, 20, 21, 22, 23], [18, 20, 21, 22, 23],
+                         {'scratch_itch': [-0.1, 0, 0.975], 'feeding': [-0.1, 0.2, 0.975], 'drinking': [-0.1, 0.2, 0.975],
+                          'bed_bathing': [-0.2, 0, 0.975], 'dressing': [1.8, 0.7, 0.975], 'arm_manipulation': [-0.3, 0.6, 0.975]},
+                         {'scratch_itch': [0, np.pi / 2.0, 0], 'feeding': [np.pi / 2.0, 0, np.pi / 2.0], 'drinking': [0, -np.pi / 2.0, np.pi],
+                          'bed_bathing': [0, np.pi / 2.0, 0], 'dressing': [[0, -np.pi / 2.0, 0], [np.pi / 2.0, -np.pi / 2.0, 0]],
+                          'arm_manipulation': [0, -np.pi / 2.0, np.pi]},
+                         wheelchair_mounted=False, half_range=False)
