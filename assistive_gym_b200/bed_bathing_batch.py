@@ -107,6 +107,38 @@ class BedBathingBatch:
             self.targets_local[g] = (capsule_points([0, 0, 0], [0, 0, -ul], ur, 0.03), capsule_points([0, 0, 0], [0, 0, -fl], fr, 0.03))
         self.max_targets = max(len(u) + len(f) for u, f in self.targets_local.values())
 
+    # ------------------------------------------------------------------ params for the fused kernels
+    def bathing_params(self):
+        from . import capi
+        sc = self.scene
+        P = capi.AgBathingParams()
+        P.robot_body, P.tool_body = self.robot, self.tool
+        P.human_body_m, P.human_body_f = self.humans['male'], self.humans['female']
+        for i, l in enumerate(self.arm_links):
+            P.arm_links[i] = l; P.arm_lower[i] = self.arm_lower[i]; P.arm_upper[i] = self.arm_upper[i]
+        P.ee_link, P.cloth_link = self.ee_link, self.cloth_link
+        for i, l in enumerate((R_SHOULDER, R_ELBOW, R_WRIST)):
+            P.arm_points_m[i] = self.gl(self.humans['male'], l); P.arm_points_f[i] = self.gl(self.humans['female'], l)
+        for g, tag in (('male', 'm'), ('female', 'f')):
+            hb = self.humans[g]
+            l0, nl = int(sc['body_link0'][hb]), int(sc['body_nlinks'][hb])
+            cols = [c for c in range(sc.n_colliders) if l0 <= sc['col_link'][c] < l0 + nl]
+            assert cols == list(range(cols[0], cols[0] + len(cols)))          # a body's colliders are contiguous
+            setattr(P, 'human_col0_' + tag, cols[0]); setattr(P, 'human_ncol_' + tag, len(cols))
+        P.n_targets_max = self.max_targets
+        P.action_multiplier, P.frame_skip = 0.05, 5
+        P.w_distance, P.w_action, P.w_wiping = 1.0, 0.01, 5.0                # config.ini [bed_bathing]
+        P.c_v, P.c_f, P.c_hf = 0.25, 0.01, 0.05                              # config.ini [human_preferences]
+        P.task_success_threshold = 0.3
+        return P
+
+    def start_fused(self, sim, sample=None):
+        """Arm the fused per-step kernels for the envs last put in place by `reset`."""
+        s = sample or self.last_sample
+        tw, valid = self.targets_world(sim, s)
+        sim.bathing_init(self.bathing_params(), s['male'], tw, valid)
+        return tw, valid
+
     # ------------------------------------------------------------------ batched reset
     def sample(self, n, rng):
         nj = 41

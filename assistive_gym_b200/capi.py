@@ -66,6 +66,18 @@ class AgFeedingParams(C.Structure):
                 ('task_success_threshold', C.c_float), ('seed', C.c_uint64)]
 
 
+class AgBathingParams(C.Structure):
+    _fields_ = [('robot_body', C.c_int32), ('tool_body', C.c_int32), ('human_body_m', C.c_int32), ('human_body_f', C.c_int32),
+                ('arm_links', C.c_int32 * 7), ('ee_link', C.c_int32), ('cloth_link', C.c_int32),
+                ('arm_points_m', C.c_int32 * 3), ('arm_points_f', C.c_int32 * 3),
+                ('human_col0_m', C.c_int32), ('human_ncol_m', C.c_int32), ('human_col0_f', C.c_int32), ('human_ncol_f', C.c_int32),
+                ('n_targets_max', C.c_int32),
+                ('arm_lower', C.c_float * 7), ('arm_upper', C.c_float * 7),
+                ('action_multiplier', C.c_float), ('frame_skip', C.c_int32),
+                ('w_distance', C.c_float), ('w_action', C.c_float), ('w_wiping', C.c_float),
+                ('c_v', C.c_float), ('c_f', C.c_float), ('c_hf', C.c_float), ('task_success_threshold', C.c_float)]
+
+
 import numpy as np  # noqa: E402
 
 CONTACT_DTYPE = np.dtype([('link_a', np.int32), ('link_b', np.int32), ('pos_a', np.float32, 3), ('pos_b', np.float32, 3),
@@ -115,6 +127,9 @@ def load_library(path=None):
     lib.ag_set_hard_limits.argtypes = [vp, ci, vp, ci]
     lib.ag_feeding_step_dev.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.ag_feeding_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.ag_bathing_init.argtypes = [vp, C.POINTER(AgBathingParams), vp, vp, vp]
+    lib.ag_bathing_step_dev.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.ag_bathing_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.ag_state_size.restype = C.c_size_t
     lib.ag_state_size.argtypes = [vp]
     lib.ag_state_get.argtypes = [vp, vp]
@@ -137,7 +152,7 @@ EXPORTED_SYMBOLS = [
     'ag_set_base_pose', 'ag_set_base_velocity', 'ag_set_joint_state', 'ag_set_link_friction',
     'ag_set_body_active', 'ag_forward_kinematics', 'ag_set_motor_host', 'ag_set_motor_targets_dev', 'ag_set_motor_targets_host',
     'ag_step', 'ag_get_joint_states', 'ag_get_link_states', 'ag_get_contacts', 'ag_contact_force_sum',
-    'ag_closest_points', 'ag_feeding_init', 'ag_feeding_reset_episode', 'ag_feeding_set_tremor', 'ag_set_hard_limits', 'ag_feeding_step_dev',
+    'ag_closest_points', 'ag_feeding_init', 'ag_feeding_reset_episode', 'ag_feeding_set_tremor', 'ag_set_hard_limits', 'ag_feeding_step_dev', 'ag_bathing_init', 'ag_bathing_step_dev', 'ag_bathing_step_host',
     'ag_feeding_step_host', 'ag_state_size', 'ag_state_get', 'ag_state_set', 'ag_kernel_launches',
     'ag_overflow_count', 'ag_get_solver_stats', 'ag_get_pgs_cycles', 'ag_profile_enable', 'ag_profile_get',
 ]

@@ -215,7 +215,10 @@ AG_HDN inline void feeding_post_body(int e, const SimDev& S, const KP& p) {
   int head = male ? P.head_link_m : P.head_link_f;
   // poses
   int lr = AG_LDG(S.body_link0 + P.robot_body), ltool = AG_LDG(S.body_link0 + P.tool_body);
-  f3 rp = ld3(S.lpos, lr, N, e); q4 rq = ld4(S.lquat, lr, N, e);
+  // robot base pose = its inertial frame, as p.getBasePositionAndOrientation reports it (agent.py:49,58-63)
+  q4 rq = ld4(S.lquat, lr, N, e);
+  f3 rp = ld3(S.lpos, lr, N, e) + qrot(rq, tv3(S.link_com, lr));
+  rq = qmul(rq, tv4(S.link_iquat, lr));
   q4 rqi = qconj(rq);
   f3 sp = ld3(S.lpos, ltool, N, e) + qrot(ld4(S.lquat, ltool, N, e), tv3(S.link_com, ltool));
   q4 sq = qmul(ld4(S.lquat, ltool, N, e), tv4(S.link_iquat, ltool));

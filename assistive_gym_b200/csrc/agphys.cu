@@ -12,6 +12,7 @@
 #include "ag_device.cuh"
 #include "ag_solver.cuh"
 #include "ag_feeding.cuh"
+#include "ag_bathing.cuh"
 
 #ifndef AG_CPU_EMU
 #include <cuda_runtime.h>
@@ -85,6 +86,9 @@ AG_KERNEL(k_closest, closest_body)
 AG_KERNEL(k_feed_pre, feeding_pre_body)
 AG_KERNEL(k_feed_food, feeding_food_body)
 AG_KERNEL(k_feed_post, feeding_post_body)
+AG_KERNEL(k_bath_pre, bathing_pre_body)
+AG_KERNEL(k_bath_dist, bathing_dist_body)
+AG_KERNEL(k_bath_post, bathing_post_body)
 
 // ------------------------------------------------------------------ host object
 struct AgSim {
@@ -103,6 +107,8 @@ struct AgSim {
   int* d_mask; int* d_links; int* d_icount;
   // feeding
   FeedDev F; FeedDev* F_dev; bool feeding;
+  BathDev B; BathDev* B_dev; bool bathing;
+  float *h_bpin_in, *h_bpin_out, *d_baction, *d_bobs, *d_breward, *d_bdone, *d_binfo;
   float *d_action, *d_obs, *d_reward, *d_done, *d_info;
   float *h_pin_in, *h_pin_out;
   int pgs_lanes;
@@ -235,7 +241,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   AgSim* s = new AgSim();
   memset(&s->S, 0, sizeof(SimDev));
   memset(&s->F, 0, sizeof(FeedDev));
-  s->cfg = *cfg; s->device = device; s->launches = 0; s->feeding = false; s->stream = nullptr; s->F_dev = nullptr; s->profiling = false;
+  s->cfg = *cfg; s->device = device; s->launches = 0; s->feeding = false; s->bathing = false; s->B_dev = nullptr; s->stream = nullptr; s->F_dev = nullptr; s->profiling = false;
   s->d_stage = nullptr; s->stage_floats = 0;
 #ifndef AG_CPU_EMU
   if (cudaSetDevice(device) != cudaSuccess) { g_err = "cudaSetDevice failed (is a CUDA device present? there is no CPU fallback)"; delete s; return nullptr; }
@@ -910,6 +916,99 @@ int ag_feeding_step_host(AgSim* s, const float* action, float* obs, float* rewar
   memcpy(reward, s->h_pin_out + (size_t)N * 25, sizeof(float) * N);
   memcpy(done, s->h_pin_out + (size_t)N * 26, sizeof(float) * N);
   if (info) memcpy(info, s->h_pin_out + (size_t)N * 27, sizeof(float) * N * 4);
+  return 0;
+}
+
+// ------------------------------------------------------------------ fused BedBathingEnv path
+int ag_bathing_init(AgSim* s, const AgBathingParams* p, const int32_t* gender_is_male, const float* targets_world, const int32_t* targets_valid) {
+  const int N = s->S.N;
+  BathDev& B = s->B;
+  B.P = *p;
+  const int T = p->n_targets_max;
+  if (T <= 0 || T > 4096) return fail("bad target count");
+  for (int j = 0; j < 7; j++) if (p->arm_links[j] < 0 || p->arm_links[j] >= s->nl) return fail("bad link");
+  if (p->cloth_link < 0 || p->cloth_link >= s->nl || p->ee_link < 0 || p->ee_link >= s->nl) return fail("bad link");
+  if (!s->bathing) {
+    B.male = dalloc<int>(s, N); B.iteration = dalloc<int>(s, N); B.task_success = dalloc<int>(s, N); B.total_targets = dalloc<int>(s, N);
+    B.action = dalloc<float>(s, (size_t)N * 7);
+    B.targets = dalloc<float>(s, (size_t)T * 3 * N); B.alive = dalloc<int>(s, (size_t)T * N);
+    B.n_slots = p->human_ncol_m > p->human_ncol_f ? p->human_ncol_m : p->human_ncol_f;
+    B.dist_part = dalloc<float>(s, (size_t)(B.n_slots > 0 ? B.n_slots : 1) * N);
+    s->d_baction = dalloc<float>(s, (size_t)N * 7); s->d_bobs = dalloc<float>(s, (size_t)N * 24);
+    s->d_breward = dalloc<float>(s, N); s->d_bdone = dalloc<float>(s, N); s->d_binfo = dalloc<float>(s, (size_t)N * 4);
+    s->B_dev = dalloc<BathDev>(s, 1);
+    if (!s->B_dev || !s->d_binfo || !B.dist_part) return fail("device allocation failed");
+#ifndef AG_CPU_EMU
+    CK(cudaMallocHost((void**)&s->h_bpin_in, sizeof(float) * N * 7));
+    CK(cudaMallocHost((void**)&s->h_bpin_out, sizeof(float) * N * 30));
+#else
+    s->h_bpin_in = (float*)malloc(sizeof(float) * N * 7); s->h_bpin_out = (float*)malloc(sizeof(float) * N * 30);
+#endif
+  } else if (T != s->B.P.n_targets_max) return fail("target count changed");
+  std::vector<float> tw((size_t)T * 3 * N); std::vector<int> al((size_t)T * N), tot(N, 0), zero(N, 0);
+  for (int e = 0; e < N; e++)
+    for (int t = 0; t < T; t++) {
+      int v = targets_valid[(size_t)e * T + t] != 0;
+      al[(size_t)t * N + e] = v; tot[e] += v;
+      for (int c = 0; c < 3; c++) tw[((size_t)t * 3 + c) * N + e] = targets_world[((size_t)e * T + t) * 3 + c];
+    }
+  if (h2d(s, B.targets, tw.data(), tw.size() * sizeof(float)) || h2d(s, B.alive, al.data(), al.size() * sizeof(int))) return -1;
+  if (h2d(s, B.total_targets, tot.data(), sizeof(int) * N) || h2d(s, B.male, gender_is_male, sizeof(int) * N)) return -1;
+  if (h2d(s, B.iteration, zero.data(), sizeof(int) * N) || h2d(s, B.task_success, zero.data(), sizeof(int) * N)) return -1;
+  if (h2d(s, s->B_dev, &s->B, sizeof(BathDev))) return fail("BathDev upload failed");
+  s->bathing = true;
+  return 0;
+}
+static int bathing_step_enqueue(AgSim* s, const float* action_dev, float* obs, float* reward, float* done, float* info) {
+  const int N = s->S.N;
+  KP p = kp0(); p.p0 = action_dev; p.p1 = s->B_dev;
+  LAUNCH(s, k_bath_pre, N, p);
+  for (int i = 0; i < s->B.P.frame_skip * (s->cfg.num_substeps > 0 ? s->cfg.num_substeps : 1); i++) substep(s);
+  KP z = kp0();
+  LAUNCH(s, k_fk, N, z);
+  KP a = kp0(); a.p0 = s->S.movcol; a.i0 = s->S.nmovcol;
+  LAUNCH(s, k_aabb, (size_t)s->S.nmovcol * N, a);
+  KP l = kp0(); l.p0 = s->S.movlink; l.i0 = s->S.nmovlink;
+  LAUNCH(s, k_linkaabb, (size_t)s->S.nmovlink * N, l);
+  KP d = kp0(); d.p1 = s->B_dev;
+  LAUNCH(s, k_bath_dist, (size_t)N * s->B.n_slots, d);
+  KP q = kp0(); q.p0 = action_dev; q.p1 = s->B_dev; q.p2 = obs; q.p3 = reward; q.p4 = done; q.p5 = info;
+  LAUNCH(s, k_bath_post, N, q);
+  return 0;
+}
+int ag_bathing_step_dev(AgSim* s, const float* action_dev, float* obs_dev, float* reward_dev, float* done_dev, float* info_dev) {
+  if (!s->bathing) return fail("ag_bathing_init not called");
+  int rc = bathing_step_enqueue(s, action_dev, obs_dev, reward_dev, done_dev, info_dev);
+#ifndef AG_CPU_EMU
+  CK(cudaGetLastError());
+#endif
+  return rc;
+}
+int ag_bathing_step_host(AgSim* s, const float* action, float* obs, float* reward, float* done, float* info) {
+  if (!s->bathing) return fail("ag_bathing_init not called");
+  const int N = s->S.N;
+  memcpy(s->h_bpin_in, action, sizeof(float) * N * 7);
+#ifndef AG_CPU_EMU
+  CK(cudaMemcpyAsync(s->d_baction, s->h_bpin_in, sizeof(float) * N * 7, cudaMemcpyHostToDevice, s->stream));
+#else
+  memcpy(s->d_baction, s->h_bpin_in, sizeof(float) * N * 7);
+#endif
+  if (bathing_step_enqueue(s, s->d_baction, s->d_bobs, s->d_breward, s->d_bdone, s->d_binfo)) return -1;
+#ifndef AG_CPU_EMU
+  CK(cudaMemcpyAsync(s->h_bpin_out, s->d_bobs, sizeof(float) * N * 24, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(s->h_bpin_out + (size_t)N * 24, s->d_breward, sizeof(float) * N, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(s->h_bpin_out + (size_t)N * 25, s->d_bdone, sizeof(float) * N, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(s->h_bpin_out + (size_t)N * 26, s->d_binfo, sizeof(float) * N * 4, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+#else
+  memcpy(s->h_bpin_out, s->d_bobs, sizeof(float) * N * 24); memcpy(s->h_bpin_out + (size_t)N * 24, s->d_breward, sizeof(float) * N);
+  memcpy(s->h_bpin_out + (size_t)N * 25, s->d_bdone, sizeof(float) * N); memcpy(s->h_bpin_out + (size_t)N * 26, s->d_binfo, sizeof(float) * N * 4);
+#endif
+  memcpy(obs, s->h_bpin_out, sizeof(float) * N * 24);
+  memcpy(reward, s->h_bpin_out + (size_t)N * 24, sizeof(float) * N);
+  memcpy(done, s->h_bpin_out + (size_t)N * 25, sizeof(float) * N);
+  if (info) memcpy(info, s->h_bpin_out + (size_t)N * 26, sizeof(float) * N * 4);
   return 0;
 }
 

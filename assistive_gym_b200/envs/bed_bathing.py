@@ -1,9 +1,11 @@
 """`BedBathingEnv` (reference envs/bed_bathing.py) on the batched backend.
 
-The step goes through the reference-shaped per-call API (`take_step` + `_get_obs` + `get_total_force`
-+ `human_preferences`), vectorised over `n_envs`; the per-contact Python loop of `get_total_force`
-(bed_bathing.py:41-78) becomes one masked distance test of every tool-cloth contact against every
-remaining wiping target.  No fused kernel for this task yet (FeedingEnv has one)."""
+`step` runs the fused kernels (`ag_bathing_step_host`): action -> PD targets -> 5 substeps -> obs /
+reward / done, wiping targets included.  `step_reference_api` performs the same step the way the
+reference does it -- `take_step` + `_get_obs` + `get_total_force` + `human_preferences` through the
+per-call `Agent` API, vectorised over `n_envs` (the per-contact Python loop of `get_total_force`,
+bed_bathing.py:41-78, becomes one masked distance test of every tool-cloth contact against every
+remaining wiping target) -- and exists so that tests can show the two paths agree."""
 import numpy as np
 
 from .. import capi
@@ -24,8 +26,21 @@ class BedBathingEnv(AssistiveEnv):
         self._cfg = config or capi.default_config()
         self._sim_lib = None
 
-    # ------------------------------------------------------------------ step (bed_bathing.py:12-39)
+    # ------------------------------------------------------------------ fused step (bed_bathing.py:12-39)
     def step(self, action):
+        a = np.asarray(action, dtype=np.float32).reshape(self.n_envs, -1)
+        obs, rew, done, info = self.id.bathing_step_host(a)
+        self.iteration += 1
+        self.total_force_on_human, self.tool_force_on_human, self.new_contact_points = info[:, 0], info[:, 2], info[:, 3].astype(int)
+        self.task_success += self.new_contact_points
+        out = {'total_force_on_human': info[:, 0], 'task_success': info[:, 1].astype(int), 'action_robot_len': self.action_robot_len,
+               'action_human_len': self.action_human_len, 'obs_robot_len': self.obs_robot_len, 'obs_human_len': self.obs_human_len}
+        if self.n_envs == 1:
+            return obs[0], float(rew[0]), bool(done[0] > 0.5), {k_: (v[0] if isinstance(v, np.ndarray) else v) for k_, v in out.items()}
+        return obs, rew, done > 0.5, out
+
+    # ------------------------------------------------------------------ the same step through the reference-shaped API
+    def step_reference_api(self, action):
         a = np.asarray(action, dtype=np.float64).reshape(self.n_envs, -1)
         self.take_step(a)
         obs = self._get_obs()
@@ -96,7 +111,7 @@ class BedBathingEnv(AssistiveEnv):
         return self._get_obs()[0] if self.n_envs == 1 else self._get_obs()
 
     def generate_targets(self, s):                                         # bed_bathing.py:173-203
-        self.targets_pos_world, self.targets_alive = self._bb.targets_world(self.id, s)
+        self.targets_pos_world, self.targets_alive = self._bb.start_fused(self.id, s)
         self.total_target_count = self.targets_alive.sum(axis=1)
 
     def update_targets(self):

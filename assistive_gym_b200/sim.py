@@ -192,6 +192,24 @@ class BatchSim:
         o = _i32(np.broadcast_to(np.asarray(on, dtype=np.int32), (self.n,)))
         self._ck(self.lib.ag_feeding_set_tremor(self.h, _p(o), _p(_f32(rest, (self.n, 4))), _p(_f32(amplitude, (self.n, 4)))))
 
+    # ---- fused bed-bathing path
+    def bathing_init(self, params, gender_is_male, targets_world, targets_valid):
+        g = _i32(np.broadcast_to(np.asarray(gender_is_male, dtype=np.int32), (self.n,)))
+        T = int(params.n_targets_max)
+        tw = _f32(targets_world, (self.n, T, 3)); tv = _i32(np.ascontiguousarray(targets_valid, dtype=np.int32).reshape(self.n, T))
+        self._ck(self.lib.ag_bathing_init(self.h, C.byref(params), _p(g), _p(tw), _p(tv)))
+
+    def bathing_step_host(self, action):
+        a = _f32(action, (self.n, 7))
+        obs = np.zeros((self.n, 24), dtype=np.float32)
+        rew, done = np.zeros(self.n, dtype=np.float32), np.zeros(self.n, dtype=np.float32)
+        info = np.zeros((self.n, 4), dtype=np.float32)
+        self._ck(self.lib.ag_bathing_step_host(self.h, _p(a), _p(obs), _p(rew), _p(done), _p(info)))
+        return obs, rew, done, info
+
+    def bathing_step_dev(self, action_ptr, obs_ptr, reward_ptr, done_ptr, info_ptr):
+        self._ck(self.lib.ag_bathing_step_dev(self.h, C.c_void_p(action_ptr), C.c_void_p(obs_ptr), C.c_void_p(reward_ptr), C.c_void_p(done_ptr), C.c_void_p(info_ptr)))
+
     def feeding_reset_episode(self, mask=None):
         self._ck(self.lib.ag_feeding_reset_episode(self.h, _p(_i32(mask))))
 

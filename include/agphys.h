@@ -206,6 +206,32 @@ int ag_feeding_step_dev(AgSim* sim, const float* action_dev, float* obs_dev, flo
 /* host-buffer variant (pinned or pageable): H2D of action, D2H of obs/reward/done/info inside */
 int ag_feeding_step_host(AgSim* sim, const float* action, float* obs, float* reward, float* done, float* info);
 
+/* --- fused BedBathingEnv path (bed_bathing.py:12-111 + env.py:174-274): action -> PD targets ->
+ * frame_skip substeps -> obs[24] / reward / done; wiping targets are points on the person's right arm
+ * (bed_bathing.py:173-203), a target within 0.025 m of a wiper-cloth contact point counts once
+ * (bed_bathing.py:41-78).  SURVEY.md §8(a) row B1. ------------------------------------------- */
+typedef struct AgBathingParams {
+  int32_t robot_body, tool_body, human_body_m, human_body_f;
+  int32_t arm_links[7];         /* controllable joints (global link ids) */
+  int32_t ee_link;              /* left_end_effector */
+  int32_t cloth_link;           /* wiper link 1 (global link id): `if linkA in [1]` */
+  int32_t arm_points_m[3], arm_points_f[3];   /* right shoulder, elbow, wrist links (global ids) */
+  int32_t human_col0_m, human_ncol_m, human_col0_f, human_ncol_f;   /* collider ranges of the two persons */
+  int32_t n_targets_max;        /* padded target count T (129 male / 91 female) */
+  float   arm_lower[7], arm_upper[7];
+  float   action_multiplier;    /* 0.05 env.py:188 */
+  int32_t frame_skip;           /* 5 */
+  float   w_distance, w_action, w_wiping;   /* config.ini [bed_bathing] */
+  float   c_v, c_f, c_hf;                   /* config.ini [human_preferences] */
+  float   task_success_threshold;
+} AgBathingParams;
+/* targets_world [N][T][3], targets_valid [N][T] (host); the person must already be frozen in place */
+int ag_bathing_init(AgSim* sim, const AgBathingParams* p, const int32_t* gender_is_male, const float* targets_world,
+                    const int32_t* targets_valid);
+/* obs [N][24], reward [N], done [N], info [N][4] = total force on person, task success, cloth force on person, new targets */
+int ag_bathing_step_dev(AgSim* sim, const float* action_dev, float* obs_dev, float* reward_dev, float* done_dev, float* info_dev);
+int ag_bathing_step_host(AgSim* sim, const float* action, float* obs, float* reward, float* done, float* info);
+
 /* --- checkpoint / parity: full per-env dynamic state as a flat float blob -------------------- */
 size_t ag_state_size(const AgSim* sim);           /* floats per env */
 int    ag_state_get(AgSim* sim, float* out);      /* [N][state_size] host */

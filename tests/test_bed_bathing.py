@@ -67,12 +67,17 @@ def _pressed_pair(bb, make_sim, n, seed):
         gap = np.minimum(gap, np.where(np.arange(32)[None, :] < k[:, None], c['distance'], np.inf).min(axis=1))
     h0 = 0.25 - (gap - 0.005)
     q_hi, e_hi = bb.solve_ik(bb.base_pos, bb.base_quat, mid + np.stack([0 * h0, 0 * h0, h0], axis=1), rng, max_restarts=12)
-    q_lo, e_lo = bb.solve_ik(bb.base_pos, bb.base_quat, mid + np.stack([0 * h0, 0 * h0, h0 - 0.05], axis=1), rng, max_restarts=12)
+    # the pressing pose: 5 cm lower, continued from the start pose so that it is the neighbouring IK branch
+    from assistive_gym_b200.kinematics import ik_dls, q_from_rpy
+    tq = np.broadcast_to(q_from_rpy(SAWYER['ee_orient_rpy']), (n, 4)).copy()
+    q_lo, pe, oe = ik_dls(bb.kin, bb.base_pos, bb.base_quat, q_hi.copy(), arm, SAWYER['ee'] + 1, mid + np.stack([0 * h0, 0 * h0, h0 - 0.05], axis=1), tq,
+                          bb.arm_lower, bb.arm_upper, iters=200)
+    e_lo = np.maximum(pe, oe)
     for sim in (cpu, dev):
         put(sim, q_hi)
         sim.set_motor(bb.arm_links, 1, target=q_lo[:, arm], kp=[0.1] * 7, kd=[1.0] * 7, max_force=[5.0] * 7)
     dev.state_set(cpu.state_get())
-    return cpu, dev, s, (e_hi, e_lo)
+    return cpu, dev, s, (e_hi, e_lo, q_lo)
 
 
 def _check_wiper_on_arm(bb, make_sim, n):
@@ -91,7 +96,7 @@ def _check_wiper_on_arm(bb, make_sim, n):
             fmax = max(fmax, th_c.max())
             rel = max(rel, (np.abs(th_c - th_d)[big] / th_c[big]).max())
         dq = max(dq, np.abs(cpu.get_joint_states(bb.arm_links)[0] - dev.get_joint_states(bb.arm_links)[0]).max())
-    res = dict(force=fmax, force_rel=rel, dq=dq, wiped_cpu=wiped_c.tolist(), wiped_dev=wiped_d.tolist(), ik=np.round(np.maximum(*ik), 3).tolist())
+    res = dict(force=fmax, force_rel=rel, dq=dq, wiped_cpu=wiped_c.tolist(), wiped_dev=wiped_d.tolist(), ik=np.round(np.maximum(ik[0], ik[1]), 3).tolist())
     print('wiper on arm', res)
     assert fmax > 0.5, res                                      # the case must produce live cloth-on-arm contact
     assert rel < 0.05 and dq < 1e-4, res                        # north-star tolerances: 5 % force, 1e-4 rad
@@ -116,12 +121,62 @@ def _check_env_surface(lib, n):
     env.close()
 
 
+def _check_fused_vs_api(lib, n):
+    """Fused kernels vs the per-call API path from identical resets; a strong arm motor makes the wiper touch the arm."""
+    from assistive_gym_b200 import envs
+    a, b = (envs.make('assistive_gym:BedBathingSawyer-v1', n_envs=n, seed=9) for _ in range(2))
+    a._sim_lib = b._sim_lib = lib
+    oa, ob = np.atleast_2d(a.reset()), np.atleast_2d(b.reset())
+    assert np.allclose(oa, ob, atol=1e-6)
+    rng = np.random.default_rng(2)
+    for k in range(5):
+        act = rng.uniform(-1, 1, size=(n, 7)).astype(np.float32)
+        o1, r1, d1, i1 = a.step(act if n > 1 else act[0])
+        o2, r2, d2, i2 = b.step_reference_api(act)
+        assert np.abs(np.atleast_2d(o1) - np.atleast_2d(o2)).max() < 1e-4, (k, np.abs(np.atleast_2d(o1) - np.atleast_2d(o2)).max(axis=0))
+        assert np.abs(np.atleast_1d(r1) - np.atleast_1d(r2)).max() < 1e-3, (k, r1, r2)
+        assert np.array_equal(np.atleast_1d(i1['task_success']), np.atleast_1d(i2['task_success']))
+    a.close(); b.close()
+
+
+def _check_fused_wiping(bb, make_sim, n):
+    """The pressed-wiper case through the fused kernels (device) against `total_force` on the oracle."""
+    cpu, dev, s, ik = _pressed_pair(bb, make_sim, n, seed=4)
+    tw, alive = bb.targets_world(cpu, s)
+    alive_c = alive.copy()
+    dev.bathing_init(bb.bathing_params(), s['male'], tw, alive)
+    from tests.parity_cases import take_step_targets
+    arm = np.array(SAWYER['arm']) + 1
+    q_lo = ik[2][:, arm]
+    wiped_c = np.zeros(n, int); wiped_d = np.zeros(n, int)
+    for k in range(12):
+        q = cpu.get_joint_states(bb.arm_links)[0]
+        act = np.clip((q_lo - q) / 0.25, -1, 1).astype(np.float32)          # drive towards the pressing pose
+        cpu.set_motor_targets(bb.arm_links, take_step_targets(q, act, bb.arm_lower, bb.arm_upper))
+        cpu.step(5)
+        obs, rew, done, info = dev.bathing_step_host(act)
+        tf, th, tot, new = bb.total_force(cpu, tw, alive_c)
+        wiped_c += new; wiped_d += info[:, 3].astype(int)
+        assert np.abs(info[:, 0] - tot).max() < 0.05 * max(1.0, tot.max()), (k, info[:, 0], tot)
+        assert np.abs(obs[:, 7:14] - ((q_now := cpu.get_joint_states(bb.arm_links)[0]) + np.pi) % (2 * np.pi) + np.pi).max() < 1e-4
+    print('fused wiping', wiped_c.tolist(), wiped_d.tolist())
+    assert wiped_c.sum() > 0 and np.array_equal(wiped_c, wiped_d)
+
+
 def test_wiper_on_arm_cpu_harness(bathing, emu_lib):
     _check_wiper_on_arm(bathing, lambda sc, cfg, n: BatchSim(sc, cfg, n, _lib=emu_lib), 2)
 
 
 def test_env_surface_cpu_harness(emu_lib):
     _check_env_surface(emu_lib, 3)
+
+
+def test_fused_vs_api_cpu_harness(emu_lib):
+    _check_fused_vs_api(emu_lib, 3)
+
+
+def test_fused_wiping_cpu_harness(bathing, emu_lib):
+    _check_fused_wiping(bathing, lambda sc, cfg, n: BatchSim(sc, cfg, n, _lib=emu_lib), 2)
 
 
 @pytest.mark.gpu
@@ -132,3 +187,13 @@ def test_wiper_on_arm_gpu(bathing, gpu_lib):
 @pytest.mark.gpu
 def test_env_surface_gpu(gpu_lib):
     _check_env_surface(None, 16)
+
+
+@pytest.mark.gpu
+def test_fused_vs_api_gpu(gpu_lib):
+    _check_fused_vs_api(None, 16)
+
+
+@pytest.mark.gpu
+def test_fused_wiping_gpu(bathing, gpu_lib):
+    _check_fused_wiping(bathing, lambda sc, cfg, n: BatchSim(sc, cfg, n, device=0), 8)
