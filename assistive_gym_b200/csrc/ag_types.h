@@ -8,12 +8,13 @@
 #include <stdint.h>
 #include <stddef.h>
 
-#define AG_MAXND 16          // max articulated DoFs per env (all articulated bodies together)
+#define AG_MAXND 16          // max DoFs of ONE articulated body (an env may hold several: Jaco 10 + head chains 4 + 4)
 #define AG_MAX_HULL 64       // max core vertices per collider
 #define AG_CF 20             // floats per contact record
 #define AG_CFR 10            // floats per raw (unsorted) contact record: the first 10 fields
 
-// contact record fields (float index within the [AG_CF] record)
+// contact record fields (float index within the [AG_CF] record); the RHS / DINV / MU fields are unused since the
+// solver rows moved to the packed row stream (ag_solver.cuh), the layout is kept for the read-back kernels
 enum {
   CF_PAX = 0, CF_PAY, CF_PAZ, CF_PBX, CF_PBY, CF_PBZ, CF_NX, CF_NY, CF_NZ, CF_DIST,
   CF_RHS_N, CF_DINV_N, CF_RHS_T1, CF_DINV_T1, CF_RHS_T2, CF_DINV_T2, CF_MU, CF_LAM_N, CF_LAM_T1, CF_LAM_T2
@@ -27,7 +28,7 @@ struct SimDev {
   float dt; int iters; float erp, contact_erp, slop, resid_thr, contact_thr, lin_damp, ang_damp, vmax;
   int cone, gyro, maxc;
   // ---- template sizes
-  int nb, nl, nc, npair, ncon, nf, nart, ND, nparts, nmovcol, nmovlink, nalllink, nas /* art-side slots */, ngr /* generic rows */;
+  int nb, nl, nc, npair, ncon, nf, nart, ND, nparts, nmovcol, nmovlink, nalllink, ngr /* fixed-constraint rows = 6 ncon */;
   // ---- template tables (device, read-only)
   const int *body_link0, *body_nlinks, *body_kind, *body_idx;
   const float* body_gravity;

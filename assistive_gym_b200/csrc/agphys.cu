@@ -353,7 +353,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
     for (int c = link_col0[k]; c < link_col0[k] + link_ncol[k]; c++) { allcol.push_back(c); if (mov) movcol.push_back(c); }
   }
   S.nmovcol = (int)movcol.size(); S.nmovlink = (int)movlink.size(); S.nalllink = (int)alllink.size();
-  S.ngr = 6 * S.ncon; S.nas = 0;
+  S.ngr = 6 * S.ncon;
 
   // ---- upload template
   auto f32 = [](const double* p, size_t n) { std::vector<float> v(n); for (size_t i = 0; i < n; i++) v[i] = (float)p[i]; return v; };
