@@ -123,6 +123,9 @@ struct AgSim {
   float *d_action, *d_obs, *d_reward, *d_done, *d_info;
   float *h_pin_in, *h_pin_out;
   int pgs_lanes; bool pgs_generic;
+  // CUDA-graph replay of the fused env step (one graph per entry point, keyed by its device pointers)
+  bool use_graph;
+  struct StepGraph { void* exec; const void* key[5]; uint64_t launches; bool valid; } graphs[2];
   // profiling
   bool profiling;
   std::vector<std::string> knames;
@@ -252,7 +255,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   AgSim* s = new AgSim();
   memset(&s->S, 0, sizeof(SimDev));
   memset(&s->F, 0, sizeof(FeedDev));
-  s->cfg = *cfg; s->device = device; s->launches = 0; s->feeding = false; s->bathing = false; s->B_dev = nullptr; s->stream = nullptr; s->F_dev = nullptr; s->profiling = false;
+  s->cfg = *cfg; s->device = device; s->launches = 0; s->feeding = false; s->bathing = false; s->use_graph = true; s->graphs[0].valid = s->graphs[1].valid = false; s->B_dev = nullptr; s->stream = nullptr; s->F_dev = nullptr; s->profiling = false;
   s->d_stage = nullptr; s->stage_floats = 0;
 #ifndef AG_CPU_EMU
   if (cudaSetDevice(device) != cudaSuccess) { g_err = "cudaSetDevice failed (is a CUDA device present? there is no CPU fallback)"; delete s; return nullptr; }
@@ -454,6 +457,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
     const char* lp = getenv("AG_PGS_LANES");
     s->pgs_lanes = lp ? atoi(lp) : 1;
     { const char* gp = getenv("AG_PGS_GENERIC"); s->pgs_generic = gp && atoi(gp) != 0; }
+    { const char* gg = getenv("AG_GRAPH"); if (gg && atoi(gg) == 0) s->use_graph = false; }
     if (s->pgs_lanes != 1 && s->pgs_lanes != 2 && s->pgs_lanes != 4 && s->pgs_lanes != 8 && s->pgs_lanes != 32) s->pgs_lanes = 1;
     size_t smem = (size_t)rs_lane_floats(S) * s->pgs_lanes * sizeof(float) + 8 * S.rs_nbuf * s->pgs_lanes;
     if (smem > 227 * 1024) { g_err = "PGS shared-memory footprint exceeds 227 KB per CTA: lower max_contacts or AG_PGS_LANES"; ag_destroy(s); return nullptr; }
@@ -489,10 +493,13 @@ void ag_destroy(AgSim* s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   for (void* p : s->allocs) cudaFree(p);
   if (s->feeding) { cudaFreeHost(s->h_pin_in); cudaFreeHost(s->h_pin_out); }
+  if (s->bathing) { cudaFreeHost(s->h_bpin_in); cudaFreeHost(s->h_bpin_out); }
+  for (int g = 0; g < 2; g++) if (s->graphs[g].valid) cudaGraphExecDestroy((cudaGraphExec_t)s->graphs[g].exec);
   if (s->stream) cudaStreamDestroy(s->stream);
 #else
   for (void* p : s->allocs) free(p);
   if (s->feeding) { free(s->h_pin_in); free(s->h_pin_out); }
+  if (s->bathing) { free(s->h_bpin_in); free(s->h_bpin_out); }
 #endif
   delete s;
 }
@@ -825,27 +832,76 @@ int ag_overflow_count(AgSim* s) {
   return n;
 }
 
+// ------------------------------------------------------------------ CUDA-graph replay of a fused env step
+// One env step is ~90 small launches (14 kernels + 3 memsets per substep); captured once per set of device
+// pointers and replayed with a single cudaGraphLaunch.  Falls back to direct launches while profiling
+// (per-kernel events), when AG_GRAPH=0, or if capture fails.
+typedef int (*StepEnqueue)(AgSim*, const float*, float*, float*, float*, float*);
+static void drop_graph(AgSim* s, int which) {
+#ifndef AG_CPU_EMU
+  if (s->graphs[which].valid) { cudaGraphExecDestroy((cudaGraphExec_t)s->graphs[which].exec); s->graphs[which].valid = false; }
+#else
+  (void)s; (void)which;
+#endif
+}
+static int run_step(AgSim* s, int which, StepEnqueue enq, const float* action, float* obs, float* reward, float* done, float* info) {
+#ifndef AG_CPU_EMU
+  if (s->use_graph && !s->profiling) {
+    AgSim::StepGraph& G = s->graphs[which];
+    const void* key[5] = {action, obs, reward, done, info};
+    if (G.valid && memcmp(G.key, key, sizeof(key)) != 0) { cudaGraphExecDestroy((cudaGraphExec_t)G.exec); G.valid = false; }
+    if (!G.valid) {
+      uint64_t l0 = s->launches;
+      cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+      if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        int rc = enq(s, action, obs, reward, done, info);
+        cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
+        if (rc == 0 && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+          G.exec = exec; memcpy(G.key, key, sizeof(key)); G.launches = s->launches - l0; G.valid = true;
+        }
+        if (graph) cudaGraphDestroy(graph);
+      }
+      s->launches = l0;
+      if (!G.valid) { cudaGetLastError(); s->use_graph = false; }
+    }
+    if (G.valid) {
+      CK(cudaGraphLaunch((cudaGraphExec_t)G.exec, s->stream));
+      s->launches += G.launches;
+      return 0;
+    }
+  }
+#else
+  (void)which;
+#endif
+  return enq(s, action, obs, reward, done, info);
+}
+
 // ------------------------------------------------------------------ fused FeedingEnv path
 int ag_feeding_init(AgSim* s, const AgFeedingParams* p, const int32_t* gender_is_male) {
   const int N = s->S.N;
   FeedDev& F = s->F;
   F.P = *p;
   if (p->n_foods > 16) return fail("too many foods");
-  F.male = dalloc<int>(s, N); F.food_state = dalloc<int>(s, N); F.iteration = dalloc<int>(s, N); F.task_success = dalloc<int>(s, N);
-  F.food_near = dalloc<int>(s, (size_t)N * 16);
-  F.action = dalloc<float>(s, (size_t)N * 7); F.rng = dalloc<unsigned long long>(s, N);
-  F.tremor_on = dalloc<int>(s, N); F.tremor_rest = dalloc<float>(s, (size_t)N * 4); F.tremor_amp = dalloc<float>(s, (size_t)N * 4);
-  s->d_action = dalloc<float>(s, (size_t)N * 7); s->d_obs = dalloc<float>(s, (size_t)N * 25);
-  s->d_reward = dalloc<float>(s, N); s->d_done = dalloc<float>(s, N); s->d_info = dalloc<float>(s, (size_t)N * 4);
-  if (!s->d_info) return fail("device allocation failed");
-  if (h2d(s, F.male, gender_is_male, sizeof(int) * N)) return -1;
+  drop_graph(s, 0);           // the captured step refers to the previous FeedDev
+  if (!s->feeding) {          // buffers are allocated once; a later init (episode reset) only refreshes their contents
+    F.male = dalloc<int>(s, N); F.food_state = dalloc<int>(s, N); F.iteration = dalloc<int>(s, N); F.task_success = dalloc<int>(s, N);
+    F.food_near = dalloc<int>(s, (size_t)N * 16);
+    F.action = dalloc<float>(s, (size_t)N * 7); F.rng = dalloc<unsigned long long>(s, N);
+    F.tremor_on = dalloc<int>(s, N); F.tremor_rest = dalloc<float>(s, (size_t)N * 4); F.tremor_amp = dalloc<float>(s, (size_t)N * 4);
+    s->d_action = dalloc<float>(s, (size_t)N * 7); s->d_obs = dalloc<float>(s, (size_t)N * 25);
+    s->d_reward = dalloc<float>(s, N); s->d_done = dalloc<float>(s, N); s->d_info = dalloc<float>(s, (size_t)N * 4);
+    s->F_dev = dalloc<FeedDev>(s, 1);
+    if (!s->d_info || !s->F_dev) return fail("device allocation failed");
 #ifndef AG_CPU_EMU
-  CK(cudaMallocHost((void**)&s->h_pin_in, sizeof(float) * N * 7));
-  CK(cudaMallocHost((void**)&s->h_pin_out, sizeof(float) * N * 31));
+    CK(cudaMallocHost((void**)&s->h_pin_in, sizeof(float) * N * 7));
+    CK(cudaMallocHost((void**)&s->h_pin_out, sizeof(float) * N * 31));
 #else
-  s->h_pin_in = (float*)malloc(sizeof(float) * N * 7); s->h_pin_out = (float*)malloc(sizeof(float) * N * 31);
+    s->h_pin_in = (float*)malloc(sizeof(float) * N * 7); s->h_pin_out = (float*)malloc(sizeof(float) * N * 31);
 #endif
-  s->F_dev = dalloc<FeedDev>(s, 1);
+  } else {
+    if (dev_zero(s, F.tremor_on, sizeof(int) * N) || dev_zero(s, F.rng, sizeof(unsigned long long) * N)) return -1;
+  }
+  if (h2d(s, F.male, gender_is_male, sizeof(int) * N)) return -1;
   if (!s->F_dev || h2d(s, s->F_dev, &s->F, sizeof(FeedDev))) return fail("FeedDev upload failed");
   s->feeding = true;
   return ag_feeding_reset_episode(s, nullptr);
@@ -898,7 +954,7 @@ static int feeding_step_enqueue(AgSim* s, const float* action_dev, float* obs, f
 }
 int ag_feeding_step_dev(AgSim* s, const float* action_dev, float* obs_dev, float* reward_dev, float* done_dev, float* info_dev) {
   if (!s->feeding) return fail("ag_feeding_init not called");
-  int rc = feeding_step_enqueue(s, action_dev, obs_dev, reward_dev, done_dev, info_dev);
+  int rc = run_step(s, 0, feeding_step_enqueue, action_dev, obs_dev, reward_dev, done_dev, info_dev);
 #ifndef AG_CPU_EMU
   CK(cudaGetLastError());
 #endif
@@ -913,7 +969,7 @@ int ag_feeding_step_host(AgSim* s, const float* action, float* obs, float* rewar
 #else
   memcpy(s->d_action, s->h_pin_in, sizeof(float) * N * 7);
 #endif
-  if (feeding_step_enqueue(s, s->d_action, s->d_obs, s->d_reward, s->d_done, s->d_info)) return -1;
+  if (run_step(s, 0, feeding_step_enqueue, s->d_action, s->d_obs, s->d_reward, s->d_done, s->d_info)) return -1;
 #ifndef AG_CPU_EMU
   CK(cudaMemcpyAsync(s->h_pin_out, s->d_obs, sizeof(float) * N * 25, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaMemcpyAsync(s->h_pin_out + (size_t)N * 25, s->d_reward, sizeof(float) * N, cudaMemcpyDeviceToHost, s->stream));
@@ -937,6 +993,7 @@ int ag_bathing_init(AgSim* s, const AgBathingParams* p, const int32_t* gender_is
   const int N = s->S.N;
   BathDev& B = s->B;
   B.P = *p;
+  drop_graph(s, 1);
   const int T = p->n_targets_max;
   if (T <= 0 || T > 4096) return fail("bad target count");
   for (int j = 0; j < 7; j++) if (p->arm_links[j] < 0 || p->arm_links[j] >= s->nl) return fail("bad link");
@@ -991,7 +1048,7 @@ static int bathing_step_enqueue(AgSim* s, const float* action_dev, float* obs, f
 }
 int ag_bathing_step_dev(AgSim* s, const float* action_dev, float* obs_dev, float* reward_dev, float* done_dev, float* info_dev) {
   if (!s->bathing) return fail("ag_bathing_init not called");
-  int rc = bathing_step_enqueue(s, action_dev, obs_dev, reward_dev, done_dev, info_dev);
+  int rc = run_step(s, 1, bathing_step_enqueue, action_dev, obs_dev, reward_dev, done_dev, info_dev);
 #ifndef AG_CPU_EMU
   CK(cudaGetLastError());
 #endif
@@ -1006,7 +1063,7 @@ int ag_bathing_step_host(AgSim* s, const float* action, float* obs, float* rewar
 #else
   memcpy(s->d_baction, s->h_bpin_in, sizeof(float) * N * 7);
 #endif
-  if (bathing_step_enqueue(s, s->d_baction, s->d_bobs, s->d_breward, s->d_bdone, s->d_binfo)) return -1;
+  if (run_step(s, 1, bathing_step_enqueue, s->d_baction, s->d_bobs, s->d_breward, s->d_bdone, s->d_binfo)) return -1;
 #ifndef AG_CPU_EMU
   CK(cudaMemcpyAsync(s->h_bpin_out, s->d_bobs, sizeof(float) * N * 24, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaMemcpyAsync(s->h_bpin_out + (size_t)N * 24, s->d_breward, sizeof(float) * N, cudaMemcpyDeviceToHost, s->stream));
