@@ -67,17 +67,6 @@ __global__ void __launch_bounds__(LANES) k_pgs(SimDev S, KP p) {
   const unsigned base = (unsigned)__cvta_generic_to_shared(pgs_smem);
   if (tid < p.n) pgs_body(tid, S, p, pgs_smem + threadIdx.x * stride, base + threadIdx.x * stride * 4, base + LANES * stride * 4 + 8 * S.rs_nbuf * threadIdx.x);
 }
-// experiment (AG_PGS_GENERIC=1): same body, but the lane's shared-memory pointer is laundered so the compiler
-// addresses it as a generic pointer (LD/ST) instead of re-deriving the shared-window address per record (S2R)
-__global__ void __launch_bounds__(1) k_pgs_generic(SimDev S, KP p) {
-  extern __shared__ __align__(128) float pgs_smem[];
-  const int stride = p.i0;
-  int tid = blockIdx.x;
-  const unsigned base = (unsigned)__cvta_generic_to_shared(pgs_smem);
-  float* sm = pgs_smem;
-  asm volatile("" : "+l"(sm));
-  if (tid < p.n) pgs_body(tid, S, p, sm, base, base + stride * 4);
-}
 #else
 static void k_pgs(SimDev S, KP p) {
   std::vector<float> buf((size_t)rs_lane_floats(S) + 8);
@@ -122,7 +111,7 @@ struct AgSim {
   float *h_bpin_in, *h_bpin_out, *d_baction, *d_bobs, *d_breward, *d_bdone, *d_binfo;
   float *d_action, *d_obs, *d_reward, *d_done, *d_info;
   float *h_pin_in, *h_pin_out;
-  int pgs_lanes; bool pgs_generic;
+  int pgs_lanes;
   // CUDA-graph replay of the fused env step (one graph per entry point, keyed by its device pointers)
   bool use_graph;
   struct StepGraph { void* exec; const void* key[5]; uint64_t launches; bool valid; } graphs[2];
@@ -456,15 +445,13 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
     // shorten the per-warp iteration count (max over fewer envs) and reduce divergence.
     const char* lp = getenv("AG_PGS_LANES");
     s->pgs_lanes = lp ? atoi(lp) : 1;
-    { const char* gp = getenv("AG_PGS_GENERIC"); s->pgs_generic = gp && atoi(gp) != 0; }
     { const char* gg = getenv("AG_GRAPH"); if (gg && atoi(gg) == 0) s->use_graph = false; }
     if (s->pgs_lanes != 1 && s->pgs_lanes != 2 && s->pgs_lanes != 4 && s->pgs_lanes != 8 && s->pgs_lanes != 32) s->pgs_lanes = 1;
     size_t smem = (size_t)rs_lane_floats(S) * s->pgs_lanes * sizeof(float) + 8 * S.rs_nbuf * s->pgs_lanes;
     if (smem > 227 * 1024) { g_err = "PGS shared-memory footprint exceeds 227 KB per CTA: lower max_contacts or AG_PGS_LANES"; ag_destroy(s); return nullptr; }
     cudaError_t ce = cudaSuccess;
     switch (s->pgs_lanes) {
-      case 1: ce = cudaFuncSetAttribute(k_pgs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-              if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_pgs_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
+      case 1: ce = cudaFuncSetAttribute(k_pgs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
       case 2: ce = cudaFuncSetAttribute(k_pgs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
       case 4: ce = cudaFuncSetAttribute(k_pgs<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
       case 8: ce = cudaFuncSetAttribute(k_pgs<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
@@ -686,7 +673,7 @@ static void substep(AgSim* s) {
     if (ps >= 0) prof_mark(s, ps, true);
     dim3 grid((N + L - 1) / L);
     switch (L) {
-      case 1: if (s->pgs_generic) k_pgs_generic<<<grid, 1, smem, s->stream>>>(S, kp); else k_pgs<1><<<grid, 1, smem, s->stream>>>(S, kp); break;
+      case 1: k_pgs<1><<<grid, 1, smem, s->stream>>>(S, kp); break;
       case 2: k_pgs<2><<<grid, 2, smem, s->stream>>>(S, kp); break;
       case 4: k_pgs<4><<<grid, 4, smem, s->stream>>>(S, kp); break;
       case 8: k_pgs<8><<<grid, 8, smem, s->stream>>>(S, kp); break;

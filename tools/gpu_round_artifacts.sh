@@ -5,9 +5,6 @@ TAG=${1:-rXX}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -3 > gpurun_out/gpu_tests_$TAG.log; cat gpurun_out/gpu_tests_$TAG.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-AG_PGS_GENERIC=1 python bench.py --steps 10 --warmup 3 2>&1 | grep "^{" | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('generic-pointer PGS variant', round(d['value']), round(d['roofline']['per_kernel_ms_per_step']['k_pgs'],2))"
 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_$TAG.log 2>&1
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_l.log 2>&1
