@@ -224,12 +224,23 @@ class FeedingBatch:
         # (ik_random_restarts collision_objects, robot.py:107-112; env.py:300-309)
         obstacles = [self.humans['male'], self.humans['female'], self.table, self.wheelchair]
         self.ik_resamples = 0
-        for attempt in range(8):
+        bpn, bqn = np.broadcast_to(self.robot_base_pos, (n, 3)), np.broadcast_to(self.robot_base_quat, (n, 4))
+        zero3 = np.zeros((n, 3))
+        for attempt in range(30):       # the reference keeps drawing restarts (up to 1000) until the pose is collision-free
             arm_q = qik[:, np.array(JACO['arm']) + 1]
             sim.set_joint_state(self.arm_links, q=arm_q, qd=np.zeros_like(arm_q))
+            # the spoon rides on the gripper: its start pose is part of the collision test (env.py:300-305, tools=[self.tool])
+            qfull = qik.copy()
+            qfull[:, np.array(JACO['gripper']) + 1] = JACO['gripper_pos']
+            pos, quat = self.kin.fk(bpn, bqn, qfull)
+            cp, cq = self.kin.link_com_pose(pos, quat, JACO['tool_joint'] + 1)
+            sim.set_base_pose(self.tool, cp + q_rot(cq, self.tool_pos_offset), q_mul(cq, np.broadcast_to(self.tool_quat_offset, (n, 4))))
+            sim.set_base_velocity(self.tool, zero3, zero3)
+            sim.forward_kinematics()
             hit = np.zeros(n, dtype=bool)
             for ob in obstacles:
                 hit |= sim.closest_points(self.robot, ob, 0.0, max_pts=1)[1] > 0
+                hit |= sim.closest_points(self.tool, ob, 0.0, max_pts=1)[1] > 0
             idx = np.nonzero(hit)[0]
             if len(idx) == 0:
                 break
