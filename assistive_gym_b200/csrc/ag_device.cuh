@@ -509,6 +509,7 @@ AG_HDN inline void narrow_body(int tid, const SimDev& S, const KP&) {
   }
 }
 
+AG_HD void contact_refs(const SimDev& S, int e, unsigned key, int& refA, int& refB);   // ag_solver.cuh
 // K4: deterministic order: rank each contact by its key.  thread = (slot, env).
 AG_HDN inline void sort_body(int tid, const SimDev& S, const KP&) {
   const int N = S.N;
@@ -524,6 +525,7 @@ AG_HDN inline void sort_body(int tid, const SimDev& S, const KP&) {
   for (int j = 0; j < n; j++) rank += (S.c_key[(size_t)j * N + e] < key) ? 1 : 0;
   if (rank >= S.maxc) return;
   S.s_key[(size_t)rank * N + e] = key;
+  { int ra, rb2; contact_refs(S, e, key, ra, rb2); S.s_ref[(size_t)rank * 4 * N + e] = ra; S.s_ref[((size_t)rank * 4 + 1) * N + e] = rb2; }
   for (int f = 0; f <= CF_DIST; f++) cf_st(S.s_data, rank, f, N, e, S.c_data[((size_t)slot * AG_CFR + f) * N + e]);
 }
 

@@ -193,6 +193,15 @@ AG_HD bool con_sides(const SimDev& S, int e, int c, int& refA, int& refB, bool& 
   return ((refA | refB) & 3) != 0;
 }
 
+// Sides of contact `key` in record order; called by K4 for every sorted contact (one thread each) so that K6a's
+// sequential pass only reads two ints per contact.
+AG_HD void contact_refs(const SimDev& S, int e, unsigned key, int& refA, int& refB) {
+  unsigned pairk = key >> 2;
+  int ca = (int)(pairk / (unsigned)S.nc), cb = (int)(pairk % (unsigned)S.nc);
+  refA = link_ref(S, e, AG_LDG(S.col_link + ca)); refB = link_ref(S, e, AG_LDG(S.col_link + cb));
+  if (rs_swap_sides(refA, refB)) { int t = refA; refA = refB; refB = t | (1 << 30); }   // bit 30 of refB: sides were swapped
+}
+
 // K6a: one lane per env: the slot layout of this substep's row stream in solver order -- joint-limit rows,
 // motor rows, fixed-constraint rows, contact normal rows (contact order), friction pairs (contact order).
 // Cheap and sequential; the records themselves are written by K6b with one thread per row.
@@ -231,14 +240,7 @@ AG_HDN inline void rows_body(int e, const SimDev& S, const KP&) {
     for (int s = 0; s < cnt; s++) {
       size_t rb = (size_t)s * 4 * N + e;
       int refA, refB;
-      if (pass == 0) {
-        unsigned pairk = S.s_key[(size_t)s * N + e] >> 2;
-        int ca = (int)(pairk / (unsigned)S.nc), cb = (int)(pairk % (unsigned)S.nc);
-        refA = link_ref(S, e, AG_LDG(S.col_link + ca)); refB = link_ref(S, e, AG_LDG(S.col_link + cb));
-        if (rs_swap_sides(refA, refB)) { int t = refA; refA = refB; refB = t | (1 << 30); }   // bit 30 of refB: sides were swapped
-        S.s_ref[rb] = refA; S.s_ref[rb + N] = refB;
-        refB &= ~(1 << 30);
-      } else { refA = S.s_ref[rb]; refB = S.s_ref[rb + N] & ~(1 << 30); }
+      refA = S.s_ref[rb]; refB = S.s_ref[rb + N] & ~(1 << 30);     // written by K4 (contact_refs), bit 30 = sides swapped
       int offA, nA, offB, nB, ns = 0;
       side_dims(S, refA, offA, nA); side_dims(S, refB, offB, nB);
       int o = -1;
