@@ -65,7 +65,12 @@ __global__ void __launch_bounds__(LANES) k_pgs(SimDev S, KP p) {
   const int stride = p.i0;                           // rs_lane_floats(S)
   int tid = blockIdx.x * LANES + threadIdx.x;
   const unsigned base = (unsigned)__cvta_generic_to_shared(pgs_smem);
-  if (tid < p.n) pgs_body(tid, S, p, pgs_smem + threadIdx.x * stride, base + threadIdx.x * stride * 4, base + LANES * stride * 4 + 8 * S.rs_nbuf * threadIdx.x);
+  // The lane's pointer is made opaque and re-declared as shared: ptxas then keeps ONE converted shared address in a
+  // register instead of re-materialising the `pgs_smem` symbol (S2R SR_CgaCtaId + 2 LEA) in front of every record.
+  float* sm = pgs_smem + threadIdx.x * stride;
+  asm volatile("" : "+l"(sm));
+  __builtin_assume(__isShared(sm));
+  if (tid < p.n) pgs_body(tid, S, p, sm, base + threadIdx.x * stride * 4, base + LANES * stride * 4 + 8 * S.rs_nbuf * threadIdx.x);
 }
 #else
 static void k_pgs(SimDev S, KP p) {
