@@ -1,0 +1,74 @@
+"""`AssistiveVecEnv` — the batched env as a learner sees it (SURVEY.md §8(b) "fused vector path", §8(f)2).
+
+The reference trains one `gym.Env` per RLlib worker process (`learn.py:26,61-69`); here ONE object steps
+`n_envs` environments on one GPU.  `step(actions)` takes and returns torch CUDA tensors: the action tensor's
+`data_ptr()` goes straight into `ag_feeding_step_dev` / `ag_bathing_step_dev`, observations / rewards / dones are
+written into pre-allocated device tensors on the simulation's own stream, and nothing crosses PCIe.  Episodes of
+all envs have the same length (200 steps, feeding.py:37), so the batch resets together; `auto_reset` does it inside
+`step` the way vector-env wrappers do (the terminal observation is kept in `info['terminal_observation']`).
+With numpy inputs the host-buffer entry points are used instead (pinned staging inside the C ABI)."""
+import numpy as np
+
+
+class AssistiveVecEnv:
+    def __init__(self, env_id='assistive_gym:FeedingJaco-v1', n_envs=4096, device=0, seed=1001, auto_reset=True, config=None, _lib=None):
+        from . import envs
+        self.env = envs.make(env_id, n_envs=n_envs, device=device, seed=seed, config=config)
+        if _lib is not None:
+            self.env._sim_lib = _lib
+        self.n_envs, self.device, self.auto_reset = n_envs, device, auto_reset
+        self.task = self.env.task
+        self.observation_space, self.action_space = self.env.observation_space, self.env.action_space
+        self.obs_dim, self.act_dim = self.observation_space.shape[0], self.action_space.shape[0]
+        self._step_dev = None
+        self._buf = None
+
+    # ------------------------------------------------------------------ gym-style API
+    def reset(self):
+        obs = np.atleast_2d(self.env.reset())
+        sim = self.env.id
+        self._step_dev = sim.feeding_step_dev if self.task == 'feeding' else sim.bathing_step_dev
+        self._step_host = sim.feeding_step_host if self.task == 'feeding' else sim.bathing_step_host
+        self._t = 0
+        return obs
+
+    def _tensors(self, like):
+        import torch
+        if self._buf is None or self._buf[0].device != like.device:
+            n = self.n_envs
+            mk = lambda *shape: torch.zeros(shape, device=like.device, dtype=torch.float32)
+            self._buf = (mk(n, self.obs_dim), mk(n), mk(n), mk(n, 4))
+            self._stream = torch.cuda.ExternalStream(self.env.id.stream_ptr(), device=like.device)
+        return self._buf
+
+    def step(self, actions):
+        """actions: torch CUDA tensor [n_envs, act_dim] (float32, contiguous) -> device tensors, or numpy -> numpy."""
+        if self._step_dev is None:
+            raise RuntimeError('call reset() first')
+        is_torch = hasattr(actions, 'data_ptr')
+        if is_torch:
+            import torch
+            a = actions.to(dtype=torch.float32).contiguous()
+            obs, rew, done, info = self._tensors(a)
+            # the caller's stream produced `a`; the simulation runs on its own stream
+            self._stream.wait_stream(torch.cuda.current_stream(a.device))
+            self._step_dev(a.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), info.data_ptr())
+            torch.cuda.current_stream(a.device).wait_stream(self._stream)
+            out = (obs, rew, done > 0.5, {'total_force_on_human': info[:, 0], 'task_success': info[:, 1]})
+            finished = None     # decided from the step counter: no device read-back
+        else:
+            obs, rew, done, info = self._step_host(np.asarray(actions, dtype=np.float32).reshape(self.n_envs, -1))
+            out = (obs, rew, done > 0.5, {'total_force_on_human': info[:, 0], 'task_success': info[:, 1]})
+        self._t += 1
+        self.env.iteration = self._t
+        if self.auto_reset and self._t >= 200:
+            term = out[0].clone() if is_torch else out[0].copy()
+            new_obs = self.reset()
+            if is_torch:
+                import torch
+                new_obs = torch.as_tensor(new_obs, device=out[0].device, dtype=torch.float32)
+            out = (new_obs, out[1], out[2], dict(out[3], terminal_observation=term))
+        return out
+
+    def close(self):
+        self.env.close()

@@ -1,0 +1,47 @@
+"""`AssistiveVecEnv` (SURVEY.md §8(b) fused vector path): host path on the CPU harness, device-tensor path on the GPU."""
+import numpy as np
+import pytest
+
+from assistive_gym_b200.vec_env import AssistiveVecEnv
+
+
+def _check_host_path(lib, env_id, obs_dim):
+    v = AssistiveVecEnv(env_id, n_envs=3, seed=11, _lib=lib)
+    obs = v.reset()
+    assert obs.shape == (3, obs_dim)
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        o, r, d, info = v.step(rng.uniform(-1, 1, size=(3, 7)).astype(np.float32))
+        assert o.shape == (3, obs_dim) and r.shape == (3,) and d.dtype == bool and not d.any()
+        assert np.all(np.isfinite(o)) and np.all(np.isfinite(r))
+    # episode end: all envs finish together after 200 steps and the batch resets inside step()
+    v._t = 199
+    o, r, d, info = v.step(np.zeros((3, 7), dtype=np.float32))
+    assert 'terminal_observation' in info and v._t == 0 and o.shape == (3, obs_dim)
+    v.close()
+
+
+def test_vec_env_host_path_feeding(emu_lib):
+    _check_host_path(emu_lib, 'assistive_gym:FeedingJaco-v1', 25)
+
+
+def test_vec_env_host_path_bed_bathing(emu_lib):
+    _check_host_path(emu_lib, 'assistive_gym:BedBathingSawyer-v1', 24)
+
+
+@pytest.mark.gpu
+def test_vec_env_device_tensors(gpu_lib):
+    import torch
+    v = AssistiveVecEnv('assistive_gym:FeedingJaco-v1', n_envs=64, seed=3)
+    obs0 = v.reset()
+    g = torch.Generator(device='cuda').manual_seed(0)
+    host = AssistiveVecEnv('assistive_gym:FeedingJaco-v1', n_envs=64, seed=3)
+    host.reset()
+    for _ in range(3):
+        a = torch.rand((64, 7), generator=g, device='cuda') * 2 - 1
+        o, r, d, info = v.step(a)
+        assert o.is_cuda and o.shape == (64, 25) and r.shape == (64,)
+        oh, rh, dh, ih = host.step(a.cpu().numpy())
+        torch.cuda.synchronize()
+        assert np.array_equal(o.cpu().numpy(), oh) and np.array_equal(r.cpu().numpy(), rh)     # same kernels, same bits
+    v.close(); host.close()
