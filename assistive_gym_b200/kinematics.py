@@ -22,10 +22,20 @@ def q_conj(q):
     return q * np.array([-1.0, -1.0, -1.0, 1.0])
 
 
+def _cross(a, b):
+    """np.cross for [..., 3] operands without its axis shuffling (the IK loop calls this ~10^4 times per reset)."""
+    a, b = np.broadcast_arrays(a, b)
+    out = np.empty(a.shape, dtype=np.result_type(a, b))
+    out[..., 0] = a[..., 1] * b[..., 2] - a[..., 2] * b[..., 1]
+    out[..., 1] = a[..., 2] * b[..., 0] - a[..., 0] * b[..., 2]
+    out[..., 2] = a[..., 0] * b[..., 1] - a[..., 1] * b[..., 0]
+    return out
+
+
 def q_rot(q, v):
     u = q[..., :3]
-    t = 2.0 * np.cross(u, v)
-    return v + q[..., 3:4] * t + np.cross(u, t)
+    t = 2.0 * _cross(u, v)
+    return v + q[..., 3:4] * t + _cross(u, t)
 
 
 def q_axis(axis, ang):
@@ -58,14 +68,15 @@ class BodyKinematics:
         self.lower = scene['link_lower'][sl]
         self.upper = scene['link_upper'][sl]
 
-    def fk(self, base_pos, base_quat, q):
-        """q: [N, nl] joint values indexed by local link (column 0 unused).  Returns pos [N,nl,3], quat [N,nl,4]."""
+    def fk(self, base_pos, base_quat, q, upto=None):
+        """q: [N, nl] joint values indexed by local link (column 0 unused).  Returns pos [N,nl,3], quat [N,nl,4].
+        `upto`: only links 0..upto are computed (links are in DFS pre-order, so a link's ancestors precede it)."""
         N = q.shape[0]
         pos = np.zeros((N, self.nl, 3))
         quat = np.zeros((N, self.nl, 4))
         pos[:, 0] = base_pos
         quat[:, 0] = base_quat
-        for k in range(1, self.nl):
+        for k in range(1, self.nl if upto is None else upto + 1):
             p = self.parent[k]
             jp = pos[:, p] + q_rot(quat[:, p], self.jpos[k])
             jq = q_mul(quat[:, p], np.broadcast_to(self.jquat[k], (N, 4)))
@@ -94,7 +105,7 @@ class BodyKinematics:
                 continue
             a = q_rot(quat[:, jl], self.axis[jl])
             if self.jtype[jl] == 1:
-                J[:, :3, c] = np.cross(a, point - pos[:, jl])
+                J[:, :3, c] = _cross(a, point - pos[:, jl])
                 J[:, 3:, c] = a
             elif self.jtype[jl] == 2:
                 J[:, :3, c] = a
@@ -102,24 +113,31 @@ class BodyKinematics:
 
 
 def ik_dls(kin, base_pos, base_quat, q_init, joints, ee, target_pos, target_quat, lower, upper,
-           iters=200, damping=0.05, step_clip=0.2):
-    """Damped least squares IK for link `ee` (link frame).  q_init [N, nl]; returns q [N, nl], pos_err, ori_err."""
+           iters=200, damping=0.05, step_clip=0.2, tol=1e-5):
+    """Damped least squares IK for link `ee` (link frame).  q_init [N, nl]; returns q [N, nl], pos_err, ori_err.
+    Envs whose 6-D error has dropped below `tol` leave the active set, so late iterations only touch stragglers."""
     q = q_init.copy()
-    N = q.shape[0]
-    lam2 = damping ** 2
+    lam2I = damping ** 2 * np.eye(6)
+    base_pos, base_quat = np.broadcast_to(base_pos, (q.shape[0], 3)), np.broadcast_to(base_quat, (q.shape[0], 4))
+    act = np.arange(q.shape[0])
     for _ in range(iters):
-        pos, quat = kin.fk(base_pos, base_quat, q)
-        ep = target_pos - pos[:, ee]
-        qe = q_mul(target_quat, q_conj(quat[:, ee]))
+        qa = q[act]
+        pos, quat = kin.fk(base_pos[act], base_quat[act], qa, upto=ee)
+        ep = target_pos[act] - pos[:, ee]
+        qe = q_mul(target_quat[act], q_conj(quat[:, ee]))
         qe = qe * np.where(qe[:, 3:4] < 0, -1.0, 1.0)
-        eo = 2.0 * qe[:, :3]
-        err = np.concatenate([ep, eo], axis=1)
+        err = np.concatenate([ep, 2.0 * qe[:, :3]], axis=1)
+        live = np.abs(err).max(axis=1) > tol
+        if not live.any():
+            break
+        if not live.all():
+            act, qa, pos, quat, err = act[live], qa[live], pos[live], quat[live], err[live]
         J = kin.jacobian(pos, quat, ee, pos[:, ee], joints)
-        JJt = J @ np.transpose(J, (0, 2, 1)) + lam2 * np.eye(6)
-        dq = np.einsum('nij,nj->ni', np.transpose(J, (0, 2, 1)), np.linalg.solve(JJt, err[..., None])[..., 0])
-        dq = np.clip(dq, -step_clip, step_clip)
-        q[:, joints] = np.clip(q[:, joints] + dq, lower, upper)
-    pos, quat = kin.fk(base_pos, base_quat, q)
+        Jt = np.transpose(J, (0, 2, 1))
+        dq = np.einsum('nij,nj->ni', Jt, np.linalg.solve(J @ Jt + lam2I, err[..., None])[..., 0])
+        qa[:, joints] = np.clip(qa[:, joints] + np.clip(dq, -step_clip, step_clip), lower, upper)
+        q[act] = qa
+    pos, quat = kin.fk(base_pos, base_quat, q, upto=ee)
     pe = np.linalg.norm(target_pos - pos[:, ee], axis=1)
     oe = np.minimum(np.linalg.norm(target_quat - quat[:, ee], axis=1), np.linalg.norm(target_quat + quat[:, ee], axis=1))
     return q, pe, oe
