@@ -495,13 +495,17 @@ AG_HDN inline void pgs_body(int slot, const SimDev& S, const KP&, float* sm, rs_
       if ((pend >> b) & 1u) { rs_wait(bar0 + 8 * b, (phase >> b) & 1u); phase ^= 1u << b; pend &= ~(1u << b); }
       const float* cb = buf + b * RS_CHUNK * RS_SLOT;
       int ns = total - k * RS_CHUNK; if (ns > RS_CHUNK) ns = RS_CHUNK;
+      v4 hnext = ldv4(cb);                        // header of the chunk's first record
       for (int sl = 0; sl < ns;) {
         const float* r = cb + sl * RS_SLOT;
-        // the whole slot in one round of vector loads; decode afterwards
-        const v4 h = ldv4(r), c = ldv4(r + 4), q2 = ldv4(r + 8), q3 = ldv4(r + 12), q4v = ldv4(r + 16), q5 = ldv4(r + 20), q6 = ldv4(r + 24), q7 = ldv4(r + 28);
+        // the header was loaded while the previous record was being solved; the rest of the slot comes in one round
+        // of vector loads and is consumed from registers
+        const v4 h = hnext;
+        const v4 c = ldv4(r + 4), q2 = ldv4(r + 8), q3 = ldv4(r + 12), q4v = ldv4(r + 16), q5 = ldv4(r + 20), q6 = ldv4(r + 24), q7 = ldv4(r + 28);
         const int hk = f2i_bits(h.x);
         const int code = hk & 15;
         sl += (hk >> 4) > 0 ? (hk >> 4) : 1;
+        if (code >= 2 && sl < ns) hnext = ldv4(cb + sl * RS_SLOT);      // (the F-run loops below fetch their own successors)
         const int wa = f2i_bits(h.y), li = f2i_bits(h.w);
         const int offA = wa & 0xffff;
         if (code < 2) {
@@ -523,7 +527,7 @@ AG_HDN inline void pgs_body(int slot, const SimDev& S, const KP&, float* sm, rs_
               lam[lic] = sum;
               a0.x += m0.x * dl; a0.y += m0.y * dl; a0.z += m0.z * dl; a0.w += m0.w * dl; a1.x += m1.x * dl; a1.y += m1.y * dl;
               resid = fmaxf(resid, dl * dl);
-              if (!more || f2i_bits(hn.x) != (RK_ROW_F | (1 << 4)) || (f2i_bits(hn.y) & 0xffff) != curA) break;
+              if (!more || f2i_bits(hn.x) != (RK_ROW_F | (1 << 4)) || (f2i_bits(hn.y) & 0xffff) != curA) { hnext = hn; break; }
               sl += 1; cc = cn; j0 = j0n; j1 = j1n; m0 = m0n; m1 = m1n; lic = f2i_bits(hn.w);
             }
           } else {                                          // RK_FRIC_F
@@ -548,7 +552,7 @@ AG_HDN inline void pgs_body(int slot, const SimDev& S, const KP&, float* sm, rs_
                 a1.x += p6.x * d1 + p7.z * d2; a1.y += p6.y * d1 + p7.w * d2;
                 resid = fmaxf(resid, fmaxf(d1 * d1, d2 * d2));
               }
-              if (!more || f2i_bits(hn.x) != (RK_FRIC_F | (1 << 4)) || (f2i_bits(hn.y) & 0xffff) != curA) break;
+              if (!more || f2i_bits(hn.x) != (RK_FRIC_F | (1 << 4)) || (f2i_bits(hn.y) & 0xffff) != curA) { hnext = hn; break; }
               sl += 1; hh = hn; cc = cn; p2 = n2; p3 = n3; p4 = n4; p5 = n5; p6 = n6; p7 = n7;
             }
           }
