@@ -167,11 +167,19 @@ class BedBathingBatch:
             out[g] = (links, q)
         return out
 
-    def solve_ik(self, base_pos, base_quat, target_pos, rng, max_restarts=8, threshold=0.03):
+    def solve_ik(self, base_pos, base_quat, target_pos, rng, max_restarts=8, threshold=0.03, sim=None, idx=None):
         """IK of the 7 arm joints to the start pose for every env from its own base pose (robot.py:84-121, threshold
-        0.03 as position_robot_toc asks)."""
+        0.03 as position_robot_toc asks).  With a `sim` that offers `ik_solve` the solve runs on the device for the envs
+        `idx` (their base poses must already be set in the sim; arrays are the rows of `idx`)."""
         n = len(target_pos)
         kin = self.kin
+        if sim is not None and hasattr(sim, 'ik_solve'):
+            mask = np.zeros(sim.n, dtype=np.int32); mask[idx] = 1
+            tp = np.zeros((sim.n, 3)); tp[idx] = target_pos
+            q7, err = sim.ik_solve(self.arm_links, self.ee_link, tp, q_from_rpy(SAWYER['ee_orient_rpy']), max_restarts=max_restarts, iters=100,
+                                   threshold=threshold, seed=int(rng.integers(1, 2 ** 31 - 1)), mask=mask)
+            q = np.zeros((n, kin.nl)); q[:, np.array(SAWYER['arm']) + 1] = q7[idx]
+            return q, err[idx].astype(np.float64)
         tq = np.broadcast_to(q_from_rpy(SAWYER['ee_orient_rpy']), (n, 4)).copy()
         joints = np.array(SAWYER['arm']) + 1
         lo, hi = self.arm_lower, self.arm_upper
@@ -249,8 +257,10 @@ class BedBathingBatch:
                 yaw = np.deg2rad(rng.uniform(-30, 30, size=m))
                 bp = np.array([-0.85, -0.4, 0]) + np.array(SAWYER['toc_base_pos_offset']) + rp
                 bq = np.stack([np.zeros(m), np.zeros(m), np.sin(yaw / 2), np.cos(yaw / 2)], axis=1)
-                q, err = self.solve_ik(bp, bq, target[todo], rng)
-                base_pos[todo], base_quat[todo], qik[todo], ik_err[todo] = bp, bq, q, err
+                base_pos[todo], base_quat[todo] = bp, bq
+                sim.set_base_pose(self.robot, base_pos, base_quat)
+                q, err = self.solve_ik(bp, bq, target[todo], rng, sim=sim, idx=todo)
+                qik[todo], ik_err[todo] = q, err
             # collision test of robot + tool against person and bed at this pose (env.py:300-309)
             sim.set_base_pose(self.robot, base_pos, base_quat)
             arm_q = qik[:, np.array(SAWYER['arm']) + 1]

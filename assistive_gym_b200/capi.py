@@ -130,6 +130,7 @@ def load_library(path=None):
     lib.ag_bathing_init.argtypes = [vp, C.POINTER(AgBathingParams), vp, vp, vp]
     lib.ag_bathing_step_dev.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.ag_bathing_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.ag_ik_solve.argtypes = [vp, ci, vp, ci, vp, vp, ci, ci, C.c_float, C.c_uint64, vp, vp, vp]
     lib.ag_state_size.restype = C.c_size_t
     lib.ag_state_size.argtypes = [vp]
     lib.ag_state_get.argtypes = [vp, vp]
@@ -152,7 +153,7 @@ EXPORTED_SYMBOLS = [
     'ag_set_base_pose', 'ag_set_base_velocity', 'ag_set_joint_state', 'ag_set_link_friction',
     'ag_set_body_active', 'ag_forward_kinematics', 'ag_set_motor_host', 'ag_set_motor_targets_dev', 'ag_set_motor_targets_host',
     'ag_step', 'ag_get_joint_states', 'ag_get_link_states', 'ag_get_contacts', 'ag_contact_force_sum',
-    'ag_closest_points', 'ag_feeding_init', 'ag_feeding_reset_episode', 'ag_feeding_set_tremor', 'ag_set_hard_limits', 'ag_feeding_step_dev', 'ag_bathing_init', 'ag_bathing_step_dev', 'ag_bathing_step_host',
+    'ag_closest_points', 'ag_feeding_init', 'ag_feeding_reset_episode', 'ag_feeding_set_tremor', 'ag_set_hard_limits', 'ag_feeding_step_dev', 'ag_ik_solve', 'ag_bathing_init', 'ag_bathing_step_dev', 'ag_bathing_step_host',
     'ag_feeding_step_host', 'ag_state_size', 'ag_state_get', 'ag_state_set', 'ag_kernel_launches',
     'ag_overflow_count', 'ag_get_solver_stats', 'ag_get_pgs_cycles', 'ag_profile_enable', 'ag_profile_get',
 ]

@@ -13,6 +13,7 @@
 #include "ag_solver.cuh"
 #include "ag_feeding.cuh"
 #include "ag_bathing.cuh"
+#include "ag_ik.cuh"
 
 #ifndef AG_CPU_EMU
 #include <cuda_runtime.h>
@@ -91,6 +92,7 @@ AG_KERNEL(k_closest, closest_body)
 AG_KERNEL(k_feed_pre, feeding_pre_body)
 AG_KERNEL(k_feed_food, feeding_food_body)
 AG_KERNEL(k_feed_post, feeding_post_body)
+AG_KERNEL(k_ik, ik_body)
 AG_KERNEL(k_bath_pre, bathing_pre_body)
 AG_KERNEL(k_bath_dist, bathing_dist_body)
 AG_KERNEL(k_bath_post, bathing_post_body)
@@ -768,6 +770,43 @@ int ag_closest_points(AgSim* s, int body_a, int body_b, float distance, int max_
   LAUNCH(s, k_closest, N, p);
   if (out && max_pts > 0 && d2h(s, out, st, (size_t)N * max_pts * sizeof(AgContact))) return -1;
   if (count && d2h(s, count, s->d_icount, sizeof(int) * N)) return -1;
+  return 0;
+}
+
+int ag_ik_solve(AgSim* s, int n_joints, const int32_t* joint_links, int ee_link, const float* target_pos, const float* target_quat,
+                int max_restarts, int iters, float threshold, uint64_t seed, const int32_t* env_mask, float* q_out, float* err_out) {
+  const int N = s->S.N;
+  if (n_joints < 1 || n_joints > AG_IK_MAXJ) return fail("ag_ik_solve: 1..8 joints");
+  if (ee_link < 0 || ee_link >= s->nl) return fail("bad link");
+  std::vector<int> parent(s->nl), jtype(s->nl);
+  std::vector<float> lo(s->nl), hi(s->nl);
+  d2h(s, parent.data(), s->S.link_parent, sizeof(int) * s->nl); d2h(s, jtype.data(), s->S.link_jtype, sizeof(int) * s->nl);
+  d2h(s, lo.data(), s->S.link_lower, sizeof(float) * s->nl); d2h(s, hi.data(), s->S.link_upper, sizeof(float) * s->nl);
+  IkDev K; memset(&K, 0, sizeof(K));
+  K.body = s->link_body[ee_link]; K.ee_link = ee_link; K.n_joints = n_joints; K.max_restarts = max_restarts; K.iters = iters;
+  K.threshold = threshold; K.damping = 0.05f; K.step_clip = 0.2f; K.seed = seed;
+  std::vector<int> chain;
+  for (int k = ee_link; k >= 0 && k != s->body_link0[K.body]; k = parent[k]) chain.push_back(k);
+  if ((int)chain.size() > AG_IK_MAXCHAIN) return fail("ag_ik_solve: chain too long");
+  std::reverse(chain.begin(), chain.end());
+  K.n_chain = (int)chain.size();
+  for (int i = 0; i < K.n_chain; i++) { K.chain[i] = chain[i]; K.chain_joint[i] = -1; }
+  for (int j = 0; j < n_joints; j++) {
+    int k = joint_links[j], at = -1;
+    for (int i = 0; i < K.n_chain; i++) if (chain[i] == k) at = i;
+    if (at < 0 || (jtype[k] != 1 && jtype[k] != 2)) return fail("ag_ik_solve: joint is not a movable joint on the path to the end effector");
+    K.chain_joint[at] = j; K.lower[j] = lo[k]; K.upper[j] = hi[k]; K.col_jtype[j] = jtype[k];
+  }
+  size_t need = (size_t)N * (3 + 4 + n_joints + 1) + (sizeof(IkDev) + 3) / 4;
+  float* st = stage(s, need);
+  if (!st) return fail("staging alloc failed");
+  float *d_tp = st, *d_tq = st + (size_t)N * 3, *d_q = d_tq + (size_t)N * 4, *d_err = d_q + (size_t)N * n_joints;
+  IkDev* d_K = (IkDev*)(d_err + N);
+  if (h2d(s, d_tp, target_pos, sizeof(float) * 3 * N) || h2d(s, d_tq, target_quat, sizeof(float) * 4 * N) || h2d(s, d_K, &K, sizeof(IkDev))) return -1;
+  if (set_mask(s, env_mask)) return -1;
+  KP p = kp0(); p.p0 = d_K; p.p1 = d_tp; p.p2 = d_tq; p.p3 = d_q; p.p4 = d_err; p.p5 = env_mask ? s->d_mask : nullptr;
+  LAUNCH(s, k_ik, N, p);
+  if (d2h(s, q_out, d_q, sizeof(float) * n_joints * N) || d2h(s, err_out, d_err, sizeof(float) * N)) return -1;
   return 0;
 }
 

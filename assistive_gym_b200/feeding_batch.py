@@ -156,10 +156,22 @@ class FeedingBatch:
             bowl_offset=np.concatenate([rng.uniform(-0.05, 0.05, size=(n, 2)), np.zeros((n, 1))], axis=1),
         )
 
-    def solve_ik(self, n, target_pos, rng, max_restarts=20, threshold=0.01):
+    def solve_ik(self, n, target_pos, rng, max_restarts=20, threshold=0.01, sim=None, idx=None):
         """Batched replacement of ik_random_restarts (robot.py:84-121): DLS from random rest poses,
-        re-sampling only the envs that have not reached the 0.01 position/orientation threshold."""
+        re-sampling only the envs that have not reached the 0.01 position/orientation threshold.
+        With a `sim` that offers `ik_solve` (the CUDA build / its host harness) the solve runs on the device for the
+        envs `idx` (default: all) and `target_pos` is the full [sim.n, 3] array; the numpy path serves the CPU oracle."""
         kin = self.kin
+        if sim is not None and hasattr(sim, 'ik_solve'):
+            mask = None
+            if idx is not None:
+                mask = np.zeros(sim.n, dtype=np.int32); mask[idx] = 1
+            q7, err = sim.ik_solve(self.arm_links, self.ee_link, target_pos, q_from_rpy(JACO['ee_orient_rpy']), max_restarts=max_restarts,
+                                   iters=120, threshold=threshold, seed=int(rng.integers(1, 2 ** 31 - 1)), mask=mask)
+            sel = slice(None) if idx is None else idx
+            q = np.zeros((sim.n if idx is None else len(idx), kin.nl))
+            q[:, np.array(JACO['arm']) + 1] = q7[sel]
+            return q, err[sel].astype(np.float64)
         tq = np.broadcast_to(q_from_rpy(JACO['ee_orient_rpy']), (n, 4)).copy()
         bp = np.broadcast_to(self.robot_base_pos, (n, 3))
         bq = np.broadcast_to(self.robot_base_quat, (n, 4))
@@ -217,7 +229,7 @@ class FeedingBatch:
         self.human_q = q
         # robot: IK to the randomised end-effector target, gripper open
         target = np.array([-0.15, -0.65, 1.15]) + s['ee_offset']
-        qik, ik_err = self.solve_ik(n, target, rng)
+        qik, ik_err = self.solve_ik(n, target, rng, sim=sim)
         gq = np.full((n, 3), JACO['gripper_pos'])
         sim.set_joint_state(self.gripper_links, q=gq, qd=np.zeros_like(gq))
         # resample IK solutions whose arm touches the person, the table or the wheelchair
@@ -245,7 +257,7 @@ class FeedingBatch:
             if len(idx) == 0:
                 break
             self.ik_resamples += len(idx)
-            q2, e2 = self.solve_ik(len(idx), target[idx], rng)
+            q2, e2 = self.solve_ik(len(idx), target if hasattr(sim, 'ik_solve') else target[idx], rng, sim=sim, idx=idx)
             qik[idx], ik_err[idx] = q2, e2
         self.ik_err = ik_err
         self.ik_colliding = int(hit.sum())

@@ -192,6 +192,15 @@ class BatchSim:
         o = _i32(np.broadcast_to(np.asarray(on, dtype=np.int32), (self.n,)))
         self._ck(self.lib.ag_feeding_set_tremor(self.h, _p(o), _p(_f32(rest, (self.n, 4))), _p(_f32(amplitude, (self.n, 4)))))
 
+    def ik_solve(self, joint_links, ee_link, target_pos, target_quat, max_restarts=20, iters=120, threshold=0.01, seed=1, mask=None):
+        """Batched DLS IK with random restarts on the device (robot.py:84-121); returns q [n, n_joints], err [n]."""
+        jl = _i32(joint_links)
+        tp = _f32(target_pos, (self.n, 3)); tq = _f32(np.broadcast_to(np.asarray(target_quat, dtype=np.float32), (self.n, 4)))
+        q = np.zeros((self.n, len(jl)), dtype=np.float32); err = np.zeros(self.n, dtype=np.float32)
+        self._ck(self.lib.ag_ik_solve(self.h, len(jl), _p(jl), int(ee_link), _p(tp), _p(tq), int(max_restarts), int(iters), float(threshold),
+                                      int(seed), _p(_i32(mask)), _p(q), _p(err)))
+        return q, err
+
     # ---- fused bed-bathing path
     def bathing_init(self, params, gender_is_male, targets_world, targets_valid):
         g = _i32(np.broadcast_to(np.asarray(gender_is_male, dtype=np.int32), (self.n,)))

@@ -232,6 +232,16 @@ int ag_bathing_init(AgSim* sim, const AgBathingParams* p, const int32_t* gender_
 int ag_bathing_step_dev(AgSim* sim, const float* action_dev, float* obs_dev, float* reward_dev, float* done_dev, float* info_dev);
 int ag_bathing_step_host(AgSim* sim, const float* action, float* obs, float* reward, float* done, float* info);
 
+/* --- batched inverse kinematics for reset (Robot.ik_random_restarts agents/robot.py:84-121 via
+ * AssistiveEnv.init_robot_pose envs/env.py:296): damped least squares with random restarts inside
+ * the joint limits, one env per thread.  `joint_links` [n_joints <= 8]: the solved joints (global link ids, all on the
+ * path from the body's base to `ee_link`); other joints on that path keep their current angles.  target_pos [N][3],
+ * target_quat [N][4] (link frame of ee_link), env_mask [N] or NULL, q_out [N][n_joints], err_out [N] =
+ * max(position error, quaternion distance) of the best restart.  Host buffers; uses the body's current base pose. */
+int ag_ik_solve(AgSim* sim, int n_joints, const int32_t* joint_links, int ee_link, const float* target_pos,
+                const float* target_quat, int max_restarts, int iters, float threshold, uint64_t seed,
+                const int32_t* env_mask, float* q_out, float* err_out);
+
 /* --- checkpoint / parity: full per-env dynamic state as a flat float blob -------------------- */
 size_t ag_state_size(const AgSim* sim);           /* floats per env */
 int    ag_state_get(AgSim* sim, float* out);      /* [N][state_size] host */
