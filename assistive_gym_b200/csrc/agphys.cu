@@ -797,11 +797,11 @@ int ag_ik_solve(AgSim* s, int n_joints, const int32_t* joint_links, int ee_link,
     if (at < 0 || (jtype[k] != 1 && jtype[k] != 2)) return fail("ag_ik_solve: joint is not a movable joint on the path to the end effector");
     K.chain_joint[at] = j; K.lower[j] = lo[k]; K.upper[j] = hi[k]; K.col_jtype[j] = jtype[k];
   }
-  size_t need = (size_t)N * (3 + 4 + n_joints + 1) + (sizeof(IkDev) + 3) / 4;
-  float* st = stage(s, need);
+  size_t nfl = ((size_t)N * (3 + 4 + n_joints + 1) + 3) & ~(size_t)3;     // IkDev holds a 64-bit seed: keep it 16-byte aligned
+  float* st = stage(s, nfl + (sizeof(IkDev) + 3) / 4);
   if (!st) return fail("staging alloc failed");
   float *d_tp = st, *d_tq = st + (size_t)N * 3, *d_q = d_tq + (size_t)N * 4, *d_err = d_q + (size_t)N * n_joints;
-  IkDev* d_K = (IkDev*)(d_err + N);
+  IkDev* d_K = (IkDev*)(st + nfl);
   if (h2d(s, d_tp, target_pos, sizeof(float) * 3 * N) || h2d(s, d_tq, target_quat, sizeof(float) * 4 * N) || h2d(s, d_K, &K, sizeof(IkDev))) return -1;
   if (set_mask(s, env_mask)) return -1;
   KP p = kp0(); p.p0 = d_K; p.p1 = d_tp; p.p2 = d_tq; p.p3 = d_q; p.p4 = d_err; p.p5 = env_mask ? s->d_mask : nullptr;
