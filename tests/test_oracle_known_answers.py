@@ -192,3 +192,63 @@ def test_aba_matches_crba_inverse(feeding):
     sim.step(1)
     qd = sim.get_joint_states(feeding.arm_links)[1]
     assert np.abs(qd).max() < 1e-10
+
+
+def test_sliding_box_decelerates_at_mu_g():
+    """Box launched along a horizontal plane: Coulomb friction decelerates it at mu g until it stops; the stopping
+    distance is v0^2 / (2 mu g) (no damping, explicit-velocity stepping adds at most one step of v0 dt)."""
+    b = SceneBuilder()
+    b.set_gravity([0, 0, -9.81])
+    plane = b.load_urdf('plane')
+    b.change_dynamics(plane, -1, lateral_friction=0.5)
+    sh = b.create_collision_shape('box', half_extents=[0.1, 0.1, 0.05])
+    box = b.create_multibody(base_mass=2.0, base_shape=sh, base_pos=[0, 0, 0.0502])
+    b.change_dynamics(box, -1, lateral_friction=0.8)           # combined mu = 0.4
+    sc = b.finalize()
+    sim = OracleSim(sc, capi.default_config(linear_damping=0, angular_damping=0, residual_threshold=0), 1)
+    sim.step(10)                                                # settle the contact
+    v0, mu = 1.0, 0.4
+    sim.set_base_velocity(box, [[v0, 0, 0]], [[0, 0, 0]])
+    link = [int(sc['body_link0'][box])]
+    x0 = sim.get_link_states(link)['pos'][0, 0, 0]
+    sim.step(5)
+    v5 = sim.get_link_states(link)['lin_vel'][0, 0, 0]
+    assert abs(v5 - (v0 - mu * 9.81 * 5 * 0.02)) < 0.02         # constant deceleration mu g
+    sim.step(60)
+    st = sim.get_link_states(link)
+    assert abs(st['lin_vel'][0, 0, 0]) < 1e-3
+    d = st['pos'][0, 0, 0] - x0
+    assert abs(d - v0 ** 2 / (2 * mu * 9.81)) < 0.03, d
+
+
+def test_hard_limit_clamps_and_zeroes_velocity():
+    """Human.enforce_joint_limits (agent.py:240-250) as a flag: after every step a joint beyond its limit is put back on
+    the limit with zero velocity -- unlike the limit ROW, which only pushes back with erp."""
+    b = SceneBuilder()
+    b.set_gravity([0, 0, 0])
+    sh = b.create_collision_shape('sphere', radius=0.05)
+    b.create_multibody(base_mass=0, base_pos=[0, 0, 2], link_masses=[1.0], link_shapes=[sh], link_positions=[[0, 0, 0]],
+                       link_orientations=[[0, 0, 0, 1]], link_inertial_positions=[[0, -1.0, 0]],
+                       link_inertial_orientations=[[0, 0, 0, 1]], link_parents=[0], link_joint_types=['revolute'],
+                       link_joint_axes=[[1, 0, 0]], link_lower=[-0.3], link_upper=[0.3])
+    sc = b.finalize()
+    for hard in (False, True):
+        sim = OracleSim(sc, capi.default_config(linear_damping=0, angular_damping=0), 1)
+        if hard:
+            sim.set_hard_limits([1], True)
+        sim.set_joint_state([1], q=[[0.29]], qd=[[3.0]])       # 0.06 rad per step: crosses the limit in the first step
+        sim.step(1)
+        q, qd, _ = sim.get_joint_states([1])
+        if hard:
+            assert q[0, 0] == 0.3 and qd[0, 0] == 0.0
+        else:
+            assert q[0, 0] > 0.3                                # the row acts from the next step on: overshoot remains
+
+
+def test_velocity_motor_tracks_target_speed():
+    """VELOCITY_CONTROL row (mode 2): with ample maxForce the joint runs at the target speed after one step."""
+    sc, _ = _pendulum()
+    sim = OracleSim(sc, capi.default_config(linear_damping=0, angular_damping=0), 1)
+    sim.set_motor([1], 2, target=[[0.7]], kp=[0.0], kd=[1.0], max_force=[500.0])
+    sim.step(3)
+    assert abs(sim.get_joint_states([1])[1][0, 0] - 0.7) < 1e-6
