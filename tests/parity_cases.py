@@ -243,3 +243,55 @@ def feeding_semantics_reference(fb, sim, action, state):
     state['iteration'] += 1
     done = state['iteration'] >= 200
     return obs, reward, done, total
+
+
+def readback_errors(fb, make_sim, n=4, seed=6):
+    """every read-back call of agents/agent.py (getJointStates, getLinkState incl. COM frame and
+    velocities, getContactPoints, getClosestPoints) on the product next to the oracle, from the same state."""
+    cfg = capi.default_config(residual_threshold=0.0)
+    cpu, dev, s = synced_pair(fb, make_sim, n, seed, cfg, settle=25)
+    rng = np.random.default_rng(seed)
+    tgt = cpu.get_joint_states(fb.arm_links)[0] + rng.uniform(-0.2, 0.2, size=(n, 7))
+    for sim in (cpu, dev):
+        sim.set_motor_targets(fb.arm_links, tgt)
+    dev.state_set(cpu.state_get())
+    cpu.step(1)
+    dev.step(1)
+    out = {}
+    sc = fb.scene
+    l0, nl = int(sc['body_link0'][fb.robot]), int(sc['body_nlinks'][fb.robot])
+    links = list(range(l0, l0 + nl)) + [int(sc['body_link0'][fb.tool]), int(sc['body_link0'][fb.bowl])]
+    qa, qda, ta = cpu.get_joint_states(fb.arm_links + fb.gripper_links)
+    qb, qdb, tb = dev.get_joint_states(fb.arm_links + fb.gripper_links)
+    out.update(q=np.abs(qa - qb).max(), qd=np.abs(qda - qdb).max(), tau=np.abs(ta - tb).max(), tau_max=np.abs(ta).max())
+    a, b = cpu.get_link_states(links), dev.get_link_states(links)
+    for k in ('pos', 'com_pos', 'lin_vel', 'ang_vel'):
+        out[k] = np.abs(a[k] - b[k]).max()
+    for k in ('quat', 'com_quat'):
+        out[k] = np.minimum(np.abs(a[k] - b[k]).max(axis=-1), np.abs(a[k] + b[k]).max(axis=-1)).max()
+    # contacts of the bowl (rests on the table) and of the tool (holds the food): same count, positions, forces
+    cerr, ferr, ncontacts = 0.0, 0.0, 0
+    for body in (fb.bowl, fb.tool):
+        ca, na = cpu.get_contacts(body, max_pts=32)
+        cb, nb_ = dev.get_contacts(body, max_pts=32)
+        out['count_equal'] = out.get('count_equal', True) and bool(np.array_equal(na, nb_))
+        for e in range(n):
+            if na[e] != nb_[e] or na[e] == 0:
+                continue
+            # order by (link_b, position) so the comparison does not depend on the listing order
+            ka = np.lexsort(np.round(ca[e, :na[e]]['pos_a'], 4).T[::-1]); kb = np.lexsort(np.round(cb[e, :nb_[e]]['pos_a'], 4).T[::-1])
+            cerr = max(cerr, np.abs(ca[e, :na[e]]['pos_a'][ka] - cb[e, :nb_[e]]['pos_a'][kb]).max())
+            ferr = max(ferr, np.abs(ca[e, :na[e]]['normal_force'][ka] - cb[e, :nb_[e]]['normal_force'][kb]).max())
+            ncontacts += int(na[e])
+    out.update(contact_pos=cerr, contact_force=ferr, n_contacts=ncontacts)
+    # closest points: robot vs table / wheelchair within 0.3 m, tool vs bowl within 1 m
+    derr = 0.0
+    for ba, bb, dist in ((fb.robot, fb.table, 0.3), (fb.robot, fb.wheelchair, 0.3), (fb.tool, fb.bowl, 1.0)):
+        pa, na = cpu.closest_points(ba, bb, dist, max_pts=64)
+        pb, nb_ = dev.closest_points(ba, bb, dist, max_pts=64)
+        out['count_equal'] = out['count_equal'] and bool(np.array_equal(na, nb_))
+        for e in range(n):
+            if na[e] and na[e] == nb_[e]:
+                derr = max(derr, abs(np.sort(pa[e, :na[e]]['distance'])[0] - np.sort(pb[e, :nb_[e]]['distance'])[0]))
+    out['closest_dist'] = derr
+    return out

@@ -72,6 +72,17 @@ def test_fused_feeding_step_semantics(feeding, make_sim, impairment):
         assert np.array_equal(done > 0.5, done_ref)
 
 
+def test_readback_calls(feeding, make_sim):
+    """A4-A7: getJointStates / getLinkState / getContactPoints / getClosestPoints equivalents vs the oracle."""
+    r = pc.readback_errors(feeding, make_sim, n=2)
+    assert r['count_equal'] and r['n_contacts'] > 0, r
+    assert r['q'] < 1e-6 and r['qd'] < 1e-4 and r['tau'] < 1e-3 * max(1.0, r['tau_max']), r
+    assert r['pos'] < 1e-5 and r['com_pos'] < 1e-5 and r['quat'] < 1e-5 and r['com_quat'] < 1e-5, r
+    assert r['lin_vel'] < 1e-3 and r['ang_vel'] < 1e-3, r
+    assert r['contact_pos'] < 1e-4 and r['contact_force'] < 0.05 * 9.81, r
+    assert r['closest_dist'] < 1e-5, r
+
+
 def test_contact_budget_overflow_flag(feeding, make_sim):
     cfg = capi.default_config(max_contacts=8)
     sim = make_sim(feeding.scene, cfg, 2)
