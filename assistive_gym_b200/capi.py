@@ -140,6 +140,7 @@ def load_library(path=None):
     lib.ag_overflow_count.argtypes = [vp]
     lib.ag_get_solver_stats.argtypes = [vp, vp, vp]
     lib.ag_get_pgs_cycles.argtypes = [vp, vp]
+    lib.ag_get_pgs_trips.argtypes = [vp, vp, vp]
     lib.ag_profile_enable.argtypes = [vp, ci]
     lib.ag_profile_get.argtypes = [vp, ci, vp, ci, vp, vp]
     if path is None:
@@ -155,5 +156,5 @@ EXPORTED_SYMBOLS = [
     'ag_step', 'ag_get_joint_states', 'ag_get_link_states', 'ag_get_contacts', 'ag_contact_force_sum',
     'ag_closest_points', 'ag_feeding_init', 'ag_feeding_reset_episode', 'ag_feeding_set_tremor', 'ag_set_hard_limits', 'ag_feeding_step_dev', 'ag_ik_solve', 'ag_bathing_init', 'ag_bathing_step_dev', 'ag_bathing_step_host',
     'ag_feeding_step_host', 'ag_state_size', 'ag_state_get', 'ag_state_set', 'ag_kernel_launches',
-    'ag_overflow_count', 'ag_get_solver_stats', 'ag_get_pgs_cycles', 'ag_profile_enable', 'ag_profile_get',
+    'ag_overflow_count', 'ag_get_solver_stats', 'ag_get_pgs_cycles', 'ag_get_pgs_trips', 'ag_profile_enable', 'ag_profile_get',
 ]

@@ -43,7 +43,7 @@ struct SimDev {
   const int* con_link; const float *con_pivot, *con_quat, *con_maxforce;
   const int* free_body; const float* free_invm;
   const int *art_body, *art_dl0, *art_nd, *art_voff;   // art_voff: start of the articulation's block in the solver's velocity vector
-  int NDp;                                             // dof part of that vector (every articulation padded to 4)
+  int NDp;                                             // dof part of that vector (every articulation padded to 8)
   const int *dl_link, *dl_parent, *dl_type, *dl_art, *dl_part0, *dl_nparts;
   const float *dl_mass, *dl_mc, *dl_J, *dl_damping;
   const float *pt_mass, *pt_com, *pt_I;
@@ -65,7 +65,7 @@ struct SimDev {
   int maxraw;                                          // capacity of the raw (arrival-order) contact buffer = 4 maxc
   unsigned *c_key, *s_key;                             // [maxraw][N] unsorted / [maxc][N] sorted
   float *c_data, *s_data;                              // [maxraw][AG_CFR][N] raw / [maxc][AG_CF][N] sorted
-  int *s_ref;                                          // [maxc][4][N]: refA, refB, stream slot of the normal row, of the friction pair
+  int *s_ref;                                          // [maxc][4][N]: refA, refB, record (rs_enc) of the normal row, friction record offset / 16
   int* overflow;                                       // [N]
   // ---- solver scratch
   float *fcom, *fIinv;                                 // [nf][3|6][N]
@@ -74,12 +74,14 @@ struct SimDev {
   float* dv;                                           // [ND + 6 nf][N]
   float* dr_lam;                                       // [3 ND][N] impulses of the dof rows: lower limit, upper limit, motor
   float* gr_lam;                                       // [ngr][N] impulses of the fixed-constraint rows
-  int rs_nbuf;                                         // ring depth of K7 (1 KB chunks per env in shared memory)
-  int* row_off;                                        // [3 ND + ngr][N] stream slot of each dof / fixed-constraint row (-1: not live)
-  float* rs_data; int rs_cap; int* rs_nslots;          // packed row stream: [N][rs_cap] slots of 32 floats (ag_solver.cuh), used slots [N]
+  int rs_area;                                         // floats of K7's per-CTA stream area (four envs share it)
+  int* row_off;                                        // [3 ND + ngr][N] record (rs_enc) of each dof / fixed-constraint row (-1: not live)
+  int* row_pair;                                       // [3 ND + ngr][N] the row sharing the record of a first row (-1: none)
+  float* rs_data; int rs_cap; int* rs_nfloats;         // packed row stream: [N][rs_cap] floats (ag_solver.cuh), used floats [N]
   int* iters_used;                                     // [N]
-  int* pgs_order; int* pgs_hist;                       // heaviest-first env order for K7 + its 64-bucket histogram
-  int* pgs_cycles;                                     // [N] SM cycles spent in k_pgs by each env's lane (diagnostic)
+  int* pgs_order;                                      // heaviest-first env order for K7
+  int* pgs_cycles;                                     // [N] SM cycles spent in k_pgs by each env's lane group (diagnostic)
+  int* pgs_trips;                                      // [N] records consumed by the env's warp in k_pgs (diagnostic)
 };
 
 // kernel-specific small parameter block

@@ -57,32 +57,37 @@ AG_KERNEL(k_sort, sort_body)
 AG_KERNEL(k_dyn, dyn_body)
 AG_KERNEL(k_rows, rows_body)
 AG_KERNEL(k_crows, crows_body)
-// k_pgs: LANES envs per CTA (one env per thread); per-lane shared memory = velocity deltas + impulses +
-// a two-deep ring of 1 KB row-stream chunks filled by TMA bulk copies (see ag_solver.cuh)
+// k_pgs: one warp per CTA = four envs, eight lanes each; per-env shared memory = velocity deltas + impulses +
+// a two-deep ring of 2 KB row-stream chunks filled by TMA bulk copies (see ag_solver.cuh).
+// k_order: heaviest-first env order for k_pgs (64-bucket counting sort, one CTA).
 #ifndef AG_CPU_EMU
-template <int LANES>
-__global__ void __launch_bounds__(LANES) k_pgs(SimDev S, KP p) {
+__global__ void __launch_bounds__(32) k_pgs(SimDev S, KP p) {
   extern __shared__ __align__(128) float pgs_smem[];
-  const int stride = p.i0;                           // rs_lane_floats(S)
-  int tid = blockIdx.x * LANES + threadIdx.x;
-  const unsigned base = (unsigned)__cvta_generic_to_shared(pgs_smem);
-  // The lane's pointer is made opaque and re-declared as shared: ptxas then keeps ONE converted shared address in a
-  // register instead of re-materialising the `pgs_smem` symbol (S2R SR_CgaCtaId + 2 LEA) in front of every record.
-  float* sm = pgs_smem + threadIdx.x * stride;
-  asm volatile("" : "+l"(sm));
-  __builtin_assume(__isShared(sm));
-  if (tid < p.n) pgs_body(tid, S, p, sm, base + threadIdx.x * stride * 4, base + LANES * stride * 4 + 8 * S.rs_nbuf * threadIdx.x);
+  pgs_warp(S, pgs_smem, p.i0, blockIdx.x * 4);
+}
+__global__ void __launch_bounds__(1024) k_order(SimDev S, KP) {
+  __shared__ int hist[64];
+  if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (int e = threadIdx.x; e < S.N; e += blockDim.x) atomicAdd(&hist[pgs_work_bucket(S, e)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) { int acc = 0; for (int b = 0; b < 64; b++) { int c = hist[b]; hist[b] = acc; acc += c; } }
+  __syncthreads();
+  for (int e = threadIdx.x; e < S.N; e += blockDim.x) S.pgs_order[atomicAdd(&hist[pgs_work_bucket(S, e)], 1)] = e;
 }
 #else
 static void k_pgs(SimDev S, KP p) {
-  std::vector<float> buf((size_t)rs_lane_floats(S) + 8);
+  std::vector<float> buf((size_t)rs_nv(S) + rs_nlam(S) + 8);
   float* base = (float*)(((uintptr_t)buf.data() + 15) & ~(uintptr_t)15);
-  for (int tid = 0; tid < p.n; tid++) pgs_body(tid, S, p, base, (rs_addr)base, 0);
+  for (int tid = 0; tid < p.n; tid++) pgs_body_host(tid, S, base);
+}
+static void k_order(SimDev S, KP) {
+  int hist[64] = {0};
+  for (int e = 0; e < S.N; e++) hist[pgs_work_bucket(S, e)]++;
+  int acc = 0; for (int b = 0; b < 64; b++) { int c = hist[b]; hist[b] = acc; acc += c; }
+  for (int e = 0; e < S.N; e++) S.pgs_order[hist[pgs_work_bucket(S, e)]++] = e;
 }
 #endif
-AG_KERNEL(k_order_hist, order_hist_body)
-AG_KERNEL(k_order_prefix, order_prefix_body)
-AG_KERNEL(k_order_scatter, order_scatter_body)
 AG_KERNEL(k_integrate, integrate_body)
 AG_KERNEL(k_gather, gather_body)
 AG_KERNEL(k_scatter, scatter_body)
@@ -118,7 +123,6 @@ struct AgSim {
   float *h_bpin_in, *h_bpin_out, *d_baction, *d_bobs, *d_breward, *d_bdone, *d_binfo;
   float *d_action, *d_obs, *d_reward, *d_done, *d_info;
   float *h_pin_in, *h_pin_out;
-  int pgs_lanes;
   // CUDA-graph replay of the fused env step (one graph per entry point, keyed by its device pointers)
   bool use_graph;
   struct StepGraph { void* exec; const void* key[5]; uint64_t launches; bool valid; } graphs[2];
@@ -407,7 +411,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   S.art_body = upload(s, art_body); S.art_dl0 = upload(s, art_dl0); S.art_nd = upload(s, art_nd);
   {
     std::vector<int> art_voff; int acc = 0;
-    for (int nd_a : art_nd) { art_voff.push_back(acc); acc += (nd_a + 3) & ~3; }
+    for (int nd_a : art_nd) { art_voff.push_back(acc); acc += (nd_a + 7) & ~7; }
     S.art_voff = upload(s, art_voff); S.NDp = acc;
   }
   S.dl_link = upload(s, dl_link); S.dl_parent = upload(s, dl_parent); S.dl_type = upload(s, dl_type); S.dl_art = upload(s, dl_art);
@@ -425,8 +429,8 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   S.lpos = dalloc<float>(s, (size_t)nl * 3 * N); S.lquat = dalloc<float>(s, (size_t)nl * 4 * N);
   S.cmin = dalloc<float>(s, (size_t)nc * 3 * N); S.cmax = dalloc<float>(s, (size_t)nc * 3 * N);
   S.lmin = dalloc<float>(s, (size_t)nl * 3 * N); S.lmax = dalloc<float>(s, (size_t)nl * 3 * N);
-  S.c_count = dalloc<int>(s, N); S.overflow = dalloc<int>(s, N); S.iters_used = dalloc<int>(s, N); S.pgs_cycles = dalloc<int>(s, N);
-  S.pgs_order = dalloc<int>(s, N); S.pgs_hist = dalloc<int>(s, 64);
+  S.c_count = dalloc<int>(s, N); S.overflow = dalloc<int>(s, N); S.iters_used = dalloc<int>(s, N); S.pgs_cycles = dalloc<int>(s, N); S.pgs_trips = dalloc<int>(s, N);
+  S.pgs_order = dalloc<int>(s, N);
   S.maxcand = 4 * S.maxc; S.cand_count = dalloc<int>(s, N); S.cand = dalloc<unsigned>(s, (size_t)S.maxcand * N); S.cand_s = dalloc<unsigned>(s, (size_t)S.maxcand * N);
   if ((size_t)nc * nc >= (1u << 24)) { g_err = "too many colliders (pair id must fit 24 bits)"; ag_destroy(s); return nullptr; }
   S.maxraw = 4 * S.maxc;
@@ -438,33 +442,36 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   S.Minv = dalloc<float>(s, (size_t)S.ND * S.ND * N);
   S.dv = dalloc<float>(s, (size_t)(S.ND + 6 * S.nf) * N);
   S.dr_lam = dalloc<float>(s, (size_t)3 * S.ND * N);
-  // row stream: worst case 4 slots per contact (free-free: 1 normal + 2 friction; articulated sides: 2 + 3) plus chunk padding
-  { const char* nbp = getenv("AG_PGS_NBUF"); S.rs_nbuf = nbp ? atoi(nbp) : 2; if (S.rs_nbuf != 2 && S.rs_nbuf != 4 && S.rs_nbuf != 8) S.rs_nbuf = 2; }
-  S.rs_cap = ((3 * S.ND + 3 * S.ngr + 4 * S.maxc + 8) + RS_CHUNK - 1) / RS_CHUNK * RS_CHUNK;
-  S.rs_data = dalloc<float>(s, (size_t)S.rs_cap * RS_SLOT * N); S.rs_nslots = dalloc<int>(s, N);
-  S.gr_lam = dalloc<float>(s, (size_t)S.ngr * N); S.row_off = dalloc<int>(s, (size_t)(3 * S.ND + S.ngr) * N);
+  // row stream: dof rows pair up (two lane blocks for an articulation of > 8 dofs), 3 records per fixed constraint, and
+  // per contact a normal row (half a record when it pairs up) + a friction record of two lane blocks; 30 % slack for
+  // chunk padding and articulated sides.  An env that needs more is flagged (ag_overflow_count).
+  {
+    size_t fl = (size_t)(3 * S.ND / 2 + 2) * rs_rec_floats(2) + (size_t)3 * S.ncon * rs_rec_floats(3) + (size_t)S.maxc * 2 * rs_rec_floats(2);
+    fl = fl + fl * 3 / 10 + 1024;
+    S.rs_cap = (int)((fl + 1023) / 1024 * 1024);
+  }
+  {
+    // K7's stream area: shared memory of an SM split between `k` resident CTAs (four envs each); what a CTA does not
+    // need for velocities and impulses holds the four row streams.  k = 2 keeps ~26 KB per env (FeedingJaco: 22 KB mean).
+    const char* kp = getenv("AG_PGS_CTAS_PER_SM");
+    int k = kp ? atoi(kp) : 2; if (k < 1) k = 1; if (k > 8) k = 8;
+    long budget = (233472 / k - 1024) / 4 - 4L * (rs_nv(S) + rs_nlam(S) + 64) - 8;
+    long need = 4L * S.rs_cap;
+    if (budget > need) budget = need;
+    if (budget < 4 * RS_MAXREC) budget = 4 * RS_MAXREC;
+    S.rs_area = (int)(budget / 64 * 64);
+  }
+  if (rs_nv(S) + 8 >= 65536 || rs_nlam(S) >= 65536) { g_err = "solver index space exceeds 16 bits: lower max_contacts"; ag_destroy(s); return nullptr; }
+  S.rs_data = dalloc<float>(s, (size_t)S.rs_cap * N); S.rs_nfloats = dalloc<int>(s, N);
+  S.gr_lam = dalloc<float>(s, (size_t)S.ngr * N); S.row_off = dalloc<int>(s, (size_t)(3 * S.ND + S.ngr) * N); S.row_pair = dalloc<int>(s, (size_t)(3 * S.ND + S.ngr) * N);
   s->d_mask = dalloc<int>(s, N); s->d_links = dalloc<int>(s, 1024); s->d_icount = dalloc<int>(s, N);
-  if (!S.gr_lam || !S.rs_data || !S.rs_nslots || !S.s_data) { g_err = "device allocation failed"; ag_destroy(s); return nullptr; }
+  if (!S.gr_lam || !S.rs_data || !S.rs_nfloats || !S.row_pair || !S.s_data) { g_err = "device allocation failed"; ag_destroy(s); return nullptr; }
 #ifndef AG_CPU_EMU
   {
-    // Lanes (envs) per CTA of the latency-bound per-env kernels.  4096 envs are only 128 full warps
-    // for 592 warp schedulers, so partially filled warps (8 envs each) put a warp on every scheduler,
-    // shorten the per-warp iteration count (max over fewer envs) and reduce divergence.
-    const char* lp = getenv("AG_PGS_LANES");
-    s->pgs_lanes = lp ? atoi(lp) : 1;
     { const char* gg = getenv("AG_GRAPH"); if (gg && atoi(gg) == 0) s->use_graph = false; }
-    if (s->pgs_lanes != 1 && s->pgs_lanes != 2 && s->pgs_lanes != 4 && s->pgs_lanes != 8 && s->pgs_lanes != 32) s->pgs_lanes = 1;
-    size_t smem = (size_t)rs_lane_floats(S) * s->pgs_lanes * sizeof(float) + 8 * S.rs_nbuf * s->pgs_lanes;
-    if (smem > 227 * 1024) { g_err = "PGS shared-memory footprint exceeds 227 KB per CTA: lower max_contacts or AG_PGS_LANES"; ag_destroy(s); return nullptr; }
-    cudaError_t ce = cudaSuccess;
-    switch (s->pgs_lanes) {
-      case 1: ce = cudaFuncSetAttribute(k_pgs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
-      case 2: ce = cudaFuncSetAttribute(k_pgs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
-      case 4: ce = cudaFuncSetAttribute(k_pgs<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
-      case 8: ce = cudaFuncSetAttribute(k_pgs<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
-      default: ce = cudaFuncSetAttribute(k_pgs<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
-    }
-    if (ce != cudaSuccess) { g_err = "cudaFuncSetAttribute(k_pgs) failed"; ag_destroy(s); return nullptr; }
+    size_t smem = (size_t)rs_cta_floats(S) * sizeof(float) + 32;
+    if (smem > 227 * 1024) { g_err = "PGS shared-memory footprint exceeds 227 KB per CTA: lower max_contacts"; ag_destroy(s); return nullptr; }
+    if (cudaFuncSetAttribute(k_pgs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { g_err = "cudaFuncSetAttribute(k_pgs) failed"; ag_destroy(s); return nullptr; }
   }
 #endif
   // defaults: friction from the template, all bodies active, identity quaternions
@@ -664,32 +671,22 @@ static void substep(AgSim* s) {
   LAUNCH(s, k_dyn, N, z);
   LAUNCH(s, k_rows, N, z);
   LAUNCH(s, k_crows, (size_t)(S.maxc + 3 * S.ND + S.ngr) * N, z);
-  {   // heaviest-first env order for the PGS kernel
-    dev_zero(s, S.pgs_hist, sizeof(int) * 64);
-    KP o = kp0(); o.p1 = S.pgs_hist;
-    LAUNCH(s, k_order_hist, N, o);
-    LAUNCH(s, k_order_prefix, 1, o);
-    LAUNCH(s, k_order_scatter, N, o);
-  }
 #ifndef AG_CPU_EMU
   {
-    KP kp = z; kp.n = N; kp.i0 = rs_lane_floats(S);
-    int L = s->pgs_lanes;
-    size_t smem = (size_t)kp.i0 * L * sizeof(float) + 8 * S.rs_nbuf * L;
-    int ps = s->profiling ? prof_slot(s, "k_pgs") : -1;
+    int ps = s->profiling ? prof_slot(s, "k_order") : -1;
     if (ps >= 0) prof_mark(s, ps, true);
-    dim3 grid((N + L - 1) / L);
-    switch (L) {
-      case 1: k_pgs<1><<<grid, 1, smem, s->stream>>>(S, kp); break;
-      case 2: k_pgs<2><<<grid, 2, smem, s->stream>>>(S, kp); break;
-      case 4: k_pgs<4><<<grid, 4, smem, s->stream>>>(S, kp); break;
-      case 8: k_pgs<8><<<grid, 8, smem, s->stream>>>(S, kp); break;
-      default: k_pgs<32><<<grid, 32, smem, s->stream>>>(S, kp); break;
-    }
+    k_order<<<1, 1024, 0, s->stream>>>(S, z);
     if (ps >= 0) prof_mark(s, ps, false);
-    s->launches++;
+    KP kp = z; kp.n = N; kp.i0 = S.rs_area;
+    size_t smem = (size_t)rs_cta_floats(S) * sizeof(float) + 32;
+    ps = s->profiling ? prof_slot(s, "k_pgs") : -1;
+    if (ps >= 0) prof_mark(s, ps, true);
+    k_pgs<<<(N + 3) / 4, 32, smem, s->stream>>>(S, kp);
+    if (ps >= 0) prof_mark(s, ps, false);
+    s->launches += 2;
   }
 #else
+  k_order(S, z);
   LAUNCH(s, k_pgs, N, z);
 #endif
   LAUNCH(s, k_integrate, N, z);
@@ -848,6 +845,11 @@ int ag_state_set(AgSim* s, const float* in) {
 }
 
 int ag_get_pgs_cycles(AgSim* s, int32_t* cycles) { return d2h(s, cycles, s->S.pgs_cycles, sizeof(int) * s->S.N); }
+int ag_get_pgs_trips(AgSim* s, int32_t* trips, int32_t* stream_floats) {
+  if (trips && d2h(s, trips, s->S.pgs_trips, sizeof(int) * s->S.N)) return -1;
+  if (stream_floats && d2h(s, stream_floats, s->S.rs_nfloats, sizeof(int) * s->S.N)) return -1;
+  return 0;
+}
 
 int ag_get_solver_stats(AgSim* s, int32_t* contacts, int32_t* iters) {
   if (contacts && d2h(s, contacts, s->S.c_count, sizeof(int) * s->S.N)) return -1;

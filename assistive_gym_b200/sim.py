@@ -159,6 +159,13 @@ class BatchSim:
         self._ck(self.lib.ag_get_pgs_cycles(self.h, _p(c)))
         return c
 
+    def pgs_trips(self):
+        """(records consumed by the env's warp, floats of the env's row stream) of the last PGS launch."""
+        t = np.zeros(self.n, dtype=np.int32)
+        f = np.zeros(self.n, dtype=np.int32)
+        self._ck(self.lib.ag_get_pgs_trips(self.h, _p(t), _p(f)))
+        return t, f
+
     def profile_enable(self, on=True):
         self._ck(self.lib.ag_profile_enable(self.h, int(bool(on))))
 

@@ -293,7 +293,7 @@ def main():
                           'envs_over_contact_budget': overflow,
                           'contacts_per_env': {'mean': float(ccount.mean()), 'p50': float(np.percentile(ccount, 50)), 'p99': float(np.percentile(ccount, 99)), 'max': int(ccount.max())},
                           'pgs_iters_per_env': {'mean': float(citers.mean()), 'p50': float(np.percentile(citers, 50)), 'p99': float(np.percentile(citers, 99)), 'max': int(citers.max())},
-                          'pgs_lanes_per_cta': int(os.environ.get('AG_PGS_LANES', '4')),
+                          'pgs_lanes_per_env': 8,
                           'collective': 'all_gather(reward) per step' if world > 1 else 'none'},
                'clocks': clk,
                'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n * 7 * 4, 'd2h_bytes_per_step': n * 31 * 4},

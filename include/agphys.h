@@ -258,7 +258,8 @@ int      ag_overflow_count(AgSim* sim);            /* envs that exceeded the con
 /* per-env contact count and PGS iterations used in the last substep (host int32[N] buffers, may be NULL) */
 int      ag_get_solver_stats(AgSim* sim, int32_t* contacts, int32_t* iters);
 /* SM cycles each env's lane spent inside the PGS kernel of the last substep (load-balance diagnostic) */
-int      ag_get_pgs_cycles(AgSim* sim, int32_t* cycles);           /* envs that exceeded the contact budget last step */
+int      ag_get_pgs_cycles(AgSim* sim, int32_t* cycles);           /* diagnostic: SM cycles each env spent in the last PGS launch */
+int      ag_get_pgs_trips(AgSim* sim, int32_t* trips, int32_t* stream_floats);  /* diagnostic: records its warp consumed / floats of its row stream */
 
 #ifdef __cplusplus
 }

@@ -522,6 +522,12 @@ struct Solver {
     return t;
   }
   bool finish(Row& r) {
+    // two links of the same articulated body (self-collision): both sides act on the same dof vector, so the row is
+    // ONE side with J = J_a + J_b (the diagonal needs the cross terms J_a M^-1 J_b^T)
+    if (r.n[0] > 0 && r.n[1] == r.n[0] && r.off[0] == r.off[1]) {
+      for (int i = 0; i < r.n[0]; i++) { r.J[0][i] += r.J[1][i]; r.MiJ[0][i] += r.MiJ[1][i]; }
+      r.n[1] = 0;
+    }
     real d = 0;
     for (int sd = 0; sd < 2; sd++) for (int i = 0; i < r.n[sd]; i++) d += r.J[sd][i] * r.MiJ[sd][i];
     if (d <= real(1e-30)) return false;
