@@ -21,13 +21,15 @@ class AgConfig(C.Structure):
                 ('residual_threshold', C.c_double), ('contact_threshold', C.c_double),
                 ('linear_damping', C.c_double), ('angular_damping', C.c_double),
                 ('max_coord_velocity', C.c_double), ('hull_margin', C.c_double),
-                ('cone_friction', C.c_int), ('gyroscopic', C.c_int), ('max_contacts', C.c_int)]
+                ('cone_friction', C.c_int), ('gyroscopic', C.c_int), ('max_contacts', C.c_int),
+                ('warmstart_contact', C.c_double), ('warmstart_joint', C.c_double)]
 
 
 def default_config(**kw):
     c = AgConfig(dt=0.02, num_substeps=1, num_solver_iters=50, erp=0.2, contact_erp=0.08, linear_slop=1e-5,
                  residual_threshold=1e-7, contact_threshold=0.02, linear_damping=0.04, angular_damping=0.04,
-                 max_coord_velocity=100.0, hull_margin=0.001, cone_friction=1, gyroscopic=1, max_contacts=128)
+                 max_coord_velocity=100.0, hull_margin=0.001, cone_friction=1, gyroscopic=1, max_contacts=128,
+                 warmstart_contact=0.0, warmstart_joint=0.0)
     for k, v in kw.items():
         if not hasattr(c, k):
             raise AttributeError(k)

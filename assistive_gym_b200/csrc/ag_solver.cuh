@@ -58,8 +58,9 @@ AG_HD int rs_nv(const SimDev& S) { return (S.NDp + 8 * S.nf + 8 + 31) & ~31; }
 // impulses: [3 ND dof rows][ngr fixed-constraint rows][3 per contact][dummy]
 AG_HD int rs_dummy(const SimDev& S) { return 3 * S.ND + S.ngr + 3 * S.maxc; }
 AG_HD int rs_nlam(const SimDev& S) { return (3 * S.ND + S.ngr + 3 * S.maxc + 1 + 31) & ~31; }
-// shared memory of a K7 CTA (four envs): per env velocity deltas, impulses, a block of zeros; then the stream area
-AG_HD int rs_cta_floats(const SimDev& S) { return 4 * (rs_nv(S) + rs_nlam(S) + 64) + S.rs_area; }
+// shared memory of a K7 CTA (four envs): per env velocity deltas, impulses, 32 zeros, a null record, the 4 KB stream ring
+AG_HD int rs_env_floats(const SimDev& S) { return rs_nv(S) + rs_nlam(S) + 64 + 1024; }
+AG_HD int rs_cta_floats(const SimDev& S) { return 4 * rs_env_floats(S); }
 
 // ------------------------------------------------------------------ K6: constraint rows
 // side reference encoding: (idx << 2) | kind, kind: 0 static, 1 free body (idx = f), 2 articulated (idx = dyn link)
@@ -193,6 +194,11 @@ AG_HD void rs_pad_header(const SimDev& S, float* rec, int mode, int floats) {
   rec[1] = i2f_bits(null | (null << 16)); rec[2] = rec[1];
   rec[3] = i2f_bits(dummy | (dummy << 16)); rec[4] = i2f_bits(dummy);
   for (int i = 5; i < RS_HDR; i++) rec[i] = 0.f;
+}
+// word i of a null record's header (what rs_pad_header(S, rec, RM_BOX, 0) writes)
+AG_HD float rs_null_word(const SimDev& S, int i) {
+  const int null = rs_null(S), dummy = rs_dummy(S);
+  return i == 1 || i == 2 ? i2f_bits(null | (null << 16)) : (i == 3 ? i2f_bits(dummy | (dummy << 16)) : (i == 4 ? i2f_bits(dummy) : i2f_bits(0)));
 }
 AG_HD int rs_alloc(const SimDev&, RsCur& c, int nf) {
   if (c.pos + nf > c.capf) { c.over = true; return -1; }
@@ -328,7 +334,10 @@ AG_HDN inline void rows_body(int e, const SimDev& S, const KP&) {
     if (h.nv > 0 && S.s_ref[rb + 2 * (size_t)N] >= 0) o = rs_alloc(S, c, rs_rec_floats(h.nv));
     S.s_ref[rb + 3 * (size_t)N] = o < 0 ? -1 : o / RS_UNIT;
   }
-  S.rs_nfloats[e] = c.pos;
+  if (c.pos % 32 != 0) {                            // K7 refills its ring in 32-float pieces: pad with a null record
+    if (c.pos + RS_UNIT <= c.capf) { rs_pad_header(S, c.rs + c.pos, RM_PAD, RS_UNIT); c.pos += RS_UNIT; } else c.over = true;
+  }
+  S.rs_nfloats[e] = c.over ? (c.pos / 32) * 32 : c.pos;
   if (c.over) S.overflow[e] = 1;
 }
 
@@ -532,6 +541,22 @@ __device__ __forceinline__ void rs_fetch(rs_addr dst, const float* src, unsigned
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// predicated forms (no branch: a lane-dependent branch in front of warp-wide shuffles leaves the warp diverged)
+__device__ __forceinline__ void rs_bar_init_if(rs_addr bar, bool on) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %1, 0; @p mbarrier.init.shared::cta.b64 [%0], 1; }" :: "r"(bar), "r"((int)on) : "memory");
+}
+__device__ __forceinline__ void rs_fetch_if(rs_addr dst, const float* src, unsigned bytes, rs_addr bar, bool on) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0;\n"
+               "  @p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n"
+               "  @p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3]; }"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar), "r"((int)on) : "memory");
+}
+__device__ __forceinline__ bool rs_try_wait(rs_addr bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void rs_wait(rs_addr bar, unsigned parity) {
   unsigned ok;
   do {
@@ -547,74 +572,75 @@ __device__ __forceinline__ float rs_sum8(float x) {            // sum over the 8
 }
 struct RsHdr { v4 a, b, c, d; };
 __device__ __forceinline__ RsHdr rs_ld_hdr(const float* p) { RsHdr h; h.a = ldv4(p); h.b = ldv4(p + 4); h.c = ldv4(p + 8); h.d = ldv4(p + 12); return h; }
+// 16-byte asynchronous copy global -> shared by the executing lane (LDGSTS), predicated
+__device__ __forceinline__ void rs_cp16(rs_addr dst, const float* src, bool on) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p cp.async.cg.shared.global [%0], [%1], 16; }" :: "r"(dst), "l"(src), "r"((int)on) : "memory");
+}
+__device__ __forceinline__ void rs_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int W> __device__ __forceinline__ void rs_cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(W) : "memory"); }
 
-// One warp = four envs (lane group g = lane / 8), lock-step.  Shared memory of the CTA (`sm`): per env its velocity
-// deltas, impulses and a 32-float block of zeros, then ONE area of `SA` floats that holds the four row streams.
-// Each stream is fetched once (TMA bulk copies, one mbarrier per env) and every PGS iteration then runs out of shared
-// memory; the part of a stream that does not fit (rare: the area is shared by need) is read from global memory in place.
-__device__ __forceinline__ void pgs_warp(const SimDev& S, float* sm, int SA, int warp_slot0) {
+#define RS_RING 1024          // floats of an env's stream ring (4 KB)
+#define RS_PIECE 32           // floats per refill piece: 8 lanes x 16 B
+#define RS_KPF 5              // refill pieces per record consumed: 160 floats >= the largest record, so the ring stays full
+#define RS_WAITG 3            // cp.async groups (= records) that may still be in flight
+
+// One warp = four envs (lane group g = lane / 8), lock-step.  Shared memory per env (`sm`): velocity deltas, impulses,
+// 32 zeros, a null record, and a 4 KB ring through which the env's row stream flows once per sweep:
+//   * the first tile of the stream is staged by one TMA bulk copy per env (mbarrier complete_tx),
+//   * from then on every lane copies 16 B pieces with cp.async right behind the consumer (RS_KPF pieces of 128 B per
+//     record and env), so the refill is SIMT-uniform -- no elected lane, no spin loop -- and a record is consumed
+//     RS_WAITG + 1 records after its bytes were requested (cp.async.wait_group).
+// The stream stays in HBM / L2; ~6.5 KB of shared memory per env keep every env of the batch resident at once.
+__device__ __forceinline__ void pgs_warp(const SimDev& S, float* sm, int, int warp_slot0) {
   const int lane = threadIdx.x & 31, g = lane >> 3, l = lane & 7;
   const int N = S.N;
   const int slot = warp_slot0 + g;
   const bool valid = slot < N;
   const int e = valid ? S.pgs_order[slot] : 0;
-  const int NV = rs_nv(S), NL = rs_nlam(S), EF = NV + NL + 64;
+  const int NV = rs_nv(S), NL = rs_nlam(S), EF = rs_env_floats(S);
   float* v = sm + (size_t)g * EF;
   float* lam = v + NV;
   float* zblk = lam + NL;                          // 32 zeros: the lane block of an absent slot; then 16 floats: a null record
-  float* area = sm + (size_t)4 * EF;
-  const rs_addr bar = rs_smem_addr(area + SA) + 8 * g;
+  float* nullrec = zblk + 32;
+  float* ring = nullrec + 32;
+  const rs_addr ring_s = rs_smem_addr(ring);
+  const rs_addr bar = rs_smem_addr(sm + (size_t)4 * EF) + 8 * g;
   const long long t_begin = clock64();
-  for (int i = l; i < EF; i += 8) v[i] = 0.f;
+  for (int i = l; i < NV + NL + 32; i += 8) v[i] = 0.f;
   const float* rs = S.rs_data + (size_t)e * S.rs_cap;
-  const int total = valid ? S.rs_nfloats[e] : 0;
-  // ---- share the stream area: everybody gets min(need, SA / 4), what is left goes to those who need more
-  int res, off;
-  {
-    const int t0 = __shfl_sync(0xffffffffu, total, 0), t1 = __shfl_sync(0xffffffffu, total, 8), t2 = __shfl_sync(0xffffffffu, total, 16), t3 = __shfl_sync(0xffffffffu, total, 24);
-    const int q = (SA / 4) & ~(RS_UNIT - 1);
-    int r0 = min(t0, q), r1 = min(t1, q), r2 = min(t2, q), r3 = min(t3, q);
-    int left = SA - 4 * q + (4 * q - r0 - r1 - r2 - r3);
-    int x;
-    x = min(t0 - r0, left); r0 += x; left -= x;
-    x = min(t1 - r1, left); r1 += x; left -= x;
-    x = min(t2 - r2, left); r2 += x; left -= x;
-    x = min(t3 - r3, left); r3 += x; left -= x;
-    res = g == 0 ? r0 : (g == 1 ? r1 : (g == 2 ? r2 : r3));
-    off = g == 0 ? 0 : (g == 1 ? r0 : (g == 2 ? r0 + r1 : r0 + r1 + r2));
-  }
-  const float* sres = area + off;                  // resident prefix [0, res) of the env's stream
-  if (l == 0) {
-    rs_bar_init(bar);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (res > 0) {
-      rs_expect(bar, (unsigned)res * 4);
-      for (int o = 0; o < res; o += 4096) { int n = res - o; if (n > 4096) n = 4096; rs_fetch(rs_smem_addr(sres + o), rs + o, (unsigned)n * 4, bar); }
-    }
-  }
+  const int total = valid ? S.rs_nfloats[e] : 0;     // a multiple of RS_PIECE (K6a pads)
+  // ---- fill the ring (all of it: the stream repeats every sweep).  A stream of at least a ring: ONE TMA bulk copy;
+  // a shorter one wraps inside the ring: 128 B pieces by cp.async.  No lane-dependent branch anywhere.
+  const bool big = total >= RS_RING;
+  for (int i = l; i < 16; i += 8) nullrec[i] = rs_null_word(S, i);
+  rs_bar_init_if(bar, l == 0);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
-  if (res > 0) rs_wait(bar, 0);
-  __syncwarp();                                    // the lane groups leave the wait at different times: reconverge for good
-  // a record is read from shared memory if it lies inside the resident prefix for sure
-  const int res_lim = res - RS_MAXREC;
-  const bool all_res = __all_sync(0xffffffffu, res >= total);
-#ifdef AG_PGS_DEBUG
-  if (blockIdx.x < 2 && l == 0) printf("pgs blk %d g %d total %d res %d off %d SA %d all_res %d\n", blockIdx.x, g, total, res, off, SA, (int)all_res);
-#endif
+  rs_fetch_if(ring_s, rs, RS_RING * 4, bar, l == 0 && big);
+  int ppos = 0, pabs = 0;
+  for (int j = 0; j < RS_RING / RS_PIECE; j++) {
+    const bool on = !big && total > 0;
+    rs_cp16(ring_s + ((pabs + 4 * l) << 2), rs + ppos + 4 * l, on);
+    pabs += RS_PIECE; ppos += RS_PIECE;
+    ppos = ppos >= total ? 0 : ppos;
+  }
+  rs_cp_commit();
+  rs_cp_wait<0>();
+  ppos = big ? (total == RS_RING ? 0 : RS_RING) : ppos;
+  pabs = RS_RING;
+  { bool ok; do { ok = big ? rs_try_wait(bar, 0) : true; } while (!__all_sync(0xffffffffu, ok)); }   // warp-uniform loop
+  __syncwarp();
+  // refill state: `ppos` next stream position to request (wraps at `total`: the next sweep follows seamlessly),
+  // `pabs` the same as a running count = ring position
   bool active = total > 0 && S.iters > 0;
   int it = 0, used = 0;
-  // a finished env parks on a null record (nv 0, size 0, null slots, dummy impulses) that lives in front of the area
-  float* nullrec = zblk + 32;
-  if (l == 0) rs_pad_header(S, nullrec, RM_BOX, 0);
-  __syncwarp();
-  const int nullpos = (int)(nullrec - sres);
-  int cur = active ? 0 : nullpos;
+  int cur = 0, cabs = 0;                           // stream position / running count of the record in H, Q
   const float* zb = zblk + 4 * l;
-  RsHdr H = rs_ld_hdr(((all_res || cur <= res_lim) ? sres : rs) + cur);
+  RsHdr H = rs_ld_hdr(active ? ring : nullrec);
   v4 Q0, Q1, Q2, Q3;
   {
     const int nv = f2i_bits(H.a.x) & 7;
-    const float* lb = ((all_res || cur <= res_lim) ? sres : rs) + cur + RS_HDR + 4 * l;
+    const float* lb = ring + RS_HDR + 4 * l;
     Q0 = ldv4(nv > 0 ? lb : zb); Q1 = ldv4(nv > 1 ? lb + RS_LB : zb); Q2 = ldv4(nv > 2 ? lb + 2 * RS_LB : zb); Q3 = ldv4(nv > 3 ? lb + 3 * RS_LB : zb);
   }
   __syncwarp();
@@ -625,58 +651,97 @@ __device__ __forceinline__ void pgs_warp(const SimDev& S, float* sm, int SA, int
   long long guard = (long long)S.iters * (S.rs_cap / RS_UNIT + 2) + 16;     // a corrupt stream must not hang the GPU
   const long long guard0 = guard;
   bool act_lag = true;
-  // The loop body has NO divergent branch (selects only): the warp must be converged at the shuffles, a diverged warp
-  // takes a collective slow path that costs thousands of cycles per record.  It is software pipelined: record t's
-  // header and lane blocks were loaded during record t-1, and the loop condition votes on the flag of the trip before
-  // (one idle trip at the end) so that neither a load nor the vote sits on the dependent chain
+#ifdef AG_PGS_DEBUG
+  int dbg_bad = 0, dbg_first = -1;
+#endif
+  // The loop body has NO divergent branch (selects and predicated copies only): the warp must be converged at the
+  // shuffles, a diverged warp takes a collective slow path that costs thousands of cycles per record.  It is software
+  // pipelined: record t's header and lane blocks were loaded during record t-1, and the loop condition votes on the
+  // flag of the trip before (one idle trip at the end) so that neither a load nor the vote sits on the dependent chain
   //   LDS v -> fma -> 3 x (shfl, add) -> solve -> fma -> STS v.
-  // ALLRES: every env's stream is resident -> plain LDS; otherwise generic loads from whichever space holds the record.
-#define RS_LOOP(ALLRES)                                                                                                   \
-  while (__any_sync(0xffffffffu, act_lag) && --guard > 0) {                                                               \
-    act_lag = active;                                                                                                     \
-    const int meta = f2i_bits(H.a.x), w1 = f2i_bits(H.a.y), w2 = f2i_bits(H.a.z), w3 = f2i_bits(H.a.w);                   \
-    const int mode = (meta >> 4) & 3, size = (meta >> 8) * RS_UNIT;                                                       \
-    float* vp0 = v + (w1 & 0xffff) + l; float* vp1 = v + (w1 >> 16) + l; float* vp2 = v + (w2 & 0xffff) + l; float* vp3 = v + (w2 >> 16) + l; \
-    const float x0 = *vp0, x1 = *vp1, x2 = *vp2, x3 = *vp3;                                                               \
-    float* lp1 = lam + (w3 & 0xffff); float* lp2 = lam + (w3 >> 16);                                                      \
-    const float lam1 = *lp1, lam2 = *lp2, lamn = lam[f2i_bits(H.b.x)];                                                    \
-    const bool at_end = active && cur + size >= total;                                                                    \
-    const int next = active ? (at_end ? 0 : cur + size) : nullpos;                                                        \
-    const float* nb = ((ALLRES || next <= res_lim) ? sres : rs) + next;                                                   \
-    const RsHdr Hn = rs_ld_hdr(nb);                                                                                       \
-    float p1 = (Q0.x * x0 + Q1.x * x1) + (Q2.x * x2 + Q3.x * x3);                                                         \
-    float p2 = (Q0.z * x0 + Q1.z * x1) + (Q2.z * x2 + Q3.z * x3);                                                         \
-    p1 += __shfl_xor_sync(0xffffffffu, p1, 1); p2 += __shfl_xor_sync(0xffffffffu, p2, 1);                                 \
-    const int nvn = f2i_bits(Hn.a.x) & 7;                                                                                 \
-    const float* lbn = nb + RS_HDR + 4 * l;                                                                               \
-    const v4 Qn0 = ldv4(nvn > 0 ? lbn : zb), Qn1 = ldv4(nvn > 1 ? lbn + RS_LB : zb), Qn2 = ldv4(nvn > 2 ? lbn + 2 * RS_LB : zb), Qn3 = ldv4(nvn > 3 ? lbn + 3 * RS_LB : zb); \
-    p1 += __shfl_xor_sync(0xffffffffu, p1, 2); p2 += __shfl_xor_sync(0xffffffffu, p2, 2);                                 \
-    p1 += __shfl_xor_sync(0xffffffffu, p1, 4); p2 += __shfl_xor_sync(0xffffffffu, p2, 4);                                 \
-    const RsSol r = rs_solve2(mode, cone_cfg, !active, p1, p2, lam1, lam2, lamn, H.c, H.d, H.b.y, H.b.z);                 \
-    *lp1 = r.s1; *lp2 = r.s2;                                                                                             \
-    *vp0 = x0 + Q0.y * r.d1 + Q0.w * r.d2;                                                                                \
-    *vp1 = x1 + Q1.y * r.d1 + Q1.w * r.d2;                                                                                \
-    *vp2 = x2 + Q2.y * r.d1 + Q2.w * r.d2;                                                                                \
-    *vp3 = x3 + Q3.y * r.d1 + Q3.w * r.d2;                                                                                \
-    resid = fmaxf(resid, fmaxf(r.d1 * r.d1, r.d2 * r.d2));                                                                \
-    cur = next;                                                                                                           \
-    /* end of a sweep (never for a finished env): selects only */                                                        \
-    it += at_end ? 1 : 0;                                                                                                 \
-    used = at_end ? it : used;                                                                                            \
-    active = active && !(at_end && ((thr > 0.f && resid <= thr) || it >= iters));                                         \
-    resid = at_end ? 0.f : resid;                                                                                         \
-    H = Hn; Q0 = Qn0; Q1 = Qn1; Q2 = Qn2; Q3 = Qn3;                                                                       \
+  while (__any_sync(0xffffffffu, act_lag) && --guard > 0) {
+    act_lag = active;
+    const int meta = f2i_bits(H.a.x), w1 = f2i_bits(H.a.y), w2 = f2i_bits(H.a.z), w3 = f2i_bits(H.a.w);
+    const int mode = (meta >> 4) & 3, size = (meta >> 8) * RS_UNIT;
+    float* vp0 = v + (w1 & 0xffff) + l; float* vp1 = v + (w1 >> 16) + l; float* vp2 = v + (w2 & 0xffff) + l; float* vp3 = v + (w2 >> 16) + l;
+    const float x0 = *vp0, x1 = *vp1, x2 = *vp2, x3 = *vp3;
+    float* lp1 = lam + (w3 & 0xffff); float* lp2 = lam + (w3 >> 16);
+    const float lam1 = *lp1, lam2 = *lp2, lamn = lam[f2i_bits(H.b.x)];
+    const bool at_end = active && cur + size >= total;
+    const int next = at_end ? 0 : cur + size;
+    const int nabs = cabs + size;                    // (a finished env: size 0)
+    // ---- the next record: its bytes were requested at least RS_WAITG + 1 records ago.  Proof: the ring starts full and
+    // a trip refills up to 160 floats while it consumes at most 144, so after every trip the requests reach at least
+    // RS_RING - 63 floats beyond the next record; the record read now ends at most 4 * 144 + 144 = 720 floats beyond
+    // where the next record was four trips ago, i.e. inside what had been requested by then.
+#ifdef AG_PGS_SYNC_ALL
+    rs_cp_wait<0>();
+#else
+    rs_cp_wait<RS_WAITG>();
+#endif
+    __syncwarp();                                    // pieces copied by the other lanes of the group
+    const float* nrec = active ? ring + (nabs & (RS_RING - 1)) : nullrec;
+    RsHdr Hn;
+    Hn.a = ldv4(nrec);
+    Hn.b = ldv4(active ? ring + ((nabs + 4) & (RS_RING - 1)) : nullrec + 4);
+    Hn.c = ldv4(active ? ring + ((nabs + 8) & (RS_RING - 1)) : nullrec + 8);
+    Hn.d = ldv4(active ? ring + ((nabs + 12) & (RS_RING - 1)) : nullrec + 12);
+#ifdef AG_PGS_DEBUG
+    if (active) {
+      const float* gr = rs + next;
+      bool bad = f2i_bits(Hn.a.x) != f2i_bits(gr[0]) || f2i_bits(Hn.a.y) != f2i_bits(gr[1]) || f2i_bits(Hn.d.w) != f2i_bits(gr[15]);
+      if (bad) { dbg_bad++; if (dbg_first < 0) dbg_first = (int)(guard0 - guard); }
+    }
+#endif
+    float p1 = (Q0.x * x0 + Q1.x * x1) + (Q2.x * x2 + Q3.x * x3);
+    float p2 = (Q0.z * x0 + Q1.z * x1) + (Q2.z * x2 + Q3.z * x3);
+    p1 += __shfl_xor_sync(0xffffffffu, p1, 1); p2 += __shfl_xor_sync(0xffffffffu, p2, 1);
+    const int nvn = active ? (f2i_bits(Hn.a.x) & 7) : 0;
+    const int lb0 = nabs + RS_HDR + 4 * l;
+    const v4 Qn0 = ldv4(nvn > 0 ? ring + (lb0 & (RS_RING - 1)) : zb), Qn1 = ldv4(nvn > 1 ? ring + ((lb0 + RS_LB) & (RS_RING - 1)) : zb);
+    const v4 Qn2 = ldv4(nvn > 2 ? ring + ((lb0 + 2 * RS_LB) & (RS_RING - 1)) : zb), Qn3 = ldv4(nvn > 3 ? ring + ((lb0 + 3 * RS_LB) & (RS_RING - 1)) : zb);
+#ifdef AG_PGS_DEBUG
+    if (active) {
+      const float* gq = rs + next + RS_HDR + 4 * l;
+      bool bad = (nvn > 0 && (Qn0.x != gq[0] || Qn0.w != gq[3])) || (nvn > 1 && (Qn1.x != gq[32] || Qn1.w != gq[35])) || (nvn > 2 && Qn2.y != gq[65]) || (nvn > 3 && Qn3.y != gq[97]);
+      if (bad) { dbg_bad++; if (dbg_first < 0) dbg_first = (int)(guard0 - guard); }
+    }
+#endif
+    p1 += __shfl_xor_sync(0xffffffffu, p1, 2); p2 += __shfl_xor_sync(0xffffffffu, p2, 2);
+    // ---- refill: everything in front of the next record is consumed; request up to RS_KPF pieces behind it
+#pragma unroll
+    for (int j = 0; j < RS_KPF; j++) {
+      const bool on = active && pabs + RS_PIECE <= nabs + RS_RING;
+      rs_cp16(ring_s + (((pabs + 4 * l) & (RS_RING - 1)) << 2), rs + ppos + 4 * l, on);
+      pabs += on ? RS_PIECE : 0;
+      ppos += on ? RS_PIECE : 0;
+      ppos = ppos >= total ? 0 : ppos;
+    }
+    rs_cp_commit();
+    p1 += __shfl_xor_sync(0xffffffffu, p1, 4); p2 += __shfl_xor_sync(0xffffffffu, p2, 4);
+    const RsSol r = rs_solve2(mode, cone_cfg, !active, p1, p2, lam1, lam2, lamn, H.c, H.d, H.b.y, H.b.z);
+    *lp1 = r.s1; *lp2 = r.s2;
+    *vp0 = x0 + Q0.y * r.d1 + Q0.w * r.d2;
+    *vp1 = x1 + Q1.y * r.d1 + Q1.w * r.d2;
+    *vp2 = x2 + Q2.y * r.d1 + Q2.w * r.d2;
+    *vp3 = x3 + Q3.y * r.d1 + Q3.w * r.d2;
+    resid = fmaxf(resid, fmaxf(r.d1 * r.d1, r.d2 * r.d2));
+    cur = next; cabs = nabs;
+    // end of a sweep (never for a finished env): selects only
+    it += at_end ? 1 : 0;
+    used = at_end ? it : used;
+    active = active && !(at_end && ((thr > 0.f && resid <= thr) || it >= iters));
+    resid = at_end ? 0.f : resid;
+    H = Hn; Q0 = Qn0; Q1 = Qn1; Q2 = Qn2; Q3 = Qn3;
   }
-  if (all_res) { RS_LOOP(true) } else { RS_LOOP(false) }
-#undef RS_LOOP
+  rs_cp_wait<0>();
   __syncwarp();
   if (!valid) return;
   // ---- write back (8 lanes per env)
-  if (l == 0) { S.iters_used[e] = used; S.pgs_cycles[e] = (int)(clock64() - t_begin); S.pgs_trips[e] = (int)(guard0 - guard)
+  if (l == 0) { S.iters_used[e] = used; S.pgs_cycles[e] = (int)(clock64() - t_begin); S.pgs_trips[e] = (int)(guard0 - guard); }
 #ifdef AG_PGS_DEBUG
-      + (all_res ? (1 << 24) : 0)
+  { int tb = dbg_bad; for (int o = 1; o < 8; o <<= 1) tb += __shfl_xor_sync(0xffffffffu, tb, o); if (l == 0) S.pgs_trips[e] = tb * 65536 + (dbg_first & 0xffff); }
 #endif
-      ; }
   const int ND = S.ND;
   for (int a = 0; a < S.nart; a++) {
     int d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a), vo = AG_LDG(S.art_voff + a);
@@ -689,6 +754,82 @@ __device__ __forceinline__ void pgs_warp(const SimDev& S, float* sm, int SA, int
   for (int i = l; i < 3 * cnt; i += 8) { int s = i / 3, c = i - 3 * s; cf_st(S.s_data, s, CF_LAM_N + c, N, e, lam[3 * ND + S.ngr + i]); }
 }
 #endif
+
+// Host restatement of the DEVICE loop of K7 for one env (tests only): the same ring indexing, refill schedule, software
+// pipelining, finished-env parking and lane partition, with the asynchronous copies done synchronously.
+AG_HDN inline void pgs_env_emul(int slot, const SimDev& S, float* sm) {
+  const int RING = 1024, PIECE = 32, KPF = 5;
+  const int e = S.pgs_order[slot];
+  const int N = S.N, ND = S.ND;
+  const int NV = rs_nv(S), NL = rs_nlam(S);
+  float* v = sm; float* lam = v + NV; float* zblk = lam + NL; float* nullrec = zblk + 32; float* ring = nullrec + 32;
+  for (int i = 0; i < NV + NL + 32; i++) v[i] = 0.f;
+  rs_pad_header(S, nullrec, RM_BOX, 0);
+  const float* rs = S.rs_data + (size_t)e * S.rs_cap;
+  const int total = S.rs_nfloats[e];
+  for (int i = 0; i < RING && total > 0; i++) ring[i] = rs[i % total];
+  int ppos = total > 0 ? RING % total : 0, pabs = RING;
+  bool active = total > 0 && S.iters > 0;
+  int it = 0, used = 0, cur = 0, cabs = 0;
+  float H[16], Q[4][8][4];
+  for (int i = 0; i < 16; i++) H[i] = (active ? ring : nullrec)[i];
+  { int nv = f2i_bits(H[0]) & 7; for (int k = 0; k < 4; k++) for (int l = 0; l < 8; l++) for (int c = 0; c < 4; c++) Q[k][l][c] = nv > k ? ring[RS_HDR + k * RS_LB + 4 * l + c] : 0.f; }
+  float resid = 0.f;
+  bool act_lag = true;
+  long guard = (long)S.iters * (S.rs_cap / RS_UNIT + 2) + 16;
+  while (act_lag && --guard > 0) {
+    act_lag = active;
+    const int meta = f2i_bits(H[0]), w1 = f2i_bits(H[1]), w2 = f2i_bits(H[2]), w3 = f2i_bits(H[3]);
+    const int mode = (meta >> 4) & 3, size = (meta >> 8) * RS_UNIT;
+    const int sl[4] = {w1 & 0xffff, w1 >> 16, w2 & 0xffff, w2 >> 16};
+    float* lp1 = lam + (w3 & 0xffff); float* lp2 = lam + (w3 >> 16);
+    const float lam1 = *lp1, lam2 = *lp2, lamn = lam[f2i_bits(H[4])];
+    const bool at_end = active && cur + size >= total;
+    const int next = at_end ? 0 : cur + size;
+    const int nabs = cabs + size;
+    float Hn[16], Qn[4][8][4];
+    for (int i = 0; i < 16; i++) Hn[i] = active ? ring[(nabs + i) & (RING - 1)] : nullrec[i];
+    const int nvn = active ? (f2i_bits(Hn[0]) & 7) : 0;
+    for (int k = 0; k < 4; k++) for (int l = 0; l < 8; l++) for (int c = 0; c < 4; c++) Qn[k][l][c] = nvn > k ? ring[(nabs + RS_HDR + k * RS_LB + 4 * l + c) & (RING - 1)] : 0.f;
+    float p1 = 0.f, p2 = 0.f, x[4][8];
+    for (int l = 0; l < 8; l++) { for (int k = 0; k < 4; k++) x[k][l] = v[sl[k] + l];
+      p1 += (Q[0][l][0] * x[0][l] + Q[1][l][0] * x[1][l]) + (Q[2][l][0] * x[2][l] + Q[3][l][0] * x[3][l]);
+      p2 += (Q[0][l][2] * x[0][l] + Q[1][l][2] * x[1][l]) + (Q[2][l][2] * x[2][l] + Q[3][l][2] * x[3][l]); }
+    for (int j = 0; j < KPF; j++) {
+      const bool on = active && pabs + PIECE <= nabs + RING;
+      if (on) { for (int i = 0; i < PIECE; i++) ring[(pabs + i) & (RING - 1)] = rs[ppos + i]; pabs += PIECE; ppos += PIECE; }
+      ppos = ppos >= total ? 0 : ppos;
+    }
+    v4 hc, hd; hc.x = H[8]; hc.y = H[9]; hc.z = H[10]; hc.w = H[11]; hd.x = H[12]; hd.y = H[13]; hd.z = H[14]; hd.w = H[15];
+    const RsSol r = rs_solve2(mode, S.cone != 0, !active, p1, p2, lam1, lam2, lamn, hc, hd, H[5], H[6]);
+    *lp1 = r.s1; *lp2 = r.s2;
+    for (int k = 0; k < 4; k++) for (int l = 0; l < 8; l++) v[sl[k] + l] = x[k][l] + Q[k][l][1] * r.d1 + Q[k][l][3] * r.d2;
+    resid = fmaxf(resid, fmaxf(r.d1 * r.d1, r.d2 * r.d2));
+    cur = next; cabs = nabs;
+    it += at_end ? 1 : 0;
+    used = at_end ? it : used;
+    active = active && !(at_end && ((S.resid_thr > 0.f && resid <= S.resid_thr) || it >= S.iters));
+    resid = at_end ? 0.f : resid;
+    for (int i = 0; i < 16; i++) H[i] = Hn[i];
+    memcpy(Q, Qn, sizeof(Q));
+  }
+  S.iters_used[e] = used;
+  for (int a = 0; a < S.nart; a++) {
+    int d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a), vo = AG_LDG(S.art_voff + a);
+    for (int i = 0; i < nd; i++) S.dv[(size_t)(d0 + i) * N + e] = v[vo + i];
+  }
+  for (int f = 0; f < S.nf; f++)
+    for (int c = 0; c < 6; c++) S.dv[(size_t)(ND + 6 * f + c) * N + e] = v[S.NDp + 8 * f + c];
+  for (int r = 0; r < 3 * ND; r++) S.dr_lam[(size_t)r * N + e] = lam[r];
+  for (int r = 0; r < S.ngr; r++) S.gr_lam[(size_t)r * N + e] = lam[3 * ND + r];
+  int cnt = S.c_count[e]; if (cnt > S.maxc) cnt = S.maxc;
+  for (int s2 = 0; s2 < cnt; s2++) {
+    const float* ll = lam + 3 * ND + S.ngr + 3 * s2;
+    cf_st(S.s_data, s2, CF_LAM_N, N, e, ll[0]);
+    cf_st(S.s_data, s2, CF_LAM_T1, N, e, ll[1]);
+    cf_st(S.s_data, s2, CF_LAM_T2, N, e, ll[2]);
+  }
+}
 
 // Host restatement of K7 for the kernel-logic harness (tests only): the same stream, records consumed one after the
 // other, entries summed in lane-block order.  `sm`: rs_nv + rs_nlam floats.

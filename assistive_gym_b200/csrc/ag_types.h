@@ -74,7 +74,6 @@ struct SimDev {
   float* dv;                                           // [ND + 6 nf][N]
   float* dr_lam;                                       // [3 ND][N] impulses of the dof rows: lower limit, upper limit, motor
   float* gr_lam;                                       // [ngr][N] impulses of the fixed-constraint rows
-  int rs_area;                                         // floats of K7's per-CTA stream area (four envs share it)
   int* row_off;                                        // [3 ND + ngr][N] record (rs_enc) of each dof / fixed-constraint row (-1: not live)
   int* row_pair;                                       // [3 ND + ngr][N] the row sharing the record of a first row (-1: none)
   float* rs_data; int rs_cap; int* rs_nfloats;         // packed row stream: [N][rs_cap] floats (ag_solver.cuh), used floats [N]

@@ -77,9 +77,10 @@ __global__ void __launch_bounds__(1024) k_order(SimDev S, KP) {
 }
 #else
 static void k_pgs(SimDev S, KP p) {
-  std::vector<float> buf((size_t)rs_nv(S) + rs_nlam(S) + 8);
+  std::vector<float> buf((size_t)rs_env_floats(S) + 8);
   float* base = (float*)(((uintptr_t)buf.data() + 15) & ~(uintptr_t)15);
-  for (int tid = 0; tid < p.n; tid++) pgs_body_host(tid, S, base);
+  static const bool emul = getenv("AG_EMU_PLAIN_PGS") == nullptr;     // default: the restatement of the device loop
+  for (int tid = 0; tid < p.n; tid++) { if (emul) pgs_env_emul(tid, S, base); else pgs_body_host(tid, S, base); }
 }
 static void k_order(SimDev S, KP) {
   int hist[64] = {0};
@@ -143,7 +144,10 @@ static void* dev_alloc(AgSim* s, size_t bytes) {
   if (bytes == 0) bytes = 16;
 #ifndef AG_CPU_EMU
   if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
-  cudaMemset(p, 0, bytes);
+  // zero on the sim's OWN stream: it is a non-blocking stream, so a cudaMemset on the legacy default stream would not be
+  // ordered against the copies / kernels that use the buffer next (a staging buffer grown inside an API call was
+  // sometimes zeroed AFTER the host data had been copied into it)
+  if (s->stream) cudaMemsetAsync(p, 0, bytes, s->stream); else { cudaMemset(p, 0, bytes); cudaDeviceSynchronize(); }
 #else
   p = calloc(1, bytes);
 #endif
@@ -248,6 +252,7 @@ void ag_default_config(AgConfig* c) {
   c->linear_slop = 1e-5; c->residual_threshold = 1e-7; c->contact_threshold = 0.02;
   c->linear_damping = 0.04; c->angular_damping = 0.04; c->max_coord_velocity = 100; c->hull_margin = 0.001;
   c->cone_friction = 1; c->gyroscopic = 1; c->max_contacts = 128;
+  c->warmstart_contact = 0.0; c->warmstart_joint = 0.0;
 }
 
 AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int device) {
@@ -449,17 +454,6 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
     size_t fl = (size_t)(3 * S.ND / 2 + 2) * rs_rec_floats(2) + (size_t)3 * S.ncon * rs_rec_floats(3) + (size_t)S.maxc * 2 * rs_rec_floats(2);
     fl = fl + fl * 3 / 10 + 1024;
     S.rs_cap = (int)((fl + 1023) / 1024 * 1024);
-  }
-  {
-    // K7's stream area: shared memory of an SM split between `k` resident CTAs (four envs each); what a CTA does not
-    // need for velocities and impulses holds the four row streams.  k = 2 keeps ~26 KB per env (FeedingJaco: 22 KB mean).
-    const char* kp = getenv("AG_PGS_CTAS_PER_SM");
-    int k = kp ? atoi(kp) : 2; if (k < 1) k = 1; if (k > 8) k = 8;
-    long budget = (233472 / k - 1024) / 4 - 4L * (rs_nv(S) + rs_nlam(S) + 64) - 8;
-    long need = 4L * S.rs_cap;
-    if (budget > need) budget = need;
-    if (budget < 4 * RS_MAXREC) budget = 4 * RS_MAXREC;
-    S.rs_area = (int)(budget / 64 * 64);
   }
   if (rs_nv(S) + 8 >= 65536 || rs_nlam(S) >= 65536) { g_err = "solver index space exceeds 16 bits: lower max_contacts"; ag_destroy(s); return nullptr; }
   S.rs_data = dalloc<float>(s, (size_t)S.rs_cap * N); S.rs_nfloats = dalloc<int>(s, N);
@@ -677,7 +671,7 @@ static void substep(AgSim* s) {
     if (ps >= 0) prof_mark(s, ps, true);
     k_order<<<1, 1024, 0, s->stream>>>(S, z);
     if (ps >= 0) prof_mark(s, ps, false);
-    KP kp = z; kp.n = N; kp.i0 = S.rs_area;
+    KP kp = z; kp.n = N;
     size_t smem = (size_t)rs_cta_floats(S) * sizeof(float) + 32;
     ps = s->profiling ? prof_slot(s, "k_pgs") : -1;
     if (ps >= 0) prof_mark(s, ps, true);

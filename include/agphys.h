@@ -56,6 +56,10 @@ typedef struct AgConfig {
   int    cone_friction;      /* 1      implicit cone over the 2 friction directions; 0 = pyramid */
   int    gyroscopic;         /* 1      include w x Iw for free bodies */
   int    max_contacts;       /* per-env contact budget for the solver (default 128); overflow is flagged */
+  double warmstart_contact;  /* 0      (Bullet m_warmstartingFactor = 0.85, but its multibody solver of the reference's era does not warm start): a contact that persists (same collider pair, same manifold
+                                       point index) starts the solve from factor * its last normal impulse; 0 disables */
+  double warmstart_joint;    /* 0      the same for joint-limit, motor and fixed-constraint rows (Bullet's multibody solver of
+                                       the reference's era starts these from zero) */
 } AgConfig;
 
 /* Immutable scene template (host arrays, copied by ag_create).  Built on the host by the

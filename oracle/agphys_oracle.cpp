@@ -85,6 +85,9 @@ struct Env {
   std::vector<Contact> contacts;
   int overflow;
   int last_iters;
+  // warm-start cache: impulses of the last solve, keyed by what the row is
+  std::vector<std::pair<unsigned, real>> ws_contacts;   // (collider pair * 4 + manifold point index, normal impulse), ascending key
+  std::vector<real> ws_limit, ws_motor, ws_fixed;       // [2 nl] (lower, upper), [nl], [6 ncon]
 };
 
 struct Row {
@@ -600,8 +603,10 @@ void step_env(const Scene& s, const AgConfig& cfg, Env& e) {
 
     // 3. constraint rows.  Order: joint limits, motors, fixed constraints, contact normals, friction.
     std::vector<Row>& rows = so.rows;
-    std::vector<int> motor_row(s.nl, -1);
+    std::vector<int> motor_row(s.nl, -1), limit_row(2 * s.nl, -1), fixed_row(6 * s.ncon, -1);
     real erp = (real)cfg.erp;
+    const real wsc = (real)cfg.warmstart_contact, wsj = (real)cfg.warmstart_joint;
+    if ((int)e.ws_limit.size() != 2 * s.nl) { e.ws_limit.assign(2 * s.nl, 0); e.ws_motor.assign(s.nl, 0); e.ws_fixed.assign(6 * s.ncon, 0); }
     for (int k = 0; k < s.nl; k++) {     // joint limits: a row only while the limit is violated
       if (!s.link_live[k] || !s.link_haslimit[k] || so.body_off[s.link_body[k]] < 0) continue;
       for (int sgn = 0; sgn < 2; sgn++) {
@@ -615,6 +620,8 @@ void step_env(const Scene& s, const AgConfig& cfg, Env& e) {
         if (!so.finish(r)) continue;
         real rel = so.jv(r, so.vel);
         r.rhs = (-pen * erp / dt - rel) * r.diag_inv; r.lo = 0; r.hi = real(1e30);
+        r.lambda = std::max(real(0), wsj * e.ws_limit[2 * k + sgn]);
+        limit_row[2 * k + sgn] = (int)rows.size();
         rows.push_back(r);
       }
     }
@@ -634,6 +641,7 @@ void step_env(const Scene& s, const AgConfig& cfg, Env& e) {
       if (e.motor_mode[k] == AG_MOTOR_POSITION) vt = e.motor_kp[k] * (e.motor_target[k] - e.q[k]) / dt + qd + e.motor_kd[k] * (0 - qd);
       else vt = e.motor_target[k];
       r.rhs = (vt - so.jv(r, so.vel)) * r.diag_inv; r.lo = -maxi; r.hi = maxi;
+      r.lambda = std::min(maxi, std::max(-maxi, wsj * e.ws_motor[k]));
       motor_row[k] = (int)rows.size();
       rows.push_back(r);
     }
@@ -655,11 +663,18 @@ void step_env(const Scene& s, const AgConfig& cfg, Env& e) {
         if (!so.finish(r)) continue;
         real err = i < 3 ? perr[i] : aerr[i - 3];
         r.rhs = (-err * erp / dt - so.jv(r, so.vel)) * r.diag_inv; r.lo = -maxi; r.hi = maxi;
+        r.lambda = std::min(maxi, std::max(-maxi, wsj * e.ws_fixed[6 * c + i]));
+        fixed_row[6 * c + i] = (int)rows.size();
         rows.push_back(r);
       }
     }
     int first_contact_row = (int)rows.size();
     std::vector<int> crow(e.contacts.size(), -1);
+    std::vector<unsigned> ckeys(e.contacts.size());
+    for (size_t ci = 0, run = 0; ci < e.contacts.size(); ci++) {     // manifold point index = position within the collider pair's run
+      if (ci > 0 && e.contacts[ci].col_a == e.contacts[ci - 1].col_a && e.contacts[ci].col_b == e.contacts[ci - 1].col_b) run++; else run = 0;
+      ckeys[ci] = ((unsigned)e.contacts[ci].col_a * (unsigned)s.nc + (unsigned)e.contacts[ci].col_b) * 4u + (unsigned)run;
+    }
     for (size_t ci = 0; ci < e.contacts.size(); ci++) {
       Contact& c = e.contacts[ci];
       Row r;
@@ -671,6 +686,11 @@ void step_env(const Scene& s, const AgConfig& cfg, Env& e) {
       real poserr, velerr = -rel;
       if (pen > 0) { poserr = 0; velerr -= pen / dt; } else poserr = -pen * (real)cfg.contact_erp / dt;
       r.rhs = (poserr + velerr) * r.diag_inv; r.lo = 0; r.hi = real(1e30);
+      if (wsc > 0) {                      // a persisting contact starts from its last normal impulse
+        unsigned key = ckeys[ci];
+        auto itp = std::lower_bound(e.ws_contacts.begin(), e.ws_contacts.end(), std::make_pair(key, real(-1e30)));
+        if (itp != e.ws_contacts.end() && itp->first == key) r.lambda = wsc * itp->second;
+      }
       crow[ci] = (int)rows.size();
       rows.push_back(r);
     }
@@ -695,6 +715,7 @@ void step_env(const Scene& s, const AgConfig& cfg, Env& e) {
     auto apply = [&](Row& r, real dl) {
       for (int sd = 0; sd < 2; sd++) for (int i = 0; i < r.n[sd]; i++) so.dv[r.off[sd] + i] += r.MiJ[sd][i] * dl;
     };
+    for (int ri = 0; ri < first_friction_row; ri++) if (rows[ri].lambda != 0) apply(rows[ri], rows[ri].lambda);   // warm start
     int iters = 0;
     for (int it = 0; it < cfg.num_solver_iters; it++) {
       real resid = 0;
@@ -756,6 +777,13 @@ void step_env(const Scene& s, const AgConfig& cfg, Env& e) {
       }
     }
     for (int k = 0; k < s.nl; k++) if (motor_row[k] >= 0) e.motor_applied[k] = rows[motor_row[k]].lambda / dt;
+    for (int k = 0; k < s.nl; k++) {
+      e.ws_motor[k] = motor_row[k] >= 0 ? rows[motor_row[k]].lambda : 0;
+      for (int sgn = 0; sgn < 2; sgn++) e.ws_limit[2 * k + sgn] = limit_row[2 * k + sgn] >= 0 ? rows[limit_row[2 * k + sgn]].lambda : 0;
+    }
+    for (int i = 0; i < 6 * s.ncon; i++) e.ws_fixed[i] = fixed_row[i] >= 0 ? rows[fixed_row[i]].lambda : 0;
+    e.ws_contacts.clear();
+    for (size_t ci = 0; ci < e.contacts.size(); ci++) if (crow[ci] >= 0) e.ws_contacts.push_back(std::make_pair(ckeys[ci], rows[crow[ci]].lambda));
     for (size_t ci = 0; ci < e.contacts.size(); ci++) {
       Contact& c = e.contacts[ci];
       if (crow[ci] < 0) continue;
@@ -797,6 +825,7 @@ const char* oracle_last_error() { return g_err.c_str(); }
 
 void oracle_default_config(AgConfig* c) {
   c->dt = 0.02; c->num_substeps = 1; c->num_solver_iters = 50; c->erp = 0.2; c->contact_erp = 0.08;
+  c->warmstart_contact = 0.0; c->warmstart_joint = 0.0;
   c->linear_slop = 1e-5; c->residual_threshold = 1e-7; c->contact_threshold = 0.02;
   c->linear_damping = 0.04; c->angular_damping = 0.04; c->max_coord_velocity = 100; c->hull_margin = 0.001;
   c->cone_friction = 1; c->gyroscopic = 1; c->max_contacts = 128;
