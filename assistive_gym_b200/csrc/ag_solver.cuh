@@ -36,11 +36,12 @@
 #define RS_MAXREC (RS_HDR + 4 * RS_LB)
 // record modes
 enum { RM_BOX = 0, RM_CONE = 1, RM_PAD = 2 };
-// Header (ints are stored as raw bits):
-//   [0] nv | mode << 4 | (record floats / 16) << 8      nv = number of lane blocks (0..4)
-//   [1] slot0 | slot1 << 16   [2] slot2 | slot3 << 16   start index of each block's 8 entries in the velocity vector
-//   [3] li1 | li2 << 16                                  impulse indices of the two rows
-//   [4] lin                                              RM_CONE: impulse index of the contact's normal row
+// Header (ints are stored as raw bits; offsets are BYTE offsets from the start of the env's velocity block in K7's
+// shared memory, where the impulses follow the velocities, so K7 forms an address with one add):
+//   [0] nv | mode << 4 | (record bytes) << 8             nv = number of lane blocks (0..4)
+//   [1] slot0 | slot1 << 16   [2] slot2 | slot3 << 16   each block's 8 entries in the velocity vector (4 * index)
+//   [3] li1 | li2 << 16                                  the two rows' impulses (4 * (rs_nv + index))
+//   [4] lin                                              RM_CONE: impulse of the contact's normal row
 //   [5] w21   [6] mu   [7] -
 //   [8..11] rhs1 dinv1 lo1 hi1   [12..15] rhs2 dinv2 lo2 hi2     (RM_CONE ignores lo/hi)
 // Lane block k, lane l: [J1 M1 J2 M2] of velocity entry slot_k + l.  Unused slots point at the env's null block
@@ -59,8 +60,8 @@ AG_HD int rs_nv(const SimDev& S) { return (S.NDp + 8 * S.nf + 8 + 31) & ~31; }
 AG_HD int rs_dummy(const SimDev& S) { return 3 * S.ND + S.ngr + 3 * S.maxc; }
 AG_HD int rs_nlam(const SimDev& S) { return (3 * S.ND + S.ngr + 3 * S.maxc + 1 + 31) & ~31; }
 // shared memory of a K7 CTA (four envs): per env velocity deltas, impulses, 32 zeros, a null record, the 4 KB stream ring
-AG_HD int rs_env_floats(const SimDev& S) { return rs_nv(S) + rs_nlam(S) + 64 + 1024; }
-AG_HD int rs_cta_floats(const SimDev& S) { return 4 * rs_env_floats(S); }
+AG_HD int rs_env_floats(const SimDev& S) { return rs_nv(S) + rs_nlam(S) + 64 + 1024; }      // (host emulation layout)
+AG_HD int rs_cta_floats(const SimDev& S) { return 1024 + 4 * 1024 + 4 * (rs_nv(S) + rs_nlam(S)); }
 
 // ------------------------------------------------------------------ K6: constraint rows
 // side reference encoding: (idx << 2) | kind, kind: 0 static, 1 free body (idx = f), 2 articulated (idx = dyn link)
@@ -108,6 +109,11 @@ AG_HD RsShape rs_shape(const SimDev& S, int refA, int refB) {
 }
 AG_HD int rs_shape_key(const RsShape& h) { return h.nv == 0 ? -1 : (h.sl[0] | (h.merged ? 0x8000 : 0) | ((h.nB > 0 && !h.merged ? h.offB + 1 : 0) << 16)); }
 AG_HD int rs_rec_floats(int nv) { return RS_HDR + RS_LB * nv; }
+// header encodings
+AG_HD int rs_enc_meta(int nv, int mode, int floats) { return nv | (mode << 4) | ((floats * 4) << 8); }
+AG_HD int rs_enc_slot(int idx) { return idx * 4; }
+AG_HD int rs_enc_lam(const SimDev& S, int li) { return (rs_nv(S) + li) * 4; }
+AG_HD int rs_meta_floats(int meta) { return (meta >> 8) / 4; }
 
 // address of (J, M) of entry i of the side whose first lane block is `slot0`, for row `row` (0 / 1) of record `rec`
 AG_HD float* rs_entry(float* rec, int slot0, int i, int row) { return rec + RS_HDR + (slot0 + (i >> 3)) * RS_LB + (i & 7) * 4 + 2 * row; }
@@ -166,18 +172,19 @@ AG_HD void rs_zero_blocks(float* rec, int nv) {
 // structural part of a header + null second row; the rows' numbers are filled in by rs_set_row
 AG_HD void rs_header(const SimDev& S, float* rec, const RsShape& h, int mode) {
   const int dummy = rs_dummy(S);
-  rec[0] = i2f_bits(h.nv | (mode << 4) | ((rs_rec_floats(h.nv) / RS_UNIT) << 8));
-  rec[1] = i2f_bits(h.sl[0] | (h.sl[1] << 16)); rec[2] = i2f_bits(h.sl[2] | (h.sl[3] << 16));
-  rec[3] = i2f_bits(dummy | (dummy << 16)); rec[4] = i2f_bits(dummy);
+  rec[0] = i2f_bits(rs_enc_meta(h.nv, mode, rs_rec_floats(h.nv)));
+  rec[1] = i2f_bits(rs_enc_slot(h.sl[0]) | (rs_enc_slot(h.sl[1]) << 16)); rec[2] = i2f_bits(rs_enc_slot(h.sl[2]) | (rs_enc_slot(h.sl[3]) << 16));
+  rec[3] = i2f_bits(rs_enc_lam(S, dummy) | (rs_enc_lam(S, dummy) << 16)); rec[4] = i2f_bits(rs_enc_lam(S, dummy));
   for (int i = 5; i < RS_HDR; i++) rec[i] = 0.f;
 }
-AG_HD void rs_set_li(float* rec, int row, int li) {
+AG_HD void rs_set_li(const SimDev& S, float* rec, int row, int li0) {
+  const int li = rs_enc_lam(S, li0);
   int w = f2i_bits(rec[3]);
   w = row == 0 ? ((w & ~0xffff) | li) : ((w & 0xffff) | (li << 16));
   rec[3] = i2f_bits(w);
 }
-AG_HD void rs_set_row(float* rec, int row, int li, float rhs, float dinv, float lo, float hi) {
-  rs_set_li(rec, row, li);
+AG_HD void rs_set_row(const SimDev& S, float* rec, int row, int li, float rhs, float dinv, float lo, float hi) {
+  rs_set_li(S, rec, row, li);
   float* d = rec + 8 + 4 * row;
   d[0] = rhs; d[1] = dinv; d[2] = lo; d[3] = hi;
 }
@@ -190,14 +197,14 @@ AG_HD void rs_null_row(float* rec, int nv, int row) {
 struct RsCur { int pos; float* rs; int capf; bool over; };
 AG_HD void rs_pad_header(const SimDev& S, float* rec, int mode, int floats) {
   const int null = rs_null(S), dummy = rs_dummy(S);
-  rec[0] = i2f_bits(0 | (mode << 4) | ((floats / RS_UNIT) << 8));
-  rec[1] = i2f_bits(null | (null << 16)); rec[2] = rec[1];
-  rec[3] = i2f_bits(dummy | (dummy << 16)); rec[4] = i2f_bits(dummy);
+  rec[0] = i2f_bits(rs_enc_meta(0, mode, floats));
+  rec[1] = i2f_bits(rs_enc_slot(null) | (rs_enc_slot(null) << 16)); rec[2] = rec[1];
+  rec[3] = i2f_bits(rs_enc_lam(S, dummy) | (rs_enc_lam(S, dummy) << 16)); rec[4] = i2f_bits(rs_enc_lam(S, dummy));
   for (int i = 5; i < RS_HDR; i++) rec[i] = 0.f;
 }
 // word i of a null record's header (what rs_pad_header(S, rec, RM_BOX, 0) writes)
 AG_HD float rs_null_word(const SimDev& S, int i) {
-  const int null = rs_null(S), dummy = rs_dummy(S);
+  const int null = rs_enc_slot(rs_null(S)), dummy = rs_enc_lam(S, rs_dummy(S));
   return i == 1 || i == 2 ? i2f_bits(null | (null << 16)) : (i == 3 ? i2f_bits(dummy | (dummy << 16)) : (i == 4 ? i2f_bits(dummy) : i2f_bits(0)));
 }
 AG_HD int rs_alloc(const SimDev&, RsCur& c, int nf) {
@@ -342,9 +349,9 @@ AG_HDN inline void rows_body(int e, const SimDev& S, const KP&) {
 }
 
 // finish a box row after its sides were emitted: diagonal, rhs, bounds; a vanishing diagonal nulls the row
-AG_HD void rs_finish_box(float* rec, int nv, int row, int li, float num, float lo, float hi) {
+AG_HD void rs_finish_box(const SimDev& S, float* rec, int nv, int row, int li, float num, float lo, float hi) {
   float diag = rs_row_diag(rec, nv, row);
-  if (diag > 1e-20f) { float dinv = 1.0f / diag; rs_set_row(rec, row, li, num * dinv, dinv, lo, hi); }
+  if (diag > 1e-20f) { float dinv = 1.0f / diag; rs_set_row(S, rec, row, li, num * dinv, dinv, lo, hi); }
   else rs_null_row(rec, nv, row);
 }
 
@@ -374,7 +381,7 @@ AG_HDN inline void drow_body(int r, int e, const SimDev& S) {
         q[0] = (i == dd[row] - d0) ? R.sgn : 0.f;
         q[1] = R.sgn * S.Minv[((size_t)(d0 + i) * S.ND + dd[row]) * N + e];
       }
-      rs_set_row(rec, row, rr, R.rhs, R.dinv, R.lo, R.hi);
+      rs_set_row(S, rec, row, rr, R.rhs, R.dinv, R.lo, R.hi);
     }
     if (r2 >= 0) rec[5] = sg[0] * sg[1] * S.Minv[((size_t)dd[1] * S.ND + dd[0]) * N + e];
     return;
@@ -406,7 +413,7 @@ AG_HDN inline void drow_body(int r, int e, const SimDev& S) {
     float rel = 0.f;
     emit_side(S, e, refA, pa, lin * sg, ang * sg, rec, 0, row, false, rel);
     emit_side(S, e, refB, pb, lin * (-sg), ang * (-sg), rec, h.slotB, row, h.merged, rel);
-    rs_finish_box(rec, h.nv, row, r + row, -err * S.erp / dt - rel, -maxi, maxi);
+    rs_finish_box(S, rec, h.nv, row, r + row, -err * S.erp / dt - rel, -maxi, maxi);
   }
   if (r2 >= 0) rec[5] = rs_row_w21(rec, h.nv);
 }
@@ -451,7 +458,7 @@ AG_HDN inline void crows_body(int tid, const SimDev& S, const KP&) {
       float pen = dist + S.slop;
       float poserr, velerr = -rel;
       if (pen > 0.f) { poserr = 0.f; velerr -= pen / dt; } else poserr = -pen * S.contact_erp / dt;
-      rs_finish_box(rec, h.nv, row, lam0 + 3 * s, poserr + velerr, 0.f, 1e30f);
+      rs_finish_box(S, rec, h.nv, row, lam0 + 3 * s, poserr + velerr, 0.f, 1e30f);
     }
     if (nrow == 2) rec[5] = rs_row_w21(rec, h.nv);
   }
@@ -474,10 +481,10 @@ AG_HDN inline void crows_body(int tid, const SimDev& S, const KP&) {
       emit_side(S, e, refA, pa, t * sg, f3(), rec, 0, row, false, rel);
       emit_side(S, e, refB, pb, t * (-sg), f3(), rec, h.slotB, row, h.merged, rel);
       float diag = rs_row_diag(rec, h.nv, row);
-      if (diag > 1e-20f) { float dinv = 1.0f / diag; rs_set_row(rec, row, lam0 + 3 * slot + 1 + row, -rel * dinv, dinv, 0.f, 0.f); }
-      else { rs_null_row(rec, h.nv, row); rs_set_li(rec, row, lam0 + 3 * slot + 1 + row); }
+      if (diag > 1e-20f) { float dinv = 1.0f / diag; rs_set_row(S, rec, row, lam0 + 3 * slot + 1 + row, -rel * dinv, dinv, 0.f, 0.f); }
+      else { rs_null_row(rec, h.nv, row); rs_set_li(S, rec, row, lam0 + 3 * slot + 1 + row); }
     }
-    rec[4] = i2f_bits(lam0 + 3 * slot); rec[6] = mu;
+    rec[4] = i2f_bits(rs_enc_lam(S, lam0 + 3 * slot)); rec[6] = mu;
   }
 }
 
@@ -571,177 +578,174 @@ __device__ __forceinline__ float rs_sum8(float x) {            // sum over the 8
   return x;
 }
 struct RsHdr { v4 a, b, c, d; };
-__device__ __forceinline__ RsHdr rs_ld_hdr(const float* p) { RsHdr h; h.a = ldv4(p); h.b = ldv4(p + 4); h.c = ldv4(p + 8); h.d = ldv4(p + 12); return h; }
-// 16-byte asynchronous copy global -> shared by the executing lane (LDGSTS), predicated
-__device__ __forceinline__ void rs_cp16(rs_addr dst, const float* src, bool on) {
-  asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p cp.async.cg.shared.global [%0], [%1], 16; }" :: "r"(dst), "l"(src), "r"((int)on) : "memory");
+// 16-byte asynchronous copy global -> shared by the executing lane (LDGSTS), predicated, with a compile-time byte offset
+template <int OFF> __device__ __forceinline__ void rs_cp16(rs_addr dst, const void* src, bool on) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p cp.async.cg.shared.global [%0+%3], [%1+%3], 16; }" :: "r"(dst), "l"(src), "r"((int)on), "n"(OFF) : "memory");
 }
 __device__ __forceinline__ void rs_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int W> __device__ __forceinline__ void rs_cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(W) : "memory"); }
+// Shared-memory accesses of the K7 loop, as volatile asm on 32-bit shared addresses: they stay in program order (a
+// velocity load must follow the previous record's store to the same entry) and never become generic loads.
+__device__ __forceinline__ float rs_lds(rs_addr a) { float r; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a)); return r; }
+template <int OFF> __device__ __forceinline__ v4 rs_lds4(rs_addr a) {
+  v4 r; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a), "n"(OFF)); return r;
+}
+__device__ __forceinline__ void rs_sts(rs_addr a, float x) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(x)); }
+__device__ __forceinline__ void rs_sts_if(rs_addr a, float x, bool on) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p st.shared.f32 [%0], %1; }" :: "r"(a), "f"(x), "r"((int)on));
+}
+__device__ __forceinline__ void rs_sts4_if(rs_addr a, v4 x, bool on) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %5, 0; @p st.shared.v4.f32 [%0], {%1, %2, %3, %4}; }" :: "r"(a), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w), "r"((int)on));
+}
+__device__ __forceinline__ rs_addr rs_wrap(rs_addr ring, int byte) {        // ring | (byte & 4095): the ring is 4 KB aligned
+  rs_addr r; asm("lop3.b32 %0, %1, 4095, %2, 0xEA;" : "=r"(r) : "r"(byte), "r"(ring)); return r;
+}
 
-#define RS_RING 1024          // floats of an env's stream ring (4 KB)
+#define RS_RING 1024          // floats of an env's stream ring (4 KB, 4 KB aligned)
 #define RS_PIECE 32           // floats per refill piece: 8 lanes x 16 B
-#define RS_KPF 5              // refill pieces per record consumed: 160 floats >= the largest record, so the ring stays full
+#define RS_KPF 6              // refill pieces per record consumed (192 floats > the largest record: the ring stays full)
 #define RS_WAITG 3            // cp.async groups (= records) that may still be in flight
 
-// One warp = four envs (lane group g = lane / 8), lock-step.  Shared memory per env (`sm`): velocity deltas, impulses,
-// 32 zeros, a null record, and a 4 KB ring through which the env's row stream flows once per sweep:
-//   * the first tile of the stream is staged by one TMA bulk copy per env (mbarrier complete_tx),
-//   * from then on every lane copies 16 B pieces with cp.async right behind the consumer (RS_KPF pieces of 128 B per
-//     record and env), so the refill is SIMT-uniform -- no elected lane, no spin loop -- and a record is consumed
+// One record of one env group.  (H, Q): header and lane blocks of the record solved now (loaded one trip earlier);
+// (Hn, Qn): filled with the next record's.  See pgs_warp.
+#define RS_TRIP(H, Q0_, Q1_, Q2_, Q3_, Hn, Qn0_, Qn1_, Qn2_, Qn3_)                                                        \
+  {                                                                                                                       \
+    const int meta = f2i_bits(H.a.x), w1 = f2i_bits(H.a.y), w2 = f2i_bits(H.a.z), w3 = f2i_bits(H.a.w);                   \
+    const int nv = meta & 7, mode = (meta >> 4) & 3;                                                                      \
+    const rs_addr a0 = vbl + (w1 & 0xffff), a1 = vbl + ((unsigned)w1 >> 16), a2 = vbl + (w2 & 0xffff), a3 = vbl + ((unsigned)w2 >> 16); \
+    const rs_addr l1 = vb + (w3 & 0xffff), l2 = vb + ((unsigned)w3 >> 16), ln = vb + f2i_bits(H.b.x);                     \
+    const float x0 = rs_lds(a0), x1 = rs_lds(a1), x2 = rs_lds(a2), x3 = rs_lds(a3);                                       \
+    const float lam1 = rs_lds(l1), lam2 = rs_lds(l2), lamn = rs_lds(ln);                                                  \
+    const int adv = active ? (int)((unsigned)meta >> 8) : 0;                                                              \
+    const int nb = cb + adv;                                                                                              \
+    left -= adv;                                                                                                          \
+    const bool at_end = active && left == 0;                                                                              \
+    left = at_end ? totalB : left;                                                                                        \
+    rs_cp_wait<RS_WAITG>();                                                                                               \
+    __syncwarp();                               /* pieces copied by the other lanes of the group */                       \
+    const rs_addr ha = rs_wrap(ring_s, nb);                                                                               \
+    Hn.a = rs_lds4<0>(ha); Hn.b = rs_lds4<16>(ha); Hn.c = rs_lds4<32>(ha); Hn.d = rs_lds4<48>(ha);                         \
+    float p1 = (Q0_.x * x0 + Q1_.x * x1) + (Q2_.x * x2 + Q3_.x * x3);                                                     \
+    float p2 = (Q0_.z * x0 + Q1_.z * x1) + (Q2_.z * x2 + Q3_.z * x3);                                                     \
+    p1 += __shfl_xor_sync(0xffffffffu, p1, 1); p2 += __shfl_xor_sync(0xffffffffu, p2, 1);                                 \
+    const int bl = nb + cl;                      /* lane blocks of the next record (beyond its nv blocks: finite garbage, times x = 0) */ \
+    Qn0_ = rs_lds4<0>(rs_wrap(ring_s, bl)); Qn1_ = rs_lds4<0>(rs_wrap(ring_s, bl + 128));                                 \
+    Qn2_ = rs_lds4<0>(rs_wrap(ring_s, bl + 256)); Qn3_ = rs_lds4<0>(rs_wrap(ring_s, bl + 384));                           \
+    p1 += __shfl_xor_sync(0xffffffffu, p1, 2); p2 += __shfl_xor_sync(0xffffffffu, p2, 2);                                 \
+    /* refill: everything in front of the next record is consumed; up to RS_KPF pieces of 128 B right behind the */      \
+    /* requests so far, not across the end of the ring or of the sweep (the next trip goes on from there)         */      \
+    {                                                                                                                     \
+      int n = min(min((nb + 4096 - pbyte) >> 7, (4096 - (pbyte & 4095)) >> 7), min((totalB - ppos) >> 7, RS_KPF));       \
+      n = active ? n : 0;                                                                                                 \
+      const rs_addr dst = rs_wrap(ring_s, pbyte) + 16 * l;                                                                \
+      const char* src = rsl + ppos;                                                                                       \
+      rs_cp16<0>(dst, src, n > 0); rs_cp16<128>(dst, src, n > 1); rs_cp16<256>(dst, src, n > 2);                          \
+      rs_cp16<384>(dst, src, n > 3); rs_cp16<512>(dst, src, n > 4); rs_cp16<640>(dst, src, n > 5);                        \
+      rs_cp_commit();                                                                                                     \
+      pbyte += n << 7; ppos += n << 7;                                                                                    \
+      ppos = ppos == totalB ? 0 : ppos;                                                                                   \
+    }                                                                                                                     \
+    p1 += __shfl_xor_sync(0xffffffffu, p1, 4); p2 += __shfl_xor_sync(0xffffffffu, p2, 4);                                 \
+    const RsSol r = rs_solve2(mode, cone_cfg, !active, p1, p2, lam1, lam2, lamn, H.c, H.d, H.b.y, H.b.z);                 \
+    rs_sts(l1, r.s1); rs_sts(l2, r.s2);                                                                                   \
+    rs_sts_if(a0, x0 + Q0_.y * r.d1 + Q0_.w * r.d2, nv > 0);                                                              \
+    rs_sts_if(a1, x1 + Q1_.y * r.d1 + Q1_.w * r.d2, nv > 1);                                                              \
+    rs_sts_if(a2, x2 + Q2_.y * r.d1 + Q2_.w * r.d2, nv > 2);                                                              \
+    rs_sts_if(a3, x3 + Q3_.y * r.d1 + Q3_.w * r.d2, nv > 3);                                                              \
+    resid = fmaxf(resid, fmaxf(r.d1 * r.d1, r.d2 * r.d2));                                                                \
+    it += at_end ? 1 : 0;                                                                                                 \
+    const bool stop = at_end && ((thr > 0.f && resid <= thr) || it >= iters);                                             \
+    resid = at_end ? 0.f : resid;                                                                                         \
+    /* a finished env parks: a null record (size 0) goes where its next record would have been read */                   \
+    rs_sts4_if(ha + 16 * l, nullq, stop && l < 4);                                                                        \
+    active = active && !stop;                                                                                             \
+    cb = nb;                                                                                                              \
+  }
+
+// One warp = four envs (lane group g = lane / 8), lock-step.  Shared memory: per env a 4 KB ring (4 KB aligned) through
+// which the env's row stream flows once per sweep, then per env velocity deltas and impulses:
+//   * the ring is filled by one TMA bulk copy per env (mbarrier complete_tx); a stream shorter than the ring wraps
+//     inside it and is staged by cp.async pieces instead,
+//   * from then on every lane copies 16 B pieces with cp.async right behind the consumer (up to RS_KPF pieces of 128 B
+//     per record and env), so the refill is SIMT-uniform -- no elected lane, no spin loop -- and a record is consumed
 //     RS_WAITG + 1 records after its bytes were requested (cp.async.wait_group).
 // The stream stays in HBM / L2; ~6.5 KB of shared memory per env keep every env of the batch resident at once.
+// There is NO lane-dependent branch in front of the loop's shuffles: a diverged warp executes them on a collective slow
+// path that costs thousands of cycles per record (measured), so everything is selects and predicated instructions.
 __device__ __forceinline__ void pgs_warp(const SimDev& S, float* sm, int, int warp_slot0) {
   const int lane = threadIdx.x & 31, g = lane >> 3, l = lane & 7;
   const int N = S.N;
   const int slot = warp_slot0 + g;
   const bool valid = slot < N;
   const int e = valid ? S.pgs_order[slot] : 0;
-  const int NV = rs_nv(S), NL = rs_nlam(S), EF = rs_env_floats(S);
-  float* v = sm + (size_t)g * EF;
-  float* lam = v + NV;
-  float* zblk = lam + NL;                          // 32 zeros: the lane block of an absent slot; then 16 floats: a null record
-  float* nullrec = zblk + 32;
-  float* ring = nullrec + 32;
-  const rs_addr ring_s = rs_smem_addr(ring);
-  const rs_addr bar = rs_smem_addr(sm + (size_t)4 * EF) + 8 * g;
+  const int NV = rs_nv(S), NL = rs_nlam(S), EF = NV + NL;
+  const rs_addr sm_s = rs_smem_addr(sm);
+  const rs_addr ring0 = (sm_s + 4095u) & ~4095u;                    // the CTA asked for 4 KB of slack
+  const rs_addr ring_s = ring0 + 4096u * g;
+  float* v = (float*)((char*)sm + (ring0 - sm_s) + 4 * 4096) + (size_t)g * EF;
+  const rs_addr vb = rs_smem_addr(v), vbl = vb + 4 * l;
+  const rs_addr bar = rs_smem_addr(v - (size_t)g * EF + (size_t)4 * EF) + 8 * g;
   const long long t_begin = clock64();
-  for (int i = l; i < NV + NL + 32; i += 8) v[i] = 0.f;
+  for (int i = l; i < EF; i += 8) v[i] = 0.f;
   const float* rs = S.rs_data + (size_t)e * S.rs_cap;
+  const char* rsl = (const char*)(rs + 4 * l);
   const int total = valid ? S.rs_nfloats[e] : 0;     // a multiple of RS_PIECE (K6a pads)
+  const int totalB = total > 0 ? total * 4 : 128;
+  v4 nullq;                                          // lane l < 4: quad l of a null record's header
+  nullq.x = rs_null_word(S, 4 * (l & 3)); nullq.y = rs_null_word(S, 4 * (l & 3) + 1); nullq.z = rs_null_word(S, 4 * (l & 3) + 2); nullq.w = rs_null_word(S, 4 * (l & 3) + 3);
   // ---- fill the ring (all of it: the stream repeats every sweep).  A stream of at least a ring: ONE TMA bulk copy;
-  // a shorter one wraps inside the ring: 128 B pieces by cp.async.  No lane-dependent branch anywhere.
+  // a shorter one wraps inside the ring: 128 B pieces by cp.async; an env without rows: zeros and a null record.
   const bool big = total >= RS_RING;
-  for (int i = l; i < 16; i += 8) nullrec[i] = rs_null_word(S, i);
   rs_bar_init_if(bar, l == 0);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
   rs_fetch_if(ring_s, rs, RS_RING * 4, bar, l == 0 && big);
-  int ppos = 0, pabs = 0;
-  for (int j = 0; j < RS_RING / RS_PIECE; j++) {
-    const bool on = !big && total > 0;
-    rs_cp16(ring_s + ((pabs + 4 * l) << 2), rs + ppos + 4 * l, on);
-    pabs += RS_PIECE; ppos += RS_PIECE;
-    ppos = ppos >= total ? 0 : ppos;
+  {
+    int pp = 0;
+    v4 z; z.x = z.y = z.z = z.w = 0.f;
+    for (int j = 0; j < RS_RING / RS_PIECE; j++) {
+      rs_cp16<0>(ring_s + 128 * j + 16 * l, rsl + pp, !big && total > 0);
+      rs_sts4_if(ring_s + 128 * j + 16 * l, z, total == 0);
+      pp += 128; pp = pp >= totalB ? 0 : pp;
+    }
+    rs_cp_commit();
+    rs_cp_wait<0>();
+    __syncwarp();
+    rs_sts4_if(ring_s + 16 * l, nullq, total == 0 && l < 4);
   }
-  rs_cp_commit();
-  rs_cp_wait<0>();
-  ppos = big ? (total == RS_RING ? 0 : RS_RING) : ppos;
-  pabs = RS_RING;
+  int ppos = (RS_RING * 4) % totalB, pbyte = RS_RING * 4;
   { bool ok; do { ok = big ? rs_try_wait(bar, 0) : true; } while (!__all_sync(0xffffffffu, ok)); }   // warp-uniform loop
   __syncwarp();
-  // refill state: `ppos` next stream position to request (wraps at `total`: the next sweep follows seamlessly),
-  // `pabs` the same as a running count = ring position
   bool active = total > 0 && S.iters > 0;
-  int it = 0, used = 0;
-  int cur = 0, cabs = 0;                           // stream position / running count of the record in H, Q
-  const float* zb = zblk + 4 * l;
-  RsHdr H = rs_ld_hdr(active ? ring : nullrec);
-  v4 Q0, Q1, Q2, Q3;
-  {
-    const int nv = f2i_bits(H.a.x) & 7;
-    const float* lb = ring + RS_HDR + 4 * l;
-    Q0 = ldv4(nv > 0 ? lb : zb); Q1 = ldv4(nv > 1 ? lb + RS_LB : zb); Q2 = ldv4(nv > 2 ? lb + 2 * RS_LB : zb); Q3 = ldv4(nv > 3 ? lb + 3 * RS_LB : zb);
-  }
-  __syncwarp();
+  int it = 0, cb = 0, left = totalB;
+  const int cl = 64 + 16 * l;
+  RsHdr HA, HB;
+  v4 QA0, QA1, QA2, QA3, QB0, QB1, QB2, QB3;
+  HA.a = rs_lds4<0>(ring_s); HA.b = rs_lds4<16>(ring_s); HA.c = rs_lds4<32>(ring_s); HA.d = rs_lds4<48>(ring_s);
+  QA0 = rs_lds4<0>(ring_s + cl); QA1 = rs_lds4<128>(ring_s + cl); QA2 = rs_lds4<256>(ring_s + cl); QA3 = rs_lds4<384>(ring_s + cl);
+  HB = HA; QB0 = QA0; QB1 = QA1; QB2 = QA2; QB3 = QA3;
   float resid = 0.f;
   const bool cone_cfg = S.cone != 0;
   const float thr = S.resid_thr;
   const int iters = S.iters;
-  long long guard = (long long)S.iters * (S.rs_cap / RS_UNIT + 2) + 16;     // a corrupt stream must not hang the GPU
-  const long long guard0 = guard;
+  int guard = (S.iters * (S.rs_cap / RS_UNIT + 2) + 16) / 2 + 2;     // a corrupt stream must not hang the GPU
+  const int guard0 = guard;
   bool act_lag = true;
-#ifdef AG_PGS_DEBUG
-  int dbg_bad = 0, dbg_first = -1;
-#endif
-  // The loop body has NO divergent branch (selects and predicated copies only): the warp must be converged at the
-  // shuffles, a diverged warp takes a collective slow path that costs thousands of cycles per record.  It is software
-  // pipelined: record t's header and lane blocks were loaded during record t-1, and the loop condition votes on the
-  // flag of the trip before (one idle trip at the end) so that neither a load nor the vote sits on the dependent chain
+  // The loop is software pipelined -- record t's header and lane blocks were loaded during record t-1 -- and unrolled
+  // by two with the register sets swapped; the loop condition votes on the flag of two trips before (idle trips at the
+  // end), so neither a load nor the vote sits on the dependent chain
   //   LDS v -> fma -> 3 x (shfl, add) -> solve -> fma -> STS v.
   while (__any_sync(0xffffffffu, act_lag) && --guard > 0) {
     act_lag = active;
-    const int meta = f2i_bits(H.a.x), w1 = f2i_bits(H.a.y), w2 = f2i_bits(H.a.z), w3 = f2i_bits(H.a.w);
-    const int mode = (meta >> 4) & 3, size = (meta >> 8) * RS_UNIT;
-    float* vp0 = v + (w1 & 0xffff) + l; float* vp1 = v + (w1 >> 16) + l; float* vp2 = v + (w2 & 0xffff) + l; float* vp3 = v + (w2 >> 16) + l;
-    const float x0 = *vp0, x1 = *vp1, x2 = *vp2, x3 = *vp3;
-    float* lp1 = lam + (w3 & 0xffff); float* lp2 = lam + (w3 >> 16);
-    const float lam1 = *lp1, lam2 = *lp2, lamn = lam[f2i_bits(H.b.x)];
-    const bool at_end = active && cur + size >= total;
-    const int next = at_end ? 0 : cur + size;
-    const int nabs = cabs + size;                    // (a finished env: size 0)
-    // ---- the next record: its bytes were requested at least RS_WAITG + 1 records ago.  Proof: the ring starts full and
-    // a trip refills up to 160 floats while it consumes at most 144, so after every trip the requests reach at least
-    // RS_RING - 63 floats beyond the next record; the record read now ends at most 4 * 144 + 144 = 720 floats beyond
-    // where the next record was four trips ago, i.e. inside what had been requested by then.
-#ifdef AG_PGS_SYNC_ALL
-    rs_cp_wait<0>();
-#else
-    rs_cp_wait<RS_WAITG>();
-#endif
-    __syncwarp();                                    // pieces copied by the other lanes of the group
-    const float* nrec = active ? ring + (nabs & (RS_RING - 1)) : nullrec;
-    RsHdr Hn;
-    Hn.a = ldv4(nrec);
-    Hn.b = ldv4(active ? ring + ((nabs + 4) & (RS_RING - 1)) : nullrec + 4);
-    Hn.c = ldv4(active ? ring + ((nabs + 8) & (RS_RING - 1)) : nullrec + 8);
-    Hn.d = ldv4(active ? ring + ((nabs + 12) & (RS_RING - 1)) : nullrec + 12);
-#ifdef AG_PGS_DEBUG
-    if (active) {
-      const float* gr = rs + next;
-      bool bad = f2i_bits(Hn.a.x) != f2i_bits(gr[0]) || f2i_bits(Hn.a.y) != f2i_bits(gr[1]) || f2i_bits(Hn.d.w) != f2i_bits(gr[15]);
-      if (bad) { dbg_bad++; if (dbg_first < 0) dbg_first = (int)(guard0 - guard); }
-    }
-#endif
-    float p1 = (Q0.x * x0 + Q1.x * x1) + (Q2.x * x2 + Q3.x * x3);
-    float p2 = (Q0.z * x0 + Q1.z * x1) + (Q2.z * x2 + Q3.z * x3);
-    p1 += __shfl_xor_sync(0xffffffffu, p1, 1); p2 += __shfl_xor_sync(0xffffffffu, p2, 1);
-    const int nvn = active ? (f2i_bits(Hn.a.x) & 7) : 0;
-    const int lb0 = nabs + RS_HDR + 4 * l;
-    const v4 Qn0 = ldv4(nvn > 0 ? ring + (lb0 & (RS_RING - 1)) : zb), Qn1 = ldv4(nvn > 1 ? ring + ((lb0 + RS_LB) & (RS_RING - 1)) : zb);
-    const v4 Qn2 = ldv4(nvn > 2 ? ring + ((lb0 + 2 * RS_LB) & (RS_RING - 1)) : zb), Qn3 = ldv4(nvn > 3 ? ring + ((lb0 + 3 * RS_LB) & (RS_RING - 1)) : zb);
-#ifdef AG_PGS_DEBUG
-    if (active) {
-      const float* gq = rs + next + RS_HDR + 4 * l;
-      bool bad = (nvn > 0 && (Qn0.x != gq[0] || Qn0.w != gq[3])) || (nvn > 1 && (Qn1.x != gq[32] || Qn1.w != gq[35])) || (nvn > 2 && Qn2.y != gq[65]) || (nvn > 3 && Qn3.y != gq[97]);
-      if (bad) { dbg_bad++; if (dbg_first < 0) dbg_first = (int)(guard0 - guard); }
-    }
-#endif
-    p1 += __shfl_xor_sync(0xffffffffu, p1, 2); p2 += __shfl_xor_sync(0xffffffffu, p2, 2);
-    // ---- refill: everything in front of the next record is consumed; request up to RS_KPF pieces behind it
-#pragma unroll
-    for (int j = 0; j < RS_KPF; j++) {
-      const bool on = active && pabs + RS_PIECE <= nabs + RS_RING;
-      rs_cp16(ring_s + (((pabs + 4 * l) & (RS_RING - 1)) << 2), rs + ppos + 4 * l, on);
-      pabs += on ? RS_PIECE : 0;
-      ppos += on ? RS_PIECE : 0;
-      ppos = ppos >= total ? 0 : ppos;
-    }
-    rs_cp_commit();
-    p1 += __shfl_xor_sync(0xffffffffu, p1, 4); p2 += __shfl_xor_sync(0xffffffffu, p2, 4);
-    const RsSol r = rs_solve2(mode, cone_cfg, !active, p1, p2, lam1, lam2, lamn, H.c, H.d, H.b.y, H.b.z);
-    *lp1 = r.s1; *lp2 = r.s2;
-    *vp0 = x0 + Q0.y * r.d1 + Q0.w * r.d2;
-    *vp1 = x1 + Q1.y * r.d1 + Q1.w * r.d2;
-    *vp2 = x2 + Q2.y * r.d1 + Q2.w * r.d2;
-    *vp3 = x3 + Q3.y * r.d1 + Q3.w * r.d2;
-    resid = fmaxf(resid, fmaxf(r.d1 * r.d1, r.d2 * r.d2));
-    cur = next; cabs = nabs;
-    // end of a sweep (never for a finished env): selects only
-    it += at_end ? 1 : 0;
-    used = at_end ? it : used;
-    active = active && !(at_end && ((thr > 0.f && resid <= thr) || it >= iters));
-    resid = at_end ? 0.f : resid;
-    H = Hn; Q0 = Qn0; Q1 = Qn1; Q2 = Qn2; Q3 = Qn3;
+    RS_TRIP(HA, QA0, QA1, QA2, QA3, HB, QB0, QB1, QB2, QB3)
+    RS_TRIP(HB, QB0, QB1, QB2, QB3, HA, QA0, QA1, QA2, QA3)
   }
   rs_cp_wait<0>();
   __syncwarp();
   if (!valid) return;
   // ---- write back (8 lanes per env)
-  if (l == 0) { S.iters_used[e] = used; S.pgs_cycles[e] = (int)(clock64() - t_begin); S.pgs_trips[e] = (int)(guard0 - guard); }
-#ifdef AG_PGS_DEBUG
-  { int tb = dbg_bad; for (int o = 1; o < 8; o <<= 1) tb += __shfl_xor_sync(0xffffffffu, tb, o); if (l == 0) S.pgs_trips[e] = tb * 65536 + (dbg_first & 0xffff); }
-#endif
+  float* lam = v + NV;
+  if (l == 0) { S.iters_used[e] = it; S.pgs_cycles[e] = (int)(clock64() - t_begin); S.pgs_trips[e] = 2 * (guard0 - guard); }
   const int ND = S.ND;
   for (int a = 0; a < S.nart; a++) {
     int d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a), vo = AG_LDG(S.art_voff + a);
@@ -756,64 +760,73 @@ __device__ __forceinline__ void pgs_warp(const SimDev& S, float* sm, int, int wa
 #endif
 
 // Host restatement of the DEVICE loop of K7 for one env (tests only): the same ring indexing, refill schedule, software
-// pipelining, finished-env parking and lane partition, with the asynchronous copies done synchronously.
+// pipelining, finished-env parking, "blocks beyond nv are read but multiply zeros" and lane partition, with the
+// asynchronous copies done synchronously.  `sm`: rs_env_floats floats.
 AG_HDN inline void pgs_env_emul(int slot, const SimDev& S, float* sm) {
-  const int RING = 1024, PIECE = 32, KPF = 5;
+  const int RING = 1024, KPF = 6;
   const int e = S.pgs_order[slot];
   const int N = S.N, ND = S.ND;
   const int NV = rs_nv(S), NL = rs_nlam(S);
-  float* v = sm; float* lam = v + NV; float* zblk = lam + NL; float* nullrec = zblk + 32; float* ring = nullrec + 32;
-  for (int i = 0; i < NV + NL + 32; i++) v[i] = 0.f;
-  rs_pad_header(S, nullrec, RM_BOX, 0);
+  float* v = sm; float* lam = v + NV; float* ring = lam + NL + 64;
+  for (int i = 0; i < NV + NL; i++) v[i] = 0.f;
   const float* rs = S.rs_data + (size_t)e * S.rs_cap;
   const int total = S.rs_nfloats[e];
-  for (int i = 0; i < RING && total > 0; i++) ring[i] = rs[i % total];
-  int ppos = total > 0 ? RING % total : 0, pabs = RING;
+  const int totalB = total > 0 ? total * 4 : 128;
+  for (int i = 0; i < RING; i++) ring[i] = total > 0 ? rs[i % total] : 0.f;
+  if (total == 0) for (int i = 0; i < 16; i++) ring[i] = rs_null_word(S, i);
+  int ppos = (RING * 4) % totalB, pbyte = RING * 4;
   bool active = total > 0 && S.iters > 0;
-  int it = 0, used = 0, cur = 0, cabs = 0;
+  int it = 0, cb = 0, left = totalB;
   float H[16], Q[4][8][4];
-  for (int i = 0; i < 16; i++) H[i] = (active ? ring : nullrec)[i];
-  { int nv = f2i_bits(H[0]) & 7; for (int k = 0; k < 4; k++) for (int l = 0; l < 8; l++) for (int c = 0; c < 4; c++) Q[k][l][c] = nv > k ? ring[RS_HDR + k * RS_LB + 4 * l + c] : 0.f; }
+  for (int i = 0; i < 16; i++) H[i] = ring[i];
+  for (int k = 0; k < 4; k++) for (int l = 0; l < 8; l++) for (int c = 0; c < 4; c++) Q[k][l][c] = ring[RS_HDR + k * RS_LB + 4 * l + c];
   float resid = 0.f;
   bool act_lag = true;
   long guard = (long)S.iters * (S.rs_cap / RS_UNIT + 2) + 16;
-  while (act_lag && --guard > 0) {
-    act_lag = active;
+  for (int half = 0; (half & 1) || (act_lag && --guard > 0); half++) {
+    if (!(half & 1)) act_lag = active;                    // the device loop votes once per two trips
     const int meta = f2i_bits(H[0]), w1 = f2i_bits(H[1]), w2 = f2i_bits(H[2]), w3 = f2i_bits(H[3]);
-    const int mode = (meta >> 4) & 3, size = (meta >> 8) * RS_UNIT;
-    const int sl[4] = {w1 & 0xffff, w1 >> 16, w2 & 0xffff, w2 >> 16};
-    float* lp1 = lam + (w3 & 0xffff); float* lp2 = lam + (w3 >> 16);
-    const float lam1 = *lp1, lam2 = *lp2, lamn = lam[f2i_bits(H[4])];
-    const bool at_end = active && cur + size >= total;
-    const int next = at_end ? 0 : cur + size;
-    const int nabs = cabs + size;
+    const int nv = meta & 7, mode = (meta >> 4) & 3;
+    const int sl[4] = {(w1 & 0xffff) / 4, (int)((unsigned)w1 >> 16) / 4, (w2 & 0xffff) / 4, (int)((unsigned)w2 >> 16) / 4};
+    float* lp1 = v + (w3 & 0xffff) / 4; float* lp2 = v + ((unsigned)w3 >> 16) / 4;
+    const float lam1 = *lp1, lam2 = *lp2, lamn = v[f2i_bits(H[4]) / 4];
+    const int adv = active ? (int)((unsigned)meta >> 8) : 0;
+    const int nb = cb + adv;
+    left -= adv;
+    const bool at_end = active && left == 0;
+    left = at_end ? totalB : left;
     float Hn[16], Qn[4][8][4];
-    for (int i = 0; i < 16; i++) Hn[i] = active ? ring[(nabs + i) & (RING - 1)] : nullrec[i];
-    const int nvn = active ? (f2i_bits(Hn[0]) & 7) : 0;
-    for (int k = 0; k < 4; k++) for (int l = 0; l < 8; l++) for (int c = 0; c < 4; c++) Qn[k][l][c] = nvn > k ? ring[(nabs + RS_HDR + k * RS_LB + 4 * l + c) & (RING - 1)] : 0.f;
+    for (int i = 0; i < 16; i++) Hn[i] = ring[((nb / 4) + i) & (RING - 1)];
+    for (int k = 0; k < 4; k++) for (int l = 0; l < 8; l++) for (int c = 0; c < 4; c++) Qn[k][l][c] = ring[((nb / 4) + RS_HDR + k * RS_LB + 4 * l + c) & (RING - 1)];
     float p1 = 0.f, p2 = 0.f, x[4][8];
     for (int l = 0; l < 8; l++) { for (int k = 0; k < 4; k++) x[k][l] = v[sl[k] + l];
       p1 += (Q[0][l][0] * x[0][l] + Q[1][l][0] * x[1][l]) + (Q[2][l][0] * x[2][l] + Q[3][l][0] * x[3][l]);
       p2 += (Q[0][l][2] * x[0][l] + Q[1][l][2] * x[1][l]) + (Q[2][l][2] * x[2][l] + Q[3][l][2] * x[3][l]); }
-    for (int j = 0; j < KPF; j++) {
-      const bool on = active && pabs + PIECE <= nabs + RING;
-      if (on) { for (int i = 0; i < PIECE; i++) ring[(pabs + i) & (RING - 1)] = rs[ppos + i]; pabs += PIECE; ppos += PIECE; }
-      ppos = ppos >= total ? 0 : ppos;
+    {
+      int n = (nb + 4096 - pbyte) >> 7;
+      if (((4096 - (pbyte & 4095)) >> 7) < n) n = (4096 - (pbyte & 4095)) >> 7;
+      if (((totalB - ppos) >> 7) < n) n = (totalB - ppos) >> 7;
+      if (n > KPF) n = KPF;
+      if (!active) n = 0;
+      for (int i = 0; i < 32 * n; i++) ring[((pbyte / 4) + i) & (RING - 1)] = rs[ppos / 4 + i];
+      pbyte += n << 7; ppos += n << 7;
+      ppos = ppos == totalB ? 0 : ppos;
     }
     v4 hc, hd; hc.x = H[8]; hc.y = H[9]; hc.z = H[10]; hc.w = H[11]; hd.x = H[12]; hd.y = H[13]; hd.z = H[14]; hd.w = H[15];
     const RsSol r = rs_solve2(mode, S.cone != 0, !active, p1, p2, lam1, lam2, lamn, hc, hd, H[5], H[6]);
     *lp1 = r.s1; *lp2 = r.s2;
-    for (int k = 0; k < 4; k++) for (int l = 0; l < 8; l++) v[sl[k] + l] = x[k][l] + Q[k][l][1] * r.d1 + Q[k][l][3] * r.d2;
+    for (int k = 0; k < nv; k++) for (int l = 0; l < 8; l++) v[sl[k] + l] = x[k][l] + Q[k][l][1] * r.d1 + Q[k][l][3] * r.d2;
     resid = fmaxf(resid, fmaxf(r.d1 * r.d1, r.d2 * r.d2));
-    cur = next; cabs = nabs;
     it += at_end ? 1 : 0;
-    used = at_end ? it : used;
-    active = active && !(at_end && ((S.resid_thr > 0.f && resid <= S.resid_thr) || it >= S.iters));
+    const bool stop = at_end && ((S.resid_thr > 0.f && resid <= S.resid_thr) || it >= S.iters);
     resid = at_end ? 0.f : resid;
+    if (stop) for (int i = 0; i < 16; i++) ring[((nb / 4) + i) & (RING - 1)] = rs_null_word(S, i);
+    active = active && !stop;
+    cb = nb;
     for (int i = 0; i < 16; i++) H[i] = Hn[i];
     memcpy(Q, Qn, sizeof(Q));
   }
-  S.iters_used[e] = used;
+  S.iters_used[e] = it;
   for (int a = 0; a < S.nart; a++) {
     int d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a), vo = AG_LDG(S.art_voff + a);
     for (int i = 0; i < nd; i++) S.dv[(size_t)(d0 + i) * N + e] = v[vo + i];
@@ -848,14 +861,14 @@ AG_HDN inline void pgs_body_host(int slot, const SimDev& S, float* sm) {
     for (int pos = 0; pos < total;) {
       const float* rec = rs + pos;
       const int meta = f2i_bits(rec[0]), w1 = f2i_bits(rec[1]), w2 = f2i_bits(rec[2]), w3 = f2i_bits(rec[3]);
-      const int nv = meta & 7, mode = (meta >> 4) & 3, size = (meta >> 8) * RS_UNIT;
+      const int nv = meta & 7, mode = (meta >> 4) & 3, size = rs_meta_floats(meta);
       pos += size > 0 ? size : RS_UNIT;
       if (mode == RM_PAD) continue;
-      const int sl[4] = {w1 & 0xffff, w1 >> 16, w2 & 0xffff, w2 >> 16};
+      const int sl[4] = {(w1 & 0xffff) / 4, (w1 >> 16) / 4, (w2 & 0xffff) / 4, (w2 >> 16) / 4};
       float p1 = 0.f, p2 = 0.f;
       for (int kk = 0; kk < nv; kk++) for (int l = 0; l < 8; l++) { const float* q = rec + RS_HDR + kk * RS_LB + 4 * l; float x = v[sl[kk] + l]; p1 += q[0] * x; p2 += q[2] * x; }
-      float* lp1 = lam + (w3 & 0xffff); float* lp2 = lam + (w3 >> 16);
-      RsSol r = rs_solve2(mode, S.cone != 0, false, p1, p2, *lp1, *lp2, lam[f2i_bits(rec[4])], ldv4(rec + 8), ldv4(rec + 12), rec[5], rec[6]);
+      float* lp1 = v + (w3 & 0xffff) / 4; float* lp2 = v + (w3 >> 16) / 4;
+      RsSol r = rs_solve2(mode, S.cone != 0, false, p1, p2, *lp1, *lp2, v[f2i_bits(rec[4]) / 4], ldv4(rec + 8), ldv4(rec + 12), rec[5], rec[6]);
       *lp1 = r.s1; *lp2 = r.s2;
       for (int kk = 0; kk < nv; kk++) for (int l = 0; l < 8; l++) { const float* q = rec + RS_HDR + kk * RS_LB + 4 * l; v[sl[kk] + l] += q[1] * r.d1 + q[3] * r.d2; }
       resid = fmaxf(resid, fmaxf(r.d1 * r.d1, r.d2 * r.d2));
