@@ -128,6 +128,8 @@ def load_library(path=None):
     lib.ag_feeding_set_tremor.argtypes = [vp, vp, vp, vp]
     lib.ag_set_hard_limits.argtypes = [vp, ci, vp, ci]
     lib.ag_feeding_step_dev.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.ag_feeding_step_host_begin.argtypes = [vp, vp]
+    lib.ag_feeding_step_host_end.argtypes = [vp, vp, vp, vp, vp]
     lib.ag_feeding_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.ag_bathing_init.argtypes = [vp, C.POINTER(AgBathingParams), vp, vp, vp]
     lib.ag_bathing_step_dev.argtypes = [vp, vp, vp, vp, vp, vp]
@@ -157,6 +159,6 @@ EXPORTED_SYMBOLS = [
     'ag_set_body_active', 'ag_forward_kinematics', 'ag_set_motor_host', 'ag_set_motor_targets_dev', 'ag_set_motor_targets_host',
     'ag_step', 'ag_get_joint_states', 'ag_get_link_states', 'ag_get_contacts', 'ag_contact_force_sum',
     'ag_closest_points', 'ag_feeding_init', 'ag_feeding_reset_episode', 'ag_feeding_set_tremor', 'ag_set_hard_limits', 'ag_feeding_step_dev', 'ag_ik_solve', 'ag_bathing_init', 'ag_bathing_step_dev', 'ag_bathing_step_host',
-    'ag_feeding_step_host', 'ag_state_size', 'ag_state_get', 'ag_state_set', 'ag_kernel_launches',
+    'ag_feeding_step_host', 'ag_feeding_step_host_begin', 'ag_feeding_step_host_end', 'ag_state_size', 'ag_state_get', 'ag_state_set', 'ag_kernel_launches',
     'ag_overflow_count', 'ag_get_solver_stats', 'ag_get_pgs_cycles', 'ag_get_pgs_trips', 'ag_profile_enable', 'ag_profile_get',
 ]

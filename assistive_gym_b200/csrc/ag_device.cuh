@@ -45,26 +45,25 @@ AG_HD void ld_plane(const float* planes, int k, f3& n, float& d) {
 }
 
 // ------------------------------------------------------------------ K1: forward kinematics
-// One lane per env.  p.i0 != 0: all bodies (reset / after teleports); else only movable bodies.
-AG_HDN inline void fk_body(int e, const SimDev& S, const KP& p) {
+// thread = (body, env), env fastest.  p.i0 != 0: all bodies (reset / after teleports); else only movable bodies.
+AG_HDN inline void fk_body(int tid, const SimDev& S, const KP& p) {
   const int N = S.N;
-  for (int b = 0; b < S.nb; b++) {
-    if (!p.i0 && (AG_LDG(S.body_kind + b) == BK_STATIC || S.body_mode[(size_t)b * N + e] != 1)) continue;   // off / frozen bodies keep their poses
-    int l0 = AG_LDG(S.body_link0 + b), nlk = AG_LDG(S.body_nlinks + b);
-    f3 bp = ld3(S.base_pos, b, N, e);
-    q4 bq = ld4(S.base_quat, b, N, e);
-    st3(S.lpos, l0, N, e, bp); st4(S.lquat, l0, N, e, bq);
-    for (int k = l0 + 1; k < l0 + nlk; k++) {
-      int par = AG_LDG(S.link_parent + k);
-      f3 pp = ld3(S.lpos, par, N, e);
-      q4 pq = ld4(S.lquat, par, N, e);
-      f3 jp = pp + qrot(pq, tv3(S.link_jpos, k));
-      q4 jq = qmul(pq, tv4(S.link_jquat, k));
-      int jt = AG_LDG(S.link_jtype + k);
-      if (jt == 1) jq = qmul(jq, qaxis(tv3(S.link_axis, k), ld1(S.jq, k, N, e)));
-      else if (jt == 2) jp = jp + qrot(jq, tv3(S.link_axis, k) * ld1(S.jq, k, N, e));
-      st3(S.lpos, k, N, e, jp); st4(S.lquat, k, N, e, qnormalize(jq));
-    }
+  const int e = tid % N, b = tid / N;
+  if (!p.i0 && (AG_LDG(S.body_kind + b) == BK_STATIC || S.body_mode[(size_t)b * N + e] != 1)) return;   // off / frozen bodies keep their poses
+  int l0 = AG_LDG(S.body_link0 + b), nlk = AG_LDG(S.body_nlinks + b);
+  f3 bp = ld3(S.base_pos, b, N, e);
+  q4 bq = ld4(S.base_quat, b, N, e);
+  st3(S.lpos, l0, N, e, bp); st4(S.lquat, l0, N, e, bq);
+  for (int k = l0 + 1; k < l0 + nlk; k++) {
+    int par = AG_LDG(S.link_parent + k);
+    f3 pp = ld3(S.lpos, par, N, e);
+    q4 pq = ld4(S.lquat, par, N, e);
+    f3 jp = pp + qrot(pq, tv3(S.link_jpos, k));
+    q4 jq = qmul(pq, tv4(S.link_jquat, k));
+    int jt = AG_LDG(S.link_jtype + k);
+    if (jt == 1) jq = qmul(jq, qaxis(tv3(S.link_axis, k), ld1(S.jq, k, N, e)));
+    else if (jt == 2) jp = jp + qrot(jq, tv3(S.link_axis, k) * ld1(S.jq, k, N, e));
+    st3(S.lpos, k, N, e, jp); st4(S.lquat, k, N, e, qnormalize(jq));
   }
 }
 
@@ -728,28 +727,32 @@ AG_HDN inline void dyn_body(int e, const SimDev& S, const KP&) {
 
 
 // ------------------------------------------------------------------ K8: apply deltas, integrate
-AG_HDN inline void integrate_body(int e, const SimDev& S, const KP&) {
+// `dvf(i)`: solver delta of velocity entry i (dofs first, then 6 per free body); items are dealt to `stride` lanes
+// starting at `first` (the PGS kernel integrates with the 8 lanes of the env's group straight from shared memory,
+// the stand-alone kernel with one lane from S.dv).
+template <class DV>
+AG_HD void integrate_env(int e, const SimDev& S, DV dvf, int first, int stride) {
   const int N = S.N;
   const float dt = S.dt, vmax = S.vmax;
-  for (int f = 0; f < S.nf; f++) {
+  for (int f = first; f < S.nf; f += stride) {
     int b = AG_LDG(S.free_body + f);
     if (S.body_mode[(size_t)b * N + e] != 1) continue;
     int l0 = AG_LDG(S.body_link0 + b);
     int o = S.ND + 6 * f;
     f3 v = ld3(S.base_lin, b, N, e), w = ld3(S.base_ang, b, N, e);
-    v = f3(clampf(v.x + ld1(S.dv, o, N, e), -vmax, vmax), clampf(v.y + ld1(S.dv, o + 1, N, e), -vmax, vmax), clampf(v.z + ld1(S.dv, o + 2, N, e), -vmax, vmax));
-    w = f3(clampf(w.x + ld1(S.dv, o + 3, N, e), -vmax, vmax), clampf(w.y + ld1(S.dv, o + 4, N, e), -vmax, vmax), clampf(w.z + ld1(S.dv, o + 5, N, e), -vmax, vmax));
+    v = f3(clampf(v.x + dvf(o), -vmax, vmax), clampf(v.y + dvf(o + 1), -vmax, vmax), clampf(v.z + dvf(o + 2), -vmax, vmax));
+    w = f3(clampf(w.x + dvf(o + 3), -vmax, vmax), clampf(w.y + dvf(o + 4), -vmax, vmax), clampf(w.z + dvf(o + 5), -vmax, vmax));
     st3(S.base_lin, b, N, e, v); st3(S.base_ang, b, N, e, w);
     f3 com = ld3(S.fcom, f, N, e) + v * dt;
     q4 qn = qnormalize(qmul(qexp(w * dt), ld4(S.base_quat, b, N, e)));
     st4(S.base_quat, b, N, e, qn);
     st3(S.base_pos, b, N, e, com - qrot(qn, tv3(S.link_com, l0)));
   }
-  for (int d = 0; d < S.ND; d++) {
+  for (int d = first; d < S.ND; d += stride) {
     int k = AG_LDG(S.dl_link + d);
     int b = AG_LDG(S.link_body + k);
     if (S.body_mode[(size_t)b * N + e] != 1) continue;
-    float qd = clampf(ld1(S.jqd, k, N, e) + ld1(S.dv, d, N, e), -vmax, vmax);
+    float qd = clampf(ld1(S.jqd, k, N, e) + dvf(d), -vmax, vmax);
     float qn = ld1(S.jq, k, N, e) + dt * qd;
     if (S.hard_limit[k]) {                      // Human.enforce_joint_limits: teleport back, zero velocity
       float lo = AG_LDG(S.link_lower + k), hi = AG_LDG(S.link_upper + k);
@@ -757,7 +760,16 @@ AG_HDN inline void integrate_body(int e, const SimDev& S, const KP&) {
     }
     st1(S.jqd, k, N, e, qd);
     st1(S.jq, k, N, e, qn);
-    st1(S.motor_applied, k, N, e, ld1(S.dr_lam, 2 * S.ND + d, N, e) / dt);
   }
-  S.c_count[e] = S.c_count[e] > S.maxc ? S.maxc : S.c_count[e];
+  if (first == 0) S.c_count[e] = S.c_count[e] > S.maxc ? S.maxc : S.c_count[e];
+}
+struct DvGlobal { const SimDev* S; int e; AG_HD float operator()(int i) const { return S->dv[(size_t)i * S->N + e]; } };
+AG_HDN inline void integrate_body(int e, const SimDev& S, const KP&) {
+  DvGlobal dv; dv.S = &S; dv.e = e;
+  integrate_env(e, S, dv, 0, 1);
+  for (int d = 0; d < S.ND; d++) {
+    int k = AG_LDG(S.dl_link + d);
+    if (S.body_mode[(size_t)AG_LDG(S.link_body + k) * S.N + e] != 1) continue;
+    st1(S.motor_applied, k, S.N, e, ld1(S.dr_lam, 2 * S.ND + d, S.N, e) / S.dt);
+  }
 }

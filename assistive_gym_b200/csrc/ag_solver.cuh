@@ -418,6 +418,57 @@ AG_HDN inline void drow_body(int r, int e, const SimDev& S) {
   if (r2 >= 0) rec[5] = rs_row_w21(rec, h.nv);
 }
 
+// ---- K6b fast path: records whose sides are free bodies (or static): both rows are built in registers and the record
+// goes out as 16-byte stores (header: 4, each lane block: 8) instead of ~90 scattered 4-byte stores and read-backs.
+struct FreeSide { float J[6], M[6], rel; };
+AG_HD FreeSide free_side_zero() { FreeSide r; for (int i = 0; i < 6; i++) { r.J[i] = 0.f; r.M[i] = 0.f; } r.rel = 0.f; return r; }
+// unit force `lin` at world point p on free body `idx` (side reference kind 1); anything else: zeros
+AG_HD FreeSide free_side(const SimDev& S, int e, int ref, f3 p, f3 lin) {
+  FreeSide r = free_side_zero();
+  if ((ref & 3) != 1) return r;
+  const int N = S.N, idx = ref >> 2;
+  int b = AG_LDG(S.free_body + idx);
+  float invm = AG_LDG(S.free_invm + idx);
+  f3 t = cross(p - ld3(S.fcom, idx, N, e), lin);
+  f3 it = mul(ld_Iinv(S, idx, e), t);
+  f3 v = ld3(S.base_lin, b, N, e), w = ld3(S.base_ang, b, N, e);
+  r.rel = dot(lin, v) + dot(t, w);
+  r.J[0] = lin.x; r.J[1] = lin.y; r.J[2] = lin.z; r.J[3] = t.x; r.J[4] = t.y; r.J[5] = t.z;
+  r.M[0] = lin.x * invm; r.M[1] = lin.y * invm; r.M[2] = lin.z * invm; r.M[3] = it.x; r.M[4] = it.y; r.M[5] = it.z;
+  return r;
+}
+AG_HD float fs_dot(const FreeSide& a, const FreeSide& b) {        // a.J . b.M
+  float d = 0.f;
+  for (int i = 0; i < 6; i++) d += a.J[i] * b.M[i];
+  return d;
+}
+AG_HD void rs_put_free_block(float* blk, const FreeSide& r1, const FreeSide& r2) {
+  for (int i = 0; i < 6; i++) { v4 q; q.x = r1.J[i]; q.y = r1.M[i]; q.z = r2.J[i]; q.w = r2.M[i]; stv4(blk + 4 * i, q); }
+  v4 z; z.x = z.y = z.z = z.w = 0.f;
+  stv4(blk + 24, z); stv4(blk + 28, z);
+}
+// header of a record in registers
+struct RsHead { float w[RS_HDR]; };
+AG_HD RsHead rs_head(const SimDev& S, const RsShape& h, int mode) {
+  RsHead H;
+  const int dummy = rs_enc_lam(S, rs_dummy(S));
+  H.w[0] = i2f_bits(rs_enc_meta(h.nv, mode, rs_rec_floats(h.nv)));
+  H.w[1] = i2f_bits(rs_enc_slot(h.sl[0]) | (rs_enc_slot(h.sl[1]) << 16)); H.w[2] = i2f_bits(rs_enc_slot(h.sl[2]) | (rs_enc_slot(h.sl[3]) << 16));
+  H.w[3] = i2f_bits(dummy | (dummy << 16)); H.w[4] = i2f_bits(dummy);
+  for (int i = 5; i < RS_HDR; i++) H.w[i] = 0.f;
+  return H;
+}
+AG_HD void rs_head_row(const SimDev& S, RsHead& H, int row, int li0, float rhs, float dinv, float lo, float hi) {
+  const int li = rs_enc_lam(S, li0);
+  int w = f2i_bits(H.w[3]);
+  w = row == 0 ? ((w & ~0xffff) | li) : ((w & 0xffff) | (li << 16));
+  H.w[3] = i2f_bits(w);
+  H.w[8 + 4 * row] = rhs; H.w[9 + 4 * row] = dinv; H.w[10 + 4 * row] = lo; H.w[11 + 4 * row] = hi;
+}
+AG_HD void rs_head_store(float* rec, const RsHead& H) {
+  for (int i = 0; i < 4; i++) { v4 q; q.x = H.w[4 * i]; q.y = H.w[4 * i + 1]; q.z = H.w[4 * i + 2]; q.w = H.w[4 * i + 3]; stv4(rec + 4 * i, q); }
+}
+
 // K6b: thread = (row, env): rows [0, maxc) are the sorted contacts, rows [maxc, maxc + 3 ND + ngr) the dof and
 // fixed-constraint rows.  The thread of contact s writes the normal record that STARTS at s (one or two rows) and the
 // friction record of s.
@@ -436,36 +487,65 @@ AG_HDN inline void crows_body(int tid, const SimDev& S, const KP&) {
   float* rs = S.rs_data + (size_t)e * S.rs_cap;
   const float dt = S.dt;
   const int lam0 = 3 * S.ND + S.ngr;
+  const bool fast = (refA & 3) == 1 && (refB & 3) != 2;      // sides: a free body and (nothing | a free body)
   if (!(info & 1)) {
     float* rec = rs + (size_t)(info >> 2) * RS_UNIT;
-    rs_header(S, rec, h, RM_BOX);
-    rs_zero_blocks(rec, h.nv);
     const int nrow = (info & 2) ? 2 : 1;
-    for (int row = 0; row < nrow; row++) {
-      const int s = slot + row;
-      f3 pa(cf_ld(S.s_data, s, CF_PAX, N, e), cf_ld(S.s_data, s, CF_PAY, N, e), cf_ld(S.s_data, s, CF_PAZ, N, e));
-      f3 pb(cf_ld(S.s_data, s, CF_PBX, N, e), cf_ld(S.s_data, s, CF_PBY, N, e), cf_ld(S.s_data, s, CF_PBZ, N, e));
-      f3 n(cf_ld(S.s_data, s, CF_NX, N, e), cf_ld(S.s_data, s, CF_NY, N, e), cf_ld(S.s_data, s, CF_NZ, N, e));
-      float dist = cf_ld(S.s_data, s, CF_DIST, N, e);
-      // the row's own sides (the partner contact touches the same bodies, but maybe other links of an articulation);
-      // K4 may have swapped them (rs_swap_sides): the J entries carry the sign
-      const int rA = S.s_ref[(size_t)s * 4 * N + e], rB0 = S.s_ref[(size_t)s * 4 * N + e + N];
-      float sg = 1.f;
-      if (rB0 & (1 << 30)) { f3 tp = pa; pa = pb; pb = tp; sg = -1.f; }
-      float rel = 0.f;
-      emit_side(S, e, rA, pa, n * sg, f3(), rec, 0, row, false, rel);
-      emit_side(S, e, rB0 & ~(1 << 30), pb, n * (-sg), f3(), rec, h.slotB, row, h.merged, rel);
-      float pen = dist + S.slop;
-      float poserr, velerr = -rel;
-      if (pen > 0.f) { poserr = 0.f; velerr -= pen / dt; } else poserr = -pen * S.contact_erp / dt;
-      rs_finish_box(S, rec, h.nv, row, lam0 + 3 * s, poserr + velerr, 0.f, 1e30f);
+    if (fast) {
+      RsHead H = rs_head(S, h, RM_BOX);
+      FreeSide a[2], b[2];
+      a[1] = free_side_zero(); b[1] = free_side_zero();
+#pragma unroll
+      for (int row = 0; row < 2; row++) {
+        if (row >= nrow) break;
+        const int s = slot + row;
+        f3 pa(cf_ld(S.s_data, s, CF_PAX, N, e), cf_ld(S.s_data, s, CF_PAY, N, e), cf_ld(S.s_data, s, CF_PAZ, N, e));
+        f3 pb(cf_ld(S.s_data, s, CF_PBX, N, e), cf_ld(S.s_data, s, CF_PBY, N, e), cf_ld(S.s_data, s, CF_PBZ, N, e));
+        f3 n(cf_ld(S.s_data, s, CF_NX, N, e), cf_ld(S.s_data, s, CF_NY, N, e), cf_ld(S.s_data, s, CF_NZ, N, e));
+        float dist = cf_ld(S.s_data, s, CF_DIST, N, e);
+        const int rA = S.s_ref[(size_t)s * 4 * N + e], rB0 = S.s_ref[(size_t)s * 4 * N + e + N];
+        float sg = 1.f;
+        if (rB0 & (1 << 30)) { f3 tp = pa; pa = pb; pb = tp; sg = -1.f; }
+        a[row] = free_side(S, e, rA, pa, n * sg); b[row] = free_side(S, e, rB0 & ~(1 << 30), pb, n * (-sg));
+        float diag = fs_dot(a[row], a[row]) + fs_dot(b[row], b[row]);
+        float rel = a[row].rel + b[row].rel;
+        float pen = dist + S.slop;
+        float poserr, velerr = -rel;
+        if (pen > 0.f) { poserr = 0.f; velerr -= pen / dt; } else poserr = -pen * S.contact_erp / dt;
+        if (diag > 1e-20f) { float dinv = 1.0f / diag; rs_head_row(S, H, row, lam0 + 3 * s, (poserr + velerr) * dinv, dinv, 0.f, 1e30f); }
+        else { a[row] = free_side_zero(); b[row] = free_side_zero(); }
+      }
+      if (nrow == 2) H.w[5] = fs_dot(a[1], a[0]) + fs_dot(b[1], b[0]);
+      rs_head_store(rec, H);
+      rs_put_free_block(rec + RS_HDR, a[0], a[1]);
+      if (h.nv > 1) rs_put_free_block(rec + RS_HDR + RS_LB, b[0], b[1]);
+    } else {
+      rs_header(S, rec, h, RM_BOX);
+      rs_zero_blocks(rec, h.nv);
+      for (int row = 0; row < nrow; row++) {
+        const int s = slot + row;
+        f3 pa(cf_ld(S.s_data, s, CF_PAX, N, e), cf_ld(S.s_data, s, CF_PAY, N, e), cf_ld(S.s_data, s, CF_PAZ, N, e));
+        f3 pb(cf_ld(S.s_data, s, CF_PBX, N, e), cf_ld(S.s_data, s, CF_PBY, N, e), cf_ld(S.s_data, s, CF_PBZ, N, e));
+        f3 n(cf_ld(S.s_data, s, CF_NX, N, e), cf_ld(S.s_data, s, CF_NY, N, e), cf_ld(S.s_data, s, CF_NZ, N, e));
+        float dist = cf_ld(S.s_data, s, CF_DIST, N, e);
+        // the row's own sides (the partner contact touches the same bodies, but maybe other links of an articulation);
+        // K4 may have swapped them (rs_swap_sides): the J entries carry the sign
+        const int rA = S.s_ref[(size_t)s * 4 * N + e], rB0 = S.s_ref[(size_t)s * 4 * N + e + N];
+        float sg = 1.f;
+        if (rB0 & (1 << 30)) { f3 tp = pa; pa = pb; pb = tp; sg = -1.f; }
+        float rel = 0.f;
+        emit_side(S, e, rA, pa, n * sg, f3(), rec, 0, row, false, rel);
+        emit_side(S, e, rB0 & ~(1 << 30), pb, n * (-sg), f3(), rec, h.slotB, row, h.merged, rel);
+        float pen = dist + S.slop;
+        float poserr, velerr = -rel;
+        if (pen > 0.f) { poserr = 0.f; velerr -= pen / dt; } else poserr = -pen * S.contact_erp / dt;
+        rs_finish_box(S, rec, h.nv, row, lam0 + 3 * s, poserr + velerr, 0.f, 1e30f);
+      }
+      if (nrow == 2) rec[5] = rs_row_w21(rec, h.nv);
     }
-    if (nrow == 2) rec[5] = rs_row_w21(rec, h.nv);
   }
   if (of >= 0) {
     float* rec = rs + (size_t)of * RS_UNIT;
-    rs_header(S, rec, h, RM_CONE);
-    rs_zero_blocks(rec, h.nv);
     f3 pa(cf_ld(S.s_data, slot, CF_PAX, N, e), cf_ld(S.s_data, slot, CF_PAY, N, e), cf_ld(S.s_data, slot, CF_PAZ, N, e));
     f3 pb(cf_ld(S.s_data, slot, CF_PBX, N, e), cf_ld(S.s_data, slot, CF_PBY, N, e), cf_ld(S.s_data, slot, CF_PBZ, N, e));
     f3 n(cf_ld(S.s_data, slot, CF_NX, N, e), cf_ld(S.s_data, slot, CF_NY, N, e), cf_ld(S.s_data, slot, CF_NZ, N, e));
@@ -475,16 +555,36 @@ AG_HDN inline void crows_body(int tid, const SimDev& S, const KP&) {
     int ka = AG_LDG(S.col_link + (int)(pairk / (unsigned)S.nc)), kb = AG_LDG(S.col_link + (int)(pairk % (unsigned)S.nc));
     float mu = ld1(S.friction, ka, N, e) * ld1(S.friction, kb, N, e);
     f3 t1, t2; plane_space(n, t1, t2);
-    for (int row = 0; row < 2; row++) {
-      f3 t = row == 0 ? t1 : t2;
-      float rel = 0.f;
-      emit_side(S, e, refA, pa, t * sg, f3(), rec, 0, row, false, rel);
-      emit_side(S, e, refB, pb, t * (-sg), f3(), rec, h.slotB, row, h.merged, rel);
-      float diag = rs_row_diag(rec, h.nv, row);
-      if (diag > 1e-20f) { float dinv = 1.0f / diag; rs_set_row(S, rec, row, lam0 + 3 * slot + 1 + row, -rel * dinv, dinv, 0.f, 0.f); }
-      else { rs_null_row(rec, h.nv, row); rs_set_li(S, rec, row, lam0 + 3 * slot + 1 + row); }
+    if (fast) {
+      RsHead H = rs_head(S, h, RM_CONE);
+      FreeSide a[2], b[2];
+#pragma unroll
+      for (int row = 0; row < 2; row++) {
+        f3 t = row == 0 ? t1 : t2;
+        a[row] = free_side(S, e, refA, pa, t * sg); b[row] = free_side(S, e, refB, pb, t * (-sg));
+        float diag = fs_dot(a[row], a[row]) + fs_dot(b[row], b[row]);
+        float rel = a[row].rel + b[row].rel;
+        if (diag > 1e-20f) { float dinv = 1.0f / diag; rs_head_row(S, H, row, lam0 + 3 * slot + 1 + row, -rel * dinv, dinv, 0.f, 0.f); }
+        else { a[row] = free_side_zero(); b[row] = free_side_zero(); rs_head_row(S, H, row, lam0 + 3 * slot + 1 + row, 0.f, 0.f, 0.f, 0.f); }
+      }
+      H.w[4] = i2f_bits(rs_enc_lam(S, lam0 + 3 * slot)); H.w[6] = mu;
+      rs_head_store(rec, H);
+      rs_put_free_block(rec + RS_HDR, a[0], a[1]);
+      if (h.nv > 1) rs_put_free_block(rec + RS_HDR + RS_LB, b[0], b[1]);
+    } else {
+      rs_header(S, rec, h, RM_CONE);
+      rs_zero_blocks(rec, h.nv);
+      for (int row = 0; row < 2; row++) {
+        f3 t = row == 0 ? t1 : t2;
+        float rel = 0.f;
+        emit_side(S, e, refA, pa, t * sg, f3(), rec, 0, row, false, rel);
+        emit_side(S, e, refB, pb, t * (-sg), f3(), rec, h.slotB, row, h.merged, rel);
+        float diag = rs_row_diag(rec, h.nv, row);
+        if (diag > 1e-20f) { float dinv = 1.0f / diag; rs_set_row(S, rec, row, lam0 + 3 * slot + 1 + row, -rel * dinv, dinv, 0.f, 0.f); }
+        else { rs_null_row(rec, h.nv, row); rs_set_li(S, rec, row, lam0 + 3 * slot + 1 + row); }
+      }
+      rec[4] = i2f_bits(rs_enc_lam(S, lam0 + 3 * slot)); rec[6] = mu;
     }
-    rec[4] = i2f_bits(rs_enc_lam(S, lam0 + 3 * slot)); rec[6] = mu;
   }
 }
 
@@ -523,7 +623,8 @@ AG_HD RsSol rs_solve2(int mode, bool cone_cfg, bool dead, float p1, float p2, fl
   const float m2 = c1 * c1 + c2 * c2;
   const bool scale = can_scale && m2 > lim2;
 #if defined(__CUDA_ARCH__)
-  const float kk = scale ? lim * rsqrtf(m2) : 1.0f;
+  float rq; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rq) : "f"(m2));     // (scale => m2 > lim^2 >= 0; a denormal m2 cannot exceed a normal lim^2, and lim = 0 with a denormal m2 gives 0 * big = 0)
+  const float kk = scale ? lim * rq : 1.0f;
 #else
   const float kk = scale ? lim / sqrtf(m2) : 1.0f;
 #endif
@@ -590,6 +691,13 @@ __device__ __forceinline__ float rs_lds(rs_addr a) { float r; asm volatile("ld.s
 template <int OFF> __device__ __forceinline__ v4 rs_lds4(rs_addr a) {
   v4 r; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a), "n"(OFF)); return r;
 }
+__device__ __forceinline__ float rs_lds_if(rs_addr a, bool on) {            // 0 if not `on`
+  float r; asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; mov.f32 %0, 0f00000000; @p ld.shared.f32 %0, [%1]; }" : "=f"(r) : "r"(a), "r"((int)on)); return r;
+}
+__device__ __forceinline__ v4 rs_lds4_if(rs_addr a, bool on) {              // zeros if not `on`
+  v4 r; asm volatile("{ .reg .pred p; setp.ne.b32 p, %5, 0; mov.f32 %0, 0f00000000; mov.f32 %1, 0f00000000; mov.f32 %2, 0f00000000; mov.f32 %3, 0f00000000;\n"
+                     "  @p ld.shared.v4.f32 {%0, %1, %2, %3}, [%4]; }" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a), "r"((int)on)); return r;
+}
 __device__ __forceinline__ void rs_sts(rs_addr a, float x) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(x)); }
 __device__ __forceinline__ void rs_sts_if(rs_addr a, float x, bool on) {
   asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p st.shared.f32 [%0], %1; }" :: "r"(a), "f"(x), "r"((int)on));
@@ -614,7 +722,7 @@ __device__ __forceinline__ rs_addr rs_wrap(rs_addr ring, int byte) {        // r
     const int nv = meta & 7, mode = (meta >> 4) & 3;                                                                      \
     const rs_addr a0 = vbl + (w1 & 0xffff), a1 = vbl + ((unsigned)w1 >> 16), a2 = vbl + (w2 & 0xffff), a3 = vbl + ((unsigned)w2 >> 16); \
     const rs_addr l1 = vb + (w3 & 0xffff), l2 = vb + ((unsigned)w3 >> 16), ln = vb + f2i_bits(H.b.x);                     \
-    const float x0 = rs_lds(a0), x1 = rs_lds(a1), x2 = rs_lds(a2), x3 = rs_lds(a3);                                       \
+    const float x0 = rs_lds_if(a0, nv > 0), x1 = rs_lds_if(a1, nv > 1), x2 = rs_lds_if(a2, nv > 2), x3 = rs_lds_if(a3, nv > 3); \
     const float lam1 = rs_lds(l1), lam2 = rs_lds(l2), lamn = rs_lds(ln);                                                  \
     const int adv = active ? (int)((unsigned)meta >> 8) : 0;                                                              \
     const int nb = cb + adv;                                                                                              \
@@ -628,9 +736,6 @@ __device__ __forceinline__ rs_addr rs_wrap(rs_addr ring, int byte) {        // r
     float p1 = (Q0_.x * x0 + Q1_.x * x1) + (Q2_.x * x2 + Q3_.x * x3);                                                     \
     float p2 = (Q0_.z * x0 + Q1_.z * x1) + (Q2_.z * x2 + Q3_.z * x3);                                                     \
     p1 += __shfl_xor_sync(0xffffffffu, p1, 1); p2 += __shfl_xor_sync(0xffffffffu, p2, 1);                                 \
-    const int bl = nb + cl;                      /* lane blocks of the next record (beyond its nv blocks: finite garbage, times x = 0) */ \
-    Qn0_ = rs_lds4<0>(rs_wrap(ring_s, bl)); Qn1_ = rs_lds4<0>(rs_wrap(ring_s, bl + 128));                                 \
-    Qn2_ = rs_lds4<0>(rs_wrap(ring_s, bl + 256)); Qn3_ = rs_lds4<0>(rs_wrap(ring_s, bl + 384));                           \
     p1 += __shfl_xor_sync(0xffffffffu, p1, 2); p2 += __shfl_xor_sync(0xffffffffu, p2, 2);                                 \
     /* refill: everything in front of the next record is consumed; up to RS_KPF pieces of 128 B right behind the */      \
     /* requests so far, not across the end of the ring or of the sweep (the next trip goes on from there)         */      \
@@ -660,6 +765,13 @@ __device__ __forceinline__ rs_addr rs_wrap(rs_addr ring, int byte) {        // r
     rs_sts4_if(ha + 16 * l, nullq, stop && l < 4);                                                                        \
     active = active && !stop;                                                                                             \
     cb = nb;                                                                                                              \
+    /* lane blocks of the next record, last: its header has long arrived, so only its nv blocks are fetched */           \
+    {                                                                                                                     \
+      const int nvn = f2i_bits(Hn.a.x) & 7;                                                                               \
+      const int bl = nb + cl;                                                                                             \
+      Qn0_ = rs_lds4_if(rs_wrap(ring_s, bl), nvn > 0); Qn1_ = rs_lds4_if(rs_wrap(ring_s, bl + 128), nvn > 1);             \
+      Qn2_ = rs_lds4_if(rs_wrap(ring_s, bl + 256), nvn > 2); Qn3_ = rs_lds4_if(rs_wrap(ring_s, bl + 384), nvn > 3);       \
+    }                                                                                                                     \
   }
 
 // One warp = four envs (lane group g = lane / 8), lock-step.  Shared memory: per env a 4 KB ring (4 KB aligned) through
@@ -722,7 +834,7 @@ __device__ __forceinline__ void pgs_warp(const SimDev& S, float* sm, int, int wa
   RsHdr HA, HB;
   v4 QA0, QA1, QA2, QA3, QB0, QB1, QB2, QB3;
   HA.a = rs_lds4<0>(ring_s); HA.b = rs_lds4<16>(ring_s); HA.c = rs_lds4<32>(ring_s); HA.d = rs_lds4<48>(ring_s);
-  QA0 = rs_lds4<0>(ring_s + cl); QA1 = rs_lds4<128>(ring_s + cl); QA2 = rs_lds4<256>(ring_s + cl); QA3 = rs_lds4<384>(ring_s + cl);
+  { const int nv0 = f2i_bits(HA.a.x) & 7; QA0 = rs_lds4_if(ring_s + cl, nv0 > 0); QA1 = rs_lds4_if(ring_s + cl + 128, nv0 > 1); QA2 = rs_lds4_if(ring_s + cl + 256, nv0 > 2); QA3 = rs_lds4_if(ring_s + cl + 384, nv0 > 3); }
   HB = HA; QB0 = QA0; QB1 = QA1; QB2 = QA2; QB3 = QA3;
   float resid = 0.f;
   const bool cone_cfg = S.cone != 0;
@@ -743,19 +855,24 @@ __device__ __forceinline__ void pgs_warp(const SimDev& S, float* sm, int, int wa
   rs_cp_wait<0>();
   __syncwarp();
   if (!valid) return;
-  // ---- write back (8 lanes per env)
+  // ---- write back and integrate (8 lanes per env): impulses for the read-back calls, then K8 straight from shared memory
   float* lam = v + NV;
   if (l == 0) { S.iters_used[e] = it; S.pgs_cycles[e] = (int)(clock64() - t_begin); S.pgs_trips[e] = 2 * (guard0 - guard); }
   const int ND = S.ND;
-  for (int a = 0; a < S.nart; a++) {
-    int d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a), vo = AG_LDG(S.art_voff + a);
-    for (int i = l; i < nd; i += 8) S.dv[(size_t)(d0 + i) * N + e] = v[vo + i];
-  }
-  for (int i = l; i < 6 * S.nf; i += 8) { int f = i / 6, c = i - 6 * f; S.dv[(size_t)(ND + i) * N + e] = v[S.NDp + 8 * f + c]; }
-  for (int r = l; r < 3 * ND; r += 8) S.dr_lam[(size_t)r * N + e] = lam[r];
   for (int r = l; r < S.ngr; r += 8) S.gr_lam[(size_t)r * N + e] = lam[3 * ND + r];
   int cnt = S.c_count[e]; if (cnt > S.maxc) cnt = S.maxc;
   for (int i = l; i < 3 * cnt; i += 8) { int s = i / 3, c = i - 3 * s; cf_st(S.s_data, s, CF_LAM_N + c, N, e, lam[3 * ND + S.ngr + i]); }
+  for (int d = l; d < ND; d += 8) {
+    int k = AG_LDG(S.dl_link + d);
+    if (S.body_mode[(size_t)AG_LDG(S.link_body + k) * N + e] == 1) st1(S.motor_applied, k, N, e, lam[2 * ND + d] / S.dt);
+  }
+  __syncwarp();                                    // c_count is clamped by lane 0 of the group in integrate_env
+  struct DvShared { const float* v; const SimDev* S; __device__ __forceinline__ float operator()(int i) const {
+    // entry i of the solver's velocity vector: dof d -> its articulation's block, free body f -> its 8-float block
+    if (i >= S->ND) { int f = (i - S->ND) / 6, c = (i - S->ND) - 6 * f; return v[S->NDp + 8 * f + c]; }
+    int a = AG_LDG(S->dl_art + i); return v[AG_LDG(S->art_voff + a) + (i - AG_LDG(S->art_dl0 + a))];
+  } } dvs; dvs.v = v; dvs.S = &S;
+  integrate_env(e, S, dvs, l, 8);
 }
 #endif
 

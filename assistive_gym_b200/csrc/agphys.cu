@@ -125,7 +125,7 @@ struct AgSim {
   float *d_action, *d_obs, *d_reward, *d_done, *d_info;
   float *h_pin_in, *h_pin_out;
   // CUDA-graph replay of the fused env step (one graph per entry point, keyed by its device pointers)
-  bool use_graph;
+  bool use_graph; int graph_failures;
   struct StepGraph { void* exec; const void* key[5]; uint64_t launches; bool valid; } graphs[2];
   // profiling
   bool profiling;
@@ -230,6 +230,25 @@ static void prof_mark(AgSim* s, int slot, bool begin) {
 
 static KP kp0() { KP p; memset(&p, 0, sizeof(p)); return p; }
 
+// Every entry point runs against the sim's own GPU and leaves the caller's current device untouched (a learner may keep
+// torch on cuda:0 while a sim lives on cuda:1; allocations, launches and graph replays must not land on the wrong one).
+struct DevGuard {
+  int prev;
+  explicit DevGuard(int device) : prev(-1) {
+#ifndef AG_CPU_EMU
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) cudaSetDevice(device); else prev = -1;
+#else
+    (void)device;
+#endif
+  }
+  ~DevGuard() {
+#ifndef AG_CPU_EMU
+    if (prev >= 0) cudaSetDevice(prev);
+#endif
+  }
+};
+
 // ------------------------------------------------------------------ quaternion helpers on the host (double)
 struct HQ { double x, y, z, w; };
 static HQ hq_mul(HQ a, HQ b) {
@@ -257,13 +276,14 @@ void ag_default_config(AgConfig* c) {
 
 AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int device) {
   if (!d || !cfg || n_envs <= 0) { g_err = "ag_create: bad arguments"; return nullptr; }
+  DevGuard guard__(device);
   AgSim* s = new AgSim();
   memset(&s->S, 0, sizeof(SimDev));
   memset(&s->F, 0, sizeof(FeedDev));
-  s->cfg = *cfg; s->device = device; s->launches = 0; s->feeding = false; s->bathing = false; s->use_graph = true; s->graphs[0].valid = s->graphs[1].valid = false; s->B_dev = nullptr; s->stream = nullptr; s->F_dev = nullptr; s->profiling = false;
+  s->cfg = *cfg; s->device = device; s->launches = 0; s->feeding = false; s->bathing = false; s->use_graph = true; s->graph_failures = 0; s->graphs[0].valid = s->graphs[1].valid = false; s->B_dev = nullptr; s->stream = nullptr; s->F_dev = nullptr; s->profiling = false;
   s->d_stage = nullptr; s->stage_floats = 0;
 #ifndef AG_CPU_EMU
-  if (cudaSetDevice(device) != cudaSuccess) { g_err = "cudaSetDevice failed (is a CUDA device present? there is no CPU fallback)"; delete s; return nullptr; }
+  { int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { g_err = "no such CUDA device (is a CUDA device present? there is no CPU fallback)"; delete s; return nullptr; } }
   if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { g_err = "cudaStreamCreate failed"; delete s; return nullptr; }
 #endif
   SimDev& S = s->S;
@@ -484,6 +504,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
 
 void ag_destroy(AgSim* s) {
   if (!s) return;
+  DevGuard guard__(s->device);
 #ifndef AG_CPU_EMU
   if (s->stream) cudaStreamSynchronize(s->stream);
   for (void* p : s->allocs) cudaFree(p);
@@ -499,16 +520,21 @@ void ag_destroy(AgSim* s) {
   delete s;
 }
 
-int ag_num_envs(const AgSim* s) { return s->S.N; }
-void* ag_stream(AgSim* s) { return (void*)s->stream; }
-uint64_t ag_kernel_launches(const AgSim* s) { return s->launches; }
+int ag_num_envs(const AgSim* s) {
+  DevGuard guard__(s->device); return s->S.N; }
+void* ag_stream(AgSim* s) {
+  DevGuard guard__(s->device); return (void*)s->stream; }
+uint64_t ag_kernel_launches(const AgSim* s) {
+  DevGuard guard__(s->device); return s->launches; }
 
 int ag_profile_enable(AgSim* s, int on) {
+  DevGuard guard__(s->device);
   s->profiling = on != 0;
   return 0;
 }
 // Resolves the recorded events: per kernel name total milliseconds and launch count since the last call.
 int ag_profile_get(AgSim* s, int max_names, char* names, int name_stride, float* total_ms, int32_t* counts) {
+  DevGuard guard__(s->device);
   int n = (int)s->knames.size();
   if (n > max_names) n = max_names;
   for (int i = 0; i < n; i++) { total_ms[i] = 0.f; counts[i] = 0; snprintf(names + (size_t)i * name_stride, name_stride, "%s", s->knames[i].c_str()); }
@@ -577,31 +603,37 @@ static int gather_host(AgSim* s, const float* srcdev, int comp, int nitems, cons
 }
 
 int ag_set_base_pose(AgSim* s, int body, const float* pos, const float* quat, const int32_t* mask) {
+  DevGuard guard__(s->device);
   if (body < 0 || body >= s->nb) return fail("bad body");
   if (pos && scatter_host(s, s->S.base_pos, 3, 1, &body, pos, mask)) return -1;
   if (quat && scatter_host(s, s->S.base_quat, 4, 1, &body, quat, mask)) return -1;
   return 0;
 }
 int ag_set_base_velocity(AgSim* s, int body, const float* lin, const float* ang, const int32_t* mask) {
+  DevGuard guard__(s->device);
   if (body < 0 || body >= s->nb) return fail("bad body");
   if (lin && scatter_host(s, s->S.base_lin, 3, 1, &body, lin, mask)) return -1;
   if (ang && scatter_host(s, s->S.base_ang, 3, 1, &body, ang, mask)) return -1;
   return 0;
 }
 int ag_set_joint_state(AgSim* s, int n, const int32_t* links, const float* q, const float* qd, const int32_t* mask) {
+  DevGuard guard__(s->device);
   if (q && scatter_host(s, s->S.jq, 1, n, links, q, mask)) return -1;
   if (qd && scatter_host(s, s->S.jqd, 1, n, links, qd, mask)) return -1;
   return 0;
 }
 int ag_set_link_friction(AgSim* s, int link, const float* mu, const int32_t* mask) {
+  DevGuard guard__(s->device);
   return scatter_host(s, s->S.friction, 1, 1, &link, mu, mask);
 }
 int ag_set_body_active(AgSim* s, int body, const int32_t* active) {
+  DevGuard guard__(s->device);
   if (body < 0 || body >= s->nb) return fail("bad body");
   return h2d(s, s->S.body_mode + (size_t)body * s->S.N, active, sizeof(int) * s->S.N);
 }
 
 int ag_set_hard_limits(AgSim* s, int n, const int32_t* links, int on) {
+  DevGuard guard__(s->device);
   std::vector<int> h(s->nl);
   if (d2h(s, h.data(), s->S.hard_limit, sizeof(int) * s->nl)) return -1;
   for (int j = 0; j < n; j++) { if (links[j] < 0 || links[j] >= s->nl) return fail("bad link"); h[links[j]] = on ? 1 : 0; }
@@ -610,29 +642,32 @@ int ag_set_hard_limits(AgSim* s, int n, const int32_t* links, int on) {
 
 static void run_fk_all(AgSim* s) {
   KP p = kp0(); p.i0 = 1;
-  LAUNCH(s, k_fk, s->S.N, p);
+  LAUNCH(s, k_fk, (size_t)s->S.nb * s->S.N, p);
   KP a = kp0(); a.p0 = s->S.allcol; a.i0 = s->S.nc;
   LAUNCH(s, k_aabb, (size_t)s->S.nc * s->S.N, a);
   KP l = kp0(); l.p0 = s->S.alllink; l.i0 = s->S.nalllink;
   LAUNCH(s, k_linkaabb, (size_t)s->S.nalllink * s->S.N, l);
 }
 
-int ag_forward_kinematics(AgSim* s) { run_fk_all(s); return 0; }
+int ag_forward_kinematics(AgSim* s) {
+  DevGuard guard__(s->device); run_fk_all(s); return 0; }
 
 int ag_set_motor_host(AgSim* s, int n, const int32_t* links, int mode, const float* target, const float* kp, const float* kd, const float* maxf) {
+  DevGuard guard__(s->device);
   std::vector<int> mm(s->nl); std::vector<float> a(s->nl), b(s->nl), c(s->nl);
-  d2h(s, mm.data(), s->S.motor_mode, sizeof(int) * s->nl); d2h(s, a.data(), s->S.motor_kp, sizeof(float) * s->nl);
-  d2h(s, b.data(), s->S.motor_kd, sizeof(float) * s->nl); d2h(s, c.data(), s->S.motor_maxf, sizeof(float) * s->nl);
+  if (d2h(s, mm.data(), s->S.motor_mode, sizeof(int) * s->nl) || d2h(s, a.data(), s->S.motor_kp, sizeof(float) * s->nl) ||
+      d2h(s, b.data(), s->S.motor_kd, sizeof(float) * s->nl) || d2h(s, c.data(), s->S.motor_maxf, sizeof(float) * s->nl)) return -1;
   for (int j = 0; j < n; j++) {
     int k = links[j]; if (k < 0 || k >= s->nl) return fail("bad link");
     mm[k] = mode; if (kp) a[k] = kp[j]; b[k] = kd ? kd[j] : 1.0f; if (maxf) c[k] = maxf[j];
   }
-  h2d(s, s->S.motor_mode, mm.data(), sizeof(int) * s->nl); h2d(s, s->S.motor_kp, a.data(), sizeof(float) * s->nl);
-  h2d(s, s->S.motor_kd, b.data(), sizeof(float) * s->nl); h2d(s, s->S.motor_maxf, c.data(), sizeof(float) * s->nl);
+  if (h2d(s, s->S.motor_mode, mm.data(), sizeof(int) * s->nl) || h2d(s, s->S.motor_kp, a.data(), sizeof(float) * s->nl) ||
+      h2d(s, s->S.motor_kd, b.data(), sizeof(float) * s->nl) || h2d(s, s->S.motor_maxf, c.data(), sizeof(float) * s->nl)) return -1;
   if (target) return scatter_host(s, s->S.motor_target, 1, n, links, target, nullptr);
   return 0;
 }
 int ag_set_motor_targets_dev(AgSim* s, int n, const int32_t* links, const float* target_dev) {
+  DevGuard guard__(s->device);
   if (n > 1024) return fail("too many items");
   if (check_items(s, s->S.motor_target, n, links)) return -1;
   if (h2d(s, s->d_links, links, sizeof(int) * n)) return -1;
@@ -642,6 +677,7 @@ int ag_set_motor_targets_dev(AgSim* s, int n, const int32_t* links, const float*
 }
 
 int ag_set_motor_targets_host(AgSim* s, int n, const int32_t* links, const float* target) {
+  DevGuard guard__(s->device);
   return scatter_host(s, s->S.motor_target, 1, n, links, target, nullptr);
 }
 
@@ -649,7 +685,7 @@ static void substep(AgSim* s) {
   SimDev& S = s->S;
   const int N = S.N;
   KP z = kp0();
-  LAUNCH(s, k_fk, N, z);
+  LAUNCH(s, k_fk, (size_t)S.nb * N, z);
   KP a = kp0(); a.p0 = S.movcol; a.i0 = S.nmovcol;
   LAUNCH(s, k_aabb, (size_t)S.nmovcol * N, a);
   KP l = kp0(); l.p0 = S.movlink; l.i0 = S.nmovlink;
@@ -682,15 +718,16 @@ static void substep(AgSim* s) {
 #else
   k_order(S, z);
   LAUNCH(s, k_pgs, N, z);
+  LAUNCH(s, k_integrate, N, z);                      // (fused into k_pgs on the device)
 #endif
-  LAUNCH(s, k_integrate, N, z);
 }
 
 int ag_step(AgSim* s, int n_steps) {
+  DevGuard guard__(s->device);
   int sub = s->cfg.num_substeps > 0 ? s->cfg.num_substeps : 1;
   for (int i = 0; i < n_steps * sub; i++) substep(s);
   KP z = kp0();
-  LAUNCH(s, k_fk, s->S.N, z);
+  LAUNCH(s, k_fk, (size_t)s->S.nb * s->S.N, z);
 #ifndef AG_CPU_EMU
   CK(cudaGetLastError());
 #endif
@@ -698,6 +735,7 @@ int ag_step(AgSim* s, int n_steps) {
 }
 
 int ag_get_joint_states(AgSim* s, int n, const int32_t* links, float* q, float* qd, float* tau) {
+  DevGuard guard__(s->device);
   if (q && gather_host(s, s->S.jq, 1, n, links, q)) return -1;
   if (qd && gather_host(s, s->S.jqd, 1, n, links, qd)) return -1;
   if (tau && gather_host(s, s->S.motor_applied, 1, n, links, tau)) return -1;
@@ -705,6 +743,7 @@ int ag_get_joint_states(AgSim* s, int n, const int32_t* links, float* q, float* 
 }
 
 int ag_get_link_states(AgSim* s, int n, const int32_t* links, float* pos, float* quat, float* com_pos, float* com_quat, float* lin_vel, float* ang_vel) {
+  DevGuard guard__(s->device);
   const int N = s->S.N;
   if (n > 1024) return fail("too many items");
   for (int j = 0; j < n; j++) if (links[j] < 0 || links[j] >= s->nl) return fail("bad link");
@@ -730,7 +769,9 @@ int ag_get_link_states(AgSim* s, int n, const int32_t* links, float* pos, float*
 
 static int contact_query(AgSim* s, int body_a, int body_b, int link_a, int link_b, int max_pts, AgContact* out, int32_t* count, float* fsum) {
   const int N = s->S.N;
-  if (body_a < 0 || body_a >= s->nb) return fail("bad body");
+  if (body_a < 0 || body_a >= s->nb || body_b >= s->nb) return fail("bad body");
+  if (max_pts < 0) return fail("bad max_pts");
+  if (link_a >= s->body_nlinks[body_a] - 1 || (body_b >= 0 && link_b >= s->body_nlinks[body_b] - 1)) return fail("bad link");
   size_t rec = sizeof(AgContact) / sizeof(float);
   float* st = stage(s, (size_t)N * max_pts * rec + (size_t)N);
   if (!st) return fail("staging alloc failed");
@@ -745,12 +786,15 @@ static int contact_query(AgSim* s, int body_a, int body_b, int link_a, int link_
   return 0;
 }
 int ag_get_contacts(AgSim* s, int body_a, int body_b, int link_a, int link_b, int max_pts, AgContact* out, int32_t* count) {
+  DevGuard guard__(s->device);
   return contact_query(s, body_a, body_b, link_a, link_b, max_pts, out, count, nullptr);
 }
 int ag_contact_force_sum(AgSim* s, int body_a, int body_b, int link_a, int link_b, float* out) {
+  DevGuard guard__(s->device);
   return contact_query(s, body_a, body_b, link_a, link_b, 0, nullptr, nullptr, out);
 }
 int ag_closest_points(AgSim* s, int body_a, int body_b, float distance, int max_pts, AgContact* out, int32_t* count) {
+  DevGuard guard__(s->device);
   const int N = s->S.N;
   if (body_a < 0 || body_a >= s->nb || body_b < 0 || body_b >= s->nb) return fail("bad body");
   run_fk_all(s);
@@ -766,6 +810,7 @@ int ag_closest_points(AgSim* s, int body_a, int body_b, float distance, int max_
 
 int ag_ik_solve(AgSim* s, int n_joints, const int32_t* joint_links, int ee_link, const float* target_pos, const float* target_quat,
                 int max_restarts, int iters, float threshold, uint64_t seed, const int32_t* env_mask, float* q_out, float* err_out) {
+  DevGuard guard__(s->device);
   const int N = s->S.N;
   if (n_joints < 1 || n_joints > AG_IK_MAXJ) return fail("ag_ik_solve: 1..8 joints");
   if (ee_link < 0 || ee_link >= s->nl) return fail("bad link");
@@ -801,13 +846,15 @@ int ag_ik_solve(AgSim* s, int n_joints, const int32_t* joint_links, int ee_link,
   return 0;
 }
 
-size_t ag_state_size(const AgSim* s) { return (size_t)s->nb * 13 + (size_t)s->nl * 2; }
+size_t ag_state_size(const AgSim* s) {
+  DevGuard guard__(s->device); return (size_t)s->nb * 13 + (size_t)s->nl * 2; }
 int ag_state_get(AgSim* s, float* out) {
+  DevGuard guard__(s->device);
   const int N = s->S.N; size_t sz = ag_state_size(s);
   std::vector<float> bp((size_t)s->nb * 3 * N), bq((size_t)s->nb * 4 * N), bl((size_t)s->nb * 3 * N), ba((size_t)s->nb * 3 * N), q((size_t)s->nl * N), qd((size_t)s->nl * N);
-  d2h(s, bp.data(), s->S.base_pos, bp.size() * 4); d2h(s, bq.data(), s->S.base_quat, bq.size() * 4);
-  d2h(s, bl.data(), s->S.base_lin, bl.size() * 4); d2h(s, ba.data(), s->S.base_ang, ba.size() * 4);
-  d2h(s, q.data(), s->S.jq, q.size() * 4); d2h(s, qd.data(), s->S.jqd, qd.size() * 4);
+  if (d2h(s, bp.data(), s->S.base_pos, bp.size() * 4) || d2h(s, bq.data(), s->S.base_quat, bq.size() * 4) ||
+      d2h(s, bl.data(), s->S.base_lin, bl.size() * 4) || d2h(s, ba.data(), s->S.base_ang, ba.size() * 4) ||
+      d2h(s, q.data(), s->S.jq, q.size() * 4) || d2h(s, qd.data(), s->S.jqd, qd.size() * 4)) return -1;
   for (int e = 0; e < N; e++) {
     float* o = out + sz * e;
     for (int b = 0; b < s->nb; b++) {
@@ -820,6 +867,7 @@ int ag_state_get(AgSim* s, float* out) {
   return 0;
 }
 int ag_state_set(AgSim* s, const float* in) {
+  DevGuard guard__(s->device);
   const int N = s->S.N; size_t sz = ag_state_size(s);
   std::vector<float> bp((size_t)s->nb * 3 * N), bq((size_t)s->nb * 4 * N), bl((size_t)s->nb * 3 * N), ba((size_t)s->nb * 3 * N), q((size_t)s->nl * N), qd((size_t)s->nl * N);
   for (int e = 0; e < N; e++) {
@@ -831,27 +879,31 @@ int ag_state_set(AgSim* s, const float* in) {
     }
     for (int k = 0; k < s->nl; k++) { q[(size_t)k * N + e] = o[0]; qd[(size_t)k * N + e] = o[1]; o += 2; }
   }
-  h2d(s, s->S.base_pos, bp.data(), bp.size() * 4); h2d(s, s->S.base_quat, bq.data(), bq.size() * 4);
-  h2d(s, s->S.base_lin, bl.data(), bl.size() * 4); h2d(s, s->S.base_ang, ba.data(), ba.size() * 4);
-  h2d(s, s->S.jq, q.data(), q.size() * 4); h2d(s, s->S.jqd, qd.data(), qd.size() * 4);
+  if (h2d(s, s->S.base_pos, bp.data(), bp.size() * 4) || h2d(s, s->S.base_quat, bq.data(), bq.size() * 4) ||
+      h2d(s, s->S.base_lin, bl.data(), bl.size() * 4) || h2d(s, s->S.base_ang, ba.data(), ba.size() * 4) ||
+      h2d(s, s->S.jq, q.data(), q.size() * 4) || h2d(s, s->S.jqd, qd.data(), qd.size() * 4)) return -1;
   run_fk_all(s);
   return 0;
 }
 
-int ag_get_pgs_cycles(AgSim* s, int32_t* cycles) { return d2h(s, cycles, s->S.pgs_cycles, sizeof(int) * s->S.N); }
+int ag_get_pgs_cycles(AgSim* s, int32_t* cycles) {
+  DevGuard guard__(s->device); return d2h(s, cycles, s->S.pgs_cycles, sizeof(int) * s->S.N); }
 int ag_get_pgs_trips(AgSim* s, int32_t* trips, int32_t* stream_floats) {
+  DevGuard guard__(s->device);
   if (trips && d2h(s, trips, s->S.pgs_trips, sizeof(int) * s->S.N)) return -1;
   if (stream_floats && d2h(s, stream_floats, s->S.rs_nfloats, sizeof(int) * s->S.N)) return -1;
   return 0;
 }
 
 int ag_get_solver_stats(AgSim* s, int32_t* contacts, int32_t* iters) {
+  DevGuard guard__(s->device);
   if (contacts && d2h(s, contacts, s->S.c_count, sizeof(int) * s->S.N)) return -1;
   if (iters && d2h(s, iters, s->S.iters_used, sizeof(int) * s->S.N)) return -1;
   return 0;
 }
 
 int ag_overflow_count(AgSim* s) {
+  DevGuard guard__(s->device);
   std::vector<int> o(s->S.N);
   if (d2h(s, o.data(), s->S.overflow, sizeof(int) * s->S.N)) return -1;
   int n = 0; for (int v : o) n += v != 0;
@@ -874,6 +926,10 @@ static void drop_graph(AgSim* s, int which) {
 static int run_step(AgSim* s, int which, StepEnqueue enq, const float* action, float* obs, float* reward, float* done, float* info) {
 #ifndef AG_CPU_EMU
   if (s->use_graph && !s->profiling) {
+    // The graph is captured against the sim's OWN action buffer: a learner hands in a freshly allocated action tensor
+    // every step, and a graph keyed on that address would be re-captured (~90 launches + instantiate) each time.
+    float* own = which == 0 ? s->d_action : s->d_baction;
+    if (action != own) { CK(cudaMemcpyAsync(own, action, sizeof(float) * 7 * s->S.N, cudaMemcpyDeviceToDevice, s->stream)); action = own; }
     AgSim::StepGraph& G = s->graphs[which];
     const void* key[5] = {action, obs, reward, done, info};
     if (G.valid && memcmp(G.key, key, sizeof(key)) != 0) { cudaGraphExecDestroy((cudaGraphExec_t)G.exec); G.valid = false; }
@@ -884,12 +940,12 @@ static int run_step(AgSim* s, int which, StepEnqueue enq, const float* action, f
         int rc = enq(s, action, obs, reward, done, info);
         cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
         if (rc == 0 && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
-          G.exec = exec; memcpy(G.key, key, sizeof(key)); G.launches = s->launches - l0; G.valid = true;
+          G.exec = exec; memcpy(G.key, key, sizeof(key)); G.launches = s->launches - l0; G.valid = true; s->graph_failures = 0;
         }
         if (graph) cudaGraphDestroy(graph);
       }
       s->launches = l0;
-      if (!G.valid) { cudaGetLastError(); s->use_graph = false; }
+      if (!G.valid) { cudaGetLastError(); if (++s->graph_failures >= 3) s->use_graph = false; }   // a transient failure: try again next step
     }
     if (G.valid) {
       CK(cudaGraphLaunch((cudaGraphExec_t)G.exec, s->stream));
@@ -905,6 +961,7 @@ static int run_step(AgSim* s, int which, StepEnqueue enq, const float* action, f
 
 // ------------------------------------------------------------------ fused FeedingEnv path
 int ag_feeding_init(AgSim* s, const AgFeedingParams* p, const int32_t* gender_is_male) {
+  DevGuard guard__(s->device);
   const int N = s->S.N;
   FeedDev& F = s->F;
   F.P = *p;
@@ -934,6 +991,7 @@ int ag_feeding_init(AgSim* s, const AgFeedingParams* p, const int32_t* gender_is
   return ag_feeding_reset_episode(s, nullptr);
 }
 int ag_feeding_set_tremor(AgSim* s, const int32_t* on, const float* rest, const float* amplitude) {
+  DevGuard guard__(s->device);
   if (!s->feeding) return fail("ag_feeding_init not called");
   const int N = s->S.N;
   std::vector<int> o(N, 0); std::vector<float> r((size_t)4 * N, 0.f), a((size_t)4 * N, 0.f);
@@ -947,6 +1005,7 @@ int ag_feeding_set_tremor(AgSim* s, const int32_t* on, const float* rest, const 
 }
 
 int ag_feeding_reset_episode(AgSim* s, const int32_t* env_mask) {
+  DevGuard guard__(s->device);
   if (!s->feeding) return fail("ag_feeding_init not called");
   const int N = s->S.N;
   std::vector<int> fs(N), it(N), ts(N); std::vector<unsigned long long> rng(N);
@@ -968,7 +1027,7 @@ static int feeding_step_enqueue(AgSim* s, const float* action_dev, float* obs, f
   LAUNCH(s, k_feed_pre, N, p);
   for (int i = 0; i < s->F.P.frame_skip * (s->cfg.num_substeps > 0 ? s->cfg.num_substeps : 1); i++) substep(s);
   KP z = kp0();
-  LAUNCH(s, k_fk, N, z);
+  LAUNCH(s, k_fk, (size_t)s->S.nb * N, z);
   KP a = kp0(); a.p0 = s->S.movcol; a.i0 = s->S.nmovcol;
   LAUNCH(s, k_aabb, (size_t)s->S.nmovcol * N, a);
   KP l = kp0(); l.p0 = s->S.movlink; l.i0 = s->S.nmovlink;
@@ -980,6 +1039,7 @@ static int feeding_step_enqueue(AgSim* s, const float* action_dev, float* obs, f
   return 0;
 }
 int ag_feeding_step_dev(AgSim* s, const float* action_dev, float* obs_dev, float* reward_dev, float* done_dev, float* info_dev) {
+  DevGuard guard__(s->device);
   if (!s->feeding) return fail("ag_feeding_init not called");
   int rc = run_step(s, 0, feeding_step_enqueue, action_dev, obs_dev, reward_dev, done_dev, info_dev);
 #ifndef AG_CPU_EMU
@@ -987,7 +1047,11 @@ int ag_feeding_step_dev(AgSim* s, const float* action_dev, float* obs_dev, float
 #endif
   return rc;
 }
-int ag_feeding_step_host(AgSim* s, const float* action, float* obs, float* reward, float* done, float* info) {
+// host-buffer step in two halves: `begin` stages the actions (pinned) and enqueues H2D, the fused step and the D2H
+// read-back on the sim's stream and returns; `end` waits for that stream and hands the results out.  Several sims
+// (sub-batches of one batch, each on its own stream) overlap this way; ag_feeding_step_host = begin + end.
+int ag_feeding_step_host_begin(AgSim* s, const float* action) {
+  DevGuard guard__(s->device);
   if (!s->feeding) return fail("ag_feeding_init not called");
   const int N = s->S.N;
   memcpy(s->h_pin_in, action, sizeof(float) * N * 7);
@@ -1002,11 +1066,19 @@ int ag_feeding_step_host(AgSim* s, const float* action, float* obs, float* rewar
   CK(cudaMemcpyAsync(s->h_pin_out + (size_t)N * 25, s->d_reward, sizeof(float) * N, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaMemcpyAsync(s->h_pin_out + (size_t)N * 26, s->d_done, sizeof(float) * N, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaMemcpyAsync(s->h_pin_out + (size_t)N * 27, s->d_info, sizeof(float) * N * 4, cudaMemcpyDeviceToHost, s->stream));
-  CK(cudaStreamSynchronize(s->stream));
-  CK(cudaGetLastError());
 #else
   memcpy(s->h_pin_out, s->d_obs, sizeof(float) * N * 25); memcpy(s->h_pin_out + (size_t)N * 25, s->d_reward, sizeof(float) * N);
   memcpy(s->h_pin_out + (size_t)N * 26, s->d_done, sizeof(float) * N); memcpy(s->h_pin_out + (size_t)N * 27, s->d_info, sizeof(float) * N * 4);
+#endif
+  return 0;
+}
+int ag_feeding_step_host_end(AgSim* s, float* obs, float* reward, float* done, float* info) {
+  DevGuard guard__(s->device);
+  if (!s->feeding) return fail("ag_feeding_init not called");
+  const int N = s->S.N;
+#ifndef AG_CPU_EMU
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
 #endif
   memcpy(obs, s->h_pin_out, sizeof(float) * N * 25);
   memcpy(reward, s->h_pin_out + (size_t)N * 25, sizeof(float) * N);
@@ -1014,9 +1086,14 @@ int ag_feeding_step_host(AgSim* s, const float* action, float* obs, float* rewar
   if (info) memcpy(info, s->h_pin_out + (size_t)N * 27, sizeof(float) * N * 4);
   return 0;
 }
+int ag_feeding_step_host(AgSim* s, const float* action, float* obs, float* reward, float* done, float* info) {
+  if (ag_feeding_step_host_begin(s, action)) return -1;
+  return ag_feeding_step_host_end(s, obs, reward, done, info);
+}
 
 // ------------------------------------------------------------------ fused BedBathingEnv path
 int ag_bathing_init(AgSim* s, const AgBathingParams* p, const int32_t* gender_is_male, const float* targets_world, const int32_t* targets_valid) {
+  DevGuard guard__(s->device);
   const int N = s->S.N;
   BathDev& B = s->B;
   B.P = *p;
@@ -1062,7 +1139,7 @@ static int bathing_step_enqueue(AgSim* s, const float* action_dev, float* obs, f
   LAUNCH(s, k_bath_pre, N, p);
   for (int i = 0; i < s->B.P.frame_skip * (s->cfg.num_substeps > 0 ? s->cfg.num_substeps : 1); i++) substep(s);
   KP z = kp0();
-  LAUNCH(s, k_fk, N, z);
+  LAUNCH(s, k_fk, (size_t)s->S.nb * N, z);
   KP a = kp0(); a.p0 = s->S.movcol; a.i0 = s->S.nmovcol;
   LAUNCH(s, k_aabb, (size_t)s->S.nmovcol * N, a);
   KP l = kp0(); l.p0 = s->S.movlink; l.i0 = s->S.nmovlink;
@@ -1074,6 +1151,7 @@ static int bathing_step_enqueue(AgSim* s, const float* action_dev, float* obs, f
   return 0;
 }
 int ag_bathing_step_dev(AgSim* s, const float* action_dev, float* obs_dev, float* reward_dev, float* done_dev, float* info_dev) {
+  DevGuard guard__(s->device);
   if (!s->bathing) return fail("ag_bathing_init not called");
   int rc = run_step(s, 1, bathing_step_enqueue, action_dev, obs_dev, reward_dev, done_dev, info_dev);
 #ifndef AG_CPU_EMU
@@ -1082,6 +1160,7 @@ int ag_bathing_step_dev(AgSim* s, const float* action_dev, float* obs_dev, float
   return rc;
 }
 int ag_bathing_step_host(AgSim* s, const float* action, float* obs, float* reward, float* done, float* info) {
+  DevGuard guard__(s->device);
   if (!s->bathing) return fail("ag_bathing_init not called");
   const int N = s->S.N;
   memcpy(s->h_bpin_in, action, sizeof(float) * N * 7);

@@ -237,6 +237,78 @@ class BatchSim:
         self._ck(self.lib.ag_feeding_step_host(self.h, _p(a), _p(obs), _p(rew), _p(done), _p(info)))
         return obs, rew, done, info
 
+    def feeding_step_host_begin(self, action):
+        self._host_a = _f32(action, (self.n, 7))
+        self._ck(self.lib.ag_feeding_step_host_begin(self.h, _p(self._host_a)))
+
+    def feeding_step_host_end(self):
+        obs = np.zeros((self.n, 25), dtype=np.float32)
+        rew, done = np.zeros(self.n, dtype=np.float32), np.zeros(self.n, dtype=np.float32)
+        info = np.zeros((self.n, 4), dtype=np.float32)
+        self._ck(self.lib.ag_feeding_step_host_end(self.h, _p(obs), _p(rew), _p(done), _p(info)))
+        return obs, rew, done, info
+
     def feeding_step_dev(self, action_ptr, obs_ptr, reward_ptr, done_ptr, info_ptr):
         self._ck(self.lib.ag_feeding_step_dev(self.h, C.c_void_p(action_ptr), C.c_void_p(obs_ptr), C.c_void_p(reward_ptr),
                                               C.c_void_p(done_ptr), C.c_void_p(info_ptr)))
+
+
+class BatchSimGroup:
+    """One batch as G independent sub-batches, each a `BatchSim` on its own CUDA stream.
+
+    Envs are independent: nothing ties env A's sub-step to env B's except that a kernel launch covers
+    the whole batch and ends with its slowest env -- in `k_pgs` the few envs that need all 50 sweeps keep a handful of
+    warps busy for twice as long as the mean.  With the batch split into sub-batches that are enqueued back to back on
+    separate streams, one sub-batch's tails are filled by the others' kernels.  The sub-batches are contiguous env
+    ranges: entry points take whole-batch buffers and hand each sub-sim its slice."""
+
+    def __init__(self, scene, cfg=None, n_envs=1, groups=1, device=0, _lib=None):
+        if n_envs % groups:
+            raise ValueError('n_envs must be a multiple of the number of sub-batches')
+        self.n, self.groups, self.m = n_envs, groups, n_envs // groups
+        self.sims = [BatchSim(scene, cfg, self.m, device=device, _lib=_lib) for _ in range(groups)]
+
+    def slices(self):
+        return [slice(g * self.m, (g + 1) * self.m) for g in range(self.groups)]
+
+    def stream_ptrs(self):
+        return [sim.stream_ptr() for sim in self.sims]
+
+    def feeding_step_dev(self, action_ptr, obs_ptr, reward_ptr, done_ptr, info_ptr):
+        """whole-batch device buffers ([n, 7], [n, 25], [n], [n], [n, 4] float32, contiguous); asynchronous"""
+        for g, sim in enumerate(self.sims):
+            o = 4 * g * self.m
+            sim.feeding_step_dev(action_ptr + 7 * o, obs_ptr + 25 * o, reward_ptr + o, done_ptr + o, info_ptr + 4 * o)
+
+    def feeding_step_host(self, action):
+        a = _f32(action, (self.n, 7))
+        for sl, sim in zip(self.slices(), self.sims):
+            sim.feeding_step_host_begin(a[sl])
+        parts = [sim.feeding_step_host_end() for sim in self.sims]
+        return tuple(np.concatenate([p[k] for p in parts], axis=0) for k in range(4))
+
+    def kernel_launches(self):
+        return sum(sim.kernel_launches() for sim in self.sims)
+
+    def overflow_count(self):
+        return sum(sim.overflow_count() for sim in self.sims)
+
+    def solver_stats(self):
+        parts = [sim.solver_stats() for sim in self.sims]
+        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
+    def pgs_trips(self):
+        parts = [sim.pgs_trips() for sim in self.sims]
+        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
+    def profile_enable(self, on=True):
+        for sim in self.sims:
+            sim.profile_enable(on)
+
+    def profile_get(self):
+        out = {}
+        for sim in self.sims:
+            for k, (ms, cnt) in sim.profile_get().items():
+                a = out.get(k, (0.0, 0))
+                out[k] = (a[0] + ms, a[1] + cnt)
+        return out

@@ -87,6 +87,30 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def usable_cores():
+    """Host threads this process may really use: the affinity mask capped by the cgroup CPU quota (a 1-GPU lease can be
+    a slice of a 128-thread host: os.cpu_count() over-subscribed it 20x and the CPU arm swung 5.7x between boxes)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ('/sys/fs/cgroup/cpu.max', '/sys/fs/cgroup/cpu/cpu.cfs_quota_us'):
+        try:
+            txt = open(path).read().split()
+            if path.endswith('cpu.max'):
+                if txt[0] != 'max':
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
 def cpu_oracle_rate(fb, n_envs, env_steps, threads, seed=0):
     """env-steps/s of the CPU oracle on a bounded sample of the same workload."""
     from assistive_gym_b200 import capi
@@ -110,32 +134,58 @@ def cpu_oracle_rate(fb, n_envs, env_steps, threads, seed=0):
     return n_envs * env_steps / dt, dt
 
 
+def pybullet_rate(env_steps):
+    """The real reference, if it can be imported on this box: gym.make('assistive_gym:FeedingJaco-v1') stepped with
+    random actions in one process.  None when PyBullet / the reference are absent."""
+    try:
+        import pybullet  # noqa: F401
+        import gym
+        import assistive_gym  # noqa: F401  (the reference package, not this repo's shim)
+        if getattr(assistive_gym, '__agphys_shim__', False):
+            return None
+        env = gym.make('assistive_gym:FeedingJaco-v1')
+        env.seed(1001)
+        env.reset()
+        rng = np.random.default_rng(0)
+        t0 = time.perf_counter()
+        for _ in range(env_steps):
+            env.step(rng.uniform(-1, 1, size=7))
+        return env_steps / (time.perf_counter() - t0)
+    except Exception:
+        return None
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU path.  PyBullet cannot be installed here,
-    so this arm times the oracle port on all host cores; kind = "port"."""
+    """--impl reference: the reference's CPU path on the box's host cores.  PyBullet is tried first (never installable
+    in the build container); otherwise the oracle port is timed, kind = "port", on the SAME workload
+    size as the product arm (batch envs per GPU), with all usable host threads and with one."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     from assistive_gym_b200.feeding_batch import FeedingBatch
     fb = FeedingBatch()
-    cores = os.cpu_count() or 1
-    n_envs = max(cores * 8, 32)
-    for _ in range(min(args.warmup, 1)):
-        cpu_oracle_rate(fb, cores, 1, cores)
+    cores = usable_cores()
+    n_envs = args.batch
+    pb = pybullet_rate(200)
+    env_steps = 2                                     # per timed sample: bounded so that --steps K ends within minutes
+    cpu_oracle_rate(fb, max(cores, 8), 1, cores)      # warm-up (library load, first-touch)
     rates, times = [], []
-    per_step_envsteps = 5
-    for _ in range(max(1, min(args.steps, 5))):
-        r, t = cpu_oracle_rate(fb, n_envs, per_step_envsteps, cores)
+    for _ in range(max(1, min(args.steps, 3))):
+        r, t = cpu_oracle_rate(fb, n_envs, env_steps, cores)
         rates.append(r)
         times.append(t)
     v = float(np.median(rates))
-    sample = '%d envs x %d env-steps per timed sample, %d samples, oracle port (CPU restatement - PyBullet unavailable), %d threads' % (
-        n_envs, per_step_envsteps, len(rates), cores)
+    r1, t1 = cpu_oracle_rate(fb, max(n_envs // max(cores, 1), 32), env_steps, 1)
+    sample = '%d envs x %d env-steps per timed sample, %d samples, oracle port (CPU restatement - PyBullet %s), %d threads' % (
+        n_envs, env_steps, len(rates), 'timed separately' if pb else 'unavailable', cores)
     out = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
-           'warmup': args.warmup, 'ms_per_step': 1000.0 * float(np.median(times)), 'higher_is_better': True, 'scaling': 'weak',
+           'warmup': args.warmup, 'ms_per_step': 1000.0 * float(np.median(times)) / env_steps, 'higher_is_better': True, 'scaling': 'weak',
            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-           'config': {'workload': 'FeedingJaco-v1, CPU restatement (PyBullet unavailable), %d envs' % n_envs, 'l2': 'n/a (CPU)'},
-           'cpu_baseline': {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+           'config': {'workload': 'FeedingJaco-v1, batch %d, CPU restatement (PyBullet %s)' % (n_envs, 'also timed' if pb else 'unavailable'),
+                      'global_batch': n_envs, 'l2': 'n/a (CPU)'},
+           'cpu_baseline': {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample,
+                            'one_thread': {'value': float(r1), 'cores': 1},
+                            'pybullet_one_process': ({'value': float(pb), 'cores': 1, 'kind': 'reference'} if pb else None)},
            'e2e': {'value': v, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
            'gpu_launches': 0}
     print(json.dumps(out))
@@ -157,6 +207,22 @@ def ncu_traffic(kernel):
     return (tot if tot > 0 else None), os.path.relpath(files[-1], ROOT)
 
 
+def ncu_metrics(kernel, names):
+    """selected metrics of the newest committed ncu summary of `kernel` ({} if there is none)"""
+    import csv
+    import glob
+    files = sorted(f for f in glob.glob(os.path.join(ROOT, 'profiles', 'r*_ncu_%s.csv' % kernel)))
+    out = {}
+    if files:
+        for r in csv.reader(open(files[-1])):
+            if len(r) >= 4 and r[1] in names:
+                try:
+                    out[names[r[1]]] = float(r[3].replace(',', ''))
+                except ValueError:
+                    pass
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -166,6 +232,7 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='envs per GPU')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--profile-kernels', type=int, default=1)
+    ap.add_argument('--sub-batches', type=int, default=int(os.environ.get('AG_SUB_BATCHES', '1')), help='independent sub-batches per GPU, each on its own stream')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -182,21 +249,25 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     from assistive_gym_b200 import capi
     from assistive_gym_b200.feeding_batch import FeedingBatch
-    from assistive_gym_b200.sim import BatchSim
+    from assistive_gym_b200.sim import BatchSimGroup
 
     n = args.batch
     W = max(args.warmup, 3)
     K = args.steps
     fb = FeedingBatch()
     cfg = capi.default_config()
-    sim = BatchSim(fb.scene, cfg, n, device=local_rank)
+    G = max(1, args.sub_batches)
+    sim = BatchSimGroup(fb.scene, cfg, n, groups=G, device=local_rank)
     # per-env seeds derive from the GLOBAL env id so results do not depend on the partition
     from assistive_gym_b200.sharding import sample_block, shard_range
     lo, hi = shard_range(rank, world, world * n)
-    rng = np.random.default_rng(1001 + rank * n)           # only used for IK random restarts
-    s = fb.reset(sim, rng, settle_steps=25, sample=sample_block(fb, lo, hi))
-    fb.start_fused(sim, s, seed=1001 + rank * n)
-    stream = torch.cuda.ExternalStream(sim.stream_ptr(), device=local_rank)
+    for g, sub in enumerate(sim.sims):
+        rng = np.random.default_rng(1001 + rank * n + g)       # only used for IK random restarts
+        sg = fb.reset(sub, rng, settle_steps=25, sample=sample_block(fb, lo + g * sim.m, lo + (g + 1) * sim.m))
+        fb.start_fused(sub, sg, seed=1001 + rank * n + g * sim.m)
+    # `stream`: the bench's own stream; every step forks from it to the sub-batches' streams and joins back
+    sub_streams = [torch.cuda.ExternalStream(p, device=local_rank) for p in sim.stream_ptrs()]
+    stream = torch.cuda.Stream(device=local_rank)
     dev = torch.device('cuda', local_rank)
     gen = torch.Generator(device=dev)
     gen.manual_seed(rank)
@@ -205,15 +276,32 @@ def main():
     rew = torch.zeros(n, device=dev)
     done = torch.zeros(n, device=dev)
     info = torch.zeros((n, 4), device=dev)
-    rew_all = torch.zeros(world * n, device=dev) if world > 1 else None
+    # the single collective of the path: all-gather of the reward tensor, every step, double-buffered
+    # and issued on a side stream so that gathering step i overlaps simulating step i+1
+    rew_db = [torch.zeros(n, device=dev) for _ in range(2)] if world > 1 else None
+    rew_all = [torch.zeros(world * n, device=dev) for _ in range(2)] if world > 1 else None
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)      # 256 MiB > 126 MB L2
     torch.cuda.synchronize()
 
+    def gather_reward(i, src):
+        """enqueue: copy the step's reward out of the way (sim stream), gather it on the side stream"""
+        with torch.cuda.stream(stream):
+            rew_db[i % 2].copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            dist.all_gather_into_tensor(rew_all[i % 2], rew_db[i % 2])
+
     def one_step(i):
+        for ss in sub_streams:
+            ss.wait_stream(stream)
         sim.feeding_step_dev(actions[i].data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), info.data_ptr())
-        if world > 1:   # the single collective of the path: all-gather of the reward tensor
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(rew_all, rew)
+        for ss in sub_streams:
+            stream.wait_stream(ss)
+        if world > 1:
+            gather_reward(i, rew)
 
     for i in range(W):
         one_step(i)
@@ -224,8 +312,7 @@ def main():
     torch.cuda.synchronize()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    if args.profile_kernels:
-        sim.profile_enable(True)
+    # ---- value: device-resident, CUDA-graph replay of the fused step (the path a learner uses), collective included
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     for i in range(K):
@@ -235,14 +322,14 @@ def main():
             starts[i].record(stream)
         one_step(W + i)
         with torch.cuda.stream(stream):
+            if world > 1:
+                stream.wait_stream(side)      # the step is done when its reward is gathered
             stops[i].record(stream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     clk = clocks.stop()
-    prof = sim.profile_get() if args.profile_kernels else {}
-    sim.profile_enable(False)
     launches = sim.kernel_launches() - launches0
     elapsed_ms = float(sum(a.elapsed_time(b) for a, b in zip(starts, stops)))
     t = torch.tensor([elapsed_ms], device=dev)
@@ -250,16 +337,46 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
     value = world * n * K / (elapsed_ms / 1000.0)
+    # the same K steps timed back to back (no flush, no per-step sync): how much the pipeline overlap is worth
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        e0 = torch.cuda.Event(enable_timing=True); e0.record(stream)
+    for i in range(K):
+        one_step(W + i)
+    with torch.cuda.stream(stream):
+        if world > 1:
+            stream.wait_stream(side)
+        e1 = torch.cuda.Event(enable_timing=True); e1.record(stream)
+    torch.cuda.synchronize()
+    b2b_ms = e0.elapsed_time(e1) / K
 
-    # ---- e2e: host buffers through the reference-facing call (H2D + D2H inside the timed region)
+    # ---- per-kernel split: a separate pass with direct launches and an event pair around every kernel
+    prof = {}
+    if args.profile_kernels:
+        sim.profile_enable(True)
+        for i in range(min(K, 5)):
+            sim.feeding_step_dev(actions[W + i].data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), info.data_ptr())
+            torch.cuda.synchronize()          # sub-batch after sub-batch: the per-kernel times are not overlapped
+        torch.cuda.synchronize()
+        prof = sim.profile_get()
+        sim.profile_enable(False)
+        sc_ = K / float(min(K, 5))
+        prof = {k: (v[0] * sc_, int(round(v[1] * sc_))) for k, v in prof.items()}     # scaled to K steps (the code below divides by K)
+
+    # ---- e2e: host buffers through the reference-facing call (H2D + D2H inside the timed region, collective included)
     host_actions = np.random.default_rng(7 + rank).uniform(-1, 1, size=(K, n, 7)).astype(np.float32)
     sim.feeding_step_host(host_actions[0])
+    r_dev = torch.zeros(n, device=dev)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for i in range(K):
         o_h, r_h, d_h, i_h = sim.feeding_step_host(host_actions[i])
+        if world > 1:
+            with torch.cuda.stream(stream):
+                r_dev.copy_(torch.from_numpy(r_h), non_blocking=True)
+            gather_reward(i, r_dev)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device=dev)
@@ -268,6 +385,7 @@ def main():
     e2e_value = world * n * K / float(t.item())
     overflow = sim.overflow_count()
     ccount, citers = sim.solver_stats()
+    stream_bytes = 4 * sim.pgs_trips()[1]
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -276,13 +394,20 @@ def main():
             top = max(prof.items(), key=lambda kv: kv[1][0])
             name, (ms, cnt) = top
             per_launch_ms = ms / max(cnt, 1)
-            achieved = n * B_SUBSTEP / (per_launch_ms * 1e-3) / 1e9
+            achieved = (n // G) * B_SUBSTEP / (per_launch_ms * 1e-3) / 1e9
             total_kernel_ms = sum(v[0] for v in prof.values())
             roof = {'bound': 'hbm', 'kernel': name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                     'traffic': ncu_traffic(name)[0], 'traffic_source': ncu_traffic(name)[1], 'peak_source': peak_src, 'kernel_ms_per_launch': per_launch_ms,
                     'kernel_share_of_step': ms / total_kernel_ms if total_kernel_ms else None,
                     'step_frac': value * B_STEP / 1e9 / peak / world,
                     'per_kernel_ms_per_step': {k: v[0] / K for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+                    # what actually bounds the kernel: issue slots x lane utilisation (from the committed ncu summary)
+                    'issue': ncu_metrics(name, {'smsp__thread_inst_executed_per_inst_executed.ratio': 'active_lanes_per_instruction',
+                                                'smsp__issue_active.avg.pct_of_peak_sustained_active': 'issue_active_pct',
+                                                'smsp__inst_executed.sum': 'warp_instructions_per_launch',
+                                                'lts__t_sector_hit_rate.pct': 'l2_hit_pct'}),
+                    # bytes the kernel really streams per launch: every env's row stream once per PGS sweep
+                    'row_stream_gb_per_launch': float(stream_bytes.astype(np.float64).dot(citers.astype(np.float64)) / 1e9),
                     'note': 'the step is latency/issue bound, not HBM bound (SURVEY.md 8(d)); frac is reported per contract'}
         out = {'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
                'ms_per_step': elapsed_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
@@ -294,15 +419,19 @@ def main():
                           'contacts_per_env': {'mean': float(ccount.mean()), 'p50': float(np.percentile(ccount, 50)), 'p99': float(np.percentile(ccount, 99)), 'max': int(ccount.max())},
                           'pgs_iters_per_env': {'mean': float(citers.mean()), 'p50': float(np.percentile(citers, 50)), 'p99': float(np.percentile(citers, 99)), 'max': int(citers.max())},
                           'pgs_lanes_per_env': 8,
-                          'collective': 'all_gather(reward) per step' if world > 1 else 'none'},
+                          'collective': 'all_gather(reward) every step, double-buffered on a side stream (inside both timed regions)' if world > 1 else 'none',
+                          'ms_per_step_back_to_back': b2b_ms},
                'clocks': clk,
                'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n * 7 * 4, 'd2h_bytes_per_step': n * 31 * 4},
                'gpu_launches': int(launches), 'roofline': roof}
         if not args.no_cpu:
-            cores = os.cpu_count() or 1
-            v, tsec = cpu_oracle_rate(fb, max(8 * cores, 32), 10, cores)
+            cores = usable_cores()
+            ne = max(8 * cores, 32)
+            v, tsec = cpu_oracle_rate(fb, ne, 5, cores)
+            v1, t1 = cpu_oracle_rate(fb, 16, 5, 1)
             out['cpu_baseline'] = {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
-                                   'sample': '%d envs x 10 env-steps (%.1f s), CPU restatement (PyBullet unavailable), %d threads' % (max(8 * cores, 32), tsec, cores)}
+                                   'sample': '%d envs x 5 env-steps (%.1f s), CPU restatement (PyBullet unavailable), %d threads (affinity / cgroup quota)' % (ne, tsec, cores),
+                                   'one_thread': {'value': v1, 'cores': 1, 'sample': '16 envs x 5 env-steps (%.1f s)' % t1}}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

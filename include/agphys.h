@@ -3,7 +3,7 @@
  * Drop-in boundary: the reference drives its physics through ~60 `pybullet` C-extension calls
  * (SURVEY.md §8(b)); every entry point below cites the reference call site(s) it replaces
  * (paths relative to /root/reference/assistive_gym/envs).  The host-side mirror
- * (`assistive_gym_b200/bullet_shim.py`) binds these with ctypes; INTEGRATION.md shows the stub a
+ * (`assistive_gym_b200/capi.py` + `assistive_gym_b200/sim.py`) binds these with ctypes; INTEGRATION.md shows the stub a
  * maintainer of the reference would add.
  *
  * Conventions
@@ -209,6 +209,10 @@ int ag_feeding_step_dev(AgSim* sim, const float* action_dev, float* obs_dev, flo
                         float* done_dev, float* info_dev);
 /* host-buffer variant (pinned or pageable): H2D of action, D2H of obs/reward/done/info inside */
 int ag_feeding_step_host(AgSim* sim, const float* action, float* obs, float* reward, float* done, float* info);
+/* the same in two halves, so that several sims (sub-batches on their own streams) overlap: `begin` stages the actions and
+ * enqueues H2D + step + D2H on the sim's stream and returns, `end` waits for the stream and hands the results out */
+int ag_feeding_step_host_begin(AgSim* sim, const float* action);
+int ag_feeding_step_host_end(AgSim* sim, float* obs, float* reward, float* done, float* info);
 
 /* --- fused BedBathingEnv path (bed_bathing.py:12-111 + env.py:174-274): action -> PD targets ->
  * frame_skip substeps -> obs[24] / reward / done; wiping targets are points on the person's right arm
@@ -247,6 +251,9 @@ int ag_ik_solve(AgSim* sim, int n_joints, const int32_t* joint_links, int ee_lin
                 const int32_t* env_mask, float* q_out, float* err_out);
 
 /* --- checkpoint / parity: full per-env dynamic state as a flat float blob -------------------- */
+/* KINEMATIC state only (base pose / velocity of every body, q / qd of every link): what a parity test needs to put two
+ * simulations into the same configuration.  Motor targets and modes, body modes, per-env friction, the hard-limit flags
+ * and the fused episodes' bookkeeping (food state, iteration, tremor phase) are NOT part of it. */
 size_t ag_state_size(const AgSim* sim);           /* floats per env */
 int    ag_state_get(AgSim* sim, float* out);      /* [N][state_size] host */
 int    ag_state_set(AgSim* sim, const float* in);

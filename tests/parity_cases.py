@@ -295,3 +295,49 @@ def readback_errors(fb, make_sim, n=4, seed=6):
                 derr = max(derr, abs(np.sort(pa[e, :na[e]]['distance'])[0] - np.sort(pb[e, :nb_[e]]['distance'])[0]))
     out['closest_dist'] = derr
     return out
+
+
+def population_errors(fb, make_sim, n=1024, seed=21, env_steps=40, threads=8, f32_control=True):
+    """The BENCHMARKED configuration (bench.py: foods on, default early exit at 1e-7, random actions), 200 substeps, as a
+    population: per-env maximum error of the product against the fp64 oracle, and -- the control -- of the fp32 build
+    of the SAME oracle against the fp64 one, which measures how much of the spread is fp32-vs-fp64 sensitivity
+    (1 g food spheres bouncing, active-set flips at the early exit) rather than the CUDA implementation.
+    Returns {name: {'q': [n], 'tool': [n], 'ee': [n]}} for name in ('product', 'oracle_f32')."""
+    cfg = capi.default_config()
+    cpu, dev, s = synced_pair(fb, make_sim, n, seed, cfg, threads=threads)
+    sims = {'product': dev}
+    if f32_control:
+        c32 = OracleSim(fb.scene, cfg, n, f32=True, threads=threads)
+        fb.reset(c32, np.random.default_rng(seed), settle_steps=0, sample=s)
+        c32.state_set(cpu.state_get())
+        c32.set_motor_targets(fb.arm_links, cpu.get_joint_states(fb.arm_links)[0])
+        sims['oracle_f32'] = c32
+    L = feeding_links(fb)
+    links = [L['tool'], L['ee']]
+    rng = np.random.default_rng(seed + 100)
+    out = {k: dict(q=np.zeros(n), tool=np.zeros(n), ee=np.zeros(n)) for k in sims}
+    for it in range(env_steps):
+        act = rng.uniform(-1, 1, size=(n, 7))
+        apply_tremor(fb, (cpu,) + tuple(sims.values()), s, it + 1)
+        tgt = take_step_targets(cpu.get_joint_states(fb.arm_links)[0], act, fb.arm_lower, fb.arm_upper)
+        for sim in (cpu,) + tuple(sims.values()):
+            sim.set_motor_targets(fb.arm_links, tgt)
+            sim.step(5)
+        qa, pa = cpu.get_joint_states(fb.arm_links)[0], cpu.get_link_states(links)['pos']
+        for k, sim in sims.items():
+            dq = np.abs(qa - sim.get_joint_states(fb.arm_links)[0]).max(axis=1)
+            dp = np.abs(pa - sim.get_link_states(links)['pos']).max(axis=2)
+            out[k]['q'] = np.maximum(out[k]['q'], dq)
+            out[k]['tool'] = np.maximum(out[k]['tool'], dp[:, 0])
+            out[k]['ee'] = np.maximum(out[k]['ee'], dp[:, 1])
+    return out
+
+
+def population_summary(e):
+    """median / p90 / p99 / max and the fraction of envs inside the north-star tolerances"""
+    r = {}
+    for k, tol in (('q', TOL_RAD), ('tool', TOL_M), ('ee', TOL_M)):
+        x = e[k]
+        r[k] = dict(median=float(np.median(x)), p90=float(np.quantile(x, 0.9)), p99=float(np.quantile(x, 0.99)), max=float(x.max()),
+                    within=float((x < tol).mean()))
+    return r

@@ -186,3 +186,22 @@ def test_overflow_determinism_gpu(feeding, mk_gpu):
 @pytest.mark.gpu
 def test_abi_errors_gpu(gpu_lib):
     _check_abi_errors(gpu_lib)
+
+
+@pytest.mark.gpu
+def test_entry_points_keep_the_callers_device(feeding, mk_gpu):
+    """every entry point runs on the sim's GPU and restores the caller's current device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        # one GPU: the guard must at least be a no-op that leaves device 0 current
+        sim = mk_gpu(feeding.scene, capi.default_config(), 4)
+        feeding.reset(sim, np.random.default_rng(0), settle_steps=1)
+        assert torch.cuda.current_device() == 0
+        return
+    torch.cuda.set_device(0)
+    from assistive_gym_b200.sim import BatchSim
+    sim = BatchSim(feeding.scene, capi.default_config(), 4, device=1)
+    feeding.reset(sim, np.random.default_rng(0), settle_steps=1)
+    sim.step(2)
+    assert np.all(np.isfinite(sim.state_get()))
+    assert torch.cuda.current_device() == 0

@@ -48,6 +48,55 @@ def test_rollout_strict_population(feeding, make_sim):
     assert np.median(q) < 1e-5 and (q < pc.TOL_RAD).mean() >= 0.9 and q.max() < 5e-3, err
 
 
+def test_benchmarked_config_population(feeding, make_sim):
+    """parity ON THE CONFIGURATION bench.py measures (foods on, early exit 1e-7, random actions)
+    at n = 1024 over 200 substeps, reported as a distribution, with the oracle's own fp32 build as the control.
+    Measured on the B200: the free-running rollout of this configuration is chaotic at the level
+    of the north-star tolerance -- the fp32 build of the ORACLE ITSELF ends up a median 1.4e-3 rad from its fp64 build --
+    so what can be asserted is (a) the CUDA build is as close to the fp64 oracle as the oracle's fp32 build is, quantile
+    by quantile, and (b) re-synchronised every env step, the CUDA build meets the tolerances for (nearly) every env."""
+    import json
+    import os
+    thr = max(1, len(os.sched_getaffinity(0)))
+    e = pc.population_errors(feeding, make_sim, n=1024, seed=21, env_steps=40, threads=thr)
+    prod, ctrl = pc.population_summary(e['product']), pc.population_summary(e['oracle_f32'])
+    print('population n=1024 foods on early exit: product', json.dumps(prod))
+    print('population n=1024 foods on early exit: oracle fp32 control', json.dumps(ctrl))
+    for k in ('q', 'tool', 'ee'):
+        assert prod[k]['within'] >= ctrl[k]['within'] - 0.05, (k, prod[k], ctrl[k])
+        for qn in ('median', 'p90', 'p99'):
+            assert prod[k][qn] <= 1.5 * ctrl[k][qn] + 1e-6, (k, qn, prod[k], ctrl[k])
+
+
+def test_benchmarked_config_resynchronised_population(feeding, make_sim):
+    """The same configuration at n = 1024, state copied from the oracle before every env step (5 substeps with the
+    default early exit): the step function itself, without chaotic drift."""
+    import json
+    import os
+    n = 1024
+    cfg = capi.default_config()
+    cpu, dev, s = pc.synced_pair(feeding, make_sim, n, 31, cfg, threads=max(1, len(os.sched_getaffinity(0))))
+    fb = feeding
+    L = pc.feeding_links(fb)
+    links = [L['tool'], L['ee']]
+    rng = np.random.default_rng(5)
+    eq, et = np.zeros(n), np.zeros(n)
+    for it in range(8):
+        act = rng.uniform(-1, 1, size=(n, 7))
+        tgt = pc.take_step_targets(cpu.get_joint_states(fb.arm_links)[0], act, fb.arm_lower, fb.arm_upper)
+        dev.state_set(cpu.state_get())
+        for sim in (cpu, dev):
+            sim.set_motor_targets(fb.arm_links, tgt)
+            sim.step(5)
+        eq = np.maximum(eq, np.abs(cpu.get_joint_states(fb.arm_links)[0] - dev.get_joint_states(fb.arm_links)[0]).max(axis=1))
+        et = np.maximum(et, np.abs(cpu.get_link_states(links)['pos'] - dev.get_link_states(links)['pos']).max(axis=(1, 2)))
+    res = dict(q=dict(median=float(np.median(eq)), p99=float(np.quantile(eq, 0.99)), max=float(eq.max()), within=float((eq < pc.TOL_RAD).mean())),
+               pos=dict(median=float(np.median(et)), p99=float(np.quantile(et, 0.99)), max=float(et.max()), within=float((et < pc.TOL_M).mean())))
+    print('resynchronised population n=1024 foods on early exit:', json.dumps(res))
+    assert res['q']['median'] < 1e-5 and res['pos']['median'] < 1e-5, res
+    assert res['q']['within'] >= 0.97 and res['pos']['within'] >= 0.99, res
+
+
 def test_onestep_synchronised(feeding, make_sim):
     err = pc.onestep_errors(feeding, make_sim, n=8, seed=1, steps=30)
     print('one-step errors', err)

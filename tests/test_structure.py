@@ -102,3 +102,20 @@ def test_package_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dirpath, f)).read()
                 assert 'oracle_py' not in src and 'liboracle' not in src and 'libagphys_emu' not in src, f
+
+
+def test_assistive_gym_shim_resolves_reference_ids():
+    """reference assistive_gym/__init__.py:6-13 + learn.py:61-69: `assistive_gym:<Task><Robot>-v1` ids and the env classes."""
+    import importlib
+    import assistive_gym
+    assert assistive_gym.__agphys_shim__
+    mod = importlib.import_module('assistive_gym.envs')
+    for env_id in ('FeedingJaco-v1', 'BedBathingSawyer-v1'):
+        cls = getattr(mod, env_id.split('-')[0] + 'Env')          # learn.py:65-66 (co-op path)
+        assert assistive_gym.ENV_REGISTRY[env_id] is cls
+    try:
+        assistive_gym.make('assistive_gym:DressingPR2-v1')
+    except KeyError as e:
+        assert 'not built' in str(e)
+    else:
+        raise AssertionError('an id that is not built must not resolve')
