@@ -284,6 +284,37 @@ class BedBathingBatch:
         sim.forward_kinematics()
         return s
 
+    def hover_over_forearm(self, sim, s, rng, gap=0.003):
+        """Start pose for the dense tool-skin contact workload: the arm is moved so that the
+        wiping pad hovers `gap` above the middle of the person's right forearm (any joint action then presses it onto the
+        skin or lifts it off).  Uses the sim's own closest-point query; returns the IK error per env."""
+        n = sim.n
+        male = s['male'].astype(bool)
+        mid = np.zeros((n, 3))
+        for g, hb in self.humans.items():
+            ls = sim.get_link_states([self.gl(hb, R_ELBOW), self.gl(hb, R_WRIST)])['pos']
+            on = male if g == 'male' else ~male
+            mid[on] = 0.5 * (ls[on, 0] + ls[on, 1])
+        arm = np.array(SAWYER['arm']) + 1
+
+        def put(q):
+            qfull = q.copy(); qfull[:, np.array(SAWYER['gripper']) + 1] = SAWYER['gripper_pos']
+            sim.set_joint_state(self.arm_links, q=q[:, arm], qd=np.zeros((n, 7)))
+            self.place_tool(sim, self.base_pos, self.base_quat, qfull)
+            sim.forward_kinematics()
+
+        q_hi, _ = self.solve_ik(self.base_pos, self.base_quat, mid + [0, 0, 0.25], rng, max_restarts=12, sim=sim, idx=np.arange(n))
+        put(q_hi)
+        d = np.full(n, np.inf)
+        for hb in self.humans.values():
+            c, k = sim.closest_points(self.tool, hb, 1.0, max_pts=32)
+            d = np.minimum(d, np.where(np.arange(32)[None, :] < k[:, None], c['distance'], np.inf).min(axis=1))
+        h0 = 0.25 - (np.where(np.isfinite(d), d, 0.25) - gap)
+        q_lo, err = self.solve_ik(self.base_pos, self.base_quat, mid + np.stack([0 * h0, 0 * h0, h0], axis=1), rng, max_restarts=12, sim=sim, idx=np.arange(n))
+        put(q_lo)
+        sim.set_motor_targets(self.arm_links, q_lo[:, arm])
+        return err
+
     # ------------------------------------------------------------------ wiping targets (generate_targets / update_targets)
     def targets_world(self, sim, s):
         """World positions [n, max_targets, 3] of the targets on the active person's right upper arm and forearm, a

@@ -191,6 +191,65 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def run_bedbathing(args):
+    """BASELINE.json configs[2]: BedBathingSawyer-v1 @ batch 4096 on one B200, fused step, from a start pose with the
+    wiping pad 3 mm above the forearm (random joint actions press it onto the skin): device-timed value + host-buffer e2e."""
+    import torch
+    from assistive_gym_b200 import capi
+    from assistive_gym_b200.bed_bathing_batch import BedBathingBatch
+    from assistive_gym_b200.sim import BatchSim
+    if args.impl == 'reference':
+        print(json.dumps({'impl': 'reference', 'unavailable': 'the bedbathing line has no CPU arm (the oracle is timed on the headline workload only)'}))
+        return
+    n, K, W = args.batch, args.steps, max(args.warmup, 3)
+    bb = BedBathingBatch()
+    sim = BatchSim(bb.scene, capi.default_config(), n)
+    rng = np.random.default_rng(0)
+    t0 = time.time()
+    s = bb.reset(sim, rng)
+    ik_err = bb.hover_over_forearm(sim, s, rng)
+    bb.start_fused(sim, s)
+    reset_s = time.time() - t0
+    stream = torch.cuda.ExternalStream(sim.stream_ptr())
+    dev = torch.device('cuda')
+    act = torch.rand((K + W, n, 7), device=dev) * 2 - 1
+    obs = torch.zeros((n, 24), device=dev); rew = torch.zeros(n, device=dev); done = torch.zeros(n, device=dev); info = torch.zeros((n, 4), device=dev)
+    torch.cuda.synchronize()
+    for i in range(W):
+        sim.bathing_step_dev(act[i].data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), info.data_ptr())
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0); clocks.start()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cs, fs = [], []
+    with torch.cuda.stream(stream):
+        a.record(stream)
+    for i in range(K):
+        sim.bathing_step_dev(act[W + i].data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), info.data_ptr())
+    with torch.cuda.stream(stream):
+        b.record(stream)
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms = a.elapsed_time(b) / K
+    cnt, it = sim.solver_stats()
+    host_a = np.random.default_rng(1).uniform(-1, 1, size=(K, n, 7)).astype(np.float32)
+    sim.bathing_step_host(host_a[0])
+    t0 = time.perf_counter()
+    for i in range(K):
+        sim.bathing_step_host(host_a[i])
+    e2e = n * K / (time.perf_counter() - t0)
+    force = info[:, 2].cpu().numpy()
+    print(json.dumps({'metric': 'env-steps/sec BedBathingSawyer-v1 @batch%d' % n, 'value': n / ms * 1e3, 'unit': 'env-steps/s', 'n_gpus': 1, 'steps': K, 'warmup': W,
+                      'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                      'config': {'workload': 'BedBathingSawyer-v1, batch %d, fused step, wiping pad started 3 mm above the forearm, random actions' % n,
+                                 'global_batch': n, 'l2': 'not flushed (back-to-back steps)', 'reset_s': reset_s,
+                                 'ik_unresolved': int((ik_err >= 0.03).sum()),
+                                 'contacts_per_env': {'mean': float(cnt.mean()), 'p99': float(np.percentile(cnt, 99)), 'max': int(cnt.max())},
+                                 'envs_with_tool_force': float((force > 0).mean()), 'tool_force_mean_N': float(force[force > 0].mean()) if (force > 0).any() else 0.0,
+                                 'pgs_iters_per_env': {'mean': float(it.mean()), 'max': int(it.max())}},
+                      'clocks': clk, 'e2e': {'value': e2e, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n * 7 * 4, 'd2h_bytes_per_step': n * 30 * 4},
+                      'gpu_launches': int(sim.kernel_launches())}))
+
+
 def ncu_traffic(kernel):
     """DRAM bytes (read + write) of one launch of `kernel` from the newest committed `ncu --set full` summary
     (profiles/r*_ncu_<kernel>.csv, written by tools/ncu_summary.py); (None, None) if there is none."""
@@ -232,8 +291,11 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='envs per GPU')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--profile-kernels', type=int, default=1)
+    ap.add_argument('--workload', default='feeding', choices=['feeding', 'bedbathing'], help="'bedbathing': BASELINE.json configs[2] (dense tool-skin contact), a secondary line")
     ap.add_argument('--sub-batches', type=int, default=int(os.environ.get('AG_SUB_BATCHES', '1')), help='independent sub-batches per GPU, each on its own stream')
     args = ap.parse_args()
+    if args.workload == 'bedbathing':
+        return run_bedbathing(args)
     if args.impl == 'reference':
         return run_reference(args)
 
