@@ -82,6 +82,62 @@ class AgBathingParams(C.Structure):
 
 import numpy as np  # noqa: E402
 
+class AgClothDesc(C.Structure):
+    _fields_ = [('n_nodes', C.c_int32), ('n_links', C.c_int32), ('n_colours', C.c_int32), ('n_nf', C.c_int32),
+                ('n_anchors', C.c_int32), ('n_col_links', C.c_int32),
+                ('links', C.c_void_p), ('link_rest2', C.c_void_p), ('colour_off', C.c_void_p), ('nf_off', C.c_void_p),
+                ('nf_pair', C.c_void_p), ('node_area', C.c_void_p), ('inv_mass', C.c_double),
+                ('kLST', C.c_double), ('kDP', C.c_double), ('kDG', C.c_double), ('kLF', C.c_double), ('kDF', C.c_double),
+                ('kCHR', C.c_double), ('kKHR', C.c_double), ('kAHR', C.c_double), ('margin', C.c_double),
+                ('air_density', C.c_double), ('piterations', C.c_int32), ('gravity', C.c_double * 3),
+                ('anchor_node', C.c_void_p), ('anchor_local', C.c_void_p), ('col_links', C.c_void_p),
+                ('col_link_bsphere', C.c_void_p), ('col_link_static', C.c_void_p), ('max_contacts', C.c_int32)]
+
+
+def link_bounding_spheres(scene, links):
+    """Bounding sphere (centre, radius) of each link's colliders in the link frame, from the scene arrays."""
+    out = np.zeros((len(links), 4))
+    col_link = np.asarray(scene['col_link'])
+    for i, k in enumerate(links):
+        cs = np.nonzero(col_link == k)[0]
+        if len(cs) == 0:
+            continue
+        lo = np.min([np.asarray(scene['col_center'])[c] - np.asarray(scene['col_half'])[c] - scene['col_radius'][c] for c in cs], axis=0)
+        hi = np.max([np.asarray(scene['col_center'])[c] + np.asarray(scene['col_half'])[c] + scene['col_radius'][c] for c in cs], axis=0)
+        if not np.all(np.isfinite(lo)) or np.any(hi - lo > 1e3):       # a half-space: never culled
+            out[i] = [0, 0, 0, 1e6]
+        else:
+            out[i, :3] = 0.5 * (lo + hi)
+            out[i, 3] = 0.5 * np.linalg.norm(hi - lo)
+    return out
+
+
+def make_cloth_desc(model, scene, col_links, col_static, anchor_nodes_public, anchor_local, gravity=(0, 0, -9.81),
+                    max_contacts=1024):
+    """AgClothDesc (+ the arrays it points to, to be kept alive) from a cloth.ClothModel.  Node ids inside are INTERNAL."""
+    P = model.params
+    keep = dict(
+        links=np.ascontiguousarray(model.links, dtype=np.int32), rest2=np.ascontiguousarray(model.link_rest2, dtype=np.float64),
+        coff=np.ascontiguousarray(model.colour_off, dtype=np.int32), nf_off=np.ascontiguousarray(model.nf_off, dtype=np.int32),
+        nf_pair=np.ascontiguousarray(model.nf_pair, dtype=np.int32), area=np.ascontiguousarray(model.node_area, dtype=np.float64),
+        anode=np.ascontiguousarray(model.rank[np.asarray(anchor_nodes_public, dtype=np.int64)], dtype=np.int32),
+        alocal=np.ascontiguousarray(anchor_local, dtype=np.float64).reshape(-1, 3),
+        clinks=np.ascontiguousarray(col_links, dtype=np.int32), cstatic=np.ascontiguousarray(col_static, dtype=np.int32),
+        bs=np.ascontiguousarray(link_bounding_spheres(scene, col_links), dtype=np.float64))
+    d = AgClothDesc(n_nodes=model.n_nodes, n_links=len(keep['links']), n_colours=model.n_colours, n_nf=len(keep['nf_pair']),
+                    n_anchors=len(keep['anode']), n_col_links=len(keep['clinks']),
+                    links=keep['links'].ctypes.data, link_rest2=keep['rest2'].ctypes.data, colour_off=keep['coff'].ctypes.data,
+                    nf_off=keep['nf_off'].ctypes.data, nf_pair=keep['nf_pair'].ctypes.data, node_area=keep['area'].ctypes.data,
+                    inv_mass=model.inv_mass, kLST=P['kLST'], kDP=P['kDP'], kDG=P['kDG'], kLF=P['kLF'], kDF=P['kDF'],
+                    kCHR=P['kCHR'], kKHR=P['kKHR'], kAHR=P['kAHR'], margin=P['margin'], air_density=P['air_density'],
+                    piterations=int(P['piterations']), gravity=(C.c_double * 3)(*gravity),
+                    anchor_node=keep['anode'].ctypes.data, anchor_local=keep['alocal'].ctypes.data,
+                    col_links=keep['clinks'].ctypes.data, col_link_bsphere=keep['bs'].ctypes.data,
+                    col_link_static=keep['cstatic'].ctypes.data, max_contacts=int(max_contacts))
+    d._keep = keep
+    return d
+
+
 CONTACT_DTYPE = np.dtype([('link_a', np.int32), ('link_b', np.int32), ('pos_a', np.float32, 3), ('pos_b', np.float32, 3),
                           ('normal', np.float32, 3), ('distance', np.float32), ('normal_force', np.float32)])
 assert CONTACT_DTYPE.itemsize == C.sizeof(AgContact)
@@ -134,6 +190,14 @@ def load_library(path=None):
     lib.ag_bathing_init.argtypes = [vp, C.POINTER(AgBathingParams), vp, vp, vp]
     lib.ag_bathing_step_dev.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.ag_bathing_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.ag_cloth_init.argtypes = [vp, C.POINTER(AgClothDesc)]
+    lib.ag_cloth_set_state.argtypes = [vp, vp, vp, vp]
+    lib.ag_cloth_get_state.argtypes = [vp, vp, vp]
+    lib.ag_cloth_set_anchor.argtypes = [vp, vp, vp]
+    lib.ag_cloth_anchor_follow.argtypes = [vp, ci]
+    lib.ag_cloth_set_gravity.argtypes = [vp, vp]
+    lib.ag_cloth_get_contacts.argtypes = [vp, ci, vp, vp, vp, vp, vp]
+    lib.ag_cloth_device_state.argtypes = [vp, vp, vp, vp]
     lib.ag_ik_solve.argtypes = [vp, ci, vp, ci, vp, vp, ci, ci, C.c_float, C.c_uint64, vp, vp, vp]
     lib.ag_state_size.restype = C.c_size_t
     lib.ag_state_size.argtypes = [vp]
@@ -160,5 +224,7 @@ EXPORTED_SYMBOLS = [
     'ag_step', 'ag_get_joint_states', 'ag_get_link_states', 'ag_get_contacts', 'ag_contact_force_sum',
     'ag_closest_points', 'ag_feeding_init', 'ag_feeding_reset_episode', 'ag_feeding_set_tremor', 'ag_set_hard_limits', 'ag_feeding_step_dev', 'ag_ik_solve', 'ag_bathing_init', 'ag_bathing_step_dev', 'ag_bathing_step_host',
     'ag_feeding_step_host', 'ag_feeding_step_host_begin', 'ag_feeding_step_host_end', 'ag_state_size', 'ag_state_get', 'ag_state_set', 'ag_kernel_launches',
+    'ag_cloth_init', 'ag_cloth_set_state', 'ag_cloth_get_state', 'ag_cloth_set_anchor', 'ag_cloth_anchor_follow', 'ag_cloth_set_gravity',
+    'ag_cloth_get_contacts', 'ag_cloth_device_state',
     'ag_overflow_count', 'ag_get_solver_stats', 'ag_get_pgs_cycles', 'ag_get_pgs_trips', 'ag_profile_enable', 'ag_profile_get',
 ]

@@ -1,0 +1,466 @@
+// ag_cloth.cuh — K8: the cloth of the Dressing task (reference envs/dressing.py:25 getSoftBodyData, :146-154 loadCloth /
+// clothParams, :184 numSubSteps = 8, :210 the attachment teleported to the end effector).
+//
+// What it restates (Bullet's btSoftBody position-based solver, recalled -- DESIGN.md section 9; every coefficient is a
+// field of AgClothDesc): per substep of dt/numSubSteps
+//   predictMotion:   v += g dt; aerodynamic drag (kDG, V_Point model incl. ApplyClampedForce); q = x; x += v dt
+//   collisions:      node vs rigid shapes at the START-of-substep link poses, signed distance < margin -> rigid contact
+//                    (normal, plane offset, friction switch c3 from the predicted motion)
+//   position solver: piterations x [anchors (kAHR), rigid contacts (kCHR / kKHR, kDF), links (kLST) in list order]
+//   velocities:      v = (x - q) / dt * (1 - kDP)
+// Multibody link colliders are not btRigidBody, so Bullet of the reference's era treats them as static shapes with zero
+// velocity: the coupling is one way (cloth feels the bodies, bodies do not feel the cloth).  That is what makes the B200
+// mapping below possible: the rigid substeps of one stepSimulation run first and leave the link poses of every substep in
+// a snapshot buffer; ONE launch of k_cloth then advances the cloth through all numSubSteps substeps.
+//
+// B200 mapping.  One CTA of 1024 threads per env, the env's node positions resident in shared memory as float4 (64 KB) for
+// the whole launch; previous positions q and velocities v of a thread's own nodes (node = k * 1024 + thread) live in its
+// registers.  HBM traffic per env and launch: x and v read once and written once (190 KB) instead of once per substep.
+// Links are relaxed colour by colour (links of one colour share no node; the list is colour-major, so this is the
+// sequential Gauss-Seidel sweep of the list), one __syncthreads per colour.  Contacts are found by the owner thread of a
+// node, slots are assigned by a block-wide prefix sum (deterministic order), solved by the owner thread.
+#pragma once
+#include "ag_device.cuh"
+
+#define AG_CLOTH_T 1024          // threads per CTA (= envs are independent CTAs)
+#define AG_CLOTH_MAXANCH 8
+#define AG_CLOTH_MAXCL 64        // collider links per env
+#define AG_CLOTH_MAXCOL 16       // link colours
+#define AG_CLOTH_HITS 6          // contacts one thread can find per substep (over its <= NPT nodes)
+#define AG_CLOTH_EPS 1.1920929e-7f
+#define AG_CLOTH_CCF 8           // floats per exported contact: node, x, y, z, fx, fy, fz, link
+
+struct ClothDev {
+  int nn, nnp, nlinks, ncol, nanch, ncl, maxcc, K, piters, export_contacts;
+  float dt, im, kLSTh, kDP, kDG, kLF, kDF, kCHR, kKHR, kAHR, margin, density;
+  float gx, gy, gz;
+  int col_off[AG_CLOTH_MAXCOL + 1];
+  int anch_node[AG_CLOTH_MAXANCH];
+  float anch_local[AG_CLOTH_MAXANCH][3];
+  // template tables
+  const unsigned* link_ij;     // [nlinks] node i | node j << 16, colour-major
+  const float* link_rest2;     // [nlinks]
+  const int* nf_off;           // [nn + 1]
+  const unsigned* nf_pair;     // [nf] next | next-next << 16 (face winding)
+  const float* node_area;      // [nn]
+  const int* cl_link;          // [ncl] global link ids of the rigid links the cloth collides with
+  const float* cl_bs;          // [ncl][4] bounding sphere of the link's colliders in the link frame
+  const int* cl_static;        // [ncl] 1: static shape (kKHR), 0: movable (kCHR)
+  // per-env state
+  float* x;                    // [N][3][nnp]
+  float* v;                    // [N][3][nnp]
+  float* anchor_pos;           // [3][N] position of the (kinematic, identity-orientation) anchor body
+  float* snap;                 // [K][ncl][7][N] link poses at the start of each substep
+  // outputs of the last substep of a launch
+  int* cc_count;               // [N]
+  float* cc_data;              // [N][maxcc][AG_CLOTH_CCF]
+  int* overflow;               // [N]
+};
+
+struct ClothContact { f3 n; float offset, c3, c4; f3 acc; int node, link; };
+
+// signed distance of a point (link frame) to the union of the link's colliders, outward normal of the nearest one
+AG_HDN inline float cloth_sdf_link(const SimDev& S, int link, f3 p, f3& nrm) {
+  int c0 = AG_LDG(S.link_col0 + link), nc = AG_LDG(S.link_ncol + link);
+  float best = 1e30f;
+  nrm = f3(0.f, 0.f, 1.f);
+  for (int c = c0; c < c0 + nc; c++) {
+    int type = AG_LDG(S.col_type + c), v0 = AG_LDG(S.col_v0 + c);
+    float r = AG_LDG(S.col_radius + c), d; f3 n;
+    if (type == 0 /*sphere*/ || type == 1 /*capsule*/) {
+      f3 a = tv3(S.verts, v0), cp = a;
+      if (type == 1) {
+        f3 ab = tv3(S.verts, v0 + 1) - a;
+        float t = clampf(dot(p - a, ab) / fmaxf(dot(ab, ab), 1e-20f), 0.f, 1.f);
+        cp = a + ab * t;
+      }
+      f3 w = p - cp; float L = norm(w);
+      d = L - r; n = L > 1e-12f ? w * (1.f / L) : f3(0.f, 0.f, 1.f);
+    } else {                         // hull / half-space: the face plane the point is farthest outside of (exact inside)
+      int p0 = AG_LDG(S.col_p0 + c), np = AG_LDG(S.col_np + c);
+      float m = -1e30f; n = f3(0.f, 0.f, 1.f);
+      for (int k = p0; k < p0 + np; k++) { f3 pn; float pd; ld_plane(S.planes, k, pn, pd); float s = dot(pn, p) - pd; if (s > m) { m = s; n = pn; } }
+      d = m - r;
+    }
+    if (d < best) { best = d; nrm = n; }
+  }
+  return best;
+}
+
+struct ClothLinkPose { m3 R; f3 pos; f3 bc; float br; };   // world pose of a collider link + its bounding sphere (margin included)
+
+AG_HD ClothLinkPose cloth_link_pose(const ClothDev& C, int sub, int L, int N, int e) {
+  const float* s = C.snap + ((size_t)(sub * C.ncl + L) * 7) * N + e;
+  ClothLinkPose P;
+  P.pos = f3(s[0], s[(size_t)N], s[2 * (size_t)N]);
+  P.R = qmat(q4(s[3 * (size_t)N], s[4 * (size_t)N], s[5 * (size_t)N], s[6 * (size_t)N]));
+  f3 bl(AG_LDG(C.cl_bs + 4 * L), AG_LDG(C.cl_bs + 4 * L + 1), AG_LDG(C.cl_bs + 4 * L + 2));
+  P.bc = P.pos + mul(P.R, bl); P.br = AG_LDG(C.cl_bs + 4 * L + 3) + C.margin;
+  return P;
+}
+
+// node vs collider link L (Bullet btSoftColliders::CollideSDF_RS::DoNode + btSoftBody::checkContact, static shape)
+AG_HD bool cloth_detect(const SimDev& S, const ClothDev& C, const ClothLinkPose& P, int L, int N, int e, f3 x, f3 q, ClothContact& c) {
+  f3 w = x - P.bc;
+  if (dot(w, w) > P.br * P.br) return false;
+  int link = AG_LDG(C.cl_link + L);
+  f3 nl;
+  float dst = cloth_sdf_link(S, link, mulT(P.R, x - P.pos), nl) - C.margin;
+  if (!(dst < 0.f)) return false;
+  c.n = mul(P.R, nl);
+  c.offset = -dot(c.n, x - c.n * dst);
+  f3 vr = x - q;                                   // va = 0 (static shape)
+  float dn = dot(vr, c.n);
+  f3 fv = vr - c.n * dn;
+  float fc = C.kDF * S.friction[(size_t)link * N + e];
+  c.c3 = dot(fv, fv) < (dn * fc) * (dn * fc) ? 0.f : 1.f - fc;
+  c.c4 = AG_LDG(C.cl_static + L) ? C.kKHR : C.kCHR;
+  c.acc = f3(0.f, 0.f, 0.f);
+  c.link = link;
+  return true;
+}
+
+// btSoftBody::PSolve_RContacts for one contact of a node (c0 * c2 = identity for a static shape)
+AG_HD void cloth_contact_solve(f3& x, f3 q, f3 n, float offset, float c3, float c4, float mrg, f3& acc) {
+  f3 vr = x - q;
+  float dn = dot(vr, n);
+  if (dn <= AG_CLOTH_EPS) {
+    float dp = fminf(dot(x, n) + offset, mrg);
+    f3 fv = vr - n * dn;
+    f3 d = vr - fv * c3 + n * (dp * c4);
+    x -= d; acc += d;
+  }
+}
+// btSoftBody::PSolve_Anchors for a static, identity-orientation anchor body at `ap`
+AG_HD void cloth_anchor_solve(f3& x, f3 q, f3 wa, float kAHR) { x += (q - x) + (wa - x) * kAHR; }
+
+// btSoftBody::predictMotion for one node: gravity, aerodynamics (addAeroForceToNode, V_Point; the reference sets kDG = 10),
+// explicit Euler.  `nrm` is the node normal of the start-of-substep configuration (normalised sum of face cross products).
+AG_HD void cloth_predict(const ClothDev& C, f3 nrm, float area, f3& x, f3& v) {
+  const float dt = C.dt;
+  v += f3(C.gx, C.gy, C.gz) * dt;
+  f3 f(0.f, 0.f, 0.f);
+  float v2 = dot(v, v);
+  if ((C.kDG > 0.f || C.kLF > 0.f) && v2 > AG_CLOTH_EPS) {
+    f3 vn = v * (1.f / sqrtf(v2));
+    float dvn = dot(v, nrm);
+    if (dvn < 0.f) { nrm = -nrm; dvn = -dvn; }       // Bullet flips the normal towards the flow for every V_ model
+    if (dvn > 0.f) {
+      float c1 = area * dvn * v2 * 0.5f * C.density;
+      f3 force = nrm * (-c1 * C.kLF) + vn * (-c1 * C.kDG);
+      float dtim = dt * C.im;
+      f3 fd = force * dtim;
+      if (dot(fd, fd) > v2) {                          // ApplyClampedForce: never reverse the velocity
+        f3 fn = force * (1.f / norm(force));
+        f -= fn * (dot(v, fn) / dtim);
+      } else f += force;
+    }
+  }
+  v += f * (C.im * dt);
+  x += v * dt;
+}
+
+// btSoftBody::PSolve_Links for one link, uniform node mass: c0 = 2 im / kLST, k im = (c1 - len) / (c1 + len) * kLST / 2
+AG_HD void cloth_link_solve(f3& a, f3& b, float rest2, float kLSTh) {
+  f3 del = b - a;
+  float len = dot(del, del);
+  if (rest2 + len > AG_CLOTH_EPS) {
+    float s = (rest2 - len) / (rest2 + len) * kLSTh;
+    a -= del * s; b += del * s;
+  }
+}
+
+// ------------------------------------------------------------------ small per-lane kernels
+// snapshot of the collider links' poses at the start of substep p.i0 (thread = (collider link, env))
+AG_HDN inline void cloth_snap_body(int tid, const SimDev& S, const KP& p) {
+  const ClothDev& C = *(const ClothDev*)p.p0;
+  const int N = S.N, e = tid % N, L = tid / N;
+  int link = AG_LDG(C.cl_link + L);
+  float* s = C.snap + ((size_t)(p.i0 * C.ncl + L) * 7) * N + e;
+  f3 lp = ld3(S.lpos, link, N, e); q4 lq = ld4(S.lquat, link, N, e);
+  s[0] = lp.x; s[(size_t)N] = lp.y; s[2 * (size_t)N] = lp.z;
+  s[3 * (size_t)N] = lq.x; s[4 * (size_t)N] = lq.y; s[5 * (size_t)N] = lq.z; s[6 * (size_t)N] = lq.w;
+}
+// the anchor body follows a link (reference dressing.py:210 update_targets; thread = env)
+AG_HDN inline void cloth_follow_body(int tid, const SimDev& S, const KP& p) {
+  const ClothDev& C = *(const ClothDev*)p.p0;
+  st3(C.anchor_pos, 0, S.N, tid, ld3(S.lpos, p.i0, S.N, tid));
+}
+
+// ------------------------------------------------------------------ K8: the cloth kernel
+#if defined(__CUDACC__) && !defined(AG_CPU_EMU)
+template <int NPT>
+__global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
+  extern __shared__ __align__(16) float cl_smem[];
+  constexpr int T = AG_CLOTH_T;
+  const int N = S.N, e = blockIdx.x, t = threadIdx.x;
+  float4* xs = (float4*)cl_smem;                               // [NPT * T]
+  float* lk = cl_smem + 4 * NPT * T;                           // [ncl][16]  R, pos, bounding sphere
+  float* pool = lk + 16 * AG_CLOTH_MAXCL;                      // [maxcc][12] n, offset | c3, c4, node, link | acc, -
+  int* misc = (int*)(pool + 12 * C.maxcc);                     // [40] warp sums for the scan, total
+  const int nn = C.nn;
+  const size_t xb = (size_t)e * 3 * C.nnp;
+  f3 q[NPT], v[NPT];
+  // ---- load
+#pragma unroll
+  for (int k = 0; k < NPT; k++) {
+    int i = k * T + t;
+    f3 xx(0.f, 0.f, 0.f); v[k] = f3(0.f, 0.f, 0.f);
+    if (i < nn) {
+      xx = f3(C.x[xb + i], C.x[xb + C.nnp + i], C.x[xb + 2 * (size_t)C.nnp + i]);
+      v[k] = f3(C.v[xb + i], C.v[xb + C.nnp + i], C.v[xb + 2 * (size_t)C.nnp + i]);
+    }
+    xs[i] = make_float4(xx.x, xx.y, xx.z, 0.f);
+    q[k] = xx;
+  }
+  const f3 ap = ld3(C.anchor_pos, 0, N, e);
+  int total = 0;
+  __syncthreads();
+  for (int sub = 0; sub < C.K; sub++) {
+    // ---- collider link poses of this substep
+    if (t < C.ncl) {
+      ClothLinkPose P = cloth_link_pose(C, sub, t, N, e);
+      float* o = lk + 16 * t;
+#pragma unroll
+      for (int a = 0; a < 9; a++) o[a] = P.R.m[a];
+      o[9] = P.pos.x; o[10] = P.pos.y; o[11] = P.pos.z; o[12] = P.bc.x; o[13] = P.bc.y; o[14] = P.bc.z; o[15] = P.br;
+    }
+    // ---- predict own nodes (reads the neighbours' start-of-substep positions for the node normal)
+    f3 xn[NPT];
+#pragma unroll
+    for (int k = 0; k < NPT; k++) {
+      int i = k * T + t;
+      xn[k] = q[k];
+      if (i < nn) {
+        float4 me = xs[i]; f3 a(me.x, me.y, me.z);
+        q[k] = a;
+        f3 ns(0.f, 0.f, 0.f);
+        int f0 = __ldg(C.nf_off + i), f1 = __ldg(C.nf_off + i + 1);
+        for (int f = f0; f < f1; f++) {
+          unsigned pr = __ldg(C.nf_pair + f);
+          float4 b4 = xs[pr & 0xffffu], c4 = xs[pr >> 16];
+          ns += cross(f3(b4.x, b4.y, b4.z) - a, f3(c4.x, c4.y, c4.z) - a);
+        }
+        float nl = norm(ns);
+        if (nl > AG_CLOTH_EPS) ns = ns * (1.f / nl);
+        f3 xx = a;
+        cloth_predict(C, ns, __ldg(C.node_area + i), xx, v[k]);
+        xn[k] = xx;
+      }
+    }
+    __syncthreads();                                           // every normal is computed, link poses are written
+    // ---- publish the prediction, find contacts of own nodes
+    int hits[AG_CLOTH_HITS]; int nh = 0; bool over = false;
+#pragma unroll
+    for (int k = 0; k < NPT; k++) {
+      int i = k * T + t;
+      if (i < nn) {
+        xs[i] = make_float4(xn[k].x, xn[k].y, xn[k].z, 0.f);
+        bool anchored = false;
+        for (int a = 0; a < C.nanch; a++) anchored |= C.anch_node[a] == i;
+        if (!anchored) {
+          for (int L = 0; L < C.ncl; L++) {
+            const float* o = lk + 16 * L;
+            f3 w = xn[k] - f3(o[12], o[13], o[14]);
+            if (dot(w, w) > o[15] * o[15]) continue;
+            ClothLinkPose P;
+            for (int a = 0; a < 9; a++) P.R.m[a] = o[a];
+            P.pos = f3(o[9], o[10], o[11]); P.bc = f3(o[12], o[13], o[14]); P.br = o[15];
+            ClothContact c;
+            if (cloth_detect(S, C, P, L, N, e, xn[k], q[k], c)) { if (nh < AG_CLOTH_HITS) hits[nh++] = (k << 8) | L; else over = true; }
+          }
+        }
+      }
+    }
+    // block-wide exclusive prefix sum of nh -> deterministic contact slots
+    int incl = nh;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, d); if ((t & 31) >= d) incl += o; }
+    if ((t & 31) == 31) misc[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32) {
+      int w = misc[t], wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, wi, d); if (t >= d) wi += o; }
+      misc[t] = wi - w;
+      if (t == 31) misc[32] = wi;
+    }
+    __syncthreads();
+    const int base = misc[t >> 5] + incl - nh;
+    total = misc[32];
+    if (total > C.maxcc) { over = true; total = C.maxcc; }
+    for (int h = 0; h < nh; h++) {
+      int slot = base + h;
+      if (slot >= C.maxcc) break;
+      int k = hits[h] >> 8, L = hits[h] & 0xff;
+      const float* o = lk + 16 * L;
+      ClothLinkPose P;
+      for (int a = 0; a < 9; a++) P.R.m[a] = o[a];
+      P.pos = f3(o[9], o[10], o[11]); P.bc = f3(o[12], o[13], o[14]); P.br = o[15];
+      f3 xk(0.f, 0.f, 0.f), qk(0.f, 0.f, 0.f);
+#pragma unroll
+      for (int kk = 0; kk < NPT; kk++) if (kk == k) { xk = xn[kk]; qk = q[kk]; }
+      ClothContact c;
+      cloth_detect(S, C, P, L, N, e, xk, qk, c);
+      float* r = pool + 12 * slot;
+      r[0] = c.n.x; r[1] = c.n.y; r[2] = c.n.z; r[3] = c.offset; r[4] = c.c3; r[5] = c.c4;
+      r[6] = __int_as_float(k * T + t); r[7] = __int_as_float(c.link); r[8] = 0.f; r[9] = 0.f; r[10] = 0.f;
+    }
+    if (over) C.overflow[e] = 1;
+    __syncthreads();
+    // ---- position solver
+    for (int it = 0; it < C.piters; it++) {
+      // anchors and rigid contacts touch only the owner's nodes
+      for (int a = 0; a < C.nanch; a++) {
+        int i = C.anch_node[a];
+        if ((i & (T - 1)) == t) {
+          float4 me = xs[i]; f3 xx(me.x, me.y, me.z), qq(0.f, 0.f, 0.f);
+#pragma unroll
+          for (int kk = 0; kk < NPT; kk++) if (kk == i / T) qq = q[kk];
+          cloth_anchor_solve(xx, qq, ap + f3(C.anch_local[a][0], C.anch_local[a][1], C.anch_local[a][2]), C.kAHR);
+          xs[i] = make_float4(xx.x, xx.y, xx.z, 0.f);
+        }
+      }
+      for (int h = 0; h < nh; h++) {
+        int slot = base + h;
+        if (slot >= C.maxcc) break;
+        int k = hits[h] >> 8, i = k * T + t;
+        float* r = pool + 12 * slot;
+        float4 me = xs[i]; f3 xx(me.x, me.y, me.z), qq(0.f, 0.f, 0.f), acc(r[8], r[9], r[10]);
+#pragma unroll
+        for (int kk = 0; kk < NPT; kk++) if (kk == k) qq = q[kk];
+        cloth_contact_solve(xx, qq, f3(r[0], r[1], r[2]), r[3], r[4], r[5], C.margin, acc);
+        xs[i] = make_float4(xx.x, xx.y, xx.z, 0.f);
+        r[8] = acc.x; r[9] = acc.y; r[10] = acc.z;
+      }
+      __syncthreads();
+      for (int col = 0; col < C.ncol; col++) {
+        for (int l = C.col_off[col] + t; l < C.col_off[col + 1]; l += T) {
+          unsigned ij = __ldg(C.link_ij + l);
+          float r2 = __ldg(C.link_rest2 + l);
+          int i = ij & 0xffffu, j = ij >> 16;
+          float4 a4 = xs[i], b4 = xs[j];
+          f3 a(a4.x, a4.y, a4.z), b(b4.x, b4.y, b4.z);
+          cloth_link_solve(a, b, r2, C.kLSTh);
+          xs[i] = make_float4(a.x, a.y, a.z, 0.f); xs[j] = make_float4(b.x, b.y, b.z, 0.f);
+        }
+        __syncthreads();
+      }
+    }
+    // ---- velocities
+    const float vc = (1.f - C.kDP) / C.dt;
+#pragma unroll
+    for (int k = 0; k < NPT; k++) {
+      int i = k * T + t;
+      if (i < nn) { float4 me = xs[i]; v[k] = (f3(me.x, me.y, me.z) - q[k]) * vc; }
+    }
+    // (the next substep's prediction reads xs, final since the last colour's barrier; the contact pool is rewritten only
+    //  after that substep's first barrier, the link poses before it -- both were last read before the barrier above)
+  }
+  // ---- store
+#pragma unroll
+  for (int k = 0; k < NPT; k++) {
+    int i = k * T + t;
+    if (i < nn) {
+      float4 me = xs[i];
+      C.x[xb + i] = me.x; C.x[xb + C.nnp + i] = me.y; C.x[xb + 2 * (size_t)C.nnp + i] = me.z;
+      C.v[xb + i] = v[k].x; C.v[xb + C.nnp + i] = v[k].y; C.v[xb + 2 * (size_t)C.nnp + i] = v[k].z;
+    }
+  }
+  // contacts of the last substep: node, position, force = accumulated correction / (im dt^2)
+  if (t == 0) C.cc_count[e] = total;
+  if (C.export_contacts) {
+    const float fs = 1.f / (C.im * C.dt * C.dt);
+    for (int s = t; s < total; s += T) {
+      const float* r = pool + 12 * s;
+      int i = __float_as_int(r[6]);
+      float4 me = xs[i];
+      float* o = C.cc_data + ((size_t)e * C.maxcc + s) * AG_CLOTH_CCF;
+      o[0] = r[6]; o[1] = me.x; o[2] = me.y; o[3] = me.z; o[4] = -r[8] * fs; o[5] = -r[9] * fs; o[6] = -r[10] * fs; o[7] = r[7];
+    }
+  }
+}
+#endif
+
+// ------------------------------------------------------------------ host restatement of the device loop (CPU harness)
+// Same per-node / per-link functions, plain loops: nodes in thread-major order (so contact slots come out in the order the
+// block-wide prefix sum gives them), links in list order.
+#if !defined(__CUDA_ARCH__)
+#include <vector>
+static inline void cloth_env_host(const SimDev& S, const ClothDev& C, int e) {
+  const int N = S.N, T = AG_CLOTH_T, nn = C.nn, NPT = (nn + T - 1) / T;
+  const size_t xb = (size_t)e * 3 * C.nnp;
+  std::vector<f3> x(nn), q(nn), v(nn), xn(nn);
+  for (int i = 0; i < nn; i++) {
+    x[i] = f3(C.x[xb + i], C.x[xb + C.nnp + i], C.x[xb + 2 * (size_t)C.nnp + i]);
+    v[i] = f3(C.v[xb + i], C.v[xb + C.nnp + i], C.v[xb + 2 * (size_t)C.nnp + i]);
+  }
+  const f3 ap = ld3(C.anchor_pos, 0, N, e);
+  std::vector<ClothContact> cc;
+  for (int sub = 0; sub < C.K; sub++) {
+    std::vector<ClothLinkPose> P(C.ncl);
+    for (int L = 0; L < C.ncl; L++) P[L] = cloth_link_pose(C, sub, L, N, e);
+    for (int i = 0; i < nn; i++) {
+      q[i] = x[i];
+      f3 ns(0.f, 0.f, 0.f);
+      for (int f = C.nf_off[i]; f < C.nf_off[i + 1]; f++) {
+        unsigned pr = C.nf_pair[f];
+        ns += cross(x[pr & 0xffffu] - x[i], x[pr >> 16] - x[i]);
+      }
+      float nl = norm(ns);
+      if (nl > AG_CLOTH_EPS) ns = ns * (1.f / nl);
+      xn[i] = x[i];
+      cloth_predict(C, ns, C.node_area[i], xn[i], v[i]);
+    }
+    x = xn;
+    cc.clear();
+    bool over = false;
+    for (int t = 0; t < T; t++) {
+      int nh = 0;
+      for (int k = 0; k < NPT; k++) {
+        int i = k * T + t;
+        if (i >= nn) continue;
+        bool anchored = false;
+        for (int a = 0; a < C.nanch; a++) anchored |= C.anch_node[a] == i;
+        if (anchored) continue;
+        for (int L = 0; L < C.ncl; L++) {
+          ClothContact c;
+          if (cloth_detect(S, C, P[L], L, N, e, x[i], q[i], c)) {
+            if (nh < AG_CLOTH_HITS) { nh++; c.node = i; cc.push_back(c); } else over = true;
+          }
+        }
+      }
+    }
+    if ((int)cc.size() > C.maxcc) { over = true; cc.resize(C.maxcc); }
+    if (over) C.overflow[e] = 1;
+    for (int it = 0; it < C.piters; it++) {
+      for (int a = 0; a < C.nanch; a++) {
+        int i = C.anch_node[a];
+        cloth_anchor_solve(x[i], q[i], ap + f3(C.anch_local[a][0], C.anch_local[a][1], C.anch_local[a][2]), C.kAHR);
+      }
+      for (auto& c : cc) cloth_contact_solve(x[c.node], q[c.node], c.n, c.offset, c.c3, c.c4, C.margin, c.acc);
+      for (int l = 0; l < C.nlinks; l++) {
+        unsigned ij = C.link_ij[l];
+        cloth_link_solve(x[ij & 0xffffu], x[ij >> 16], C.link_rest2[l], C.kLSTh);
+      }
+    }
+    const float vc = (1.f - C.kDP) / C.dt;
+    for (int i = 0; i < nn; i++) v[i] = (x[i] - q[i]) * vc;
+  }
+  for (int i = 0; i < nn; i++) {
+    C.x[xb + i] = x[i].x; C.x[xb + C.nnp + i] = x[i].y; C.x[xb + 2 * (size_t)C.nnp + i] = x[i].z;
+    C.v[xb + i] = v[i].x; C.v[xb + C.nnp + i] = v[i].y; C.v[xb + 2 * (size_t)C.nnp + i] = v[i].z;
+  }
+  C.cc_count[e] = (int)cc.size();
+  if (C.export_contacts) {
+    const float fs = 1.f / (C.im * C.dt * C.dt);
+    for (size_t s = 0; s < cc.size(); s++) {
+      float* o = C.cc_data + ((size_t)e * C.maxcc + s) * AG_CLOTH_CCF;
+      int i = cc[s].node;
+      union { int i; float f; } u; u.i = i; o[0] = u.f;
+      o[1] = x[i].x; o[2] = x[i].y; o[3] = x[i].z; o[4] = -cc[s].acc.x * fs; o[5] = -cc[s].acc.y * fs; o[6] = -cc[s].acc.z * fs;
+      u.i = cc[s].link; o[7] = u.f;
+    }
+  }
+}
+#endif

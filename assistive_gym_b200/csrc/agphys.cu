@@ -14,6 +14,7 @@
 #include "ag_feeding.cuh"
 #include "ag_bathing.cuh"
 #include "ag_ik.cuh"
+#include "ag_cloth.cuh"
 
 #ifndef AG_CPU_EMU
 #include <cuda_runtime.h>
@@ -102,6 +103,8 @@ AG_KERNEL(k_ik, ik_body)
 AG_KERNEL(k_bath_pre, bathing_pre_body)
 AG_KERNEL(k_bath_dist, bathing_dist_body)
 AG_KERNEL(k_bath_post, bathing_post_body)
+AG_KERNEL(k_cloth_snap, cloth_snap_body)
+AG_KERNEL(k_cloth_follow, cloth_follow_body)
 
 // ------------------------------------------------------------------ host object
 struct AgSim {
@@ -124,6 +127,8 @@ struct AgSim {
   float *h_bpin_in, *h_bpin_out, *d_baction, *d_bobs, *d_breward, *d_bdone, *d_binfo;
   float *d_action, *d_obs, *d_reward, *d_done, *d_info;
   float *h_pin_in, *h_pin_out;
+  // cloth (Dressing): one k_cloth launch per stepSimulation = `C.K` rigid substeps
+  ClothDev C; ClothDev* C_dev; bool cloth; int cloth_sub, cloth_npt;
   // CUDA-graph replay of the fused env step (one graph per entry point, keyed by its device pointers)
   bool use_graph; int graph_failures;
   struct StepGraph { void* exec; const void* key[5]; uint64_t launches; bool valid; } graphs[2];
@@ -280,7 +285,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   AgSim* s = new AgSim();
   memset(&s->S, 0, sizeof(SimDev));
   memset(&s->F, 0, sizeof(FeedDev));
-  s->cfg = *cfg; s->device = device; s->launches = 0; s->feeding = false; s->bathing = false; s->use_graph = true; s->graph_failures = 0; s->graphs[0].valid = s->graphs[1].valid = false; s->B_dev = nullptr; s->stream = nullptr; s->F_dev = nullptr; s->profiling = false;
+  s->cfg = *cfg; s->device = device; s->launches = 0; s->feeding = false; s->bathing = false; s->cloth = false; s->cloth_sub = 0; s->C_dev = nullptr; s->use_graph = true; s->graph_failures = 0; s->graphs[0].valid = s->graphs[1].valid = false; s->B_dev = nullptr; s->stream = nullptr; s->F_dev = nullptr; s->profiling = false;
   s->d_stage = nullptr; s->stage_floats = 0;
 #ifndef AG_CPU_EMU
   { int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { g_err = "no such CUDA device (is a CUDA device present? there is no CPU fallback)"; delete s; return nullptr; } }
@@ -681,11 +686,16 @@ int ag_set_motor_targets_host(AgSim* s, int n, const int32_t* links, const float
   return scatter_host(s, s->S.motor_target, 1, n, links, target, nullptr);
 }
 
+static void cloth_launch(AgSim* s);
 static void substep(AgSim* s) {
   SimDev& S = s->S;
   const int N = S.N;
   KP z = kp0();
   LAUNCH(s, k_fk, (size_t)S.nb * N, z);
+  if (s->cloth) {                                      // the cloth collides with the link poses at the START of the substep
+    KP cs = kp0(); cs.p0 = s->C_dev; cs.i0 = s->cloth_sub;
+    LAUNCH(s, k_cloth_snap, (size_t)s->C.ncl * N, cs);
+  }
   KP a = kp0(); a.p0 = S.movcol; a.i0 = S.nmovcol;
   LAUNCH(s, k_aabb, (size_t)S.nmovcol * N, a);
   KP l = kp0(); l.p0 = S.movlink; l.i0 = S.nmovlink;
@@ -720,6 +730,7 @@ static void substep(AgSim* s) {
   LAUNCH(s, k_pgs, N, z);
   LAUNCH(s, k_integrate, N, z);                      // (fused into k_pgs on the device)
 #endif
+  if (s->cloth && ++s->cloth_sub == s->C.K) { s->cloth_sub = 0; cloth_launch(s); }
 }
 
 int ag_step(AgSim* s, int n_steps) {
@@ -957,6 +968,170 @@ static int run_step(AgSim* s, int which, StepEnqueue enq, const float* action, f
   (void)which;
 #endif
   return enq(s, action, obs, reward, done, info);
+}
+
+// ------------------------------------------------------------------ cloth (K8, ag_cloth.cuh)
+static void cloth_launch(AgSim* s) {
+#ifndef AG_CPU_EMU
+  size_t smem = ((size_t)4 * s->cloth_npt * AG_CLOTH_T + 16 * AG_CLOTH_MAXCL + 12 * (size_t)s->C.maxcc + 40) * sizeof(float);
+  int ps = s->profiling ? prof_slot(s, "k_cloth") : -1;
+  if (ps >= 0) prof_mark(s, ps, true);
+  if (s->cloth_npt == 4) k_cloth<4><<<s->S.N, AG_CLOTH_T, smem, s->stream>>>(s->S, s->C);
+  else k_cloth<8><<<s->S.N, AG_CLOTH_T, smem, s->stream>>>(s->S, s->C);
+  if (ps >= 0) prof_mark(s, ps, false);
+#else
+  for (int e = 0; e < s->S.N; e++) cloth_env_host(s->S, s->C, e);
+#endif
+  s->launches++;
+}
+
+int ag_cloth_init(AgSim* s, const AgClothDesc* d) {
+  DevGuard guard__(s->device);
+  if (s->cloth) return fail("ag_cloth_init: the sim already has a cloth");
+  if (!d || d->n_nodes <= 0 || d->n_nodes > 65535) return fail("ag_cloth_init: 1..65535 nodes");
+  if (d->n_nodes > 8 * AG_CLOTH_T) return fail("ag_cloth_init: more than 8192 nodes");
+  if (d->n_colours < 1 || d->n_colours > AG_CLOTH_MAXCOL) return fail("ag_cloth_init: 1..16 link colours");
+  if (d->n_anchors < 0 || d->n_anchors > AG_CLOTH_MAXANCH) return fail("ag_cloth_init: at most 8 anchors");
+  if (d->n_col_links < 0 || d->n_col_links > AG_CLOTH_MAXCL) return fail("ag_cloth_init: at most 64 collider links");
+  const int N = s->S.N, nn = d->n_nodes;
+  ClothDev& C = s->C;
+  memset(&C, 0, sizeof(C));
+  C.nn = nn; C.nlinks = d->n_links; C.ncol = d->n_colours; C.nanch = d->n_anchors; C.ncl = d->n_col_links;
+  s->cloth_npt = nn <= 4 * AG_CLOTH_T ? 4 : 8;
+  C.nnp = (nn + 31) / 32 * 32;
+  C.maxcc = d->max_contacts > 0 ? d->max_contacts : 1024;
+  C.K = s->cfg.num_substeps > 0 ? s->cfg.num_substeps : 1;
+  C.piters = d->piterations; C.export_contacts = 1;
+  C.dt = s->S.dt; C.im = (float)d->inv_mass; C.kLSTh = (float)(0.5 * d->kLST); C.kDP = (float)d->kDP; C.kDG = (float)d->kDG; C.kLF = (float)d->kLF;
+  C.kDF = (float)d->kDF; C.kCHR = (float)d->kCHR; C.kKHR = (float)d->kKHR; C.kAHR = (float)d->kAHR; C.margin = (float)d->margin; C.density = (float)d->air_density;
+  C.gx = (float)d->gravity[0]; C.gy = (float)d->gravity[1]; C.gz = (float)d->gravity[2];
+  for (int c = 0; c <= d->n_colours; c++) C.col_off[c] = d->colour_off[c];
+  if (C.col_off[0] != 0 || C.col_off[d->n_colours] != d->n_links) return fail("ag_cloth_init: colour offsets do not cover the link list");
+  std::vector<unsigned> lij(d->n_links); std::vector<float> lr(d->n_links);
+  {
+    std::vector<int> seen(nn, -1);                     // links of one colour must not share a node (the kernel relaxes them concurrently)
+    for (int c = 0; c < d->n_colours; c++)
+      for (int l = C.col_off[c]; l < C.col_off[c + 1]; l++) {
+        int a = d->links[2 * l], b = d->links[2 * l + 1];
+        if (a < 0 || b < 0 || a >= nn || b >= nn || a == b) return fail("ag_cloth_init: bad link");
+        if (seen[a] == c || seen[b] == c) return fail("ag_cloth_init: two links of one colour share a node");
+        seen[a] = seen[b] = c;
+        lij[l] = (unsigned)a | ((unsigned)b << 16); lr[l] = (float)d->link_rest2[l];
+      }
+  }
+  std::vector<unsigned> nfp(d->n_nf);
+  for (int f = 0; f < d->n_nf; f++) nfp[f] = (unsigned)d->nf_pair[2 * f] | ((unsigned)d->nf_pair[2 * f + 1] << 16);
+  std::vector<float> area(nn), bs((size_t)4 * d->n_col_links);
+  for (int i = 0; i < nn; i++) area[i] = (float)d->node_area[i];
+  for (size_t i = 0; i < bs.size(); i++) bs[i] = (float)d->col_link_bsphere[i];
+  for (int a = 0; a < d->n_anchors; a++) {
+    if (d->anchor_node[a] < 0 || d->anchor_node[a] >= nn) return fail("ag_cloth_init: bad anchor node");
+    C.anch_node[a] = d->anchor_node[a];
+    for (int k = 0; k < 3; k++) C.anch_local[a][k] = (float)d->anchor_local[3 * a + k];
+  }
+  for (int L = 0; L < d->n_col_links; L++) if (d->col_links[L] < 0 || d->col_links[L] >= s->nl) return fail("ag_cloth_init: bad collider link");
+  C.link_ij = upload(s, lij); C.link_rest2 = upload(s, lr);
+  C.nf_off = upload(s, std::vector<int>(d->nf_off, d->nf_off + nn + 1)); C.nf_pair = upload(s, nfp);
+  C.node_area = upload(s, area);
+  C.cl_link = upload(s, std::vector<int>(d->col_links, d->col_links + d->n_col_links)); C.cl_bs = upload(s, bs);
+  C.cl_static = upload(s, std::vector<int>(d->col_link_static, d->col_link_static + d->n_col_links));
+  C.x = dalloc<float>(s, (size_t)N * 3 * C.nnp); C.v = dalloc<float>(s, (size_t)N * 3 * C.nnp);
+  C.anchor_pos = dalloc<float>(s, (size_t)3 * N);
+  C.snap = dalloc<float>(s, (size_t)C.K * std::max(C.ncl, 1) * 7 * N);
+  C.cc_count = dalloc<int>(s, N); C.cc_data = dalloc<float>(s, (size_t)N * C.maxcc * AG_CLOTH_CCF); C.overflow = s->S.overflow;   // the same sticky per-env flags as the rigid budgets (ag_overflow_count)
+  s->C_dev = dalloc<ClothDev>(s, 1);
+  if (!C.cc_data || !C.overflow || !s->C_dev || !C.snap || !C.v) return fail("ag_cloth_init: device allocation failed");
+  if (h2d(s, s->C_dev, &C, sizeof(ClothDev))) return -1;
+#ifndef AG_CPU_EMU
+  size_t smem = ((size_t)4 * s->cloth_npt * AG_CLOTH_T + 16 * AG_CLOTH_MAXCL + 12 * (size_t)C.maxcc + 40) * sizeof(float);
+  if (smem > 227 * 1024) return fail("ag_cloth_init: cloth + contact budget exceed 227 KB of shared memory");
+  if (s->cloth_npt == 4) CK(cudaFuncSetAttribute(k_cloth<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else CK(cudaFuncSetAttribute(k_cloth<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+  drop_graph(s, 0); drop_graph(s, 1);
+  s->cloth = true; s->cloth_sub = 0;
+  return 0;
+}
+static int cloth_refresh(AgSim* s) { return h2d(s, s->C_dev, &s->C, sizeof(ClothDev)); }
+
+int ag_cloth_set_state(AgSim* s, const float* x, const float* v, const int32_t* mask) {
+  DevGuard guard__(s->device);
+  if (!s->cloth) return fail("ag_cloth_init not called");
+  const int N = s->S.N, nn = s->C.nn, nnp = s->C.nnp;
+  std::vector<float> buf((size_t)N * 3 * nnp);
+  for (int which = 0; which < 2; which++) {
+    const float* src = which ? v : x; float* dst = which ? s->C.v : s->C.x;
+    if (!src) continue;
+    if (mask && d2h(s, buf.data(), dst, buf.size() * sizeof(float))) return -1;
+    if (!mask) std::fill(buf.begin(), buf.end(), 0.f);
+    for (int e = 0; e < N; e++) if (!mask || mask[e])
+      for (int i = 0; i < nn; i++) for (int c = 0; c < 3; c++) buf[((size_t)e * 3 + c) * nnp + i] = src[((size_t)e * nn + i) * 3 + c];
+    if (h2d(s, dst, buf.data(), buf.size() * sizeof(float))) return -1;
+  }
+  return 0;
+}
+int ag_cloth_get_state(AgSim* s, float* x, float* v) {
+  DevGuard guard__(s->device);
+  if (!s->cloth) return fail("ag_cloth_init not called");
+  const int N = s->S.N, nn = s->C.nn, nnp = s->C.nnp;
+  std::vector<float> buf((size_t)N * 3 * nnp);
+  for (int which = 0; which < 2; which++) {
+    float* dst = which ? v : x; const float* src = which ? s->C.v : s->C.x;
+    if (!dst) continue;
+    if (d2h(s, buf.data(), src, buf.size() * sizeof(float))) return -1;
+    for (int e = 0; e < N; e++) for (int i = 0; i < nn; i++) for (int c = 0; c < 3; c++) dst[((size_t)e * nn + i) * 3 + c] = buf[((size_t)e * 3 + c) * nnp + i];
+  }
+  return 0;
+}
+int ag_cloth_set_anchor(AgSim* s, const float* pos, const int32_t* mask) {
+  DevGuard guard__(s->device);
+  if (!s->cloth) return fail("ag_cloth_init not called");
+  const int N = s->S.N;
+  std::vector<float> buf((size_t)3 * N);
+  if (d2h(s, buf.data(), s->C.anchor_pos, buf.size() * sizeof(float))) return -1;
+  for (int e = 0; e < N; e++) if (!mask || mask[e]) for (int c = 0; c < 3; c++) buf[(size_t)c * N + e] = pos[(size_t)e * 3 + c];
+  return h2d(s, s->C.anchor_pos, buf.data(), buf.size() * sizeof(float));
+}
+int ag_cloth_anchor_follow(AgSim* s, int link) {
+  DevGuard guard__(s->device);
+  if (!s->cloth) return fail("ag_cloth_init not called");
+  if (link < 0 || link >= s->nl) return fail("bad link");
+  KP p = kp0(); p.p0 = s->C_dev; p.i0 = link;
+  LAUNCH(s, k_cloth_follow, s->S.N, p);
+  return 0;
+}
+int ag_cloth_set_gravity(AgSim* s, const double g[3]) {
+  DevGuard guard__(s->device);
+  if (!s->cloth) return fail("ag_cloth_init not called");
+  s->C.gx = (float)g[0]; s->C.gy = (float)g[1]; s->C.gz = (float)g[2];
+  drop_graph(s, 0); drop_graph(s, 1);                  // k_cloth takes ClothDev by value: a captured step holds the old gravity
+  return cloth_refresh(s);
+}
+int ag_cloth_get_contacts(AgSim* s, int max_pts, int32_t* count, int32_t* node, float* pos, float* force, int32_t* link) {
+  DevGuard guard__(s->device);
+  if (!s->cloth) return fail("ag_cloth_init not called");
+  if (max_pts < 0) return fail("max_pts < 0");
+  const int N = s->S.N, M = s->C.maxcc;
+  std::vector<int> cnt(N); std::vector<float> data((size_t)N * M * AG_CLOTH_CCF);
+  if (d2h(s, cnt.data(), s->C.cc_count, sizeof(int) * N) || d2h(s, data.data(), s->C.cc_data, data.size() * sizeof(float))) return -1;
+  for (int e = 0; e < N; e++) {
+    if (count) count[e] = cnt[e];
+    for (int k = 0; k < std::min(cnt[e], max_pts); k++) {
+      const float* r = &data[((size_t)e * M + k) * AG_CLOTH_CCF];
+      size_t o = (size_t)e * max_pts + k;
+      int32_t id; memcpy(&id, r, 4); if (node) node[o] = id;
+      memcpy(&id, r + 7, 4); if (link) link[o] = id;
+      for (int c = 0; c < 3; c++) { if (pos) pos[3 * o + c] = r[1 + c]; if (force) force[3 * o + c] = r[4 + c]; }
+    }
+  }
+  return 0;
+}
+int ag_cloth_device_state(AgSim* s, float** x_dev, float** v_dev, int32_t* nnp) {
+  if (!s->cloth) return fail("ag_cloth_init not called");
+  if (x_dev) *x_dev = s->C.x;
+  if (v_dev) *v_dev = s->C.v;
+  if (nnp) *nnp = s->C.nnp;
+  return 0;
 }
 
 // ------------------------------------------------------------------ fused FeedingEnv path

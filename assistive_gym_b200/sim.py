@@ -226,6 +226,46 @@ class BatchSim:
     def bathing_step_dev(self, action_ptr, obs_ptr, reward_ptr, done_ptr, info_ptr):
         self._ck(self.lib.ag_bathing_step_dev(self.h, C.c_void_p(action_ptr), C.c_void_p(obs_ptr), C.c_void_p(reward_ptr), C.c_void_p(done_ptr), C.c_void_p(info_ptr)))
 
+    # ---- cloth (ag_cloth_*; node arrays in the PUBLIC node order of the ClothModel)
+    def cloth_init(self, model, col_links, col_static, anchor_nodes, anchor_local, gravity=(0, 0, -9.81), max_contacts=1024):
+        self.cloth_model = model
+        self._cloth_desc = capi.make_cloth_desc(model, self.scene, col_links, col_static, anchor_nodes, anchor_local, gravity, max_contacts)
+        self._ck(self.lib.ag_cloth_init(self.h, C.byref(self._cloth_desc)))
+
+    def cloth_set_state(self, x=None, v=None, mask=None):
+        m = self.cloth_model
+        xi = None if x is None else _f32(m.to_internal(np.asarray(x)), (self.n, m.n_nodes, 3))
+        vi = None if v is None else _f32(m.to_internal(np.asarray(v)), (self.n, m.n_nodes, 3))
+        mk = None if mask is None else _i32(mask)
+        self._ck(self.lib.ag_cloth_set_state(self.h, _p(xi), _p(vi), _p(mk)))
+
+    def cloth_get_state(self):
+        m = self.cloth_model
+        x = np.empty((self.n, m.n_nodes, 3), dtype=np.float32)
+        v = np.empty_like(x)
+        self._ck(self.lib.ag_cloth_get_state(self.h, _p(x), _p(v)))
+        return m.to_public(x), m.to_public(v)
+
+    def cloth_set_anchor(self, pos, mask=None):
+        mk = None if mask is None else _i32(mask)
+        self._ck(self.lib.ag_cloth_set_anchor(self.h, _p(_f32(pos, (self.n, 3))), _p(mk)))
+
+    def cloth_anchor_follow(self, link):
+        self._ck(self.lib.ag_cloth_anchor_follow(self.h, int(link)))
+
+    def cloth_set_gravity(self, g):
+        gg = (C.c_double * 3)(*[float(a) for a in g])
+        self._ck(self.lib.ag_cloth_set_gravity(self.h, gg))
+
+    def cloth_get_contacts(self, max_pts=1024):
+        cnt = np.zeros(self.n, dtype=np.int32)
+        node = np.zeros((self.n, max_pts), dtype=np.int32)
+        link = np.zeros((self.n, max_pts), dtype=np.int32)
+        pos = np.zeros((self.n, max_pts, 3), dtype=np.float32)
+        force = np.zeros((self.n, max_pts, 3), dtype=np.float32)
+        self._ck(self.lib.ag_cloth_get_contacts(self.h, max_pts, _p(cnt), _p(node), _p(pos), _p(force), _p(link)))
+        return cnt, self.cloth_model.order[node], pos, force, link
+
     def feeding_reset_episode(self, mask=None):
         self._ck(self.lib.ag_feeding_reset_episode(self.h, _p(_i32(mask))))
 

@@ -240,6 +240,46 @@ int ag_bathing_init(AgSim* sim, const AgBathingParams* p, const int32_t* gender_
 int ag_bathing_step_dev(AgSim* sim, const float* action_dev, float* obs_dev, float* reward_dev, float* done_dev, float* info_dev);
 int ag_bathing_step_host(AgSim* sim, const float* action, float* obs, float* reward, float* done, float* info);
 
+/* --- cloth: p.loadCloth / p.clothParams / p.getSoftBodyData (dressing.py:25,146-154), stepped inside ag_step with the
+ * world's numSubSteps (dressing.py:184).  SURVEY.md section 8(a) row D1.  The model restates Bullet's btSoftBody position
+ * solver (recalled): node masses uniform, links = mesh edges, one-way coupling with the rigid links
+ * listed in `col_links` (multibody link colliders are static shapes for btSoftBody). ------------------------------- */
+typedef struct AgClothDesc {
+  int32_t n_nodes, n_links, n_colours, n_nf, n_anchors, n_col_links;
+  const int32_t* links;        /* [n_links][2] node ids, colour-major: links of one colour share no node */
+  const double*  link_rest2;   /* [n_links] squared rest length (btSoftBody::Link::m_c1) */
+  const int32_t* colour_off;   /* [n_colours + 1] */
+  const int32_t* nf_off;       /* [n_nodes + 1] node -> adjacent faces ... */
+  const int32_t* nf_pair;      /* [n_nf][2] ... as the two other nodes of the face in winding order */
+  const double*  node_area;    /* [n_nodes] a third of the adjacent face areas (btSoftBody::updateArea) */
+  double inv_mass;             /* of every node: n_nodes / total mass (loadCloth mass=0.16) */
+  double kLST, kDP, kDG, kLF, kDF, kCHR, kKHR, kAHR;   /* p.clothParams (dressing.py:147) */
+  double margin;               /* collisionMargin (0.04) */
+  double air_density;          /* btSoftBodyWorldInfo::air_density (1.2) */
+  int32_t piterations;
+  double gravity[3];           /* world gravity acting on the cloth */
+  const int32_t* anchor_node;  /* [n_anchors] (loadCloth anchors=[...]) */
+  const double*  anchor_local; /* [n_anchors][3] node position relative to the anchor body at attachment time */
+  const int32_t* col_links;    /* [n_col_links] global link ids whose colliders the cloth collides with */
+  const double*  col_link_bsphere; /* [n_col_links][4] bounding sphere (centre, radius) of each link's colliders, link frame */
+  const int32_t* col_link_static;  /* [n_col_links] 1: static shape (contact hardness kKHR), 0: movable (kCHR) */
+  int32_t max_contacts;        /* per-env rigid-contact budget of one substep (default 1024); overflow is flagged */
+} AgClothDesc;
+int ag_cloth_init(AgSim* sim, const AgClothDesc* desc);
+/* node positions / velocities, host [N][n_nodes][3]; NULL skips; env_mask [N] or NULL */
+int ag_cloth_set_state(AgSim* sim, const float* x, const float* v, const int32_t* env_mask);
+int ag_cloth_get_state(AgSim* sim, float* x, float* v);
+/* position of the (kinematic, identity-orientation) anchor body, host [N][3] (cloth_attachment.set_base_pos_orient, dressing.py:192) */
+int ag_cloth_set_anchor(AgSim* sim, const float* pos, const int32_t* env_mask);
+/* the same from the current world position of a link, on the device (update_targets, dressing.py:210) */
+int ag_cloth_anchor_follow(AgSim* sim, int link);
+int ag_cloth_set_gravity(AgSim* sim, const double g[3]);      /* p.setGravity (dressing.py:178,195) as felt by the cloth */
+/* rigid contacts of the last substep, as p.getSoftBodyData reports them: count [N]; per contact (host, [N][max_pts]) the
+ * node id, its position [3] and the contact force on the node [3] (accumulated position correction / (inv_mass dt^2)) */
+int ag_cloth_get_contacts(AgSim* sim, int max_pts, int32_t* count, int32_t* node, float* pos, float* force, int32_t* link);
+/* device pointers for fused consumers: x / v are [N][3][n_nodes_padded] */
+int ag_cloth_device_state(AgSim* sim, float** x_dev, float** v_dev, int32_t* n_nodes_padded);
+
 /* --- batched inverse kinematics for reset (Robot.ik_random_restarts agents/robot.py:84-121 via
  * AssistiveEnv.init_robot_pose envs/env.py:296): damped least squares with random restarts inside
  * the joint limits, one env per thread.  `joint_links` [n_joints <= 8]: the solved joints (global link ids, all on the

@@ -99,11 +99,16 @@ struct Row {
   real mu;
 };
 
+#include "oracle_cloth.h"
+
 struct Sim {
   Scene sc;
   AgConfig cfg;
   int N;
   std::vector<Env> envs;
+  bool has_cloth = false;
+  OCloth cloth;
+  std::vector<OClothEnv> cloth_envs;
 };
 
 thread_local std::string g_err;
@@ -554,7 +559,7 @@ void plane_space(V3 n, V3& t1, V3& t2) {
   }
 }
 
-void step_env(const Scene& s, const AgConfig& cfg, Env& e) {
+void step_env(const Scene& s, const AgConfig& cfg, Env& e, const OCloth* cloth = nullptr, OClothEnv* cloth_env = nullptr) {
   const real dt = (real)(cfg.dt / std::max(1, cfg.num_substeps));
   for (int sub = 0; sub < std::max(1, cfg.num_substeps); sub++) {
     // 1. kinematics + collision detection at the current positions
@@ -795,6 +800,9 @@ void step_env(const Scene& s, const AgConfig& cfg, Env& e) {
       e.contacts[ci].lambda_t1 = rows[fr].lambda; e.contacts[ci].lambda_t2 = rows[fr + 1].lambda; fr += 2;
     }
     (void)first_contact_row;
+    // the cloth solves after the rigid world of this substep, against the START-of-substep poses (e.lpos, e.wverts: the
+    // kinematics above ran before the integration)
+    if (cloth) ocloth_substep(s, e, *cloth, *cloth_env, dt);
   }
   forward_kinematics(s, e);
 }
@@ -911,7 +919,7 @@ int oracle_step(void* h, int n_steps, int n_threads) {
 #pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads > 0 ? n_threads : 1)
 #endif
   for (int i = 0; i < s->N; i++)
-    for (int k = 0; k < n_steps; k++) step_env(s->sc, s->cfg, s->envs[i]);
+    for (int k = 0; k < n_steps; k++) step_env(s->sc, s->cfg, s->envs[i], s->has_cloth ? &s->cloth : nullptr, s->has_cloth ? &s->cloth_envs[i] : nullptr);
   (void)n_threads;
   return 0;
 }
@@ -1063,6 +1071,74 @@ int oracle_state_set(void* h, const double* in) {
 }
 
 // diagnostics used by unit tests: generalized inverse mass matrix of a fixed-base body (CRBA route)
+
+// ---- cloth (mirrors ag_cloth_* of include/agphys.h, double I/O)
+int oracle_cloth_init(void* h, const AgClothDesc* d) {
+  Sim* s = (Sim*)h;
+  OCloth& C = s->cloth;
+  C.nn = d->n_nodes; C.piters = d->piterations; C.maxcc = d->max_contacts > 0 ? d->max_contacts : 1024;
+  C.links.assign(d->links, d->links + 2 * d->n_links);
+  C.rest2.resize(d->n_links); for (int l = 0; l < d->n_links; l++) C.rest2[l] = (real)d->link_rest2[l];
+  C.nf_off.assign(d->nf_off, d->nf_off + d->n_nodes + 1); C.nf_pair.assign(d->nf_pair, d->nf_pair + 2 * d->n_nf);
+  C.area.resize(d->n_nodes); for (int i = 0; i < d->n_nodes; i++) C.area[i] = (real)d->node_area[i];
+  C.im = (real)d->inv_mass; C.kLST = (real)d->kLST; C.kDP = (real)d->kDP; C.kDG = (real)d->kDG; C.kLF = (real)d->kLF; C.kDF = (real)d->kDF;
+  C.kCHR = (real)d->kCHR; C.kKHR = (real)d->kKHR; C.kAHR = (real)d->kAHR; C.margin = (real)d->margin; C.density = (real)d->air_density;
+  C.gravity = V3((real)d->gravity[0], (real)d->gravity[1], (real)d->gravity[2]);
+  C.anchor_node.assign(d->anchor_node, d->anchor_node + d->n_anchors);
+  C.anchor_local.clear(); for (int a = 0; a < d->n_anchors; a++) C.anchor_local.push_back(rd3(d->anchor_local, a));
+  C.col_links.assign(d->col_links, d->col_links + d->n_col_links); C.col_static.assign(d->col_link_static, d->col_link_static + d->n_col_links);
+  C.bs_c.clear(); C.bs_r.clear();
+  for (int L = 0; L < d->n_col_links; L++) { C.bs_c.push_back(V3((real)d->col_link_bsphere[4 * L], (real)d->col_link_bsphere[4 * L + 1], (real)d->col_link_bsphere[4 * L + 2])); C.bs_r.push_back((real)d->col_link_bsphere[4 * L + 3]); }
+  s->cloth_envs.assign(s->N, OClothEnv());
+  for (auto& ce : s->cloth_envs) { ce.x.assign(C.nn, V3()); ce.v.assign(C.nn, V3()); ce.q.assign(C.nn, V3()); }
+  s->has_cloth = true;
+  return 0;
+}
+int oracle_cloth_set_state(void* h, const double* x, const double* v, const int32_t* mask) {
+  Sim* s = (Sim*)h; int nn = s->cloth.nn;
+  for (int e = 0; e < s->N; e++) if (mask_on(mask, e)) for (int i = 0; i < nn; i++) {
+    if (x) s->cloth_envs[e].x[i] = rd3(x, e * nn + i);
+    if (v) s->cloth_envs[e].v[i] = rd3(v, e * nn + i);
+  }
+  return 0;
+}
+int oracle_cloth_get_state(void* h, double* x, double* v) {
+  Sim* s = (Sim*)h; int nn = s->cloth.nn;
+  for (int e = 0; e < s->N; e++) for (int i = 0; i < nn; i++) for (int c = 0; c < 3; c++) {
+    if (x) x[((size_t)e * nn + i) * 3 + c] = s->cloth_envs[e].x[i][c];
+    if (v) v[((size_t)e * nn + i) * 3 + c] = s->cloth_envs[e].v[i][c];
+  }
+  return 0;
+}
+int oracle_cloth_set_anchor(void* h, const double* pos, const int32_t* mask) {
+  Sim* s = (Sim*)h;
+  for (int e = 0; e < s->N; e++) if (mask_on(mask, e)) s->cloth_envs[e].anchor_pos = rd3(pos, e);
+  return 0;
+}
+int oracle_cloth_anchor_follow(void* h, int link) {
+  Sim* s = (Sim*)h;
+  for (int e = 0; e < s->N; e++) s->cloth_envs[e].anchor_pos = s->envs[e].lpos[link];
+  return 0;
+}
+int oracle_cloth_set_gravity(void* h, const double* g) { ((Sim*)h)->cloth.gravity = V3((real)g[0], (real)g[1], (real)g[2]); return 0; }
+int oracle_cloth_get_contacts(void* h, int max_pts, int32_t* count, int32_t* node, double* pos, double* force, int32_t* link) {
+  Sim* s = (Sim*)h;
+  double dt = s->cfg.dt / std::max(1, s->cfg.num_substeps);
+  double fs = 1.0 / ((double)s->cloth.im * dt * dt);
+  for (int e = 0; e < s->N; e++) {
+    const OClothEnv& ce = s->cloth_envs[e];
+    if (count) count[e] = (int)ce.contacts.size();
+    for (int k = 0; k < std::min((int)ce.contacts.size(), max_pts); k++) {
+      const OClothContact& c = ce.contacts[k];
+      size_t o = (size_t)e * max_pts + k;
+      if (node) node[o] = c.node;
+      if (link) link[o] = c.link;
+      for (int a = 0; a < 3; a++) { if (pos) pos[3 * o + a] = ce.x[c.node][a]; if (force) force[3 * o + a] = -(double)c.acc[a] * fs; }
+    }
+  }
+  return 0;
+}
+
 int oracle_mass_matrix_inv(void* h, int env, int body, double* out) {
   Sim* s = (Sim*)h; Env& e = s->envs[env];
   forward_kinematics(s->sc, e);

@@ -58,6 +58,14 @@ def _load(f32=False):
     lib.oracle_state_size.argtypes = [vp]
     lib.oracle_state_get.argtypes = [vp, vp]
     lib.oracle_state_set.argtypes = [vp, vp]
+    from assistive_gym_b200.capi import AgClothDesc
+    lib.oracle_cloth_init.argtypes = [vp, C.POINTER(AgClothDesc)]
+    lib.oracle_cloth_set_state.argtypes = [vp, vp, vp, vp]
+    lib.oracle_cloth_get_state.argtypes = [vp, vp, vp]
+    lib.oracle_cloth_set_anchor.argtypes = [vp, vp, vp]
+    lib.oracle_cloth_anchor_follow.argtypes = [vp, ci]
+    lib.oracle_cloth_set_gravity.argtypes = [vp, vp]
+    lib.oracle_cloth_get_contacts.argtypes = [vp, ci, vp, vp, vp, vp, vp]
     lib.oracle_mass_matrix_inv.argtypes = [vp, ci, ci, vp]
     lib.oracle_gjk.argtypes = [vp, ci, vp, ci, vp, vp, vp]
     _libs[key] = lib
@@ -188,6 +196,46 @@ class OracleSim:
         cnt = np.zeros(self.n, dtype=np.int32)
         self.lib.oracle_closest_points(self.h, body_a, body_b, float(distance), max_pts, _p(out), _p(cnt))
         return out, cnt
+
+    # ---- cloth (node arrays in the PUBLIC node order of the ClothModel)
+    def cloth_init(self, model, col_links, col_static, anchor_nodes, anchor_local, gravity=(0, 0, -9.81), max_contacts=1024):
+        from assistive_gym_b200 import capi
+        self.cloth_model = model
+        self._cloth_desc = capi.make_cloth_desc(model, self.scene, col_links, col_static, anchor_nodes, anchor_local, gravity, max_contacts)
+        self.lib.oracle_cloth_init(self.h, C.byref(self._cloth_desc))
+
+    def cloth_set_state(self, x=None, v=None, mask=None):
+        m = self.cloth_model
+        xi = None if x is None else _f64(m.to_internal(np.asarray(x)), (self.n, m.n_nodes, 3))
+        vi = None if v is None else _f64(m.to_internal(np.asarray(v)), (self.n, m.n_nodes, 3))
+        mk = None if mask is None else _i32(mask)
+        self.lib.oracle_cloth_set_state(self.h, _p(xi), _p(vi), _p(mk))
+
+    def cloth_get_state(self):
+        m = self.cloth_model
+        x = np.empty((self.n, m.n_nodes, 3), dtype=np.float64)
+        v = np.empty_like(x)
+        self.lib.oracle_cloth_get_state(self.h, _p(x), _p(v))
+        return m.to_public(x), m.to_public(v)
+
+    def cloth_set_anchor(self, pos, mask=None):
+        mk = None if mask is None else _i32(mask)
+        self.lib.oracle_cloth_set_anchor(self.h, _p(_f64(pos, (self.n, 3))), _p(mk))
+
+    def cloth_anchor_follow(self, link):
+        self.lib.oracle_cloth_anchor_follow(self.h, int(link))
+
+    def cloth_set_gravity(self, g):
+        self.lib.oracle_cloth_set_gravity(self.h, _p(np.asarray(g, dtype=np.float64)))
+
+    def cloth_get_contacts(self, max_pts=1024):
+        cnt = np.zeros(self.n, dtype=np.int32)
+        node = np.zeros((self.n, max_pts), dtype=np.int32)
+        link = np.zeros((self.n, max_pts), dtype=np.int32)
+        pos = np.zeros((self.n, max_pts, 3), dtype=np.float64)
+        force = np.zeros((self.n, max_pts, 3), dtype=np.float64)
+        self.lib.oracle_cloth_get_contacts(self.h, max_pts, _p(cnt), _p(node), _p(pos), _p(force), _p(link))
+        return cnt, self.cloth_model.order[node], pos, force, link
 
     def num_contacts(self):
         cnt, it = np.zeros(self.n, dtype=np.int32), np.zeros(self.n, dtype=np.int32)

@@ -257,6 +257,34 @@ def compile_urdf(urdf_path):
             'n_hull_verts': stats.get('verts', 0), 'max_hull_verts': MAX_HULL_VERTS}
 
 
+def compile_cloth(path):
+    """Triangle mesh of a cloth (reference dressing.py:146 `p.loadCloth(...hospitalgown_reduced.obj...)`).
+
+    Node numbering restates the old tinyobjloader bundled with Bullet (recalled): a node is created for every distinct
+    `v/vt/vn` corner triple, numbered in order of FIRST APPEARANCE in the face list -- not in `v` line order.  This is
+    pinned by the reference's own constants (tests/test_cloth_model.py): with this numbering the anchor nodes
+    [2086, 2087, 2088, 2041] (dressing.py:146) sit within 2.4 cm of `cloth_orig_pos` (dressing.py:140) and the six sleeve
+    nodes (dressing.py:149-150) form a 15 cm ring; with `v` line order they are scattered over the gown.
+    """
+    V, F = [], []
+    for line in open(path, errors='ignore'):
+        if line.startswith('v '):
+            V.append([float(x) for x in line.split()[1:4]])
+        elif line.startswith('f '):
+            F.append(line.split()[1:4])
+    V = np.array(V, dtype=np.float64)
+    ids, order, faces = {}, [], []
+    for f in F:
+        t = []
+        for c in f:
+            if c not in ids:
+                ids[c] = len(order)
+                order.append(int(c.split('/')[0]) - 1)
+            t.append(ids[c])
+        faces.append(t)
+    return V[np.array(order)], np.array(faces, dtype=np.int32)
+
+
 def compile_mesh_asset(path, name):
     stats = {}
     hulls = compile_mesh_hulls(path, [1.0, 1.0, 1.0], stats)
@@ -275,6 +303,9 @@ URDFS = {
     'sawyer': 'sawyer/sawyer.urdf',
     'bed': 'bed/bed.urdf',
     'wiper': 'bed_bathing/wiper.urdf',
+}
+CLOTHS = {
+    'hospitalgown_reduced': 'clothing/hospitalgown_reduced.obj',
 }
 MESHES = {
     'spoon_vhacd': 'dinnerware/spoon_vhacd.obj',
@@ -312,6 +343,14 @@ def main():
         m = compile_mesh_asset(os.path.join(adir, rel), name)
         json.dump(m, open(os.path.join(args.out, name + '.agmesh.json'), 'w'), separators=(',', ':'))
         print('%-16s hulls=%d verts=%d simplify_err=%.2e m' % (name, m['n_hulls'], m['n_hull_verts'], m['hull_simplify_err_m']))
+
+
+    for name, rel in CLOTHS.items():
+        if args.only and name != args.only:
+            continue
+        v, f = compile_cloth(os.path.join(adir, rel))
+        np.savez_compressed(os.path.join(args.out, name + '.agcloth.npz'), verts=v, faces=f)
+        print('%-16s cloth nodes=%d faces=%d' % (name, len(v), len(f)))
 
 
 if __name__ == '__main__':
