@@ -82,6 +82,19 @@ class AgBathingParams(C.Structure):
 
 import numpy as np  # noqa: E402
 
+class AgDressingParams(C.Structure):
+    _fields_ = [('robot_body', C.c_int32), ('human_body_m', C.c_int32), ('human_body_f', C.c_int32),
+                ('arm_links', C.c_int32 * 7), ('ee_link', C.c_int32),
+                ('arm_points_m', C.c_int32 * 3), ('arm_points_f', C.c_int32 * 3),
+                ('arm_lower', C.c_float * 7), ('arm_upper', C.c_float * 7),
+                ('hand_radius_m', C.c_float), ('elbow_radius_m', C.c_float), ('shoulder_radius_m', C.c_float),
+                ('hand_radius_f', C.c_float), ('elbow_radius_f', C.c_float), ('shoulder_radius_f', C.c_float),
+                ('tri1', C.c_int32 * 3), ('tri2', C.c_int32 * 3),
+                ('action_multiplier', C.c_float), ('frame_skip', C.c_int32),
+                ('w_dressing', C.c_float), ('w_action', C.c_float), ('c_v', C.c_float), ('c_d', C.c_float),
+                ('task_success_threshold', C.c_float)]
+
+
 class AgClothDesc(C.Structure):
     _fields_ = [('n_nodes', C.c_int32), ('n_links', C.c_int32), ('n_colours', C.c_int32), ('n_nf', C.c_int32),
                 ('n_anchors', C.c_int32), ('n_col_links', C.c_int32),
@@ -198,6 +211,10 @@ def load_library(path=None):
     lib.ag_cloth_set_gravity.argtypes = [vp, vp]
     lib.ag_cloth_get_contacts.argtypes = [vp, ci, vp, vp, vp, vp, vp]
     lib.ag_cloth_device_state.argtypes = [vp, vp, vp, vp]
+    lib.ag_dressing_init.argtypes = [vp, C.POINTER(AgDressingParams), vp]
+    lib.ag_dressing_reset_episode.argtypes = [vp, vp]
+    lib.ag_dressing_step_dev.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.ag_dressing_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.ag_ik_solve.argtypes = [vp, ci, vp, ci, vp, vp, ci, ci, C.c_float, C.c_uint64, vp, vp, vp]
     lib.ag_state_size.restype = C.c_size_t
     lib.ag_state_size.argtypes = [vp]
@@ -225,6 +242,6 @@ EXPORTED_SYMBOLS = [
     'ag_closest_points', 'ag_feeding_init', 'ag_feeding_reset_episode', 'ag_feeding_set_tremor', 'ag_set_hard_limits', 'ag_feeding_step_dev', 'ag_ik_solve', 'ag_bathing_init', 'ag_bathing_step_dev', 'ag_bathing_step_host',
     'ag_feeding_step_host', 'ag_feeding_step_host_begin', 'ag_feeding_step_host_end', 'ag_state_size', 'ag_state_get', 'ag_state_set', 'ag_kernel_launches',
     'ag_cloth_init', 'ag_cloth_set_state', 'ag_cloth_get_state', 'ag_cloth_set_anchor', 'ag_cloth_anchor_follow', 'ag_cloth_set_gravity',
-    'ag_cloth_get_contacts', 'ag_cloth_device_state',
+    'ag_cloth_get_contacts', 'ag_cloth_device_state', 'ag_dressing_init', 'ag_dressing_reset_episode', 'ag_dressing_step_dev', 'ag_dressing_step_host',
     'ag_overflow_count', 'ag_get_solver_stats', 'ag_get_pgs_cycles', 'ag_get_pgs_trips', 'ag_profile_enable', 'ag_profile_get',
 ]

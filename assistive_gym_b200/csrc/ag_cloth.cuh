@@ -24,9 +24,9 @@
 
 #define AG_CLOTH_T 1024          // threads per CTA (= envs are independent CTAs)
 #define AG_CLOTH_MAXANCH 8
-#define AG_CLOTH_MAXCL 64        // collider links per env
+#define AG_CLOTH_MAXCL 96        // collider links per env
 #define AG_CLOTH_MAXCOL 16       // link colours
-#define AG_CLOTH_HITS 6          // contacts one thread can find per substep (over its <= NPT nodes)
+#define AG_CLOTH_HITS 12         // contacts one thread can find per substep (over its <= NPT nodes)
 #define AG_CLOTH_EPS 1.1920929e-7f
 #define AG_CLOTH_CCF 8           // floats per exported contact: node, x, y, z, fx, fy, fz, link
 
@@ -98,11 +98,15 @@ AG_HD ClothLinkPose cloth_link_pose(const ClothDev& C, int sub, int L, int N, in
   P.bc = P.pos + mul(P.R, bl); P.br = AG_LDG(C.cl_bs + 4 * L + 3) + C.margin;
   return P;
 }
+// links of a body that is switched off in this env (the other-gender person) do not exist for the cloth
+AG_HD bool cloth_link_active(const SimDev& S, const ClothDev& C, int L, int N, int e) {
+  return S.body_mode[(size_t)AG_LDG(S.link_body + AG_LDG(C.cl_link + L)) * N + e] != 0;
+}
 
 // node vs collider link L (Bullet btSoftColliders::CollideSDF_RS::DoNode + btSoftBody::checkContact, static shape)
 AG_HD bool cloth_detect(const SimDev& S, const ClothDev& C, const ClothLinkPose& P, int L, int N, int e, f3 x, f3 q, ClothContact& c) {
   f3 w = x - P.bc;
-  if (dot(w, w) > P.br * P.br) return false;
+  if (!(P.br > 0.f) || dot(w, w) > P.br * P.br) return false;
   int link = AG_LDG(C.cl_link + L);
   f3 nl;
   float dst = cloth_sdf_link(S, link, mulT(P.R, x - P.pos), nl) - C.margin;
@@ -198,6 +202,7 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
   float* lk = cl_smem + 4 * NPT * T;                           // [ncl][16]  R, pos, bounding sphere
   float* pool = lk + 16 * AG_CLOTH_MAXCL;                      // [maxcc][12] n, offset | c3, c4, node, link | acc, -
   int* misc = (int*)(pool + 12 * C.maxcc);                     // [40] warp sums for the scan, total
+  float* wbox = (float*)(misc + 40);                           // [32][6] per-warp bounding boxes of the predicted nodes
   const int nn = C.nn;
   const size_t xb = (size_t)e * 3 * C.nnp;
   f3 q[NPT], v[NPT];
@@ -217,14 +222,6 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
   int total = 0;
   __syncthreads();
   for (int sub = 0; sub < C.K; sub++) {
-    // ---- collider link poses of this substep
-    if (t < C.ncl) {
-      ClothLinkPose P = cloth_link_pose(C, sub, t, N, e);
-      float* o = lk + 16 * t;
-#pragma unroll
-      for (int a = 0; a < 9; a++) o[a] = P.R.m[a];
-      o[9] = P.pos.x; o[10] = P.pos.y; o[11] = P.pos.z; o[12] = P.bc.x; o[13] = P.bc.y; o[14] = P.bc.z; o[15] = P.br;
-    }
     // ---- predict own nodes (reads the neighbours' start-of-substep positions for the node normal)
     f3 xn[NPT];
 #pragma unroll
@@ -248,19 +245,47 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
         xn[k] = xx;
       }
     }
-    __syncthreads();                                           // every normal is computed, link poses are written
-    // ---- publish the prediction, find contacts of own nodes
+    // bounding box of the predicted cloth, per warp -> shared memory
+    {
+      f3 lo(1e30f, 1e30f, 1e30f), hi(-1e30f, -1e30f, -1e30f);
+#pragma unroll
+      for (int k = 0; k < NPT; k++) if (k * T + t < nn) { lo = fmin3(lo, xn[k]); hi = fmax3(hi, xn[k]); }
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, d)); lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, d)); lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, d));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, d)); hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, d)); hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, d));
+      }
+      if ((t & 31) == 0) { float* w = wbox + 6 * (t >> 5); w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = hi.x; w[4] = hi.y; w[5] = hi.z; }
+    }
+    __syncthreads();                                           // every normal is computed, the warp boxes are written
+    // ---- collider link poses of this substep; a link whose bounding sphere misses the cloth's box is skipped by everyone
+    if (t < C.ncl) {
+      ClothLinkPose P = cloth_link_pose(C, sub, t, N, e);
+      float* o = lk + 16 * t;
+#pragma unroll
+      for (int a = 0; a < 9; a++) o[a] = P.R.m[a];
+      f3 lo(1e30f, 1e30f, 1e30f), hi(-1e30f, -1e30f, -1e30f);
+      for (int w = 0; w < T / 32; w++) { lo = fmin3(lo, f3(wbox[6 * w], wbox[6 * w + 1], wbox[6 * w + 2])); hi = fmax3(hi, f3(wbox[6 * w + 3], wbox[6 * w + 4], wbox[6 * w + 5])); }
+      f3 cp = fmax3(lo, fmin3(hi, P.bc)) - P.bc;               // box point nearest to the sphere centre
+      bool on = cloth_link_active(S, C, t, N, e) && dot(cp, cp) <= P.br * P.br;
+      o[9] = P.pos.x; o[10] = P.pos.y; o[11] = P.pos.z; o[12] = P.bc.x; o[13] = P.bc.y; o[14] = P.bc.z; o[15] = on ? P.br : 0.f;
+    }
+    // ---- publish the prediction
+#pragma unroll
+    for (int k = 0; k < NPT; k++) { int i = k * T + t; if (i < nn) xs[i] = make_float4(xn[k].x, xn[k].y, xn[k].z, 0.f); }
+    __syncthreads();
+    // ---- find contacts of own nodes
     int hits[AG_CLOTH_HITS]; int nh = 0; bool over = false;
 #pragma unroll
     for (int k = 0; k < NPT; k++) {
       int i = k * T + t;
       if (i < nn) {
-        xs[i] = make_float4(xn[k].x, xn[k].y, xn[k].z, 0.f);
         bool anchored = false;
         for (int a = 0; a < C.nanch; a++) anchored |= C.anch_node[a] == i;
         if (!anchored) {
           for (int L = 0; L < C.ncl; L++) {
             const float* o = lk + 16 * L;
+            if (!(o[15] > 0.f)) continue;
             f3 w = xn[k] - f3(o[12], o[13], o[14]);
             if (dot(w, w) > o[15] * o[15]) continue;
             ClothLinkPose P;
@@ -399,7 +424,7 @@ static inline void cloth_env_host(const SimDev& S, const ClothDev& C, int e) {
   std::vector<ClothContact> cc;
   for (int sub = 0; sub < C.K; sub++) {
     std::vector<ClothLinkPose> P(C.ncl);
-    for (int L = 0; L < C.ncl; L++) P[L] = cloth_link_pose(C, sub, L, N, e);
+    for (int L = 0; L < C.ncl; L++) { P[L] = cloth_link_pose(C, sub, L, N, e); if (!cloth_link_active(S, C, L, N, e)) P[L].br = 0.f; }
     for (int i = 0; i < nn; i++) {
       q[i] = x[i];
       f3 ns(0.f, 0.f, 0.f);

@@ -15,6 +15,7 @@
 #include "ag_bathing.cuh"
 #include "ag_ik.cuh"
 #include "ag_cloth.cuh"
+#include "ag_dressing.cuh"
 
 #ifndef AG_CPU_EMU
 #include <cuda_runtime.h>
@@ -103,6 +104,8 @@ AG_KERNEL(k_ik, ik_body)
 AG_KERNEL(k_bath_pre, bathing_pre_body)
 AG_KERNEL(k_bath_dist, bathing_dist_body)
 AG_KERNEL(k_bath_post, bathing_post_body)
+AG_KERNEL(k_dress_pre, dressing_pre_body)
+AG_KERNEL(k_dress_post, dressing_post_body)
 AG_KERNEL(k_cloth_snap, cloth_snap_body)
 AG_KERNEL(k_cloth_follow, cloth_follow_body)
 
@@ -129,9 +132,11 @@ struct AgSim {
   float *h_pin_in, *h_pin_out;
   // cloth (Dressing): one k_cloth launch per stepSimulation = `C.K` rigid substeps
   ClothDev C; ClothDev* C_dev; bool cloth; int cloth_sub, cloth_npt;
+  DressPost DP; DressPost* DP_dev; bool dressing;
+  float *h_dpin_in, *h_dpin_out, *d_daction, *d_dobs, *d_dreward, *d_ddone, *d_dinfo;
   // CUDA-graph replay of the fused env step (one graph per entry point, keyed by its device pointers)
   bool use_graph; int graph_failures;
-  struct StepGraph { void* exec; const void* key[5]; uint64_t launches; bool valid; } graphs[2];
+  struct StepGraph { void* exec; const void* key[5]; uint64_t launches; bool valid; } graphs[3];
   // profiling
   bool profiling;
   std::vector<std::string> knames;
@@ -285,7 +290,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   AgSim* s = new AgSim();
   memset(&s->S, 0, sizeof(SimDev));
   memset(&s->F, 0, sizeof(FeedDev));
-  s->cfg = *cfg; s->device = device; s->launches = 0; s->feeding = false; s->bathing = false; s->cloth = false; s->cloth_sub = 0; s->C_dev = nullptr; s->use_graph = true; s->graph_failures = 0; s->graphs[0].valid = s->graphs[1].valid = false; s->B_dev = nullptr; s->stream = nullptr; s->F_dev = nullptr; s->profiling = false;
+  s->cfg = *cfg; s->device = device; s->launches = 0; s->feeding = false; s->bathing = false; s->cloth = false; s->cloth_sub = 0; s->C_dev = nullptr; s->dressing = false; s->DP_dev = nullptr; s->graphs[2].valid = false; s->use_graph = true; s->graph_failures = 0; s->graphs[0].valid = s->graphs[1].valid = false; s->B_dev = nullptr; s->stream = nullptr; s->F_dev = nullptr; s->profiling = false;
   s->d_stage = nullptr; s->stage_floats = 0;
 #ifndef AG_CPU_EMU
   { int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { g_err = "no such CUDA device (is a CUDA device present? there is no CPU fallback)"; delete s; return nullptr; } }
@@ -515,12 +520,14 @@ void ag_destroy(AgSim* s) {
   for (void* p : s->allocs) cudaFree(p);
   if (s->feeding) { cudaFreeHost(s->h_pin_in); cudaFreeHost(s->h_pin_out); }
   if (s->bathing) { cudaFreeHost(s->h_bpin_in); cudaFreeHost(s->h_bpin_out); }
-  for (int g = 0; g < 2; g++) if (s->graphs[g].valid) cudaGraphExecDestroy((cudaGraphExec_t)s->graphs[g].exec);
+  if (s->dressing) { cudaFreeHost(s->h_dpin_in); cudaFreeHost(s->h_dpin_out); }
+  for (int g = 0; g < 3; g++) if (s->graphs[g].valid) cudaGraphExecDestroy((cudaGraphExec_t)s->graphs[g].exec);
   if (s->stream) cudaStreamDestroy(s->stream);
 #else
   for (void* p : s->allocs) free(p);
   if (s->feeding) { free(s->h_pin_in); free(s->h_pin_out); }
   if (s->bathing) { free(s->h_bpin_in); free(s->h_bpin_out); }
+  if (s->dressing) { free(s->h_dpin_in); free(s->h_dpin_out); }
 #endif
   delete s;
 }
@@ -939,7 +946,7 @@ static int run_step(AgSim* s, int which, StepEnqueue enq, const float* action, f
   if (s->use_graph && !s->profiling) {
     // The graph is captured against the sim's OWN action buffer: a learner hands in a freshly allocated action tensor
     // every step, and a graph keyed on that address would be re-captured (~90 launches + instantiate) each time.
-    float* own = which == 0 ? s->d_action : s->d_baction;
+    float* own = which == 0 ? s->d_action : (which == 1 ? s->d_baction : s->d_daction);
     if (action != own) { CK(cudaMemcpyAsync(own, action, sizeof(float) * 7 * s->S.N, cudaMemcpyDeviceToDevice, s->stream)); action = own; }
     AgSim::StepGraph& G = s->graphs[which];
     const void* key[5] = {action, obs, reward, done, info};
@@ -973,7 +980,7 @@ static int run_step(AgSim* s, int which, StepEnqueue enq, const float* action, f
 // ------------------------------------------------------------------ cloth (K8, ag_cloth.cuh)
 static void cloth_launch(AgSim* s) {
 #ifndef AG_CPU_EMU
-  size_t smem = ((size_t)4 * s->cloth_npt * AG_CLOTH_T + 16 * AG_CLOTH_MAXCL + 12 * (size_t)s->C.maxcc + 40) * sizeof(float);
+  size_t smem = ((size_t)4 * s->cloth_npt * AG_CLOTH_T + 16 * AG_CLOTH_MAXCL + 12 * (size_t)s->C.maxcc + 40 + 192) * sizeof(float);
   int ps = s->profiling ? prof_slot(s, "k_cloth") : -1;
   if (ps >= 0) prof_mark(s, ps, true);
   if (s->cloth_npt == 4) k_cloth<4><<<s->S.N, AG_CLOTH_T, smem, s->stream>>>(s->S, s->C);
@@ -992,7 +999,7 @@ int ag_cloth_init(AgSim* s, const AgClothDesc* d) {
   if (d->n_nodes > 8 * AG_CLOTH_T) return fail("ag_cloth_init: more than 8192 nodes");
   if (d->n_colours < 1 || d->n_colours > AG_CLOTH_MAXCOL) return fail("ag_cloth_init: 1..16 link colours");
   if (d->n_anchors < 0 || d->n_anchors > AG_CLOTH_MAXANCH) return fail("ag_cloth_init: at most 8 anchors");
-  if (d->n_col_links < 0 || d->n_col_links > AG_CLOTH_MAXCL) return fail("ag_cloth_init: at most 64 collider links");
+  if (d->n_col_links < 0 || d->n_col_links > AG_CLOTH_MAXCL) return fail("ag_cloth_init: at most 96 collider links");
   const int N = s->S.N, nn = d->n_nodes;
   ClothDev& C = s->C;
   memset(&C, 0, sizeof(C));
@@ -1043,12 +1050,12 @@ int ag_cloth_init(AgSim* s, const AgClothDesc* d) {
   if (!C.cc_data || !C.overflow || !s->C_dev || !C.snap || !C.v) return fail("ag_cloth_init: device allocation failed");
   if (h2d(s, s->C_dev, &C, sizeof(ClothDev))) return -1;
 #ifndef AG_CPU_EMU
-  size_t smem = ((size_t)4 * s->cloth_npt * AG_CLOTH_T + 16 * AG_CLOTH_MAXCL + 12 * (size_t)C.maxcc + 40) * sizeof(float);
+  size_t smem = ((size_t)4 * s->cloth_npt * AG_CLOTH_T + 16 * AG_CLOTH_MAXCL + 12 * (size_t)C.maxcc + 40 + 192) * sizeof(float);
   if (smem > 227 * 1024) return fail("ag_cloth_init: cloth + contact budget exceed 227 KB of shared memory");
   if (s->cloth_npt == 4) CK(cudaFuncSetAttribute(k_cloth<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else CK(cudaFuncSetAttribute(k_cloth<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
-  drop_graph(s, 0); drop_graph(s, 1);
+  drop_graph(s, 0); drop_graph(s, 1); drop_graph(s, 2);
   s->cloth = true; s->cloth_sub = 0;
   return 0;
 }
@@ -1104,7 +1111,7 @@ int ag_cloth_set_gravity(AgSim* s, const double g[3]) {
   DevGuard guard__(s->device);
   if (!s->cloth) return fail("ag_cloth_init not called");
   s->C.gx = (float)g[0]; s->C.gy = (float)g[1]; s->C.gz = (float)g[2];
-  drop_graph(s, 0); drop_graph(s, 1);                  // k_cloth takes ClothDev by value: a captured step holds the old gravity
+  drop_graph(s, 0); drop_graph(s, 1); drop_graph(s, 2);   // k_cloth takes ClothDev by value: a captured step holds the old gravity
   return cloth_refresh(s);
 }
 int ag_cloth_get_contacts(AgSim* s, int max_pts, int32_t* count, int32_t* node, float* pos, float* force, int32_t* link) {
@@ -1131,6 +1138,99 @@ int ag_cloth_device_state(AgSim* s, float** x_dev, float** v_dev, int32_t* nnp) 
   if (x_dev) *x_dev = s->C.x;
   if (v_dev) *v_dev = s->C.v;
   if (nnp) *nnp = s->C.nnp;
+  return 0;
+}
+
+// ------------------------------------------------------------------ fused DressingEnv path
+int ag_dressing_reset_episode(AgSim* s, const int32_t* env_mask) {
+  DevGuard guard__(s->device);
+  if (!s->dressing) return fail("ag_dressing_init not called");
+  const int N = s->S.N;
+  std::vector<int> it(N); std::vector<float> ts(N);
+  if (d2h(s, it.data(), s->DP.D.iteration, sizeof(int) * N) || d2h(s, ts.data(), s->DP.D.task_success, sizeof(float) * N)) return -1;
+  for (int e = 0; e < N; e++) if (!env_mask || env_mask[e]) { it[e] = 0; ts[e] = 0.f; }
+  if (h2d(s, s->DP.D.iteration, it.data(), sizeof(int) * N) || h2d(s, s->DP.D.task_success, ts.data(), sizeof(float) * N)) return -1;
+  return 0;
+}
+int ag_dressing_init(AgSim* s, const AgDressingParams* p, const int32_t* gender_is_male) {
+  DevGuard guard__(s->device);
+  if (!s->cloth) return fail("ag_dressing_init: ag_cloth_init first");
+  const int N = s->S.N;
+  for (int j = 0; j < 7; j++) if (p->arm_links[j] < 0 || p->arm_links[j] >= s->nl) return fail("ag_dressing_init: bad arm link");
+  for (int j = 0; j < 3; j++) if (p->tri1[j] < 0 || p->tri1[j] >= s->C.nn || p->tri2[j] < 0 || p->tri2[j] >= s->C.nn) return fail("ag_dressing_init: bad sleeve node");
+  if (p->ee_link < 0 || p->ee_link >= s->nl) return fail("ag_dressing_init: bad end effector link");
+  DressDev& D = s->DP.D;
+  D.P = *p;
+  drop_graph(s, 2);
+  if (!s->dressing) {
+    D.male = dalloc<int>(s, N); D.iteration = dalloc<int>(s, N); D.task_success = dalloc<float>(s, N); D.action = dalloc<float>(s, (size_t)N * 7);
+    s->d_daction = dalloc<float>(s, (size_t)N * 7); s->d_dobs = dalloc<float>(s, (size_t)N * 24);
+    s->d_dreward = dalloc<float>(s, N); s->d_ddone = dalloc<float>(s, N); s->d_dinfo = dalloc<float>(s, (size_t)N * 4);
+    s->DP_dev = dalloc<DressPost>(s, 1);
+    if (!s->d_dinfo || !s->DP_dev) return fail("device allocation failed");
+#ifndef AG_CPU_EMU
+    CK(cudaMallocHost((void**)&s->h_dpin_in, sizeof(float) * N * 7));
+    CK(cudaMallocHost((void**)&s->h_dpin_out, sizeof(float) * N * 30));
+#else
+    s->h_dpin_in = (float*)malloc(sizeof(float) * N * 7); s->h_dpin_out = (float*)malloc(sizeof(float) * N * 30);
+#endif
+  }
+  s->DP.C = s->C_dev;
+  if (h2d(s, D.male, gender_is_male, sizeof(int) * N)) return -1;
+  if (h2d(s, s->DP_dev, &s->DP, sizeof(DressPost))) return -1;
+  s->dressing = true;
+  return ag_dressing_reset_episode(s, nullptr);
+}
+static int dressing_step_enqueue(AgSim* s, const float* action_dev, float* obs, float* reward, float* done, float* info) {
+  const int N = s->S.N;
+  KP p = kp0(); p.p0 = action_dev; p.p1 = s->DP_dev;
+  LAUNCH(s, k_dress_pre, N, p);
+  const int sub = s->cfg.num_substeps > 0 ? s->cfg.num_substeps : 1;
+  KP z = kp0();
+  for (int f = 0; f < s->DP.D.P.frame_skip; f++) {
+    for (int i = 0; i < sub; i++) substep(s);                        // the last one launches k_cloth
+    LAUNCH(s, k_fk, (size_t)s->S.nb * N, z);
+    KP c = kp0(); c.p0 = s->C_dev; c.i0 = s->DP.D.P.ee_link;         // update_targets (dressing.py:210)
+    LAUNCH(s, k_cloth_follow, N, c);
+  }
+  KP q = kp0(); q.p0 = action_dev; q.p1 = s->DP_dev; q.p2 = obs; q.p3 = reward; q.p4 = done; q.p5 = info;
+  LAUNCH(s, k_dress_post, N, q);
+  return 0;
+}
+int ag_dressing_step_dev(AgSim* s, const float* action_dev, float* obs_dev, float* reward_dev, float* done_dev, float* info_dev) {
+  DevGuard guard__(s->device);
+  if (!s->dressing) return fail("ag_dressing_init not called");
+  if (s->cloth_sub != 0) return fail("ag_dressing_step: a stepSimulation is half done (ag_step with a partial substep count?)");
+  int rc = run_step(s, 2, dressing_step_enqueue, action_dev, obs_dev, reward_dev, done_dev, info_dev);
+#ifndef AG_CPU_EMU
+  CK(cudaGetLastError());
+#endif
+  return rc;
+}
+int ag_dressing_step_host(AgSim* s, const float* action, float* obs, float* reward, float* done, float* info) {
+  DevGuard guard__(s->device);
+  if (!s->dressing) return fail("ag_dressing_init not called");
+  const int N = s->S.N;
+  memcpy(s->h_dpin_in, action, sizeof(float) * N * 7);
+#ifndef AG_CPU_EMU
+  CK(cudaMemcpyAsync(s->d_daction, s->h_dpin_in, sizeof(float) * N * 7, cudaMemcpyHostToDevice, s->stream));
+#else
+  memcpy(s->d_daction, s->h_dpin_in, sizeof(float) * N * 7);
+#endif
+  if (ag_dressing_step_dev(s, s->d_daction, s->d_dobs, s->d_dreward, s->d_ddone, s->d_dinfo)) return -1;
+  float* o = s->h_dpin_out;
+#ifndef AG_CPU_EMU
+  CK(cudaMemcpyAsync(o, s->d_dobs, sizeof(float) * N * 24, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(o + (size_t)N * 24, s->d_dreward, sizeof(float) * N, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(o + (size_t)N * 25, s->d_ddone, sizeof(float) * N, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(o + (size_t)N * 26, s->d_dinfo, sizeof(float) * N * 4, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+#else
+  memcpy(o, s->d_dobs, sizeof(float) * N * 24); memcpy(o + (size_t)N * 24, s->d_dreward, sizeof(float) * N);
+  memcpy(o + (size_t)N * 25, s->d_ddone, sizeof(float) * N); memcpy(o + (size_t)N * 26, s->d_dinfo, sizeof(float) * N * 4);
+#endif
+  memcpy(obs, o, sizeof(float) * N * 24); memcpy(reward, o + (size_t)N * 24, sizeof(float) * N);
+  memcpy(done, o + (size_t)N * 25, sizeof(float) * N); memcpy(info, o + (size_t)N * 26, sizeof(float) * N * 4);
   return 0;
 }
 

@@ -1,7 +1,8 @@
 from .bed_bathing_envs import BedBathingSawyerEnv  # noqa: F401
+from .dressing_envs import DressingPR2Env  # noqa: F401
 from .feeding_envs import FeedingJacoEnv  # noqa: F401
 
-ENV_REGISTRY = {'FeedingJaco-v1': FeedingJacoEnv, 'BedBathingSawyer-v1': BedBathingSawyerEnv}
+ENV_REGISTRY = {'FeedingJaco-v1': FeedingJacoEnv, 'BedBathingSawyer-v1': BedBathingSawyerEnv, 'DressingPR2-v1': DressingPR2Env}
 
 
 def make(env_id, **kw):

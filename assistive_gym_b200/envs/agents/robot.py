@@ -88,3 +88,14 @@ class Sawyer(Robot):
                           'bed_bathing': [0, np.pi / 2.0, 0], 'dressing': [[0, -np.pi / 2.0, 0], [np.pi / 2.0, -np.pi / 2.0, 0]],
                           'arm_manipulation': [0, -np.pi / 2.0, np.pi]},
                          wheelchair_mounted=False, half_range=False)
+
+
+class PR2(Robot):
+    """reference envs/agents/pr2.py:7-49 (the constants of the Dressing hot path; the wheel / right-arm tables are kept
+    because `controllable_joints` selects among them)."""
+
+    def __init__(self, controllable_joints='right'):
+        super().__init__(controllable_joints, [42, 43, 44, 46, 47, 49, 50], [64, 65, 66, 68, 69, 71, 72], list(range(3, 15)), 54, 76,
+                         [57, 58, 59, 60], [79, 80, 81, 82], {'dressing': [0] * 4}, 54, 76, {}, {},
+                         list(range(49, 64)), list(range(71, 86)), {'dressing': [1.7, 0.7, 0]},
+                         {'dressing': [[0, 0, np.pi], [0, 0, np.pi * 3 / 2.0]]}, wheelchair_mounted=False, half_range=False)

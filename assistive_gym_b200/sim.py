@@ -266,6 +266,26 @@ class BatchSim:
         self._ck(self.lib.ag_cloth_get_contacts(self.h, max_pts, _p(cnt), _p(node), _p(pos), _p(force), _p(link)))
         return cnt, self.cloth_model.order[node], pos, force, link
 
+    # ---- fused dressing path
+    def dressing_init(self, params, gender_is_male):
+        self._dress_params = params
+        self._ck(self.lib.ag_dressing_init(self.h, C.byref(params), _p(_i32(gender_is_male))))
+
+    def dressing_reset_episode(self, mask=None):
+        self._ck(self.lib.ag_dressing_reset_episode(self.h, _p(_i32(mask))))
+
+    def dressing_step_host(self, action):
+        a = _f32(action, (self.n, 7))
+        obs = np.empty((self.n, 24), dtype=np.float32)
+        rew = np.empty(self.n, dtype=np.float32)
+        done = np.empty(self.n, dtype=np.float32)
+        info = np.empty((self.n, 4), dtype=np.float32)
+        self._ck(self.lib.ag_dressing_step_host(self.h, _p(a), _p(obs), _p(rew), _p(done), _p(info)))
+        return obs, rew, done, info
+
+    def dressing_step_dev(self, action_ptr, obs_ptr, reward_ptr, done_ptr, info_ptr):
+        self._ck(self.lib.ag_dressing_step_dev(self.h, action_ptr, obs_ptr, reward_ptr, done_ptr, info_ptr))
+
     def feeding_reset_episode(self, mask=None):
         self._ck(self.lib.ag_feeding_reset_episode(self.h, _p(_i32(mask))))
 

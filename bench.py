@@ -250,6 +250,111 @@ def run_bedbathing(args):
                       'gpu_launches': int(sim.kernel_launches())}))
 
 
+def run_dressing(args):
+    """BASELINE.json configs[3]: DressingPR2-v1 @ batch 2048 on one B200 (cloth-capsule contact path), fused step: device-timed
+    value, host-buffer e2e, the roofline of k_cloth (the one HBM-shaped kernel of the repo: SURVEY.md 8(d), 190 KB of cloth
+    state per env and substep) and the CPU oracle on a bounded sample."""
+    import torch
+    from assistive_gym_b200 import capi
+    from assistive_gym_b200.dressing_batch import DressingBatch
+    from assistive_gym_b200.sim import BatchSim
+    n, K, W = (args.batch if args.batch != BATCH_PER_GPU else 2048), args.steps, max(args.warmup, 3)
+    db = DressingBatch()
+    cfg = capi.default_config(num_substeps=8)
+    rng = np.random.default_rng(0)
+    if args.impl == 'reference':
+        from oracle.oracle_py import OracleSim
+        cores = usable_cores()
+        ne = max(cores, 8)
+        gpu_free = None
+        try:                                   # the reset needs the device IK: replay a stored reset when there is no GPU
+            gsim = BatchSim(db.scene, cfg, ne)
+            smp = db.reset(gsim, rng, attempts=10, settle_steps=0)
+            gsim.close()
+        except Exception as ex:                # pragma: no cover
+            print(json.dumps({'impl': 'reference', 'unavailable': 'dressing CPU arm needs the device IK for its reset: %s' % ex}))
+            return
+        orc = OracleSim(db.scene, cfg, ne, threads=cores)
+        db.reset(orc, rng, sample=smp, settle_steps=0)
+        t0 = time.perf_counter()
+        steps = 0
+        while time.perf_counter() - t0 < 15.0 or steps < 1:
+            orc.step(1); orc.cloth_anchor_follow(db.ee_link); steps += 1
+        dt = time.perf_counter() - t0
+        v = ne * steps / 5.0 / dt
+        print(json.dumps({'metric': 'env-steps/sec DressingPR2-v1 @batch%d' % n, 'impl': 'reference', 'value': v, 'unit': 'env-steps/s', 'n_gpus': 1, 'steps': K, 'warmup': W,
+                          'ms_per_step': 1e3 * n / v, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                          'config': {'workload': 'DressingPR2-v1, CPU restatement (PyBullet unavailable), %d envs x %d stepSimulation calls' % (ne, steps)},
+                          'cpu_baseline': {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': '%d envs x %d stepSimulation (%.1f s)' % (ne, steps, dt)},
+                          'e2e': {'value': v, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+    sim = BatchSim(db.scene, cfg, n)
+    t0 = time.time()
+    smp = db.reset(sim, rng, attempts=args.toc_attempts, settle_steps=50)
+    db.start_fused(sim, smp)
+    reset_s = time.time() - t0
+    stream = torch.cuda.ExternalStream(sim.stream_ptr())
+    dev = torch.device('cuda')
+    act = torch.rand((K + W, n, 7), device=dev) * 2 - 1
+    obs = torch.zeros((n, 24), device=dev); rew = torch.zeros(n, device=dev); done = torch.zeros(n, device=dev); info = torch.zeros((n, 4), device=dev)
+    torch.cuda.synchronize()
+    for i in range(W):
+        sim.dressing_step_dev(act[i].data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), info.data_ptr())
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0); clocks.start()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = sim.kernel_launches()
+    with torch.cuda.stream(stream):
+        a.record(stream)
+    for i in range(K):
+        sim.dressing_step_dev(act[W + i].data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), info.data_ptr())
+    with torch.cuda.stream(stream):
+        b.record(stream)
+    torch.cuda.synchronize()
+    launches = sim.kernel_launches() - l0
+    clk = clocks.stop()
+    ms = a.elapsed_time(b) / K
+    # per-kernel split in a separate pass (events around every launch, no graph)
+    sim.profile_enable(True)
+    for i in range(2):
+        sim.dressing_step_dev(act[i].data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), info.data_ptr())
+    torch.cuda.synchronize()
+    prof = sim.profile_get()
+    sim.profile_enable(False)
+    per_kernel = {k_: v[0] / 2 for k_, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    cloth_ms = prof['k_cloth'][0] / prof['k_cloth'][1]
+    host_a = np.random.default_rng(1).uniform(-1, 1, size=(K, n, 7)).astype(np.float32)
+    sim.dressing_step_host(host_a[0])
+    t0 = time.perf_counter()
+    for i in range(K):
+        sim.dressing_step_host(host_a[i])
+    e2e = n * K / (time.perf_counter() - t0)
+    ccnt = sim.cloth_get_contacts(1)[0]
+    rcnt, it = sim.solver_stats()
+    peak, peak_src = measured_peak()
+    nn = db.cloth.n_nodes
+    alg = n * 8 * nn * 6 * 4 * 2                     # x and v of every node read and written once per substep, 8 substeps per launch
+    ach = alg / cloth_ms / 1e6
+    traffic, traffic_src = ncu_traffic('k_cloth')
+    info_h = info.cpu().numpy()
+    print(json.dumps({'metric': 'env-steps/sec DressingPR2-v1 @batch%d' % n, 'value': n / ms * 1e3, 'unit': 'env-steps/s', 'n_gpus': 1, 'steps': K, 'warmup': W,
+                      'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                      'config': {'workload': 'DressingPR2-v1, batch %d, fused step: 5 x (8 rigid substeps + 1 cloth launch), gown 3966 nodes / 11640 links, 5 position iterations, random actions' % n,
+                                 'global_batch': n, 'l2': 'not flushed; the per-step working set (cloth state %d MB) exceeds L2' % (n * nn * 6 * 4 // 2 ** 20),
+                                 'reset_s': reset_s, 'toc_attempts': args.toc_attempts, 'goals_reached_mean': float(np.mean(db.goals_reached)), 'base_unresolved': int(db.unresolved),
+                                 'cloth_contacts_per_env': {'mean': float(ccnt.mean()), 'p99': float(np.percentile(ccnt, 99)), 'max': int(ccnt.max())},
+                                 'rigid_contacts_per_env': {'mean': float(rcnt.mean()), 'max': int(rcnt.max())},
+                                 'envs_over_budget': int(sim.overflow_count()),
+                                 'sleeve_state_counts': {str(k_): int((info_h[:, 3] == k_).sum()) for k_ in (0, 1, 2, 3)},
+                                 'cloth_force_mean_N': float(obs[:, 23].mean().item())},
+                      'clocks': clk, 'e2e': {'value': e2e, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n * 7 * 4, 'd2h_bytes_per_step': n * 30 * 4},
+                      'gpu_launches': int(launches),
+                      'roofline': {'bound': 'hbm', 'kernel': 'k_cloth', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': traffic, 'traffic_source': traffic_src,
+                                   'peak_source': peak_src, 'kernel_ms_per_launch': cloth_ms, 'kernel_share_of_step': 5 * cloth_ms / ms,
+                                   'algorithmic_bytes_per_launch': alg, 'per_kernel_ms_per_step': per_kernel,
+                                   'note': 'algorithmic bytes = 190 KB per env and substep (SURVEY.md 8(d)); the kernel keeps the cloth in shared memory over the 8 substeps of a launch, so its DRAM traffic is ~1/8 of that'}}))
+
+
 def ncu_traffic(kernel):
     """DRAM bytes (read + write) of one launch of `kernel` from the newest committed `ncu --set full` summary
     (profiles/r*_ncu_<kernel>.csv, written by tools/ncu_summary.py); (None, None) if there is none."""
@@ -291,11 +396,14 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='envs per GPU')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--profile-kernels', type=int, default=1)
-    ap.add_argument('--workload', default='feeding', choices=['feeding', 'bedbathing'], help="'bedbathing': BASELINE.json configs[2] (dense tool-skin contact), a secondary line")
+    ap.add_argument('--workload', default='feeding', choices=['feeding', 'bedbathing', 'dressing'], help="'bedbathing': BASELINE.json configs[2] (dense tool-skin contact), 'dressing': configs[3] (cloth); secondary lines")
+    ap.add_argument('--toc-attempts', type=int, default=10, help='dressing: random base poses ranked per reset (the reference uses 50)')
     ap.add_argument('--sub-batches', type=int, default=int(os.environ.get('AG_SUB_BATCHES', '1')), help='independent sub-batches per GPU, each on its own stream')
     args = ap.parse_args()
     if args.workload == 'bedbathing':
         return run_bedbathing(args)
+    if args.workload == 'dressing':
+        return run_dressing(args)
     if args.impl == 'reference':
         return run_reference(args)
 

@@ -280,6 +280,29 @@ int ag_cloth_get_contacts(AgSim* sim, int max_pts, int32_t* count, int32_t* node
 /* device pointers for fused consumers: x / v are [N][3][n_nodes_padded] */
 int ag_cloth_device_state(AgSim* sim, float** x_dev, float** v_dev, int32_t* n_nodes_padded);
 
+/* --- fused DressingEnv path (dressing.py:12-106 + env.py:174-274 + util.py:125-202): action -> PD targets -> frame_skip x
+ * (numSubSteps rigid substeps, one cloth launch, the cloth's anchor body follows the end effector) -> sleeve-on-arm reward,
+ * cloth forces on the person, obs [24] / reward / done.  Needs ag_cloth_init.  SURVEY.md section 8(a) row D1. ---------- */
+typedef struct AgDressingParams {
+  int32_t robot_body, human_body_m, human_body_f;
+  int32_t arm_links[7];         /* controllable joints (global link ids): PR2 left arm */
+  int32_t ee_link;              /* left_end_effector */
+  int32_t arm_points_m[3], arm_points_f[3];   /* left shoulder, elbow, wrist links (global ids) */
+  float   arm_lower[7], arm_upper[7];
+  float   hand_radius_m, elbow_radius_m, shoulder_radius_m, hand_radius_f, elbow_radius_f, shoulder_radius_f; /* human_creation.py:89,140 */
+  int32_t tri1[3], tri2[3];     /* sleeve-opening nodes (dressing.py:149-150), cloth-internal ids */
+  float   action_multiplier;    /* 0.05 env.py:188 */
+  int32_t frame_skip;           /* 5 */
+  float   w_dressing, w_action; /* config.ini [dressing] */
+  float   c_v, c_d;             /* config.ini [human_preferences] velocity_weight, dressing_force_weight */
+  float   task_success_threshold;
+} AgDressingParams;
+int ag_dressing_init(AgSim* sim, const AgDressingParams* p, const int32_t* gender_is_male);
+int ag_dressing_reset_episode(AgSim* sim, const int32_t* env_mask);
+/* obs [N][24], reward [N], done [N], info [N][4] = total force on the person, task success, reward_dressing, sleeve state */
+int ag_dressing_step_dev(AgSim* sim, const float* action_dev, float* obs_dev, float* reward_dev, float* done_dev, float* info_dev);
+int ag_dressing_step_host(AgSim* sim, const float* action, float* obs, float* reward, float* done, float* info);
+
 /* --- batched inverse kinematics for reset (Robot.ik_random_restarts agents/robot.py:84-121 via
  * AssistiveEnv.init_robot_pose envs/env.py:296): damped least squares with random restarts inside
  * the joint limits, one env per thread.  `joint_links` [n_joints <= 8]: the solved joints (global link ids, all on the

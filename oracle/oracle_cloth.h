@@ -104,6 +104,7 @@ inline void ocloth_substep(const Scene& s, const Env& e, const OCloth& C, OCloth
     if (anchored[i]) continue;
     for (size_t L = 0; L < C.col_links.size(); L++) {
       int link = C.col_links[L];
+      if (e.body_mode[s.link_body[link]] == 0) continue;       // a body switched off in this env does not exist for the cloth
       V3 bc = e.lpos[link] + qrot(e.lquat[link], C.bs_c[L]);
       real br = C.bs_r[L] + C.margin;
       if (dot(x[i] - bc, x[i] - bc) > br * br) continue;

@@ -1,0 +1,107 @@
+"""DressingPR2-v1 (BASELINE.json configs[3]): the fused step of the product against a numpy
+restatement of reference envs/dressing.py driven through the CPU oracle, from the same reset.
+
+The reset (base-pose search with the device IK) needs the product; its outcome (base pose, start joint angles) is stored
+in the sample and replayed into the oracle, so both sides start in the same state."""
+import numpy as np
+import pytest
+
+from assistive_gym_b200 import capi
+from assistive_gym_b200.dressing_batch import CLOTH_ANCHORS, PR2, DressingBatch, jlwki
+from assistive_gym_b200.sim import BatchSim
+from oracle.oracle_py import OracleSim
+from tests.dressing_cases import DressingReference
+
+
+@pytest.fixture(scope='module')
+def dressing():
+    return DressingBatch()
+
+
+def test_scene_recipe(dressing):
+    db, sc = dressing, dressing.scene
+    # PR2 link numbering = PyBullet's DFS order: the reference's tables address the left arm / gripper / tool frame by index
+    names = [l.name for l in db.builder.links[int(sc['body_link0'][db.robot]) + 1:]]
+    assert [names[j] for j in PR2['arm']] == ['l_shoulder_pan_link', 'l_shoulder_lift_link', 'l_upper_arm_roll_link', 'l_elbow_flex_link',
+                                             'l_forearm_roll_link', 'l_wrist_flex_link', 'l_wrist_roll_link']     # pr2.py:9
+    assert names[PR2['ee']] == 'l_gripper_tool_frame'                                                          # pr2.py:12
+    live = [k for k in range(sc.n_links) if sc['link_body'][k] == db.robot and sc['link_jtype'][k] in (1, 2)]
+    assert len(live) == 11                                     # 7 arm + 4 gripper joints, everything else welded
+    assert len(db.cloth_links) <= 96 and db.cloth.n_nodes == 3966
+    # JLWKI of an isotropic Jacobian with mid-range joints is 1 (robot.py:184-186)
+    J = np.zeros((1, 6, 7)); J[0, :6, :6] = np.eye(6)
+    assert abs(jlwki(J, np.zeros((1, 7)), -np.ones(7), np.ones(7))[0] - 1.0) < 1e-4
+
+
+def _pair(lib, db, n, attempts=12, settle=3, seed=0):
+    cfg = capi.default_config(num_substeps=8)
+    prod = BatchSim(db.scene, cfg, n, _lib=lib)
+    rng = np.random.default_rng(seed)
+    smp = db.reset(prod, rng, attempts=attempts, settle_steps=0)
+    assert db.unresolved == 0 and np.all(db.goals_reached >= 1)
+    orc = OracleSim(db.scene, cfg, n, threads=4)
+    db.reset(orc, np.random.default_rng(seed), sample=smp, settle_steps=0)
+    for s in (prod, orc):                                      # a short settle at half gravity on both sides (dressing.py:178-193)
+        s.cloth_set_gravity([0, 0, -9.81 / 2])
+        s.step(settle)
+        s.cloth_set_gravity([0, 0, -9.81])
+    return prod, orc, smp
+
+
+def _fused_step_vs_reference(lib, n=3, steps=2):
+    db = DressingBatch()
+    prod, orc, smp = _pair(lib, db, n)
+    # same state on both sides before the compared steps
+    xo, vo = orc.cloth_get_state()
+    prod.cloth_set_state(xo, vo)
+    prod.state_set(orc.state_get().astype(np.float32))
+    db.start_fused(prod, smp)
+    ref = DressingReference(db, orc, smp['male'])
+    rng = np.random.default_rng(5)
+    for it in range(steps):
+        a = rng.uniform(-1, 1, size=(n, 7))
+        obs, rew, done, info = prod.dressing_step_host(a.astype(np.float32))
+        obs_r, rew_r, done_r, info_r = ref.step(a)
+        xp, _ = prod.cloth_get_state()
+        xo, vo = orc.cloth_get_state()
+        err = np.abs(xp - xo).max(axis=2)
+        assert np.median(err) < 1e-5 and (err > 1e-3).mean() < 0.02, (np.median(err), (err > 1e-3).mean())      # north star: 1e-3 m
+        assert np.abs(obs[:, :7] - obs_r[:, :7]).max() < 1e-3                     # end effector pose in the robot frame
+        assert np.abs(obs[:, 7:14] - obs_r[:, 7:14]).max() < 1e-4                 # joint angles (north star: 1e-4 rad)
+        assert np.abs(obs[:, 14:23] - obs_r[:, 14:23]).max() < 1e-3               # shoulder / elbow / wrist
+        assert np.array_equal(info[:, 3], info_r[:, 3])                           # sleeve state
+        assert np.abs(info[:, 2] - info_r[:, 2]).max() < 2e-3                     # reward_dressing (a distance)
+        cf, cf_r = obs[:, 23], obs_r[:, 23]
+        assert np.all(np.abs(cf - cf_r) <= 0.05 * np.maximum(cf_r, 1.0) + 0.5), (cf, cf_r)       # cloth force on the person (5 %)
+        assert np.abs(rew - rew_r).max() < 0.02 + 0.01 * 0.05 * np.abs(cf_r).max()
+        assert np.array_equal(done, done_r)
+        prod.cloth_set_state(xo, vo)                                               # re-synchronise
+        prod.state_set(orc.state_get().astype(np.float32))
+    assert prod.overflow_count() == 0
+
+
+def test_fused_dressing_step_host_compiled(emu_lib):
+    _fused_step_vs_reference(emu_lib)
+
+
+@pytest.mark.gpu
+def test_fused_dressing_step_cuda(gpu_lib):
+    _fused_step_vs_reference(gpu_lib, n=4, steps=3)
+
+
+@pytest.mark.gpu
+def test_dressing_env_episode_cuda(gpu_lib):
+    """The gym-facing env: reset + 20 fused steps at n = 64, finite, contact budgets respected, cloth stays attached."""
+    from assistive_gym_b200.envs import make
+    env = make('DressingPR2-v1', n_envs=64, toc_attempts=8)
+    obs = env.reset()
+    assert obs.shape == (64, 24) and np.all(np.isfinite(obs))
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        obs, rew, done, info = env.step(rng.uniform(-1, 1, size=(64, 7)))
+    assert np.all(np.isfinite(obs)) and np.all(np.isfinite(rew))
+    x, _ = env.id.cloth_get_state()
+    ee = env.id.get_link_states([env._db.ee_link])['pos'][:, 0]
+    d = np.linalg.norm(x[:, CLOTH_ANCHORS[0]] - ee, axis=1)
+    assert d.max() < 0.08, d.max()                # anchor node within a few cm of the end effector (local offset 2 cm)
+    assert env.id.overflow_count() == 0

@@ -303,6 +303,7 @@ URDFS = {
     'sawyer': 'sawyer/sawyer.urdf',
     'bed': 'bed/bed.urdf',
     'wiper': 'bed_bathing/wiper.urdf',
+    'pr2': 'PR2/pr2_no_torso_lift_tall.urdf',
 }
 CLOTHS = {
     'hospitalgown_reduced': 'clothing/hospitalgown_reduced.obj',
