@@ -20,6 +20,7 @@ import numpy as np
 
 from .human_model import create_human
 from .kinematics import BodyKinematics, ik_dls, q_from_rpy, q_mul, q_rot
+from .toc import position_robot_toc
 from .scene import SceneBuilder, quat_from_rpy
 
 MOTOR_POSITION = 1
@@ -208,7 +209,7 @@ class BedBathingBatch:
         sim.set_base_velocity(self.tool, np.zeros((n, 3)), np.zeros((n, 3)))
         return tp, tq
 
-    def reset(self, sim, rng, sample=None, base_attempts=6):
+    def reset(self, sim, rng, sample=None, base_attempts=6, toc_attempts=50):
         n = sim.n
         sc = self.scene
         s = sample or self.sample(n, rng)
@@ -245,25 +246,13 @@ class BedBathingBatch:
         obstacles = [self.humans['male'], self.humans['female'], self.bed]
         self.base_draws = 0
         replay = 'base_pos' in s            # a stored reset (same draws, e.g. oracle and product side of a parity test)
-        for attempt in range(1 if replay else base_attempts):
-            if len(todo) == 0:
-                break
-            m = len(todo)
-            self.base_draws += m
-            if replay:
-                base_pos, base_quat, qik, ik_err = s['base_pos'].copy(), s['base_quat'].copy(), s['qik'].copy(), s['ik_err'].copy()
-            else:
-                rp = np.stack([rng.uniform(-0.5, 0, size=m), rng.uniform(-0.5, 0.5, size=m), np.zeros(m)], axis=1)   # right_side=True
-                yaw = np.deg2rad(rng.uniform(-30, 30, size=m))
-                bp = np.array([-0.85, -0.4, 0]) + np.array(SAWYER['toc_base_pos_offset']) + rp
-                bq = np.stack([np.zeros(m), np.zeros(m), np.sin(yaw / 2), np.cos(yaw / 2)], axis=1)
-                base_pos[todo], base_quat[todo] = bp, bq
-                sim.set_base_pose(self.robot, base_pos, base_quat)
-                q, err = self.solve_ik(bp, bq, target[todo], rng, sim=sim, idx=todo)
-                qik[todo], ik_err[todo] = q, err
-            # collision test of robot + tool against person and bed at this pose (env.py:300-309)
+        use_toc = (not replay) and toc_attempts > 0 and hasattr(sim, 'ik_solve')
+        arm_local = np.array(SAWYER['arm']) + 1
+
+        def collides(base_pos, base_quat, qik):
+            """robot + tool against person and bed at this pose (env.py:300-309)"""
             sim.set_base_pose(self.robot, base_pos, base_quat)
-            arm_q = qik[:, np.array(SAWYER['arm']) + 1]
+            arm_q = qik[:, arm_local]
             sim.set_joint_state(self.arm_links, q=arm_q, qd=np.zeros_like(arm_q))
             qfull = qik.copy(); qfull[:, np.array(SAWYER['gripper']) + 1] = SAWYER['gripper_pos']
             self.place_tool(sim, base_pos, base_quat, qfull)
@@ -272,8 +261,52 @@ class BedBathingBatch:
             for ob in obstacles:
                 hit |= sim.closest_points(self.robot, ob, 0.0, max_pts=1)[1] > 0
                 hit |= sim.closest_points(self.tool, ob, 0.0, max_pts=1)[1] > 0
-            bad = hit | (ik_err >= 0.03)
+            return hit
+
+        if use_toc:
+            # Robot.position_robot_toc (robot.py:123-221, called from env.py:299 with attempts=50): random base poses ranked by
+            # goals reached (start pose + shoulder / elbow / wrist of the arm to be washed, position only) and JLWKI
+            limb = np.zeros((n, 3, 3))
+            for g, hb in self.humans.items():
+                on = male if g == 'male' else ~male
+                ls = sim.get_link_states([self.gl(hb, R_SHOULDER), self.gl(hb, R_ELBOW), self.gl(hb, R_WRIST)])['pos']
+                limb[on] = ls[on]
+            tq = np.tile(q_from_rpy(SAWYER['ee_orient_rpy']), (n, 1))
+            base0 = np.array([-0.85, -0.4, 0]) + np.array(SAWYER['toc_base_pos_offset'])
+            mask = np.ones(n, dtype=bool)
+            reached = np.zeros(n, dtype=int)
+            for _ in range(3):                                                   # env.py:282
+                bp, bq, bj, num, _man = position_robot_toc(sim, rng, self.robot, self.arm_links, self.ee_link, self.kin, arm_local, SAWYER['ee'] + 1,
+                                                           self.arm_lower, self.arm_upper, base0, [(target, tq)] + [(limb[:, j], None) for j in range(3)],
+                                                           right_side=True, base_yaw=0.0, attempts=toc_attempts, mask=mask)
+                self.base_draws += int(mask.sum()) * toc_attempts
+                base_pos[mask], base_quat[mask], reached[mask] = bp[mask], bq[mask], num[mask]
+                qik[np.ix_(mask, arm_local)] = bj[mask]
+                ik_err[mask] = np.where(num[mask] >= 1, 0.0, np.inf)
+                mask = collides(base_pos, base_quat, qik) | (ik_err >= 0.03)
+                if not mask.any():
+                    break
+            todo = np.nonzero(mask)[0]
+            self.goals_reached = reached
+        for attempt in range(0 if use_toc else (1 if replay else base_attempts)):
+            if len(todo) == 0:
+                break
+            m = len(todo)
+            self.base_draws += m
+            if replay:
+                base_pos, base_quat, qik, ik_err = s['base_pos'].copy(), s['base_quat'].copy(), s['qik'].copy(), s['ik_err'].copy()
+            else:                               # a sim without the device IK (the CPU oracle): first feasible draw of the same distribution
+                rp = np.stack([rng.uniform(-0.5, 0, size=m), rng.uniform(-0.5, 0.5, size=m), np.zeros(m)], axis=1)   # right_side=True
+                yaw = np.deg2rad(rng.uniform(-30, 30, size=m))
+                bp = np.array([-0.85, -0.4, 0]) + np.array(SAWYER['toc_base_pos_offset']) + rp
+                bq = np.stack([np.zeros(m), np.zeros(m), np.sin(yaw / 2), np.cos(yaw / 2)], axis=1)
+                base_pos[todo], base_quat[todo] = bp, bq
+                sim.set_base_pose(self.robot, base_pos, base_quat)
+                q, err = self.solve_ik(bp, bq, target[todo], rng, sim=sim, idx=todo)
+                qik[todo], ik_err[todo] = q, err
+            bad = collides(base_pos, base_quat, qik) | (ik_err >= 0.03)
             todo = np.nonzero(bad)[0]
+        collides(base_pos, base_quat, qik)      # leaves robot, arm and tool at the chosen pose
         self.ik_err, self.unresolved = ik_err, int(len(todo))
         self.base_pos, self.base_quat = base_pos, base_quat
         if not replay:

@@ -70,6 +70,7 @@ AG_HDN inline void ik_body(int e, const SimDev& S, const KP& p) {
   const float* tpp = (const float*)p.p1 + (size_t)e * 3;
   const float* tqp = (const float*)p.p2 + (size_t)e * 4;
   f3 tp(tpp[0], tpp[1], tpp[2]); q4 tq(tqp[0], tqp[1], tqp[2], tqp[3]);
+  const bool pos_only = !(tq.w == tq.w);         // a NaN target orientation: position-only goal (`target_orient=None`, robot.py:86,100)
   const int nj = K.n_joints;
   unsigned long long rs = (K.seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(e + 1)) | 1ull;
   float best[AG_IK_MAXJ], best_err = 1e30f;
@@ -87,18 +88,19 @@ AG_HDN inline void ik_body(int e, const SimDev& S, const KP& p) {
       f3 dp = tp - ep;
       q4 qe = qmul(tq, qconj(eq));
       if (qe.w < 0.f) qe = q4(-qe.x, -qe.y, -qe.z, -qe.w);
+      if (pos_only) qe = q4(0.f, 0.f, 0.f, 1.f);
       float er[6] = {dp.x, dp.y, dp.z, 2.f * qe.x, 2.f * qe.y, 2.f * qe.z};
       // the reference's success test: position distance and orientation (quaternion) distance (robot.py:100-104)
       float oe = fminf(sqrtf((tq.x - eq.x) * (tq.x - eq.x) + (tq.y - eq.y) * (tq.y - eq.y) + (tq.z - eq.z) * (tq.z - eq.z) + (tq.w - eq.w) * (tq.w - eq.w)),
                        sqrtf((tq.x + eq.x) * (tq.x + eq.x) + (tq.y + eq.y) * (tq.y + eq.y) + (tq.z + eq.z) * (tq.z + eq.z) + (tq.w + eq.w) * (tq.w + eq.w)));
-      err = fmaxf(norm(dp), oe);
+      err = pos_only ? norm(dp) : fmaxf(norm(dp), oe);
       float m6 = 0.f; for (int i = 0; i < 6; i++) m6 = fmaxf(m6, fabsf(er[i]));
       if (it == K.iters || m6 < 1e-5f) break;
       float J[6 * AG_IK_MAXJ];
       for (int j = 0; j < nj; j++) {
         f3 a = axw[j];
         int jt = K.col_jtype[j];
-        f3 lin = jt == 1 ? cross(a, ep - org[j]) : a, ang = jt == 1 ? a : f3();
+        f3 lin = jt == 1 ? cross(a, ep - org[j]) : a, ang = (jt == 1 && !pos_only) ? a : f3();
         J[0 * nj + j] = lin.x; J[1 * nj + j] = lin.y; J[2 * nj + j] = lin.z; J[3 * nj + j] = ang.x; J[4 * nj + j] = ang.y; J[5 * nj + j] = ang.z;
       }
       float A[36];

@@ -18,6 +18,7 @@ from . import capi
 from .cloth import ClothModel
 from .human_model import create_human
 from .kinematics import BodyKinematics, q_axis, q_from_rpy, q_mul, q_rot
+from .toc import jlwki, position_robot_toc  # noqa: F401
 from .scene import JOINT_FIXED, JOINT_PRISMATIC, JOINT_REVOLUTE, SceneBuilder, quat_from_rpy, quat_mul, quat_rotate
 
 MOTOR_POSITION = 1
@@ -36,16 +37,6 @@ TRIANGLE1, TRIANGLE2 = [1180, 2819, 30], [1322, 13, 696]    # dressing.py:149-15
 CLOTH_ORIG_POS = np.array([0.34658437, -0.30296362, 1.20023387])      # dressing.py:140
 CLOTH_POSITION = np.array([0.02, -0.38, 0.84])              # dressing.py:146 (scaled with the mesh)
 CLOTH_SCALE = 1.4
-
-
-def jlwki(J, q, lower, upper, order=6):
-    """Joint-limited-weighted kinematic isotropy of Jacobians J [N,6,7] at joint angles q [N,7] (robot.py:173-186,223-235)."""
-    qr = 0.5 * (upper - lower)
-    w = 1.0 - np.power(0.5, (qr - np.abs(qr - q + lower)) / (0.05 * qr) + 1)
-    w = np.maximum(w, 0.001)
-    JW = np.einsum('nij,nj,nkj->nik', J, w, J)
-    det = np.maximum(np.linalg.det(JW), 0.0)
-    return np.power(det, 1.0 / order) / (np.trace(JW, axis1=1, axis2=2) / order)
 
 
 class DressingBatch:
@@ -152,52 +143,12 @@ class DressingBatch:
             out[g] = (links, q)
         return out
 
-    def arm_jacobian(self, base_pos, base_quat, q7):
-        """Geometric Jacobian [N,6,7] of the end-effector link's centre of mass w.r.t. the 7 arm joints (robot.py:170-177)."""
-        n = len(q7)
-        kin = self.kin
-        q = np.zeros((n, kin.nl))
-        q[:, np.array(PR2['arm']) + 1] = q7
-        ee = PR2['ee'] + 1
-        pos, quat = kin.fk(base_pos, base_quat, q, upto=ee)
-        point = pos[:, ee] + q_rot(quat[:, ee], kin.com[ee])
-        return kin.jacobian(pos, quat, ee, point, np.array(PR2['arm']) + 1)
-
     def position_robot_toc(self, sim, rng, start, targets, attempts=50, mask=None):
-        """Robot.position_robot_toc (robot.py:123-221) for all envs at once: `attempts` random base poses, for each the start
-        goal and the target goals are solved by IK (device, one random restart, 100 iterations, threshold 0.03); poses are
-        ranked by goals reached, then by the sum of JLWKI over reached goals; the start goal must be reachable."""
-        n = sim.n
-        mask = np.ones(n, dtype=bool) if mask is None else mask
-        goals = [start] + list(targets)
-        best_num = np.full(n, -1); best_man = np.zeros(n)
-        best_pos = np.zeros((n, 3)); best_quat = np.tile([0, 0, 0, 1.0], (n, 1)); best_q = np.tile(PR2['left_preset'], (n, 1)).astype(np.float64)
+        """Robot.position_robot_toc for the left arm (dressing.py:134: right_side=False, base yaw pi, 50 attempts)."""
         base0 = np.array([-0.85, -0.4, 0]) + np.array(PR2['toc_base_pos_offset'])
-        it = 0
-        while it < attempts or np.any(mask & (best_num < 0)):
-            it += 1
-            if it > attempts + 50:
-                break
-            rp = np.stack([rng.uniform(0, 0.5, size=n), rng.uniform(-0.5, 0.5, size=n), np.zeros(n)], axis=1)    # right_side=False
-            yaw = np.pi + np.deg2rad(rng.uniform(-30, 30, size=n))
-            bp = base0 + rp
-            bq = np.stack([np.zeros(n), np.zeros(n), np.sin(yaw / 2), np.cos(yaw / 2)], axis=1)
-            sim.set_base_pose(self.robot, bp, bq, mask=mask.astype(np.int32))
-            num = np.zeros(n, dtype=int); man = np.zeros(n); valid = mask.copy(); q_start = np.zeros((n, 7))
-            for j, (tp, tq) in enumerate(goals):
-                q7, err = sim.ik_solve(self.arm_links, self.ee_link, tp, tq, max_restarts=1, iters=100, threshold=0.03,
-                                       seed=int(rng.integers(1, 2 ** 31 - 1)), mask=valid.astype(np.int32))
-                ok = valid & (err < 0.03)
-                if ok.any():
-                    score = np.zeros(n)
-                    score[ok] = jlwki(self.arm_jacobian(bp[ok], bq[ok], q7[ok].astype(np.float64)), q7[ok].astype(np.float64), self.arm_lower, self.arm_upper)
-                    num += ok; man += np.where(ok, score, 0.0)
-                if j == 0:
-                    q_start = q7.astype(np.float64); valid &= ok
-            better = valid & (num > 0) & ((num > best_num) | ((num == best_num) & (man > best_man)))
-            best_num[better], best_man[better] = num[better], man[better]
-            best_pos[better], best_quat[better], best_q[better] = bp[better], bq[better], q_start[better]
-        return best_pos, best_quat, best_q, best_num, best_man
+        return position_robot_toc(sim, rng, self.robot, self.arm_links, self.ee_link, self.kin, np.array(PR2['arm']) + 1, PR2['ee'] + 1,
+                                  self.arm_lower, self.arm_upper, base0, [start] + list(targets), right_side=False, base_yaw=np.pi,
+                                  attempts=attempts, mask=mask, default_q=PR2['left_preset'])
 
     def reset(self, sim, rng, sample=None, attempts=50, settle_steps=50, outer_iterations=3):
         n = sim.n

@@ -206,7 +206,7 @@ def run_bedbathing(args):
     sim = BatchSim(bb.scene, capi.default_config(), n)
     rng = np.random.default_rng(0)
     t0 = time.time()
-    s = bb.reset(sim, rng)
+    s = bb.reset(sim, rng, toc_attempts=args.toc_attempts)
     ik_err = bb.hover_over_forearm(sim, s, rng)
     bb.start_fused(sim, s)
     reset_s = time.time() - t0
@@ -397,7 +397,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--profile-kernels', type=int, default=1)
     ap.add_argument('--workload', default='feeding', choices=['feeding', 'bedbathing', 'dressing'], help="'bedbathing': BASELINE.json configs[2] (dense tool-skin contact), 'dressing': configs[3] (cloth); secondary lines")
-    ap.add_argument('--toc-attempts', type=int, default=10, help='dressing: random base poses ranked per reset (the reference uses 50)')
+    ap.add_argument('--toc-attempts', type=int, default=10, help='dressing / bedbathing: random base poses ranked per reset (the reference uses 50)')
     ap.add_argument('--sub-batches', type=int, default=int(os.environ.get('AG_SUB_BATCHES', '1')), help='independent sub-batches per GPU, each on its own stream')
     args = ap.parse_args()
     if args.workload == 'bedbathing':
