@@ -11,9 +11,9 @@ import numpy as np
 
 
 class AssistiveVecEnv:
-    def __init__(self, env_id='assistive_gym:FeedingJaco-v1', n_envs=4096, device=0, seed=1001, auto_reset=True, config=None, _lib=None):
+    def __init__(self, env_id='assistive_gym:FeedingJaco-v1', n_envs=4096, device=0, seed=1001, auto_reset=True, config=None, _lib=None, **env_kw):
         from . import envs
-        self.env = envs.make(env_id, n_envs=n_envs, device=device, seed=seed, config=config)
+        self.env = envs.make(env_id, n_envs=n_envs, device=device, seed=seed, config=config, **env_kw)
         if _lib is not None:
             self.env._sim_lib = _lib
         self.n_envs, self.device, self.auto_reset = n_envs, device, auto_reset
@@ -27,8 +27,8 @@ class AssistiveVecEnv:
     def reset(self):
         obs = np.atleast_2d(self.env.reset())
         sim = self.env.id
-        self._step_dev = sim.feeding_step_dev if self.task == 'feeding' else sim.bathing_step_dev
-        self._step_host = sim.feeding_step_host if self.task == 'feeding' else sim.bathing_step_host
+        self._step_dev = {'feeding': sim.feeding_step_dev, 'bed_bathing': sim.bathing_step_dev, 'dressing': sim.dressing_step_dev}[self.task]
+        self._step_host = {'feeding': sim.feeding_step_host, 'bed_bathing': sim.bathing_step_host, 'dressing': sim.dressing_step_host}[self.task]
         self._t = 0
         return obs
 
@@ -72,3 +72,47 @@ class AssistiveVecEnv:
 
     def close(self):
         self.env.close()
+
+
+class AssistiveRLlibVectorEnv:
+    """The batched backend behind the interface RLlib's `VectorEnv` asks of a vectorised env (`vector_reset`, `reset_at`,
+    `vector_step`, `get_sub_environments`; reference learn.py:41,61-69 hands RLlib one `gym.Env` per worker -- with this
+    adapter one worker owns `n_envs` lock-step envs on its GPU).  RLlib itself is not a dependency: the class is duck-typed,
+    `ray.rllib.env.VectorEnv.register` / `to_base_env` accept it where RLlib is installed.
+
+    Episodes of all envs end together (200 steps, feeding.py:37): the first `reset_at` after the batch is done re-randomises
+    the whole batch, the following `reset_at(i)` calls of the same round read row i of that reset."""
+
+    def __init__(self, env_id='assistive_gym:FeedingJaco-v1', n_envs=64, device=0, seed=1001, config=None, _lib=None, **env_kw):
+        self.vec = AssistiveVecEnv(env_id, n_envs=n_envs, device=device, seed=seed, auto_reset=False, config=config, _lib=_lib, **env_kw)
+        self.num_envs = n_envs
+        self.observation_space, self.action_space = self.vec.observation_space, self.vec.action_space
+        self._obs = None
+        self._fresh = np.zeros(n_envs, dtype=bool)
+
+    def vector_reset(self):
+        self._obs = self.vec.reset()
+        self._fresh[:] = False
+        return [self._obs[i] for i in range(self.num_envs)]
+
+    def reset_at(self, index=None):
+        index = 0 if index is None else int(index)
+        if self._obs is None or self._fresh[index] or self.vec._t >= 200:
+            self._obs = self.vec.reset()
+            self._fresh[:] = False
+        self._fresh[index] = True
+        return self._obs[index]
+
+    def vector_step(self, actions):
+        obs, rew, done, info = self.vec.step(np.asarray(actions, dtype=np.float32).reshape(self.num_envs, -1))
+        self._obs = obs
+        self._fresh[:] = False
+        infos = [{k: (v[i].item() if hasattr(v[i], 'item') else v[i]) for k, v in info.items()} for i in range(self.num_envs)]
+        over = self.vec._t >= 200               # the env's own counter says the same (feeding.py:37); this one survives a replayed state
+        return [obs[i] for i in range(self.num_envs)], [float(r) for r in rew], [bool(d) or over for d in done], infos
+
+    def get_sub_environments(self):
+        return []        # there are no per-env Python objects: the sub-environments are lanes of one simulation
+
+    def try_render_at(self, index=None):
+        return None

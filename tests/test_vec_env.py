@@ -2,11 +2,11 @@
 import numpy as np
 import pytest
 
-from assistive_gym_b200.vec_env import AssistiveVecEnv
+from assistive_gym_b200.vec_env import AssistiveRLlibVectorEnv, AssistiveVecEnv
 
 
-def _check_host_path(lib, env_id, obs_dim):
-    v = AssistiveVecEnv(env_id, n_envs=3, seed=11, _lib=lib)
+def _check_host_path(lib, env_id, obs_dim, **kw):
+    v = AssistiveVecEnv(env_id, n_envs=3, seed=11, _lib=lib, **kw)
     obs = v.reset()
     assert obs.shape == (3, obs_dim)
     rng = np.random.default_rng(0)
@@ -27,6 +27,28 @@ def test_vec_env_host_path_feeding(emu_lib):
 
 def test_vec_env_host_path_bed_bathing(emu_lib):
     _check_host_path(emu_lib, 'assistive_gym:BedBathingSawyer-v1', 24)
+
+
+def test_vec_env_host_path_dressing(emu_lib):
+    _check_host_path(emu_lib, 'assistive_gym:DressingPR2-v1', 24, toc_attempts=6)
+
+
+def test_rllib_vector_env_interface(emu_lib):
+    """vector_reset / reset_at / vector_step / get_sub_environments as RLlib's VectorEnv drives them (learn.py:41)."""
+    v = AssistiveRLlibVectorEnv('assistive_gym:FeedingJaco-v1', n_envs=3, seed=5, _lib=emu_lib)
+    obs = v.vector_reset()
+    assert len(obs) == 3 and obs[0].shape == (25,) and v.num_envs == 3 and v.get_sub_environments() == []
+    o, r, d, infos = v.vector_step([v.action_space.sample() for _ in range(3)])
+    assert len(o) == 3 and isinstance(r[0], float) and d == [False] * 3 and set(infos[0]) == {'total_force_on_human', 'task_success'}
+    v.vec._t = 199
+    o, r, d, infos = v.vector_step(np.zeros((3, 7)))
+    assert d == [True] * 3
+    first = v.reset_at(0)                   # the batch resets once ...
+    assert v.vec._t == 0 and first.shape == (25,)
+    again = [v.reset_at(i) for i in (1, 2)]  # ... and the other envs of the round read their rows of the same reset
+    assert v.vec._t == 0 and all(a.shape == (25,) for a in again)
+    assert np.array_equal(v.reset_at(0), v._obs[0]) and v.vec._t == 0       # a second reset of env 0 starts a new round
+    v.vec.close()
 
 
 @pytest.mark.gpu
