@@ -193,7 +193,10 @@ AG_HDN inline void cloth_follow_body(int tid, const SimDev& S, const KP& p) {
 
 // ------------------------------------------------------------------ K8: the cloth kernel
 #if defined(__CUDACC__) && !defined(AG_CPU_EMU)
-template <int NPT>
+// QS: previous positions q (during a substep) / velocities v (between substeps) of a thread's own nodes live in a second
+// shared-memory array instead of registers (same arithmetic, bit-identical results; frees 6 NPT registers under the
+// 64-register limit of a 1024-thread CTA)
+template <int NPT, bool QS>
 __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
   extern __shared__ __align__(16) float cl_smem[];
   constexpr int T = AG_CLOTH_T;
@@ -203,20 +206,28 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
   float* pool = lk + 16 * AG_CLOTH_MAXCL;                      // [maxcc][12] n, offset | c3, c4, node, link | acc, -
   int* misc = (int*)(pool + 12 * C.maxcc);                     // [40] warp sums for the scan, total
   float* wbox = (float*)(misc + 40);                           // [32][6] per-warp bounding boxes of the predicted nodes
+  float4* qs = (float4*)(wbox + 192);                          // [NPT * T] (QS only)
   const int nn = C.nn;
   const size_t xb = (size_t)e * 3 * C.nnp;
-  f3 q[NPT], v[NPT];
+  f3 q[QS ? 1 : NPT], v[QS ? 1 : NPT];
+  auto getq = [&](int k, int i) -> f3 {
+    if constexpr (QS) { float4 t4 = qs[i]; (void)k; return f3(t4.x, t4.y, t4.z); }
+    else { f3 r(0.f, 0.f, 0.f); (void)i;
+#pragma unroll
+      for (int kk = 0; kk < NPT; kk++) if (kk == k) r = q[kk];
+      return r; }
+  };
   // ---- load
 #pragma unroll
   for (int k = 0; k < NPT; k++) {
     int i = k * T + t;
-    f3 xx(0.f, 0.f, 0.f); v[k] = f3(0.f, 0.f, 0.f);
+    f3 xx(0.f, 0.f, 0.f), vv(0.f, 0.f, 0.f);
     if (i < nn) {
       xx = f3(C.x[xb + i], C.x[xb + C.nnp + i], C.x[xb + 2 * (size_t)C.nnp + i]);
-      v[k] = f3(C.v[xb + i], C.v[xb + C.nnp + i], C.v[xb + 2 * (size_t)C.nnp + i]);
+      vv = f3(C.v[xb + i], C.v[xb + C.nnp + i], C.v[xb + 2 * (size_t)C.nnp + i]);
     }
     xs[i] = make_float4(xx.x, xx.y, xx.z, 0.f);
-    q[k] = xx;
+    if constexpr (QS) qs[i] = make_float4(vv.x, vv.y, vv.z, 0.f); else { q[k] = xx; v[k] = vv; }
   }
   const f3 ap = ld3(C.anchor_pos, 0, N, e);
   int total = 0;
@@ -227,10 +238,9 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
 #pragma unroll
     for (int k = 0; k < NPT; k++) {
       int i = k * T + t;
-      xn[k] = q[k];
+      xn[k] = f3(0.f, 0.f, 0.f);
       if (i < nn) {
         float4 me = xs[i]; f3 a(me.x, me.y, me.z);
-        q[k] = a;
         f3 ns(0.f, 0.f, 0.f);
         int f0 = __ldg(C.nf_off + i), f1 = __ldg(C.nf_off + i + 1);
         for (int f = f0; f < f1; f++) {
@@ -240,8 +250,10 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
         }
         float nl = norm(ns);
         if (nl > AG_CLOTH_EPS) ns = ns * (1.f / nl);
-        f3 xx = a;
-        cloth_predict(C, ns, __ldg(C.node_area + i), xx, v[k]);
+        f3 xx = a, vv;
+        if constexpr (QS) { float4 v4 = qs[i]; vv = f3(v4.x, v4.y, v4.z); } else vv = v[k];
+        cloth_predict(C, ns, __ldg(C.node_area + i), xx, vv);
+        if constexpr (QS) qs[i] = make_float4(a.x, a.y, a.z, 0.f); else { q[k] = a; v[k] = vv; }
         xn[k] = xx;
       }
     }
@@ -292,7 +304,7 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
             for (int a = 0; a < 9; a++) P.R.m[a] = o[a];
             P.pos = f3(o[9], o[10], o[11]); P.bc = f3(o[12], o[13], o[14]); P.br = o[15];
             ClothContact c;
-            if (cloth_detect(S, C, P, L, N, e, xn[k], q[k], c)) { if (nh < AG_CLOTH_HITS) hits[nh++] = (k << 8) | L; else over = true; }
+            if (cloth_detect(S, C, P, L, N, e, xn[k], getq(k, i), c)) { if (nh < AG_CLOTH_HITS) hits[nh++] = (k << 8) | L; else over = true; }
           }
         }
       }
@@ -322,9 +334,9 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
       ClothLinkPose P;
       for (int a = 0; a < 9; a++) P.R.m[a] = o[a];
       P.pos = f3(o[9], o[10], o[11]); P.bc = f3(o[12], o[13], o[14]); P.br = o[15];
-      f3 xk(0.f, 0.f, 0.f), qk(0.f, 0.f, 0.f);
+      f3 xk(0.f, 0.f, 0.f), qk = getq(k, k * T + t);
 #pragma unroll
-      for (int kk = 0; kk < NPT; kk++) if (kk == k) { xk = xn[kk]; qk = q[kk]; }
+      for (int kk = 0; kk < NPT; kk++) if (kk == k) xk = xn[kk];
       ClothContact c;
       cloth_detect(S, C, P, L, N, e, xk, qk, c);
       float* r = pool + 12 * slot;
@@ -339,9 +351,7 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
       for (int a = 0; a < C.nanch; a++) {
         int i = C.anch_node[a];
         if ((i & (T - 1)) == t) {
-          float4 me = xs[i]; f3 xx(me.x, me.y, me.z), qq(0.f, 0.f, 0.f);
-#pragma unroll
-          for (int kk = 0; kk < NPT; kk++) if (kk == i / T) qq = q[kk];
+          float4 me = xs[i]; f3 xx(me.x, me.y, me.z), qq = getq(i / T, i);
           cloth_anchor_solve(xx, qq, ap + f3(C.anch_local[a][0], C.anch_local[a][1], C.anch_local[a][2]), C.kAHR);
           xs[i] = make_float4(xx.x, xx.y, xx.z, 0.f);
         }
@@ -351,9 +361,7 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
         if (slot >= C.maxcc) break;
         int k = hits[h] >> 8, i = k * T + t;
         float* r = pool + 12 * slot;
-        float4 me = xs[i]; f3 xx(me.x, me.y, me.z), qq(0.f, 0.f, 0.f), acc(r[8], r[9], r[10]);
-#pragma unroll
-        for (int kk = 0; kk < NPT; kk++) if (kk == k) qq = q[kk];
+        float4 me = xs[i]; f3 xx(me.x, me.y, me.z), qq = getq(k, i), acc(r[8], r[9], r[10]);
         cloth_contact_solve(xx, qq, f3(r[0], r[1], r[2]), r[3], r[4], r[5], C.margin, acc);
         xs[i] = make_float4(xx.x, xx.y, xx.z, 0.f);
         r[8] = acc.x; r[9] = acc.y; r[10] = acc.z;
@@ -377,7 +385,10 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
 #pragma unroll
     for (int k = 0; k < NPT; k++) {
       int i = k * T + t;
-      if (i < nn) { float4 me = xs[i]; v[k] = (f3(me.x, me.y, me.z) - q[k]) * vc; }
+      if (i < nn) {
+        float4 me = xs[i]; f3 vv = (f3(me.x, me.y, me.z) - getq(k, i)) * vc;
+        if constexpr (QS) qs[i] = make_float4(vv.x, vv.y, vv.z, 0.f); else v[k] = vv;
+      }
     }
     // (the next substep's prediction reads xs, final since the last colour's barrier; the contact pool is rewritten only
     //  after that substep's first barrier, the link poses before it -- both were last read before the barrier above)
@@ -389,7 +400,9 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
     if (i < nn) {
       float4 me = xs[i];
       C.x[xb + i] = me.x; C.x[xb + C.nnp + i] = me.y; C.x[xb + 2 * (size_t)C.nnp + i] = me.z;
-      C.v[xb + i] = v[k].x; C.v[xb + C.nnp + i] = v[k].y; C.v[xb + 2 * (size_t)C.nnp + i] = v[k].z;
+      f3 vv;
+      if constexpr (QS) { float4 v4 = qs[i]; vv = f3(v4.x, v4.y, v4.z); } else vv = v[k];
+      C.v[xb + i] = vv.x; C.v[xb + C.nnp + i] = vv.y; C.v[xb + 2 * (size_t)C.nnp + i] = vv.z;
     }
   }
   // contacts of the last substep: node, position, force = accumulated correction / (im dt^2)

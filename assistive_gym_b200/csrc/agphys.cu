@@ -131,7 +131,7 @@ struct AgSim {
   float *d_action, *d_obs, *d_reward, *d_done, *d_info;
   float *h_pin_in, *h_pin_out;
   // cloth (Dressing): one k_cloth launch per stepSimulation = `C.K` rigid substeps
-  ClothDev C; ClothDev* C_dev; bool cloth; int cloth_sub, cloth_npt;
+  ClothDev C; ClothDev* C_dev; bool cloth; int cloth_sub, cloth_npt, cloth_qs;
   DressPost DP; DressPost* DP_dev; bool dressing;
   float *h_dpin_in, *h_dpin_out, *d_daction, *d_dobs, *d_dreward, *d_ddone, *d_dinfo;
   // CUDA-graph replay of the fused env step (one graph per entry point, keyed by its device pointers)
@@ -978,13 +978,18 @@ static int run_step(AgSim* s, int which, StepEnqueue enq, const float* action, f
 }
 
 // ------------------------------------------------------------------ cloth (K8, ag_cloth.cuh)
+static size_t cloth_smem_bytes(const AgSim* s) {
+  size_t f = (size_t)4 * s->cloth_npt * AG_CLOTH_T + 16 * AG_CLOTH_MAXCL + 12 * (size_t)s->C.maxcc + 40 + 192;
+  if (s->cloth_qs) f += (size_t)4 * s->cloth_npt * AG_CLOTH_T;
+  return f * sizeof(float);
+}
 static void cloth_launch(AgSim* s) {
 #ifndef AG_CPU_EMU
-  size_t smem = ((size_t)4 * s->cloth_npt * AG_CLOTH_T + 16 * AG_CLOTH_MAXCL + 12 * (size_t)s->C.maxcc + 40 + 192) * sizeof(float);
+  size_t smem = cloth_smem_bytes(s);
   int ps = s->profiling ? prof_slot(s, "k_cloth") : -1;
   if (ps >= 0) prof_mark(s, ps, true);
-  if (s->cloth_npt == 4) k_cloth<4><<<s->S.N, AG_CLOTH_T, smem, s->stream>>>(s->S, s->C);
-  else k_cloth<8><<<s->S.N, AG_CLOTH_T, smem, s->stream>>>(s->S, s->C);
+  if (s->cloth_npt == 4) { if (s->cloth_qs) k_cloth<4, true><<<s->S.N, AG_CLOTH_T, smem, s->stream>>>(s->S, s->C); else k_cloth<4, false><<<s->S.N, AG_CLOTH_T, smem, s->stream>>>(s->S, s->C); }
+  else { if (s->cloth_qs) k_cloth<8, true><<<s->S.N, AG_CLOTH_T, smem, s->stream>>>(s->S, s->C); else k_cloth<8, false><<<s->S.N, AG_CLOTH_T, smem, s->stream>>>(s->S, s->C); }
   if (ps >= 0) prof_mark(s, ps, false);
 #else
   for (int e = 0; e < s->S.N; e++) cloth_env_host(s->S, s->C, e);
@@ -1049,11 +1054,13 @@ int ag_cloth_init(AgSim* s, const AgClothDesc* d) {
   s->C_dev = dalloc<ClothDev>(s, 1);
   if (!C.cc_data || !C.overflow || !s->C_dev || !C.snap || !C.v) return fail("ag_cloth_init: device allocation failed");
   if (h2d(s, s->C_dev, &C, sizeof(ClothDev))) return -1;
+  { const char* qs = getenv("AG_CLOTH_QS"); s->cloth_qs = qs ? atoi(qs) != 0 : 1; }
+  if (s->cloth_npt == 8 && s->cloth_qs && (size_t)C.maxcc > 512) s->cloth_qs = 0;          // 2 x 128 KB of node arrays leave no room for a big pool
 #ifndef AG_CPU_EMU
-  size_t smem = ((size_t)4 * s->cloth_npt * AG_CLOTH_T + 16 * AG_CLOTH_MAXCL + 12 * (size_t)C.maxcc + 40 + 192) * sizeof(float);
+  size_t smem = cloth_smem_bytes(s);
   if (smem > 227 * 1024) return fail("ag_cloth_init: cloth + contact budget exceed 227 KB of shared memory");
-  if (s->cloth_npt == 4) CK(cudaFuncSetAttribute(k_cloth<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  else CK(cudaFuncSetAttribute(k_cloth<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (s->cloth_npt == 4) { CK(cudaFuncSetAttribute(k_cloth<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); CK(cudaFuncSetAttribute(k_cloth<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); }
+  else { CK(cudaFuncSetAttribute(k_cloth<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); CK(cudaFuncSetAttribute(k_cloth<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); }
 #endif
   drop_graph(s, 0); drop_graph(s, 1); drop_graph(s, 2);
   s->cloth = true; s->cloth_sub = 0;

@@ -144,3 +144,18 @@ def test_cloth_cuda_deterministic_and_batch_invariant(gpu_lib):
         outs.append(sims[0].cloth_get_state()[0])
     assert np.array_equal(outs[0], outs[1])
     assert np.array_equal(outs[0][:4], outs[2][:4])
+
+
+@pytest.mark.gpu
+def test_cloth_cuda_register_and_shared_memory_variants_agree(gpu_lib, monkeypatch):
+    """k_cloth<.., QS = false> keeps q / v of a thread's nodes in registers, QS = true in a second shared-memory array: the same
+    arithmetic in the same order, so the results must agree bit for bit."""
+    mp, mo = _makers(gpu_lib)
+    model = cc.grid_cloth()
+    outs = []
+    for qs in ('0', '1'):
+        monkeypatch.setenv('AG_CLOTH_QS', qs)
+        sims, _, _ = cc.make_pair(mp, mp, model, n=5, height=0.36, seed=7)
+        sims[0].step(6)
+        outs.append(sims[0].cloth_get_state())
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
