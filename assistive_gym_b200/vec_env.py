@@ -11,11 +11,21 @@ import numpy as np
 
 
 class AssistiveVecEnv:
-    def __init__(self, env_id='assistive_gym:FeedingJaco-v1', n_envs=4096, device=0, seed=1001, auto_reset=True, config=None, _lib=None, **env_kw):
+    def __init__(self, env_id='assistive_gym:FeedingJaco-v1', n_envs=4096, device=0, seed=1001, auto_reset=True, config=None, _lib=None,
+                 double_buffer=False, **env_kw):
+        """double_buffer: a second copy of the batch is re-randomised by a background thread (the C ABI releases the GIL; its
+        kernels run on that copy's own stream) while the first one is stepped; at the end of an episode the two swap, so
+        `step` never waits for the 0.5 s of reset orchestration (reference env.py:92-97 rebuilds the world at every reset)."""
         from . import envs
         self.env = envs.make(env_id, n_envs=n_envs, device=device, seed=seed, config=config, **env_kw)
         if _lib is not None:
             self.env._sim_lib = _lib
+        self._standby = None
+        if double_buffer:
+            self._standby = envs.make(env_id, n_envs=n_envs, device=device, seed=seed + 7919, config=config, **env_kw)
+            if _lib is not None:
+                self._standby._sim_lib = _lib
+        self._bg, self._bg_obs, self._bg_err = None, None, None
         self.n_envs, self.device, self.auto_reset = n_envs, device, auto_reset
         self.task = self.env.task
         self.observation_space, self.action_space = self.env.observation_space, self.env.action_space
@@ -24,8 +34,30 @@ class AssistiveVecEnv:
         self._buf = None
 
     # ------------------------------------------------------------------ gym-style API
+    def _reset_standby(self):
+        try:
+            self._bg_obs = np.atleast_2d(self._standby.reset())
+        except Exception as ex:          # surfaced by the next reset()
+            self._bg_err = ex
+
+    def _start_standby(self):
+        import threading
+        self._bg_obs, self._bg_err = None, None
+        self._bg = threading.Thread(target=self._reset_standby, daemon=True)
+        self._bg.start()
+
     def reset(self):
-        obs = np.atleast_2d(self.env.reset())
+        if self._standby is not None and self._bg is not None:
+            self._bg.join()
+            if self._bg_err is not None:
+                raise self._bg_err
+            self.env, self._standby = self._standby, self.env          # the freshly reset copy becomes the live one
+            obs = self._bg_obs
+            self._buf = None                                            # device tensors are bound to a sim's stream
+        else:
+            obs = np.atleast_2d(self.env.reset())
+        if self._standby is not None:
+            self._start_standby()
         sim = self.env.id
         self._step_dev = {'feeding': sim.feeding_step_dev, 'bed_bathing': sim.bathing_step_dev, 'dressing': sim.dressing_step_dev}[self.task]
         self._step_host = {'feeding': sim.feeding_step_host, 'bed_bathing': sim.bathing_step_host, 'dressing': sim.dressing_step_host}[self.task]
@@ -71,7 +103,11 @@ class AssistiveVecEnv:
         return out
 
     def close(self):
+        if self._bg is not None:
+            self._bg.join()
         self.env.close()
+        if self._standby is not None:
+            self._standby.close()
 
 
 class AssistiveRLlibVectorEnv:

@@ -33,6 +33,23 @@ def test_vec_env_host_path_dressing(emu_lib):
     _check_host_path(emu_lib, 'assistive_gym:DressingPR2-v1', 24, toc_attempts=6)
 
 
+def test_vec_env_double_buffered_reset(emu_lib):
+    """The standby copy is re-randomised in the background and swapped in at the end of the episode."""
+    v = AssistiveVecEnv('assistive_gym:FeedingJaco-v1', n_envs=3, seed=11, _lib=emu_lib, double_buffer=True)
+    o0 = v.reset()
+    first = v.env
+    rng = np.random.default_rng(0)
+    for _ in range(2):
+        o, r, d, info = v.step(rng.uniform(-1, 1, size=(3, 7)).astype(np.float32))
+    v._t = 199
+    o, r, d, info = v.step(np.zeros((3, 7), dtype=np.float32))
+    assert v.env is not first and v._standby is first and 'terminal_observation' in info
+    assert o.shape == (3, 25) and np.all(np.isfinite(o)) and not np.array_equal(o, o0)      # a different draw
+    o, r, d, info = v.step(np.zeros((3, 7), dtype=np.float32))
+    assert np.all(np.isfinite(o)) and np.all(np.isfinite(r))
+    v.close()
+
+
 def test_rllib_vector_env_interface(emu_lib):
     """vector_reset / reset_at / vector_step / get_sub_environments as RLlib's VectorEnv drives them (learn.py:41)."""
     v = AssistiveRLlibVectorEnv('assistive_gym:FeedingJaco-v1', n_envs=3, seed=5, _lib=emu_lib)
