@@ -169,7 +169,11 @@ AG_HD void cloth_link_solve(f3& a, f3& b, float rest2, float kLSTh) {
   f3 del = b - a;
   float len = dot(del, del);
   if (rest2 + len > AG_CLOTH_EPS) {
-    float s = (rest2 - len) / (rest2 + len) * kLSTh;
+#if defined(__CUDA_ARCH__)
+    float s = (rest2 - len) * kLSTh * __frcp_rn(rest2 + len);       // correctly rounded reciprocal: no IEEE-division slow path in the hot loop
+#else
+    float s = (rest2 - len) * kLSTh * (1.0f / (rest2 + len));
+#endif
     a -= del * s; b += del * s;
   }
 }
