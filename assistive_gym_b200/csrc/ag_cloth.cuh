@@ -30,6 +30,8 @@
 #define AG_CLOTH_EPS 1.1920929e-7f
 #define AG_CLOTH_CCF 8           // floats per exported contact: node, x, y, z, fx, fy, fz, link
 
+struct alignas(8) ClothLinkRec { unsigned ij; float rest2; };
+
 struct ClothDev {
   int nn, nnp, nlinks, ncol, nanch, ncl, maxcc, K, piters, export_contacts;
   float dt, im, kLSTh, kDP, kDG, kLF, kDF, kCHR, kKHR, kAHR, margin, density;
@@ -40,6 +42,7 @@ struct ClothDev {
   // template tables
   const unsigned* link_ij;     // [nlinks] node i | node j << 16, colour-major
   const float* link_rest2;     // [nlinks]
+  const struct ClothLinkRec* link_tab;   // [nlinks] the two above interleaved (one 8-byte load per link)
   const int* nf_off;           // [nn + 1]
   const unsigned* nf_pair;     // [nf] next | next-next << 16 (face winding)
   const float* node_area;      // [nn]
@@ -167,15 +170,14 @@ AG_HD void cloth_predict(const ClothDev& C, f3 nrm, float area, f3& x, f3& v) {
 // btSoftBody::PSolve_Links for one link, uniform node mass: c0 = 2 im / kLST, k im = (c1 - len) / (c1 + len) * kLST / 2
 AG_HD void cloth_link_solve(f3& a, f3& b, float rest2, float kLSTh) {
   f3 del = b - a;
-  float len = dot(del, del);
-  if (rest2 + len > AG_CLOTH_EPS) {
+  float len = dot(del, del), sum = rest2 + len;
 #if defined(__CUDA_ARCH__)
-    float s = (rest2 - len) * kLSTh * __frcp_rn(rest2 + len);       // correctly rounded reciprocal: no IEEE-division slow path in the hot loop
+  float s = (rest2 - len) * kLSTh * __frcp_rn(sum);                 // correctly rounded reciprocal: no IEEE-division slow path in the hot loop
 #else
-    float s = (rest2 - len) * kLSTh * (1.0f / (rest2 + len));
+  float s = (rest2 - len) * kLSTh * (1.0f / sum);
 #endif
-    a -= del * s; b += del * s;
-  }
+  s = sum > AG_CLOTH_EPS ? s : 0.f;                                 // Bullet skips degenerate links; a select keeps the loop branch-free
+  a -= del * s; b += del * s;
 }
 
 // ------------------------------------------------------------------ small per-lane kernels
@@ -373,8 +375,9 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
       __syncthreads();
       for (int col = 0; col < C.ncol; col++) {
         for (int l = C.col_off[col] + t; l < C.col_off[col + 1]; l += T) {
-          unsigned ij = __ldg(C.link_ij + l);
-          float r2 = __ldg(C.link_rest2 + l);
+          uint2 lt = __ldg((const uint2*)(C.link_tab + l));
+          unsigned ij = lt.x;
+          float r2 = __uint_as_float(lt.y);
           int i = ij & 0xffffu, j = ij >> 16;
           float4 a4 = xs[i], b4 = xs[j];
           f3 a(a4.x, a4.y, a4.z), b(b4.x, b4.y, b4.z);

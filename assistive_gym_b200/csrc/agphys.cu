@@ -1043,6 +1043,11 @@ int ag_cloth_init(AgSim* s, const AgClothDesc* d) {
   }
   for (int L = 0; L < d->n_col_links; L++) if (d->col_links[L] < 0 || d->col_links[L] >= s->nl) return fail("ag_cloth_init: bad collider link");
   C.link_ij = upload(s, lij); C.link_rest2 = upload(s, lr);
+  {
+    std::vector<ClothLinkRec> tab(d->n_links);
+    for (int l = 0; l < d->n_links; l++) { tab[l].ij = lij[l]; tab[l].rest2 = lr[l]; }
+    C.link_tab = upload(s, tab);
+  }
   C.nf_off = upload(s, std::vector<int>(d->nf_off, d->nf_off + nn + 1)); C.nf_pair = upload(s, nfp);
   C.node_area = upload(s, area);
   C.cl_link = upload(s, std::vector<int>(d->col_links, d->col_links + d->n_col_links)); C.cl_bs = upload(s, bs);
