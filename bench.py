@@ -207,12 +207,12 @@ def run_bedbathing(args):
     rng = np.random.default_rng(0)
     t0 = time.time()
     s = bb.reset(sim, rng, toc_attempts=args.toc_attempts)
-    ik_err = bb.hover_over_forearm(sim, s, rng)
+    ik_err = bb.hover_over_forearm(sim, s, rng, gap=-args.press_mm * 1e-3)      # the pad starts pressed into the forearm
     bb.start_fused(sim, s)
     reset_s = time.time() - t0
     stream = torch.cuda.ExternalStream(sim.stream_ptr())
     dev = torch.device('cuda')
-    act = torch.rand((K + W, n, 7), device=dev) * 2 - 1
+    act = (torch.rand((K + W, n, 7), device=dev) * 2 - 1) * args.action_scale
     obs = torch.zeros((n, 24), device=dev); rew = torch.zeros(n, device=dev); done = torch.zeros(n, device=dev); info = torch.zeros((n, 4), device=dev)
     torch.cuda.synchronize()
     for i in range(W):
@@ -231,7 +231,7 @@ def run_bedbathing(args):
     clk = clocks.stop()
     ms = a.elapsed_time(b) / K
     cnt, it = sim.solver_stats()
-    host_a = np.random.default_rng(1).uniform(-1, 1, size=(K, n, 7)).astype(np.float32)
+    host_a = (np.random.default_rng(1).uniform(-1, 1, size=(K, n, 7)) * args.action_scale).astype(np.float32)
     sim.bathing_step_host(host_a[0])
     t0 = time.perf_counter()
     for i in range(K):
@@ -240,7 +240,7 @@ def run_bedbathing(args):
     force = info[:, 2].cpu().numpy()
     print(json.dumps({'metric': 'env-steps/sec BedBathingSawyer-v1 @batch%d' % n, 'value': n / ms * 1e3, 'unit': 'env-steps/s', 'n_gpus': 1, 'steps': K, 'warmup': W,
                       'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                      'config': {'workload': 'BedBathingSawyer-v1, batch %d, fused step, wiping pad started 3 mm above the forearm, random actions' % n,
+                      'config': {'workload': 'BedBathingSawyer-v1, batch %d, fused step, wiping pad started pressed %.0f mm into the forearm, random actions x %.2f' % (n, args.press_mm, args.action_scale),
                                  'global_batch': n, 'l2': 'not flushed (back-to-back steps)', 'reset_s': reset_s,
                                  'ik_unresolved': int((ik_err >= 0.03).sum()),
                                  'contacts_per_env': {'mean': float(cnt.mean()), 'p99': float(np.percentile(cnt, 99)), 'max': int(cnt.max())},
@@ -397,6 +397,8 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--profile-kernels', type=int, default=1)
     ap.add_argument('--workload', default='feeding', choices=['feeding', 'bedbathing', 'dressing'], help="'bedbathing': BASELINE.json configs[2] (dense tool-skin contact), 'dressing': configs[3] (cloth); secondary lines")
+    ap.add_argument('--press-mm', type=float, default=5.0, help='bedbathing: start depth of the wiping pad in the forearm (SURVEY.md 8(d) C2: 5 mm)')
+    ap.add_argument('--action-scale', type=float, default=0.2, help='bedbathing: scale of the random actions (small actions keep the pad on the skin)')
     ap.add_argument('--toc-attempts', type=int, default=10, help='dressing / bedbathing: random base poses ranked per reset (the reference uses 50)')
     ap.add_argument('--sub-batches', type=int, default=int(os.environ.get('AG_SUB_BATCHES', '1')), help='independent sub-batches per GPU, each on its own stream')
     args = ap.parse_args()
