@@ -12,6 +12,13 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 
 
+def pytest_collection_modifyitems(config, items):
+    """The round's newest GPU paths (cloth, Dressing) run after the established ones, so that `-x` on a fresh box reports
+    the long-standing parity tests before anything that has had less time on the hardware."""
+    late = ('test_cloth_parity', 'test_dressing')
+    items.sort(key=lambda it: any(m in it.nodeid for m in late))       # stable: relative order is otherwise unchanged
+
+
 @pytest.fixture(scope='session')
 def feeding():
     from assistive_gym_b200.feeding_batch import FeedingBatch
