@@ -86,6 +86,7 @@ class AgDressingParams(C.Structure):
     _fields_ = [('robot_body', C.c_int32), ('human_body_m', C.c_int32), ('human_body_f', C.c_int32),
                 ('arm_links', C.c_int32 * 7), ('ee_link', C.c_int32),
                 ('arm_points_m', C.c_int32 * 3), ('arm_points_f', C.c_int32 * 3),
+                ('human_arm_m', C.c_int32 * 10), ('human_arm_f', C.c_int32 * 10),
                 ('arm_lower', C.c_float * 7), ('arm_upper', C.c_float * 7),
                 ('hand_radius_m', C.c_float), ('elbow_radius_m', C.c_float), ('shoulder_radius_m', C.c_float),
                 ('hand_radius_f', C.c_float), ('elbow_radius_f', C.c_float), ('shoulder_radius_f', C.c_float),
@@ -186,6 +187,7 @@ def load_library(path=None):
     lib.ag_set_motor_host.argtypes = [vp, ci, vp, ci, vp, vp, vp, vp]
     lib.ag_set_motor_targets_dev.argtypes = [vp, ci, vp, vp]
     lib.ag_set_motor_targets_host.argtypes = [vp, ci, vp, vp]
+    lib.ag_set_motor_force_scale.argtypes = [vp, ci, vp, vp]
     lib.ag_step.argtypes = [vp, ci]
     lib.ag_get_joint_states.argtypes = [vp, ci, vp, vp, vp, vp]
     lib.ag_get_link_states.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, vp]
@@ -213,6 +215,7 @@ def load_library(path=None):
     lib.ag_cloth_device_state.argtypes = [vp, vp, vp, vp]
     lib.ag_dressing_init.argtypes = [vp, C.POINTER(AgDressingParams), vp]
     lib.ag_dressing_reset_episode.argtypes = [vp, vp]
+    lib.ag_dressing_set_tremor.argtypes = [vp, vp, vp, vp]
     lib.ag_dressing_step_dev.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.ag_dressing_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.ag_ik_solve.argtypes = [vp, ci, vp, ci, vp, vp, ci, ci, C.c_float, C.c_uint64, vp, vp, vp]
@@ -242,6 +245,6 @@ EXPORTED_SYMBOLS = [
     'ag_closest_points', 'ag_feeding_init', 'ag_feeding_reset_episode', 'ag_feeding_set_tremor', 'ag_set_hard_limits', 'ag_feeding_step_dev', 'ag_ik_solve', 'ag_bathing_init', 'ag_bathing_step_dev', 'ag_bathing_step_host',
     'ag_feeding_step_host', 'ag_feeding_step_host_begin', 'ag_feeding_step_host_end', 'ag_state_size', 'ag_state_get', 'ag_state_set', 'ag_kernel_launches',
     'ag_cloth_init', 'ag_cloth_set_state', 'ag_cloth_get_state', 'ag_cloth_set_anchor', 'ag_cloth_anchor_follow', 'ag_cloth_set_gravity',
-    'ag_cloth_get_contacts', 'ag_cloth_device_state', 'ag_dressing_init', 'ag_dressing_reset_episode', 'ag_dressing_step_dev', 'ag_dressing_step_host',
+    'ag_cloth_get_contacts', 'ag_cloth_device_state', 'ag_dressing_init', 'ag_dressing_reset_episode', 'ag_dressing_set_tremor', 'ag_set_motor_force_scale', 'ag_dressing_step_dev', 'ag_dressing_step_host',
     'ag_overflow_count', 'ag_get_solver_stats', 'ag_get_pgs_cycles', 'ag_get_pgs_trips', 'ag_profile_enable', 'ag_profile_get',
 ]

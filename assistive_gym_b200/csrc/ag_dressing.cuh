@@ -12,6 +12,8 @@ struct DressDev {
   int *male, *iteration;
   float* task_success;            // [N] best reward_dressing so far (dressing.py:66-67)
   float* action;                  // [7][N]
+  int* tremor_on;                 // [N] the person's impairment is 'tremor' (human.py:80-92)
+  float *tremor_rest, *tremor_amp; // [10][N] target_joint_angles of the left arm joints and the tremor amplitudes
 };
 
 // action -> PD targets of the robot's 7 arm joints (env.py:187-217)
@@ -33,6 +35,13 @@ AG_HDN inline void dressing_pre_body(int e, const SimDev& S, const KP& p) {
       q += a;
     }
     st1(S.motor_target, k, N, e, q);
+  }
+  // a tremor human is an agent (env.py:130): its arm targets flip sign around the rest pose every env step (env.py:212-215)
+  if (D.tremor_on[e]) {
+    bool male = D.male[e] != 0;
+    float sgn = (D.iteration[e] % 2 == 0) ? 1.f : -1.f;
+    for (int j = 0; j < 10; j++)
+      st1(S.motor_target, male ? D.P.human_arm_m[j] : D.P.human_arm_f[j], N, e, D.tremor_rest[(size_t)j * N + e] + sgn * D.tremor_amp[(size_t)j * N + e]);
   }
 }
 

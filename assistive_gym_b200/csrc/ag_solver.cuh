@@ -232,6 +232,7 @@ AG_HD bool dof_row(const SimDev& S, int e, int kind, int d, DofRow& R) {
   } else {
     int mode = S.motor_mode[k];
     float maxi = S.motor_maxf[k] * dt;
+    if (S.motor_fscale) maxi *= ld1(S.motor_fscale, k, N, e);
     if (mode == 0 || !(maxi > 0.f)) return false;
     float vt = (mode == 1) ? (S.motor_kp[k] * (ld1(S.motor_target, k, N, e) - q) / dt + qd - S.motor_kd[k] * qd)
                            : ld1(S.motor_target, k, N, e);

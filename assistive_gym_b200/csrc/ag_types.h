@@ -51,6 +51,7 @@ struct SimDev {
   int* motor_mode; float *motor_kp, *motor_kd, *motor_maxf;
   int* hard_limit;                                     // [nl] clamp q to limits after integration (Human.enforce_joint_limits)
   float *motor_target, *motor_applied;       // [nl][N]
+  float* motor_fscale;                       // [nl][N] per-env scale of motor_maxf (Human.strength, human.py:86), or null
   // ---- per-env state
   float *base_pos, *base_quat, *base_lin, *base_ang;   // [nb][3|4][N]
   float *jq, *jqd;                                     // [nl][N]

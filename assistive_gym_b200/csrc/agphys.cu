@@ -149,6 +149,7 @@ struct AgSim {
 #define CKP(x) do { cudaError_t err__ = (x); if (err__ != cudaSuccess) { g_err = std::string(#x) + ": " + cudaGetErrorString(err__); return nullptr; } } while (0)
 #endif
 
+extern "C" { static void drop_graph(AgSim* s, int which); }
 static void* dev_alloc(AgSim* s, size_t bytes) {
   void* p = nullptr;
   if (bytes == 0) bytes = 16;
@@ -678,6 +679,18 @@ int ag_set_motor_host(AgSim* s, int n, const int32_t* links, int mode, const flo
   if (target) return scatter_host(s, s->S.motor_target, 1, n, links, target, nullptr);
   return 0;
 }
+int ag_set_motor_force_scale(AgSim* s, int n, const int32_t* links, const float* scale) {
+  DevGuard guard__(s->device);
+  if (!s->S.motor_fscale) {
+    const size_t cnt = (size_t)s->nl * s->S.N;
+    s->S.motor_fscale = dalloc<float>(s, cnt);
+    if (!s->S.motor_fscale) return fail("device allocation failed");
+    std::vector<float> ones(cnt, 1.0f);
+    if (h2d(s, s->S.motor_fscale, ones.data(), cnt * sizeof(float))) return -1;
+    for (int g = 0; g < 3; g++) drop_graph(s, g);        // captured kernels hold the SimDev of before (null pointer)
+  }
+  return scatter_host(s, s->S.motor_fscale, 1, n, links, scale, nullptr);
+}
 int ag_set_motor_targets_dev(AgSim* s, int n, const int32_t* links, const float* target_dev) {
   DevGuard guard__(s->device);
   if (n > 1024) return fail("too many items");
@@ -1176,6 +1189,7 @@ int ag_dressing_init(AgSim* s, const AgDressingParams* p, const int32_t* gender_
   drop_graph(s, 2);
   if (!s->dressing) {
     D.male = dalloc<int>(s, N); D.iteration = dalloc<int>(s, N); D.task_success = dalloc<float>(s, N); D.action = dalloc<float>(s, (size_t)N * 7);
+    D.tremor_on = dalloc<int>(s, N); D.tremor_rest = dalloc<float>(s, (size_t)N * 10); D.tremor_amp = dalloc<float>(s, (size_t)N * 10);
     s->d_daction = dalloc<float>(s, (size_t)N * 7); s->d_dobs = dalloc<float>(s, (size_t)N * 24);
     s->d_dreward = dalloc<float>(s, N); s->d_ddone = dalloc<float>(s, N); s->d_dinfo = dalloc<float>(s, (size_t)N * 4);
     s->DP_dev = dalloc<DressPost>(s, 1);
@@ -1187,11 +1201,25 @@ int ag_dressing_init(AgSim* s, const AgDressingParams* p, const int32_t* gender_
     s->h_dpin_in = (float*)malloc(sizeof(float) * N * 7); s->h_dpin_out = (float*)malloc(sizeof(float) * N * 30);
 #endif
   }
+  else if (dev_zero(s, D.tremor_on, sizeof(int) * N)) return -1;
+  for (int j = 0; j < 10; j++) if (p->human_arm_m[j] < 0 || p->human_arm_m[j] >= s->nl || p->human_arm_f[j] < 0 || p->human_arm_f[j] >= s->nl) return fail("ag_dressing_init: bad human arm link");
   s->DP.C = s->C_dev;
   if (h2d(s, D.male, gender_is_male, sizeof(int) * N)) return -1;
   if (h2d(s, s->DP_dev, &s->DP, sizeof(DressPost))) return -1;
   s->dressing = true;
   return ag_dressing_reset_episode(s, nullptr);
+}
+int ag_dressing_set_tremor(AgSim* s, const int32_t* on, const float* rest, const float* amplitude) {
+  DevGuard guard__(s->device);
+  if (!s->dressing) return fail("ag_dressing_init not called");
+  const int N = s->S.N;
+  std::vector<int> o(N, 0); std::vector<float> r((size_t)10 * N, 0.f), a((size_t)10 * N, 0.f);
+  if (on) for (int e = 0; e < N; e++) {
+    o[e] = on[e];
+    for (int j = 0; j < 10; j++) { r[(size_t)j * N + e] = rest ? rest[(size_t)e * 10 + j] : 0.f; a[(size_t)j * N + e] = amplitude ? amplitude[(size_t)e * 10 + j] : 0.f; }
+  }
+  if (h2d(s, s->DP.D.tremor_on, o.data(), sizeof(int) * N) || h2d(s, s->DP.D.tremor_rest, r.data(), sizeof(float) * 10 * N)) return -1;
+  return h2d(s, s->DP.D.tremor_amp, a.data(), sizeof(float) * 10 * N);
 }
 static int dressing_step_enqueue(AgSim* s, const float* action_dev, float* obs, float* reward, float* done, float* info) {
   const int N = s->S.N;

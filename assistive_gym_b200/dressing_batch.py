@@ -10,7 +10,10 @@ Differences forced by lock-step batching / the 32-DoF budget of one env (DESIGN.
   * both genders are instantiated, one is switched off per env;
   * of PR2's 44 non-fixed joints the left arm (7) and the left gripper (4) are simulated; every other joint is welded at
     the angle `reset_joints` gives it (the reference holds them with default velocity motors under zero gravity);
-  * the person's `weakness` / `tremor` impairments are not drawn (motor force limits are per joint, not per env).
+  * `impairment == 'limits'` scales the person's joint limits per env in the reference (human.py:85); joint limits are template
+    data here, so it is drawn but has no effect; `weakness` (per-env motor force scale) and `tremor` are simulated;
+  * a tremor person is clamped to its joint limits after every stepSimulation (env.py:226-229); the clamp flag is per joint,
+    not per env, so it is on for the arm joints of every env (the limit rows keep non-tremor arms inside anyway).
 """
 import numpy as np
 
@@ -115,6 +118,8 @@ class DressingBatch:
         P.ee_link = self.ee_link
         for i, l in enumerate((L_SHOULDER, L_ELBOW, L_WRIST)):
             P.arm_points_m[i] = self.gl(self.humans['male'], l); P.arm_points_f[i] = self.gl(self.humans['female'], l)
+        for i in range(10):
+            P.human_arm_m[i] = self.human_arm_links['male'][i]; P.human_arm_f[i] = self.human_arm_links['female'][i]
         P.hand_radius_m, P.elbow_radius_m, P.shoulder_radius_m = RADII['male']
         P.hand_radius_f, P.elbow_radius_f, P.shoulder_radius_f = RADII['female']
         for i in range(3):
@@ -126,9 +131,15 @@ class DressingBatch:
         return P
 
     # ------------------------------------------------------------------ batched reset
-    def sample(self, n, rng):
+    def sample(self, n, rng, impairment='random'):
+        """impairment: 'random' (human.py:80-81), 'no_tremor', or one of none / limits / weakness / tremor."""
+        names = ('none', 'limits', 'weakness', 'tremor')
+        imp = rng.integers(0, 4, size=n) if impairment == 'random' else (rng.integers(0, 3, size=n) if impairment == 'no_tremor' else np.full(n, names.index(impairment)))
         return dict(plane_friction=rng.uniform(0.025, 0.5, size=n),                  # env.py:120
                     male=rng.integers(0, 2, size=n).astype(np.int32),                # human.py:76-77
+                    impairment=imp.astype(np.int32),
+                    strength=np.where(imp == 2, rng.uniform(0.25, 1.0, size=n), 1.0),                                       # human.py:86
+                    tremors=np.where((imp == 3)[:, None], rng.uniform(np.deg2rad(-10), np.deg2rad(10), size=(n, 10)), 0.0),   # human.py:92
                     ee_offset=rng.uniform(-0.05, 0.05, size=(n, 3)))                 # dressing.py:129
 
     def human_pose(self):
@@ -166,6 +177,9 @@ class DressingBatch:
             al = self.human_arm_links[g]
             tgt = np.tile(q[LEFT_ARM_JOINTS], (n, 1))
             sim.set_motor(al, MOTOR_POSITION, target=tgt, kp=[0.01] * 10, kd=[1.0] * 10, max_force=[1.0] * 10)
+            sim.set_motor_force_scale(al, np.repeat(s.get('strength', np.ones(n))[:, None], 10, axis=1))                    # forces = 1 * strength (human.py:126)
+            sim.set_hard_limits(al, True)
+        self.human_rest = np.tile(self.human_pose()['male'][1][LEFT_ARM_JOINTS], (n, 1))      # target_joint_angles (human.py:122); the presets are the same for both genders
         sim.forward_kinematics()
         limb = np.zeros((n, 3, 3))
         for g, hb in self.humans.items():
@@ -223,3 +237,6 @@ class DressingBatch:
     def start_fused(self, sim, sample=None):
         s = sample or self.last_sample
         sim.dressing_init(self.dressing_params(), s['male'])
+        imp = s.get('impairment')
+        if imp is not None and np.any(imp == 3):
+            sim.dressing_set_tremor((imp == 3).astype(np.int32), self.human_rest, s['tremors'])

@@ -89,6 +89,10 @@ class BatchSim:
         mf = _f32(max_force, (n,)) if max_force is not None else None
         self._ck(self.lib.ag_set_motor_host(self.h, n, _p(links), int(mode), _p(target), _p(kp), _p(kd), _p(mf)))
 
+    def set_motor_force_scale(self, links, scale):
+        links = _i32(links)
+        self._ck(self.lib.ag_set_motor_force_scale(self.h, len(links), _p(links), _p(_f32(scale, (self.n, len(links))))))
+
     def set_motor_targets(self, links, target):
         links = _i32(links)
         t = _f32(target, (self.n, len(links)))
@@ -270,6 +274,9 @@ class BatchSim:
     def dressing_init(self, params, gender_is_male):
         self._dress_params = params
         self._ck(self.lib.ag_dressing_init(self.h, C.byref(params), _p(_i32(gender_is_male))))
+
+    def dressing_set_tremor(self, on, rest, amplitude):
+        self._ck(self.lib.ag_dressing_set_tremor(self.h, _p(_i32(on)), _p(_f32(rest, (self.n, 10))), _p(_f32(amplitude, (self.n, 10)))))
 
     def dressing_reset_episode(self, mask=None):
         self._ck(self.lib.ag_dressing_reset_episode(self.h, _p(_i32(mask))))

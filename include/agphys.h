@@ -158,6 +158,8 @@ int ag_set_motor_host(AgSim* sim, int n, const int32_t* links, int mode, const f
                       const float* kp, const float* kd, const float* max_force);
 int ag_set_motor_targets_dev(AgSim* sim, int n, const int32_t* links, const float* target_dev);
 int ag_set_motor_targets_host(AgSim* sim, int n, const int32_t* links, const float* target);
+/* per-env scale [N][n] of the joints' max_force (Human.strength, human.py:86,126: `forces = reactive_force * strength`) */
+int ag_set_motor_force_scale(AgSim* sim, int n, const int32_t* links, const float* scale);
 
 /* --- the hot path: p.stepSimulation (env.py:226; feeding.py:179) ----------------------------- */
 int ag_step(AgSim* sim, int n_steps);
@@ -288,6 +290,7 @@ typedef struct AgDressingParams {
   int32_t arm_links[7];         /* controllable joints (global link ids): PR2 left arm */
   int32_t ee_link;              /* left_end_effector */
   int32_t arm_points_m[3], arm_points_f[3];   /* left shoulder, elbow, wrist links (global ids) */
+  int32_t human_arm_m[10], human_arm_f[10];   /* the person's controllable joints (human.left_arm_joints, dressing_envs.py:13) */
   float   arm_lower[7], arm_upper[7];
   float   hand_radius_m, elbow_radius_m, shoulder_radius_m, hand_radius_f, elbow_radius_f, shoulder_radius_f; /* human_creation.py:89,140 */
   int32_t tri1[3], tri2[3];     /* sleeve-opening nodes (dressing.py:149-150), cloth-internal ids */
@@ -299,6 +302,9 @@ typedef struct AgDressingParams {
 } AgDressingParams;
 int ag_dressing_init(AgSim* sim, const AgDressingParams* p, const int32_t* gender_is_male);
 int ag_dressing_reset_episode(AgSim* sim, const int32_t* env_mask);
+/* tremor impairment of the person (human.py:80-92, env.py:212-215): per env on/off, rest angles [N][10] and amplitudes [N][10] of
+ * the left arm joints; targets flip sign every env step.  NULL `on` switches tremor off. */
+int ag_dressing_set_tremor(AgSim* sim, const int32_t* on, const float* rest, const float* amplitude);
 /* obs [N][24], reward [N], done [N], info [N][4] = total force on the person, task success, reward_dressing, sleeve state */
 int ag_dressing_step_dev(AgSim* sim, const float* action_dev, float* obs_dev, float* reward_dev, float* done_dev, float* info_dev);
 int ag_dressing_step_host(AgSim* sim, const float* action, float* obs, float* reward, float* done, float* info);

@@ -73,7 +73,7 @@ struct Env {
   std::vector<Quat> base_quat;
   std::vector<real> q, qd;                        // per link
   std::vector<int> motor_mode, hard_limit;
-  std::vector<real> motor_target, motor_kp, motor_kd, motor_maxf, motor_applied;
+  std::vector<real> motor_target, motor_kp, motor_kd, motor_maxf, motor_applied, motor_fscale;
   std::vector<real> friction;                     // per link
   std::vector<int> body_mode;                     // 0 inactive, 1 normal, 2 frozen
   // derived
@@ -633,7 +633,7 @@ void step_env(const Scene& s, const AgConfig& cfg, Env& e, const OCloth* cloth =
     for (int k = 0; k < s.nl; k++) {     // joint motors
       e.motor_applied[k] = 0;
       if (!s.link_live[k] || e.motor_mode[k] == AG_MOTOR_OFF || so.body_off[s.link_body[k]] < 0) continue;
-      real maxi = e.motor_maxf[k] * dt;
+      real maxi = e.motor_maxf[k] * dt * e.motor_fscale[k];       // Human.strength scales the force limit (human.py:86,126)
       if (maxi <= 0) continue;
       Row r; int b = s.link_body[k];
       r.off[0] = so.body_off[b]; r.n[0] = s.body_ndof[b]; r.off[1] = 0; r.n[1] = 0;
@@ -813,7 +813,7 @@ void init_env(const Scene& s, Env& e) {
   e.q.assign(s.nl, 0); e.qd.assign(s.nl, 0);
   e.motor_mode.assign(s.nl, AG_MOTOR_OFF); e.hard_limit.assign(s.nl, 0);
   e.motor_target.assign(s.nl, 0); e.motor_kp.assign(s.nl, 0); e.motor_kd.assign(s.nl, 0);
-  e.motor_maxf.assign(s.nl, 0); e.motor_applied.assign(s.nl, 0);
+  e.motor_maxf.assign(s.nl, 0); e.motor_applied.assign(s.nl, 0); e.motor_fscale.assign(s.nl, 1);
   e.friction = s.link_friction;
   e.body_mode.assign(s.nb, 1);
   e.lpos.assign(s.nl, V3()); e.lquat.assign(s.nl, Quat());
@@ -901,6 +901,11 @@ int oracle_set_motor(void* h, int n, const int32_t* links, int mode, const doubl
     if (kd) e.motor_kd[k] = (real)kd[j];
     if (maxf) e.motor_maxf[k] = (real)maxf[j];
   }
+  return 0;
+}
+int oracle_set_motor_force_scale(void* h, int n, const int32_t* links, const double* scale) {
+  Sim* s = (Sim*)h;
+  for (int i = 0; i < s->N; i++) for (int j = 0; j < n; j++) s->envs[i].motor_fscale[links[j]] = (real)scale[i * n + j];
   return 0;
 }
 int oracle_set_motor_targets(void* h, int n, const int32_t* links, const double* target) {

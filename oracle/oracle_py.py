@@ -46,6 +46,7 @@ def _load(f32=False):
     lib.oracle_set_motor.argtypes = [vp, ci, vp, ci, vp, vp, vp, vp]
     lib.oracle_set_hard_limits.argtypes = [vp, ci, vp, ci]
     lib.oracle_set_motor_targets.argtypes = [vp, ci, vp, vp]
+    lib.oracle_set_motor_force_scale.argtypes = [vp, ci, vp, vp]
     lib.oracle_forward_kinematics.argtypes = [vp]
     lib.oracle_step.argtypes = [vp, ci, ci]
     lib.oracle_get_joint_states.argtypes = [vp, ci, vp, vp, vp, vp]
@@ -153,6 +154,10 @@ class OracleSim:
     def set_hard_limits(self, links, on=True):
         links = _i32(links)
         self.lib.oracle_set_hard_limits(self.h, len(links), _p(links), int(bool(on)))
+
+    def set_motor_force_scale(self, links, scale):
+        links = _i32(links)
+        self.lib.oracle_set_motor_force_scale(self.h, len(links), _p(links), _p(_f64(scale, (self.n, len(links)))))
 
     def set_motor_targets(self, links, target):
         links = _i32(links)

@@ -43,10 +43,13 @@ def sleeve_on_arm_reward(t1, t2, shoulder, elbow, wrist, hand_r, elbow_r, should
 class DressingReference:
     """DressingEnv.step (dressing.py:12-77) on a per-call simulation API (the CPU oracle), batched over envs."""
 
-    def __init__(self, db, sim, male):
+    def __init__(self, db, sim, male, sample=None):
         self.db, self.sim, self.male = db, sim, np.asarray(male).astype(bool)
         self.iteration = 0
         self.task_success = np.zeros(sim.n)
+        imp = None if sample is None else sample.get('impairment')
+        self.tremor_on = np.zeros(sim.n, dtype=bool) if imp is None else (imp == 3)
+        self.tremors = np.zeros((sim.n, 10)) if sample is None or 'tremors' not in sample else sample['tremors']
 
     def step(self, action):
         db, sim, n = self.db, self.sim, self.sim.n
@@ -60,6 +63,16 @@ class DressingReference:
             q = np.where(below, db.arm_lower, q); q = np.where(above, db.arm_upper, q)
             q = q + act
         sim.set_motor_targets(db.arm_links, q)
+        if self.tremor_on.any():                                          # env.py:212-215: the tremor human's targets flip every env step
+            sgn = 1.0 if self.iteration % 2 == 0 else -1.0
+            for g, hb in db.humans.items():
+                sel = self.tremor_on & (self.male if g == 'male' else ~self.male)
+                al = db.human_arm_links[g]
+                cur = db.human_rest.copy()
+                tgt = np.where(sel[:, None], db.human_rest + sgn * self.tremors, cur)
+                if sel.any():
+                    # envs of the other gender / without tremor keep their rest targets (set at reset)
+                    sim.set_motor_targets(al, tgt)
         for _ in range(5):                                                # env.py:223-231 + dressing.py:200-210
             sim.step(1)
             sim.cloth_anchor_follow(db.ee_link)

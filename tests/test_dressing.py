@@ -37,7 +37,11 @@ def _pair(lib, db, n, attempts=12, settle=3, seed=0):
     cfg = capi.default_config(num_substeps=8)
     prod = BatchSim(db.scene, cfg, n, _lib=lib)
     rng = np.random.default_rng(seed)
-    smp = db.reset(prod, rng, attempts=attempts, settle_steps=0)
+    smp = db.sample(n, rng)
+    smp['impairment'][:] = np.arange(n) % 4                     # none, limits, weakness, tremor: every branch is exercised
+    smp['strength'] = np.where(smp['impairment'] == 2, 0.4, 1.0)
+    smp['tremors'] = np.where((smp['impairment'] == 3)[:, None], np.deg2rad(8.0) * np.sign(rng.uniform(-1, 1, size=(n, 10))), 0.0)
+    smp = db.reset(prod, rng, sample=smp, attempts=attempts, settle_steps=0)
     assert db.unresolved == 0 and np.all(db.goals_reached >= 1)
     orc = OracleSim(db.scene, cfg, n, threads=4)
     db.reset(orc, np.random.default_rng(seed), sample=smp, settle_steps=0)
@@ -48,7 +52,7 @@ def _pair(lib, db, n, attempts=12, settle=3, seed=0):
     return prod, orc, smp
 
 
-def _fused_step_vs_reference(lib, n=3, steps=2):
+def _fused_step_vs_reference(lib, n=4, steps=2):
     db = DressingBatch()
     prod, orc, smp = _pair(lib, db, n)
     # same state on both sides before the compared steps
@@ -56,7 +60,7 @@ def _fused_step_vs_reference(lib, n=3, steps=2):
     prod.cloth_set_state(xo, vo)
     prod.state_set(orc.state_get().astype(np.float32))
     db.start_fused(prod, smp)
-    ref = DressingReference(db, orc, smp['male'])
+    ref = DressingReference(db, orc, smp['male'], smp)
     rng = np.random.default_rng(5)
     for it in range(steps):
         a = rng.uniform(-1, 1, size=(n, 7))

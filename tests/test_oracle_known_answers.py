@@ -104,6 +104,14 @@ def test_motor_position_control_converges_and_respects_max_force():
     sim2.set_motor([1], 1, target=[[1.2]], kp=[0.1], kd=[1.0], max_force=[1.0])
     sim2.step(1)
     assert abs(abs(sim2.get_joint_states([1])[2][0, 0]) - 1.0) < 1e-9
+    # Human.strength (human.py:86,126): a per-env scale of the force limit
+    sim3 = OracleSim(sc, capi.default_config(linear_damping=0, angular_damping=0), 2)
+    sim3.set_joint_state([1], q=[[1.2], [1.2]])
+    sim3.set_motor([1], 1, target=[[1.2], [1.2]], kp=[0.1], kd=[1.0], max_force=[1.0])
+    sim3.set_motor_force_scale([1], [[1.0], [0.25]])
+    sim3.step(1)
+    tau = np.abs(sim3.get_joint_states([1])[2][:, 0])
+    assert abs(tau[0] - 1.0) < 1e-9 and abs(tau[1] - 0.25) < 1e-9
 
 
 def test_joint_limit_stops_motion():
