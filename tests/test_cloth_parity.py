@@ -117,7 +117,32 @@ def _gown_case(lib):
     assert P.overflow_count() == 0
 
 
-CASES = [_free_running_no_contact, _resynchronised_with_contacts, _single_substep_strict, _gown_case]
+def _golden_fixture(lib, oracle_side=False):
+    """tests/golden/cloth_gown_1step.npz (oracle-generated, committed): one stepSimulation of the gown from a stored state."""
+    import os
+    from tests.golden.make_golden_cloth import setup
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'cloth_gown_1step.npz'))
+    model = ClothModel.load()
+    scene, links, static, arm_joint = cc.obstacle_scene()
+    cfg = capi.default_config(num_substeps=8)
+    sim = OracleSim(scene, cfg, 1) if oracle_side else BatchSim(scene, cfg, 1, _lib=lib)
+    setup(sim, model, z['x_before'].astype(np.float64), z['v_before'].astype(np.float64), arm_joint, links, static)
+    sim.state_set(z['rigid_before'] if oracle_side else z['rigid_before'].astype(np.float32))
+    sim.forward_kinematics()
+    sim.step(1)
+    x, v = sim.cloth_get_state()
+    err = np.abs(x - z['x_after']).max(axis=2)
+    # the stored start state is fp32: the oracle reproduces its own fixture to rounding, the product to the parity tolerance
+    assert np.median(err) < 2e-6 and (err > 1e-4).mean() < 0.02 and err.max() < 5e-3, (np.median(err), (err > 1e-4).mean(), err.max())
+    cnt = sim.cloth_get_contacts(4096)[0]
+    assert abs(int(cnt[0]) - int(z['contact_count'][0])) <= 12
+
+
+def test_cloth_oracle_reproduces_golden_fixture():
+    _golden_fixture(None, oracle_side=True)
+
+
+CASES = [_free_running_no_contact, _resynchronised_with_contacts, _single_substep_strict, _gown_case, _golden_fixture]
 
 
 @pytest.mark.parametrize('case', CASES, ids=[c.__name__.strip('_') for c in CASES])
