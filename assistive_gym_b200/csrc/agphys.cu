@@ -16,6 +16,7 @@
 #include "ag_ik.cuh"
 #include "ag_cloth.cuh"
 #include "ag_dressing.cuh"
+#include "ag_render.cuh"
 
 #ifndef AG_CPU_EMU
 #include <cuda_runtime.h>
@@ -106,6 +107,7 @@ AG_KERNEL(k_bath_dist, bathing_dist_body)
 AG_KERNEL(k_bath_post, bathing_post_body)
 AG_KERNEL(k_dress_pre, dressing_pre_body)
 AG_KERNEL(k_dress_post, dressing_post_body)
+AG_KERNEL(k_render, render_body)
 AG_KERNEL(k_cloth_snap, cloth_snap_body)
 AG_KERNEL(k_cloth_follow, cloth_follow_body)
 
@@ -133,6 +135,7 @@ struct AgSim {
   // cloth (Dressing): one k_cloth launch per stepSimulation = `C.K` rigid substeps
   ClothDev C; ClothDev* C_dev; bool cloth; int cloth_sub, cloth_npt, cloth_qs;
   DressPost DP; DressPost* DP_dev; bool dressing;
+  size_t render_pix; int render_n; int* d_render_ids; unsigned char* d_render_rgba; float* d_render_depth; void* d_render_dev;
   float *h_dpin_in, *h_dpin_out, *d_daction, *d_dobs, *d_dreward, *d_ddone, *d_dinfo;
   // CUDA-graph replay of the fused env step (one graph per entry point, keyed by its device pointers)
   bool use_graph; int graph_failures;
@@ -291,7 +294,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   AgSim* s = new AgSim();
   memset(&s->S, 0, sizeof(SimDev));
   memset(&s->F, 0, sizeof(FeedDev));
-  s->cfg = *cfg; s->device = device; s->launches = 0; s->feeding = false; s->bathing = false; s->cloth = false; s->cloth_sub = 0; s->C_dev = nullptr; s->dressing = false; s->DP_dev = nullptr; s->graphs[2].valid = false; s->use_graph = true; s->graph_failures = 0; s->graphs[0].valid = s->graphs[1].valid = false; s->B_dev = nullptr; s->stream = nullptr; s->F_dev = nullptr; s->profiling = false;
+  s->cfg = *cfg; s->device = device; s->launches = 0; s->feeding = false; s->bathing = false; s->cloth = false; s->cloth_sub = 0; s->C_dev = nullptr; s->dressing = false; s->DP_dev = nullptr; s->render_pix = 0; s->render_n = 0; s->d_render_ids = nullptr; s->d_render_rgba = nullptr; s->d_render_depth = nullptr; s->d_render_dev = nullptr; s->graphs[2].valid = false; s->use_graph = true; s->graph_failures = 0; s->graphs[0].valid = s->graphs[1].valid = false; s->B_dev = nullptr; s->stream = nullptr; s->F_dev = nullptr; s->profiling = false;
   s->d_stage = nullptr; s->stage_floats = 0;
 #ifndef AG_CPU_EMU
   { int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { g_err = "no such CUDA device (is a CUDA device present? there is no CPU fallback)"; delete s; return nullptr; } }
@@ -1271,6 +1274,42 @@ int ag_dressing_step_host(AgSim* s, const float* action, float* obs, float* rewa
 #endif
   memcpy(obs, o, sizeof(float) * N * 24); memcpy(reward, o + (size_t)N * 24, sizeof(float) * N);
   memcpy(done, o + (size_t)N * 25, sizeof(float) * N); memcpy(info, o + (size_t)N * 26, sizeof(float) * N * 4);
+  return 0;
+}
+
+// ------------------------------------------------------------------ camera images (K9, ag_render.cuh)
+int ag_render(AgSim* s, const AgCamera* cam, int n, const int32_t* env_ids, uint8_t* rgba, float* depth) {
+  DevGuard guard__(s->device);
+  if (!cam || n <= 0 || !env_ids || !rgba) return fail("ag_render: bad arguments");
+  if (cam->width <= 0 || cam->height <= 0 || cam->width * (long long)cam->height * n > (1ll << 30)) return fail("ag_render: bad image size");
+  for (int i = 0; i < n; i++) if (env_ids[i] < 0 || env_ids[i] >= s->S.N) return fail("ag_render: bad env id");
+  // link poses and link AABBs of the current state (all bodies)
+  run_fk_all(s);
+  RenderDev R; memset(&R, 0, sizeof(R));
+  R.cam = *cam;
+  f3 eye(cam->eye[0], cam->eye[1], cam->eye[2]), tgt(cam->target[0], cam->target[1], cam->target[2]), upv(cam->up[0], cam->up[1], cam->up[2]);
+  f3 f = tgt - eye; float fl = norm(f); if (!(fl > 0.f)) return fail("ag_render: eye == target");
+  f = f * (1.f / fl);
+  f3 r = cross(f, upv); float rl = norm(r); if (!(rl > 0.f)) return fail("ag_render: up is parallel to the view direction");
+  r = r * (1.f / rl);
+  R.fwd = f; R.right = r; R.up = cross(r, f);
+  R.tan_half = tanf(0.5f * cam->fov_deg * 3.14159265358979323846f / 180.f);
+  const size_t npix = (size_t)cam->width * cam->height * n;
+  if (npix > s->render_pix || n > s->render_n) {            // grow-only scratch (an episode renders a frame per step)
+    s->render_pix = std::max(npix, s->render_pix); s->render_n = std::max(n, s->render_n);
+    s->d_render_ids = dalloc<int>(s, s->render_n); s->d_render_rgba = (unsigned char*)dev_alloc(s, s->render_pix * 4);
+    s->d_render_depth = dalloc<float>(s, s->render_pix);
+    if (!s->d_render_dev) s->d_render_dev = dev_alloc(s, sizeof(RenderDev));
+  }
+  int* d_ids = s->d_render_ids; unsigned char* d_rgba = s->d_render_rgba; float* d_depth = s->d_render_depth;
+  RenderDev* d_R = (RenderDev*)s->d_render_dev;
+  if (!d_ids || !d_rgba || !d_depth || !d_R) return fail("device allocation failed");
+  R.env_ids = d_ids; R.rgba = d_rgba; R.depth = d_depth;
+  if (h2d(s, d_ids, env_ids, sizeof(int) * n) || h2d(s, d_R, &R, sizeof(RenderDev))) return -1;
+  KP p = kp0(); p.p0 = d_R;
+  LAUNCH(s, k_render, npix, p);
+  if (d2h(s, rgba, d_rgba, npix * 4)) return -1;
+  if (depth && d2h(s, depth, d_depth, npix * sizeof(float))) return -1;
   return 0;
 }
 

@@ -109,7 +109,34 @@ class AssistiveEnv(gym.Env):
         self.disconnect()
 
     def render(self, mode='human'):
-        return None            # GUI / camera calls are no-ops on this backend
+        """There is no GUI on this backend (env.py:318-340 opens PyBullet's viewer); with mode='rgb_array' the first env's camera
+        image is returned (the collision geometry, ray-cast on the device)."""
+        if mode != 'rgb_array' or self.id is None:
+            return None
+        if getattr(self, 'view', None) is None:
+            self.setup_camera()
+        return self.get_camera_image_depth()[0]
+
+    def setup_camera(self, camera_eye=(0.5, -0.75, 1.5), camera_target=(-0.2, 0, 0.75), fov=60, camera_width=1920 // 4, camera_height=1080 // 4):
+        """env.py:342-346"""
+        self.camera_width, self.camera_height = camera_width, camera_height
+        self.view = dict(eye=tuple(camera_eye), target=tuple(camera_target), fov=float(fov))
+
+    def setup_camera_rpy(self, camera_target=(-0.2, 0, 0.75), distance=1.5, rpy=(0, -35, 40), fov=60, camera_width=1920 // 4, camera_height=1080 // 4):
+        """env.py:348-352 (computeViewMatrixFromYawPitchRoll, up axis z; convention recalled: the eye starts `distance` behind the
+        target on -y, is pitched about x and yawed about z; roll is ignored)"""
+        pitch, yaw = np.deg2rad(rpy[1]), np.deg2rad(rpy[2])
+        off = np.array([0.0, -distance * np.cos(pitch), -distance * np.sin(pitch)])
+        off = np.array([np.cos(yaw) * off[0] - np.sin(yaw) * off[1], np.sin(yaw) * off[0] + np.cos(yaw) * off[1], off[2]])
+        self.setup_camera(tuple(np.asarray(camera_target) + off), camera_target, fov, camera_width, camera_height)
+
+    def get_camera_image_depth(self, light_pos=(0, -3, 1), shadow=False, ambient=0.8, diffuse=0.3, specular=0.1, env_ids=None):
+        """env.py:354-359: (h, w, 4) uint8 image and (h, w) depth buffer; with `env_ids` a leading axis over the requested envs."""
+        assert getattr(self, 'view', None) is not None, 'You must call env.setup_camera() or env.setup_camera_rpy() before getting a camera image'
+        ids = [0] if env_ids is None else list(env_ids)
+        img, depth = self.id.render(self.view['eye'], self.view['target'], fov=self.view['fov'], width=self.camera_width, height=self.camera_height,
+                                    env_ids=ids, light_dir=light_pos, ambient=ambient, diffuse=diffuse)
+        return (img[0], depth[0]) if env_ids is None else (img, depth)
 
     def reset(self):
         self.agents = []

@@ -270,6 +270,17 @@ class BatchSim:
         self._ck(self.lib.ag_cloth_get_contacts(self.h, max_pts, _p(cnt), _p(node), _p(pos), _p(force), _p(link)))
         return cnt, self.cloth_model.order[node], pos, force, link
 
+    # ---- camera images (ag_render)
+    def render(self, eye, target, fov=60.0, width=480, height=270, env_ids=(0,), up=(0, 0, 1), near=0.01, far=100.0,
+               light_dir=(0, -3, 1), ambient=0.8, diffuse=0.3):
+        cam = capi.AgCamera(eye=(C.c_float * 3)(*eye), target=(C.c_float * 3)(*target), up=(C.c_float * 3)(*up), fov_deg=fov, aspect=width / height,
+                            near_=near, far_=far, width=width, height=height, light_dir=(C.c_float * 3)(*light_dir), ambient=ambient, diffuse=diffuse)
+        ids = _i32(list(env_ids))
+        rgba = np.zeros((len(ids), height, width, 4), dtype=np.uint8)
+        depth = np.zeros((len(ids), height, width), dtype=np.float32)
+        self._ck(self.lib.ag_render(self.h, C.byref(cam), len(ids), _p(ids), _p(rgba), _p(depth)))
+        return rgba, depth
+
     # ---- fused dressing path
     def dressing_init(self, params, gender_is_male):
         self._dress_params = params

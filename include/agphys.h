@@ -309,6 +309,19 @@ int ag_dressing_set_tremor(AgSim* sim, const int32_t* on, const float* rest, con
 int ag_dressing_step_dev(AgSim* sim, const float* action_dev, float* obs_dev, float* reward_dev, float* done_dev, float* info_dev);
 int ag_dressing_step_host(AgSim* sim, const float* action, float* obs, float* reward, float* done, float* info);
 
+/* --- camera images: p.computeViewMatrix / p.computeProjectionMatrixFOV / p.getCameraImage (env.py:342-359; learn.py:101,125).
+ * The collision geometry is ray-cast on the device (the visual meshes are not part of the scene description): RGBA8 image and
+ * OpenGL-style depth buffer per requested env.  SURVEY.md section 8(f)4. ----------------------------------------------- */
+typedef struct AgCamera {
+  float eye[3], target[3], up[3];     /* computeViewMatrix(camera_eye, camera_target, [0,0,1]) */
+  float fov_deg, aspect, near_, far_; /* computeProjectionMatrixFOV(fov, w / h, 0.01, 100) */
+  int32_t width, height;
+  float light_dir[3];                 /* getCameraImage lightDirection (env.py:355: [0,-3,1]) */
+  float ambient, diffuse;             /* lightAmbientCoeff 0.8, lightDiffuseCoeff 0.3 (env.py:355) */
+} AgCamera;
+/* rgba: host uint8 [n][height][width][4], depth: host float [n][height][width] (NULL to skip), env_ids [n] */
+int ag_render(AgSim* sim, const AgCamera* cam, int n, const int32_t* env_ids, uint8_t* rgba, float* depth);
+
 /* --- batched inverse kinematics for reset (Robot.ik_random_restarts agents/robot.py:84-121 via
  * AssistiveEnv.init_robot_pose envs/env.py:296): damped least squares with random restarts inside
  * the joint limits, one env per thread.  `joint_links` [n_joints <= 8]: the solved joints (global link ids, all on the
