@@ -190,6 +190,8 @@ def load_library(path=None):
     lib.ag_set_link_friction.argtypes = [vp, ci, vp, vp]
     lib.ag_set_body_active.argtypes = [vp, ci, vp]
     lib.ag_forward_kinematics.argtypes = [vp]
+    lib.ag_set_body_gravity.argtypes = [vp, ci, vp]
+    lib.ag_get_link_aabb.argtypes = [vp, ci, vp, vp, vp]
     lib.ag_set_motor_host.argtypes = [vp, ci, vp, ci, vp, vp, vp, vp]
     lib.ag_set_motor_targets_dev.argtypes = [vp, ci, vp, vp]
     lib.ag_set_motor_targets_host.argtypes = [vp, ci, vp, vp]
@@ -252,6 +254,6 @@ EXPORTED_SYMBOLS = [
     'ag_closest_points', 'ag_feeding_init', 'ag_feeding_reset_episode', 'ag_feeding_set_tremor', 'ag_set_hard_limits', 'ag_feeding_step_dev', 'ag_ik_solve', 'ag_bathing_init', 'ag_bathing_step_dev', 'ag_bathing_step_host',
     'ag_feeding_step_host', 'ag_feeding_step_host_begin', 'ag_feeding_step_host_end', 'ag_state_size', 'ag_state_get', 'ag_state_set', 'ag_kernel_launches',
     'ag_cloth_init', 'ag_cloth_set_state', 'ag_cloth_get_state', 'ag_cloth_set_anchor', 'ag_cloth_anchor_follow', 'ag_cloth_set_gravity',
-    'ag_cloth_get_contacts', 'ag_cloth_device_state', 'ag_render', 'ag_dressing_init', 'ag_dressing_reset_episode', 'ag_dressing_set_tremor', 'ag_set_motor_force_scale', 'ag_dressing_step_dev', 'ag_dressing_step_host',
+    'ag_cloth_get_contacts', 'ag_cloth_device_state', 'ag_render', 'ag_set_body_gravity', 'ag_get_link_aabb', 'ag_dressing_init', 'ag_dressing_reset_episode', 'ag_dressing_set_tremor', 'ag_set_motor_force_scale', 'ag_dressing_step_dev', 'ag_dressing_step_host',
     'ag_overflow_count', 'ag_get_solver_stats', 'ag_get_pgs_cycles', 'ag_get_pgs_trips', 'ag_profile_enable', 'ag_profile_get',
 ]

@@ -665,6 +665,18 @@ static void run_fk_all(AgSim* s) {
   LAUNCH(s, k_linkaabb, (size_t)s->S.nalllink * s->S.N, l);
 }
 
+int ag_set_body_gravity(AgSim* s, int body, const double g[3]) {
+  DevGuard guard__(s->device);
+  if (body < 0 || body >= s->nb) return fail("bad body");
+  float gf[3] = {(float)g[0], (float)g[1], (float)g[2]};
+  return h2d(s, (float*)s->S.body_gravity + 3 * body, gf, sizeof(gf));        // a template table shared by the envs; kernels read it at launch
+}
+int ag_get_link_aabb(AgSim* s, int n, const int32_t* links, float* aabb_min, float* aabb_max) {
+  DevGuard guard__(s->device);
+  run_fk_all(s);
+  if (gather_host(s, s->S.lmin, 3, n, links, aabb_min)) return -1;
+  return gather_host(s, s->S.lmax, 3, n, links, aabb_max);
+}
 int ag_forward_kinematics(AgSim* s) {
   DevGuard guard__(s->device); run_fk_all(s); return 0; }
 
@@ -1285,7 +1297,7 @@ int ag_render(AgSim* s, const AgCamera* cam, int n, const int32_t* env_ids, uint
   for (int i = 0; i < n; i++) if (env_ids[i] < 0 || env_ids[i] >= s->S.N) return fail("ag_render: bad env id");
   // link poses and link AABBs of the current state (all bodies)
   run_fk_all(s);
-  RenderDev R; memset(&R, 0, sizeof(R));
+  RenderDev R = RenderDev();
   R.cam = *cam;
   f3 eye(cam->eye[0], cam->eye[1], cam->eye[2]), tgt(cam->target[0], cam->target[1], cam->target[2]), upv(cam->up[0], cam->up[1], cam->up[2]);
   f3 f = tgt - eye; float fl = norm(f); if (!(fl > 0.f)) return fail("ag_render: eye == target");

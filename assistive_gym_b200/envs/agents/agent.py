@@ -155,6 +155,85 @@ class Agent:
     def reset_joints(self):
         self.set_joint_angles(self.all_joint_indices, [0] * len(self.all_joint_indices))
 
+    # ---- the rest of the reference's surface (agent.py:94-98,132-207,252-283)
+    def get_joint_max_force(self, indices=None):
+        """agent.py:94-98 (getJointInfo[10]: the URDF effort limit)"""
+        indices = self.all_joint_indices if indices is None else indices
+        mf = self.sim.scene.d.get('link_max_force')
+        return [float(mf[self._gl(j)]) if mf is not None else 0.0 for j in indices]
+
+    def get_heights(self, set_on_ground=False):
+        """agent.py:132-143: height and base height from the AABBs of the base and every link"""
+        mn, mx = self.sim.get_link_aabb([self.link0] + [self._gl(j) for j in self.all_joint_indices])
+        ok = mn[..., 2] <= mx[..., 2]                                 # links without colliders have no box
+        zmin = np.where(ok, mn[..., 2], np.inf).min(axis=1)
+        zmax = np.where(ok, mx[..., 2], -np.inf).max(axis=1)
+        height = zmax - zmin
+        base_height = np.atleast_2d(self.get_pos_orient(self.base)[0])[:, 2] - zmin
+        if set_on_ground:
+            self.set_on_ground(base_height)
+        return self._sq(height), self._sq(base_height)
+
+    def set_on_ground(self, base_height=None):
+        """agent.py:158-162"""
+        if base_height is None:
+            _, base_height = self.get_heights()
+        pos, orient = (np.atleast_2d(a) for a in self.get_base_pos_orient())
+        pos = pos.copy()
+        pos[:, 2] = np.atleast_1d(base_height) + 0.01
+        self.set_base_pos_orient(pos, orient)
+
+    def set_friction(self, links, friction):
+        self.set_frictions(links, lateral_friction=friction, spinning_friction=0, rolling_friction=0)
+
+    def set_gravity(self, ax=0.0, ay=0.0, az=-9.81):
+        """agent.py:196-197 (`p.setGravity(..., body=self.body)`, a fork feature): the same for every env"""
+        self.sim.set_body_gravity(self.body, [ax, ay, az])
+
+    def ik(self, target_joint, target_pos, target_orient, ik_indices, max_iterations=1000, half_range=False, use_current_as_rest=False, randomize_limits=False):
+        """agent.py:252-274 (`p.calculateInverseKinematics` from a random rest pose) on the device: damped least squares for the
+        joints `ik_indices` -- here the pybullet joint indices to solve for -- from one random start inside the limits;
+        `target_orient` None = position only.  Returns the joint angles [n_envs, len(ik_indices)] (squeezed for one env)."""
+        if target_orient is None:
+            tq = np.full(4, np.nan)
+        else:
+            tq = np.asarray(target_orient, dtype=np.float64)
+            if tq.shape[-1] == 3:                                        # euler angles (agent.py:253-254)
+                tq = self.get_quaternion(tq)
+        q, _err = self.sim.ik_solve([self._gl(j) for j in ik_indices], self._gl(target_joint), np.broadcast_to(np.asarray(target_pos, dtype=np.float64), (self.sim.n, 3)),
+                                    tq, max_restarts=1, iters=min(int(max_iterations), 200), threshold=1e-4, seed=int(self.np_random.randint(1, 2 ** 31 - 1)))
+        return self._sq(q.astype(np.float64))
+
+    def print_joint_info(self, show_fixed=True):
+        """agent.py:276-283"""
+        s = self.sim.scene
+        for j in self.all_joint_indices:
+            g = self._gl(j)
+            if show_fixed or int(s['link_jtype'][g]) != 0:
+                print(j, {0: 'fixed', 1: 'revolute', 2: 'prismatic'}.get(int(s['link_jtype'][g])), float(s['link_lower'][g]), float(s['link_upper'][g]))
+
+    def _template_level(self, what):
+        raise NotImplementedError('%s changes the scene template, which is immutable once the batched simulation exists: do it on the '
+                                  'SceneBuilder before `finalize()` (assistive_gym_b200/scene.py)' % what)
+
+    def set_mass(self, link, mass):                                   # agent.py:185-186 changeDynamics(mass=)
+        self._template_level('set_mass')
+
+    def set_joint_stiffness(self, joint, stiffness):                  # agent.py:192-194
+        self._template_level('set_joint_stiffness')
+
+    def set_all_joints_stiffness(self, stiffness):                    # agent.py:188-190
+        self._template_level('set_all_joints_stiffness')
+
+    def create_constraint(self, parent_link, child, child_link, **kw):   # agent.py:202-207 p.createConstraint
+        self._template_level('create_constraint')
+
+    def enable_force_torque_sensor(self, joint):                      # agent.py:199-200
+        self._template_level('enable_force_torque_sensor')
+
+    def get_force_torque_sensor(self, joint):                         # agent.py:145-146
+        self._template_level('get_force_torque_sensor')
+
     def set_frictions(self, links, lateral_friction=None, spinning_friction=None, rolling_friction=None):
         links = [links] if isinstance(links, int) else links
         if lateral_friction is not None:

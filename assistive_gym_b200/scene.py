@@ -579,6 +579,7 @@ class SceneBuilder:
         d['link_haslimit'] = np.array([l.haslimit for l in L], dtype=np.int32)
         d['link_damping'] = np.array([l.damping for l in L], dtype=np.float64)
         d['link_friction'] = np.array([l.friction for l in L], dtype=np.float64)
+        d['link_max_force'] = np.array([l.max_force for l in L], dtype=np.float64)       # URDF effort limit (getJointInfo[10])
         col_link, col_type, col_radius, col_v0, col_nv, col_p0, col_np, col_center, col_half = [], [], [], [], [], [], [], [], []
         col_thresh = []
         verts, planes = [], []

@@ -98,6 +98,17 @@ class BatchSim:
         t = _f32(target, (self.n, len(links)))
         self._ck(self.lib.ag_set_motor_targets_host(self.h, len(links), _p(links), _p(t)))
 
+    def set_body_gravity(self, body, g):
+        gg = (C.c_double * 3)(*[float(a) for a in g])
+        self._ck(self.lib.ag_set_body_gravity(self.h, int(body), gg))
+
+    def get_link_aabb(self, links):
+        links = _i32(links)
+        mn = np.zeros((self.n, len(links), 3), dtype=np.float32)
+        mx = np.zeros_like(mn)
+        self._ck(self.lib.ag_get_link_aabb(self.h, len(links), _p(links), _p(mn), _p(mx)))
+        return mn, mx
+
     def forward_kinematics(self):
         self._ck(self.lib.ag_forward_kinematics(self.h))
 

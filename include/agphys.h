@@ -148,6 +148,11 @@ int ag_set_body_active(AgSim* sim, int body, const int32_t* active);
 /* Human.enforce_joint_limits (agent.py:240-250, called every substep for a human in `agents`,
  * env.py:229): hard clamp of q to the joint limits with qd := 0, applied after integration. */
 int ag_set_hard_limits(AgSim* sim, int n, const int32_t* links, int on);
+/* p.setGravity(..., body=) of the fork (agent.py:196-197): gravity felt by one body, the same in every env */
+int ag_set_body_gravity(AgSim* sim, int body, const double g[3]);
+/* p.getAABB per link (agent.py:132-143 get_heights): world AABB of each link's colliders, [N][n][3] each; links without
+ * colliders report an empty box (min > max) */
+int ag_get_link_aabb(AgSim* sim, int n, const int32_t* links, float* aabb_min, float* aabb_max);
 /* recompute link world poses from the state (after teleports); also done by ag_step */
 int ag_forward_kinematics(AgSim* sim);
 

@@ -913,6 +913,7 @@ int oracle_set_motor_targets(void* h, int n, const int32_t* links, const double*
   for (int i = 0; i < s->N; i++) for (int j = 0; j < n; j++) s->envs[i].motor_target[links[j]] = (real)target[i * n + j];
   return 0;
 }
+int oracle_set_body_gravity(void* h, int body, const double* g) { ((Sim*)h)->sc.body_gravity[body] = V3((real)g[0], (real)g[1], (real)g[2]); return 0; }
 int oracle_forward_kinematics(void* h) {
   Sim* s = (Sim*)h;
   for (auto& e : s->envs) forward_kinematics(s->sc, e);

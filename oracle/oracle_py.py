@@ -48,6 +48,7 @@ def _load(f32=False):
     lib.oracle_set_motor_targets.argtypes = [vp, ci, vp, vp]
     lib.oracle_set_motor_force_scale.argtypes = [vp, ci, vp, vp]
     lib.oracle_forward_kinematics.argtypes = [vp]
+    lib.oracle_set_body_gravity.argtypes = [vp, ci, vp]
     lib.oracle_step.argtypes = [vp, ci, ci]
     lib.oracle_get_joint_states.argtypes = [vp, ci, vp, vp, vp, vp]
     lib.oracle_get_link_states.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, vp]
@@ -163,6 +164,9 @@ class OracleSim:
         links = _i32(links)
         target = _f64(target, (self.n, len(links)))
         self.lib.oracle_set_motor_targets(self.h, len(links), _p(links), _p(target))
+
+    def set_body_gravity(self, body, g):
+        self.lib.oracle_set_body_gravity(self.h, int(body), _p(np.asarray(g, dtype=np.float64)))
 
     def forward_kinematics(self):
         self.lib.oracle_forward_kinematics(self.h)

@@ -77,3 +77,36 @@ def test_surface_gpu(gpu_lib):
 @pytest.mark.parametrize('impairment', ['random', 'tremor'])
 def test_fused_step_equals_reference_api_gpu(gpu_lib, impairment):
     _check_fused_vs_api(None, 8, impairment)
+
+
+def test_agent_surface_extras(emu_lib):
+    """The rest of the reference's Agent surface (agent.py:94-98,132-207,252-283): per-body gravity, AABB heights, IK,
+    URDF effort limits; calls that would change the immutable scene template say so."""
+    import pytest
+    from assistive_gym_b200 import envs
+    env = envs.make('FeedingJaco-v1', n_envs=2)
+    env._sim_lib = emu_lib
+    env.reset()
+    sim, robot = env.id, env.robot
+    assert all(f > 0 for f in robot.get_joint_max_force(robot.controllable_joint_indices))
+    # heights from the link AABBs (agent.py:132-143) against the scene's collider vertices
+    height, base_height = env.tool.get_heights()
+    assert height.shape == (2,) and np.all(height > 0.005) and np.all(height < 0.3)
+    mn, mx = sim.get_link_aabb([int(sim.scene['body_link0'][env.tool.body])])
+    assert np.all(mn[:, 0] < mx[:, 0])
+    # IK to the current end-effector pose returns a configuration that reproduces it
+    ee = robot.right_end_effector
+    pos, orient = (np.atleast_2d(a) for a in robot.get_pos_orient(ee))
+    q = np.atleast_2d(robot.ik(ee, pos, orient, robot.controllable_joint_indices, max_iterations=200))
+    robot.set_joint_angles(robot.controllable_joint_indices, q)
+    pos2 = np.atleast_2d(robot.get_pos_orient(ee)[0])
+    assert np.abs(pos2 - pos).max() < 0.03
+    # per-body gravity (agent.py:196-197): the spoon is released from the arm's pull only through its own gravity
+    v0 = np.atleast_2d(env.bowl.get_velocity(env.bowl.base)) if hasattr(env, 'bowl') else None
+    env.tool.set_gravity(0, 0, -9.81)
+    env.tool.set_gravity(0, 0, 0)
+    with pytest.raises(NotImplementedError):
+        robot.set_mass(1, 2.0)
+    with pytest.raises(NotImplementedError):
+        robot.create_constraint(1, env.tool, -1)
+    env.close()

@@ -114,6 +114,19 @@ def test_motor_position_control_converges_and_respects_max_force():
     assert abs(tau[0] - 1.0) < 1e-9 and abs(tau[1] - 0.25) < 1e-9
 
 
+def test_per_body_gravity_can_be_changed_at_run_time():
+    """p.setGravity(..., body=) (agent.py:196-197): the pendulum hangs still with its gravity switched off and swings with it on."""
+    sc, _ = _pendulum()
+    sim = OracleSim(sc, capi.default_config(linear_damping=0, angular_damping=0), 1)
+    sim.set_joint_state([1], q=[[0.7]])
+    sim.set_body_gravity(0, [0, 0, 0])
+    sim.step(20)
+    assert abs(sim.get_joint_states([1])[0][0, 0] - 0.7) < 1e-9
+    sim.set_body_gravity(0, [0, 0, -9.81])
+    sim.step(5)
+    assert sim.get_joint_states([1])[0][0, 0] < 0.7 - 1e-3
+
+
 def test_joint_limit_stops_motion():
     b = SceneBuilder()
     b.set_gravity([0, 0, -9.81])
