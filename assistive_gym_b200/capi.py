@@ -82,6 +82,16 @@ class AgBathingParams(C.Structure):
 
 import numpy as np  # noqa: E402
 
+class AgScratchParams(C.Structure):
+    _fields_ = [('robot_body', C.c_int32), ('tool_body', C.c_int32), ('human_body_m', C.c_int32), ('human_body_f', C.c_int32),
+                ('arm_links', C.c_int32 * 7), ('ee_link', C.c_int32), ('tool_link0', C.c_int32), ('tool_tip_link', C.c_int32),
+                ('arm_points_m', C.c_int32 * 3), ('arm_points_f', C.c_int32 * 3),
+                ('arm_lower', C.c_float * 7), ('arm_upper', C.c_float * 7),
+                ('action_multiplier', C.c_float), ('frame_skip', C.c_int32),
+                ('w_distance', C.c_float), ('w_action', C.c_float), ('w_scratch', C.c_float),
+                ('c_v', C.c_float), ('c_f', C.c_float), ('c_hf', C.c_float), ('task_success_threshold', C.c_float)]
+
+
 class AgCamera(C.Structure):
     _fields_ = [('eye', C.c_float * 3), ('target', C.c_float * 3), ('up', C.c_float * 3), ('fov_deg', C.c_float), ('aspect', C.c_float),
                 ('near_', C.c_float), ('far_', C.c_float), ('width', C.c_int32), ('height', C.c_int32), ('light_dir', C.c_float * 3),
@@ -226,6 +236,9 @@ def load_library(path=None):
     lib.ag_dressing_set_tremor.argtypes = [vp, vp, vp, vp]
     lib.ag_dressing_step_dev.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.ag_dressing_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.ag_scratch_init.argtypes = [vp, C.POINTER(AgScratchParams), vp, vp, vp]
+    lib.ag_scratch_step_dev.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.ag_scratch_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.ag_render.argtypes = [vp, C.POINTER(AgCamera), ci, vp, vp, vp]
     lib.ag_ik_solve.argtypes = [vp, ci, vp, ci, vp, vp, ci, ci, C.c_float, C.c_uint64, vp, vp, vp]
     lib.ag_state_size.restype = C.c_size_t
@@ -254,6 +267,6 @@ EXPORTED_SYMBOLS = [
     'ag_closest_points', 'ag_feeding_init', 'ag_feeding_reset_episode', 'ag_feeding_set_tremor', 'ag_set_hard_limits', 'ag_feeding_step_dev', 'ag_ik_solve', 'ag_bathing_init', 'ag_bathing_step_dev', 'ag_bathing_step_host',
     'ag_feeding_step_host', 'ag_feeding_step_host_begin', 'ag_feeding_step_host_end', 'ag_state_size', 'ag_state_get', 'ag_state_set', 'ag_kernel_launches',
     'ag_cloth_init', 'ag_cloth_set_state', 'ag_cloth_get_state', 'ag_cloth_set_anchor', 'ag_cloth_anchor_follow', 'ag_cloth_set_gravity',
-    'ag_cloth_get_contacts', 'ag_cloth_device_state', 'ag_render', 'ag_set_body_gravity', 'ag_get_link_aabb', 'ag_dressing_init', 'ag_dressing_reset_episode', 'ag_dressing_set_tremor', 'ag_set_motor_force_scale', 'ag_dressing_step_dev', 'ag_dressing_step_host',
+    'ag_cloth_get_contacts', 'ag_cloth_device_state', 'ag_scratch_init', 'ag_scratch_step_dev', 'ag_scratch_step_host', 'ag_render', 'ag_set_body_gravity', 'ag_get_link_aabb', 'ag_dressing_init', 'ag_dressing_reset_episode', 'ag_dressing_set_tremor', 'ag_set_motor_force_scale', 'ag_dressing_step_dev', 'ag_dressing_step_host',
     'ag_overflow_count', 'ag_get_solver_stats', 'ag_get_pgs_cycles', 'ag_get_pgs_trips', 'ag_profile_enable', 'ag_profile_get',
 ]

@@ -17,6 +17,7 @@
 #include "ag_cloth.cuh"
 #include "ag_dressing.cuh"
 #include "ag_render.cuh"
+#include "ag_scratch.cuh"
 
 #ifndef AG_CPU_EMU
 #include <cuda_runtime.h>
@@ -107,6 +108,8 @@ AG_KERNEL(k_bath_dist, bathing_dist_body)
 AG_KERNEL(k_bath_post, bathing_post_body)
 AG_KERNEL(k_dress_pre, dressing_pre_body)
 AG_KERNEL(k_dress_post, dressing_post_body)
+AG_KERNEL(k_scratch_pre, scratch_pre_body)
+AG_KERNEL(k_scratch_post, scratch_post_body)
 AG_KERNEL(k_render, render_body)
 AG_KERNEL(k_cloth_snap, cloth_snap_body)
 AG_KERNEL(k_cloth_follow, cloth_follow_body)
@@ -135,11 +138,13 @@ struct AgSim {
   // cloth (Dressing): one k_cloth launch per stepSimulation = `C.K` rigid substeps
   ClothDev C; ClothDev* C_dev; bool cloth; int cloth_sub, cloth_npt, cloth_qs;
   DressPost DP; DressPost* DP_dev; bool dressing;
+  ScratchDev SD; ScratchDev* SD_dev; bool scratch;
+  float *h_spin_in, *h_spin_out, *d_saction, *d_sobs, *d_sreward, *d_sdone, *d_sinfo;
   size_t render_pix; int render_n; int* d_render_ids; unsigned char* d_render_rgba; float* d_render_depth; void* d_render_dev;
   float *h_dpin_in, *h_dpin_out, *d_daction, *d_dobs, *d_dreward, *d_ddone, *d_dinfo;
   // CUDA-graph replay of the fused env step (one graph per entry point, keyed by its device pointers)
   bool use_graph; int graph_failures;
-  struct StepGraph { void* exec; const void* key[5]; uint64_t launches; bool valid; } graphs[3];
+  struct StepGraph { void* exec; const void* key[5]; uint64_t launches; bool valid; } graphs[4];
   // profiling
   bool profiling;
   std::vector<std::string> knames;
@@ -294,7 +299,7 @@ AgSim* ag_create(const AgSceneDesc* d, const AgConfig* cfg, int n_envs, int devi
   AgSim* s = new AgSim();
   memset(&s->S, 0, sizeof(SimDev));
   memset(&s->F, 0, sizeof(FeedDev));
-  s->cfg = *cfg; s->device = device; s->launches = 0; s->feeding = false; s->bathing = false; s->cloth = false; s->cloth_sub = 0; s->C_dev = nullptr; s->dressing = false; s->DP_dev = nullptr; s->render_pix = 0; s->render_n = 0; s->d_render_ids = nullptr; s->d_render_rgba = nullptr; s->d_render_depth = nullptr; s->d_render_dev = nullptr; s->graphs[2].valid = false; s->use_graph = true; s->graph_failures = 0; s->graphs[0].valid = s->graphs[1].valid = false; s->B_dev = nullptr; s->stream = nullptr; s->F_dev = nullptr; s->profiling = false;
+  s->cfg = *cfg; s->device = device; s->launches = 0; s->feeding = false; s->bathing = false; s->cloth = false; s->cloth_sub = 0; s->C_dev = nullptr; s->dressing = false; s->DP_dev = nullptr; s->scratch = false; s->SD_dev = nullptr; s->graphs[3].valid = false; s->render_pix = 0; s->render_n = 0; s->d_render_ids = nullptr; s->d_render_rgba = nullptr; s->d_render_depth = nullptr; s->d_render_dev = nullptr; s->graphs[2].valid = false; s->use_graph = true; s->graph_failures = 0; s->graphs[0].valid = s->graphs[1].valid = false; s->B_dev = nullptr; s->stream = nullptr; s->F_dev = nullptr; s->profiling = false;
   s->d_stage = nullptr; s->stage_floats = 0;
 #ifndef AG_CPU_EMU
   { int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { g_err = "no such CUDA device (is a CUDA device present? there is no CPU fallback)"; delete s; return nullptr; } }
@@ -525,13 +530,15 @@ void ag_destroy(AgSim* s) {
   if (s->feeding) { cudaFreeHost(s->h_pin_in); cudaFreeHost(s->h_pin_out); }
   if (s->bathing) { cudaFreeHost(s->h_bpin_in); cudaFreeHost(s->h_bpin_out); }
   if (s->dressing) { cudaFreeHost(s->h_dpin_in); cudaFreeHost(s->h_dpin_out); }
-  for (int g = 0; g < 3; g++) if (s->graphs[g].valid) cudaGraphExecDestroy((cudaGraphExec_t)s->graphs[g].exec);
+  if (s->scratch) { cudaFreeHost(s->h_spin_in); cudaFreeHost(s->h_spin_out); }
+  for (int g = 0; g < 4; g++) if (s->graphs[g].valid) cudaGraphExecDestroy((cudaGraphExec_t)s->graphs[g].exec);
   if (s->stream) cudaStreamDestroy(s->stream);
 #else
   for (void* p : s->allocs) free(p);
   if (s->feeding) { free(s->h_pin_in); free(s->h_pin_out); }
   if (s->bathing) { free(s->h_bpin_in); free(s->h_bpin_out); }
   if (s->dressing) { free(s->h_dpin_in); free(s->h_dpin_out); }
+  if (s->scratch) { free(s->h_spin_in); free(s->h_spin_out); }
 #endif
   delete s;
 }
@@ -702,7 +709,7 @@ int ag_set_motor_force_scale(AgSim* s, int n, const int32_t* links, const float*
     if (!s->S.motor_fscale) return fail("device allocation failed");
     std::vector<float> ones(cnt, 1.0f);
     if (h2d(s, s->S.motor_fscale, ones.data(), cnt * sizeof(float))) return -1;
-    for (int g = 0; g < 3; g++) drop_graph(s, g);        // captured kernels hold the SimDev of before (null pointer)
+    for (int g = 0; g < 4; g++) drop_graph(s, g);        // captured kernels hold the SimDev of before (null pointer)
   }
   return scatter_host(s, s->S.motor_fscale, 1, n, links, scale, nullptr);
 }
@@ -974,7 +981,7 @@ static int run_step(AgSim* s, int which, StepEnqueue enq, const float* action, f
   if (s->use_graph && !s->profiling) {
     // The graph is captured against the sim's OWN action buffer: a learner hands in a freshly allocated action tensor
     // every step, and a graph keyed on that address would be re-captured (~90 launches + instantiate) each time.
-    float* own = which == 0 ? s->d_action : (which == 1 ? s->d_baction : s->d_daction);
+    float* own = which == 0 ? s->d_action : (which == 1 ? s->d_baction : (which == 2 ? s->d_daction : s->d_saction));
     if (action != own) { CK(cudaMemcpyAsync(own, action, sizeof(float) * 7 * s->S.N, cudaMemcpyDeviceToDevice, s->stream)); action = own; }
     AgSim::StepGraph& G = s->graphs[which];
     const void* key[5] = {action, obs, reward, done, info};
@@ -1322,6 +1329,85 @@ int ag_render(AgSim* s, const AgCamera* cam, int n, const int32_t* env_ids, uint
   LAUNCH(s, k_render, npix, p);
   if (d2h(s, rgba, d_rgba, npix * 4)) return -1;
   if (depth && d2h(s, depth, d_depth, npix * sizeof(float))) return -1;
+  return 0;
+}
+
+// ------------------------------------------------------------------ fused ScratchItchEnv path
+int ag_scratch_init(AgSim* s, const AgScratchParams* p, const int32_t* gender_is_male, const int32_t* limb_link, const float* target_local) {
+  DevGuard guard__(s->device);
+  const int N = s->S.N;
+  for (int j = 0; j < 7; j++) if (p->arm_links[j] < 0 || p->arm_links[j] >= s->nl) return fail("ag_scratch_init: bad arm link");
+  if (p->ee_link < 0 || p->ee_link >= s->nl || p->tool_tip_link < 0 || p->tool_tip_link >= s->nl || p->tool_link0 < 0 || p->tool_link0 >= s->nl) return fail("ag_scratch_init: bad link");
+  for (int e = 0; e < N; e++) if (limb_link[e] < 0 || limb_link[e] >= s->nl) return fail("ag_scratch_init: bad limb link");
+  ScratchDev& D = s->SD;
+  D.P = *p;
+  drop_graph(s, 3);
+  if (!s->scratch) {
+    D.male = dalloc<int>(s, N); D.iteration = dalloc<int>(s, N); D.task_success = dalloc<int>(s, N); D.limb_link = dalloc<int>(s, N);
+    D.target_local = dalloc<float>(s, (size_t)3 * N); D.prev_contact = dalloc<float>(s, (size_t)3 * N); D.action = dalloc<float>(s, (size_t)7 * N);
+    s->d_saction = dalloc<float>(s, (size_t)N * 7); s->d_sobs = dalloc<float>(s, (size_t)N * 30);
+    s->d_sreward = dalloc<float>(s, N); s->d_sdone = dalloc<float>(s, N); s->d_sinfo = dalloc<float>(s, (size_t)N * 4);
+    s->SD_dev = dalloc<ScratchDev>(s, 1);
+    if (!s->d_sinfo || !s->SD_dev) return fail("device allocation failed");
+#ifndef AG_CPU_EMU
+    CK(cudaMallocHost((void**)&s->h_spin_in, sizeof(float) * N * 7));
+    CK(cudaMallocHost((void**)&s->h_spin_out, sizeof(float) * N * 36));
+#else
+    s->h_spin_in = (float*)malloc(sizeof(float) * N * 7); s->h_spin_out = (float*)malloc(sizeof(float) * N * 36);
+#endif
+  }
+  std::vector<float> tl((size_t)3 * N);
+  for (int e = 0; e < N; e++) for (int c = 0; c < 3; c++) tl[(size_t)c * N + e] = target_local[(size_t)e * 3 + c];
+  if (h2d(s, D.male, gender_is_male, sizeof(int) * N) || h2d(s, D.limb_link, limb_link, sizeof(int) * N) || h2d(s, D.target_local, tl.data(), sizeof(float) * 3 * N)) return -1;
+  if (dev_zero(s, D.iteration, sizeof(int) * N) || dev_zero(s, D.task_success, sizeof(int) * N) || dev_zero(s, D.prev_contact, sizeof(float) * 3 * N)) return -1;   // scratch_itch.py:97
+  if (h2d(s, s->SD_dev, &s->SD, sizeof(ScratchDev))) return -1;
+  s->scratch = true;
+  return 0;
+}
+static int scratch_step_enqueue(AgSim* s, const float* action_dev, float* obs, float* reward, float* done, float* info) {
+  const int N = s->S.N;
+  KP p = kp0(); p.p0 = action_dev; p.p1 = s->SD_dev;
+  LAUNCH(s, k_scratch_pre, N, p);
+  for (int i = 0; i < s->SD.P.frame_skip * (s->cfg.num_substeps > 0 ? s->cfg.num_substeps : 1); i++) substep(s);
+  KP z = kp0();
+  LAUNCH(s, k_fk, (size_t)s->S.nb * N, z);
+  KP q = kp0(); q.p0 = action_dev; q.p1 = s->SD_dev; q.p2 = obs; q.p3 = reward; q.p4 = done; q.p5 = info;
+  LAUNCH(s, k_scratch_post, N, q);
+  return 0;
+}
+int ag_scratch_step_dev(AgSim* s, const float* action_dev, float* obs_dev, float* reward_dev, float* done_dev, float* info_dev) {
+  DevGuard guard__(s->device);
+  if (!s->scratch) return fail("ag_scratch_init not called");
+  int rc = run_step(s, 3, scratch_step_enqueue, action_dev, obs_dev, reward_dev, done_dev, info_dev);
+#ifndef AG_CPU_EMU
+  CK(cudaGetLastError());
+#endif
+  return rc;
+}
+int ag_scratch_step_host(AgSim* s, const float* action, float* obs, float* reward, float* done, float* info) {
+  DevGuard guard__(s->device);
+  if (!s->scratch) return fail("ag_scratch_init not called");
+  const int N = s->S.N;
+  memcpy(s->h_spin_in, action, sizeof(float) * N * 7);
+#ifndef AG_CPU_EMU
+  CK(cudaMemcpyAsync(s->d_saction, s->h_spin_in, sizeof(float) * N * 7, cudaMemcpyHostToDevice, s->stream));
+#else
+  memcpy(s->d_saction, s->h_spin_in, sizeof(float) * N * 7);
+#endif
+  if (ag_scratch_step_dev(s, s->d_saction, s->d_sobs, s->d_sreward, s->d_sdone, s->d_sinfo)) return -1;
+  float* o = s->h_spin_out;
+#ifndef AG_CPU_EMU
+  CK(cudaMemcpyAsync(o, s->d_sobs, sizeof(float) * N * 30, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(o + (size_t)N * 30, s->d_sreward, sizeof(float) * N, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(o + (size_t)N * 31, s->d_sdone, sizeof(float) * N, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(o + (size_t)N * 32, s->d_sinfo, sizeof(float) * N * 4, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+#else
+  memcpy(o, s->d_sobs, sizeof(float) * N * 30); memcpy(o + (size_t)N * 30, s->d_sreward, sizeof(float) * N);
+  memcpy(o + (size_t)N * 31, s->d_sdone, sizeof(float) * N); memcpy(o + (size_t)N * 32, s->d_sinfo, sizeof(float) * N * 4);
+#endif
+  memcpy(obs, o, sizeof(float) * N * 30); memcpy(reward, o + (size_t)N * 30, sizeof(float) * N);
+  memcpy(done, o + (size_t)N * 31, sizeof(float) * N); memcpy(info, o + (size_t)N * 32, sizeof(float) * N * 4);
   return 0;
 }
 

@@ -25,6 +25,11 @@ distance_weight = 1.0
 action_weight = 0.01
 food_reward_weight = 1.0
 task_success_threshold = 0.75
+[scratch_itch]
+distance_weight = 1.0
+action_weight = 0.01
+scratch_reward_weight = 1.0
+task_success_threshold = 25.0
 [bed_bathing]
 distance_weight = 1.0
 action_weight = 0.01

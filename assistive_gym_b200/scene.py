@@ -115,7 +115,8 @@ def load_asset(name):
 ASSET_ALIASES = {
     'plane.urdf': 'plane', 'j2s7s300_gym.urdf': 'jaco', 'wheelchair_jaco.urdf': 'wheelchair_jaco',
     'wheelchair.urdf': 'wheelchair', 'table_tall.urdf': 'table_tall', 'bowl.urdf': 'bowl',
-    'sawyer.urdf': 'sawyer', 'bed.urdf': 'bed', 'wiper.urdf': 'wiper',
+    'sawyer.urdf': 'sawyer', 'bed.urdf': 'bed', 'wiper.urdf': 'wiper', 'tool_scratch.urdf': 'tool_scratch',
+    'pr2_no_torso_lift_tall.urdf': 'pr2',
     'spoon_vhacd.obj': 'spoon_vhacd',
     'BaseHeadMeshes_v5_male_cropped_reduced_compressed_vhacd.obj': 'head_male_vhacd',
     'BaseHeadMeshes_v5_female_cropped_reduced_compressed_vhacd.obj': 'head_female_vhacd',

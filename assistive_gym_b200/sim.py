@@ -281,6 +281,23 @@ class BatchSim:
         self._ck(self.lib.ag_cloth_get_contacts(self.h, max_pts, _p(cnt), _p(node), _p(pos), _p(force), _p(link)))
         return cnt, self.cloth_model.order[node], pos, force, link
 
+    # ---- fused scratch-itch path
+    def scratch_init(self, params, gender_is_male, limb_link, target_local):
+        self._scratch_params = params
+        self._ck(self.lib.ag_scratch_init(self.h, C.byref(params), _p(_i32(gender_is_male)), _p(_i32(limb_link)), _p(_f32(target_local, (self.n, 3)))))
+
+    def scratch_step_host(self, action):
+        a = _f32(action, (self.n, 7))
+        obs = np.empty((self.n, 30), dtype=np.float32)
+        rew = np.empty(self.n, dtype=np.float32)
+        done = np.empty(self.n, dtype=np.float32)
+        info = np.empty((self.n, 4), dtype=np.float32)
+        self._ck(self.lib.ag_scratch_step_host(self.h, _p(a), _p(obs), _p(rew), _p(done), _p(info)))
+        return obs, rew, done, info
+
+    def scratch_step_dev(self, action_ptr, obs_ptr, reward_ptr, done_ptr, info_ptr):
+        self._ck(self.lib.ag_scratch_step_dev(self.h, action_ptr, obs_ptr, reward_ptr, done_ptr, info_ptr))
+
     # ---- camera images (ag_render)
     def render(self, eye, target, fov=60.0, width=480, height=270, env_ids=(0,), up=(0, 0, 1), near=0.01, far=100.0,
                light_dir=(0, -3, 1), ambient=0.8, diffuse=0.3):

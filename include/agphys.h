@@ -314,6 +314,28 @@ int ag_dressing_set_tremor(AgSim* sim, const int32_t* on, const float* rest, con
 int ag_dressing_step_dev(AgSim* sim, const float* action_dev, float* obs_dev, float* reward_dev, float* done_dev, float* info_dev);
 int ag_dressing_step_host(AgSim* sim, const float* action, float* obs, float* reward, float* done, float* info);
 
+/* --- fused ScratchItchEnv path (scratch_itch.py:10-91 + env.py:174-274): action -> PD targets -> frame_skip substeps ->
+ * obs [30] / reward / done; the target is a point on the person's right upper arm or forearm (scratch_itch.py:134-153), a tool
+ * contact within 0.025 m of it that has moved by more than 0.01 m counts as a scratch.  SURVEY.md section 8(f)3. ------------- */
+typedef struct AgScratchParams {
+  int32_t robot_body, tool_body, human_body_m, human_body_f;
+  int32_t arm_links[7];         /* controllable joints (global link ids) */
+  int32_t ee_link;              /* left_end_effector */
+  int32_t tool_link0, tool_tip_link;          /* tool links 0 and 1 (global ids): `if linkA in [0, 1]`, `tool.get_pos_orient(1)` */
+  int32_t arm_points_m[3], arm_points_f[3];   /* right shoulder, elbow, wrist links (global ids) */
+  float   arm_lower[7], arm_upper[7];
+  float   action_multiplier;    /* 0.05 env.py:188 */
+  int32_t frame_skip;           /* 5 */
+  float   w_distance, w_action, w_scratch;    /* config.ini [scratch_itch] */
+  float   c_v, c_f, c_hf;                     /* config.ini [human_preferences] */
+  float   task_success_threshold;             /* 25 scratches */
+} AgScratchParams;
+/* limb_link [N]: global id of the link that carries each env's target; target_local [N][3]: the point in that link's frame */
+int ag_scratch_init(AgSim* sim, const AgScratchParams* p, const int32_t* gender_is_male, const int32_t* limb_link, const float* target_local);
+/* obs [N][30], reward [N], done [N], info [N][4] = total force on the person, task success, tool force at the target, scratches */
+int ag_scratch_step_dev(AgSim* sim, const float* action_dev, float* obs_dev, float* reward_dev, float* done_dev, float* info_dev);
+int ag_scratch_step_host(AgSim* sim, const float* action, float* obs, float* reward, float* done, float* info);
+
 /* --- camera images: p.computeViewMatrix / p.computeProjectionMatrixFOV / p.getCameraImage (env.py:342-359; learn.py:101,125).
  * The collision geometry is ray-cast on the device (the visual meshes are not part of the scene description): RGBA8 image and
  * OpenGL-style depth buffer per requested env.  SURVEY.md section 8(f)4. ----------------------------------------------- */

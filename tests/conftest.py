@@ -15,7 +15,7 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     """The round's newest GPU paths (cloth, Dressing) run after the established ones, so that `-x` on a fresh box reports
     the long-standing parity tests before anything that has had less time on the hardware."""
-    late = ('test_cloth_parity', 'test_dressing')
+    late = ('test_cloth_parity', 'test_dressing', 'test_render', 'test_scratch_itch')
     items.sort(key=lambda it: any(m in it.nodeid for m in late))       # stable: relative order is otherwise unchanged
 
 

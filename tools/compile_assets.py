@@ -304,6 +304,7 @@ URDFS = {
     'bed': 'bed/bed.urdf',
     'wiper': 'bed_bathing/wiper.urdf',
     'pr2': 'PR2/pr2_no_torso_lift_tall.urdf',
+    'tool_scratch': 'scratcher/tool_scratch.urdf',
 }
 CLOTHS = {
     'hospitalgown_reduced': 'clothing/hospitalgown_reduced.obj',
