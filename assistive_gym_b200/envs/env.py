@@ -174,8 +174,11 @@ class AssistiveEnv(gym.Env):
                     agent.control(agent.controllable_joint_indices, agent.target_joint_angles + agent.tremors * sgn, gains[i], forces[i])
                 continue
             k = len(agent.controllable_joint_indices)
-            action = actions[:, idx:idx + k].copy()
-            idx += k
+            if isinstance(agent, Human):          # the two gender instances of the person share the human part of the action
+                action = actions[:, self.action_robot_len:self.action_robot_len + k].copy()
+            else:
+                action = actions[:, idx:idx + k].copy()
+                idx += k
             if isinstance(agent, Robot):
                 action *= agent.action_multiplier
             q = np.atleast_2d(agent.get_joint_angles(agent.controllable_joint_indices)).copy()

@@ -42,7 +42,7 @@ class FeedingEnv(AssistiveEnv):
             self.bowl.init(fb.bowl, sim, self.np_random, indices=-1)
             self.humans = {}
             for g, hb in fb.humans.items():
-                h = type(self.human)(self.human.controllable_joint_indices, controllable=False)
+                h = type(self.human)(self.human.controllable_joint_indices, controllable=self.human.controllable)
                 h.init(hb, sim, self.np_random, self.human.controllable_joint_indices)
                 self.humans[g] = h
             self.foods_agents = []
@@ -54,7 +54,9 @@ class FeedingEnv(AssistiveEnv):
         rng = np.random.default_rng(self.np_random.randint(0, 2 ** 31 - 1))
         self.robot.motor_gains = self.human.motor_gains = 0.025          # feeding.py:122
         self.agents = [self.robot]
-        s = fb.reset(self.id, rng, settle_steps=25, impairment=self.human_impairment)
+        coop = bool(self.human.controllable)
+        # (co-optimisation: the reference may also draw `tremor` for a controllable person, human.py:80-81; not combined here)
+        s = fb.reset(self.id, rng, settle_steps=25, impairment='no_tremor' if coop else self.human_impairment, simulate_head=coop)
         self.male = s['male'].astype(bool)
         self.human.gender = 'male' if self.male[0] else 'female'
         # impairments (human.py:79-92).  The reference appends a tremor human to `agents`
@@ -72,6 +74,10 @@ class FeedingEnv(AssistiveEnv):
             h.motor_gains = self.human.motor_gains
             if h.tremor_mask.any():
                 self.agents.append(h)
+        if coop:                                  # both gender instances act; the switched-off one moves nothing (env.py:130)
+            for h in self.humans.values():
+                h.motor_gains, h.motor_forces = self.human.motor_gains, self.human.motor_forces
+                self.agents.append(h)
         self.mouth_pos = np.where(self.male[:, None], fb.mouth['male'], fb.mouth['female'])
         if not self._feeding_ready:
             fb.start_fused(self.id, s, seed=self._seed)
@@ -85,10 +91,17 @@ class FeedingEnv(AssistiveEnv):
         return self._squeeze(self._get_obs())
 
     def _squeeze(self, a):
+        if isinstance(a, dict):
+            return {k: self._squeeze(v) for k, v in a.items()}
         return a[0] if self.n_envs == 1 else a
 
     # ------------------------------------------------------------------ fused step (feeding.py:12-43)
     def step(self, action):
+        if self.human.controllable:               # feeding.py:13-14,40-43: dict in, dicts out (per-call API path)
+            a = np.concatenate([np.asarray(action['robot'], dtype=np.float64).reshape(self.n_envs, -1), np.asarray(action['human'], dtype=np.float64).reshape(self.n_envs, -1)], axis=1)
+            obs, reward, done, info = self.step_reference_api(a)
+            d = bool(np.all(done)) if self.n_envs > 1 else bool(done)
+            return obs, {'robot': reward, 'human': reward}, {'robot': done, 'human': done, '__all__': d}, {'robot': info, 'human': info}
         a = np.asarray(action, dtype=np.float32).reshape(self.n_envs, -1)
         obs, rew, done, info = self.id.feeding_step_host(a)
         self.iteration += 1
@@ -126,7 +139,25 @@ class FeedingEnv(AssistiveEnv):
         tg_r = np.atleast_2d(self.robot.convert_to_realworld(self.target_pos)[0])
         self.robot_force_on_human, self.spoon_force_on_human = self.get_total_force()
         self.total_force_on_human = self.robot_force_on_human + self.spoon_force_on_human
-        return np.concatenate([sp_r, sq_r, sp_r - tg_r, q, hp_r, hq_r, self.spoon_force_on_human[:, None]], axis=1)
+        robot_obs = np.concatenate([sp_r, sq_r, sp_r - tg_r, q, hp_r, hq_r, self.spoon_force_on_human[:, None]], axis=1)
+        if agent == 'robot' or not self.human.controllable:
+            return robot_obs
+        # feeding.py:101-111: the same quantities in the person's base frame + the person's joint angles
+        def human_frame(pos, orient=None):
+            outs = []
+            for g in ('male', 'female'):
+                r = self.humans[g].convert_to_realworld(pos, orient if orient is not None else np.array([0, 0, 0, 1.0]))
+                outs.append([np.atleast_2d(x) for x in r])
+            return [np.where(self.male[:, None], m, f) for m, f in zip(*outs)]
+        qh = np.where(self.male[:, None], np.atleast_2d(self.humans['male'].get_joint_angles(self.human.controllable_joint_indices)),
+                      np.atleast_2d(self.humans['female'].get_joint_angles(self.human.controllable_joint_indices)))
+        sp_h, sq_h = human_frame(sp, sq)
+        hp_h, hq_h = human_frame(hp, hq)
+        tg_h = human_frame(self.target_pos)[0]
+        human_obs = np.concatenate([sp_h, sq_h, sp_h - tg_h, qh, hp_h, hq_h, self.robot_force_on_human[:, None], self.spoon_force_on_human[:, None]], axis=1)
+        if agent == 'human':
+            return human_obs
+        return {'robot': robot_obs, 'human': human_obs}
 
     def get_food_rewards(self):                                          # feeding.py:50-83
         n = self.n_envs
@@ -165,5 +196,6 @@ class FeedingEnv(AssistiveEnv):
         reward = (self.config('distance_weight') * (-np.linalg.norm(self.target_pos - spoon_pos, axis=1)) +
                   self.config('action_weight') * (-np.linalg.norm(a, axis=1)) + self.config('food_reward_weight') * reward_food + pref)
         done = np.full(self.n_envs, self.iteration >= 200)
-        info = {'total_force_on_human': self.total_force_on_human, 'task_success': (self.task_success >= self.total_food_count * self.config('task_success_threshold')).astype(int)}
+        info = {'total_force_on_human': self.total_force_on_human, 'task_success': (self.task_success >= self.total_food_count * self.config('task_success_threshold')).astype(int),
+                'action_robot_len': self.action_robot_len, 'action_human_len': self.action_human_len, 'obs_robot_len': self.obs_robot_len, 'obs_human_len': self.obs_human_len}
         return self._squeeze(obs), self._squeeze(reward), self._squeeze(done), info

@@ -193,7 +193,7 @@ class FeedingBatch:
             todo = todo[best_err[todo] >= threshold]
         return best_q, best_err
 
-    def reset(self, sim, rng, settle_steps=25, sample=None, impairment='random'):
+    def reset(self, sim, rng, settle_steps=25, sample=None, impairment='random', simulate_head=False):
         """Put every env of `sim` (BatchSim or the oracle wrapper) into a fresh FeedingJaco start state."""
         n = sim.n
         sc = self.scene
@@ -218,7 +218,8 @@ class FeedingBatch:
             sim.set_joint_state(links, q=q, qd=np.zeros_like(q))
             on = male if gender == 'male' else ~male
             # body mode: 0 = other gender, 1 = simulated head (tremor), 2 = frozen ("static joints")
-            sim.set_body_active(hb, np.where(on, np.where(tremor, 1, 2), 0).astype(np.int32))
+            # (a controllable human, co-optimisation envs feeding_envs.py:41-69, keeps its head chain simulated in every env)
+            sim.set_body_active(hb, np.where(on, np.where(tremor | simulate_head, 1, 2), 0).astype(np.int32))
             # take_step drives the controllable (head) joints of a tremor human with the env's motor
             # gain/force (feeding.py:122 gains 0.025, human.py:69 force 1.0) around target_joint_angles
             # (human.py:122) and clamps them to their limits after every substep (env.py:226-229)

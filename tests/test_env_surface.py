@@ -110,3 +110,30 @@ def test_agent_surface_extras(emu_lib):
     with pytest.raises(NotImplementedError):
         robot.create_constraint(1, env.tool, -1)
     env.close()
+
+
+def test_cooptimisation_env_dict_interface(emu_lib):
+    """FeedingJacoHuman-v1 (reference feeding_envs.py:56-59, feeding.py:13-14,40-43,101-111): dict actions in, dict observations /
+    rewards / dones out; the person's head joints follow the human action and respect their limits."""
+    from assistive_gym_b200 import envs
+    env = envs.make('FeedingJacoHuman-v1', n_envs=2)
+    env._sim_lib = emu_lib
+    obs = env.reset()
+    assert set(obs) == {'robot', 'human'} and obs['robot'].shape == (2, 25) and obs['human'].shape == (2, 23)
+    assert env.action_space.shape == (11,) and env.action_robot_len == 7 and env.action_human_len == 4
+    active = [env.humans['male' if m else 'female'] for m in env.male]
+    q0 = np.stack([np.atleast_2d(h.get_joint_angles(env.human.controllable_joint_indices))[e] for e, h in enumerate(active)])
+    rng = np.random.default_rng(0)
+    for _ in range(4):
+        o, r, d, info = env.step({'robot': rng.uniform(-1, 1, size=(2, 7)), 'human': np.full((2, 4), 1.0)})
+    q1 = np.stack([np.atleast_2d(h.get_joint_angles(env.human.controllable_joint_indices))[e] for e, h in enumerate(active)])
+    assert np.all(q1 - q0 > 0.01)                                           # a positive action turns every head joint
+    lo = np.array([active[0].lower_limits[j] for j in env.human.controllable_joint_indices])
+    hi = np.array([active[0].upper_limits[j] for j in env.human.controllable_joint_indices])
+    assert np.all(q1 >= lo - 1e-6) and np.all(q1 <= hi + 1e-6)
+    assert set(r) == {'robot', 'human'} and np.array_equal(r['robot'], r['human']) and set(d) == {'robot', 'human', '__all__'}
+    assert o['human'].shape == (2, 23) and np.all(np.isfinite(o['human'])) and np.allclose(o['human'][:, 10:14], q1, atol=1e-6)
+    # the robot part is what the single-agent env reports
+    assert np.allclose(o['robot'], env._get_obs('robot'))
+    assert info['robot']['action_human_len'] == 4 and info['robot']['obs_human_len'] == 23
+    env.close()
