@@ -26,7 +26,7 @@
 #define AG_CLOTH_MAXANCH 8
 #define AG_CLOTH_MAXCL 96        // collider links per env
 #define AG_CLOTH_MAXCOL 16       // link colours
-#define AG_CLOTH_HITS 12         // contacts one thread can find per substep (over its <= NPT nodes)
+#define AG_CLOTH_HITS 24         // contacts one thread can find per substep (over its <= NPT nodes)
 #define AG_CLOTH_EPS 1.1920929e-7f
 #define AG_CLOTH_CCF 8           // floats per exported contact: node, x, y, z, fx, fy, fz, link
 
@@ -63,13 +63,23 @@ struct ClothDev {
 struct ClothContact { f3 n; float offset, c3, c4; f3 acc; int node, link; };
 
 // signed distance of a point (link frame) to the union of the link's colliders, outward normal of the nearest one
-AG_HDN inline float cloth_sdf_link(const SimDev& S, int link, f3 p, f3& nrm) {
+// (colliders whose bounding box is farther than `reach` from the point are skipped: they cannot produce a distance below `reach`,
+//  and only distances below the collision margin matter to the caller -- a link of the wheelchair is 44 hulls, one of PR2's up to 100 planes)
+AG_HDN inline float cloth_sdf_link(const SimDev& S, int link, f3 p, f3& nrm, float reach = 1e30f) {
   int c0 = AG_LDG(S.link_col0 + link), nc = AG_LDG(S.link_ncol + link);
   float best = 1e30f;
   nrm = f3(0.f, 0.f, 1.f);
   for (int c = c0; c < c0 + nc; c++) {
     int type = AG_LDG(S.col_type + c), v0 = AG_LDG(S.col_v0 + c);
     float r = AG_LDG(S.col_radius + c), d; f3 n;
+    f3 bq(0.f, 0.f, 0.f);                     // signed per-axis distance of the point to the core's bounding box (link frame)
+    if (type != 3) {
+      f3 bc = tv3(S.col_center, c), bh = tv3(S.col_half, c);
+      bq = f3(fabsf(p.x - bc.x) - bh.x, fabsf(p.y - bc.y) - bh.y, fabsf(p.z - bc.z) - bh.z);
+      float lim = reach + r;
+      if (type == 2) { if (fmaxf(bq.x, fmaxf(bq.y, bq.z)) > lim) continue; }        // hulls measure with planes: per-axis test (see below)
+      else { f3 qc = fmax3(bq, f3(0.f, 0.f, 0.f)); if (dot(qc, qc) > lim * lim) continue; }
+    }
     if (type == 0 /*sphere*/ || type == 1 /*capsule*/) {
       f3 a = tv3(S.verts, v0), cp = a;
       if (type == 1) {
@@ -79,10 +89,18 @@ AG_HDN inline float cloth_sdf_link(const SimDev& S, int link, f3 p, f3& nrm) {
       }
       f3 w = p - cp; float L = norm(w);
       d = L - r; n = L > 1e-12f ? w * (1.f / L) : f3(0.f, 0.f, 1.f);
-    } else {                         // hull / half-space: the face plane the point is farthest outside of (exact inside)
+    } else {
+      // hull / half-space: the plane the point is farthest outside of -- the hull's face planes and, for hulls, the six planes of
+      // the core's bounding box (the box contains the hull, so this only tightens the lower bound outside and changes nothing inside)
       int p0 = AG_LDG(S.col_p0 + c), np = AG_LDG(S.col_np + c);
       float m = -1e30f; n = f3(0.f, 0.f, 1.f);
       for (int k = p0; k < p0 + np; k++) { f3 pn; float pd; ld_plane(S.planes, k, pn, pd); float s = dot(pn, p) - pd; if (s > m) { m = s; n = pn; } }
+      if (type == 2) {
+        f3 bc = tv3(S.col_center, c);
+        if (bq.x > m) { m = bq.x; n = f3(p.x >= bc.x ? 1.f : -1.f, 0.f, 0.f); }
+        if (bq.y > m) { m = bq.y; n = f3(0.f, p.y >= bc.y ? 1.f : -1.f, 0.f); }
+        if (bq.z > m) { m = bq.z; n = f3(0.f, 0.f, p.z >= bc.z ? 1.f : -1.f); }
+      }
       d = m - r;
     }
     if (d < best) { best = d; nrm = n; }
@@ -112,7 +130,7 @@ AG_HD bool cloth_detect(const SimDev& S, const ClothDev& C, const ClothLinkPose&
   if (!(P.br > 0.f) || dot(w, w) > P.br * P.br) return false;
   int link = AG_LDG(C.cl_link + L);
   f3 nl;
-  float dst = cloth_sdf_link(S, link, mulT(P.R, x - P.pos), nl) - C.margin;
+  float dst = cloth_sdf_link(S, link, mulT(P.R, x - P.pos), nl, C.margin) - C.margin;
   if (!(dst < 0.f)) return false;
   c.n = mul(P.R, nl);
   c.offset = -dot(c.n, x - c.n * dst);

@@ -1095,7 +1095,7 @@ int ag_cloth_init(AgSim* s, const AgClothDesc* d) {
   if (!C.cc_data || !C.overflow || !s->C_dev || !C.snap || !C.v) return fail("ag_cloth_init: device allocation failed");
   if (h2d(s, s->C_dev, &C, sizeof(ClothDev))) return -1;
   { const char* qs = getenv("AG_CLOTH_QS"); s->cloth_qs = qs ? atoi(qs) != 0 : 1; }
-  if (s->cloth_npt == 8 && s->cloth_qs && (size_t)C.maxcc > 512) s->cloth_qs = 0;          // 2 x 128 KB of node arrays leave no room for a big pool
+  if (s->cloth_qs && cloth_smem_bytes(s) > 227 * 1024) s->cloth_qs = 0;          // the second node array does not fit next to a big contact pool: q / v in registers
 #ifndef AG_CPU_EMU
   size_t smem = cloth_smem_bytes(s);
   if (smem > 227 * 1024) return fail("ag_cloth_init: cloth + contact budget exceed 227 KB of shared memory");

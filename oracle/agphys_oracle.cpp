@@ -43,6 +43,7 @@ struct Scene {
   std::vector<real> link_mass, link_lower, link_upper, link_damping, link_friction;
   std::vector<int> col_link, col_type, col_v0, col_nv, col_p0, col_np;
   std::vector<real> col_radius, col_thresh;
+  std::vector<V3> col_center, col_half;     // local bounding box of each collider's core (link frame)
   real max_thresh;
   std::vector<V3> verts;
   std::vector<real> planes;  // 4 per plane
@@ -139,7 +140,7 @@ void ingest(Scene& s, const AgSceneDesc* d) {
   s.col_v0.assign(d->col_v0, d->col_v0 + s.nc); s.col_nv.assign(d->col_nv, d->col_nv + s.nc);
   s.col_p0.assign(d->col_p0, d->col_p0 + s.nc); s.col_np.assign(d->col_np, d->col_np + s.nc);
   s.max_thresh = 0;
-  for (int i = 0; i < s.nc; i++) { s.col_radius.push_back((real)d->col_radius[i]); s.col_thresh.push_back((real)d->col_thresh[i]); s.max_thresh = std::max(s.max_thresh, (real)d->col_thresh[i]); }
+  for (int i = 0; i < s.nc; i++) { s.col_center.push_back(rd3(d->col_center, i)); s.col_half.push_back(rd3(d->col_half, i)); s.col_radius.push_back((real)d->col_radius[i]); s.col_thresh.push_back((real)d->col_thresh[i]); s.max_thresh = std::max(s.max_thresh, (real)d->col_thresh[i]); }
   for (int i = 0; i < s.nv; i++) s.verts.push_back(rd3(d->verts, i));
   for (int i = 0; i < 4 * s.np; i++) s.planes.push_back((real)d->planes[i]);
   s.pair_link.assign(d->pair_link, d->pair_link + 2 * s.npair);

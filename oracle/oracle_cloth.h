@@ -55,11 +55,23 @@ inline real ocloth_sdf_collider(const Scene& s, const Env& e, int c, V3 p, V3& n
     n = L > (real)1e-12 ? w * (1 / L) : V3(0, 0, 1);
     return L - r;
   }
+  // hulls / the ground plane: the plane the point is farthest outside of (exact inside, a lower bound of the distance outside);
+  // for hulls the six planes of the core's bounding box (link frame) take part as well
   real m = -1e30; n = V3(0, 0, 1);
   for (int k = s.col_p0[c]; k < s.col_p0[c] + s.col_np[c]; k++) {
     V3 pn(e.wplanes[4 * k], e.wplanes[4 * k + 1], e.wplanes[4 * k + 2]);
     real d = dot(pn, p) - e.wplanes[4 * k + 3];
     if (d > m) { m = d; n = pn; }
+  }
+  if (s.col_type[c] == AG_COL_HULL) {
+    int link = s.col_link[c];
+    Quat lq = e.lquat[link];
+    V3 pl = qrot(qconj(lq), p - e.lpos[link]);
+    for (int a = 0; a < 3; a++) {
+      real side = pl[a] >= s.col_center[c][a] ? 1 : -1;
+      real d = std::fabs(pl[a] - s.col_center[c][a]) - s.col_half[c][a];
+      if (d > m) { m = d; V3 ax; ax[a] = side; n = qrot(lq, ax); }
+    }
   }
   return m - r;
 }
