@@ -31,6 +31,32 @@ def _edge_colouring(links, n_nodes):
     return col
 
 
+def _bank_friendly(L):
+    """Order (and orient) the independent links of one colour so that every aligned group of 8 consecutive links touches 8 different
+    16-byte bank groups of shared memory on the i side and on the j side (node index mod 8): a quarter-warp then reads / writes its 8
+    float4 positions in one wavefront.  Greedy first fit; relaxing a link is symmetric in its two nodes, so orientation is free."""
+    rem = [tuple(int(v) for v in x) for x in L]
+    out = []
+    while rem:
+        ua = ub = 0
+        group, keep = [], []
+        for (i, j) in rem:
+            if len(group) < 8:
+                a, b = i & 7, j & 7
+                if not (ua >> a) & 1 and not (ub >> b) & 1:
+                    group.append((i, j)); ua |= 1 << a; ub |= 1 << b
+                    continue
+                if not (ua >> b) & 1 and not (ub >> a) & 1:
+                    group.append((j, i)); ua |= 1 << b; ub |= 1 << a
+                    continue
+            keep.append((i, j))
+        while len(group) < 8 and keep:
+            group.append(keep.pop(0))
+        out += group
+        rem = keep
+    return np.array(out, dtype=np.int32).reshape(-1, 2)
+
+
 def _locality_order(x, links, n_nodes):
     """Breadth-first node order over the mesh graph from the node with the smallest x coordinate (ties: index): nodes that
     share a link get nearby internal indices, which keeps a warp's shared-memory accesses of one colour clustered."""
@@ -79,10 +105,12 @@ class ClothModel:
         links = links[np.lexsort((links[:, 1], links[:, 0]))]
         col = _edge_colouring(links, self.n_nodes)
         idx = np.lexsort((links[:, 1], links[:, 0], col))                   # colour-major, then by nodes
-        self.links = np.ascontiguousarray(links[idx])
+        links = links[idx]
         self.link_colour = col[idx]
         self.n_colours = int(col.max()) + 1
         self.colour_off = np.searchsorted(self.link_colour, np.arange(self.n_colours + 1)).astype(np.int32)
+        # within a colour the order is free (the links share no node): arrange it for conflict-free shared-memory access
+        self.links = np.ascontiguousarray(np.concatenate([_bank_friendly(links[self.colour_off[c]:self.colour_off[c + 1]]) for c in range(self.n_colours)]))
         xr = self.rest[self.order]
         d = xr[self.links[:, 1]] - xr[self.links[:, 0]]
         self.link_rest2 = np.einsum('ij,ij->i', d, d)                       # Bullet m_c1 = rest length squared

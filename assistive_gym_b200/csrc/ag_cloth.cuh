@@ -36,7 +36,8 @@ struct ClothDev {
   int nn, nnp, nlinks, ncol, nanch, ncl, maxcc, K, piters, export_contacts;
   float dt, im, kLSTh, kDP, kDG, kLF, kDF, kCHR, kKHR, kAHR, margin, density;
   float gx, gy, gz;
-  int col_off[AG_CLOTH_MAXCOL + 1];
+  int col_off[AG_CLOTH_MAXCOL + 1];          // colour c = links [col_off[c], col_off[c + 1]) of link_ij / link_rest2 (list order)
+  int tab_off[AG_CLOTH_MAXCOL], tab_end[AG_CLOTH_MAXCOL];   // the same colour inside link_tab: starts aligned to 32 entries (aligned quarter-warps)
   int anch_node[AG_CLOTH_MAXANCH];
   float anch_local[AG_CLOTH_MAXANCH][3];
   // template tables
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
       }
       __syncthreads();
       for (int col = 0; col < C.ncol; col++) {
-        for (int l = C.col_off[col] + t; l < C.col_off[col + 1]; l += T) {
+        for (int l = C.tab_off[col] + t; l < C.tab_end[col]; l += T) {
           uint2 lt = __ldg((const uint2*)(C.link_tab + l));
           unsigned ij = lt.x;
           float r2 = __uint_as_float(lt.y);

@@ -1079,8 +1079,13 @@ int ag_cloth_init(AgSim* s, const AgClothDesc* d) {
   for (int L = 0; L < d->n_col_links; L++) if (d->col_links[L] < 0 || d->col_links[L] >= s->nl) return fail("ag_cloth_init: bad collider link");
   C.link_ij = upload(s, lij); C.link_rest2 = upload(s, lr);
   {
-    std::vector<ClothLinkRec> tab(d->n_links);
-    for (int l = 0; l < d->n_links; l++) { tab[l].ij = lij[l]; tab[l].rest2 = lr[l]; }
+    std::vector<ClothLinkRec> tab;                    // every colour starts at a multiple of 32 entries
+    for (int c = 0; c < d->n_colours; c++) {
+      tab.resize((tab.size() + 31) / 32 * 32, ClothLinkRec{0u, 0.f});
+      C.tab_off[c] = (int)tab.size();
+      for (int l = C.col_off[c]; l < C.col_off[c + 1]; l++) tab.push_back(ClothLinkRec{lij[l], lr[l]});
+      C.tab_end[c] = (int)tab.size();
+    }
     C.link_tab = upload(s, tab);
   }
   C.nf_off = upload(s, std::vector<int>(d->nf_off, d->nf_off + nn + 1)); C.nf_pair = upload(s, nfp);
