@@ -19,16 +19,30 @@ DRESSING_PARAMS = dict(kLST=0.055, kDP=0.01, kDG=10.0, kLF=0.0, kDF=0.39, kCHR=1
                        margin=0.04, air_density=1.2, total_mass=0.16)
 
 
-def _edge_colouring(links, n_nodes):
-    """Greedy edge colouring in list order: smallest colour not used at either end node.  Deterministic."""
-    used = np.zeros((n_nodes, 64), dtype=bool)
-    col = np.empty(len(links), dtype=np.int32)
-    for i, (a, b) in enumerate(links):
-        free = ~(used[a] | used[b])
-        c = int(np.argmax(free))
-        col[i] = c
-        used[a, c] = used[b, c] = True
-    return col
+def _edge_colouring(links, n_nodes, cap=1024):
+    """Balanced greedy edge colouring in list order: among the colours not used at either end node, the one holding the fewest links.
+    The number of colours K starts at max(maximum node degree, ceil(links / cap)) and grows until every colour holds <= `cap` links:
+    the CUDA kernel relaxes a colour with one link per thread of a 1024-thread CTA, so the gown's 11 640 links become 12 colours of
+    970 = 12 passes of the block (a first-fit colouring gives 10 colours, six of them with ~1 900 links = 16 passes).  Deterministic."""
+    deg = np.bincount(np.asarray(links).ravel(), minlength=n_nodes)
+    K = max(int(deg.max()), -(-len(links) // cap), 1)
+    while True:
+        used = np.zeros((n_nodes, K), dtype=bool)
+        count = np.zeros(K, dtype=np.int64)
+        col = np.empty(len(links), dtype=np.int32)
+        ok = True
+        for i, (a, b) in enumerate(links):
+            free = ~(used[a] | used[b]) & (count < cap)
+            if not free.any():
+                ok = False
+                break
+            c = int(np.argmin(np.where(free, count, 1 << 60)))
+            col[i] = c
+            used[a, c] = used[b, c] = True
+            count[c] += 1
+        if ok:
+            return col
+        K += 1
 
 
 def _bank_friendly(L):

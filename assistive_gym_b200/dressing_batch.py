@@ -108,6 +108,12 @@ class DressingBatch:
         self.anchor_local = x_zero[CLOTH_ANCHORS] - CLOTH_ORIG_POS
         self.x_zero = x_zero
 
+    @staticmethod
+    def config(**kw):
+        """AgConfig of the task: numSubSteps = 8 (dressing.py:184); a larger contact budget than the default, because the seated person's
+        arm and the robot's arm sweep past the wheelchair's 44 hulls (the candidate-pair budget is 4 x max_contacts)."""
+        return capi.default_config(**dict(dict(num_substeps=8, max_contacts=256), **kw))
+
     # ------------------------------------------------------------------ params of the fused step
     def dressing_params(self):
         P = capi.AgDressingParams()

@@ -17,7 +17,7 @@ class DressingEnv(AssistiveEnv):
                          obs_robot_len=(17 + len(robot.controllable_joint_indices) - (len(robot.wheel_joint_indices) if robot.mobile else 0)),
                          obs_human_len=(18 + len(human.controllable_joint_indices)))
         self._db = DressingBatch()
-        self._cfg = config or capi.default_config(num_substeps=8)          # dressing.py:184
+        self._cfg = config or DressingBatch.config()                       # numSubSteps = 8 (dressing.py:184)
         self._toc_attempts = toc_attempts
         self._sim_lib = None
 

@@ -260,7 +260,7 @@ def run_dressing(args):
     from assistive_gym_b200.sim import BatchSim
     n, K, W = (args.batch if args.batch != BATCH_PER_GPU else 2048), args.steps, max(args.warmup, 3)
     db = DressingBatch()
-    cfg = capi.default_config(num_substeps=8)
+    cfg = DressingBatch.config()
     rng = np.random.default_rng(0)
     if args.impl == 'reference':
         from oracle.oracle_py import OracleSim

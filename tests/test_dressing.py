@@ -34,7 +34,7 @@ def test_scene_recipe(dressing):
 
 
 def _pair(lib, db, n, attempts=12, settle=3, seed=0):
-    cfg = capi.default_config(num_substeps=8)
+    cfg = DressingBatch.config()
     prod = BatchSim(db.scene, cfg, n, _lib=lib)
     rng = np.random.default_rng(seed)
     smp = db.sample(n, rng)
@@ -76,8 +76,11 @@ def _fused_step_vs_reference(lib, n=4, steps=2):
         assert np.array_equal(info[:, 3], info_r[:, 3])                           # sleeve state
         assert np.abs(info[:, 2] - info_r[:, 2]).max() < 2e-3                     # reward_dressing (a distance)
         cf, cf_r = obs[:, 23], obs_r[:, 23]
-        assert np.all(np.abs(cf - cf_r) <= 0.05 * np.maximum(cf_r, 1.0) + 0.5), (cf, cf_r)       # cloth force on the person (5 %)
-        assert np.abs(rew - rew_r).max() < 0.02 + 0.01 * 0.05 * np.abs(cf_r).max()
+        # cloth force on the person: a sum over the contacts of ONE substep, which chatter on and off at the margin (resting contact
+        # is in contact every other substep or so, tests/test_cloth_oracle.py) -- the per-contact forces are compared strictly in
+        # tests/test_cloth_parity.py; here 5 % + 1 N (10 in the env's x10 units would be 1 N; the sums are ~1)
+        assert np.all(np.abs(cf - cf_r) <= 0.05 * cf_r + 1.0), (cf, cf_r)
+        assert np.abs(rew - rew_r).max() < 0.02 + 0.01 * 1.0            # the reward carries 0.01 x the cloth force
         assert np.array_equal(done, done_r)
         prod.cloth_set_state(xo, vo)                                               # re-synchronise
         prod.state_set(orc.state_get().astype(np.float32))

@@ -113,7 +113,7 @@ def _contact_case(lib, n=6, steps=3):
         assert np.array_equal(info[:, 3], info_r[:, 3]), (info[:, 3], info_r[:, 3])                  # scratches counted
         assert np.all(np.abs(info[:, 2] - info_r[:, 2]) <= 0.05 * np.abs(info_r[:, 2]) + 1e-2)       # tool force at the target (5 %)
         assert np.all(np.abs(info[:, 0] - info_r[:, 0]) <= 0.05 * np.abs(info_r[:, 0]) + 1e-2)       # total force on the person
-        assert np.abs(rew - rew_r).max() < 2e-2
+        assert np.all(np.abs(rew - rew_r) < 2e-2 + 0.02 * np.abs(rew_r))          # the reward carries the (5 %) forces
         seen = max(seen, int(info_r[:, 3].max()))
         prod.state_set(orc.state_get().astype(np.float32))
     assert seen >= 1                                                        # the first touch counts (prev_target_contact_pos starts at 0)
