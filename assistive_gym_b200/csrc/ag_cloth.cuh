@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
   float4* xs = (float4*)cl_smem;                               // [NPT * T]
   float* lk = cl_smem + 4 * NPT * T;                           // [ncl][16]  R, pos, bounding sphere
   float* pool = lk + 16 * AG_CLOTH_MAXCL;                      // [maxcc][12] n, offset | c3, c4, node, link | acc, -
-  int* misc = (int*)(pool + 12 * C.maxcc);                     // [40] warp sums for the scan, total
+  int* misc = (int*)(pool + 12 * C.maxcc);                     // [40] warp sums for the scan [0..31], total [32], active-link masks [34..36]
   float* wbox = (float*)(misc + 40);                           // [32][6] per-warp bounding boxes of the predicted nodes
   float4* qs = (float4*)(wbox + 192);                          // [NPT * T] (QS only)
   const int nn = C.nn;
@@ -296,16 +296,21 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
     }
     __syncthreads();                                           // every normal is computed, the warp boxes are written
     // ---- collider link poses of this substep; a link whose bounding sphere misses the cloth's box is skipped by everyone
-    if (t < C.ncl) {
-      ClothLinkPose P = cloth_link_pose(C, sub, t, N, e);
-      float* o = lk + 16 * t;
+    if (t < AG_CLOTH_MAXCL) {                                  // warps 0..2, whole warps
+      bool on = false;
+      if (t < C.ncl) {
+        ClothLinkPose P = cloth_link_pose(C, sub, t, N, e);
+        float* o = lk + 16 * t;
 #pragma unroll
-      for (int a = 0; a < 9; a++) o[a] = P.R.m[a];
-      f3 lo(1e30f, 1e30f, 1e30f), hi(-1e30f, -1e30f, -1e30f);
-      for (int w = 0; w < T / 32; w++) { lo = fmin3(lo, f3(wbox[6 * w], wbox[6 * w + 1], wbox[6 * w + 2])); hi = fmax3(hi, f3(wbox[6 * w + 3], wbox[6 * w + 4], wbox[6 * w + 5])); }
-      f3 cp = fmax3(lo, fmin3(hi, P.bc)) - P.bc;               // box point nearest to the sphere centre
-      bool on = cloth_link_active(S, C, t, N, e) && dot(cp, cp) <= P.br * P.br;
-      o[9] = P.pos.x; o[10] = P.pos.y; o[11] = P.pos.z; o[12] = P.bc.x; o[13] = P.bc.y; o[14] = P.bc.z; o[15] = on ? P.br : 0.f;
+        for (int a = 0; a < 9; a++) o[a] = P.R.m[a];
+        f3 lo(1e30f, 1e30f, 1e30f), hi(-1e30f, -1e30f, -1e30f);
+        for (int w = 0; w < T / 32; w++) { lo = fmin3(lo, f3(wbox[6 * w], wbox[6 * w + 1], wbox[6 * w + 2])); hi = fmax3(hi, f3(wbox[6 * w + 3], wbox[6 * w + 4], wbox[6 * w + 5])); }
+        f3 cp = fmax3(lo, fmin3(hi, P.bc)) - P.bc;             // box point nearest to the sphere centre
+        on = cloth_link_active(S, C, t, N, e) && dot(cp, cp) <= P.br * P.br;
+        o[9] = P.pos.x; o[10] = P.pos.y; o[11] = P.pos.z; o[12] = P.bc.x; o[13] = P.bc.y; o[14] = P.bc.z; o[15] = on ? P.br : 0.f;
+      }
+      unsigned bits = __ballot_sync(0xffffffffu, on);          // the surviving links as bit masks: the node loop visits only those
+      if ((t & 31) == 0) misc[34 + (t >> 5)] = (int)bits;
     }
     // ---- publish the prediction
 #pragma unroll
@@ -320,16 +325,20 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
         bool anchored = false;
         for (int a = 0; a < C.nanch; a++) anchored |= C.anch_node[a] == i;
         if (!anchored) {
-          for (int L = 0; L < C.ncl; L++) {
-            const float* o = lk + 16 * L;
-            if (!(o[15] > 0.f)) continue;
-            f3 w = xn[k] - f3(o[12], o[13], o[14]);
-            if (dot(w, w) > o[15] * o[15]) continue;
-            ClothLinkPose P;
-            for (int a = 0; a < 9; a++) P.R.m[a] = o[a];
-            P.pos = f3(o[9], o[10], o[11]); P.bc = f3(o[12], o[13], o[14]); P.br = o[15];
-            ClothContact c;
-            if (cloth_detect(S, C, P, L, N, e, xn[k], getq(k, i), c)) { if (nh < AG_CLOTH_HITS) hits[nh++] = (k << 8) | L; else over = true; }
+          for (int w = 0; w < AG_CLOTH_MAXCL / 32; w++) {
+            unsigned m = (unsigned)misc[34 + w];
+            while (m) {                                          // ascending link index, as the sequential sweep visits them
+              int L = (w << 5) + __ffs(m) - 1;
+              m &= m - 1;
+              const float* o = lk + 16 * L;
+              f3 wv = xn[k] - f3(o[12], o[13], o[14]);
+              if (dot(wv, wv) > o[15] * o[15]) continue;
+              ClothLinkPose P;
+              for (int a = 0; a < 9; a++) P.R.m[a] = o[a];
+              P.pos = f3(o[9], o[10], o[11]); P.bc = f3(o[12], o[13], o[14]); P.br = o[15];
+              ClothContact c;
+              if (cloth_detect(S, C, P, L, N, e, xn[k], getq(k, i), c)) { if (nh < AG_CLOTH_HITS) hits[nh++] = (k << 8) | L; else over = true; }
+            }
           }
         }
       }
@@ -392,9 +401,15 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
         r[8] = acc.x; r[9] = acc.y; r[10] = acc.z;
       }
       __syncthreads();
+      // the first record of a colour is fetched while the previous colour is relaxed (the table lives in L2: the contact pool and
+      // the node arrays leave the L1 too small for it)
+      uint2 nxt = make_uint2(0u, 0u);
+      if (C.tab_off[0] + t < C.tab_end[0]) nxt = __ldg((const uint2*)(C.link_tab + C.tab_off[0] + t));
       for (int col = 0; col < C.ncol; col++) {
-        for (int l = C.tab_off[col] + t; l < C.tab_end[col]; l += T) {
-          uint2 lt = __ldg((const uint2*)(C.link_tab + l));
+        uint2 lt = nxt;
+        int l = C.tab_off[col] + t;
+        if (col + 1 < C.ncol && C.tab_off[col + 1] + t < C.tab_end[col + 1]) nxt = __ldg((const uint2*)(C.link_tab + C.tab_off[col + 1] + t));
+        for (; l < C.tab_end[col]; l += T) {
           unsigned ij = lt.x;
           float r2 = __uint_as_float(lt.y);
           int i = ij & 0xffffu, j = ij >> 16;
@@ -402,6 +417,7 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
           f3 a(a4.x, a4.y, a4.z), b(b4.x, b4.y, b4.z);
           cloth_link_solve(a, b, r2, C.kLSTh);
           xs[i] = make_float4(a.x, a.y, a.z, 0.f); xs[j] = make_float4(b.x, b.y, b.z, 0.f);
+          if (l + T < C.tab_end[col]) lt = __ldg((const uint2*)(C.link_tab + l + T));      // colours larger than the block (other meshes)
         }
         __syncthreads();
       }

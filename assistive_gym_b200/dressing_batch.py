@@ -238,6 +238,10 @@ class DressingBatch:
         if settle_steps:
             sim.step(settle_steps)
         sim.cloth_set_gravity([0, 0, -9.81])
+        # the gown is created flat and partly INSIDE the seated person (dressing.py:146 places it relative to the gripper only): in the
+        # first substeps of the settle a few per cent of the envs hold more cloth contacts than the 1 024-contact budget; reported
+        # separately from the steady-state flag, which the caller reads after its own steps
+        self.settle_overflow = int(sim.overflow_count()) if hasattr(sim, 'overflow_count') else 0
         return s
 
     def start_fused(self, sim, sample=None):

@@ -344,7 +344,7 @@ def run_dressing(args):
                                  'reset_s': reset_s, 'toc_attempts': args.toc_attempts, 'goals_reached_mean': float(np.mean(db.goals_reached)), 'base_unresolved': int(db.unresolved),
                                  'cloth_contacts_per_env': {'mean': float(ccnt.mean()), 'p99': float(np.percentile(ccnt, 99)), 'max': int(ccnt.max())},
                                  'rigid_contacts_per_env': {'mean': float(rcnt.mean()), 'max': int(rcnt.max())},
-                                 'envs_over_budget': int(sim.overflow_count()),
+                                 'envs_over_budget': int(sim.overflow_count()), 'envs_over_budget_during_settle': int(db.settle_overflow),
                                  'sleeve_state_counts': {str(k_): int((info_h[:, 3] == k_).sum()) for k_ in (0, 1, 2, 3)},
                                  'cloth_force_mean_N': float(obs[:, 23].mean().item())},
                       'clocks': clk, 'e2e': {'value': e2e, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n * 7 * 4, 'd2h_bytes_per_step': n * 30 * 4},
