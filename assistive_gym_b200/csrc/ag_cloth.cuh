@@ -66,12 +66,13 @@ struct ClothContact { f3 n; float offset, c3, c4; f3 acc; int node, link; };
 // signed distance of a point (link frame) to the union of the link's colliders, outward normal of the nearest one
 // (colliders whose bounding box is farther than `reach` from the point are skipped: they cannot produce a distance below `reach`,
 //  and only distances below the collision margin matter to the caller -- a link of the wheelchair is 44 hulls, one of PR2's up to 100 planes)
-AG_HDN inline float cloth_sdf_link(const SimDev& S, int link, f3 p, f3& nrm, float reach = 1e30f) {
+AG_HDN inline float cloth_sdf_link(const SimDev& S, int link, f3 p, f3& nrm, float reach = 1e30f, unsigned long long cmask = ~0ull) {
   int c0 = AG_LDG(S.link_col0 + link), nc = AG_LDG(S.link_ncol + link);
   float best = 1e30f;
   nrm = f3(0.f, 0.f, 1.f);
   for (int c = c0; c < c0 + nc; c++) {
     int type = AG_LDG(S.col_type + c), v0 = AG_LDG(S.col_v0 + c);
+    if (c - c0 < 64 && !((cmask >> (c - c0)) & 1ull)) continue;      // culled for the caller's whole warp (k_cloth)
     float r = AG_LDG(S.col_radius + c), d; f3 n;
     f3 bq(0.f, 0.f, 0.f);                     // signed per-axis distance of the point to the core's bounding box (link frame)
     if (type != 3) {
@@ -126,12 +127,12 @@ AG_HD bool cloth_link_active(const SimDev& S, const ClothDev& C, int L, int N, i
 }
 
 // node vs collider link L (Bullet btSoftColliders::CollideSDF_RS::DoNode + btSoftBody::checkContact, static shape)
-AG_HD bool cloth_detect(const SimDev& S, const ClothDev& C, const ClothLinkPose& P, int L, int N, int e, f3 x, f3 q, ClothContact& c) {
+AG_HD bool cloth_detect(const SimDev& S, const ClothDev& C, const ClothLinkPose& P, int L, int N, int e, f3 x, f3 q, ClothContact& c, unsigned long long cmask = ~0ull) {
   f3 w = x - P.bc;
   if (!(P.br > 0.f) || dot(w, w) > P.br * P.br) return false;
   int link = AG_LDG(C.cl_link + L);
   f3 nl;
-  float dst = cloth_sdf_link(S, link, mulT(P.R, x - P.pos), nl, C.margin) - C.margin;
+  float dst = cloth_sdf_link(S, link, mulT(P.R, x - P.pos), nl, C.margin, cmask) - C.margin;
   if (!(dst < 0.f)) return false;
   c.n = mul(P.R, nl);
   c.offset = -dot(c.n, x - c.n * dst);
@@ -316,28 +317,60 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
 #pragma unroll
     for (int k = 0; k < NPT; k++) { int i = k * T + t; if (i < nn) xs[i] = make_float4(xn[k].x, xn[k].y, xn[k].z, 0.f); }
     __syncthreads();
-    // ---- find contacts of own nodes
+    // ---- find contacts of own nodes.  The 32 nodes a warp handles in one pass are neighbours on the mesh (breadth-first node
+    // order), so links -- and, for links made of many hulls (the wheelchair: 44), colliders -- are first culled against the bounding
+    // sphere of the warp's nodes, the lanes testing one collider each; every branch around the ballots is warp-uniform
     int hits[AG_CLOTH_HITS]; int nh = 0; bool over = false;
 #pragma unroll
     for (int k = 0; k < NPT; k++) {
-      int i = k * T + t;
-      if (i < nn) {
-        bool anchored = false;
-        for (int a = 0; a < C.nanch; a++) anchored |= C.anch_node[a] == i;
-        if (!anchored) {
-          for (int w = 0; w < AG_CLOTH_MAXCL / 32; w++) {
-            unsigned m = (unsigned)misc[34 + w];
-            while (m) {                                          // ascending link index, as the sequential sweep visits them
-              int L = (w << 5) + __ffs(m) - 1;
-              m &= m - 1;
-              const float* o = lk + 16 * L;
-              f3 wv = xn[k] - f3(o[12], o[13], o[14]);
-              if (dot(wv, wv) > o[15] * o[15]) continue;
-              ClothLinkPose P;
-              for (int a = 0; a < 9; a++) P.R.m[a] = o[a];
-              P.pos = f3(o[9], o[10], o[11]); P.bc = f3(o[12], o[13], o[14]); P.br = o[15];
+      const int i = k * T + t;
+      bool valid = i < nn;
+      if (valid) for (int a = 0; a < C.nanch; a++) valid &= C.anch_node[a] != i;
+      f3 lo = valid ? xn[k] : f3(1e30f, 1e30f, 1e30f), hi = valid ? xn[k] : f3(-1e30f, -1e30f, -1e30f);
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, d)); lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, d)); lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, d));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, d)); hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, d)); hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, d));
+      }
+      if (!(hi.x >= lo.x)) continue;                                  // no node of this warp in this pass
+      const f3 wc = (lo + hi) * 0.5f; const float wr = 0.5f * norm(hi - lo) + 1e-6f;
+      for (int w = 0; w < AG_CLOTH_MAXCL / 32; w++) {
+        unsigned m = (unsigned)misc[34 + w];
+        while (m) {                                                   // ascending link index, as the sequential sweep visits them
+          const int L = (w << 5) + __ffs(m) - 1;
+          m &= m - 1;
+          const float* o = lk + 16 * L;
+          { f3 dv = wc - f3(o[12], o[13], o[14]); float rr = o[15] + wr; if (dot(dv, dv) > rr * rr) continue; }
+          ClothLinkPose P;
+          for (int a = 0; a < 9; a++) P.R.m[a] = o[a];
+          P.pos = f3(o[9], o[10], o[11]); P.bc = f3(o[12], o[13], o[14]); P.br = o[15];
+          unsigned long long cmask = ~0ull;
+          const int link = __ldg(C.cl_link + L), nc = __ldg(S.link_ncol + link);
+          if (nc > 2) {
+            const f3 pl = mulT(P.R, wc - P.pos);
+            const int c0 = __ldg(S.link_col0 + link);
+            cmask = 0ull;
+            for (int r = 0; r < 2; r++) {
+              int c = c0 + r * 32 + (t & 31);
+              bool ok = false;
+              if (c < c0 + nc) {
+                if (__ldg(S.col_type + c) == 3) ok = true;
+                else {
+                  f3 bc = tv3(S.col_center, c), bh = tv3(S.col_half, c);
+                  f3 qd = fmax3(f3(fabsf(pl.x - bc.x) - bh.x, fabsf(pl.y - bc.y) - bh.y, fabsf(pl.z - bc.z) - bh.z), f3(0.f, 0.f, 0.f));
+                  float lim = wr + C.margin + __ldg(S.col_radius + c);
+                  ok = dot(qd, qd) <= lim * lim;
+                }
+              }
+              cmask |= (unsigned long long)__ballot_sync(0xffffffffu, ok) << (32 * r);
+            }
+            if (cmask == 0ull && nc <= 64) continue;
+          }
+          if (valid) {
+            f3 wv = xn[k] - P.bc;
+            if (dot(wv, wv) <= P.br * P.br) {
               ClothContact c;
-              if (cloth_detect(S, C, P, L, N, e, xn[k], getq(k, i), c)) { if (nh < AG_CLOTH_HITS) hits[nh++] = (k << 8) | L; else over = true; }
+              if (cloth_detect(S, C, P, L, N, e, xn[k], getq(k, i), c, cmask)) { if (nh < AG_CLOTH_HITS) hits[nh++] = (k << 8) | L; else over = true; }
             }
           }
         }

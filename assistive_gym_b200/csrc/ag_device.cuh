@@ -580,11 +580,14 @@ AG_HD SVf sv_scale(SVf a, float s) { SVf r; r.a = a.a * s; r.l = a.l * s; return
 AG_HD float sv_dot(SVf m, SVf f) { return dot(m.a, f.a) + dot(m.l, f.l); }
 
 // One lane per env: free bodies (gravity, damping, gyroscopic) and articulated bodies (ABA + M^-1).
-AG_HDN inline void dyn_body(int e, const SimDev& S, const KP&) {
+// thread = (work item, env): work items 0..nf-1 are the free bodies, nf..nf+nart-1 the articulated bodies (independent of each other)
+AG_HDN inline void dyn_body(int tid, const SimDev& S, const KP&) {
   const int N = S.N;
+  const int e = tid % N, work = tid / N;
   const float dt = S.dt, vmax = S.vmax, kl = S.lin_damp, ka = S.ang_damp;
   // ---- free rigid bodies
-  for (int f = 0; f < S.nf; f++) {
+  if (work < S.nf) {
+    const int f = work;
     int b = AG_LDG(S.free_body + f);
     int l0 = AG_LDG(S.body_link0 + b);
     q4 q = ld4(S.lquat, l0, N, e);
@@ -593,7 +596,7 @@ AG_HDN inline void dyn_body(int e, const SimDev& S, const KP&) {
     size_t ib = (size_t)f * 6 * N + e;
     if (S.body_mode[(size_t)b * N + e] != 1) {
       for (int i = 0; i < 6; i++) S.fIinv[ib + (size_t)i * N] = 0.f;
-      continue;
+      return;
     }
     m3 R = qmat(qmul(q, tv4(S.link_iquat, l0)));
     f3 Id = tv3(S.link_inertia, l0);
@@ -613,9 +616,11 @@ AG_HDN inline void dyn_body(int e, const SimDev& S, const KP&) {
     st3(S.base_lin, b, N, e, v); st3(S.base_ang, b, N, e, w);
     S.fIinv[ib] = Iinv.xx; S.fIinv[ib + N] = Iinv.yy; S.fIinv[ib + 2 * (size_t)N] = Iinv.zz;
     S.fIinv[ib + 3 * (size_t)N] = Iinv.xy; S.fIinv[ib + 4 * (size_t)N] = Iinv.xz; S.fIinv[ib + 5 * (size_t)N] = Iinv.yz;
+    return;
   }
   // ---- articulated bodies
-  for (int a = 0; a < S.nart; a++) {
+  {
+    const int a = work - S.nf;
     int b = AG_LDG(S.art_body + a), d0 = AG_LDG(S.art_dl0 + a), nd = AG_LDG(S.art_nd + a);
     bool active = S.body_mode[(size_t)b * N + e] == 1;
     AI IA[AG_MAXND]; SVf pA[AG_MAXND], U[AG_MAXND], c[AG_MAXND], vel[AG_MAXND];

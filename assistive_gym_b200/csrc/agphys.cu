@@ -750,7 +750,7 @@ static void substep(AgSim* s) {
   LAUNCH(s, k_csort, (size_t)S.maxcand * N, z);
   LAUNCH(s, k_narrow, (size_t)S.maxcand * N, z);
   LAUNCH(s, k_sort, (size_t)S.maxraw * N, z);
-  LAUNCH(s, k_dyn, N, z);
+  LAUNCH(s, k_dyn, (size_t)(S.nf + S.nart) * N, z);
   LAUNCH(s, k_rows, N, z);
   LAUNCH(s, k_crows, (size_t)(S.maxc + 3 * S.ND + S.ngr) * N, z);
 #ifndef AG_CPU_EMU
