@@ -321,8 +321,10 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
     // order), so links -- and, for links made of many hulls (the wheelchair: 44), colliders -- are first culled against the bounding
     // sphere of the warp's nodes, the lanes testing one collider each; every branch around the ballots is warp-uniform
     int hits[AG_CLOTH_HITS]; int nh = 0; bool over = false;
+    const bool any_link = (misc[34] | misc[35] | misc[36]) != 0;      // block-uniform
 #pragma unroll
     for (int k = 0; k < NPT; k++) {
+      if (!any_link) break;
       const int i = k * T + t;
       bool valid = i < nn;
       if (valid) for (int a = 0; a < C.nanch; a++) valid &= C.anch_node[a] != i;
@@ -335,12 +337,21 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
       if (!(hi.x >= lo.x)) continue;                                  // no node of this warp in this pass
       const f3 wc = (lo + hi) * 0.5f; const float wr = 0.5f * norm(hi - lo) + 1e-6f;
       for (int w = 0; w < AG_CLOTH_MAXCL / 32; w++) {
+        // the lanes test 32 links at once against the warp's sphere; only the survivors are visited
         unsigned m = (unsigned)misc[34 + w];
+        {
+          bool near = false;
+          if ((m >> (t & 31)) & 1u) {
+            const float* o = lk + 16 * ((w << 5) + (t & 31));
+            f3 dv = wc - f3(o[12], o[13], o[14]); float rr = o[15] + wr;
+            near = dot(dv, dv) <= rr * rr;
+          }
+          m = __ballot_sync(0xffffffffu, near);
+        }
         while (m) {                                                   // ascending link index, as the sequential sweep visits them
           const int L = (w << 5) + __ffs(m) - 1;
           m &= m - 1;
           const float* o = lk + 16 * L;
-          { f3 dv = wc - f3(o[12], o[13], o[14]); float rr = o[15] + wr; if (dot(dv, dv) > rr * rr) continue; }
           ClothLinkPose P;
           for (int a = 0; a < 9; a++) P.R.m[a] = o[a];
           P.pos = f3(o[9], o[10], o[11]); P.bc = f3(o[12], o[13], o[14]); P.br = o[15];
