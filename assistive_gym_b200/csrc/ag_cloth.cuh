@@ -28,6 +28,7 @@
 #define AG_CLOTH_MAXCOL 16       // link colours
 #define AG_CLOTH_HITS 24         // contacts one thread can find per substep (over its <= NPT nodes)
 #define AG_CLOTH_EPS 1.1920929e-7f
+#define AG_CLOTH_LKS 24          // floats per collider link in shared memory: R 9, pos 3, bounding sphere 4, round shape: a 3, b 3, r, flag
 #define AG_CLOTH_CCF 8           // floats per exported contact: node, x, y, z, fx, fy, fz, link
 
 struct alignas(8) ClothLinkRec { unsigned ij; float rest2; };
@@ -126,15 +127,9 @@ AG_HD bool cloth_link_active(const SimDev& S, const ClothDev& C, int L, int N, i
   return S.body_mode[(size_t)AG_LDG(S.link_body + AG_LDG(C.cl_link + L)) * N + e] != 0;
 }
 
-// node vs collider link L (Bullet btSoftColliders::CollideSDF_RS::DoNode + btSoftBody::checkContact, static shape)
-AG_HD bool cloth_detect(const SimDev& S, const ClothDev& C, const ClothLinkPose& P, int L, int N, int e, f3 x, f3 q, ClothContact& c, unsigned long long cmask = ~0ull) {
-  f3 w = x - P.bc;
-  if (!(P.br > 0.f) || dot(w, w) > P.br * P.br) return false;
-  int link = AG_LDG(C.cl_link + L);
-  f3 nl;
-  float dst = cloth_sdf_link(S, link, mulT(P.R, x - P.pos), nl, C.margin, cmask) - C.margin;
-  if (!(dst < 0.f)) return false;
-  c.n = mul(P.R, nl);
+// the contact record of a node at signed distance `dst` (margin already subtracted) from a shape with outward normal n
+AG_HD void cloth_contact_fill(const SimDev& S, const ClothDev& C, int L, int link, int N, int e, f3 x, f3 q, f3 n, float dst, ClothContact& c) {
+  c.n = n;
   c.offset = -dot(c.n, x - c.n * dst);
   f3 vr = x - q;                                   // va = 0 (static shape)
   float dn = dot(vr, c.n);
@@ -144,6 +139,29 @@ AG_HD bool cloth_detect(const SimDev& S, const ClothDev& C, const ClothLinkPose&
   c.c4 = AG_LDG(C.cl_static + L) ? C.kKHR : C.kCHR;
   c.acc = f3(0.f, 0.f, 0.f);
   c.link = link;
+}
+// node vs collider link L (Bullet btSoftColliders::CollideSDF_RS::DoNode + btSoftBody::checkContact, static shape)
+AG_HD bool cloth_detect(const SimDev& S, const ClothDev& C, const ClothLinkPose& P, int L, int N, int e, f3 x, f3 q, ClothContact& c, unsigned long long cmask = ~0ull) {
+  f3 w = x - P.bc;
+  if (!(P.br > 0.f) || dot(w, w) > P.br * P.br) return false;
+  int link = AG_LDG(C.cl_link + L);
+  f3 nl;
+  float dst = cloth_sdf_link(S, link, mulT(P.R, x - P.pos), nl, C.margin, cmask) - C.margin;
+  if (!(dst < 0.f)) return false;
+  cloth_contact_fill(S, C, L, link, N, e, x, q, mul(P.R, nl), dst, c);
+  return true;
+}
+// the same for a link that is ONE sphere or capsule (most links of the person), given in world space (a, b: the core's end points,
+// r: its radius): the exact distance without the trip through the link frame, and a cheap rejection
+AG_HD bool cloth_detect_round(const SimDev& S, const ClothDev& C, f3 a, f3 b, float r, int L, int N, int e, f3 x, f3 q, ClothContact& c) {
+  f3 ab = b - a;
+  float t = clampf(dot(x - a, ab) / fmaxf(dot(ab, ab), 1e-20f), 0.f, 1.f);
+  f3 w = x - (a + ab * t);
+  float d2 = dot(w, w), lim = r + C.margin;
+  if (!(d2 < lim * lim)) return false;
+  float Ln = sqrtf(d2), dst = Ln - r - C.margin;
+  if (!(dst < 0.f)) return false;
+  cloth_contact_fill(S, C, L, AG_LDG(C.cl_link + L), N, e, x, q, Ln > 1e-12f ? w * (1.f / Ln) : f3(0.f, 0.f, 1.f), dst, c);
   return true;
 }
 
@@ -228,8 +246,8 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
   constexpr int T = AG_CLOTH_T;
   const int N = S.N, e = blockIdx.x, t = threadIdx.x;
   float4* xs = (float4*)cl_smem;                               // [NPT * T]
-  float* lk = cl_smem + 4 * NPT * T;                           // [ncl][16]  R, pos, bounding sphere
-  float* pool = lk + 16 * AG_CLOTH_MAXCL;                      // [maxcc][12] n, offset | c3, c4, node, link | acc, -
+  float* lk = cl_smem + 4 * NPT * T;                           // [ncl][AG_CLOTH_LKS]
+  float* pool = lk + AG_CLOTH_LKS * AG_CLOTH_MAXCL;                      // [maxcc][12] n, offset | c3, c4, node, link | acc, -
   int* misc = (int*)(pool + 12 * C.maxcc);                     // [40] warp sums for the scan [0..31], total [32], active-link masks [34..36]
   float* wbox = (float*)(misc + 40);                           // [32][6] per-warp bounding boxes of the predicted nodes
   float4* qs = (float4*)(wbox + 192);                          // [NPT * T] (QS only)
@@ -301,9 +319,19 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
       bool on = false;
       if (t < C.ncl) {
         ClothLinkPose P = cloth_link_pose(C, sub, t, N, e);
-        float* o = lk + 16 * t;
+        float* o = lk + AG_CLOTH_LKS * t;
 #pragma unroll
         for (int a = 0; a < 9; a++) o[a] = P.R.m[a];
+        {                                                        // a link that is one sphere / capsule: its core in world space
+          int link = __ldg(C.cl_link + t), c0 = __ldg(S.link_col0 + link);
+          int ty = __ldg(S.link_ncol + link) == 1 ? __ldg(S.col_type + c0) : 2;
+          o[23] = ty <= 1 ? 1.f : 0.f;
+          if (ty <= 1) {
+            int v0 = __ldg(S.col_v0 + c0);
+            f3 aw = P.pos + mul(P.R, tv3(S.verts, v0)), bw = ty == 1 ? P.pos + mul(P.R, tv3(S.verts, v0 + 1)) : aw;
+            o[16] = aw.x; o[17] = aw.y; o[18] = aw.z; o[19] = bw.x; o[20] = bw.y; o[21] = bw.z; o[22] = __ldg(S.col_radius + c0);
+          }
+        }
         f3 lo(1e30f, 1e30f, 1e30f), hi(-1e30f, -1e30f, -1e30f);
         for (int w = 0; w < T / 32; w++) { lo = fmin3(lo, f3(wbox[6 * w], wbox[6 * w + 1], wbox[6 * w + 2])); hi = fmax3(hi, f3(wbox[6 * w + 3], wbox[6 * w + 4], wbox[6 * w + 5])); }
         f3 cp = fmax3(lo, fmin3(hi, P.bc)) - P.bc;             // box point nearest to the sphere centre
@@ -342,7 +370,7 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
         {
           bool near = false;
           if ((m >> (t & 31)) & 1u) {
-            const float* o = lk + 16 * ((w << 5) + (t & 31));
+            const float* o = lk + AG_CLOTH_LKS * ((w << 5) + (t & 31));
             f3 dv = wc - f3(o[12], o[13], o[14]); float rr = o[15] + wr;
             near = dot(dv, dv) <= rr * rr;
           }
@@ -351,7 +379,14 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
         while (m) {                                                   // ascending link index, as the sequential sweep visits them
           const int L = (w << 5) + __ffs(m) - 1;
           m &= m - 1;
-          const float* o = lk + 16 * L;
+          const float* o = lk + AG_CLOTH_LKS * L;
+          if (o[23] != 0.f) {                                          // one sphere / capsule: world-space fast path
+            if (valid) {
+              ClothContact c;
+              if (cloth_detect_round(S, C, f3(o[16], o[17], o[18]), f3(o[19], o[20], o[21]), o[22], L, N, e, xn[k], getq(k, i), c)) { if (nh < AG_CLOTH_HITS) hits[nh++] = (k << 8) | L; else over = true; }
+            }
+            continue;
+          }
           ClothLinkPose P;
           for (int a = 0; a < 9; a++) P.R.m[a] = o[a];
           P.pos = f3(o[9], o[10], o[11]); P.bc = f3(o[12], o[13], o[14]); P.br = o[15];
@@ -408,15 +443,18 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
       int slot = base + h;
       if (slot >= C.maxcc) break;
       int k = hits[h] >> 8, L = hits[h] & 0xff;
-      const float* o = lk + 16 * L;
-      ClothLinkPose P;
-      for (int a = 0; a < 9; a++) P.R.m[a] = o[a];
-      P.pos = f3(o[9], o[10], o[11]); P.bc = f3(o[12], o[13], o[14]); P.br = o[15];
+      const float* o = lk + AG_CLOTH_LKS * L;
       f3 xk(0.f, 0.f, 0.f), qk = getq(k, k * T + t);
 #pragma unroll
       for (int kk = 0; kk < NPT; kk++) if (kk == k) xk = xn[kk];
       ClothContact c;
-      cloth_detect(S, C, P, L, N, e, xk, qk, c);
+      if (o[23] != 0.f) cloth_detect_round(S, C, f3(o[16], o[17], o[18]), f3(o[19], o[20], o[21]), o[22], L, N, e, xk, qk, c);
+      else {
+        ClothLinkPose P;
+        for (int a = 0; a < 9; a++) P.R.m[a] = o[a];
+        P.pos = f3(o[9], o[10], o[11]); P.bc = f3(o[12], o[13], o[14]); P.br = o[15];
+        cloth_detect(S, C, P, L, N, e, xk, qk, c);
+      }
       float* r = pool + 12 * slot;
       r[0] = c.n.x; r[1] = c.n.y; r[2] = c.n.z; r[3] = c.offset; r[4] = c.c3; r[5] = c.c4;
       r[6] = __int_as_float(k * T + t); r[7] = __int_as_float(c.link); r[8] = 0.f; r[9] = 0.f; r[10] = 0.f;

@@ -1014,7 +1014,7 @@ static int run_step(AgSim* s, int which, StepEnqueue enq, const float* action, f
 
 // ------------------------------------------------------------------ cloth (K8, ag_cloth.cuh)
 static size_t cloth_smem_bytes(const AgSim* s) {
-  size_t f = (size_t)4 * s->cloth_npt * AG_CLOTH_T + 16 * AG_CLOTH_MAXCL + 12 * (size_t)s->C.maxcc + 40 + 192;
+  size_t f = (size_t)4 * s->cloth_npt * AG_CLOTH_T + AG_CLOTH_LKS * AG_CLOTH_MAXCL + 12 * (size_t)s->C.maxcc + 40 + 192;
   if (s->cloth_qs) f += (size_t)4 * s->cloth_npt * AG_CLOTH_T;
   return f * sizeof(float);
 }
