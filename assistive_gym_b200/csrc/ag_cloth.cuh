@@ -71,9 +71,21 @@ AG_HDN inline float cloth_sdf_link(const SimDev& S, int link, f3 p, f3& nrm, flo
   int c0 = AG_LDG(S.link_col0 + link), nc = AG_LDG(S.link_ncol + link);
   float best = 1e30f;
   nrm = f3(0.f, 0.f, 1.f);
-  for (int c = c0; c < c0 + nc; c++) {
+  // colliders culled for the caller's whole warp (k_cloth) are not even visited: the loop walks the set bits of the mask (the first 64
+  // colliders of the link; further ones are always visited), in ascending order
+  unsigned long long todo = nc >= 64 ? cmask : (cmask & ((1ull << nc) - 1ull));
+  int tail = nc > 64 ? 64 : nc;                       // [tail, nc): beyond the mask
+  while (todo || tail < nc) {
+    int c;
+    if (todo) {
+#if defined(__CUDA_ARCH__)
+      c = c0 + __ffsll((long long)todo) - 1;
+#else
+      c = c0 + __builtin_ctzll(todo);
+#endif
+      todo &= todo - 1;
+    } else c = c0 + tail++;
     int type = AG_LDG(S.col_type + c), v0 = AG_LDG(S.col_v0 + c);
-    if (c - c0 < 64 && !((cmask >> (c - c0)) & 1ull)) continue;      // culled for the caller's whole warp (k_cloth)
     float r = AG_LDG(S.col_radius + c), d; f3 n;
     f3 bq(0.f, 0.f, 0.f);                     // signed per-axis distance of the point to the core's bounding box (link frame)
     if (type != 3) {
