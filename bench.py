@@ -598,12 +598,12 @@ def main():
                'gpu_launches': int(launches), 'roofline': roof}
         if not args.no_cpu:
             cores = usable_cores()
-            ne = max(8 * cores, 32)
-            v, tsec = cpu_oracle_rate(fb, ne, 5, cores)
-            v1, t1 = cpu_oracle_rate(fb, 16, 5, 1)
+            ne, ns = max(32 * cores, 64), 40                  # ~20 k env-steps = 15-25 s of CPU work spread over the threads
+            v, tsec = cpu_oracle_rate(fb, ne, ns, cores)
+            v1, t1 = cpu_oracle_rate(fb, 64, ns, 1)
             out['cpu_baseline'] = {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
-                                   'sample': '%d envs x 5 env-steps (%.1f s), CPU restatement (PyBullet unavailable), %d threads (affinity / cgroup quota)' % (ne, tsec, cores),
-                                   'one_thread': {'value': v1, 'cores': 1, 'sample': '16 envs x 5 env-steps (%.1f s)' % t1}}
+                                   'sample': '%d envs x %d env-steps (%.2f s wall, %.0f core-seconds), CPU restatement (PyBullet unavailable), %d threads (affinity / cgroup quota)' % (ne, ns, tsec, tsec * cores, cores),
+                                   'one_thread': {'value': v1, 'cores': 1, 'sample': '64 envs x %d env-steps (%.2f s)' % (ns, t1)}}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
