@@ -67,7 +67,7 @@ struct ClothContact { f3 n; float offset, c3, c4; f3 acc; int node, link; };
 // signed distance of a point (link frame) to the union of the link's colliders, outward normal of the nearest one
 // (colliders whose bounding box is farther than `reach` from the point are skipped: they cannot produce a distance below `reach`,
 //  and only distances below the collision margin matter to the caller -- a link of the wheelchair is 44 hulls, one of PR2's up to 100 planes)
-AG_HDN inline float cloth_sdf_link(const SimDev& S, int link, f3 p, f3& nrm, float reach = 1e30f, unsigned long long cmask = ~0ull) {
+AG_HDN inline float cloth_sdf_link(const SimDev& S, int link, f3 p, f3& nrm, float reach = 1e30f, unsigned long long cmask = ~0ull, int* cbest = nullptr) {
   int c0 = AG_LDG(S.link_col0 + link), nc = AG_LDG(S.link_ncol + link);
   float best = 1e30f;
   nrm = f3(0.f, 0.f, 1.f);
@@ -107,9 +107,22 @@ AG_HDN inline float cloth_sdf_link(const SimDev& S, int link, f3 p, f3& nrm, flo
     } else {
       // hull / half-space: the plane the point is farthest outside of -- the hull's face planes and, for hulls, the six planes of
       // the core's bounding box (the box contains the hull, so this only tightens the lower bound outside and changes nothing inside)
+      // A plane the point is farther outside of than `reach` (+ the rounding radius) ends the walk: the maximum can only grow, so this
+      // collider cannot yield a distance below `reach` -- the same argument as the box test above.  Most nodes near a 124-plane gripper
+      // hull are outside its margin shell and leave after a few planes.
       int p0 = AG_LDG(S.col_p0 + c), np = AG_LDG(S.col_np + c);
       float m = -1e30f; n = f3(0.f, 0.f, 1.f);
-      for (int k = p0; k < p0 + np; k++) { f3 pn; float pd; ld_plane(S.planes, k, pn, pd); float s = dot(pn, p) - pd; if (s > m) { m = s; n = pn; } }
+      const float lim = reach + r;
+      bool sep = false;
+      for (int k = p0; k < p0 + np && !sep; k += 4) {            // four planes per trip: their loads are in flight together
+        f3 pn[4]; float sd[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { int kk = k + j < p0 + np ? k + j : p0 + np - 1; float pd; ld_plane(S.planes, kk, pn[j], pd); sd[j] = dot(pn[j], p) - pd; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (sd[j] > m) { m = sd[j]; n = pn[j]; }      // (a repeated last plane changes nothing: strict >)
+        sep = m > lim;
+      }
+      if (sep) continue;
       if (type == 2) {
         f3 bc = tv3(S.col_center, c);
         if (bq.x > m) { m = bq.x; n = f3(p.x >= bc.x ? 1.f : -1.f, 0.f, 0.f); }
@@ -118,7 +131,7 @@ AG_HDN inline float cloth_sdf_link(const SimDev& S, int link, f3 p, f3& nrm, flo
       }
       d = m - r;
     }
-    if (d < best) { best = d; nrm = n; }
+    if (d < best) { best = d; nrm = n; if (cbest) *cbest = c - c0; }
   }
   return best;
 }
@@ -153,12 +166,14 @@ AG_HD void cloth_contact_fill(const SimDev& S, const ClothDev& C, int L, int lin
   c.link = link;
 }
 // node vs collider link L (Bullet btSoftColliders::CollideSDF_RS::DoNode + btSoftBody::checkContact, static shape)
-AG_HD bool cloth_detect(const SimDev& S, const ClothDev& C, const ClothLinkPose& P, int L, int N, int e, f3 x, f3 q, ClothContact& c, unsigned long long cmask = ~0ull) {
+// (cbest, if given, receives the index within the link of the collider that made the contact: evaluating that collider alone --
+//  cmask = 1 << index -- reproduces the same record, which is how k_cloth writes the records after the slots are known)
+AG_HD bool cloth_detect(const SimDev& S, const ClothDev& C, const ClothLinkPose& P, int L, int N, int e, f3 x, f3 q, ClothContact& c, unsigned long long cmask = ~0ull, int* cbest = nullptr) {
   f3 w = x - P.bc;
   if (!(P.br > 0.f) || dot(w, w) > P.br * P.br) return false;
   int link = AG_LDG(C.cl_link + L);
   f3 nl;
-  float dst = cloth_sdf_link(S, link, mulT(P.R, x - P.pos), nl, C.margin, cmask) - C.margin;
+  float dst = cloth_sdf_link(S, link, mulT(P.R, x - P.pos), nl, C.margin, cmask, cbest) - C.margin;
   if (!(dst < 0.f)) return false;
   cloth_contact_fill(S, C, L, link, N, e, x, q, mul(P.R, nl), dst, c);
   return true;
@@ -338,6 +353,11 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
           int link = __ldg(C.cl_link + t), c0 = __ldg(S.link_col0 + link);
           int ty = __ldg(S.link_ncol + link) == 1 ? __ldg(S.col_type + c0) : 2;
           o[23] = ty <= 1 ? 1.f : 0.f;
+          if (__ldg(S.link_ncol + link) == 1 && __ldg(S.col_type + c0) == 3) {     // the ground: its plane in world space, for the patch-level test
+            f3 pn; float pd; ld_plane(S.planes, __ldg(S.col_p0 + c0), pn, pd);
+            f3 nw = mul(P.R, pn);
+            o[16] = nw.x; o[17] = nw.y; o[18] = nw.z; o[19] = pd + dot(nw, P.pos); o[22] = __ldg(S.col_radius + c0); o[23] = 2.f;
+          }
           if (ty <= 1) {
             int v0 = __ldg(S.col_v0 + c0);
             f3 aw = P.pos + mul(P.R, tv3(S.verts, v0)), bw = ty == 1 ? P.pos + mul(P.R, tv3(S.verts, v0 + 1)) : aw;
@@ -392,7 +412,9 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
           const int L = (w << 5) + __ffs(m) - 1;
           m &= m - 1;
           const float* o = lk + AG_CLOTH_LKS * L;
-          if (o[23] != 0.f) {                                          // one sphere / capsule: world-space fast path
+          if (o[23] == 2.f) {                                          // a half-space the whole patch is clear of (the floor, usually)
+            if (o[16] * wc.x + o[17] * wc.y + o[18] * wc.z - o[19] - wr > C.margin + o[22]) continue;
+          } else if (o[23] != 0.f) {                                   // one sphere / capsule: world-space fast path
             if (valid) {
               ClothContact c;
               if (cloth_detect_round(S, C, f3(o[16], o[17], o[18]), f3(o[19], o[20], o[21]), o[22], L, N, e, xn[k], getq(k, i), c)) { if (nh < AG_CLOTH_HITS) hits[nh++] = (k << 8) | L; else over = true; }
@@ -428,7 +450,8 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
             f3 wv = xn[k] - P.bc;
             if (dot(wv, wv) <= P.br * P.br) {
               ClothContact c;
-              if (cloth_detect(S, C, P, L, N, e, xn[k], getq(k, i), c, cmask)) { if (nh < AG_CLOTH_HITS) hits[nh++] = (k << 8) | L; else over = true; }
+              int cb = 0;
+              if (cloth_detect(S, C, P, L, N, e, xn[k], getq(k, i), c, cmask, &cb)) { if (nh < AG_CLOTH_HITS) hits[nh++] = (cb << 16) | (k << 8) | L; else over = true; }
             }
           }
         }
@@ -451,25 +474,47 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
     const int base = misc[t >> 5] + incl - nh;
     total = misc[32];
     if (total > C.maxcc) { over = true; total = C.maxcc; }
-    for (int h = 0; h < nh; h++) {
-      int slot = base + h;
-      if (slot >= C.maxcc) break;
-      int k = hits[h] >> 8, L = hits[h] & 0xff;
+    // The records are written once the slots are known, from the (node, link, collider) triples of the hits; the distance evaluation
+    // visits only the collider that made the contact.  In the QS variant the owner only posts the triple and the block then writes one
+    // record per thread: the hits sit on the few threads whose nodes touch the body, which the others used to wait for.
+    auto write_record = [&](int slot, int i, int L, int cb, f3 xk, f3 qk) {
       const float* o = lk + AG_CLOTH_LKS * L;
-      f3 xk(0.f, 0.f, 0.f), qk = getq(k, k * T + t);
-#pragma unroll
-      for (int kk = 0; kk < NPT; kk++) if (kk == k) xk = xn[kk];
       ClothContact c;
-      if (o[23] != 0.f) cloth_detect_round(S, C, f3(o[16], o[17], o[18]), f3(o[19], o[20], o[21]), o[22], L, N, e, xk, qk, c);
+      if (o[23] == 1.f) cloth_detect_round(S, C, f3(o[16], o[17], o[18]), f3(o[19], o[20], o[21]), o[22], L, N, e, xk, qk, c);
       else {
         ClothLinkPose P;
         for (int a = 0; a < 9; a++) P.R.m[a] = o[a];
         P.pos = f3(o[9], o[10], o[11]); P.bc = f3(o[12], o[13], o[14]); P.br = o[15];
-        cloth_detect(S, C, P, L, N, e, xk, qk, c);
+        cloth_detect(S, C, P, L, N, e, xk, qk, c, cb < 64 ? 1ull << cb : 0ull);
       }
-      float* r = pool + 12 * slot;
-      r[0] = c.n.x; r[1] = c.n.y; r[2] = c.n.z; r[3] = c.offset; r[4] = c.c3; r[5] = c.c4;
-      r[6] = __int_as_float(k * T + t); r[7] = __int_as_float(c.link); r[8] = 0.f; r[9] = 0.f; r[10] = 0.f;
+      float4* r4 = (float4*)(pool + 12 * slot);
+      r4[0] = make_float4(c.n.x, c.n.y, c.n.z, c.offset);
+      r4[1] = make_float4(c.c3, c.c4, __int_as_float(i), __int_as_float(c.link));
+      r4[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if constexpr (QS) {
+      for (int h = 0; h < nh; h++) {
+        int slot = base + h;
+        if (slot >= C.maxcc) break;
+        pool[12 * slot + 6] = __int_as_float(((hits[h] >> 8) & 0xff) * T + t);
+        pool[12 * slot + 7] = __int_as_float((hits[h] & 0xff) | (hits[h] >> 16 << 8));
+      }
+      __syncthreads();
+      for (int slot = t; slot < total; slot += T) {
+        int i = __float_as_int(pool[12 * slot + 6]), lc = __float_as_int(pool[12 * slot + 7]);
+        float4 x4 = xs[i], q4 = qs[i];
+        write_record(slot, i, lc & 0xff, lc >> 8, f3(x4.x, x4.y, x4.z), f3(q4.x, q4.y, q4.z));
+      }
+    } else {
+      for (int h = 0; h < nh; h++) {
+        int slot = base + h;
+        if (slot >= C.maxcc) break;
+        int k = (hits[h] >> 8) & 0xff;
+        f3 xk(0.f, 0.f, 0.f), qk = getq(k, k * T + t);
+#pragma unroll
+        for (int kk = 0; kk < NPT; kk++) if (kk == k) xk = xn[kk];
+        write_record(slot, k * T + t, hits[h] & 0xff, hits[h] >> 16, xk, qk);
+      }
     }
     if (over) C.overflow[e] = 1;
     __syncthreads();
@@ -484,15 +529,39 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
           xs[i] = make_float4(xx.x, xx.y, xx.z, 0.f);
         }
       }
-      for (int h = 0; h < nh; h++) {
-        int slot = base + h;
-        if (slot >= C.maxcc) break;
-        int k = hits[h] >> 8, i = k * T + t;
-        float* r = pool + 12 * slot;
-        float4 me = xs[i]; f3 xx(me.x, me.y, me.z), qq = getq(k, i), acc(r[8], r[9], r[10]);
-        cloth_contact_solve(xx, qq, f3(r[0], r[1], r[2]), r[3], r[4], r[5], C.margin, acc);
-        xs[i] = make_float4(xx.x, xx.y, xx.z, 0.f);
-        r[8] = acc.x; r[9] = acc.y; r[10] = acc.z;
+      if constexpr (QS) {
+        // One thread per contact slot, not per owner: the contacts sit on the few hundred nodes that touch the body, whose owner threads
+        // used to relax up to 4 nodes x several contacts each while the rest of the block waited at the barrier below.  A node's contacts
+        // are consecutive slots (the hits are listed node by node); the thread of the first one relaxes the run in slot order, so the
+        // result is the sequential sweep's.  Both node arrays are in shared memory in this variant, any thread can take any node.
+        for (int s0 = t; s0 < total; s0 += T) {
+          float4* r4 = (float4*)(pool + 12 * s0);
+          const int i = __float_as_int(r4[1].z);
+          if (s0 > 0 && __float_as_int(pool[12 * (s0 - 1) + 6]) == i) continue;
+          float4 me = xs[i], q4 = qs[i];
+          f3 xx(me.x, me.y, me.z), qq(q4.x, q4.y, q4.z);
+          for (int s1 = s0;;) {
+            float4 a = r4[0], b = r4[1], c = r4[2];
+            f3 acc(c.x, c.y, c.z);
+            cloth_contact_solve(xx, qq, f3(a.x, a.y, a.z), a.w, b.x, b.y, C.margin, acc);
+            r4[2] = make_float4(acc.x, acc.y, acc.z, 0.f);
+            if (++s1 >= total) break;
+            r4 += 3;
+            if (__float_as_int(r4[1].z) != i) break;
+          }
+          xs[i] = make_float4(xx.x, xx.y, xx.z, 0.f);
+        }
+      } else {
+        for (int h = 0; h < nh; h++) {
+          int slot = base + h;
+          if (slot >= C.maxcc) break;
+          int k = (hits[h] >> 8) & 0xff, i = k * T + t;
+          float* r = pool + 12 * slot;
+          float4 me = xs[i]; f3 xx(me.x, me.y, me.z), qq = getq(k, i), acc(r[8], r[9], r[10]);
+          cloth_contact_solve(xx, qq, f3(r[0], r[1], r[2]), r[3], r[4], r[5], C.margin, acc);
+          xs[i] = make_float4(xx.x, xx.y, xx.z, 0.f);
+          r[8] = acc.x; r[9] = acc.y; r[10] = acc.z;
+        }
       }
       __syncthreads();
       // the first record of a colour is fetched while the previous colour is relaxed (the table lives in L2: the contact pool and
