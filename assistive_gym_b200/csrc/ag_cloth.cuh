@@ -45,6 +45,7 @@ struct ClothDev {
   const unsigned* link_ij;     // [nlinks] node i | node j << 16, colour-major
   const float* link_rest2;     // [nlinks]
   const struct ClothLinkRec* link_tab;   // [nlinks] the two above interleaved (one 8-byte load per link)
+  const struct ClothLinkRec* link_dense; // [ncol + 1][AG_CLOTH_T] one row per colour, thread t relaxes entry t; no link: ij = ~0.  Null if a colour is larger than the block
   const int* nf_off;           // [nn + 1]
   const unsigned* nf_pair;     // [nf] next | next-next << 16 (face winding)
   const float* node_area;      // [nn]
@@ -267,12 +268,22 @@ AG_HDN inline void cloth_follow_body(int tid, const SimDev& S, const KP& p) {
 // QS: previous positions q (during a substep) / velocities v (between substeps) of a thread's own nodes live in a second
 // shared-memory array instead of registers (same arithmetic, bit-identical results; frees 6 NPT registers under the
 // 64-register limit of a 1024-thread CTA)
+__device__ __forceinline__ float4 cloth_lds4(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cloth_sts4(unsigned a, float x, float y, float z) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(a), "f"(x), "f"(y), "f"(z), "f"(0.f) : "memory");
+}
 template <int NPT, bool QS>
 __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
   extern __shared__ __align__(16) float cl_smem[];
   constexpr int T = AG_CLOTH_T;
   const int N = S.N, e = blockIdx.x, t = threadIdx.x;
   float4* xs = (float4*)cl_smem;                               // [NPT * T]
+  unsigned xs_sa = (unsigned)__cvta_generic_to_shared(xs);     // its shared-memory address, pinned in a register for the colour passes
+  asm volatile("" : "+r"(xs_sa));
   float* lk = cl_smem + 4 * NPT * T;                           // [ncl][AG_CLOTH_LKS]
   float* pool = lk + AG_CLOTH_LKS * AG_CLOTH_MAXCL;                      // [maxcc][12] n, offset | c3, c4, node, link | acc, -
   int* misc = (int*)(pool + 12 * C.maxcc);                     // [40] warp sums for the scan [0..31], total [32], active-link masks [34..36]
@@ -564,6 +575,29 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
         }
       }
       __syncthreads();
+      if (C.link_dense) {
+        // One row of the table per colour, one entry per thread: a pass is two 16-byte loads, the relaxation, two 16-byte stores and
+        // the barrier.  The pass is issue-bound (32 warps x ~40 instructions against 4 schedulers), so everything else is kept out
+        // of it: the next colour's entry is fetched one pass ahead by bumping a pointer, and the node arrays are addressed through a
+        // 32-bit shared-memory address held in a register (left to itself the compiler re-derives the base -- S2R SR_CgaCtaId,
+        // a long-scoreboard wait -- in every pass: 7 % of the kernel's samples sat on it).
+        const uint2* row = (const uint2*)C.link_dense + t;
+        uint2 nxt = __ldg(row);
+        for (int col = 0; col < C.ncol; col++) {
+          const uint2 lt = nxt;
+          row = col + 1 < C.ncol ? row + T : (const uint2*)C.link_dense + t;      // (the last pass fetches colour 0 of the next iteration)
+          nxt = __ldg(row);
+          if (lt.x != 0xffffffffu) {
+            const unsigned ai = xs_sa + ((lt.x & 0xffffu) << 4), bi = xs_sa + ((lt.x >> 16) << 4);
+            float4 a4 = cloth_lds4(ai), b4 = cloth_lds4(bi);
+            f3 a(a4.x, a4.y, a4.z), b(b4.x, b4.y, b4.z);
+            cloth_link_solve(a, b, __uint_as_float(lt.y), C.kLSTh);
+            cloth_sts4(ai, a.x, a.y, a.z); cloth_sts4(bi, b.x, b.y, b.z);
+          }
+          __syncthreads();
+        }
+        continue;
+      }
       // the first record of a colour is fetched while the previous colour is relaxed (the table lives in L2: the contact pool and
       // the node arrays leave the L1 too small for it)
       uint2 nxt = make_uint2(0u, 0u);

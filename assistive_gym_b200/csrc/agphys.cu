@@ -1087,6 +1087,15 @@ int ag_cloth_init(AgSim* s, const AgClothDesc* d) {
       C.tab_end[c] = (int)tab.size();
     }
     C.link_tab = upload(s, tab);
+    bool fits = true;
+    for (int c = 0; c < d->n_colours; c++) fits &= C.col_off[c + 1] - C.col_off[c] <= AG_CLOTH_T;
+    C.link_dense = nullptr;
+    if (fits) {                                       // one row of AG_CLOTH_T entries per colour (+ one spare row: the fetch runs a pass ahead)
+      std::vector<ClothLinkRec> dense((size_t)(d->n_colours + 1) * AG_CLOTH_T, ClothLinkRec{0xffffffffu, 0.f});
+      for (int c = 0; c < d->n_colours; c++)
+        for (int l = C.col_off[c]; l < C.col_off[c + 1]; l++) dense[(size_t)c * AG_CLOTH_T + (l - C.col_off[c])] = ClothLinkRec{lij[l], lr[l]};
+      C.link_dense = upload(s, dense);
+    }
   }
   C.nf_off = upload(s, std::vector<int>(d->nf_off, d->nf_off + nn + 1)); C.nf_pair = upload(s, nfp);
   C.node_area = upload(s, area);
