@@ -268,6 +268,22 @@ AG_HDN inline void cloth_follow_body(int tid, const SimDev& S, const KP& p) {
 // QS: previous positions q (during a substep) / velocities v (between substeps) of a thread's own nodes live in a second
 // shared-memory array instead of registers (same arithmetic, bit-identical results; frees 6 NPT registers under the
 // 64-register limit of a 1024-thread CTA)
+// Can any node of a patch (bounding box lo..hi, bounding sphere wc / wr) be within the collision margin of collider link `o` (its entry
+// of the link table in shared memory)?  Conservative, so the outcome of the search does not depend on it.  Limbs are long thin capsules:
+// their bounding sphere is several times wider than they are, the distance to the core segment is what keeps the pair list short.
+__device__ __forceinline__ bool cloth_patch_near(const float* o, f3 lo, f3 hi, f3 wc, float wr, float margin) {
+  if (o[23] == 1.f) {                                                  // one sphere / capsule, core a..b in world space
+    f3 a(o[16], o[17], o[18]), ab = f3(o[19], o[20], o[21]) - a;
+    float tt = clampf(dot(wc - a, ab) / fmaxf(dot(ab, ab), 1e-20f), 0.f, 1.f);
+    f3 w = wc - (a + ab * tt);
+    float lim = o[22] + margin + wr + 1e-5f;
+    return dot(w, w) <= lim * lim;
+  }
+  if (o[23] == 2.f) return o[16] * wc.x + o[17] * wc.y + o[18] * wc.z - o[19] - wr <= margin + o[22] + 1e-5f;      // a half-space (the floor)
+  f3 bc(o[12], o[13], o[14]);
+  f3 cp = fmax3(lo, fmin3(hi, bc)) - bc;                               // the box's point nearest to the link's bounding sphere
+  return dot(cp, cp) <= o[15] * o[15];
+}
 __device__ __forceinline__ float4 cloth_lds4(unsigned a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
@@ -413,9 +429,7 @@ __global__ void __launch_bounds__(AG_CLOTH_T, 1) k_cloth(SimDev S, ClothDev C) {
         {
           bool near = false;
           if ((m >> (t & 31)) & 1u) {
-            const float* o = lk + AG_CLOTH_LKS * ((w << 5) + (t & 31));
-            f3 dv = wc - f3(o[12], o[13], o[14]); float rr = o[15] + wr;
-            near = dot(dv, dv) <= rr * rr;
+            near = cloth_patch_near(lk + AG_CLOTH_LKS * ((w << 5) + (t & 31)), lo, hi, wc, wr, C.margin);
           }
           m = __ballot_sync(0xffffffffu, near);
         }
