@@ -433,10 +433,12 @@ def main():
     # per-env seeds derive from the GLOBAL env id so results do not depend on the partition
     from assistive_gym_b200.sharding import sample_block, shard_range
     lo, hi = shard_range(rank, world, world * n)
-    for g, sub in enumerate(sim.sims):
-        rng = np.random.default_rng(1001 + rank * n + g)       # only used for IK random restarts
-        sg = fb.reset(sub, rng, settle_steps=25, sample=sample_block(fb, lo + g * sim.m, lo + (g + 1) * sim.m))
-        fb.start_fused(sub, sg, seed=1001 + rank * n + g * sim.m)
+    def reset_all():
+        for g, sub in enumerate(sim.sims):
+            rng = np.random.default_rng(1001 + rank * n + g)       # only used for IK random restarts
+            sg = fb.reset(sub, rng, settle_steps=25, sample=sample_block(fb, lo + g * sim.m, lo + (g + 1) * sim.m))
+            fb.start_fused(sub, sg, seed=1001 + rank * n + g * sim.m)
+    reset_all()
     # `stream`: the bench's own stream; every step forks from it to the sub-batches' streams and joins back
     sub_streams = [torch.cuda.ExternalStream(p, device=local_rank) for p in sim.stream_ptrs()]
     stream = torch.cuda.Stream(device=local_rank)
@@ -509,6 +511,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
     value = world * n * K / (elapsed_ms / 1000.0)
+    rew_value_path = rew.detach().cpu().numpy().copy()        # reward of the last timed step (compared with the e2e path below)
     # the same K steps timed back to back (no flush, no per-step sync): how much the pipeline overlap is worth
     torch.cuda.synchronize()
     with torch.cuda.stream(stream):
@@ -536,15 +539,21 @@ def main():
         prof = {k: (v[0] * sc_, int(round(v[1] * sc_))) for k, v in prof.items()}     # scaled to K steps (the code below divides by K)
 
     # ---- e2e: host buffers through the reference-facing call (H2D + D2H inside the timed region, collective included)
-    host_actions = np.random.default_rng(7 + rank).uniform(-1, 1, size=(K, n, 7)).astype(np.float32)
-    sim.feeding_step_host(host_actions[0])
+    # The SAME env steps as the device-resident measurement: the batch is reset to the same start state and driven with the same
+    # actions (W untimed steps, then K timed ones), so the two numbers differ by the transfers and the per-step synchronisation only
+    # (a batch stepped on with random actions drifts towards more contacts: steps 50+ cost ~10 % more than steps 5-25).
+    host_actions = actions.detach().cpu().numpy().astype(np.float32)
+    torch.cuda.synchronize()
+    reset_all()
+    for i in range(W):
+        sim.feeding_step_host(host_actions[i])
     r_dev = torch.zeros(n, device=dev)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for i in range(K):
-        o_h, r_h, d_h, i_h = sim.feeding_step_host(host_actions[i])
+        o_h, r_h, d_h, i_h = sim.feeding_step_host(host_actions[W + i])
         if world > 1:
             with torch.cuda.stream(stream):
                 r_dev.copy_(torch.from_numpy(r_h), non_blocking=True)
@@ -555,6 +564,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n * K / float(t.item())
+    e2e_diff = float(np.max(np.abs(r_h - rew_value_path)))     # same start state, same actions: the two paths must agree
     overflow = sim.overflow_count()
     ccount, citers = sim.solver_stats()
     stream_bytes = 4 * sim.pgs_trips()[1]
@@ -592,7 +602,8 @@ def main():
                           'pgs_iters_per_env': {'mean': float(citers.mean()), 'p50': float(np.percentile(citers, 50)), 'p99': float(np.percentile(citers, 99)), 'max': int(citers.max())},
                           'pgs_lanes_per_env': 8,
                           'collective': 'all_gather(reward) every step, double-buffered on a side stream (inside both timed regions)' if world > 1 else 'none',
-                          'ms_per_step_back_to_back': b2b_ms},
+                          'ms_per_step_back_to_back': b2b_ms,
+                          'e2e_same_steps_as_value': True, 'e2e_reward_max_abs_diff_vs_value_path': e2e_diff},
                'clocks': clk,
                'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n * 7 * 4, 'd2h_bytes_per_step': n * 31 * 4},
                'gpu_launches': int(launches), 'roofline': roof}
