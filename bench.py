@@ -323,12 +323,19 @@ def run_dressing(args):
     sim.profile_enable(False)
     per_kernel = {k_: v[0] / 2 for k_, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
     cloth_ms = prof['k_cloth'][0] / prof['k_cloth'][1]
-    host_a = np.random.default_rng(1).uniform(-1, 1, size=(K, n, 7)).astype(np.float32)
-    sim.dressing_step_host(host_a[0])
+    # e2e over the SAME env steps as `value`: the stored reset is replayed (same base poses, start angles, gown) and the batch is driven
+    # with the same actions, W untimed + K timed steps from host buffers
+    host_a = act.cpu().numpy().astype(np.float32)
+    over_steps, over_settle = int(sim.overflow_count()), int(db.settle_overflow)       # (the flags are cleared when read)
+    db.reset(sim, np.random.default_rng(0), sample=smp, settle_steps=50)
+    db.start_fused(sim, smp)
+    for i in range(W):
+        sim.dressing_step_host(host_a[i])
     t0 = time.perf_counter()
     for i in range(K):
-        sim.dressing_step_host(host_a[i])
+        sim.dressing_step_host(host_a[W + i])
     e2e = n * K / (time.perf_counter() - t0)
+    over_steps = max(over_steps, int(sim.overflow_count()))
     ccnt = sim.cloth_get_contacts(1)[0]
     rcnt, it = sim.solver_stats()
     peak, peak_src = measured_peak()
@@ -344,7 +351,7 @@ def run_dressing(args):
                                  'reset_s': reset_s, 'toc_attempts': args.toc_attempts, 'goals_reached_mean': float(np.mean(db.goals_reached)), 'base_unresolved': int(db.unresolved),
                                  'cloth_contacts_per_env': {'mean': float(ccnt.mean()), 'p99': float(np.percentile(ccnt, 99)), 'max': int(ccnt.max())},
                                  'rigid_contacts_per_env': {'mean': float(rcnt.mean()), 'max': int(rcnt.max())},
-                                 'envs_over_budget': int(sim.overflow_count()), 'envs_over_budget_during_settle': int(db.settle_overflow),
+                                 'envs_over_budget': over_steps, 'envs_over_budget_during_settle': over_settle, 'e2e_same_steps_as_value': True,
                                  'sleeve_state_counts': {str(k_): int((info_h[:, 3] == k_).sum()) for k_ in (0, 1, 2, 3)},
                                  'cloth_force_mean_N': float(obs[:, 23].mean().item())},
                       'clocks': clk, 'e2e': {'value': e2e, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n * 7 * 4, 'd2h_bytes_per_step': n * 30 * 4},
