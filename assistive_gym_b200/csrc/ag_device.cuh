@@ -438,22 +438,23 @@ AG_HD int ag_atomic_add(int* p, int k) {
 #endif
 }
 
-// K3a: thread = (link pair p, env lane), env fastest; p.i0 = padded env count.  Cheap AABB culls only:
+// K3a: thread = (slice of a link pair, env lane), env fastest (SimDev::pair_slice: a pair's colliders of link a, cut so that a
+// thread makes at most ~64 collider box tests); p.i0 = padded env count.  Cheap AABB culls only:
 // surviving collider pairs are appended to the env's candidate list.  Light kernel (few registers,
 // full occupancy); the heavy GJK work runs in K3b with one thread per candidate.
 AG_HDN inline void pairs_body(int tid, const SimDev& S, const KP& kp) {
   const int N = S.N;
   int Npad = kp.i0;
-  int e = tid % Npad, pr = tid / Npad;
+  int e = tid % Npad, sl = tid / Npad;
   if (e >= N) return;
-  int la = AG_LDG(S.pair_link + 2 * pr), lb = AG_LDG(S.pair_link + 2 * pr + 1);
+  int la = AG_LDG(S.pair_slice + 4 * sl), lb = AG_LDG(S.pair_slice + 4 * sl + 1);
   int ba = AG_LDG(S.link_body + la), bb = AG_LDG(S.link_body + lb);
   if (S.body_mode[(size_t)ba * N + e] == 0 || S.body_mode[(size_t)bb * N + e] == 0) return;
   float fac = S.contact_thr;
   f3 lamin = ld3(S.lmin, la, N, e), lamax = ld3(S.lmax, la, N, e), lbmin = ld3(S.lmin, lb, N, e), lbmax = ld3(S.lmax, lb, N, e);
   float tla = AG_LDG(S.link_thresh + la), tlb = AG_LDG(S.link_thresh + lb);
   if (!aabb_ov(lamin, lamax, lbmin, lbmax, fac * fminf(tla, tlb))) return;
-  int ca0 = AG_LDG(S.link_col0 + la), nca = AG_LDG(S.link_ncol + la), cb0 = AG_LDG(S.link_col0 + lb), ncb = AG_LDG(S.link_ncol + lb);
+  int ca0 = AG_LDG(S.pair_slice + 4 * sl + 2), nca = AG_LDG(S.pair_slice + 4 * sl + 3), cb0 = AG_LDG(S.link_col0 + lb), ncb = AG_LDG(S.link_ncol + lb);
   for (int ca = ca0; ca < ca0 + nca; ca++) {
     f3 amin = ld3(S.cmin, ca, N, e), amax = ld3(S.cmax, ca, N, e);
     float tha = AG_LDG(S.col_thresh + ca);

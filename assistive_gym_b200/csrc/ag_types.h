@@ -39,6 +39,7 @@ struct SimDev {
   const float* vertq; const int* col_g0;               // core vertices packed 4 at a time ([x0..3][y0..3][z0..3]) for the GJK support search, first group per collider
   float max_thresh;
   const int* pair_link;
+  int nslice; const int* pair_slice;                   // [nslice][4] broadphase work items: link a, link b, first collider of a, colliders of a in this slice (<= 64 collider tests each)
   const int *movcol, *movlink, *allcol, *alllink;
   const int* con_link; const float *con_pivot, *con_quat, *con_maxforce;
   const int* free_body; const float* free_invm;
