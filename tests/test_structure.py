@@ -119,3 +119,32 @@ def test_assistive_gym_shim_resolves_reference_ids():
         assert 'not built' in str(e)
     else:
         raise AssertionError('an id that is not built must not resolve')
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The bench lines kept under profiles/ (written by bench.py on the GPU box) carry every key the measurement contract names."""
+    import glob
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, 'profiles', 'r02[w-z]_bench*.json')))
+    assert files
+    base = {'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'e2e'}
+    for f in files:
+        line = [ln for ln in open(f) if ln.startswith('{')][0]
+        d = json.loads(line)
+        assert base <= set(d), (f, base - set(d))
+        assert 'workload' in d['config'] and d['higher_is_better'] is True and d['scaling'] == 'weak' and d['vs_baseline'] is None
+        assert {'value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'} <= set(d['e2e'])
+        if d.get('impl') == 'reference':
+            assert d['cpu_baseline']['kind'] in ('port', 'reference') and d['e2e']['h2d_bytes_per_step'] == 0 and d['cpu_baseline']['cores'] >= 1
+            continue
+        assert d['gpu_launches'] > 0 and d['dtype'] == 'f32'
+        assert {'sm_mhz', 'sm_max_mhz', 'reasons'} <= set(d['clocks'])
+        assert not set(d['clocks']['reasons']) & {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
+        if 'bedbathing' in f:                       # the secondary BedBathing line carries value / e2e / clocks only
+            continue
+        r = d['roofline']
+        assert {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'} <= set(r) and r['bound'] in ('hbm', 'tensor')
+        assert abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
+        if 'cpu_baseline' in d:
+            assert {'value', 'unit', 'cores', 'kind', 'sample'} <= set(d['cpu_baseline'])
