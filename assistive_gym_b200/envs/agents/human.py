@@ -40,3 +40,39 @@ class Human(Agent):
         self.tremors = np.zeros(10)
         self.motor_forces, self.motor_gains = 1.0, 0.05
         self.gender = 'male'          # per-env genders live in the env (`male` mask); N == 1 mirrors the reference attribute
+        self.limits_model = None      # the realistic joint-limit classifier (human.py:73), loaded on first use
+        self.arm_previous_valid_pose = {True: None, False: None}      # human.py:68: per arm, here [n_envs][4] with NaN = none yet
+
+    def enforce_realistic_joint_limits(self, env_mask=None):
+        """human.py:134-152, for every env at once: the shoulder / elbow angles of the controllable arm are classified by the
+        joint-limit MLP; a reachable pose is remembered, an unreachable one is replaced by the env's last reachable pose (joint
+        velocities zeroed, as `set_joint_angles` does).  `env_mask`: envs in which this person exists (the other gender's copy
+        is switched off)."""
+        ci = self.controllable_joint_indices
+        if self.j_right_shoulder_x not in ci and self.j_left_shoulder_x not in ci:
+            return
+        right = self.j_right_shoulder_x in ci
+        indices = ([self.j_right_shoulder_x, self.j_right_shoulder_y, self.j_right_shoulder_z, self.j_right_elbow] if right else
+                   [self.j_left_shoulder_x, self.j_left_shoulder_y, self.j_left_shoulder_z, self.j_left_elbow])
+        if self.limits_model is None:
+            from ...limits_model import load_model
+            self.limits_model = load_model()
+        ang = np.atleast_2d(self.get_joint_angles(indices))
+        tz, tx, ty, qe = ang.T
+        sgn = -1.0 if right else 1.0
+        two_pi = 2 * np.pi
+        x = np.stack([(sgn * tz + two_pi) % two_pi, (tx + two_pi) % two_pi, sgn * ty, (-qe + two_pi) % two_pi], axis=1)     # the angle convention of the training data
+        ok = self.limits_model.predict_classes(x)[:, 0] == 1
+        if env_mask is not None:
+            ok = ok | ~np.asarray(env_mask, dtype=bool)
+        prev = self.arm_previous_valid_pose[right]
+        if prev is None:
+            prev = np.full(ang.shape, np.nan)
+        prev = np.where(ok[:, None], ang, prev)
+        self.arm_previous_valid_pose[right] = prev
+        back = ~ok & ~np.isnan(prev[:, 0])
+        if back.any():
+            lo = np.array([self.lower_limits[j] for j in indices]); hi = np.array([self.upper_limits[j] for j in indices])
+            self.sim.set_joint_state([self._gl(j) for j in indices], q=np.clip(np.where(back[:, None], prev, ang), lo, hi), qd=np.zeros_like(ang),
+                                     mask=back.astype(np.int32))
+            self.sim.forward_kinematics()

@@ -195,6 +195,8 @@ class AssistiveEnv(gym.Env):
                 for agent in self.agents:
                     if isinstance(agent, Human):
                         agent.enforce_joint_limits()
+                        if agent.controllable:                   # env.py:230-231
+                            agent.enforce_realistic_joint_limits(getattr(agent, 'env_mask', None))
                 self.update_targets()
 
     def update_targets(self):

@@ -137,3 +137,83 @@ def test_cooptimisation_env_dict_interface(emu_lib):
     assert np.allclose(o['robot'], env._get_obs('robot'))
     assert info['robot']['action_human_len'] == 4 and info['robot']['obs_human_len'] == 23
     env.close()
+
+
+def test_realistic_joint_limit_classifier():
+    """The joint-limit MLP (reference envs/env.py:39, agents/human.py:134-152) compiled out of the Keras file: layer shapes, and the
+    poses the tasks start the person in are reachable while a hyper-extended elbow / a shoulder turned far back are not."""
+    from assistive_gym_b200.limits_model import load_model
+    m = load_model()
+    assert [w.shape for w, _, _ in m.layers] == [(4, 64), (64, 64), (64, 64), (64, 1)] and [a for _, _, a in m.layers] == ['tanh'] * 3 + ['sigmoid']
+
+    def conv(tz, tx, ty, qe, right=True):                       # human.py:141-146
+        s = -1 if right else 1
+        return [(s * tz + 2 * np.pi) % (2 * np.pi), (tx + 2 * np.pi) % (2 * np.pi), s * ty, (-qe + 2 * np.pi) % (2 * np.pi)]
+    d = np.deg2rad
+    ok = m.predict_classes([conv(0, 0, 0, 0), conv(d(30), 0, 0, d(-90)), conv(0, 0, 0, d(-90), right=False)])[:, 0]
+    bad = m.predict_classes([conv(0, 0, 0, d(90)), conv(d(-150), 0, 0, 0), conv(0, 0, 0, d(-150))])[:, 0]
+    assert ok.tolist() == [1, 1, 1] and bad.tolist() == [0, 0, 0]
+    p = m.predict(np.random.default_rng(0).uniform(-7, 7, size=(256, 4)))
+    assert p.shape == (256, 1) and np.all((p >= 0) & (p <= 1))
+
+
+def test_keras_file_compiles_to_the_committed_weights():
+    """tools/compile_assets.py reads the reference's HDF5 file with its own minimal reader (no h5py in this image); skipped on boxes
+    without the reference tree."""
+    import os
+    import sys
+    ref = '/root/reference/assistive_gym/envs/assets/realistic_arm_limits_model.h5'
+    if not os.path.exists(ref):
+        pytest.skip('reference assets not present')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, 'tools'))
+    from compile_assets import compile_keras_mlp
+    from assistive_gym_b200.limits_model import load_model
+    z = compile_keras_mlp(ref)
+    for k, (w, b, act) in enumerate(load_model().layers):
+        assert np.array_equal(z['W%d' % k], w) and np.array_equal(z['b%d' % k], b) and str(z['act%d' % k]) == act
+
+
+def test_cooptimisation_scratch_itch_keeps_the_arm_within_realistic_limits(emu_lib):
+    """ScratchItchJacoHuman-v1 (reference scratch_itch_envs.py, scratch_itch.py:11-12,39-44,75-84, env.py:229-231): dict interface; the
+    person's right arm follows the human action.  Raising the upper arm sideways: the joint itself goes to 198 degrees, the
+    classifier calls everything beyond ~115 degrees (elbow bent) unreachable and sends the arm back to the last reachable pose
+    after every substep -- with the check switched off the same actions take the arm past that."""
+    from assistive_gym_b200 import envs
+    from assistive_gym_b200.limits_model import load_model
+    model = load_model()
+
+    def reachable(q):
+        tz, tx, ty, qe = q[:, 3], q[:, 4], q[:, 5], q[:, 6]
+        x = np.stack([(-tz + 2 * np.pi) % (2 * np.pi), (tx + 2 * np.pi) % (2 * np.pi), -ty, (-qe + 2 * np.pi) % (2 * np.pi)], axis=1)
+        return model.predict_classes(x)[:, 0]
+
+    def run(check):
+        env = envs.make('ScratchItchJacoHuman-v1', n_envs=2, seed=7)
+        env._sim_lib = emu_lib
+        obs = env.reset()
+        assert set(obs) == {'robot', 'human'} and obs['robot'].shape == (2, 30) and obs['human'].shape == (2, 34)
+        assert env.action_space.shape == (17,) and env.action_robot_len == 7 and env.action_human_len == 10
+        active = [env.humans['male' if m else 'female'] for m in env.male]
+        ci = env.human.controllable_joint_indices
+        if not check:
+            for h in env.humans.values():
+                h.enforce_realistic_joint_limits = lambda *a, **k: None
+        a_h = np.zeros((2, 10)); a_h[:, 3] = 1.0                             # j_right_shoulder_x up
+        ok, out = [], None
+        for _ in range(45):
+            out = env.step({'robot': np.zeros((2, 7)), 'human': a_h})
+            q = np.stack([np.atleast_2d(h.get_joint_angles(ci))[e] for e, h in enumerate(active)])
+            ok.append(reachable(q))
+        env_obs_robot = env._get_obs('robot')
+        env.close()
+        return q, np.array(ok), out, env_obs_robot
+    q_on, ok_on, (o, r, d, info), robot_obs = run(True)
+    q_off, ok_off, _, _ = run(False)
+    assert np.all(ok_on == 1)                                               # every step ended in a reachable pose
+    assert np.all(q_on[:, 3] > np.deg2rad(60)) and np.all(q_on[:, 3] < np.deg2rad(125))
+    assert np.all(q_off[:, 3] > np.deg2rad(135)) and not np.all(ok_off == 1)  # without the check the arm goes on
+    assert set(r) == {'robot', 'human'} and np.array_equal(r['robot'], r['human']) and set(d) == {'robot', 'human', '__all__'}
+    assert o['human'].shape == (2, 34) and np.all(np.isfinite(o['human'])) and np.allclose(o['human'][:, 13:23], q_on, atol=1e-6)
+    assert np.allclose(o['robot'], robot_obs)
+    assert info['robot']['action_human_len'] == 10 and info['robot']['obs_human_len'] == 34

@@ -19,6 +19,7 @@ Usage: python tools/compile_assets.py [--ref /root/reference] [--out assistive_g
 import argparse
 import json
 import os
+import sys
 import struct
 import xml.etree.ElementTree as ET
 
@@ -316,6 +317,31 @@ MESHES = {
 }
 
 
+def compile_keras_mlp(path):
+    """Dense layers (kernel [in][out], bias [out], activation) of a Keras Sequential model saved as HDF5: the reference's
+    realistic joint-limit classifier (envs/env.py:39, agents/human.py:134-152), 4 -> 64 -> 64 -> 64 -> 1."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from minih5 import MiniH5
+    h = MiniH5(path)
+    w = {k: v for k, v in h.walk().items() if k.startswith('/model_weights/')}
+    raw = open(path, 'rb').read()
+    i = raw.find(b'{"class_name": "Sequential"')
+    cfg = json.loads(raw[i:raw.find(b'\0', i)].decode())
+    layers = cfg['config'] if isinstance(cfg['config'], list) else cfg['config']['layers']
+    out = {}
+    for n, l in enumerate(layers):
+        assert l['class_name'] == 'Dense' and l['config']['use_bias']
+        name = l['config']['name']
+        out['W%d' % n] = w['/model_weights/%s/%s/kernel:0' % (name, name)].astype(np.float32)
+        out['b%d' % n] = w['/model_weights/%s/%s/bias:0' % (name, name)].astype(np.float32)
+        out['act%d' % n] = np.array(l['config']['activation'])
+    out['n_layers'] = np.array(len(layers))
+    return out
+
+
+MLPS = {'realistic_arm_limits_model': 'realistic_arm_limits_model.h5'}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--ref', default='/root/reference')
@@ -353,6 +379,12 @@ def main():
         v, f = compile_cloth(os.path.join(adir, rel))
         np.savez_compressed(os.path.join(args.out, name + '.agcloth.npz'), verts=v, faces=f)
         print('%-16s cloth nodes=%d faces=%d' % (name, len(v), len(f)))
+    for name, rel in MLPS.items():
+        if args.only and name != args.only:
+            continue
+        m = compile_keras_mlp(os.path.join(adir, rel))
+        np.savez_compressed(os.path.join(args.out, name + '.agmlp.npz'), **m)
+        print('%-16s dense layers: %s' % (name, ' -> '.join([str(m['W0'].shape[0])] + [str(m['W%d' % k].shape[1]) for k in range(int(m['n_layers']))])))
 
 
 if __name__ == '__main__':
