@@ -40,8 +40,31 @@ class Human(Agent):
         self.tremors = np.zeros(10)
         self.motor_forces, self.motor_gains = 1.0, 0.05
         self.gender = 'male'          # per-env genders live in the env (`male` mask); N == 1 mirrors the reference attribute
+        self.limit_scale_env = None   # [n_envs] per-env scale of the joint limits (impairment 'limits', human.py:85, human_creation.py:199-236) or None
         self.limits_model = None      # the realistic joint-limit classifier (human.py:73), loaded on first use
         self.arm_previous_valid_pose = {True: None, False: None}      # human.py:68: per arm, here [n_envs][4] with NaN = none yet
+
+    def set_limit_scale(self, scale):
+        """Per-env joint-limit scale of the `limits` impairment.  The reference bakes it into the person's URDF-like description
+        (human_creation.py:199-236: lower and upper limits times the scale); the batched scene template is shared by the envs, so
+        here it acts through the host-side clamps: the action clamp of `take_step` (controllable limits become [n_envs][k]) and
+        `enforce_joint_limits` after every substep."""
+        self.limit_scale_env = np.asarray(scale, dtype=np.float64).reshape(-1)
+        lo = np.array([self.lower_limits[i] for i in self.controllable_joint_indices]); hi = np.array([self.upper_limits[i] for i in self.controllable_joint_indices])
+        self.controllable_joint_lower_limits = lo[None, :] * self.limit_scale_env[:, None]
+        self.controllable_joint_upper_limits = hi[None, :] * self.limit_scale_env[:, None]
+
+    def enforce_joint_limits(self, indices=None):
+        if self.limit_scale_env is None:
+            return super().enforce_joint_limits(indices)
+        indices = self.all_joint_indices if indices is None else indices
+        g = [self._gl(j) for j in indices]
+        q, qd, _ = self.sim.get_joint_states(g)
+        lo = np.array([self.lower_limits[j] for j in indices])[None, :] * self.limit_scale_env[:, None]
+        hi = np.array([self.upper_limits[j] for j in indices])[None, :] * self.limit_scale_env[:, None]
+        bad = (q < lo) | (q > hi)
+        if bad.any():
+            self.sim.set_joint_state(g, q=np.clip(q, lo, hi), qd=np.where(bad, 0.0, qd))
 
     def enforce_realistic_joint_limits(self, env_mask=None):
         """human.py:134-152, for every env at once: the shoulder / elbow angles of the controllable arm are classified by the

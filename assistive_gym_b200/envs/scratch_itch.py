@@ -143,7 +143,10 @@ class ScratchItchEnv(AssistiveEnv):
             for g, h in self.humans.items():
                 h.env_mask = self.male if g == 'male' else ~self.male
                 h.arm_previous_valid_pose = {True: None, False: None}
+                h.set_limit_scale(s.get('limit_scale', np.ones(self.n_envs)))     # impairment 'limits': scaled joint limits (human.py:85)
+                h.enforce_joint_limits(h.controllable_joint_indices)              # the start pose is clipped to them (human.py:115 set_joint_angles)
                 self.agents.append(h)
+            self.id.forward_kinematics()
         self._limb_links, self._target_local = sb.limb_links(s), s['target_local']
         sb.start_fused(self.id, s)
         self.task_success = np.zeros(self.n_envs, dtype=int)

@@ -99,9 +99,11 @@ class ScratchItchBatch:
                 tl[sel] = point_on_capsule(rng, length, radius, int(sel.sum()))
                 limb_joint[sel] = lj
         imp = rng.integers(0, 3, size=n)                                  # none / limits / weakness ('no_tremor', human.py:82-83)
-        return dict(plane_friction=rng.uniform(0.025, 0.5, size=n), male=male, limb_joint=limb_joint, target_local=tl,
-                    impairment=imp.astype(np.int32), strength=np.where(imp == 2, rng.uniform(0.25, 1.0, size=n), 1.0),
-                    ee_offset=rng.uniform(-0.05, 0.05, size=(n, 3)))
+        s = dict(plane_friction=rng.uniform(0.025, 0.5, size=n), male=male, limb_joint=limb_joint, target_local=tl,
+                 impairment=imp.astype(np.int32), strength=np.where(imp == 2, rng.uniform(0.25, 1.0, size=n), 1.0),
+                 ee_offset=rng.uniform(-0.05, 0.05, size=(n, 3)))
+        s['limit_scale'] = np.where(imp == 1, rng.uniform(0.5, 1.0, size=n), 1.0)      # human.py:85 (drawn last: the other fields keep their values)
+        return s
 
     def place_tool(self, sim, qfull):
         n = sim.n

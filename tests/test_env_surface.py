@@ -191,6 +191,13 @@ def test_cooptimisation_scratch_itch_keeps_the_arm_within_realistic_limits(emu_l
     def run(check):
         env = envs.make('ScratchItchJacoHuman-v1', n_envs=2, seed=7)
         env._sim_lib = emu_lib
+        orig = env._sb.sample
+
+        def sample(n, rng):                                                  # no impairment: full joint limits, full strength
+            smp = orig(n, rng)
+            smp['impairment'][:] = 0; smp['limit_scale'] = np.ones(n); smp['strength'] = np.ones(n)
+            return smp
+        env._sb.sample = sample
         obs = env.reset()
         assert set(obs) == {'robot', 'human'} and obs['robot'].shape == (2, 30) and obs['human'].shape == (2, 34)
         assert env.action_space.shape == (17,) and env.action_robot_len == 7 and env.action_human_len == 10
@@ -217,3 +224,29 @@ def test_cooptimisation_scratch_itch_keeps_the_arm_within_realistic_limits(emu_l
     assert o['human'].shape == (2, 34) and np.all(np.isfinite(o['human'])) and np.allclose(o['human'][:, 13:23], q_on, atol=1e-6)
     assert np.allclose(o['robot'], robot_obs)
     assert info['robot']['action_human_len'] == 10 and info['robot']['obs_human_len'] == 34
+
+
+def test_limits_impairment_scales_the_controllable_arm_limits(emu_lib):
+    """impairment 'limits' (human.py:85, human_creation.py:217-218): in the co-optimisation env the person's joint limits are scaled
+    per env; the start pose is clipped to them and the arm cannot be driven past them."""
+    from assistive_gym_b200 import envs
+    env = envs.make('ScratchItchJacoHuman-v1', n_envs=2, seed=3)
+    env._sim_lib = emu_lib
+    orig = env._sb.sample
+
+    def sample(n, rng):
+        s = orig(n, rng)
+        s['impairment'][:] = [1, 0]; s['limit_scale'] = np.array([0.5, 1.0]); s['strength'][:] = 1.0
+        return s
+    env._sb.sample = sample
+    env.reset()
+    active = [env.humans['male' if m else 'female'] for m in env.male]
+    elbow = lambda: np.array([np.atleast_2d(h.get_joint_angles([6]))[e, 0] for e, h in enumerate(active)])
+    q0 = elbow()
+    assert abs(q0[0] - np.deg2rad(-64)) < 1e-4 and abs(q0[1] - np.deg2rad(-90)) < 1e-4      # -128 degrees x 0.5; the preset elsewhere
+    a_h = np.zeros((2, 10)); a_h[:, 6] = -1.0                                            # bend the elbow further
+    for _ in range(12):
+        env.step({'robot': np.zeros((2, 7)), 'human': a_h})
+    q1 = elbow()
+    assert q1[0] >= np.deg2rad(-64) - 1e-5 and q1[1] < np.deg2rad(-95)
+    env.close()
