@@ -35,10 +35,12 @@ WIPER_CLOTH_LINK = 1                             # `if linkA in [1]`, bed_bathin
 
 
 def orthogonal_vector(v):
-    """util.py:115-121: a vector orthogonal to v."""
+    """util.py:115-121: v crossed with the unit vector of the axis after v's largest component (the start of the rings of
+    `capsule_points`, so the rule has to be the reference's; pinned by tests/test_reference_util_vectors.py)."""
     v = np.asarray(v, dtype=np.float64)
-    x = np.array([1.0, 0, 0]) if abs(v[0]) < 0.9 * np.linalg.norm(v) else np.array([0, 1.0, 0])
-    return np.cross(v, x)
+    y = np.zeros(3)
+    y[(int(np.argmax(np.abs(v))) + 1) % 3] = 1.0
+    return np.cross(v, y)
 
 
 def capsule_points(p1, p2, radius, distance_between_points=0.05):
