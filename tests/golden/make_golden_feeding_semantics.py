@@ -41,8 +41,9 @@ def qrot(q, v):
 class Facade:
     """the pybullet calls of the Feeding step path, answered by an OracleSim with one env"""
 
-    def __init__(self, sim, scene):
-        self.sim, self.sc = sim, scene
+    def __init__(self, sim, scene, f32_targets=False):
+        # f32_targets: motor targets rounded to fp32 before they reach the oracle, as the repo's host mirror (`Agent.control`) hands them over
+        self.sim, self.sc, self.f32 = sim, scene, f32_targets
 
     def gl(self, body, link):
         return int(self.sc['body_link0'][body]) + 1 + int(link)
@@ -73,7 +74,7 @@ class Facade:
 
         def records(c, k, body_a, body_b):
             out = []
-            for i in range(int(k[0])):
+            for i in range(min(int(k[0]), c.shape[1])):
                 r = c[0, i]
                 la, lb = int(r['link_a']) - int(sc['body_link0'][body_a]) - 1, int(r['link_b']) - int(sc['body_link0'][int(sc['link_body'][int(r['link_b'])])]) - 1
                 out.append((0, body_a, body_b, la, lb, np.array(r['pos_a'], dtype=np.float64), np.array(r['pos_b'], dtype=np.float64), np.array(r['normal'], dtype=np.float64),
@@ -82,18 +83,23 @@ class Facade:
 
         def getContactPoints(bodyA=None, bodyB=None, linkIndexA=None, linkIndexB=None, physicsClientId=None):
             c, k = sim.get_contacts(bodyA, -2 if bodyB is None else bodyB, -2 if linkIndexA is None else gl(bodyA, linkIndexA),
-                                    -2 if linkIndexB is None else gl(bodyB, linkIndexB), max_pts=64)
+                                    -2 if linkIndexB is None else gl(bodyB, linkIndexB), max_pts=256)
+            assert int(k[0]) <= 256
             return records(c, k, bodyA, bodyB)
         p.getContactPoints = getContactPoints
 
         def getClosestPoints(bodyA=None, bodyB=None, distance=0.0, linkIndexA=None, linkIndexB=None, physicsClientId=None):
-            c, k = sim.closest_points(bodyA, bodyB, distance, max_pts=64)
+            c, k = sim.closest_points(bodyA, bodyB, distance, max_pts=2048)
+            assert int(k[0]) <= 2048
             return records(c, k, bodyA, bodyB)
         p.getClosestPoints = getClosestPoints
 
         def setJointMotorControlArray(body, jointIndices=None, controlMode=None, targetPositions=None, positionGains=None, forces=None, physicsClientId=None, **k):
             links = [gl(body, j) for j in jointIndices]
-            sim.set_motor(links, 1, target=np.asarray(targetPositions, dtype=np.float64)[None], kp=list(np.asarray(positionGains, dtype=np.float64)),
+            tgt = np.asarray(targetPositions, dtype=np.float64)
+            if self.f32:
+                tgt = tgt.astype(np.float32).astype(np.float64)
+            sim.set_motor(links, 1, target=tgt[None], kp=list(np.asarray(positionGains, dtype=np.float64)),
                           kd=[1.0] * len(links), max_force=list(np.asarray(forces, dtype=np.float64)))
         p.setJointMotorControlArray = setJointMotorControlArray
 
