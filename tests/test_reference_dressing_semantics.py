@@ -1,0 +1,31 @@
+"""`DressingEnv.step` semantics (reference envs/dressing.py:12-106, :199-210 + env.py:174-274 + util.sleeve_on_arm_reward): the
+repo's numpy restatement (`tests/dressing_cases.DressingReference`, which the fused Dressing kernels are checked against in
+tests/test_dressing.py) replays the rollout of tests/golden/dressing_semantics.npz, produced by the reference's OWN step code on
+the CPU oracle (rigid bodies + cloth) through a pybullet facade incl. `getSoftBodyData`
+(tests/golden/make_golden_dressing_semantics.py).  Same physics under both; the cloth forces on the person grow to ~12 N."""
+import os
+
+import numpy as np
+
+from assistive_gym_b200.dressing_batch import DressingBatch
+from oracle.oracle_py import OracleSim
+from tests.dressing_cases import DressingReference
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'dressing_semantics.npz'))
+
+
+def test_restated_dressing_step_reproduces_the_reference_s_rollout():
+    db = DressingBatch()
+    sim = OracleSim(db.scene, DressingBatch.config(), 1)
+    smp = {k[len('sample_'):]: G[k] for k in G.files if k.startswith('sample_')}
+    db.reset(sim, np.random.default_rng(0), sample=smp, settle_steps=0)
+    sim.cloth_set_gravity([0, 0, -9.81 / 2]); sim.step(3); sim.cloth_set_gravity([0, 0, -9.81])
+    ref = DressingReference(db, sim, smp['male'], smp)
+    for t, a in enumerate(G['actions']):
+        obs, rew, done, info = ref.step(a[None])
+        assert np.allclose(obs[0, :23], G['obs'][t][:23], rtol=0, atol=1e-9), (t, np.abs(obs[0] - G['obs'][t]).max())
+        assert abs(obs[0, 23] - G['obs'][t][23]) < 1e-9 * (1 + G['obs'][t][23])          # sum of the filtered cloth forces
+        assert abs(rew[0] - G['reward'][t]) < 1e-9, (t, rew[0], G['reward'][t])
+        assert bool(done[0]) == bool(G['done'][t]) and abs(info[0, 0] - G['total_force'][t]) < 1e-6 * (1 + G['total_force'][t])
+        assert int(info[0, 3]) == int(G['sleeve'][t])
+    assert G['obs'][:, 23].max() > 5
