@@ -1,0 +1,140 @@
+"""The batched scene builders against what the reference's OWN `reset()` asks the physics engine to build
+(tests/golden/reset_recipes.json, recorded by tests/golden/make_golden_reset_recipes.py: the reference package run against a
+recording pybullet).  Link states are the origin in the recording, so tool and food placements appear there as the offsets the
+reference composes; randomised quantities (bowl offset, IK target offset, head angles, plane friction) are checked as
+"nominal + range"."""
+import inspect
+import json
+import os
+
+import numpy as np
+
+from assistive_gym_b200 import capi
+from assistive_gym_b200.feeding_batch import HUMAN_PRESET as FEED_PRESET
+from assistive_gym_b200.feeding_batch import JACO as FEED_JACO
+from assistive_gym_b200.feeding_batch import TREMOR_JOINTS, FeedingBatch
+from assistive_gym_b200.kinematics import q_from_rpy
+from assistive_gym_b200.scratch_itch_batch import HUMAN_PRESET as SCRATCH_PRESET
+from assistive_gym_b200.scratch_itch_batch import JACO as SCRATCH_JACO
+from assistive_gym_b200.scratch_itch_batch import RIGHT_ARM_JOINTS, ScratchItchBatch
+from oracle.oracle_py import OracleSim
+
+G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reset_recipes.json')))
+
+
+def _by(calls, fn):
+    return [c for c in calls if c['fn'] == fn]
+
+
+def _same_rotation(qa, qb):
+    return min(np.abs(np.asarray(qa) - np.asarray(qb)).max(), np.abs(np.asarray(qa) + np.asarray(qb)).max()) < 1e-9
+
+
+def _common(g, batch, jaco, preset, task_gripper, ik_nominal):
+    sc = batch.scene
+    loads = {c['args'][0]: c['kw'] for c in _by(g['calls'], 'loadURDF')}
+    last_pose = {}
+    for c in _by(g['calls'], 'resetBasePositionAndOrientation'):
+        last_pose[c['args'][0]] = c['kw']
+    gender = g['human_gender']
+    # bodies: where the reference puts them
+    assert np.allclose(loads['wheelchair_jaco.urdf']['basePosition'], sc['base_pos0'][batch.wheelchair])
+    assert np.allclose(last_pose[g['robot_body']]['pos'], batch.robot_base_pos) and _same_rotation(last_pose[g['robot_body']]['orn'], batch.robot_base_quat)
+    assert np.allclose(last_pose[g['human_body']]['pos'], batch.builder.bodies[batch.humans[gender]].base_pos)
+    # the tool rides on a fixed constraint at link 8 with the task's offsets, 500 N
+    con = _by(g['calls'], 'createConstraint')[0]
+    assert con['args'][:5] == [g['robot_body'], jaco['tool_joint'], g['tool_body'], -1, 4]
+    assert np.allclose(con['kw']['parentFramePosition'], batch.tool_pos_offset) and _same_rotation(con['kw']['parentFrameOrientation'], batch.tool_quat_offset)
+    assert _by(g['calls'], 'changeConstraint')[0]['kw']['maxForce'] == 500 == float(sc['con_maxforce'][0])
+    cl = np.asarray(sc['con_link']).ravel()
+    assert int(cl[0]) == batch.gl(batch.robot, jaco['tool_joint']) and int(cl[1]) == int(sc['body_link0'][batch.tool])
+    # gravity: off for robot, person and tool, on for everything else
+    off = {c['kw']['body'] for c in _by(g['calls'], 'setGravity') if 'body' in c['kw'] and c['args'] == [0, 0, 0]}
+    assert off == {g['robot_body'], g['human_body'], g['tool_body']}
+    assert _by(g['calls'], 'setGravity')[0]['args'] == [0, 0, -9.81]
+    gz = np.asarray(sc['body_gravity'])[:, 2]
+    for b in (batch.robot, batch.tool, batch.humans['male'], batch.humans['female']):
+        assert gz[b] == 0.0
+    assert gz[batch.wheelchair] == -9.81 and gz[batch.plane] == -9.81
+    # the person's joint presets; joints whose range excludes 0 start at the nearer limit (human_creation.py:301-314)
+    resets, seen = {}, {}
+    for r in g['human_joint_resets']:                                        # (the recorder's joint states are always 0, so later limit checks write the limit again)
+        resets.setdefault(r['joint'], r['value'])
+        seen.setdefault(r['joint'], []).append(r['value'])
+    for j, deg in preset.items():
+        assert any(abs(v - np.deg2rad(deg)) < 1e-12 for v in seen[j]), (j, seen[j])
+    hb = batch.humans[gender]
+    for j in (3, 13):
+        lo, hi = float(sc['link_lower'][batch.gl(hb, j)]), float(sc['link_upper'][batch.gl(hb, j)])
+        want = float(np.clip(0.0, lo, hi))                                       # the creation-time clamp of the zero pose
+        assert abs(resets[j] - want) < 1e-9, (j, resets[j], want)
+    # gripper opened to the task's position with gain 0.05 / 500 N (robot.py:76-79)
+    grip = [c for c in _by(g['calls'], 'setJointMotorControlArray') if c['args'][0] == g['robot_body']][0]['kw']
+    assert grip['jointIndices'] == jaco['gripper'] and np.allclose(grip['targetPositions'], task_gripper) and np.allclose(grip['positionGains'], 0.05) and np.allclose(grip['forces'], 500)
+    assert np.allclose(jaco['gripper_pos'], task_gripper)
+    # IK goal of the start pose: nominal + U(-0.05, 0.05)^3, the task's end-effector orientation
+    ik = _by(g['calls'], 'calculateInverseKinematics')[0]
+    assert ik['args'] == [g['robot_body'], jaco['ee']] and np.all(np.abs(np.array(ik['kw']['targetPosition']) - ik_nominal) <= 0.05 + 1e-12)
+    assert _same_rotation(ik['kw']['targetOrientation'], q_from_rpy(jaco['ee_orient_rpy']))
+    fr = [c['kw']['lateralFriction'] for c in _by(g['calls'], 'changeDynamics') if c['args'] == [0, -1] and 'lateralFriction' in c['kw']][0]
+    assert 0.025 <= fr <= 0.5
+    smp = batch.sample(256, np.random.default_rng(0))
+    assert smp['plane_friction'].min() >= 0.025 and smp['plane_friction'].max() <= 0.5 and np.abs(smp['ee_offset']).max() <= 0.05
+    return loads, last_pose, resets
+
+
+def test_feeding_scene_recipe_is_the_reference_s():
+    g = G['feeding']
+    fb = FeedingBatch()
+    sc = fb.scene
+    loads, last_pose, resets = _common(g, fb, FEED_JACO, FEED_PRESET, [1.33] * 3, np.array([-0.15, -0.65, 1.15]))
+    assert np.allclose(loads['table_tall.urdf']['basePosition'], sc['base_pos0'][fb.table])
+    bowl = np.array(loads['bowl.urdf']['basePosition'])
+    assert np.all(np.abs(bowl[:2] - [-0.15, -0.65]) <= 0.05) and bowl[2] == 0.75
+    assert np.abs(fb.sample(256, np.random.default_rng(1))['bowl_offset'][:, :2]).max() <= 0.05
+    for j in (21, 22, 23):                                                   # the head: U(-30, 30) degrees (feeding.py:125)
+        assert abs(resets[j]) <= np.deg2rad(30)
+    assert g['motor_gains'] == {'robot': 0.025, 'human': 0.025}              # feeding.py:122
+    assert g['n_step_simulation'] == 25 == inspect.signature(fb.reset).parameters['settle_steps'].default
+    # every joint of a person without tremor is made static (mass 0); the template keeps only the head chain's mass for the tremor envs
+    assert g['human_zero_mass_joints'] == list(range(42))
+    hb = fb.humans[g['human_gender']]
+    assert all(float(sc['link_mass'][fb.gl(hb, j)]) == 0.0 for j in range(42) if j not in TREMOR_JOINTS)
+    # the spoon: the reference's mesh at scale 0.08, 1 kg
+    spoon_shape = [c['kw'] for c in _by(g['calls'], 'createCollisionShape') if c['kw'].get('fileName') == 'spoon_vhacd.obj'][0]
+    assert spoon_shape['meshScale'] == [0.08] * 3
+    mb = {c['kw']['bodies'][0]: c['kw'] for c in _by(g['calls'], 'createMultiBody')}
+    assert mb[g['tool_body']]['baseMass'] == 1 == float(sc['link_mass'][int(sc['body_link0'][fb.tool])])
+    # the food: 8 spheres of radius 5 mm and 1 g on a 2 x 2 x 2 grid above the spoon
+    food = [c['kw'] for c in _by(g['calls'], 'createMultiBody') if 'batchPositions' in c['kw']][0]
+    assert len(food['bodies']) == 8 == len(fb.foods) and food['baseMass'] == 0.001
+    food_shape = _by(g['calls'], 'createCollisionShape')[food['baseCollisionShapeIndex']]['kw']
+    assert food_shape['shapeType'] == 2 and food_shape['radius'] == 0.005
+    offsets = np.array(food['batchPositions']) - np.array(last_pose[g['tool_body']]['pos'])
+    sim = OracleSim(sc, capi.default_config(), 1)
+    fb.reset(sim, np.random.default_rng(0), settle_steps=0, impairment='none')
+    ls = sim.get_link_states([int(sc['body_link0'][fb.tool])] + [int(sc['body_link0'][f]) for f in fb.foods])
+    ours = ls['pos'][0, 1:] - ls['com_pos'][0, 0]
+    assert np.allclose(ours, offsets, atol=1e-9)
+    for f in fb.foods:
+        k = int(sc['body_link0'][f])
+        c = int(np.where(np.asarray(sc['col_link']) == k)[0][0])
+        assert abs(float(sc['link_mass'][k]) - 0.001) < 1e-15 and abs(float(sc['col_radius'][c]) - 0.005) < 1e-15
+
+
+def test_scratch_itch_scene_recipe_is_the_reference_s():
+    g = G['scratch_itch']
+    sb = ScratchItchBatch()
+    sc = sb.scene
+    loads, last_pose, resets = _common(g, sb, SCRATCH_JACO, SCRATCH_PRESET, [1.0] * 3, np.array([-0.6, 0.0, 0.8]))
+    assert g['motor_gains'] == {'robot': 0.05, 'human': 0.05} and g['n_step_simulation'] == 0
+    # the scratcher is loaded at the gripper with the task's offsets (tool.py:20-25)
+    assert np.allclose(loads['tool_scratch.urdf']['basePosition'], sb.tool_pos_offset) and _same_rotation(loads['tool_scratch.urdf']['baseOrientation'], sb.tool_quat_offset)
+    # the person's right arm stays dynamic and is held by position motors of gain 0.01 and force 1 x strength (human.py:123-127)
+    assert g['human_zero_mass_joints'] == [j for j in range(42) if j not in RIGHT_ARM_JOINTS]
+    hold = [c for c in _by(g['calls'], 'setJointMotorControlArray') if c['args'][0] == g['human_body']][0]['kw']
+    assert hold['jointIndices'] == RIGHT_ARM_JOINTS and np.allclose(hold['positionGains'], 0.01)
+    assert 0.25 <= hold['forces'][0] <= 1.0 and len(set(hold['forces'])) == 1
+    hb = sb.humans[g['human_gender']]
+    assert all(float(sc['link_mass'][sb.gl(hb, j)]) == 0.0 for j in range(42) if j not in RIGHT_ARM_JOINTS)
+    assert all(float(sc['link_mass'][sb.gl(hb, j)]) > 0.0 or j in (3, 4, 0, 1, 6, 8) for j in RIGHT_ARM_JOINTS)     # (massless helper links of the 3-axis joints)
