@@ -106,6 +106,27 @@ def main():
             steps.append(dict(q=q.tolist(), action=a.tolist(), **jsonable(got)))
         t['take_step'] = dict(lower=lo.tolist(), upper=hi.tolist(), steps=steps)
         out['tasks'][cls.__name__] = jsonable(t)
+    # ---- the base-pose ranking of Robot.position_robot_toc (agents/robot.py:173-186, :223-235): the joint-limit weighting method and the two
+    # source lines that turn J and the weights into the JLWKI score, executed as they stand in the reference file
+    import inspect
+    from assistive_gym.envs.agents.jaco import Jaco
+    rob = Jaco('right')
+    src = inspect.getsource(type(rob).position_robot_toc).split('\n')
+    formula = [ln.strip() for ln in src if ln.strip().startswith('det = ') or ln.strip().startswith('jlwki = ')]
+    assert len(formula) == 2
+    cases = []
+    for _ in range(40):
+        lo, hi = rng.uniform(-3, -0.5, size=7), rng.uniform(0.5, 3, size=7)
+        q = rng.uniform(lo - 0.1, hi + 0.1)
+        if rng.random() < 0.5:
+            q = np.where(rng.random(7) < 0.4, np.where(rng.random(7) < 0.5, lo + 0.02, hi - 0.02), q)
+        J = rng.normal(size=(6, 7))
+        W = rob.joint_limited_weighting(q, lo, hi)
+        ns = dict(np=np, J=J, joint_limit_weight=W, a=6)
+        for ln in formula:
+            exec(ln, ns)
+        cases.append(dict(q=q.tolist(), lower=lo.tolist(), upper=hi.tolist(), J=J.tolist(), weights=np.diag(W).tolist(), jlwki=float(ns['jlwki'])))
+    out['jlwki'] = cases
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'env_logic.json')
     json.dump(out, open(path, 'w'), separators=(',', ':'))
     print('wrote', path, {k: (v['task'], v['obs_robot_len'], len(v['take_step']['steps'])) for k, v in out['tasks'].items()})

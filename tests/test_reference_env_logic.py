@@ -12,7 +12,8 @@ from assistive_gym_b200 import envs
 from assistive_gym_b200.envs.agents.robot import PR2, Jaco, Sawyer
 from tests.parity_cases import take_step_targets
 
-G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'env_logic.json')))['tasks']
+_ALL = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'env_logic.json')))
+G = _ALL['tasks']
 OURS = {'FeedingJacoEnv': ('FeedingJaco-v1', Jaco, 'right'), 'BedBathingSawyerEnv': ('BedBathingSawyer-v1', Sawyer, 'left'),
         'DressingPR2Env': ('DressingPR2-v1', PR2, 'left'), 'ScratchItchJacoEnv': ('ScratchItchJaco-v1', Jaco, 'left')}
 
@@ -72,3 +73,15 @@ def test_robot_constant_tables_are_the_reference_s(name):
             assert task not in v or task in ours, (k, task)              # the entry of the task this env is built for must be there
         else:
             assert np.allclose(np.asarray(ours, dtype=np.float64), np.asarray(v, dtype=np.float64), atol=1e-12), k
+
+
+def test_base_pose_ranking_score_is_the_reference_s():
+    """joint-limit weighting and the JLWKI score of `position_robot_toc` (agents/robot.py:173-186, :223-235) as `toc.py` restates them"""
+    from assistive_gym_b200.toc import jlwki, joint_limited_weighting
+    floor = 0
+    for c in _ALL['jlwki']:
+        q, lo, hi, J = (np.array(c[k]) for k in ('q', 'lower', 'upper', 'J'))
+        assert np.allclose(joint_limited_weighting(q, lo, hi), c['weights'], rtol=1e-12, atol=1e-15)
+        assert abs(jlwki(J[None], q[None], lo, hi)[0] - c['jlwki']) < 1e-12 * (1 + c['jlwki'])
+        floor += int(np.any(np.array(c['weights']) == 0.001))
+    assert floor >= 1                                                     # the 0.001 floor (angles at / beyond a limit) is exercised
