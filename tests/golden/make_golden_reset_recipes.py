@@ -45,7 +45,7 @@ def dfs_order(parents):
 
 class Recorder:
     def __init__(self):
-        self.calls, self.bodies, self.pose, self.shapes, self.ik_calls = [], [], {}, [], 0
+        self.calls, self.bodies, self.pose, self.shapes, self.ik_calls, self.ik_goal = [], [], {}, [], 0, {}
 
     def install(self):
         R = self
@@ -128,7 +128,11 @@ class Recorder:
         m.getJointState = lambda body, j, physicsClientId=None: (0.0, 0.0, (0.0,) * 6, 0.0)
         m.getJointStates = lambda body, jointIndices=None, physicsClientId=None: [(0.0, 0.0, (0.0,) * 6, 0.0) for _ in jointIndices]
         origin = (np.zeros(3), np.array([0, 0, 0, 1.0]))
-        m.getLinkState = lambda body, link, **k: (origin[0], origin[1], origin[0], origin[1], origin[0], origin[1], np.zeros(3), np.zeros(3))
+        def getLinkState(body, link, **k):
+            # the link an IK call was last asked to move is reported AT the goal (the search loops of position_robot_toc then terminate)
+            pos, orn = R.ik_goal.get((int(body), int(link)), origin)
+            return (pos, orn, origin[0], origin[1], pos, orn, np.zeros(3), np.zeros(3))
+        m.getLinkState = getLinkState
         m.getBasePositionAndOrientation = lambda body, physicsClientId=None: R.pose.get(int(body), origin)
         m.getBaseVelocity = lambda body, physicsClientId=None: (np.zeros(3), np.zeros(3))
 
@@ -146,6 +150,7 @@ class Recorder:
                 R.calls.append(('calculateInverseKinematics', (int(body), int(ee)), dict(targetPosition=np.asarray(targetPosition, float).tolist(),
                                 targetOrientation=None if targetOrientation is None else np.asarray(targetOrientation, float).tolist())))
             R.ik_calls += 1
+            R.ik_goal[(int(body), int(ee))] = (np.asarray(targetPosition, float), origin[1] if targetOrientation is None else np.asarray(targetOrientation, float))
             return np.zeros(max(1, sum(1 for j in range(nj(body)) if getJointInfo(body, j)[2] != 4)))
         m.calculateInverseKinematics = ik
 
@@ -162,6 +167,11 @@ class Recorder:
         m.invertTransform = inv
         m.multiplyTransforms = lambda positionA=None, orientationA=None, positionB=None, orientationB=None, physicsClientId=None: (
             np.asarray(positionA, float) + qrot(orientationA, positionB), qmul(np.asarray(orientationA, float), np.asarray(orientationB, float)))
+        def jac(body, link, localPosition=None, objPositions=None, objVelocities=None, objAccelerations=None, physicsClientId=None):
+            n = len(objPositions)
+            g = np.random.RandomState(0).normal(size=(6, n))
+            return g[:3].tolist(), g[3:].tolist()
+        m.calculateJacobian = jac
         m.connect = lambda *a, **k: 0
         return m
 
@@ -191,9 +201,8 @@ def main():
     ref = sys.argv[1] if len(sys.argv) > 1 else '/root/reference'
     install_stubs(ref)
     out = {}
-    # (BedBathing and Dressing place the robot with `position_robot_toc`, whose search loops do not terminate on a recorder whose IK
-    #  always answers zeros; their recipes are not recorded)
-    for key, path in (('feeding', 'assistive_gym.envs.feeding_envs.FeedingJacoEnv'), ('scratch_itch', 'assistive_gym.envs.scratch_itch_envs.ScratchItchJacoEnv')):
+    for key, path in (('feeding', 'assistive_gym.envs.feeding_envs.FeedingJacoEnv'), ('scratch_itch', 'assistive_gym.envs.scratch_itch_envs.ScratchItchJacoEnv'),
+                      ('bed_bathing', 'assistive_gym.envs.bed_bathing_envs.BedBathingSawyerEnv'), ('dressing', 'assistive_gym.envs.dressing_envs.DressingPR2Env')):
         try:
             out[key] = record(path)
             print(key, 'ok:', len(out[key]['calls']), 'calls kept,', out[key]['n_step_simulation'], 'stepSimulation')

@@ -138,3 +138,105 @@ def test_scratch_itch_scene_recipe_is_the_reference_s():
     hb = sb.humans[g['human_gender']]
     assert all(float(sc['link_mass'][sb.gl(hb, j)]) == 0.0 for j in range(42) if j not in RIGHT_ARM_JOINTS)
     assert all(float(sc['link_mass'][sb.gl(hb, j)]) > 0.0 or j in (3, 4, 0, 1, 6, 8) for j in RIGHT_ARM_JOINTS)     # (massless helper links of the 3-axis joints)
+
+
+def test_bed_bathing_scene_recipe_is_the_reference_s():
+    from assistive_gym_b200.bed_bathing_batch import SAWYER, BedBathingBatch
+    g = G['bed_bathing']
+    bb = BedBathingBatch()
+    sc = bb.scene
+    loads = {c['args'][0]: c['kw'] for c in _by(g['calls'], 'loadURDF')}
+    assert np.allclose(loads['bed.urdf']['basePosition'], sc['base_pos0'][bb.bed]) and loads['sawyer.urdf']['useFixedBase'] == 1
+    assert [c['kw'] for c in _by(g['calls'], 'changeDynamics') if c['args'] == [g['bodies'] and 3, -1] and 'lateralFriction' in c['kw']][0]['lateralFriction'] == 5
+    # the person is laid on the bed: base pose (-0.15, 0.2, 0.95) turned by -90 degrees about x, every joint perturbed by U(-0.1, 0.1), right shoulder 30 degrees,
+    # dropped for 100 steps under (0, 0, -1), then made static (bed_bathing.py:118-137)
+    lying = [c['kw'] for c in _by(g['calls'], 'resetBasePositionAndOrientation') if c['args'] == [g['human_body']]][-1]
+    assert np.allclose(lying['pos'], [-0.15, 0.2, 0.95]) and _same_rotation(lying['orn'], q_from_rpy([-np.pi / 2.0, 0, 0]))
+    seen = {}
+    for r in g['human_joint_resets']:
+        seen.setdefault(r['joint'], []).append(r['value'])
+    assert any(abs(v - np.deg2rad(30)) < 1e-12 for v in seen[3])
+    assert all(abs(v[0]) <= 0.1 for j, v in seen.items() if j not in (3, 13))
+    smp = bb.sample(64, np.random.default_rng(0))
+    assert np.abs(smp['joint_noise']).max() <= 0.1
+    assert g['n_step_simulation'] == 100 and [0, 0, -1] in [c['args'] for c in _by(g['calls'], 'setGravity') if not c['kw']]
+    assert set(range(42)) <= set(g['human_zero_mass_joints'])
+    for hb in bb.humans.values():
+        assert all(float(sc['link_mass'][bb.gl(hb, j)]) == 0.0 for j in range(42))
+    # gravity after the drop: robot and wiper 0, the person (0, 0, -1) (bed_bathing.py:157-163)
+    per_body = {c['kw']['body']: c['args'] for c in _by(g['calls'], 'setGravity') if 'body' in c['kw']}
+    assert per_body == {g['robot_body']: [0, 0, 0], g['human_body']: [0, 0, -1], g['tool_body']: [0, 0, 0]}
+    gv = np.asarray(sc['body_gravity'])
+    assert np.allclose(gv[bb.robot], 0) and np.allclose(gv[bb.tool], 0) and all(np.allclose(gv[hb], [0, 0, -1]) for hb in bb.humans.values())
+    # the wiper on a fixed constraint at link 18 with the task's offsets
+    con = _by(g['calls'], 'createConstraint')[0]
+    assert con['args'][:5] == [g['robot_body'], SAWYER['tool_joint'], g['tool_body'], -1, 4]
+    assert np.allclose(con['kw']['parentFramePosition'], bb.tool_pos_offset) and _same_rotation(con['kw']['parentFrameOrientation'], bb.tool_quat_offset)
+    assert _by(g['calls'], 'changeConstraint')[0]['kw']['maxForce'] == 500 == float(sc['con_maxforce'][0])
+    grip = [c for c in _by(g['calls'], 'setJointMotorControlArray') if c['args'][0] == g['robot_body']][0]['kw']
+    assert grip['jointIndices'] == SAWYER['gripper'] and np.allclose(grip['targetPositions'], SAWYER['gripper_pos']) and np.allclose(grip['forces'], 500)
+    # base-pose search: (-0.85, -0.4, 0) + the task's offset + (U(-0.5, 0), U(-0.5, 0.5), 0), yaw U(-30, 30) degrees (robot.py:142-144)
+    base0 = np.array([-0.85, -0.4, 0]) + np.array(SAWYER['toc_base_pos_offset'])
+    poses = [c['kw'] for c in _by(g['calls'], 'resetBasePositionAndOrientation') if c['args'] == [g['robot_body']]]
+    d = np.array([p['pos'] for p in poses]) - base0
+    assert len(poses) >= 50 and d[:, 0].min() >= -0.5 and d[:, 0].max() <= 0 and np.abs(d[:, 1]).max() <= 0.5 and np.allclose(d[:, 2], 0)
+    yaw = np.array([2 * np.arctan2(p['orn'][2], p['orn'][3]) for p in poses])
+    assert np.abs(yaw).max() <= np.deg2rad(30) + 1e-9 and np.allclose([p['orn'][:2] for p in poses], 0)
+    ik = _by(g['calls'], 'calculateInverseKinematics')[0]
+    assert ik['args'] == [g['robot_body'], SAWYER['ee']] and np.all(np.abs(np.array(ik['kw']['targetPosition']) - [-0.6, 0.2, 1.0]) <= 0.05 + 1e-12)
+    assert _same_rotation(ik['kw']['targetOrientation'], q_from_rpy(SAWYER['ee_orient_rpy']))
+    assert g['motor_gains'] == {'robot': 0.05, 'human': 0.05}
+
+
+def test_dressing_scene_recipe_is_the_reference_s():
+    from assistive_gym_b200.cloth import DRESSING_PARAMS
+    from assistive_gym_b200.dressing_batch import CLOTH_ANCHORS, CLOTH_ORIG_POS, CLOTH_POSITION, CLOTH_SCALE, LEFT_ARM_JOINTS, PR2, DressingBatch
+    from assistive_gym_b200.dressing_batch import HUMAN_PRESET as DRESS_PRESET
+    g = G['dressing']
+    db = DressingBatch()
+    sc = db.scene
+    loads = {c['args'][0]: c['kw'] for c in _by(g['calls'], 'loadURDF')}
+    assert np.allclose(loads['wheelchair.urdf']['basePosition'], sc['base_pos0'][db.wheelchair]) and loads['pr2_no_torso_lift_tall.urdf']['useFixedBase'] == 1
+    seen = {}
+    for r in g['human_joint_resets']:
+        seen.setdefault(r['joint'], []).append(r['value'])
+    for j, deg in DRESS_PRESET.items():
+        assert any(abs(v - np.deg2rad(deg)) < 1e-12 for v in seen[j]), (j, seen[j])
+    # the left arm is held by position motors of gain 0.01 and force 1 x strength; everything else of the person is static
+    hold = [c for c in _by(g['calls'], 'setJointMotorControlArray') if c['args'][0] == g['human_body']][0]['kw']
+    assert hold['jointIndices'] == LEFT_ARM_JOINTS and np.allclose(hold['positionGains'], 0.01) and 0.25 <= hold['forces'][0] <= 1.0
+    assert g['human_zero_mass_joints'] == [j for j in range(42) if j not in LEFT_ARM_JOINTS]
+    assert g['motor_gains'] == {'robot': 0.01, 'human': 0.01}                # dressing.py:121
+    # base-pose search on the person's left (right_side=False): x offset U(0, 0.5), facing backwards (yaw pi +- 30 degrees)
+    base0 = np.array([-0.85, -0.4, 0]) + np.array(PR2['toc_base_pos_offset'])
+    poses = [c['kw'] for c in _by(g['calls'], 'resetBasePositionAndOrientation') if c['args'] == [g['robot_body']]]
+    d = np.array([p['pos'] for p in poses]) - base0
+    assert len(poses) >= 50 and d[:, 0].min() >= 0 and d[:, 0].max() <= 0.5 and np.abs(d[:, 1]).max() <= 0.5 and np.allclose(d[:, 2], 0)
+    yaw = np.array([2 * np.arctan2(p['orn'][2], p['orn'][3]) for p in poses])
+    assert np.abs(np.abs(yaw) - np.pi).max() <= np.deg2rad(30) + 1e-9
+    # start goal and the three arm goals 10 cm above shoulder / elbow / wrist with the task's orientations (dressing.py:129-134)
+    iks = _by(g['calls'], 'calculateInverseKinematics')
+    assert iks[0]['args'] == [g['robot_body'], PR2['ee']] and np.all(np.abs(np.array(iks[0]['kw']['targetPosition']) - [0.45, -0.3, 1.0]) <= 0.05 + 1e-12)
+    assert _same_rotation(iks[0]['kw']['targetOrientation'], q_from_rpy(PR2['ee_orient_rpy']))
+    assert np.allclose(iks[1]['kw']['targetPosition'], [0, 0, 0.1]) and _same_rotation(iks[1]['kw']['targetOrientation'], q_from_rpy(PR2['ee_orient_shoulder_rpy']))
+    assert _same_rotation(iks[2]['kw']['targetOrientation'], q_from_rpy(PR2['ee_orient_rpy'])) and _same_rotation(iks[3]['kw']['targetOrientation'], q_from_rpy(PR2['ee_orient_rpy']))
+    grip = [c for c in _by(g['calls'], 'setJointMotorControlArray') if c['args'][0] == g['robot_body']][0]['kw']
+    assert grip['jointIndices'] == PR2['gripper'] and np.allclose(grip['targetPositions'], PR2['gripper_pos']) and np.allclose(grip['forces'], 500)
+    # the gown: mesh scale, mass, anchors, margin, solver coefficients; placed relative to the end effector (at the origin in the recording)
+    cloth = _by(g['calls'], 'loadCloth')[0]['kw']
+    assert cloth['scale'] == CLOTH_SCALE == 1.4 and cloth['mass'] == DRESSING_PARAMS['total_mass'] and cloth['anchors'] == CLOTH_ANCHORS
+    assert cloth['collisionMargin'] == DRESSING_PARAMS['margin'] and _same_rotation(cloth['orientation'], db.cloth_quat)
+    start_ee = np.array(iks[3]['kw']['targetPosition'])                     # where the recorder reports the end effector: at the last IK goal
+    assert np.allclose(cloth['position'], CLOTH_POSITION + (start_ee - CLOTH_ORIG_POS) / CLOTH_SCALE, atol=1e-9)          # dressing.py:139-146
+    cp = _by(g['calls'], 'clothParams')[0]['kw']
+    for k in ('kLST', 'kDP', 'kDG', 'kDF', 'kCHR', 'kKHR', 'kAHR', 'piterations'):
+        assert cp[k] == DRESSING_PARAMS[k], k
+    # gravity: halved while the gown settles for 50 steps, robot 0, person (0, 0, -1); 8 substeps per stepSimulation
+    glob = [c['args'] for c in _by(g['calls'], 'setGravity') if not c['kw']]
+    assert glob == [[0, 0, -9.81], [0, 0, -9.81 / 2], [0, 0, -9.81]] and g['n_step_simulation'] == 50
+    assert inspect.signature(db.reset).parameters['settle_steps'].default == 50
+    per_body = {c['kw']['body']: c['args'] for c in _by(g['calls'], 'setGravity') if 'body' in c['kw']}
+    assert per_body[g['robot_body']] == [0, 0, 0] and per_body[g['human_body']] == [0, 0, -1]
+    gv = np.asarray(sc['body_gravity'])
+    assert np.allclose(gv[db.robot], 0) and all(np.allclose(gv[hb], [0, 0, -1]) for hb in db.humans.values())
+    assert _by(g['calls'], 'setPhysicsEngineParameter')[0]['kw'] == {'numSubSteps': 8} and DressingBatch.config().num_substeps == 8
