@@ -7,9 +7,13 @@
 // vendored, not installable here — SURVEY.md §8(c)).  The reference has no tests / golden vectors.
 // This file restates the *published algorithms* Bullet uses for the path (Featherstone articulated
 // body dynamics, GJK, projected Gauss-Seidel with Bullet's row conventions as recalled in
-// SURVEY.md Appendix A).  It is checked against analytic known answers in tests/, not against
-// PyBullet.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-// legs may load this library.
+// SURVEY.md Appendix A).  It is checked against analytic known answers in tests/ (and, for the
+// articulated dynamics, against independently derived Lagrange equations), not against PyBullet:
+// the PHYSICS is unpinned.  What is pinned to the reference's own code is everything around it --
+// tests/golden/make_golden_*.py run the reference's env.step / reset / helper functions on this
+// oracle through a pybullet facade and the repo's restatements must reproduce those rollouts
+// (DESIGN.md section 5).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs may load this library.
 //
 // Deliberately independent of the CUDA implementation:
 //   * double precision, array-of-structs, one env at a time,
