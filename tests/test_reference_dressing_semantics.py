@@ -29,3 +29,22 @@ def test_restated_dressing_step_reproduces_the_reference_s_rollout():
         assert bool(done[0]) == bool(G['done'][t]) and abs(info[0, 0] - G['total_force'][t]) < 1e-6 * (1 + G['total_force'][t])
         assert int(info[0, 3]) == int(G['sleeve'][t])
     assert G['obs'][:, 23].max() > 5
+
+
+def test_restated_dressing_step_with_a_tremor_person_reproduces_the_reference_s_rollout():
+    """the same with the `tremor` impairment (env.py:130-131, :212-215): the ten left-arm joints shake about their rest targets
+    (tests/golden/make_golden_dressing_tremor_semantics.py); `DressingReference`'s tremor branch is what `dressing_pre_body` is checked against"""
+    Gt = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'dressing_tremor_semantics.npz'))
+    db = DressingBatch()
+    sim = OracleSim(db.scene, DressingBatch.config(), 1)
+    smp = {k[len('sample_'):]: Gt[k] for k in Gt.files if k.startswith('sample_')}
+    assert smp['impairment'][0] == 3 and np.abs(smp['tremors']).max() > 0.1
+    db.reset(sim, np.random.default_rng(0), sample=smp, settle_steps=0)
+    sim.cloth_set_gravity([0, 0, -9.81 / 2]); sim.step(3); sim.cloth_set_gravity([0, 0, -9.81])
+    ref = DressingReference(db, sim, smp['male'], smp)
+    for t, a in enumerate(Gt['actions']):
+        obs, rew, done, info = ref.step(a[None])
+        assert np.allclose(obs[0, :23], Gt['obs'][t][:23], rtol=0, atol=1e-9), (t, np.abs(obs[0] - Gt['obs'][t]).max())
+        assert abs(obs[0, 23] - Gt['obs'][t][23]) < 1e-9 * (1 + Gt['obs'][t][23]) and abs(rew[0] - Gt['reward'][t]) < 1e-9
+    # the shaking arm changes the rollout: it is not the one without tremor
+    assert np.abs(Gt['obs'][:, 14:23] - G['obs'][:, 14:23]).max() > 1e-3
