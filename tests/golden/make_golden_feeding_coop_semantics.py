@@ -76,6 +76,7 @@ def main():
     env.action_robot_len, env.action_human_len = 7, 4
     env.np_random = np.random.RandomState(0)
     env.update_targets()
+    start_state = sim.state_get()                                       # stored: the replay does not depend on the IK of the reset being bit-reproducible
     arng = np.random.default_rng(SEED + 1)
     a_r = arng.uniform(-1, 1, size=(N_STEPS, 7)) * 0.3
     a_h = np.concatenate([np.tile([0.0, 1.0, -1.0, 1.0], (N_STEPS // 2, 1)), np.tile([0.0, -1.0, 1.0, -1.0], (N_STEPS - N_STEPS // 2, 1))])     # nod / turn until a limit, then back
@@ -88,6 +89,7 @@ def main():
     out = {('sample_' + k): np.asarray(v) for k, v in smp.items()}
     out.update(robot_actions=a_r, human_actions=a_h, obs_robot=np.array(obs_r), obs_human=np.array(obs_h), reward=np.array(rew), head_q=head, seed=np.array(SEED),
                head_lower=np.array([h.lower_limits[j] for j in HEAD]), head_upper=np.array([h.upper_limits[j] for j in HEAD]))
+    out['start_state'] = start_state
     np.savez_compressed(os.path.join(HERE, 'feeding_coop_semantics.npz'), **out)
     print('steps', N_STEPS, 'head (deg) at steps 0, 11, 23', np.round(np.rad2deg(head[[0, 11, 23]]), 1), 'limits', np.round(np.rad2deg(out['head_lower']), 0), np.round(np.rad2deg(out['head_upper']), 0))
 

@@ -154,6 +154,7 @@ def main():
     env.action_space = types.SimpleNamespace(low=-np.ones(7), high=np.ones(7))
     env.np_random = np.random.RandomState(0)
     env.update_targets()
+    start_state = sim.state_get()                                       # stored: the replay does not depend on the IK of the reset being bit-reproducible
     arng = np.random.default_rng(SEED + 1)
     actions = arng.uniform(-1, 1, size=(N_STEPS, 7)) * 0.3              # gentle, so that the food stays on the spoon for a while
     obs, rew, done, total, success, n_foods, n_active = [], [], [], [], [], [], []
@@ -168,6 +169,7 @@ def main():
     out = {('sample_' + k): np.asarray(v) for k, v in smp.items()}
     out.update(actions=actions, obs=np.array(obs), reward=np.array(rew), done=np.array(done), total_force=np.array(total), task_success=np.array(success),
                n_foods=np.array(n_foods), n_foods_active=np.array(n_active), eat_step=np.array(EAT_STEP), eat_v0=np.array(EAT_V0), eat_food=np.array(eat_food), seed=np.array(SEED))
+    out['start_state'] = start_state
     np.savez_compressed(os.path.join(HERE, 'feeding_semantics.npz'), **out)
     print('steps', N_STEPS, 'foods left', n_foods[-1], 'active', n_active[-1], 'task_success', success[-1], 'reward range', min(rew), max(rew), 'max force', max(total))
 

@@ -77,6 +77,7 @@ def main():
     env.action_space = types.SimpleNamespace(low=-np.ones(7), high=np.ones(7))
     env.np_random = np.random.RandomState(0)
     env.update_targets()
+    start_state = sim.state_get()                                       # stored: the replay does not depend on the IK of the reset being bit-reproducible
     actions = np.random.default_rng(SEED + 1).uniform(-1, 1, size=(N_STEPS, 7)) * 0.3
     obs, rew, head = [], [], []
     for t in range(N_STEPS):
@@ -85,6 +86,7 @@ def main():
         head.append(sim.get_joint_states([fac.gl(hb, j) for j in HEAD])[0][0].copy())
     out = {('sample_' + k): np.asarray(v) for k, v in smp.items()}
     out.update(actions=actions, obs=np.array(obs), reward=np.array(rew), head_q=np.array(head), seed=np.array(SEED))
+    out['start_state'] = start_state
     np.savez_compressed(os.path.join(HERE, 'feeding_tremor_semantics.npz'), **out)
     print('tremor amplitudes (deg)', np.round(np.rad2deg(smp['tremors'][0]), 1), 'head - rest (deg) per step, joint 21:', np.round(np.rad2deg(np.array(head)[:, 1] - rest[1]), 2))
 

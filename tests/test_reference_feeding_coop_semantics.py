@@ -21,6 +21,7 @@ def test_cooptimisation_feeding_step_reproduces_the_reference_s_rollout():
     sim = OracleSim(fb.scene, capi.default_config(), 1)
     smp = fb.reset(sim, np.random.default_rng(int(G['seed'])), settle_steps=25, impairment='none', simulate_head=True)       # the generator's call
     assert all(np.array_equal(np.asarray(smp[k]), G['sample_' + k]) for k in smp if 'sample_' + k in G.files)
+    sim.state_set(G['start_state']); sim.forward_kinematics()               # exactly the generator's start state
     env = envs.make('FeedingJacoHuman-v1', n_envs=1)
     env._fb = fb
     env.id = sim                                                               # the env's per-call path on the oracle instead of the CUDA library

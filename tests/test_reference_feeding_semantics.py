@@ -22,6 +22,7 @@ def test_restated_feeding_step_reproduces_the_reference_s_rollout():
     smp = {k[len('sample_'):]: G[k] for k in G.files if k.startswith('sample_')}
     fb.reset(sim, np.random.default_rng(int(G['seed'])), settle_steps=25, impairment='none')       # the generator's call: same draws, same IK restarts
     assert all(np.array_equal(np.asarray(fb.last_sample[k]), smp[k]) for k in smp if k in fb.last_sample)
+    sim.state_set(G['start_state']); sim.forward_kinematics()               # exactly the generator's start state (the reset's IK goes through BLAS)
     state = dict(male=smp['male'], foods=np.ones((1, 8), dtype=bool), active=np.ones((1, 8), dtype=bool), iteration=np.zeros(1, dtype=int), task_success=np.zeros(1, dtype=int))
     rng_far = np.random.RandomState(0)
     events = []

@@ -20,6 +20,7 @@ def test_restated_tremor_step_reproduces_the_reference_s_rollout():
     sim = OracleSim(fb.scene, capi.default_config(), 1)
     smp = fb.reset(sim, np.random.default_rng(int(G['seed'])), settle_steps=25, impairment='tremor')                 # the generator's call
     assert all(np.array_equal(np.asarray(smp[k]), G['sample_' + k]) for k in smp if 'sample_' + k in G.files) and smp['impairment'][0] == 3
+    sim.state_set(G['start_state']); sim.forward_kinematics()               # exactly the generator's start state
     state = dict(male=smp['male'], foods=np.ones((1, 8), dtype=bool), active=np.ones((1, 8), dtype=bool), iteration=np.zeros(1, dtype=int), task_success=np.zeros(1, dtype=int))
     for t, a in enumerate(G['actions']):
         apply_tremor(fb, [sim], smp, t + 1)                                # the counter is incremented before the targets are set (env.py:185)
