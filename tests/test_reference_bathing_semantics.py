@@ -52,3 +52,24 @@ def test_restated_bed_bathing_step_reproduces_the_reference_s_rollout():
         assert abs(env.tool_force_on_human[0] - G['tool_force_on_human'][t]) < 1e-4 * (1 + G['tool_force_on_human'][t])
         assert int(env.new_contact_points[0]) == int(G['new_contact_points'][t]) and int(env.task_success[0]) == int(G['task_success'][t])
     assert G['new_contact_points'].sum() >= 2 and G['tool_force_on_human'].max() > 3
+
+
+def test_fused_kernel_bodies_reproduce_the_reference_s_rollout(emu_lib):
+    """The product's fused BedBathing step (`ag_bathing_step_host`, kernel bodies compiled for the host, fp32) from the golden rollout's
+    start, against what the reference's own `BedBathingEnv.step` returned on the fp64 oracle -- no restatement in between: the pad is
+    pressed onto the forearm, the same two targets are wiped in the same step, forces within 5 %."""
+    from assistive_gym_b200.sim import BatchSim
+    bb = BedBathingBatch()
+    cpu, prod, smp, ik = _pressed_pair(bb, lambda sc, cfg, n: BatchSim(sc, cfg, n, _lib=emu_lib), 1, seed=8)
+    prod.state_set(G['start_state'].astype(np.float32)); prod.forward_kinematics()
+    prod.set_motor(bb.arm_links, 1, target=prod.get_joint_states(bb.arm_links)[0], kp=[float(G['motor_gain'])] * 7, kd=[1.0] * 7, max_force=[float(G['motor_force'])] * 7)
+    tw, alive = bb.targets_world(cpu, smp)
+    prod.bathing_init(bb.bathing_params(), smp['male'], tw, alive)
+    wiped = 0
+    for t, a in enumerate(G['actions']):
+        obs, rew, done, info = prod.bathing_step_host(a[None].astype(np.float32))
+        assert np.abs(obs[0, :23] - G['obs'][t][:23]).max() < 2e-3, (t, np.abs(obs[0, :23] - G['obs'][t][:23]).max())
+        assert abs(info[0, 2] - G['tool_force_on_human'][t]) < 0.05 * G['tool_force_on_human'][t] + 0.05, (t, info[0, 2], G['tool_force_on_human'][t])
+        assert int(info[0, 3]) == int(G['new_contact_points'][t]) and abs(rew[0] - G['reward'][t]) < 0.05
+        wiped += int(info[0, 3])
+    assert wiped == int(G['new_contact_points'].sum()) >= 2

@@ -48,3 +48,22 @@ def test_restated_dressing_step_with_a_tremor_person_reproduces_the_reference_s_
         assert abs(obs[0, 23] - Gt['obs'][t][23]) < 1e-9 * (1 + Gt['obs'][t][23]) and abs(rew[0] - Gt['reward'][t]) < 1e-9
     # the shaking arm changes the rollout: it is not the one without tremor
     assert np.abs(Gt['obs'][:, 14:23] - G['obs'][:, 14:23]).max() > 1e-3
+
+
+def test_fused_kernel_bodies_reproduce_the_reference_s_rollout(emu_lib):
+    """The product's fused Dressing step (`ag_dressing_step_host`: rigid kernels + the cloth step + `dressing_post_body`, compiled for the
+    host, fp32) from the golden rollout's start, against what the reference's own `DressingEnv.step` returned on the fp64 oracle -- no
+    restatement in between.  The rigid part of the observation agrees to 1e-5; the summed cloth force on the person (nodes crossing
+    the 4 cm collision margin one substep earlier or later in fp32) within 35 %, the reward (which carries it at weight 0.01) within 0.02."""
+    from assistive_gym_b200.sim import BatchSim
+    db = DressingBatch()
+    prod = BatchSim(db.scene, DressingBatch.config(), 1, _lib=emu_lib)
+    smp = {k[len('sample_'):]: G[k] for k in G.files if k.startswith('sample_')}
+    db.reset(prod, np.random.default_rng(0), sample=smp, settle_steps=0)
+    prod.cloth_set_gravity([0, 0, -9.81 / 2]); prod.step(3); prod.cloth_set_gravity([0, 0, -9.81])
+    db.start_fused(prod, smp)
+    for t, a in enumerate(G['actions']):
+        obs, rew, done, info = prod.dressing_step_host(a[None].astype(np.float32))
+        assert np.abs(obs[0, :23] - G['obs'][t][:23]).max() < 1e-5, (t, np.abs(obs[0, :23] - G['obs'][t][:23]).max())
+        assert abs(obs[0, 23] - G['obs'][t][23]) < 0.35 * G['obs'][t][23] + 0.5, (t, obs[0, 23], G['obs'][t][23])
+        assert abs(rew[0] - G['reward'][t]) < 0.02 and int(info[0, 3]) == int(G['sleeve'][t])

@@ -56,3 +56,33 @@ def _qrot(q, v):
     R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
                   [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
     return R @ np.asarray(v, dtype=np.float64)
+
+
+def test_fused_kernel_bodies_reproduce_the_reference_s_rollout(emu_lib):
+    """The product's fused Feeding step (`ag_feeding_step_host`: the CUDA kernel bodies, here compiled for the host, fp32) driven with the
+    golden rollout's start state and actions, against what the reference's own `FeedingEnv.step` returned on the fp64 oracle: no
+    restatement in between.  North-star tolerances (1e-3 m, 1e-4 rad) over the first env steps; after the spilled particle (step 4)
+    the two physics paths drift apart at the 1e-4 level, which the bounds below allow for.  Rewards agree incl. the -5 of the spill
+    and the +20 of the particle tossed into the mouth."""
+    from assistive_gym_b200.sim import BatchSim
+    fb = FeedingBatch()
+    prod = BatchSim(fb.scene, capi.default_config(), 1, _lib=emu_lib)
+    smp = {k[len('sample_'):]: G[k] for k in G.files if k.startswith('sample_')}
+    fb.reset(prod, np.random.default_rng(int(G['seed'])), settle_steps=0, sample=smp)
+    prod.state_set(G['start_state'].astype(np.float32)); prod.forward_kinematics()
+    fb.start_fused(prod, smp, seed=1)
+    male = bool(smp['male'][0])
+    for t, a in enumerate(G['actions'][:20]):
+        if t == int(G['eat_step']):
+            ls = prod.get_link_states([fb.gl(fb.humans['male' if male else 'female'], 23)])
+            target = ls['pos'][0, 0].astype(np.float64) + _qrot(ls['quat'][0, 0].astype(np.float64), fb.mouth['male' if male else 'female'])
+            f = fb.foods[int(G['eat_food'])]
+            prod.set_base_pose(f, target[None], np.array([[0, 0, 0, 1.0]]))
+            prod.set_base_velocity(f, np.array([[0, 0, float(G['eat_v0'])]]), np.zeros((1, 3)))
+        obs, rew, done, info = prod.feeding_step_host(a[None].astype(np.float32))
+        e = np.abs(obs[0] - G['obs'][t])
+        tight = t <= 4
+        assert e[[0, 1, 2, 7, 8, 9, 17, 18, 19]].max() < (5e-6 if tight else 1e-3), (t, e)          # positions (spoon, spoon - target, head), metres
+        assert e[10:17].max() < (5e-6 if tight else 1e-3) and e[3:7].max() < (5e-6 if tight else 1e-3)      # joint angles (rad), spoon orientation
+        assert abs(rew[0] - G['reward'][t]) < (1e-5 if tight else 2e-2), (t, rew[0], G['reward'][t])
+    assert G['reward'][4] < -5 and G['reward'][int(G['eat_step'])] > 18

@@ -31,3 +31,20 @@ def test_restated_scratch_itch_step_reproduces_the_reference_s_rollout():
         assert abs(info[0, 0] - G['total_force'][t]) < 1e-6 * (1 + G['total_force'][t]) and abs(info[0, 2] - G['force_at_target'][t]) < 1e-6 * (1 + G['force_at_target'][t])
         assert int(info[0, 3]) == int(G['task_success'][t])
     assert G['task_success'][-1] >= 1 and G['reward'].max() > 4                 # the rollout contains counted scratches
+
+
+def test_fused_kernel_bodies_reproduce_the_reference_s_rollout(emu_lib):
+    """The product's fused ScratchItch step (`ag_scratch_step_host`: the CUDA kernel bodies compiled for the host, fp32) from the golden
+    rollout's start, against what the reference's own `ScratchItchEnv.step` returned on the fp64 oracle -- no restatement in between:
+    observation 1e-5, tool force and reward 1 %, the same scratches counted."""
+    from assistive_gym_b200.sim import BatchSim
+    sb = ScratchItchBatch()
+    prod = BatchSim(sb.scene, capi.default_config(residual_threshold=0.0), 1, _lib=emu_lib)
+    smp = {k[len('sample_'):]: G[k] for k in G.files if k.startswith('sample_')}
+    sb.reset(prod, np.random.default_rng(0), sample=smp)
+    sb.start_fused(prod, smp)
+    for t, a in enumerate(G['actions']):
+        obs, rew, done, info = prod.scratch_step_host(a[None].astype(np.float32))
+        assert np.abs(obs[0, :29] - G['obs'][t][:29]).max() < 1e-5, (t, np.abs(obs[0, :29] - G['obs'][t][:29]).max())
+        assert abs(obs[0, 29] - G['obs'][t][29]) < 0.01 * abs(G['obs'][t][29]) + 1e-3
+        assert abs(rew[0] - G['reward'][t]) < 1e-3 and int(info[0, 3]) == int(G['task_success'][t])
