@@ -25,6 +25,12 @@ distance_weight = 1.0
 action_weight = 0.01
 food_reward_weight = 1.0
 task_success_threshold = 0.75
+[drinking]
+distance_weight = 1.0
+action_weight = 0.01
+cup_tilt_weight = 0.1
+drinking_reward_weight = 1.0
+task_success_threshold = 0.75
 [scratch_itch]
 distance_weight = 1.0
 action_weight = 0.01

@@ -110,11 +110,11 @@ def test_assistive_gym_shim_resolves_reference_ids():
     import assistive_gym
     assert assistive_gym.__agphys_shim__
     mod = importlib.import_module('assistive_gym.envs')
-    for env_id in ('FeedingJaco-v1', 'BedBathingSawyer-v1', 'DressingPR2-v1', 'ScratchItchJaco-v1', 'FeedingJacoHuman-v1', 'ScratchItchJacoHuman-v1'):
+    for env_id in ('FeedingJaco-v1', 'BedBathingSawyer-v1', 'DressingPR2-v1', 'ScratchItchJaco-v1', 'FeedingJacoHuman-v1', 'ScratchItchJacoHuman-v1', 'DrinkingJaco-v1'):
         cls = getattr(mod, env_id.split('-')[0] + 'Env')          # learn.py:65-66 (co-op path)
         assert assistive_gym.ENV_REGISTRY[env_id] is cls
     try:
-        assistive_gym.make('assistive_gym:DrinkingJaco-v1')
+        assistive_gym.make('assistive_gym:ArmManipulationJaco-v1')
     except KeyError as e:
         assert 'not built' in str(e)
     else:

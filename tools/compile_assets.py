@@ -312,6 +312,7 @@ CLOTHS = {
 }
 MESHES = {
     'spoon_vhacd': 'dinnerware/spoon_vhacd.obj',
+    'cup_vhacd': 'dinnerware/plastic_coffee_cup_vhacd.obj',
     'head_male_vhacd': 'head_female_male/BaseHeadMeshes_v5_male_cropped_reduced_compressed_vhacd.obj',
     'head_female_vhacd': 'head_female_male/BaseHeadMeshes_v5_female_cropped_reduced_compressed_vhacd.obj',
 }
