@@ -202,7 +202,8 @@ def main():
     install_stubs(ref)
     out = {}
     for key, path in (('feeding', 'assistive_gym.envs.feeding_envs.FeedingJacoEnv'), ('scratch_itch', 'assistive_gym.envs.scratch_itch_envs.ScratchItchJacoEnv'),
-                      ('bed_bathing', 'assistive_gym.envs.bed_bathing_envs.BedBathingSawyerEnv'), ('dressing', 'assistive_gym.envs.dressing_envs.DressingPR2Env')):
+                      ('bed_bathing', 'assistive_gym.envs.bed_bathing_envs.BedBathingSawyerEnv'), ('dressing', 'assistive_gym.envs.dressing_envs.DressingPR2Env'),
+                      ('drinking', 'assistive_gym.envs.drinking_envs.DrinkingJacoEnv')):
         try:
             out[key] = record(path)
             print(key, 'ok:', len(out[key]['calls']), 'calls kept,', out[key]['n_step_simulation'], 'stepSimulation')

@@ -240,3 +240,34 @@ def test_dressing_scene_recipe_is_the_reference_s():
     gv = np.asarray(sc['body_gravity'])
     assert np.allclose(gv[db.robot], 0) and all(np.allclose(gv[hb], [0, 0, -1]) for hb in db.humans.values())
     assert _by(g['calls'], 'setPhysicsEngineParameter')[0]['kw'] == {'numSubSteps': 8} and DressingBatch.config().num_substeps == 8
+
+
+def test_drinking_scene_recipe_is_the_reference_s():
+    from assistive_gym_b200.drinking_batch import JACO as DRINK_JACO
+    from assistive_gym_b200.drinking_batch import N_WATER, WATER_MASS, WATER_RADIUS, DrinkingBatch
+    g = G['drinking']
+    db = DrinkingBatch()
+    sc = db.scene
+    loads, last_pose, resets = _common(g, db, DRINK_JACO, FEED_PRESET, [0.63] * 3, np.array([-0.2, -0.5, 1.1]))
+    assert g['motor_gains'] == {'robot': 0.005, 'human': 0.005}              # drinking.py:126
+    assert g['n_step_simulation'] == 50 == inspect.signature(db.reset).parameters['settle_steps'].default
+    assert _by(g['calls'], 'setPhysicsEngineParameter')[0]['kw'] == {'numSubSteps': 4, 'numSolverIterations': 10}
+    cfg = DrinkingBatch.config()
+    assert cfg.num_substeps == 4 and cfg.num_solver_iters == 10
+    for j in (21, 22, 23):
+        assert abs(resets[j]) <= np.deg2rad(30)
+    # the cup: the reference's mesh at scale 0.045, 1 kg
+    cup_shape = [c['kw'] for c in _by(g['calls'], 'createCollisionShape') if c['kw'].get('fileName') == 'plastic_coffee_cup_vhacd.obj'][0]
+    assert cup_shape['meshScale'] == [0.045] * 3
+    mb = {c['kw']['bodies'][0]: c['kw'] for c in _by(g['calls'], 'createMultiBody')}
+    assert mb[g['tool_body']]['baseMass'] == 1 == float(sc['link_mass'][int(sc['body_link0'][db.tool])])
+    # the water: 64 spheres of radius 5 mm and 1 g on a 4 x 4 x 4 grid above the cup
+    water = [c['kw'] for c in _by(g['calls'], 'createMultiBody') if 'batchPositions' in c['kw']][0]
+    assert len(water['bodies']) == 64 == N_WATER == len(db.waters) and water['baseMass'] == WATER_MASS == 0.001
+    ws = _by(g['calls'], 'createCollisionShape')[water['baseCollisionShapeIndex']]['kw']
+    assert ws['shapeType'] == 2 and ws['radius'] == WATER_RADIUS == 0.005
+    offsets = np.array(water['batchPositions']) - np.array(last_pose[g['tool_body']]['pos'])
+    sim = OracleSim(sc, cfg, 1)
+    db.reset(sim, np.random.default_rng(0), settle_steps=0, impairment='none')
+    ls = sim.get_link_states([int(sc['body_link0'][db.tool])] + [int(sc['body_link0'][w]) for w in db.waters])
+    assert np.allclose(ls['pos'][0, 1:] - ls['com_pos'][0, 0], offsets, atol=1e-9)
