@@ -57,3 +57,29 @@ def test_drinking_env_on_the_host_compiled_kernel_bodies(emu_lib):
         assert np.all(np.isfinite(o)) and np.all(np.isfinite(r))
     assert env.waters.sum(axis=1).min() >= 56
     env.close()
+
+
+def test_drinking_env_on_the_kernel_bodies_reproduces_the_reference_s_rollout(emu_lib):
+    """`DrinkingJacoEnv` on the PRODUCT's physics (kernel bodies compiled for the host, fp32; 65 free bodies per env, 4 substeps, 10 solver
+    iterations) from the golden start, against what the reference's own `DrinkingEnv.step` returned on the fp64 oracle: observation 1e-4,
+    reward 1e-2 incl. the swallowed (+10) and the spilled (-1) particle, the same particles removed."""
+    from assistive_gym_b200.sim import BatchSim
+    db = DrinkingBatch()
+    prod = BatchSim(db.scene, DrinkingBatch.config(), 1, _lib=emu_lib)
+    smp = {k[len('sample_'):]: G[k] for k in G.files if k.startswith('sample_')}
+    db.reset(prod, np.random.default_rng(0), settle_steps=0, sample=smp)
+    prod.state_set(G['start_state'].astype(np.float32)); prod.forward_kinematics()
+    env = envs.make('DrinkingJaco-v1', n_envs=1)
+    env._db = db
+    env.attach(prod)
+    env.start_episode(smp)
+    for t, a in enumerate(G['actions'][:16]):
+        for key in ('swallow', 'spill'):
+            if t == int(G[key + '_step']):
+                w = db.waters[int(G[key + '_water'])]
+                prod.set_base_pose(w, G[key + '_pos'][None], np.array([[0, 0, 0, 1.0]]))
+                prod.set_base_velocity(w, np.array([[0, 0, float(G['swallow_v0']) if key == 'swallow' else 0.0]]), np.zeros((1, 3)))
+        obs, rew, done, info = env.step(a)
+        assert np.abs(obs[:24] - G['obs'][t][:24]).max() < 1e-4 and abs(rew - G['reward'][t]) < 1e-2, (t, rew, G['reward'][t])
+        assert int(env.waters.sum()) == int(G['n_waters'][t]) and int(env.task_success[0]) == int(G['task_success'][t])
+    assert prod.overflow_count() == 0
