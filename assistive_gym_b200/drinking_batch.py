@@ -105,32 +105,39 @@ class DrinkingBatch(FeedingBatch):
             hl = [self.gl(hb, j) for j in TREMOR_JOINTS]
             sim.set_motor(hl, MOTOR_POSITION, target=q[:, list(TREMOR_JOINTS)], kp=[0.005] * 4, kd=[1.0] * 4, max_force=[1.0] * 4)     # drinking.py:126
             sim.set_hard_limits(hl, True)
+        gq0 = np.full((n, 3), JACO['gripper_pos'])
+        sim.set_joint_state(self.gripper_links, q=gq0, qd=np.zeros_like(gq0))
         if 'q7' in s:
             arm_q = s['q7'].copy()
+            self.ik_colliding = 0
         else:
+            # start pose of the arm: IK to the randomised goal, resampled while the arm or the cup touch the person or the wheelchair
+            # (ik_random_restarts with collision_objects, robot.py:107-112; env.py:300-309)
             target = np.array([-0.2, -0.5, 1.1]) + s['ee_offset']              # drinking.py:140
-            saved = JACO_FEED_ORIENT[0]
-            JACO_FEED_ORIENT[0] = JACO['ee_orient_rpy']
-            try:
-                qik, self.ik_err = self._solve_ik_drinking(n, target, rng, sim)
-            finally:
-                JACO_FEED_ORIENT[0] = saved
-            arm_q = qik
+            arm_q, self.ik_err = self._solve_ik_drinking(n, target, rng, sim, None)
+            obstacles = [self.humans['male'], self.humans['female'], self.wheelchair]
+            hit = np.zeros(n, dtype=bool)
+            for attempt in range(30):
+                sim.set_joint_state(self.arm_links, q=arm_q, qd=np.zeros_like(arm_q))
+                self._place_cup(sim, arm_q)
+                sim.forward_kinematics()
+                hit = np.zeros(n, dtype=bool)
+                for ob in obstacles:
+                    hit |= sim.closest_points(self.robot, ob, 0.0, max_pts=1)[1] > 0
+                    hit |= sim.closest_points(self.tool, ob, 0.0, max_pts=1)[1] > 0
+                if not hit.any():
+                    break
+                q2, e2 = self._solve_ik_drinking(n, target, rng, sim, hit)
+                arm_q[hit], self.ik_err[hit] = q2[hit], e2[hit]
+            self.ik_colliding = int(hit.sum())
             s['q7'] = arm_q.copy()
         gq = np.full((n, 3), JACO['gripper_pos'])
         sim.set_joint_state(self.gripper_links, q=gq, qd=np.zeros_like(gq))
         sim.set_joint_state(self.arm_links, q=arm_q, qd=np.zeros_like(arm_q))
         sim.set_motor(self.arm_links, MOTOR_POSITION, target=arm_q, kp=[0.005] * 7, kd=[1.0] * 7, max_force=[1.0] * 7)              # drinking.py:126
         sim.set_motor(self.gripper_links, MOTOR_POSITION, target=gq, kp=[0.05] * 3, kd=[1.0] * 3, max_force=[500.0] * 3)
-        # the cup at the tool joint's COM frame composed with the offsets (tool.py:49-54)
-        qfull = np.zeros((n, self.kin.nl)); qfull[:, np.array(JACO['arm']) + 1] = arm_q; qfull[:, np.array(JACO['gripper']) + 1] = JACO['gripper_pos']
-        pos, quat = self.kin.fk(np.broadcast_to(self.robot_base_pos, (n, 3)), np.broadcast_to(self.robot_base_quat, (n, 4)), qfull)
-        cp, cq = self.kin.link_com_pose(pos, quat, JACO['tool_joint'] + 1)
-        sp = cp + q_rot(cq, self.tool_pos_offset)
-        sq = q_mul(cq, np.broadcast_to(self.tool_quat_offset, (n, 4)))
+        sp, sq = self._place_cup(sim, arm_q)
         zero3 = np.zeros((n, 3))
-        sim.set_base_pose(self.tool, sp, sq)
-        sim.set_base_velocity(self.tool, zero3, zero3)
         # water above the cup (drinking.py:159-168): the cup's base position is its centre of mass frame, as PyBullet reports it
         sim.forward_kinematics()
         cup_com = sim.get_link_states([int(sc['body_link0'][self.tool])])['com_pos'][:, 0].astype(np.float64)
@@ -147,11 +154,24 @@ class DrinkingBatch(FeedingBatch):
             sim.step(settle_steps)                                              # "drop water in the cup" (drinking.py:175-176)
         return s
 
-    def _solve_ik_drinking(self, n, target, rng, sim):
+    def _place_cup(self, sim, arm_q):
+        """the cup at the tool joint's COM frame composed with the offsets (tool.py:49-54)"""
+        n = sim.n
+        qfull = np.zeros((n, self.kin.nl)); qfull[:, np.array(JACO['arm']) + 1] = arm_q; qfull[:, np.array(JACO['gripper']) + 1] = JACO['gripper_pos']
+        pos, quat = self.kin.fk(np.broadcast_to(self.robot_base_pos, (n, 3)), np.broadcast_to(self.robot_base_quat, (n, 4)), qfull)
+        cp, cq = self.kin.link_com_pose(pos, quat, JACO['tool_joint'] + 1)
+        sp = cp + q_rot(cq, self.tool_pos_offset)
+        sq = q_mul(cq, np.broadcast_to(self.tool_quat_offset, (n, 4)))
+        sim.set_base_pose(self.tool, sp, sq)
+        sim.set_base_velocity(self.tool, np.zeros((n, 3)), np.zeros((n, 3)))
+        return sp, sq
+
+    def _solve_ik_drinking(self, n, target, rng, sim, mask=None):
         """start pose of the arm: the task's end-effector orientation at the randomised position (env.py:296, robot.py:84-121)"""
         tq = q_from_rpy(JACO['ee_orient_rpy'])
         if hasattr(sim, 'ik_solve'):
-            q7, err = sim.ik_solve(self.arm_links, self.ee_link, target, tq, max_restarts=20, iters=120, threshold=0.01, seed=int(rng.integers(1, 2 ** 31 - 1)))
+            q7, err = sim.ik_solve(self.arm_links, self.ee_link, target, tq, max_restarts=20, iters=120, threshold=0.01, seed=int(rng.integers(1, 2 ** 31 - 1)),
+                                   mask=None if mask is None else mask.astype(np.int32))
             return q7.astype(np.float64), err.astype(np.float64)
         from .kinematics import ik_dls
         joints = np.array(JACO['arm']) + 1
@@ -167,5 +187,3 @@ class DrinkingBatch(FeedingBatch):
                 break
         return best_q, best_e
 
-
-JACO_FEED_ORIENT = [None]

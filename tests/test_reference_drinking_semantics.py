@@ -52,6 +52,7 @@ def test_drinking_env_on_the_host_compiled_kernel_bodies(emu_lib):
     sc = env.id.scene
     wp = env.id.get_link_states([int(sc['body_link0'][w.body]) for w in env.water_agents])['pos'].astype(np.float64)
     assert points_in_cylinder(top, bottom, 0.05, wp).sum(axis=1).min() >= 56          # the water is in the cup after the 50 settle steps
+    assert env._db.ik_colliding == 0                                              # start poses that touch the person / wheelchair are resampled (env.py:300-309)
     for _ in range(2):
         o, r, d, info = env.step(np.zeros((2, 7)))
         assert np.all(np.isfinite(o)) and np.all(np.isfinite(r))
